@@ -1,0 +1,340 @@
+"""Generate the golden fixtures in this directory FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs the read-only reference checkout):
+
+    python tests/golden/make_golden.py [--ref /root/reference]
+
+It imports the unmodified reference modules from ``<ref>/src`` (with inert stub
+modules for pytz / matplotlib / nibabel / progressbar, none of which touch the
+arithmetic), runs the hot-path functions on seeded inputs on the CPU, and writes
+small ``.npz`` files.  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so these files are what pins ``oracle/effq_oracle.py``; the
+GPU parity tests then compare the CUDA path with the oracle and with these
+files.  Nothing at test time reads ``/root/reference``.
+"""
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def import_reference(ref):
+    sys.path.insert(0, os.path.join(ref, "src"))
+    for name in ["matplotlib", "matplotlib.pyplot", "pytz", "nibabel", "progressbar"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    import importlib
+    import models  # noqa: F401  (models/__init__ re-exports classes under the module names)
+    lh, solver, ptqconv, effq, model_blk, fold_bn, hooks = [
+        sys.modules.get(f"models.{n}") or importlib.import_module(f"models.{n}")
+        for n in ("layer_helper", "solver", "PTQConv", "EfficientQConv", "model_blk", "fold_bn", "hooks")]
+    import ptqer
+    return dict(lh=lh, solver=solver, ptqconv=ptqconv, effq=effq, model_blk=model_blk,
+                fold_bn=fold_bn, hooks=hooks, ptqer=ptqer)
+
+
+def meta():
+    return dict(torch_version=torch.__version__, numpy_version=np.__version__,
+                threads=torch.get_num_threads())
+
+
+LEVEL_CASES = [(4, 0, 1), (16, 0, 1), (256, 0, 1), (4, -1, 1), (16, -1, 1), (256, -1, 1)]
+
+
+def edge_values(n_lvl, lo, hi, dtype):
+    """Rounding ties, clamp edges and near-ties for the level grid."""
+    delta = (hi - lo) / (n_lvl - 1)
+    ks = np.arange(n_lvl - 1, dtype=np.float64)
+    ties = lo + (ks + 0.5) * delta
+    near = np.concatenate([np.nextafter(ties.astype(dtype), np.array(np.inf, dtype)),
+                           np.nextafter(ties.astype(dtype), np.array(-np.inf, dtype))])
+    edges = np.array([lo, hi, lo - 1e-3, hi + 1e-3, lo - 7.0, hi + 7.0, 0.0, -0.0], dtype=np.float64)
+    return np.concatenate([ties, near.astype(np.float64), edges]).astype(dtype)
+
+
+def gen_discretize(R, out):
+    lh = R["lh"]
+    res = {}
+    g = torch.Generator().manual_seed(11)
+    base = torch.randn(8192, generator=g) * 0.8
+    for (L, lo, hi) in LEVEL_CASES:
+        for dt, name in [(torch.float32, "f32"), (torch.float64, "f64")]:
+            npdt = np.float32 if dt == torch.float32 else np.float64
+            v = torch.cat([base.to(dt), torch.from_numpy(edge_values(L, lo, hi, npdt))])
+            q = lh.discretize(v, L, lo, hi)
+            key = f"L{L}_lo{lo}_{name}"
+            res[key + "_in"] = v.numpy()
+            res[key + "_out"] = q.numpy()
+    np.savez_compressed(os.path.join(out, "discretize.npz"), **res, **{f"meta_{k}": v for k, v in meta().items()})
+
+
+def gen_fakequant_module(R, out):
+    """PTQConv._quantize_act/_quantize_w/store_int_weight/restore_fp_weight."""
+    PTQConv = R["ptqconv"].PTQConv
+    res = {}
+    g = torch.Generator().manual_seed(12)
+    for L in (4, 16, 256):
+        m = PTQConv(6, 5, 3, 1, 1, bias=True, q_weight=True, qlvl=L, q_act=True, qlvl_act=L)
+        x = torch.relu(torch.randn(2, 6, 9, 10, 11, generator=g)) * 1.7
+        w = torch.randn(5, 6, 3, 3, 3, generator=g) * 0.2
+        a_act, a_w = 1.2345678, 0.31415927
+        m.alpha_act.data = torch.tensor(a_act)
+        m.alpha_w.data = torch.tensor(a_w)
+        m.weight.data = w.clone()
+        with torch.no_grad():
+            qa = m._quantize_act(x)
+            qw = m._quantize_w()
+            m.weight.data = qw.clone()
+            m.store_int_weight()
+            wi = m.weight.data.clone()
+            m.restore_fp_weight()
+            wr = m.weight.data.clone()
+        res.update({f"L{L}_x": x.numpy(), f"L{L}_w": w.numpy(), f"L{L}_alpha_act": np.float32(a_act),
+                    f"L{L}_alpha_w": np.float32(a_w), f"L{L}_qact": qa.numpy(), f"L{L}_qw": qw.numpy(),
+                    f"L{L}_wint": wi.numpy(), f"L{L}_wrestored": wr.numpy()})
+    np.savez_compressed(os.path.join(out, "fakequant_module.npz"), **res)
+
+
+def gen_project(R, out):
+    lh = R["lh"]
+    res = {}
+    g = torch.Generator().manual_seed(13)
+    act = torch.relu(torch.randn(3, 8, 12, 12, 12, generator=g)) * 0.9
+    wt = torch.randn(16, 8, 3, 3, 3, generator=g) * 0.07
+    res["act"] = act.numpy()
+    res["wt"] = wt.numpy()
+    for name, v, lo, hi in [("act", act, 0, 1), ("wt", wt, -1, 1)]:
+        for L in (4, 16, 256):
+            calls = {"n": 0}
+            orig = lh.discretize
+
+            def counting(*a, **k):
+                calls["n"] += 1
+                return orig(*a, **k)
+            lh.discretize = counting
+            try:
+                a, b = lh.project_by_iter(v, L, lo, hi)
+            finally:
+                lh.discretize = orig
+            res[f"{name}_L{L}_a"] = np.float64(a)
+            res[f"{name}_L{L}_passes"] = np.int64(calls["n"] - 1)
+            res[f"{name}_L{L}_b"] = b.numpy()
+    np.savez_compressed(os.path.join(out, "project_by_iter.npz"), **res)
+
+
+def gen_solver(R, out):
+    solver = R["solver"]
+    res = {}
+    g = torch.Generator().manual_seed(14)
+    cases = [("k3s1p1", 2, 5, 7, 3, 1, 1, (6, 7, 8)), ("k3s2p1", 2, 4, 6, 3, 2, 1, (8, 10, 12)),
+             ("k1s1p0", 3, 6, 5, 1, 1, 0, (4, 5, 6))]
+    for name, n, c1, c2, k, s, p, sp in cases:
+        x = torch.relu(torch.randn(n, c1, *sp, generator=g))
+        w0 = torch.randn(c2, c1, k, k, k, generator=g) * 0.1
+        b0 = torch.randn(c2, generator=g) * 0.1
+        y = F.conv3d(x, w0, b0, s, p) + 0.01 * torch.randn(1, generator=g)
+        att = (torch.rand(n, *y.shape[2:], generator=g) * 3).floor() + 1.0
+        cols = solver.im2col_loop(x.numpy().astype("float32"), k, k, k, s, p)
+        qs = solver.QuadraSolver(x, y, k, k, k, (s,) * 3, (p,) * 3, device=torch.device("cpu"),
+                                 mu=0, eta=0.7, W0=w0, att=att, b0=b0)
+        gmat = w0 + 0.01 * torch.randn(w0.shape, generator=g)
+        ws, bs = qs.solve(3.0, 0.7, gmat)
+        res.update({f"{name}_x": x.numpy(), f"{name}_w0": w0.numpy(), f"{name}_b0": b0.numpy(),
+                    f"{name}_y": y.numpy(), f"{name}_att": att.numpy(), f"{name}_cols": cols,
+                    f"{name}_A0": qs.A0.numpy(), f"{name}_B0": qs.B0.numpy(), f"{name}_G": gmat.numpy(),
+                    f"{name}_wstar": ws.numpy(), f"{name}_bstar": bs.numpy(),
+                    f"{name}_geom": np.array([k, s, p], dtype=np.int64)})
+    np.savez_compressed(os.path.join(out, "solver.npz"), **res)
+
+
+def run_ref_layer(R, x, w, b, y, stride, pad, qlvl_w, qlvl_a, q_act, pyramid):
+    """EfficientQConv.ptq on one layer, recording the per-iteration losses."""
+    effq = R["effq"]
+    c2, c1, k = w.shape[0], w.shape[1], w.shape[2]
+    m = effq.EfficientQConv(c1, c2, k, stride, pad, bias=True, q_weight=True, qlvl=qlvl_w,
+                            q_act=q_act, qlvl_act=qlvl_a)
+    m.weight.data = w.clone()
+    m.bias.data = b.clone()
+    m.name = "layer"
+    m.output_fp = y.clone()
+    m.mask_pyramid = pyramid
+    m.layer_loss = []
+    hist = []
+    orig = effq.F.mse_loss
+
+    def rec(a, t, *args, **kw):
+        v = orig(a, t, *args, **kw)
+        hist.append(float(v.item()))
+        return v
+    effq.F.mse_loss = rec
+    try:
+        with torch.no_grad():
+            m.ptq(x)
+    finally:
+        effq.F.mse_loss = orig
+    final = float(m.layer_loss[0].split(":")[-1])
+    return dict(weight=m.weight.data.numpy(), bias=m.bias.data.numpy(),
+                alpha_w=np.float32(m.alpha_w.item()), alpha_act=np.float32(m.alpha_act.item()),
+                hist=np.array(hist[:200], dtype=np.float64), final=np.float64(final))
+
+
+def gen_layers(R, out):
+    res = {}
+    g = torch.Generator().manual_seed(15)
+    cases = [
+        # name, n, c1, c2, k, s, p, spatial, Lw, La, q_act
+        ("w4a4_k3", 2, 16, 16, 3, 1, 1, (8, 16, 8), 16, 16, True),
+        ("w2a2_k3", 1, 16, 32, 3, 1, 1, (8, 16, 8), 4, 4, True),
+        ("w4a4_k1", 2, 16, 32, 1, 1, 0, (8, 8, 8), 16, 16, True),
+        ("first_k3s2", 2, 4, 16, 3, 2, 1, (16, 16, 16), 256, 256, False),
+    ]
+    for name, n, c1, c2, k, s, p, sp, lw, la, qa in cases:
+        x = torch.randn(n, c1, *sp, generator=g)
+        if qa:
+            x = torch.relu(x)
+        w = torch.randn(c2, c1, k, k, k, generator=g) * (2.0 / (c1 * k ** 3)) ** 0.5
+        b = torch.randn(c2, generator=g) * 0.05
+        y = F.conv3d(x, w, b, s, p)
+        att = (torch.rand(n, *y.shape[2:], generator=g) * 3).floor() + 1.0
+        pyramid = [torch.ones(n, 3, 3, 3), att]
+        r = run_ref_layer(R, x, w, b, y, s, p, lw, la, qa, pyramid)
+        res.update({f"{name}_x": x.numpy(), f"{name}_w": w.numpy(), f"{name}_b": b.numpy(),
+                    f"{name}_y": y.numpy(), f"{name}_att": att.numpy(),
+                    f"{name}_cfg": np.array([k, s, p, lw, la, int(qa)], dtype=np.int64)})
+        res.update({f"{name}_out_{k2}": v for k2, v in r.items()})
+        print(name, "final", r["final"], "alpha_w", r["alpha_w"], "alpha_act", r["alpha_act"])
+    np.savez_compressed(os.path.join(out, "layers.npz"), **res)
+
+
+TOY = dict(num_mod=4, num_classes=3, depth=[1, 1, 1], width=[8, 16, 8], dilation=[1, 1, 1],
+           init_stride=(2, 2, 2), drop_rate=0.5, ds="simple", blk="mid", qlvl=16, qlvl_act=16,
+           q_first=[256, -1], q_last=[256, -1], n=2, size=64, task="brats", seed=16)
+
+
+def build_toy(R, QConv, cfg=TOY):
+    from models import factoryQ, factory_blk
+    hetero = {"drop_cut_thres": 128, "ds_depth_limit": 3, "aniso_pool_depth": 9999,
+              "aniso_pool_stride": (2, 2, 1)}
+    return R["model_blk"].UResQ(
+        QConv, cfg["num_mod"], cfg["num_classes"], depth_config=cfg["depth"], width_config=cfg["width"],
+        dilation_config=cfg["dilation"], init_stride=cfg["init_stride"], stride=2,
+        drop_rate=cfg["drop_rate"], nla=factoryQ.ReLU(True), bn=nn.BatchNorm3d, ds=cfg["ds"],
+        blk_type=cfg["blk"], q_weight=True, qlvl=cfg["qlvl"], q_act=True, qlvl_act=cfg["qlvl_act"],
+        q_first=cfg["q_first"], q_last=cfg["q_last"], hetero_param=hetero,
+        rb=factory_blk.ResBlockWithType, fuse_bn=True, save_mem=True, init_kernel=3)
+
+
+def seeded_state(model, seed):
+    """kaiming init (reference utils/misc.py:85-102) + perturbed BN statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if k.endswith("alpha_act") or k.endswith("alpha_w"):
+            continue
+        if v.dim() == 5:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3] * v.shape[4]
+            sd[k] = torch.randn(v.shape, generator=g) * (2.0 / fan_in) ** 0.5
+        elif k.endswith("running_mean"):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith("num_batches_tracked"):
+            sd[k] = v.clone()
+        elif k.endswith(".weight"):      # BN gamma
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith(".bias"):
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = v.clone()
+    return sd
+
+
+def gen_toy_net(R, out):
+    """The do_ptq core (reference src/ptqer.py:289-364) on a toy UResQ, CPU."""
+    from efficientq_b200 import synth
+    ptqer = R["ptqer"]
+    cfg = TOY
+    model = build_toy(R, R["effq"].EfficientQConv)
+    sd = seeded_state(model, cfg["seed"])
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    R["fold_bn"].search_fold_and_remove_bn(model)
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
+    ptqer.set_name(model)
+    ptqer.set_fp(model)
+    handles = []
+    for m in model.modules():
+        if isinstance(m, R["ptqconv"].PTQConv):
+            handles.append(m.register_forward_hook(R["hooks"].forward_hook))
+    with torch.no_grad():
+        output_fp = model(data).detach()
+    body = (data[:, 0] != 0.0).bool()
+    wmap, nums = ptqer.get_att_weight_map(output_fp, torch.ones_like(data[:, 0]).bool(), "p:0.5", task="brats")
+    pyr = ptqer.get_mask_pyramid(output_fp, body, wmap, "2,2,2", num_lvls=5, task="brats")
+    ptqer.set_mask(model, pyr)
+    for h in handles:
+        h.remove()
+    layer_loss = []
+    ptqer.set_anything(model, "layer_loss", layer_loss)
+    ptqer.set_quantizing(model)
+    with torch.no_grad():
+        output_q = model(data)
+    ptqer.set_quantized(model)
+    res = {f"sd::{k}": v.numpy() for k, v in sd.items()}
+    names, losses = [], []
+    for line in layer_loss:
+        nm, val = line.rsplit(":", 1)
+        names.append(nm.strip())
+        losses.append(float(val))
+    res["layer_names"] = np.array(names)
+    res["layer_losses"] = np.array(losses, dtype=np.float64)
+    res["class_nums"] = np.array(nums, dtype=np.int64)
+    res["wmap"] = np.array([wmap[k] for k in sorted(wmap)], dtype=np.float64)
+    res["pyr_means"] = np.array([p.mean().item() for p in pyr], dtype=np.float64)
+    res["pyr0"] = pyr[0].numpy().astype(np.uint8)
+    res["data_checksum"] = np.float64(data.double().sum().item())
+    res["out_fp_mse_vs_q"] = np.float64(F.mse_loss(output_q, output_fp).item())
+    res["out_fp_sum"] = np.float64(output_fp.double().sum().item())
+    for name, m in model.named_modules():
+        if isinstance(m, R["ptqconv"].PTQConv):
+            res[f"q::{name}.alpha_w"] = np.float32(m.alpha_w.item())
+            res[f"q::{name}.alpha_act"] = np.float32(m.alpha_act.item())
+    ptqer.store_int_weight(model)
+    for name, m in model.named_modules():
+        if isinstance(m, R["ptqconv"].PTQConv):
+            res[f"q::{name}.wint"] = m.weight.data.numpy()
+    for k, v in zip(names, losses):
+        print(f"{k:45s} {v:.6e}")
+    np.savez_compressed(os.path.join(out, "toy_net.npz"), **res)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    R = import_reference(args.ref)
+    gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
+                solver=gen_solver, layers=gen_layers, toy_net=gen_toy_net)
+    for name, fn in gens.items():
+        if args.only and name not in args.only.split(","):
+            continue
+        print("==", name)
+        fn(R, HERE)
+    with open(os.path.join(HERE, "VERSIONS.txt"), "w") as fid:
+        for k, v in meta().items():
+            fid.write(f"{k}: {v}\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""ctypes binding of ``libeffq_b200.so`` (the C-ABI declared in ``include/effq_b200.h``).
+
+There is NO fallback: if the shared library is missing or an entry point returns an
+error the call raises.  ``torch`` is used only to own device memory and streams; every
+entry point receives raw device pointers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libeffq_b200.so")
+
+
+class EffqError(RuntimeError):
+    pass
+
+
+class Geom(C.Structure):
+    """``effq_geom`` (include/effq_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("n", "c1", "d", "h", "w", "c2", "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw")]
+
+    @classmethod
+    def make(cls, x_shape, c2, ksize, stride, padding) -> "Geom":
+        n, c1, d, h, w = [int(t) for t in x_shape]
+        k = _triple(ksize)
+        s = _triple(stride)
+        p = _triple(padding)
+        return cls(n, c1, d, h, w, int(c2), k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2])
+
+    def out_spatial(self):
+        return ((self.d + 2 * self.pd - self.kd) // self.sd + 1,
+                (self.h + 2 * self.ph - self.kh) // self.sh + 1,
+                (self.w + 2 * self.pw - self.kw) // self.sw + 1)
+
+    @property
+    def taps(self):
+        return self.kd * self.kh * self.kw
+
+
+SCALE_STATE_BYTES = 48     # sizeof(effq_scale_state)
+ADMM_STATE_BYTES = 40      # sizeof(effq_admm_state)
+
+
+def _triple(v):
+    return (int(v),) * 3 if isinstance(v, int) else tuple(int(t) for t in v)
+
+
+_SIGS = {
+    "effq_abi_version": (C.c_int, []),
+    "effq_last_error": (C.c_char_p, []),
+    "effq_launch_count": (C.c_uint64, []),
+    "effq_reset_launch_count": (None, []),
+    "effq_fakequant_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_fakequant_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                       C.c_void_p, C.c_void_p]),
+    "effq_quantize_act_ndhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_scale_search_workspace": (C.c_int64, []),
+    "effq_scale_search": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_scale_partial": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                     C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "effq_scale_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "effq_conv3d_f32_workspace": (C.c_int64, [C.POINTER(Geom)]),
+    "effq_conv3d_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_conv3d_tc_supported": (C.c_int, [C.POINTER(Geom)]),
+    "effq_conv3d_tc_workspace": (C.c_int64, [C.POINTER(Geom)]),
+    "effq_conv3d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_gram_workspace": (C.c_int64, [C.POINTER(Geom), C.c_int32]),
+    "effq_gram_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_admm_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib: Optional[C.CDLL] = None
+
+
+def load(path: Optional[str] = None) -> C.CDLL:
+    """dlopen the kernel library and type every entry point.  Raises if it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EffqError(
+            f"{path} not found: build it with `python -m efficientq_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU or PyTorch fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.effq_abi_version() != 1:
+        raise EffqError("libeffq_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().effq_last_error()
+        raise EffqError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EffqError("effq_b200 kernels take CUDA tensors only (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().effq_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().effq_reset_launch_count()

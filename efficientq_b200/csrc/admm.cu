@@ -1,0 +1,187 @@
+// Fused elementwise ADMM parameter-update kernels (HBM/L2-bound, C2 x K' elements).
+// Replace the ATen elementwise chains at reference
+//   src/models/solver.py:316-325          (getAB: A and B assembly)
+//   src/models/EfficientQConv.py:107-111  (projection G = a_w*b_w, dual update)
+//   src/models/EfficientQConv.py:129-142  (rho rescale of the dual, best-iterate pick)
+// All scalars that the reference pulls to the host with .item() stay in device
+// structs, so the 200-iteration loop of one layer enqueues without a host sync.
+#include "common.cuh"
+
+namespace effq {
+
+constexpr int AD_THREADS = 256;
+
+static inline int grid_for(long long n) {
+  long long b = (n + AD_THREADS - 1) / AD_THREADS;
+  const long long cap = (long long)sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// B = (B0 + eta*W0') ; B[:, :K] += rho*(G - dual)            solver.py:317-320
+__global__ void __launch_bounds__(AD_THREADS)
+admm_rhs_kernel(const float* __restrict__ b0, const float* __restrict__ w0p, const float* __restrict__ g,
+                const float* __restrict__ dual, float rho, float eta, int c2, int k, int kp,
+                float* __restrict__ b_out) {
+  const long long total = (long long)c2 * kp;
+  for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
+       e += (long long)gridDim.x * AD_THREADS) {
+    const int r = (int)(e / kp), j = (int)(e % kp);
+    float v = __fadd_rn(b0[e], __fmul_rn(eta, w0p[e]));
+    if (j < k) {
+      const long long ge = (long long)r * k + j;
+      v = __fadd_rn(v, __fmul_rn(rho, __fsub_rn(g[ge], dual[ge])));
+    }
+    b_out[e] = v;
+  }
+}
+
+// A = A0 + rho*quasi_eye + eta*eye                            solver.py:317 / :323
+__global__ void __launch_bounds__(AD_THREADS)
+admm_lhs_kernel(const float* __restrict__ a0, float rho, float eta, int kp, int has_bias,
+                float* __restrict__ a_out) {
+  const long long total = (long long)kp * kp;
+  for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
+       e += (long long)gridDim.x * AD_THREADS) {
+    const int i = (int)(e / kp), j = (int)(e % kp);
+    float v = a0[e];
+    if (i == j) {
+      if (has_bias) {
+        const float qe = (i == kp - 1) ? 0.f : 1.f;
+        v = __fadd_rn(__fadd_rn(v, __fmul_rn(rho, qe)), eta);
+      } else {
+        v = __fadd_rn(v, __fadd_rn(rho, eta));      // (rho + mu + eta) * eye, mu = 0
+      }
+    }
+    a_out[e] = v;
+  }
+}
+
+// Projection + dual update + operand export.           EfficientQConv.py:107-111,131-137
+__global__ void __launch_bounds__(AD_THREADS)
+admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __restrict__ dual,
+                    const effq_scale_state* __restrict__ wscale, const effq_scale_state* __restrict__ xscale,
+                    int nlvl_w, int nlvl_a, int c2, int c1, int taps, int has_bias, float dual_div,
+                    float* __restrict__ g_out, float* __restrict__ bstar_out,
+                    __nv_bfloat16* __restrict__ wcodes, effq_admm_state* st) {
+  const int k = c1 * taps;
+  const long long total = (long long)c2 * k;
+  const double a64 = wscale->a;
+  const float a32 = (float)a64;
+  const QParamD q = make_qparam_d(-1.f, 1.f, nlvl_w);
+  const int c1_chunks = c1 / 8;
+  for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
+       e += (long long)gridDim.x * AD_THREADS) {
+    const int r = (int)(e / k), j = (int)(e % k);
+    const float ws = wstar[(long long)r * ldw + j];
+    const float du = dual[e];
+    const float v = __fadd_rn(ws, du);                                   // w_star + dual (fp32)
+    const double idx = level_index_d(__ddiv_rn((double)v, a64), q);      // fp64 discretize
+    const float b32 = (float)level_value_d(idx, q);                      // .float()
+    const float gq = __fmul_rn(a32, b32);                                // G = a_w * b_w
+    g_out[e] = gq;
+    dual[e] = __fdiv_rn(__fadd_rn(__fsub_rn(ws, gq), du), dual_div);     // (w*-G+dual) [/2 on rho steps]
+    if (wcodes) {
+      const int c = j / taps, t = j % taps;
+      const float code = (float)(2.0 * idx - (double)(nlvl_w - 1));      // odd integer in [-(L-1), L-1]
+      wcodes[(((long long)t * c1_chunks + (c >> 3)) * c2 + r) * 8 + (c & 7)] = __float2bfloat16_rn(code);
+    }
+  }
+  if (has_bias && bstar_out) {
+    for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < c2; r += gridDim.x * AD_THREADS)
+      bstar_out[r] = wstar[(long long)r * ldw + k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && st) {
+    st->a_w = a32;
+    const double ax = xscale ? (double)(float)xscale->a / (double)(nlvl_a - 1) : 1.0;
+    st->conv_scale = (float)(ax * (double)a32 / (double)(nlvl_w - 1));
+  }
+}
+
+__global__ void admm_decide_kernel(effq_admm_state* st, const double* __restrict__ sse, double numel,
+                                   float* __restrict__ history, int* __restrict__ take) {
+  const float loss = (float)(*sse / numel);              // F.mse_loss(...).item()
+  const int it = st->iter;
+  const int keep = (it == 0 || loss < st->best_loss) ? 1 : 0;   // EfficientQConv.py:139
+  if (keep) { st->best_loss = loss; st->best_iter = it; st->best_conv_scale = st->conv_scale; }
+  st->last_loss = loss;
+  st->sse = *sse;
+  if (history) history[it] = loss;
+  st->iter = it + 1;
+  *take = keep;
+}
+
+__global__ void __launch_bounds__(AD_THREADS)
+admm_keep_kernel(const int* __restrict__ take, const float* __restrict__ g, const float* __restrict__ bstar,
+                 long long g_numel, int c2, float* __restrict__ best_g, float* __restrict__ best_b,
+                 const uint4* __restrict__ aux_src, uint4* __restrict__ aux_dst, long long aux_vec) {
+  if (*take == 0) return;
+  for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < aux_vec;
+       e += (long long)gridDim.x * AD_THREADS) aux_dst[e] = aux_src[e];
+  for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < g_numel;
+       e += (long long)gridDim.x * AD_THREADS) best_g[e] = g[e];
+  if (bstar && best_b)
+    for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < c2; r += gridDim.x * AD_THREADS)
+      best_b[r] = bstar[r];
+}
+
+}  // namespace effq
+
+extern "C" int effq_admm_rhs(const float* b0, const float* w0p, const float* g, const float* dual,
+                             float rho, float eta, int32_t c2, int32_t k, int32_t has_bias, float* b_out,
+                             void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(b0 && w0p && g && dual && b_out, "null pointer");
+  EFFQ_CHECK_ARG(c2 > 0 && k > 0, "bad shape");
+  const int kp = k + (has_bias ? 1 : 0);
+  admm_rhs_kernel<<<grid_for((long long)c2 * kp), AD_THREADS, 0, (cudaStream_t)stream>>>(
+      b0, w0p, g, dual, rho, eta, c2, k, kp, b_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_admm_lhs(const float* a0, float rho, float eta, int32_t kp, int32_t has_bias,
+                             float* a_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(a0 && a_out && kp > 0, "bad argument");
+  admm_lhs_kernel<<<grid_for((long long)kp * kp), AD_THREADS, 0, (cudaStream_t)stream>>>(
+      a0, rho, eta, kp, has_bias, a_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
+                                 const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
+                                 int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
+                                 float* bstar_out, void* wcodes_out, effq_admm_state* st, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(wstar && dual && wscale && g_out, "null pointer");
+  EFFQ_CHECK_ARG(c2 > 0 && c1 > 0 && taps > 0 && ldw >= (int64_t)c1 * taps + (has_bias ? 1 : 0), "bad shape");
+  EFFQ_CHECK_ARG(!wcodes_out || (c1 % 8 == 0 && nlvl_w <= 256), "weight codes need c1 % 8 == 0, nlvl_w <= 256");
+  EFFQ_CHECK_ARG(dual_div != 0.f, "dual_div must be non-zero");
+  admm_project_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
+      wstar, ldw, dual, wscale, xscale, nlvl_w, nlvl_a, c2, c1, taps, has_bias, dual_div, g_out, bstar_out,
+      (__nv_bfloat16*)wcodes_out, st);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const float* g,
+                               const float* bstar, int64_t g_numel, int32_t c2, float* best_g, float* best_b,
+                               float* history, const void* aux_src, void* aux_dst, int64_t aux_bytes,
+                               void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(st && sse && g && best_g && numel > 0, "bad argument");
+  EFFQ_CHECK_ARG(aux_bytes == 0 || (aux_src && aux_dst && aux_bytes % 16 == 0 &&
+                                    ((uintptr_t)aux_src & 15) == 0 && ((uintptr_t)aux_dst & 15) == 0),
+                 "aux buffers must be 16B aligned and sized");
+  cudaStream_t s = (cudaStream_t)stream;
+  int* take = &st->take_;
+  admm_decide_kernel<<<1, 1, 0, s>>>(st, sse, numel, history, take);
+  EFFQ_LAUNCH_CHECK();
+  admm_keep_kernel<<<grid_for(g_numel), AD_THREADS, 0, s>>>(take, g, bstar, g_numel, c2, best_g, best_b,
+                                                                           (const uint4*)aux_src, (uint4*)aux_dst, aux_bytes / 16);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,131 @@
+// Shared helpers for the effq_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/effq_b200.h"
+
+namespace effq {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int  sm_count();
+
+#define EFFQ_CHECK_ARG(cond, msg)                                   \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      effq::set_error("%s: %s", __func__, msg);                     \
+      return 1;                                                     \
+    }                                                               \
+  } while (0)
+
+#define EFFQ_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      effq::set_error("%s: %s -> %s", __func__, #call, cudaGetErrorString(e_)); \
+      return 2;                                                                \
+    }                                                                          \
+  } while (0)
+
+#define EFFQ_LAUNCH_CHECK()                                                     \
+  do {                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                        \
+    if (e_ != cudaSuccess) {                                                    \
+      effq::set_error("%s: launch failed -> %s", __func__, cudaGetErrorString(e_)); \
+      return 2;                                                                 \
+    }                                                                           \
+    effq::count_launch();                                                       \
+  } while (0)
+
+struct OutDims {
+  int od, oh, ow;
+  long long vox_per_sample;   // od*oh*ow
+  long long vox;              // n*od*oh*ow
+};
+
+__host__ __device__ inline OutDims out_dims(const effq_geom& g) {
+  OutDims o;
+  o.od = (g.d + 2 * g.pd - g.kd) / g.sd + 1;
+  o.oh = (g.h + 2 * g.ph - g.kh) / g.sh + 1;
+  o.ow = (g.w + 2 * g.pw - g.kw) / g.sw + 1;
+  o.vox_per_sample = (long long)o.od * o.oh * o.ow;
+  o.vox = o.vox_per_sample * g.n;
+  return o;
+}
+
+// ---- reductions -------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of a double; result valid in thread 0. `scratch` >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();                 // scratch may be reused by back-to-back calls
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = lane < nw ? scratch[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ---- the reference's discretize, op for op (layer_helper.py:25-37) -----------
+// fp32: every operation individually rounded (no FMA contraction), IEEE division,
+// clamp that propagates NaN like torch.clamp, rintf == round-half-to-even.
+struct QParamF {
+  float lo, hi, delta;
+};
+__host__ __device__ inline QParamF make_qparam_f(float lo, float hi, int nlvl) {
+  QParamF q;
+  q.lo = lo;
+  q.hi = hi;
+  q.delta = (float)(((double)hi - (double)lo) / (double)(nlvl - 1));
+  return q;
+}
+__device__ __forceinline__ float clampf_nan(float t, float lo, float hi) {
+  return t < lo ? lo : (t > hi ? hi : t);
+}
+// level index of t (already divided by the scale)
+__device__ __forceinline__ float level_index_f(float t, const QParamF& q) {
+  t = clampf_nan(t, q.lo, q.hi);
+  return rintf(__fdiv_rn(__fsub_rn(t, q.lo), q.delta));
+}
+__device__ __forceinline__ float level_value_f(float idx, const QParamF& q) {
+  return __fadd_rn(__fmul_rn(idx, q.delta), q.lo);
+}
+
+struct QParamD {
+  double lo, hi, delta;
+};
+__host__ __device__ inline QParamD make_qparam_d(float lo, float hi, int nlvl) {
+  QParamD q;
+  q.lo = lo;
+  q.hi = hi;
+  q.delta = ((double)hi - (double)lo) / (double)(nlvl - 1);
+  return q;
+}
+__device__ __forceinline__ double level_index_d(double t, const QParamD& q) {
+  t = t < q.lo ? q.lo : (t > q.hi ? q.hi : t);
+  return rint(__ddiv_rn(__dsub_rn(t, q.lo), q.delta));
+}
+__device__ __forceinline__ double level_value_d(double idx, const QParamD& q) {
+  return __dadd_rn(__dmul_rn(idx, q.delta), q.lo);
+}
+
+}  // namespace effq

@@ -1,0 +1,511 @@
+// tcgen05 implicit-GEMM 3D convolution on integer codes with the reconstruction-error
+// reduction fused into the epilogue.  Replaces, for quantised-activation layers,
+//     out_q = F.conv3d(Qact, G, b*) ; loss = F.mse_loss(out_q, out_fp)
+// (reference src/models/EfficientQConv.py:118-122, 200x per layer, and :161-165).
+//
+// Arithmetic: Qact = a_x * cx/(La-1) and G = a_w * cw/(Lw-1) with cx in 0..La-1 and cw an
+// odd integer in [-(Lw-1), Lw-1]; both are exact in bf16 (<= 8 significant bits), the
+// products are exact and the fp32 TMEM accumulation of integers is exact below 2^24, so
+// the tensor-core result is  conv_scale * (exact integer) + bias  -- at least as accurate
+// as the reference's fp32 conv.
+//
+// GEMM view: M = output voxels (tile = 16 h-rows x 8 w, one d-plane -> 128 rows),
+// N = C2, K = taps * C1.  No im2col: the producer warps copy ONE halo block
+// (kd x (16+kh-1) x (8+kw-1) voxels x <=64 channels) per tile into shared memory in the
+// UMMA "interleaved" (no-swizzle, K-major) layout  [channel/8][halo voxel][8 channels];
+// the A descriptor of tap (a,b,c) is the same block with the start address shifted by
+// ((a*HH + b)*WP + c) voxels, so every activation byte is fetched from L2 once per tile
+// and reused by all taps.  Weights [tap][C1/8][C2][8] arrive by 1D bulk TMA copies
+// (cp.async.bulk + mbarrier complete_tx), resident for the whole kernel when they fit,
+// else through a ring.  One elected thread issues tcgen05.mma (M=128, N=C2, K=16) into a
+// double-buffered TMEM accumulator; four epilogue warps drain it with tcgen05.ld, apply
+// scale+bias, read the fp32 target (NCDHW), and reduce att*(out-target)^2.
+//
+// Warp roles (320 threads): 0 weight TMA | 1 MMA issuer + TMEM owner | 2-5 epilogue |
+// 6-9 halo producers (cp.async, zero-fill for padding / ragged edges).
+#include "common.cuh"
+
+namespace effq {
+
+constexpr int TC_THREADS = 320;
+constexpr int TC_TILE_H = 16;
+constexpr int TC_TILE_W = 8;
+constexpr int TC_PRODUCERS = 128;
+constexpr int TC_EPI = 128;
+constexpr unsigned int TC_SPIN_LIMIT = 1u << 26;
+
+struct TcParams {
+  const __nv_bfloat16* xq;     // NDHWC codes
+  const __nv_bfloat16* wq;     // [tap][C1/8][C2][8]
+  const float* bias;
+  const float* conv_scale;
+  float* out;                  // NCDHW or null
+  const float* target;         // NCDHW or null
+  const float* att;            // N,D,H,W or null
+  double* sse;
+  unsigned int* ws_done;       // workspace: [done, abort, pad, pad] then partials
+  double* ws_partial;
+  int n, c1, c2, d, h, w;
+  int kd, kh, kw, pd, ph, pw, taps;
+  int cg, n_groups, nch;       // channels per halo block, blocks per tile, cg/8
+  int hh, wp, hv;              // halo rows per plane, halo cols, halo voxels
+  int tiles_h, tiles_w;
+  long long n_tiles;
+  int n_halo_stages, n_w_stages, w_resident;
+  unsigned int halo_bytes, wtile_bytes;
+  unsigned int off_bias, off_halo, off_w;
+  unsigned int tmem_cols;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: returns false (and raises the global abort flag) instead of hanging.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile unsigned int* abort_flag) {
+  unsigned int spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0) {
+      if (*abort_flag != 0u) return false;
+      if (spins > TC_SPIN_LIMIT) { *abort_flag = 1u; __threadfence(); return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle ("interleaved") UMMA shared-memory descriptor.
+//   rows inside an 8-row core matrix are 16 B apart; sbo = bytes between 8-row groups
+//   (M/N direction); lbo = bytes between the two 8-element K chunks of one K=16 MMA.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;                  // descriptor version 1 (Blackwell)
+  return d;                                // base_offset 0, layout_type 0 = SWIZZLE_NONE
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  uint32_t i = 0;
+  i |= 1u << 4;                            // c_format = F32
+  i |= 1u << 7;                            // a_format = BF16
+  i |= 1u << 10;                           // b_format = BF16
+  i |= (uint32_t)(n >> 3) << 17;           // N / 8
+  i |= (uint32_t)(128 >> 4) << 24;         // M / 16
+  return i;
+}
+
+struct Pipe {
+  int stage;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1u; }
+  }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // barrier block (8 B each): halo_full[4] halo_empty[4] w_full[8] w_empty[8] wres tmem_full[2] tmem_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_HF = 0, B_HE = 4, B_WF = 8, B_WE = 16, B_WRES = 24, B_TF = 25, B_TE = 27, B_TMEMPTR = 30;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + B_TMEMPTR);
+  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+  const uint32_t halo0 = smem_u32(smem + p.off_halo);
+  const uint32_t wsm0 = smem_u32(smem + p.off_w);
+  __shared__ double red_scratch[32];
+  __shared__ bool is_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  volatile unsigned int* abort_flag = p.ws_done + 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_HF + i), TC_PRODUCERS); mbar_init(BAR(B_HE + i), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(BAR(B_WF + i), 1); mbar_init(BAR(B_WE + i), 1); }
+    mbar_init(BAR(B_WRES), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TF + i), 1); mbar_init(BAR(B_TE + i), TC_EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.c2; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const long long tile0 = blockIdx.x, tstep = gridDim.x;
+  double err_acc = 0.0;
+
+  if (warp == 0) {
+    // ===== weight loader (one lane) =====
+    if (lane == 0) {
+      if (p.w_resident) {
+        const uint32_t total = p.wtile_bytes * (uint32_t)(p.n_groups * p.taps);
+        mbar_expect_tx(BAR(B_WRES), total);
+        for (int g = 0; g < p.n_groups; ++g)
+          for (int t = 0; t < p.taps; ++t) {
+            const __nv_bfloat16* src = p.wq + ((long long)t * (p.c1 / 8) + (long long)g * p.nch) * p.c2 * 8;
+            bulk_g2s(wsm0 + (uint32_t)(g * p.taps + t) * p.wtile_bytes, src, p.wtile_bytes, BAR(B_WRES));
+          }
+      } else {
+        Pipe wp{0, 0};
+        bool ok = true;
+        for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep)
+          for (int g = 0; g < p.n_groups && ok; ++g)
+            for (int t = 0; t < p.taps; ++t) {
+              if (!mbar_wait(BAR(B_WE + wp.stage), wp.phase ^ 1u, abort_flag)) { ok = false; break; }
+              mbar_expect_tx(BAR(B_WF + wp.stage), p.wtile_bytes);
+              const __nv_bfloat16* src = p.wq + ((long long)t * (p.c1 / 8) + (long long)g * p.nch) * p.c2 * 8;
+              bulk_g2s(wsm0 + (uint32_t)wp.stage * p.wtile_bytes, src, p.wtile_bytes, BAR(B_WF + wp.stage));
+              wp.advance(p.n_w_stages);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(p.c2);
+      const uint32_t a_lbo = (uint32_t)p.hv * 16u, a_sbo = (uint32_t)p.wp * 16u;
+      const uint32_t b_lbo = (uint32_t)p.c2 * 16u, b_sbo = 128u;
+      const int kk_n = p.cg / 16;
+      Pipe hp{0, 0}, wp{0, 0}, ap{0, 0};
+      bool ok = true;
+      if (p.w_resident) ok = mbar_wait(BAR(B_WRES), 0, abort_flag);
+      for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
+        if (!mbar_wait(BAR(B_TE + ap.stage), ap.phase ^ 1u, abort_flag)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ap.stage * p.c2);
+        uint32_t first = 1;
+        for (int g = 0; g < p.n_groups && ok; ++g) {
+          if (!mbar_wait(BAR(B_HF + hp.stage), hp.phase, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
+          int t = 0;
+          for (int a = 0; a < p.kd && ok; ++a)
+            for (int b = 0; b < p.kh && ok; ++b)
+              for (int c = 0; c < p.kw; ++c, ++t) {
+                uint32_t wbase;
+                if (p.w_resident) {
+                  wbase = wsm0 + (uint32_t)(g * p.taps + t) * p.wtile_bytes;
+                } else {
+                  if (!mbar_wait(BAR(B_WF + wp.stage), wp.phase, abort_flag)) { ok = false; break; }
+                  tc_fence_after();
+                  wbase = wsm0 + (uint32_t)wp.stage * p.wtile_bytes;
+                }
+                const uint32_t shift = (uint32_t)((a * p.hh + b) * p.wp + c) * 16u;
+                for (int kk = 0; kk < kk_n; ++kk) {
+                  const uint64_t ad = umma_desc(hbase + shift + (uint32_t)(2 * kk) * a_lbo, a_lbo, a_sbo);
+                  const uint64_t bd = umma_desc(wbase + (uint32_t)(2 * kk) * b_lbo, b_lbo, b_sbo);
+                  tc_mma_bf16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+                if (!p.w_resident) { tc_commit(BAR(B_WE + wp.stage)); wp.advance(p.n_w_stages); }
+              }
+          tc_commit(BAR(B_HE + hp.stage));
+          hp.advance(p.n_halo_stages);
+        }
+        if (ok) tc_commit(BAR(B_TF + ap.stage));
+        ap.advance(2);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue: TMEM -> registers -> scale+bias -> out / squared error =====
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;               // tile row = hy*8 + wx
+    const int hy = row >> 3, wx = row & 7;
+    const float scale = __ldg(p.conv_scale);
+    const long long plane = (long long)p.h * p.w;
+    const long long chan = (long long)p.d * plane;
+    Pipe ap{0, 0};
+    bool ok = true;
+    for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
+      long long r = tile;
+      const int tw = (int)(r % p.tiles_w); r /= p.tiles_w;
+      const int th = (int)(r % p.tiles_h); r /= p.tiles_h;
+      const int dd = (int)(r % p.d); r /= p.d;
+      const int nn = (int)r;
+      const int oh = th * TC_TILE_H + hy, ow = tw * TC_TILE_W + wx;
+      const bool live = oh < p.h && ow < p.w;
+      const long long sp = (long long)dd * plane + (long long)oh * p.w + ow;
+      const long long base = (long long)nn * p.c2 * chan + sp;
+      if (!mbar_wait(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
+      tc_fence_after();
+      float e32 = 0.f;
+      for (int c0 = 0; c0 < p.c2; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.c2 + c0);
+        const int ncol = min(32, p.c2 - c0);
+        if (ncol == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
+        tc_wait_ld();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < ncol) {
+              const float o = fmaf(__uint_as_float(v[j]), scale, bias_s[c0 + j]);
+              const long long oi = base + (long long)(c0 + j) * chan;
+              if (p.out) p.out[oi] = o;
+              if (p.target) {
+                const float dlt = o - __ldg(p.target + oi);
+                e32 = fmaf(dlt, dlt, e32);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(B_TE + ap.stage));
+      ap.advance(2);
+      if (live && p.target) {
+        const float wv = p.att ? __ldg(p.att + (long long)nn * chan + sp) : 1.f;
+        err_acc += (double)e32 * (double)wv;
+      }
+    }
+  } else {
+    // ===== halo producers: cp.async 16 B pieces, zero-fill outside the volume =====
+    const int pw_id = warp - 6;                  // 0..3
+    const int rows = p.kd * p.hh;
+    const int items = p.wp * p.nch;
+    const int nch_shift = p.nch == 8 ? 3 : (p.nch == 4 ? 2 : 1);
+    Pipe hp{0, 0};
+    bool ok = true;
+    bool pending = false;
+    int pending_stage = 0;
+    for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
+      long long r = tile;
+      const int tw = (int)(r % p.tiles_w); r /= p.tiles_w;
+      const int th = (int)(r % p.tiles_h); r /= p.tiles_h;
+      const int dd = (int)(r % p.d); r /= p.d;
+      const int nn = (int)r;
+      const int h0 = th * TC_TILE_H - p.ph, w0 = tw * TC_TILE_W - p.pw, d0 = dd - p.pd;
+      for (int g = 0; g < p.n_groups; ++g) {
+        if (!mbar_wait(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
+        const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
+        for (int rr = pw_id; rr < rows; rr += 4) {
+          const int dz = rr / p.hh, hyy = rr - dz * p.hh;
+          const int gd = d0 + dz, gh = h0 + hyy;
+          const bool row_ok = (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h;
+          const __nv_bfloat16* rowp =
+              p.xq + ((((long long)nn * p.d + (row_ok ? gd : 0)) * p.h + (row_ok ? gh : 0)) * p.w) * p.c1 + g * p.cg;
+          for (int it = lane; it < items; it += 32) {
+            const int wxx = it >> nch_shift, j = it & (p.nch - 1);
+            const int gw = w0 + wxx;
+            const bool okk = row_ok && (unsigned)gw < (unsigned)p.w;
+            const __nv_bfloat16* src = okk ? rowp + (long long)gw * p.c1 + j * 8 : p.xq;
+            cp_async16(hbase + (uint32_t)((j * p.hv + rr * p.wp + wxx) * 16), src, okk ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (pending) {                              // previous block: complete -> visible to the async proxy -> signal
+          cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(BAR(B_HF + pending_stage));
+        }
+        pending = true;
+        pending_stage = hp.stage;
+        hp.advance(p.n_halo_stages);
+      }
+    }
+    if (pending) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(BAR(B_HF + pending_stage));
+    }
+  }
+
+  // ---- teardown -------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+  if (!p.target) return;
+  // deterministic reduction: block tree -> per-CTA partial -> last CTA folds in index order
+  const double bsum = block_sum(err_acc, red_scratch);
+  if (threadIdx.x == 0) {
+    p.ws_partial[blockIdx.x] = bsum;
+    __threadfence();
+    is_last = (atomicAdd(p.ws_done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += TC_THREADS) t += ((volatile double*)p.ws_partial)[b];
+    t = block_sum(t, red_scratch);
+    if (threadIdx.x == 0) {
+      *p.sse = (*abort_flag != 0u) ? __longlong_as_double(0x7ff8000000000000ll) : t;   // NaN on abort
+      *p.ws_done = 0;
+    }
+  }
+}
+
+static bool tc_plan(const effq_geom& g, TcParams& p) {
+  if (!((g.kd == 3 && g.kh == 3 && g.kw == 3 && g.pd == 1 && g.ph == 1 && g.pw == 1) ||
+        (g.kd == 1 && g.kh == 1 && g.kw == 1 && g.pd == 0 && g.ph == 0 && g.pw == 0)))
+    return false;
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1) return false;
+  if (g.c1 % 16 != 0 || g.c2 % 16 != 0 || g.c2 < 16 || g.c2 > 256) return false;
+  if (g.c1 > 64 && g.c1 % 64 != 0) return false;
+  if (g.c1 != 16 && g.c1 != 32 && g.c1 < 64) return false;           // nch must be 2, 4 or 8
+  p.n = g.n; p.c1 = g.c1; p.c2 = g.c2; p.d = g.d; p.h = g.h; p.w = g.w;
+  p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
+  p.taps = g.kd * g.kh * g.kw;
+  p.cg = g.c1 < 64 ? g.c1 : 64;
+  p.n_groups = g.c1 / p.cg;
+  p.nch = p.cg / 8;
+  p.hh = TC_TILE_H + g.kh - 1;
+  p.wp = TC_TILE_W + g.kw - 1;
+  p.hv = g.kd * p.hh * p.wp;
+  p.tiles_h = (g.h + TC_TILE_H - 1) / TC_TILE_H;
+  p.tiles_w = (g.w + TC_TILE_W - 1) / TC_TILE_W;
+  p.n_tiles = (long long)g.n * g.d * p.tiles_h * p.tiles_w;
+  // +16 B: the last tap's descriptor of the last 8-row group may touch one slot past the block
+  p.halo_bytes = (uint32_t)(p.nch * p.hv * 16);
+  p.halo_bytes = (p.halo_bytes + 127u) & ~127u;
+  p.wtile_bytes = (uint32_t)(p.cg * g.c2 * 2);
+  p.off_bias = 256;
+  p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 127u) & ~127u;
+  const uint32_t budget = 220u * 1024u;
+  const uint32_t w_all = p.wtile_bytes * (uint32_t)(p.n_groups * p.taps);
+  p.n_halo_stages = 2;
+  if (p.off_halo + 2u * p.halo_bytes + w_all <= budget) {
+    p.w_resident = 1;
+    p.n_w_stages = 0;
+    uint32_t left = budget - (p.off_halo + w_all);
+    int hs = (int)(left / p.halo_bytes);
+    p.n_halo_stages = hs > 4 ? 4 : hs;
+    p.off_w = p.off_halo + (uint32_t)p.n_halo_stages * p.halo_bytes;
+  } else {
+    p.w_resident = 0;
+    p.off_w = p.off_halo + 2u * p.halo_bytes;
+    if (p.off_w + 2u * p.wtile_bytes > budget) return false;
+    int ws = (int)((budget - p.off_w) / p.wtile_bytes);
+    p.n_w_stages = ws > 8 ? 8 : ws;
+  }
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * g.c2)) cols <<= 1;
+  p.tmem_cols = cols;
+  return cols <= 512;
+}
+
+static uint32_t tc_smem_bytes(const TcParams& p) {
+  const uint32_t w = p.w_resident ? p.wtile_bytes * (uint32_t)(p.n_groups * p.taps)
+                                  : p.wtile_bytes * (uint32_t)p.n_w_stages;
+  return p.off_w + w + 128u;
+}
+
+}  // namespace effq
+
+extern "C" int effq_conv3d_tc_supported(const effq_geom* g) {
+  effq::TcParams p;
+  return (g && effq::tc_plan(*g, p)) ? 1 : 0;
+}
+
+extern "C" int64_t effq_conv3d_tc_workspace(const effq_geom* g) {
+  (void)g;
+  return 16 + 8 * 1024;
+}
+
+extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const float* bias, const float* conv_scale,
+                              const effq_geom* g, float* out, const float* target, const float* att, double* sse,
+                              void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(xcodes && wcodes && conv_scale && g && workspace, "null pointer");
+  EFFQ_CHECK_ARG(out || target, "nothing to compute");
+  EFFQ_CHECK_ARG(!target || sse, "sse required with target");
+  EFFQ_CHECK_ARG(((uintptr_t)xcodes & 15) == 0 && ((uintptr_t)wcodes & 15) == 0, "operands must be 16B aligned");
+  TcParams p;
+  EFFQ_CHECK_ARG(tc_plan(*g, p), "geometry not supported by the tcgen05 path");
+  p.xq = (const __nv_bfloat16*)xcodes;
+  p.wq = (const __nv_bfloat16*)wcodes;
+  p.bias = bias;
+  p.conv_scale = conv_scale;
+  p.out = out;
+  p.target = target;
+  p.att = att;
+  p.sse = sse;
+  p.ws_done = (unsigned int*)workspace;
+  p.ws_partial = (double*)((char*)workspace + 16);
+  const uint32_t smem = tc_smem_bytes(p);
+  static uint32_t configured = 0;
+  if (smem > configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  conv3d_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,184 @@
+// Fused fake-quant kernels (HBM-bound).
+//   effq_fakequant_f32      : reference PTQConv._quantize_act/_quantize_w
+//                             (src/models/PTQConv.py:110-116 -> layer_helper.py:25-37)
+//   effq_quantize_act_ndhwc : same arithmetic, emits channels-last bf16 integer codes,
+//                             the operand format of the tcgen05 conv.
+#include "common.cuh"
+
+namespace effq {
+
+constexpr int FQ_THREADS = 256;
+constexpr int FQ_VEC = 4;        // one 128-bit load per thread per step
+constexpr int FQ_UNROLL = 4;     // independent 128-bit loads in flight per thread
+
+template <bool WRITE_Y, bool WRITE_C>
+__global__ void __launch_bounds__(FQ_THREADS)
+fakequant_f32_kernel(const float* __restrict__ x, long long numel, const float* __restrict__ alpha_p,
+                     QParamF q, float* __restrict__ y, uint8_t* __restrict__ code) {
+  const float alpha = __ldg(alpha_p);
+  const long long nvec = numel / FQ_VEC;
+  const long long stride = (long long)gridDim.x * FQ_THREADS;
+  long long i = (long long)blockIdx.x * FQ_THREADS + threadIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (; i < nvec; i += stride * FQ_UNROLL) {
+    float4 v[FQ_UNROLL];
+#pragma unroll
+    for (int u = 0; u < FQ_UNROLL; ++u) {
+      long long j = i + u * stride;
+      if (j < nvec) v[u] = __ldcs(x4 + j);          // streamed: read once
+    }
+#pragma unroll
+    for (int u = 0; u < FQ_UNROLL; ++u) {
+      long long j = i + u * stride;
+      if (j >= nvec) continue;
+      float in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float out[4];
+      uint32_t packed = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float idx = level_index_f(__fdiv_rn(in[e], alpha), q);
+        out[e] = __fmul_rn(level_value_f(idx, q), alpha);
+        packed |= ((uint32_t)(int)idx & 0xffu) << (8 * e);
+      }
+      if (WRITE_Y) __stcs(reinterpret_cast<float4*>(y) + j, make_float4(out[0], out[1], out[2], out[3]));
+      if (WRITE_C) reinterpret_cast<uint32_t*>(code)[j] = packed;
+    }
+  }
+  // tail (numel % 4), handled by block 0
+  if (blockIdx.x == 0) {
+    long long t = nvec * FQ_VEC + threadIdx.x;
+    if (t < numel) {
+      float idx = level_index_f(__fdiv_rn(x[t], alpha), q);
+      if (WRITE_Y) y[t] = __fmul_rn(level_value_f(idx, q), alpha);
+      if (WRITE_C) code[t] = (uint8_t)(int)idx;
+    }
+  }
+}
+
+// Qact = a_act * b_act with b from project_by_iter's final fp64 discretize
+// (reference EfficientQConv.py:68-70, layer_helper.py:67): fp32(a) * fp32(level(x/a)).
+__global__ void __launch_bounds__(FQ_THREADS)
+fakequant_state_kernel(const float* __restrict__ x, long long numel, const effq_scale_state* __restrict__ st,
+                       QParamD q, float* __restrict__ y) {
+  const double a64 = st->a;
+  const float a32 = (float)a64;
+  for (long long i = (long long)blockIdx.x * FQ_THREADS + threadIdx.x; i < numel;
+       i += (long long)gridDim.x * FQ_THREADS) {
+    const double idx = level_index_d(__ddiv_rn((double)__ldcs(x + i), a64), q);
+    y[i] = __fmul_rn(a32, (float)level_value_d(idx, q));
+  }
+}
+
+// NCDHW fp32 -> NDHWC bf16 codes.  One CTA handles TILE_V consecutive voxels of one
+// sample for all C channels: coalesced reads along the voxel axis per channel,
+// transpose through shared memory, one contiguous TILE_V*C*2-byte store.
+constexpr int QA_TILE_V = 64;
+constexpr int QA_THREADS = 256;
+
+template <bool F64>
+__global__ void __launch_bounds__(QA_THREADS)
+quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int nlvl,
+                          const effq_scale_state* __restrict__ st, const float* __restrict__ alpha_f32,
+                          __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __nv_bfloat16 tile[];      // [QA_TILE_V][c + 2] (pad keeps banks apart)
+  const int cp = c + 2;
+  const long long tiles_per_sample = (dhw + QA_TILE_V - 1) / QA_TILE_V;
+  const long long n_idx = blockIdx.x / tiles_per_sample;
+  const long long v0 = (blockIdx.x % tiles_per_sample) * QA_TILE_V;
+  const int nv = (int)min((long long)QA_TILE_V, dhw - v0);
+  const float* xs = x + n_idx * (long long)c * dhw + v0;
+
+  const QParamF qf = make_qparam_f(0.f, 1.f, nlvl);
+  const QParamD qd = make_qparam_d(0.f, 1.f, nlvl);
+  const double a64 = F64 ? st->a : 0.0;
+  const float a32 = F64 ? 0.f : __ldg(alpha_f32);
+
+  for (int e = threadIdx.x; e < c * QA_TILE_V; e += QA_THREADS) {
+    const int ch = e / QA_TILE_V, v = e % QA_TILE_V;
+    float code = 0.f;
+    if (v < nv) {
+      const float val = __ldcs(xs + (long long)ch * dhw + v);
+      if (F64) code = (float)level_index_d(__ddiv_rn((double)val, a64), qd);
+      else     code = level_index_f(__fdiv_rn(val, a32), qf);
+    }
+    tile[v * cp + ch] = __float2bfloat16_rn(code);
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out + (n_idx * dhw + v0) * c;
+  // c is even (checked on the host): move bf16 pairs
+  const int pairs = c / 2;
+  for (int e = threadIdx.x; e < nv * pairs; e += QA_THREADS) {
+    const int v = e / pairs, p = e % pairs;
+    const __nv_bfloat162 two = *reinterpret_cast<const __nv_bfloat162*>(&tile[v * cp + 2 * p]);
+    reinterpret_cast<__nv_bfloat162*>(dst + (long long)v * c)[p] = two;
+  }
+}
+
+}  // namespace effq
+
+extern "C" int effq_fakequant_f32(const float* x, int64_t numel, const float* alpha, float lo, float hi,
+                                  int32_t nlvl, float* y_out, uint8_t* code_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && alpha, "null input");
+  EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
+  EFFQ_CHECK_ARG(!code_out || nlvl <= 256, "uint8 codes need nlvl <= 256");
+  EFFQ_CHECK_ARG(y_out || code_out, "nothing to write");
+  EFFQ_CHECK_ARG(((uintptr_t)x & 15) == 0 && (!y_out || ((uintptr_t)y_out & 15) == 0) &&
+                     (!code_out || ((uintptr_t)code_out & 3) == 0), "pointers must be 16B aligned");
+  if (numel <= 0) return 0;
+  const QParamF q = make_qparam_f(lo, hi, nlvl);
+  const long long nvec = numel / FQ_VEC;
+  long long blocks = (nvec + (long long)FQ_THREADS * FQ_UNROLL - 1) / ((long long)FQ_THREADS * FQ_UNROLL);
+  const long long cap = (long long)sm_count() * 8;     // 8 resident CTAs/SM, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (y_out && code_out)
+    fakequant_f32_kernel<true, true><<<(unsigned)blocks, FQ_THREADS, 0, s>>>(x, numel, alpha, q, y_out, code_out);
+  else if (y_out)
+    fakequant_f32_kernel<true, false><<<(unsigned)blocks, FQ_THREADS, 0, s>>>(x, numel, alpha, q, y_out, code_out);
+  else
+    fakequant_f32_kernel<false, true><<<(unsigned)blocks, FQ_THREADS, 0, s>>>(x, numel, alpha, q, y_out, code_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_fakequant_state(const float* x, int64_t numel, const effq_scale_state* state, float lo,
+                                    float hi, int32_t nlvl, float* y_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && state && y_out, "null pointer");
+  EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
+  if (numel <= 0) return 0;
+  long long blocks = (numel + FQ_THREADS - 1) / FQ_THREADS;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  fakequant_state_kernel<<<(unsigned)blocks, FQ_THREADS, 0, (cudaStream_t)stream>>>(
+      x, numel, state, make_qparam_d(lo, hi, nlvl), y_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, int32_t nlvl,
+                                       const effq_scale_state* state, const float* alpha_f32,
+                                       int32_t use_f64, void* codes_bf16_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && codes_bf16_out, "null pointer");
+  EFFQ_CHECK_ARG(use_f64 ? state != nullptr : alpha_f32 != nullptr, "missing scale");
+  EFFQ_CHECK_ARG(nlvl >= 2 && nlvl <= 256, "nlvl out of range for bf16-exact codes");
+  EFFQ_CHECK_ARG(c > 0 && c % 2 == 0 && c <= 512, "channel count must be even and <= 512");
+  if (n <= 0 || dhw <= 0) return 0;
+  const long long tiles = (long long)n * ((dhw + QA_TILE_V - 1) / QA_TILE_V);
+  EFFQ_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
+  const size_t smem = (size_t)QA_TILE_V * (c + 2) * sizeof(__nv_bfloat16);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (smem > 48 * 1024) {
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (use_f64)
+    quantize_act_ndhwc_kernel<true><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, (__nv_bfloat16*)codes_bf16_out);
+  else
+    quantize_act_ndhwc_kernel<false><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, (__nv_bfloat16*)codes_bf16_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}

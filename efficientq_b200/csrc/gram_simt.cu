@@ -1,0 +1,214 @@
+// Normal-equation statistics without ever materialising the im2col matrix.
+// Replaces im2col_loop + QuadraSolver.getA0B0 (reference src/models/solver.py:86-111,
+// :253-257, :282-314):
+//
+//     A0 = 2 * sum_v att_v * xhat_v xhat_v^T        (K' x K')
+//     B0 = 2 * sum_v att_v * y_v    xhat_v^T        (C2 x K')
+//
+// xhat_v = the (c,kd,kh,kw)-ordered input patch of output voxel v, plus a trailing 1
+// when the layer has a bias (solver.py:255-256).  B0 is exactly conv-wgrad with
+// grad_out = att*Y; A0 is the im2col Gram matrix.
+//
+// Generic fp32 implementation (any geometry): one GEMM  [Xhat ; Y] (att.Xhat)^T with
+// the reduction over voxels, 64x64 output tiles, 4x4 register micro-tiles, patches
+// gathered on the fly, split over voxel ranges across CTAs.  fp32 FMA over short
+// runs (512 voxels) that are folded into fp64 accumulators, fp64 atomics into the
+// workspace, one finalize pass that applies 2 * x_scale^{1,2} and writes fp32.
+// When x holds integer codes the short fp32 runs are exact.
+#include "common.cuh"
+
+namespace effq {
+
+constexpr int GM_TILE = 64;
+constexpr int GM_KC = 16;               // voxels per smem step
+constexpr int GM_THREADS = 256;
+constexpr int GM_FLUSH = 32;            // steps between fp32 -> fp64 folds (512 voxels)
+
+struct RowDesc {                        // how to fetch one operand row
+  int kind;                             // 0: patch row, 1: ones, 2: y row, 3: padding (zero)
+  int c;                                // input channel or y channel
+  int a, b, d;                          // tap offsets (kd,kh,kw)
+};
+
+__device__ __forceinline__ RowDesc decode_row(int r, int k, int kp, int mrows, const effq_geom& g) {
+  RowDesc rd;
+  rd.kind = 3; rd.c = 0; rd.a = rd.b = rd.d = 0;
+  if (r < k) {
+    const int taps = g.kd * g.kh * g.kw;
+    rd.kind = 0;
+    rd.c = r / taps;
+    int t = r % taps;
+    rd.d = t % g.kw; t /= g.kw;
+    rd.b = t % g.kh; t /= g.kh;
+    rd.a = t;
+  } else if (r < kp) {
+    rd.kind = 1;
+  } else if (r < mrows) {
+    rd.kind = 2;
+    rd.c = r - kp;
+  }
+  return rd;
+}
+
+struct VoxPos {
+  int n, od, oh, ow;
+  bool live;
+  long long sp;                         // voxel index inside the sample
+};
+
+__device__ __forceinline__ float fetch(const RowDesc& rd, const VoxPos& p, const float* __restrict__ x,
+                                       const float* __restrict__ y, const effq_geom& g, const OutDims& o) {
+  if (!p.live || rd.kind == 3) return 0.f;
+  if (rd.kind == 1) return 1.f;
+  if (rd.kind == 2) return __ldg(y + ((long long)p.n * g.c2 + rd.c) * o.vox_per_sample + p.sp);
+  const int id = p.od * g.sd - g.pd + rd.a;
+  const int ih = p.oh * g.sh - g.ph + rd.b;
+  const int iw = p.ow * g.sw - g.pw + rd.d;
+  if ((unsigned)id >= (unsigned)g.d || (unsigned)ih >= (unsigned)g.h || (unsigned)iw >= (unsigned)g.w) return 0.f;
+  return __ldg(x + ((((long long)p.n * g.c1 + rd.c) * g.d + id) * g.h + ih) * g.w + iw);
+}
+
+__global__ void __launch_bounds__(GM_THREADS)
+gram_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ att,
+                effq_geom g, OutDims o, int k, int kp, int mrows, long long vox_per_split,
+                double* __restrict__ acc64) {
+  __shared__ float Ls[GM_KC][GM_TILE + 4];
+  __shared__ float Rs[GM_KC][GM_TILE + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int i0 = blockIdx.y * GM_TILE, j0 = blockIdx.x * GM_TILE;
+  const long long v_begin = (long long)blockIdx.z * vox_per_split;
+  const long long v_end = min(o.vox, v_begin + vox_per_split);
+
+  // loader role: this thread fetches voxel column `lk` of rows lr, lr+16, lr+32, lr+48
+  const int lk = threadIdx.x % GM_KC, lr = threadIdx.x / GM_KC;
+  RowDesc lrow[4], rrow[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    lrow[q] = decode_row(i0 + lr + 16 * q, k, kp, mrows, g);
+    const int j = j0 + lr + 16 * q;
+    rrow[q] = decode_row(j < kp ? j : mrows, k, kp, mrows, g);    // right operand has no y rows
+  }
+
+  float acc[4][4];
+  double acc_d[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { acc[a][b] = 0.f; acc_d[a][b] = 0.0; }
+
+  int step = 0;
+  for (long long v0 = v_begin; v0 < v_end; v0 += GM_KC, ++step) {
+    VoxPos p;
+    const long long v = v0 + lk;
+    p.live = v < v_end;
+    {
+      long long r = p.live ? v : 0;
+      p.ow = (int)(r % o.ow); r /= o.ow;
+      p.oh = (int)(r % o.oh); r /= o.oh;
+      p.od = (int)(r % o.od); r /= o.od;
+      p.n = (int)r;
+      p.sp = (p.live ? v : 0) - (long long)p.n * o.vox_per_sample;
+    }
+    const float wv = (p.live && att) ? __ldg(att + v) : 1.f;
+    float lv[4], rv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      lv[q] = fetch(lrow[q], p, x, y, g, o);
+      rv[q] = __fmul_rn(fetch(rrow[q], p, x, y, g, o), wv);      // x_col * att, solver.py:293
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Ls[lk][lr + 16 * q] = lv[q];
+      Rs[lk][lr + 16 * q] = rv[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GM_KC; ++kk) {
+      const float4 l4 = *reinterpret_cast<const float4*>(&Ls[kk][ty * 4]);
+      const float4 r4 = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4]);
+      const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+      const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(l[a], r[b], acc[a][b]);
+    }
+    if ((step + 1) % GM_FLUSH == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc_d[a][b] += (double)acc[a][b]; acc[a][b] = 0.f; }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty * 4 + a;
+    if (i >= mrows) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = j0 + tx * 4 + b;
+      if (j >= kp) continue;
+      const double t = acc_d[a][b] + (double)acc[a][b];
+      if (t != 0.0) atomicAdd(acc64 + (long long)i * kp + j, t);
+    }
+  }
+}
+
+__global__ void gram_finalize_kernel(const double* __restrict__ acc64, const float* __restrict__ x_scale,
+                                     int k, int kp, int c2, float* __restrict__ a0, float* __restrict__ b0) {
+  const double s = x_scale ? (double)__ldg(x_scale) : 1.0;
+  const long long total = (long long)(kp + c2) * kp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / kp), j = (int)(e % kp);
+    const double sj = j < k ? s : 1.0;
+    if (i < kp) {
+      const double si = i < k ? s : 1.0;
+      a0[e] = (float)(2.0 * si * sj * acc64[e]);
+    } else {
+      b0[(long long)(i - kp) * kp + j] = (float)(2.0 * sj * acc64[e]);
+    }
+  }
+}
+
+}  // namespace effq
+
+extern "C" int64_t effq_gram_workspace(const effq_geom* g, int32_t has_bias) {
+  if (!g) return 0;
+  const long long k = (long long)g->c1 * g->kd * g->kh * g->kw;
+  const long long kp = k + (has_bias ? 1 : 0);
+  return (int64_t)((kp + g->c2) * kp * 8);
+}
+
+extern "C" int effq_gram_f32(const float* x, const float* x_scale, const float* y, const float* att,
+                             const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out,
+                             void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && y && g && a0_out && b0_out && workspace, "null pointer");
+  const OutDims o = out_dims(*g);
+  EFFQ_CHECK_ARG(o.od > 0 && o.oh > 0 && o.ow > 0 && g->n > 0, "empty output");
+  const int k = g->c1 * g->kd * g->kh * g->kw;
+  const int kp = k + (has_bias ? 1 : 0);
+  const int mrows = kp + g->c2;
+  const int tx = (kp + GM_TILE - 1) / GM_TILE, ty = (mrows + GM_TILE - 1) / GM_TILE;
+  long long splits = ((long long)sm_count() * 6 + (long long)tx * ty - 1) / ((long long)tx * ty);
+  const long long max_splits = (o.vox + 511) / 512;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  long long per = (o.vox + splits - 1) / splits;
+  per = (per + GM_KC - 1) / GM_KC * GM_KC;
+  splits = (o.vox + per - 1) / per;
+  cudaStream_t s = (cudaStream_t)stream;
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, (size_t)mrows * kp * 8, s));
+  dim3 grid(tx, ty, (unsigned)splits);
+  gram_f32_kernel<<<grid, GM_THREADS, 0, s>>>(x, y, att, *g, o, k, kp, mrows, per, (double*)workspace);
+  EFFQ_LAUNCH_CHECK();
+  const long long total = (long long)mrows * kp;
+  int fb = (int)((total + 255) / 256);
+  if (fb > sm_count() * 16) fb = sm_count() * 16;
+  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, x_scale, k, kp, g->c2, a0_out, b0_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,311 @@
+// Device-resident scale search: reference project_by_iter
+// (src/models/layer_helper.py:40-70).
+//
+//   a0 = mean|v| ; repeat { b = Q(v/a) ; a = sum(b*v)/sum(b*b) } until |da| <= 1e-5
+//
+// The reference does one host round trip (.item()) per pass.  Here the whole fp64
+// fixed point runs inside ONE cooperative launch: every pass streams v (fp32) once
+// -- from HBM for activations, from L2 for the <= 7 MB weight tensors --, reduces the
+// two sums in fp64 (warp shuffle -> block -> per-CTA partial), crosses a grid
+// barrier, and every CTA then folds the partials in the same fixed order, so all
+// CTAs see bit-identical scales and the loop exit is uniform.  Algorithmic bytes
+// per pass: numel*4 (+numel*4 when v = v1 + v2).
+#include "common.cuh"
+
+namespace effq {
+
+constexpr int SS_THREADS = 512;
+constexpr int SS_MAX_CTAS = 1024;           // partial slots per parity
+constexpr unsigned long long SS_SPIN_LIMIT = 1ull << 28;
+
+struct SSWorkspace {
+  unsigned int barrier;                      // monotonically increasing arrival counter
+  unsigned int abort_flag;
+  unsigned int pad[2];
+  double partial[2][SS_MAX_CTAS][2];
+};
+
+struct VecView {
+  const float* v1;
+  const float* v2;
+  long long ld1, ld2, rows, cols;
+};
+
+__device__ __forceinline__ float load_v(const VecView& vv, long long r, long long c) {
+  float a = __ldg(vv.v1 + r * vv.ld1 + c);
+  if (vv.v2) a = __fadd_rn(a, __ldg(vv.v2 + r * vv.ld2 + c));   // fp32 add first, as `w_star + dual`
+  return a;
+}
+
+// One pass over this CTA's share.  MODE 0: {sum|v|, 0}. MODE 1: {sum b*v, sum b*b}.
+template <int MODE>
+__device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QParamD& q,
+                                          long long cta, long long nctas, double& s0, double& s1) {
+  s0 = 0.0;
+  s1 = 0.0;
+  const long long numel = vv.rows * vv.cols;
+  const bool flat = (vv.ld1 == vv.cols) && (!vv.v2 || vv.ld2 == vv.cols);
+  const long long stride = nctas * SS_THREADS;
+  long long i = cta * SS_THREADS + threadIdx.x;
+  if (flat && (numel % 4 == 0) && (((uintptr_t)vv.v1 & 15) == 0) && (!vv.v2 || ((uintptr_t)vv.v2 & 15) == 0)) {
+    const long long nvec = numel / 4;
+    const float4* p1 = reinterpret_cast<const float4*>(vv.v1);
+    const float4* p2 = reinterpret_cast<const float4*>(vv.v2);
+    for (; i < nvec; i += stride) {
+      float4 t = __ldg(p1 + i);
+      if (p2) {
+        const float4 u = __ldg(p2 + i);
+        t.x = __fadd_rn(t.x, u.x); t.y = __fadd_rn(t.y, u.y);
+        t.z = __fadd_rn(t.z, u.z); t.w = __fadd_rn(t.w, u.w);
+      }
+      const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double v = (double)e[k];
+        if (MODE == 0) {
+          s0 += fabs(v);
+        } else {
+          const double b = level_value_d(level_index_d(__ddiv_rn(v, a), q), q);
+          s0 += b * v;
+          s1 += b * b;
+        }
+      }
+    }
+  } else {
+    // strided rows (e.g. w* carries the bias column: ld = K+1): work item = (row, 512-col chunk)
+    const long long chunks = (vv.cols + SS_THREADS - 1) / SS_THREADS;
+    const long long items = vv.rows * chunks;
+    for (long long it = cta; it < items; it += nctas) {
+      const long long r = it / chunks;
+      const long long c = (it % chunks) * SS_THREADS + threadIdx.x;
+      if (c >= vv.cols) continue;
+      const double v = (double)load_v(vv, r, c);
+      if (MODE == 0) {
+        s0 += fabs(v);
+      } else {
+        const double b = level_value_d(level_index_d(__ddiv_rn(v, a), q), q);
+        s0 += b * v;
+        s1 += b * b;
+      }
+    }
+  }
+}
+
+// Every CTA folds the per-CTA partials in the same order (thread t takes slots
+// t, t+512, ... then the fixed block tree), so all CTAs get bit-identical sums.
+__device__ __forceinline__ void fold_partials(const double (*part)[2], unsigned int nctas,
+                                              double* scratch, double* bc) {
+  double t0 = 0.0, t1 = 0.0;
+  for (unsigned int b = threadIdx.x; b < nctas; b += SS_THREADS) {
+    t0 += ((const volatile double*)part[b])[0];
+    t1 += ((const volatile double*)part[b])[1];
+  }
+  t0 = block_sum(t0, scratch);
+  t1 = block_sum(t1, scratch);
+  if (threadIdx.x == 0) { bc[0] = t0; bc[1] = t1; }
+  __syncthreads();
+}
+
+// Grid barrier for a cooperative (co-resident) launch.  Bounded spin: on timeout the
+// abort flag makes every CTA leave instead of hanging the device.
+__device__ __forceinline__ bool grid_barrier(SSWorkspace* ws, unsigned int& target, unsigned int nctas) {
+  __shared__ int ok_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nctas;
+    __threadfence();
+    atomicAdd(&ws->barrier, 1u);
+    unsigned long long spins = 0;
+    int ok = 1;
+    while (*((volatile unsigned int*)&ws->barrier) < target) {
+      if (*((volatile unsigned int*)&ws->abort_flag) != 0u || ++spins > SS_SPIN_LIMIT) {
+        atomicExch(&ws->abort_flag, 1u);
+        ok = 0;
+        break;
+      }
+    }
+    __threadfence();
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, SSWorkspace* ws) {
+  __shared__ double scratch[32];
+  __shared__ double bc[2];
+  const QParamD q = make_qparam_d(lo, hi, nlvl);
+  const unsigned int nctas = gridDim.x;
+  const long long numel = vv.rows * vv.cols;
+  const int max_pass = nlvl * 100;
+  unsigned int target = 0;
+  int parity = 0;
+
+  // pass "-1": a0 = mean|v|
+  double s0, s1;
+  pass_sums<0>(vv, 0.0, q, blockIdx.x, nctas, s0, s1);
+  s0 = block_sum(s0, scratch);
+  if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = 0.0; }
+  if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+  fold_partials(ws->partial[parity], nctas, scratch, bc);
+  double a = bc[0] / (double)numel;
+  double a_prev = -999.0;
+  int passes = 0;
+  double last0 = 0.0, last1 = 0.0;
+
+  while (fabs(a - a_prev) > 1e-5 && passes < max_pass) {
+    parity ^= 1;
+    pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
+    s0 = block_sum(s0, scratch);
+    s1 = block_sum(s1, scratch);
+    if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = s1; }
+    if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+    fold_partials(ws->partial[parity], nctas, scratch, bc);
+    last0 = bc[0];
+    last1 = bc[1];
+    __syncthreads();
+    a_prev = a;
+    a = last0 / last1;
+    ++passes;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->a = a;
+    state->a_prev = a_prev;
+    state->s_bv = last0;
+    state->s_bb = last1;
+    state->passes = passes;
+    state->converged = fabs(a - a_prev) <= 1e-5 ? 1 : 0;
+    state->failed = (passes == max_pass) ? 1 : 0;
+  }
+}
+
+// ---- multi-GPU building blocks (one pass, no grid barrier) -----------------------
+struct SPWorkspace {
+  unsigned int done;
+  unsigned int pad[3];
+  double partial[SS_MAX_CTAS][2];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(SS_THREADS)
+scale_partial_kernel(VecView vv, int nlvl, float lo, float hi, const effq_scale_state* state,
+                     double* sums, SPWorkspace* ws) {
+  __shared__ double scratch[32];
+  __shared__ bool last;
+  const QParamD q = make_qparam_d(lo, hi, nlvl);
+  double s0, s1;
+  // a converged search keeps its scale: later passes are no-ops that re-emit the sums
+  const double a = MODE == 1 ? state->a : 0.0;
+  pass_sums<MODE>(vv, a, q, blockIdx.x, gridDim.x, s0, s1);
+  s0 = block_sum(s0, scratch);
+  s1 = block_sum(s1, scratch);
+  if (threadIdx.x == 0) {
+    ws->partial[blockIdx.x][0] = s0;
+    ws->partial[blockIdx.x][1] = MODE == 0 ? 0.0 : s1;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ws->done, 1u);
+    last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {                       // block-uniform
+    __shared__ double bc[2];
+    __threadfence();
+    fold_partials(ws->partial, gridDim.x, scratch, bc);
+    if (threadIdx.x == 0) {
+      sums[0] = bc[0];
+      sums[1] = MODE == 0 ? (double)(vv.rows * vv.cols) : bc[1];
+      ws->done = 0;
+    }
+  }
+}
+
+__global__ void scale_step_kernel(effq_scale_state* st, const double* sums, int mode, int nlvl) {
+  if (mode == 0) {
+    st->a = sums[0] / sums[1];
+    st->a_prev = -999.0;
+    st->passes = 0;
+    st->converged = 0;
+    st->failed = 0;
+    return;
+  }
+  if (st->converged || st->failed) return;
+  const double a_new = sums[0] / sums[1];
+  st->a_prev = st->a;
+  st->a = a_new;
+  st->s_bv = sums[0];
+  st->s_bb = sums[1];
+  st->passes += 1;
+  if (fabs(st->a - st->a_prev) <= 1e-5) st->converged = 1;
+  else if (st->passes >= nlvl * 100) st->failed = 1;
+}
+
+static int pick_ctas(long long numel, int per_sm) {
+  long long want = (numel + (long long)SS_THREADS * 16 - 1) / ((long long)SS_THREADS * 16);
+  long long cap = (long long)sm_count() * per_sm;
+  if (cap > SS_MAX_CTAS) cap = SS_MAX_CTAS;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace effq
+
+extern "C" int64_t effq_scale_search_workspace(void) {
+  size_t a = sizeof(effq::SSWorkspace), b = sizeof(effq::SPWorkspace);
+  return (int64_t)(a > b ? a : b);
+}
+
+extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
+                                 int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
+                                 void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(v1 && state && workspace, "null pointer");
+  EFFQ_CHECK_ARG(rows > 0 && cols > 0 && ld1 >= cols && (!v2 || ld2 >= cols), "bad shape");
+  EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
+  cudaStream_t s = (cudaStream_t)stream;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int occ = 0;
+    EFFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scale_search_kernel, SS_THREADS, 0));
+    EFFQ_CHECK_ARG(occ >= 1, "scale_search kernel does not fit on an SM");
+    per_sm = occ > 2 ? 2 : occ;
+  }
+  const int ctas = pick_ctas(rows * cols, per_sm);
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 16, s));     // barrier counter + abort flag
+  VecView vv{v1, v2, ld1, ld2, rows, cols};
+  SSWorkspace* ws = (SSWorkspace*)workspace;
+  void* args[] = {&vv, &nlvl, &lo, &hi, &state, &ws};
+  EFFQ_CUDA(cudaLaunchCooperativeKernel((void*)scale_search_kernel, dim3(ctas), dim3(SS_THREADS), args, 0, s));
+  count_launch();
+  return 0;
+}
+
+extern "C" int effq_scale_partial(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
+                                  int64_t cols, int32_t nlvl, float lo, float hi,
+                                  const effq_scale_state* state, int32_t mode, double* sums,
+                                  void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(v1 && state && workspace && sums, "null pointer");
+  EFFQ_CHECK_ARG(rows > 0 && cols > 0 && ld1 >= cols && (!v2 || ld2 >= cols), "bad shape");
+  EFFQ_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ctas = pick_ctas(rows * cols, 2);
+  VecView vv{v1, v2, ld1, ld2, rows, cols};
+  SPWorkspace* ws = (SPWorkspace*)workspace;
+  // ws->done must be zero on entry: zeroed by the caller once at allocation, and
+  // re-zeroed by the last CTA of every launch.
+  if (mode == 0) scale_partial_kernel<0><<<ctas, SS_THREADS, 0, s>>>(vv, nlvl, lo, hi, state, sums, ws);
+  else           scale_partial_kernel<1><<<ctas, SS_THREADS, 0, s>>>(vv, nlvl, lo, hi, state, sums, ws);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_scale_step(effq_scale_state* state, const double* sums, int32_t mode, int32_t nlvl,
+                               void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(state && sums, "null pointer");
+  scale_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, sums, mode, nlvl);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}

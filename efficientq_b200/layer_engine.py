@@ -1,0 +1,247 @@
+"""Per-layer EfficientQ calibration on the GPU (the hot loop).
+
+Mirrors reference ``EfficientQConv.ptq`` (src/models/EfficientQConv.py:33-166) and
+``QuadraSolver`` (src/models/solver.py:201-345) step for step, with every tensor
+operation replaced by a launch of the C-ABI kernels (``ops``).  What stays in
+PyTorch is plumbing only: memory, the dense SPD factorisation of the K'xK' normal
+matrix (once per distinct rho, 5 per layer -- the reference re-factorises all 200
+times, solver.py:331) and the small GEMM  w* = B A^-1  per iteration (library
+linear algebra, DESIGN.md section "solve").
+
+The 200-iteration loop enqueues without a single host synchronisation: scales,
+losses and the best-iterate decision live in device structs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .dist import DistCtx
+
+
+@dataclass
+class LayerReport:
+    name: str = ""
+    final_loss: float = 0.0          # attention-weighted, as logged in layer_loss.txt
+    best_loss: float = 0.0           # best per-iteration (unweighted) MSE
+    best_iter: int = 0
+    alpha_w: float = 0.0
+    alpha_act: Optional[float] = None
+    act_passes: int = 0
+    rho_scale: float = 1.0
+    used_tc: bool = False
+    history: Optional[List[float]] = None
+    factorizations: int = 0
+
+
+def select_att(mask_pyramid: Optional[Sequence[torch.Tensor]], out_spatial) -> Optional[torch.Tensor]:
+    """EfficientQConv.py:53-59."""
+    if not mask_pyramid:
+        return None
+    for m in mask_pyramid:
+        if tuple(m.shape[1:]) == tuple(out_spatial):
+            return m
+    return None
+
+
+def _moments(t: torch.Tensor, dist: DistCtx):
+    """(numel, unbiased std) over all ranks' shards (torch.std is unbiased, EfficientQConv.py:45-48)."""
+    td = t.double()
+    s = torch.stack([td.sum(), (td * td).sum(), torch.tensor(float(t.numel()), dtype=torch.float64, device=t.device)])
+    s = dist.all_reduce_sum(s)
+    tot, sq, n = [float(v) for v in s.tolist()]
+    var = max(sq - tot * tot / n, 0.0) / max(n - 1.0, 1.0)
+    return n, var ** 0.5
+
+
+class LayerCalibrator:
+    """Holds the reusable device scratch of one process and calibrates layers one at a time."""
+
+    def __init__(self, device, dist: Optional[DistCtx] = None, n_iter: int = 200, rho0: float = 10.0,
+                 rho_max: float = 1000.0, eta0: float = 1.0, rho_period: int = 50, keep_history: bool = False,
+                 force_generic: bool = False):
+        self.device = device
+        self.dist = dist or DistCtx()
+        self.n_iter, self.rho0, self.rho_max, self.eta0, self.rho_period = n_iter, rho0, rho_max, eta0, rho_period
+        self.keep_history = keep_history
+        self.force_generic = force_generic
+        self.xstate = ops.ScaleState(device)
+        self.wstate = ops.ScaleState(device)
+        self.st = ops.AdmmState(device)
+        self.sse = torch.zeros(1, dtype=torch.float64, device=device)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=device)
+        self.sp_ws = ops.workspace(ops.capi.load().effq_scale_search_workspace(), device)
+        self.gram_ws = None
+        self.tc_ws = ops.workspace(16 + 8 * 1024, device)
+
+    # -- activation scale search ------------------------------------------------------------
+    def _act_scale(self, x: torch.Tensor, nlvl: int) -> None:
+        if self.dist.world == 1:
+            ops.scale_search(x, nlvl, 0.0, 1.0, self.xstate)
+            return
+        # sharded volumes: one pass of local sums, all-reduce 2 doubles, device-side update
+        ops.scale_partial(x, nlvl, 0.0, 1.0, self.xstate, 0, self.sums, self.sp_ws)
+        self.dist.all_reduce_sum(self.sums)
+        ops.scale_step(self.xstate, self.sums, 0, nlvl)
+        done = False
+        while not done:
+            for _ in range(16):
+                ops.scale_partial(x, nlvl, 0.0, 1.0, self.xstate, 1, self.sums, self.sp_ws)
+                self.dist.all_reduce_sum(self.sums)
+                ops.scale_step(self.xstate, self.sums, 1, nlvl)
+            s = self.xstate.read()
+            done = bool(s["converged"] or s["failed"])
+
+    # -- the layer -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out_fp: torch.Tensor,
+            stride, padding, qlvl_w: int, qlvl_act: int, q_act: bool, mask_pyramid=None, name: str = ""):
+        """Returns (weight*, bias*, alpha_w (0-dim device fp32), alpha_act or None, layer output, report)."""
+        dev = self.device
+        dist = self.dist
+        x = x.detach().contiguous().float()
+        out_fp = out_fp.detach().contiguous().float()
+        w0 = weight.detach().contiguous().float()
+        c2, c1 = w0.shape[:2]
+        ksize = tuple(w0.shape[2:])
+        taps = ksize[0] * ksize[1] * ksize[2]
+        k = c1 * taps
+        has_bias = bias is not None
+        kp = k + (1 if has_bias else 0)
+        rep = LayerReport(name=name)
+
+        att = select_att(mask_pyramid, out_fp.shape[2:])
+        if att is not None:
+            att = att.to(dev).contiguous().float()
+
+        # rho_scale (EfficientQConv.py:44-49, :60-61) -- global statistics over all shards
+        y_n, y_std = _moments(out_fp, dist)
+        w_std = float(w0.std().item())
+        rs = max(y_n * y_std / (w0.numel() * w_std), 1.0)
+        if att is not None:
+            a_s = dist.all_reduce_sum(torch.stack([att.double().sum(),
+                                                   torch.tensor(float(att.numel()), dtype=torch.float64, device=dev)]))
+            rs *= float(a_s[0] / a_s[1])
+        rep.rho_scale = rs
+        rho, rho_m, eta = self.rho0 * rs, self.rho_max * rs, self.eta0 * rs
+
+        # activations (EfficientQConv.py:64-72)
+        use_tc = (not self.force_generic) and q_act and qlvl_act <= 256 and qlvl_w <= 256 and \
+            ops.conv3d_tc_supported(x.shape, c2, ksize, stride, padding)
+        rep.used_tc = use_tc
+        alpha_act = None
+        xcodes = None
+        if q_act:
+            self._act_scale(x, qlvl_act)
+            alpha_act = self.xstate.a_f32()
+            qx = ops.fakequant_state(x, self.xstate, qlvl_act, 0.0, 1.0)
+            if use_tc:
+                xcodes = ops.quantize_act_ndhwc(x, qlvl_act, state=self.xstate)
+        else:
+            qx = x
+
+        # normal-equation statistics (solver.py:253-272), summed over shards
+        a0, b0 = ops.gram(qx, out_fp, att, ksize, stride, padding, has_bias=has_bias, ws=self.gram_ws)
+        if dist.world > 1:
+            dist.all_reduce_sum(a0)
+            dist.all_reduce_sum(b0)
+        w0p = torch.cat([w0.reshape(c2, k), bias.detach().float().reshape(c2, 1)], 1).contiguous() if has_bias \
+            else w0.reshape(c2, k).contiguous()
+
+        g = w0.reshape(c2, k).clone()
+        dual = torch.zeros_like(g)
+        bstar = bias.detach().float().clone() if has_bias else None
+        best_g = torch.empty_like(g)
+        best_b = torch.empty_like(bstar) if has_bias else None
+        bmat = torch.empty((c2, kp), dtype=torch.float32, device=dev)
+        amat = torch.empty((kp, kp), dtype=torch.float32, device=dev)
+        hist = torch.zeros(self.n_iter, dtype=torch.float32, device=dev)
+        wcodes = best_wcodes = None
+        if use_tc:
+            wcodes = torch.empty(taps * (c1 // 8) * c2 * 8, dtype=torch.bfloat16, device=dev)
+            best_wcodes = torch.empty_like(wcodes)
+        self.st.reset()
+        numel_total = y_n                      # mse over every rank's outputs
+        ainv = None
+        rho_built = None
+        g4 = g.view(c2, c1, *ksize)
+
+        for it in range(self.n_iter):
+            if rho_built != rho:
+                # A takes 5 distinct values per layer; factor once per value (SPD: A0 is PSD, eta > 0)
+                ops.admm_lhs(a0, rho, eta, has_bias, amat)
+                chol, info = torch.linalg.cholesky_ex(amat)
+                if int(info.item()) == 0:
+                    ainv = torch.cholesky_inverse(chol)
+                else:                               # not numerically SPD: LU, as the reference (solver.py:331)
+                    ainv = torch.linalg.inv(amat)
+                rho_built = rho
+                rep.factorizations += 1
+            # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
+            ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat)
+            sol = bmat @ ainv
+            # projection + dual update (EfficientQConv.py:107-111)
+            wview = sol[:, :k] if has_bias else sol
+            ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
+            div = 1.0
+            new_rho = rho
+            if it % self.rho_period == 0:          # EfficientQConv.py:129-137
+                if rho * 2 <= rho_m:
+                    new_rho, div = rho * 2, 2.0
+                else:
+                    new_rho, div = rho_m, rho_m / rho
+            ops.admm_project(sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps,
+                             has_bias, div, g, bstar, wcodes, self.st)
+            # score the iterate (EfficientQConv.py:118-122)
+            if use_tc:
+                ops.conv3d_tc(xcodes, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
+                              target=out_fp, ws=self.tc_ws, sse=self.sse)
+            else:
+                ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
+                               ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
+            if dist.world > 1:
+                dist.all_reduce_sum(self.sse)
+            ops.admm_track(self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes)
+            rho = new_rho
+
+        # final forward with the best iterate: layer output + attention-weighted loss (:161-166)
+        if use_tc:
+            out_q, _ = ops.conv3d_tc(xcodes, best_wcodes, best_b, self.st.best_conv_scale_ptr(), c2, ksize,
+                                     want_out=True, target=out_fp, att=att, ws=self.tc_ws, sse=self.sse)
+        else:
+            out_q, _ = ops.conv3d_f32(qx, best_g.view(c2, c1, *ksize), best_b, stride, padding, want_out=True,
+                                      target=out_fp, att=att, ws=self._conv_ws(qx, c2, ksize, stride, padding),
+                                      sse=self.sse)
+        if dist.world > 1:
+            dist.all_reduce_sum(self.sse)
+        alpha_w = self.st.a_w_tensor().clone()     # LAST iterate's scale (reference quirk, :158)
+        s = self.st.read()                          # the layer's one result read-back
+        final_sse = float(self.sse.item())
+        if final_sse != final_sse:
+            raise ops.EffqError(f"{name}: tcgen05 conv aborted (barrier timeout)")
+        rep.final_loss = final_sse / numel_total
+        rep.best_loss, rep.best_iter, rep.alpha_w = s["best_loss"], s["best_iter"], s["a_w"]
+        if q_act:
+            xs = self.xstate.read()
+            rep.alpha_act, rep.act_passes = float(xs["a"]), xs["passes"]
+            if xs["failed"]:
+                raise RuntimeWarning(f"Exceed maximum iteration ({qlvl_act * 100}) for alpha optimization in var_init_iter")
+        ws_ = self.wstate.read()
+        if ws_["failed"]:
+            raise RuntimeWarning(f"Exceed maximum iteration ({qlvl_w * 100}) for alpha optimization in var_init_iter")
+        if self.keep_history:
+            rep.history = hist.cpu().tolist()
+        return best_g.view(c2, c1, *ksize), best_b, alpha_w, alpha_act, out_q, rep
+
+    _cws = None
+
+    def _conv_ws(self, x, c2, ksize, stride, padding):
+        import ctypes as C
+        g = ops.Geom.make(x.shape, c2, ksize, stride, padding)
+        need = ops.capi.load().effq_conv3d_f32_workspace(C.byref(g))
+        if self._cws is None or self._cws.numel() < need:
+            self._cws = ops.workspace(need, self.device)
+        return self._cws

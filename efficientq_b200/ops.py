@@ -1,0 +1,292 @@
+"""Tensor-level wrappers over the C-ABI (one Python function per entry point).
+
+Each wrapper checks dtype/contiguity/device, passes raw device pointers and the
+current CUDA stream to ``libeffq_b200.so`` and raises ``EffqError`` on failure.
+Nothing here computes on the host or through PyTorch ops: if the library is
+missing the first call raises (no fallback by design).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from typing import Optional, Tuple
+
+import torch
+
+from . import capi
+from .capi import Geom, EffqError, ptr, stream, check
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise EffqError(f"{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------
+# device-resident state structs
+# ---------------------------------------------------------------------------
+class ScaleState:
+    """Device copy of ``effq_scale_state``; ``read()`` is the only host sync."""
+    FMT = "<ddddiiii"
+
+    def __init__(self, device):
+        self.buf = torch.zeros(capi.SCALE_STATE_BYTES, dtype=torch.uint8, device=device)
+
+    @property
+    def p(self):
+        return ptr(self.buf)
+
+    def read(self) -> dict:
+        a, a_prev, s_bv, s_bb, passes, conv, failed, _ = struct.unpack(self.FMT, self.buf.cpu().numpy().tobytes())
+        return dict(a=a, a_prev=a_prev, s_bv=s_bv, s_bb=s_bb, passes=passes, converged=conv, failed=failed)
+
+    def a_f32(self) -> torch.Tensor:
+        """fp32(a) as a 0-dim device tensor, without a host sync."""
+        return self.buf[:8].view(torch.float64)[0].to(torch.float32)
+
+    def set_a(self, a: float) -> None:
+        self.buf[:8].view(torch.float64).fill_(a)
+
+
+class AdmmState:
+    """Device copy of ``effq_admm_state``."""
+    FMT = "<dffiiffif"
+
+    def __init__(self, device):
+        self.buf = torch.zeros(capi.ADMM_STATE_BYTES, dtype=torch.uint8, device=device)
+
+    @property
+    def p(self):
+        return ptr(self.buf)
+
+    def reset(self):
+        self.buf.zero_()
+
+    def read(self) -> dict:
+        sse, best, last, best_it, it, cs, aw, take, bcs = struct.unpack(self.FMT, self.buf.cpu().numpy().tobytes())
+        return dict(sse=sse, best_loss=best, last_loss=last, best_iter=best_it, iter=it, conv_scale=cs, a_w=aw,
+                    best_conv_scale=bcs)
+
+    def conv_scale_ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + 24)
+
+    def best_conv_scale_ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + 36)
+
+    def a_w_tensor(self) -> torch.Tensor:
+        return self.buf[28:32].view(torch.float32)[0]
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Zero-initialised scratch (the kernels' completion counters start at 0)."""
+    return torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------
+# (a) fake-quant
+# ---------------------------------------------------------------------------
+def fakequant(x: torch.Tensor, alpha: torch.Tensor, nlvl: int, lo: float, hi: float,
+              want_values: bool = True, want_codes: bool = False):
+    """discretize(x/alpha, nlvl, lo, hi)*alpha (+ uint8 codes) -- PTQConv.py:110-116."""
+    x = _f32c(x, "x")
+    alpha = _f32c(alpha.reshape(1), "alpha")
+    y = torch.empty_like(x) if want_values else None
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
+    check(capi.load().effq_fakequant_f32(ptr(x), x.numel(), ptr(alpha), float(lo), float(hi), int(nlvl),
+                                         ptr(y), ptr(codes), stream()), "effq_fakequant_f32")
+    return y, codes
+
+
+def fakequant_state(x: torch.Tensor, state: ScaleState, nlvl: int, lo: float, hi: float) -> torch.Tensor:
+    """fp32(a)*fp32(level) with the scale-search state (EfficientQConv.py:68-70)."""
+    x = _f32c(x, "x")
+    y = torch.empty_like(x)
+    check(capi.load().effq_fakequant_state(ptr(x), x.numel(), state.p, float(lo), float(hi), int(nlvl), ptr(y),
+                                           stream()), "effq_fakequant_state")
+    return y
+
+
+def quantize_act_ndhwc(x: torch.Tensor, nlvl: int, state: Optional[ScaleState] = None,
+                       alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCDHW fp32 -> (N,D,H,W,C) bf16 integer codes, the tcgen05 conv operand."""
+    x = _f32c(x, "x")
+    n, c, d, h, w = x.shape
+    out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
+    use64 = 1 if state is not None else 0
+    a = _f32c(alpha.reshape(1), "alpha") if alpha is not None else None
+    check(capi.load().effq_quantize_act_ndhwc(ptr(x), n, c, d * h * w, int(nlvl), state.p if state else None,
+                                              ptr(a), use64, ptr(out), stream()), "effq_quantize_act_ndhwc")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# (a3) scale search
+# ---------------------------------------------------------------------------
+_ss_ws = {}
+
+
+def _scale_ws(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    if key not in _ss_ws:
+        _ss_ws[key] = workspace(capi.load().effq_scale_search_workspace(), device)
+    return _ss_ws[key]
+
+
+def _pair_view(v1: torch.Tensor, v2: Optional[torch.Tensor]):
+    """(rows, cols, ld1, ld2) for v = v1 (+ v2).  v1 may be a row-strided 2-D view (w* with its
+    bias column); v2, when given, is contiguous with the same number of elements."""
+    for t in (v1, v2):
+        if t is not None and (t.dtype != torch.float32 or not t.is_cuda):
+            raise EffqError("scale search: expected CUDA float32 tensors")
+    if v2 is not None and (v2.numel() != v1.numel() or not v2.is_contiguous()):
+        raise EffqError("scale search: v2 must be contiguous and match v1 in size")
+    if v1.is_contiguous():
+        return 1, v1.numel(), v1.numel(), v1.numel()
+    if v1.dim() == 2 and v1.stride(1) == 1:
+        return v1.shape[0], v1.shape[1], v1.stride(0), v1.shape[1]
+    raise EffqError("scale search needs a contiguous tensor or a row-strided 2-D view")
+
+
+def scale_search(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: ScaleState,
+                 v2: Optional[torch.Tensor] = None) -> ScaleState:
+    """project_by_iter on the device (one cooperative launch, no host sync)."""
+    rows, cols, ld1, ld2 = _pair_view(v1, v2)
+    check(capi.load().effq_scale_search(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
+                                        state.p, ptr(_scale_ws(v1.device)), stream()), "effq_scale_search")
+    return state
+
+
+def scale_partial(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: ScaleState, mode: int,
+                  sums: torch.Tensor, ws: torch.Tensor, v2: Optional[torch.Tensor] = None) -> None:
+    rows, cols, ld1, ld2 = _pair_view(v1, v2)
+    check(capi.load().effq_scale_partial(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
+                                         state.p, int(mode), ptr(sums), ptr(ws), stream()), "effq_scale_partial")
+
+
+def scale_step(state: ScaleState, sums: torch.Tensor, mode: int, nlvl: int) -> None:
+    check(capi.load().effq_scale_step(state.p, ptr(sums), int(mode), int(nlvl), stream()), "effq_scale_step")
+
+
+# ---------------------------------------------------------------------------
+# (a10) conv forward + squared error
+# ---------------------------------------------------------------------------
+def conv3d_f32(x, w, bias, stride, padding, want_out=True, target=None, att=None, ws=None, sse=None):
+    """Generic fp32 conv (+ fused sum of att*(out-target)^2).  Returns (out, sse[1] f64)."""
+    x = _f32c(x, "x")
+    w = _f32c(w, "w")
+    g = Geom.make(x.shape, w.shape[0], w.shape[2:], stride, padding)
+    od, oh, ow = g.out_spatial()
+    out = torch.empty((g.n, g.c2, od, oh, ow), dtype=torch.float32, device=x.device) if want_out else None
+    lib = capi.load()
+    if target is not None:
+        target = _f32c(target, "target")
+        if ws is None:
+            ws = workspace(lib.effq_conv3d_f32_workspace(C.byref(g)), x.device)
+        if sse is None:
+            sse = torch.zeros(1, dtype=torch.float64, device=x.device)
+    if att is not None:
+        att = _f32c(att, "att")
+    b = _f32c(bias, "bias") if bias is not None else None
+    check(lib.effq_conv3d_f32(ptr(x), ptr(w), ptr(b), C.byref(g), ptr(out), ptr(target), ptr(att), ptr(sse),
+                              ptr(ws), stream()), "effq_conv3d_f32")
+    return out, sse
+
+
+def conv3d_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
+    g = Geom.make(x_shape, c2, ksize, stride, padding)
+    return bool(capi.load().effq_conv3d_tc_supported(C.byref(g)))
+
+
+def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, c2: int, ksize, want_out=True,
+              target=None, att=None, ws=None, sse=None):
+    """tcgen05 conv on codes.  xcodes (N,D,H,W,C1) bf16; wcodes [tap][C1/8][C2][8] bf16."""
+    if xcodes.dtype != torch.bfloat16 or not xcodes.is_contiguous() or not xcodes.is_cuda:
+        raise EffqError("conv3d_tc: xcodes must be contiguous CUDA bf16 NDHWC")
+    n, d, h, w, c1 = xcodes.shape
+    k = capi._triple(ksize)
+    pad = tuple((t - 1) // 2 for t in k)
+    g = Geom.make((n, c1, d, h, w), c2, k, 1, pad)
+    lib = capi.load()
+    out = torch.empty((n, c2, d, h, w), dtype=torch.float32, device=xcodes.device) if want_out else None
+    if ws is None:
+        ws = workspace(lib.effq_conv3d_tc_workspace(C.byref(g)), xcodes.device)
+    if target is not None:
+        target = _f32c(target, "target")
+        if sse is None:
+            sse = torch.zeros(1, dtype=torch.float64, device=xcodes.device)
+    if att is not None:
+        att = _f32c(att, "att")
+    b = _f32c(bias, "bias") if bias is not None else None
+    cs = conv_scale_ptr if not isinstance(conv_scale_ptr, torch.Tensor) else ptr(conv_scale_ptr)
+    check(lib.effq_conv3d_tc(ptr(xcodes), ptr(wcodes), ptr(b), cs, C.byref(g), ptr(out), ptr(target), ptr(att),
+                             ptr(sse), ptr(ws), stream()), "effq_conv3d_tc")
+    return out, sse
+
+
+def pack_weight_codes(wcodes_int: torch.Tensor) -> torch.Tensor:
+    """[C2][C1][kd][kh][kw] integer codes (already 2c-(L-1)) -> [tap][C1/8][C2][8] bf16.
+    Test/bring-up helper; the production path gets this layout from effq_admm_project."""
+    c2, c1 = wcodes_int.shape[:2]
+    taps = wcodes_int[0, 0].numel()
+    t = wcodes_int.reshape(c2, c1 // 8, 8, taps).permute(3, 1, 0, 2).contiguous()
+    return t.to(torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------
+# (a7+a8) normal-equation statistics
+# ---------------------------------------------------------------------------
+def gram(x, y, att, ksize, stride, padding, has_bias=True, x_scale=None, ws=None):
+    """A0 (K'xK'), B0 (C2xK') -- solver.py:282-314 without materialising im2col."""
+    x = _f32c(x, "x")
+    y = _f32c(y, "y")
+    g = Geom.make(x.shape, y.shape[1], ksize, stride, padding)
+    k = g.c1 * g.taps
+    kp = k + (1 if has_bias else 0)
+    lib = capi.load()
+    need = lib.effq_gram_workspace(C.byref(g), int(has_bias))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+    a0 = torch.empty((kp, kp), dtype=torch.float32, device=x.device)
+    b0 = torch.empty((g.c2, kp), dtype=torch.float32, device=x.device)
+    if att is not None:
+        att = _f32c(att, "att")
+    xs = _f32c(x_scale.reshape(1), "x_scale") if x_scale is not None else None
+    check(lib.effq_gram_f32(ptr(x), ptr(xs), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0), ptr(b0),
+                            ptr(ws), stream()), "effq_gram_f32")
+    return a0, b0
+
+
+# ---------------------------------------------------------------------------
+# (a9, a11) ADMM update
+# ---------------------------------------------------------------------------
+def admm_rhs(b0, w0p, g, dual, rho: float, eta: float, out):
+    c2, kp = b0.shape
+    k = g.numel() // c2
+    check(capi.load().effq_admm_rhs(ptr(b0), ptr(w0p), ptr(g), ptr(dual), float(rho), float(eta), c2, k,
+                                    int(kp != k), ptr(out), stream()), "effq_admm_rhs")
+    return out
+
+
+def admm_lhs(a0, rho: float, eta: float, has_bias: bool, out):
+    kp = a0.shape[0]
+    check(capi.load().effq_admm_lhs(ptr(a0), float(rho), float(eta), kp, int(has_bias), ptr(out), stream()),
+          "effq_admm_lhs")
+    return out
+
+
+def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], nlvl_w: int, nlvl_a: int,
+                 c2: int, c1: int, taps: int, has_bias: bool, dual_div: float, g_out, bstar_out, wcodes_out,
+                 st: AdmmState):
+    ldw = wstar.stride(0)
+    check(capi.load().effq_admm_project(ptr(wstar), ldw, ptr(dual), wstate.p, xstate.p if xstate else None,
+                                        int(nlvl_w), int(nlvl_a), c2, c1, taps, int(has_bias), float(dual_div),
+                                        ptr(g_out), ptr(bstar_out), ptr(wcodes_out), st.p, stream()),
+          "effq_admm_project")
+
+
+def admm_track(st: AdmmState, sse, numel: float, g, bstar, best_g, best_b, history, aux_src=None, aux_dst=None):
+    nb = aux_src.numel() * aux_src.element_size() if aux_src is not None else 0
+    check(capi.load().effq_admm_track(st.p, ptr(sse), float(numel), ptr(g), ptr(bstar), g.numel(),
+                                      g.shape[0], ptr(best_g), ptr(best_b), ptr(history), ptr(aux_src),
+                                      ptr(aux_dst), nb, stream()), "effq_admm_track")

@@ -1,0 +1,179 @@
+"""Per-layer quantizer modules: the drop-in boundary of the reference.
+
+``PTQConv`` mirrors reference src/models/PTQConv.py:11-175 (same constructor, the
+``alpha_act`` / ``alpha_w`` 0-dim parameters and state-dict keys, the four-state
+mode machine, ``store_int_weight`` / ``restore_fp_weight``).  ``EfficientQConv``
+mirrors src/models/EfficientQConv.py:12-166; its ``ptq(x)`` runs the layer's ADMM
+calibration on the GPU through the C-ABI kernels (``layer_engine``).  Keep
+``QConv`` in the class names: the reference duck-types on it
+(src/models/model_blk.py:26-34).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .layer_engine import LayerCalibrator
+
+__all__ = ["PTQConv", "EfficientQConv"]
+
+
+class PTQConv(nn.Conv3d):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, q_weight=True, qlvl=8, q_act=True, qlvl_act=8, **kwQ):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+        if self.dilation != (1, 1, 1) or self.groups != 1:
+            raise NotImplementedError("effq_b200 quantizer layers support dilation 1, groups 1 "
+                                      "(all the reference's configs use)")
+        self.conv_param = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+        self.q_act, self.q_weight = q_act, q_weight
+        self.qlvl_w, self.qlvl_act = qlvl, qlvl_act
+        self.kwQ = kwQ
+        self.alpha_act = nn.Parameter(torch.tensor(1.))
+        self.alpha_w = nn.Parameter(torch.tensor(1.))
+        self.act_in = self.output_fp = self.grad_in = self.grad_out = None
+        self.name = None
+        self.snap_dir = kwQ.get("snap_dir", None)
+        self.w_backup = self.b_backup = None
+        self._fp, self._quantizing, self._quantized, self._init_act = True, False, False, False
+        self._act_inited = False
+        self._wcodes_cache = None
+
+    # -- mode machine (PTQConv.py:44-72) ------------------------------------------------
+    def _mode(self, fp=False, quantizing=False, quantized=False, init_act=False):
+        self._fp, self._quantizing, self._quantized, self._init_act = fp, quantizing, quantized, init_act
+
+    def set_fp(self):
+        self._mode(fp=True)
+
+    def set_quantizing(self):
+        self._mode(quantizing=True)
+
+    def set_quantized(self):
+        self._mode(quantized=True)
+
+    def set_init_act(self):
+        self._mode(init_act=True)
+
+    def qweight_init_iter(self):
+        pass
+
+    def qparam_init(self):
+        pass
+
+    def perform_quantization(self):
+        pass
+
+    def backup_weight(self):
+        self.w_backup = self.weight.data.cpu().clone()
+        if self.bias is not None:
+            self.b_backup = self.bias.data.cpu().clone()
+
+    # -- fake-quant (PTQConv.py:110-116) through the fused CUDA kernel --------------------
+    def _quantize_w(self):
+        y, _ = ops.fakequant(self.weight.data, self.alpha_w.data, self.qlvl_w, -1.0, 1.0)
+        return y
+
+    def _quantize_act(self, x):
+        y, _ = ops.fakequant(x, self.alpha_act.data, self.qlvl_act, 0.0, 1.0)
+        return y
+
+    def init_alpha_act(self, x):
+        """PTQConv.py:74-78."""
+        st = ops.ScaleState(x.device)
+        ops.scale_search(x.contiguous(), self.qlvl_act, 0.0, 1.0, st)
+        self.alpha_act.data = st.a_f32()
+        self._act_inited = True
+        return ops.fakequant_state(x, st, self.qlvl_act, 0.0, 1.0)
+
+    def ptq(self, x):
+        raise NotImplementedError
+
+    # -- integer export (PTQConv.py:125-152) -------------------------------------------------
+    def store_int_weight(self):
+        a = self.alpha_w.data
+        b = self.weight.data / a
+        delta = 2 / (self.qlvl_w - 1)
+        w_int = torch.round((b + 1) / delta)
+        w_int = w_int.to(torch.uint8) if self.qlvl_w <= 256 else w_int.to(torch.int32)
+        self.weight.requires_grad = False
+        self.weight.data = w_int.data.cpu()
+
+    def restore_fp_weight(self):
+        delta = 2 / (self.qlvl_w - 1)
+        self.weight.data = self.alpha_w.data * (self.weight.data.float() * delta - 1)
+
+    # -- forward dispatch (PTQConv.py:154-174) ------------------------------------------------
+    def _conv(self, x):
+        out, _ = ops.conv3d_f32(x, self.weight.data, self.bias.data if self.bias is not None else None,
+                                self.stride, self.padding)
+        return out
+
+    def forward(self, x):
+        if self._fp:
+            return F.conv3d(x, self.weight, self.bias, self.stride, self.padding)
+        if self._quantizing:
+            return self.ptq(x)                      # returns conv3d(qact, weight*, bias*) of the calibrated layer
+        if self._quantized:
+            qact = self._quantize_act(x) if self.q_act else x
+            return self._conv(qact)
+        if self._init_act:
+            return self._conv(self.init_alpha_act(x))
+        raise RuntimeError(f"Unknown FP/Quant setting: FP={self._fp}, "
+                           f"Quantizing={self._quantizing}, Quantized={self._quantized}")
+
+
+class EfficientQConv(PTQConv):
+    """EfficientQ layer: ADMM with the closed-form proximal step, on the B200."""
+    _engines = {}
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, q_weight=True, qlvl=8, q_act=True, qlvl_act=8, **kwQ):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         q_weight, qlvl, q_act, qlvl_act, **kwQ)
+        self.lwq_iter, self.lwq_rho, self.lwq_rho_max, self.lwq_eta = 200, 10, 1000, 1   # EfficientQConv.py:23-26
+        self.lwq_fold_bn = True
+        self.lwq_verbose = kwQ.get("lwq_verbose", False)
+        self.mask_pyramid = None
+        self.layer_loss = None
+        self.report = None
+        self.dist = None                 # set by the orchestrator for sharded calibration
+        self.keep_history = False
+
+    def _engine(self, device) -> LayerCalibrator:
+        key = (device.index, self.lwq_iter, id(self.dist))
+        eng = EfficientQConv._engines.get(key)
+        if eng is None:
+            eng = LayerCalibrator(device, dist=self.dist, n_iter=self.lwq_iter, rho0=self.lwq_rho,
+                                  rho_max=self.lwq_rho_max, eta0=self.lwq_eta)
+            EfficientQConv._engines = {key: eng}      # one live engine (its scratch is large)
+        eng.keep_history = self.keep_history
+        return eng
+
+    def ptq(self, x):
+        """EfficientQConv.py:33-166.  Afterwards weight/bias hold the fake-quant values and
+        alpha_act/alpha_w the scales; returns the calibrated layer's output."""
+        if not x.is_cuda:
+            raise ops.EffqError("EfficientQConv.ptq needs CUDA tensors: there is no CPU path")
+        if self.output_fp is None:
+            raise RuntimeError("output_fp missing: run the FP pass with forward hooks first")
+        if self.lwq_verbose or True:
+            print(f"Calibrating {self.name}")
+        out_fp = self.output_fp.to(x.device)
+        w, b, a_w, a_act, out_q, rep = self._engine(x.device).run(
+            x, self.weight.data, self.bias.data if self.bias is not None else None, out_fp,
+            self.stride, self.padding, self.qlvl_w, self.qlvl_act, self.q_act, self.mask_pyramid,
+            name=self.name or "")
+        self.weight.data = w.clone()
+        if self.bias is not None:
+            self.bias.data = b.clone()
+        self.alpha_w.data = a_w.to(x.dtype)
+        if a_act is not None:
+            self.alpha_act.data = a_act.to(x.dtype)
+        self.report = rep
+        if self.layer_loss is not None:
+            self.layer_loss.append(f"{self.name:45s}:{rep.final_loss}")
+        self.output_fp = None                      # release the target
+        return out_q

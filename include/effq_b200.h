@@ -1,0 +1,177 @@
+/*
+ * effq_b200.h -- C-ABI of the B200-native EfficientQ PTQ calibration kernels.
+ *
+ * This is the drop-in boundary below the reference's per-layer quantizer module
+ * (reference: src/models/PTQConv.py:11-175, src/models/EfficientQConv.py:33-166).
+ * The reference has no FFI of its own (it is pure Python calling ATen library
+ * kernels); each entry point below replaces the ATen call sequence at the cited
+ * reference file:line, and INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add to bind it.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
+ *   - nothing is allocated inside the library: scratch comes in through explicit
+ *     workspace pointers whose size is returned by the matching *_workspace() query;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     no call synchronises the device unless documented;
+ *   - return value: 0 = ok, non-zero = CUDA or argument error, text via
+ *     effq_last_error() (thread-local);
+ *   - scalars that are produced on the device (scales, losses) stay on the device
+ *     so that the 200-iteration ADMM loop needs no host round trip.
+ *
+ * Layouts
+ *   activations fp32 : NCDHW (the reference's / PyTorch's native layout)
+ *   activation codes : N,D,H,W,C  bf16 (channels-last-3d), integer values 0..L-1
+ *   weights fp32     : [C2][C1][kd][kh][kw]  (== reference weight.reshape(C2,-1))
+ *   weight codes     : [tap][C1/8][C2][8] bf16, values 2c-(L-1) (odd integers)
+ *   normal equations : K' = C1*kd*kh*kw (+1 bias slot last), row order (c,kd,kh,kw)
+ *                      exactly as reference src/models/solver.py:104-108.
+ */
+#ifndef EFFQ_B200_H
+#define EFFQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFFQ_ABI_VERSION 1
+
+/* 3D convolution geometry (dilation 1, groups 1 -- all the reference's quantizer
+ * layers use, src/models/model_blk.py:98-181). */
+typedef struct effq_geom {
+  int32_t n, c1, d, h, w;   /* input  N x C1 x D x H x W        */
+  int32_t c2;               /* output channels                  */
+  int32_t kd, kh, kw;       /* kernel                           */
+  int32_t sd, sh, sw;       /* stride                           */
+  int32_t pd, ph, pw;       /* zero padding                     */
+} effq_geom;
+
+/* Device-resident state of one scale search (reference project_by_iter,
+ * src/models/layer_helper.py:40-70). */
+typedef struct effq_scale_state {
+  double  a;          /* current / final scale                               */
+  double  a_prev;     /* previous iterate                                    */
+  double  s_bv;       /* last  sum(b*v)                                      */
+  double  s_bb;       /* last  sum(b*b)                                      */
+  int32_t passes;     /* fixed-point passes executed (reference's counter c) */
+  int32_t converged;  /* 1 when |a-a_prev| <= 1e-5                           */
+  int32_t failed;     /* 1 when passes hit num_lvl*100 (reference raises)    */
+  int32_t pad_;
+} effq_scale_state;
+
+/* Device-resident bookkeeping of one layer's ADMM run
+ * (reference EfficientQConv.py:92-158). */
+typedef struct effq_admm_state {
+  double  sse;          /* last sum of squared errors written by the conv kernel */
+  float   best_loss;    /* smallest per-iteration MSE so far (fp32, as reference) */
+  float   last_loss;
+  int32_t best_iter;
+  int32_t iter;         /* iterations tracked so far                           */
+  float   conv_scale;   /* a_x*a_w/((La-1)(Lw-1)) for the code-domain conv      */
+  float   a_w;          /* fp32(a_w) of the latest projection                   */
+  int32_t take_;        /* scratch: 1 when the last tracked iterate became the best */
+  float   best_conv_scale; /* conv_scale of the best iterate                     */
+} effq_admm_state;
+
+/* ---- library ------------------------------------------------------------- */
+int         effq_abi_version(void);
+const char* effq_last_error(void);
+/* kernels launched by this library since the last reset (bench gpu_launches). */
+uint64_t    effq_launch_count(void);
+void        effq_reset_launch_count(void);
+
+/* ---- (a) fake-quant: reference layer_helper.py:25-37, PTQConv.py:110-116 ---- */
+/* y = discretize(x/alpha, nlvl, lo, hi)*alpha in fp32, op-for-op as the reference's
+ * CPU path (IEEE division, round-half-even).  y_out and/or code_out may be NULL.
+ * code_out[i] in [0, nlvl-1] (uint8, nlvl <= 256).  alpha is a device fp32 scalar. */
+int effq_fakequant_f32(const float* x, int64_t numel, const float* alpha, float lo, float hi,
+                       int32_t nlvl, float* y_out, uint8_t* code_out, void* stream);
+
+/* Qact = fp32(a) * fp32(level) with the fp64 discretize and scale of a finished scale
+ * search -- the `a_act * b_act` of EfficientQConv.py:68-70 (layer_helper.py:67). */
+int effq_fakequant_state(const float* x, int64_t numel, const effq_scale_state* state, float lo,
+                         float hi, int32_t nlvl, float* y_out, void* stream);
+
+/* Activation codes for the tensor-core conv: NCDHW fp32 -> NDHWC bf16 integer codes.
+ * use_f64 = 1 reproduces project_by_iter's final fp64 discretize with scale
+ * state->a (EfficientQConv.py:68-70); use_f64 = 0 reproduces _quantize_act with the
+ * fp32 scale alpha_f32 (PTQConv.py:114-116). */
+int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, int32_t nlvl,
+                            const effq_scale_state* state, const float* alpha_f32, int32_t use_f64,
+                            void* codes_bf16_out, void* stream);
+
+/* ---- (a3) scale search: reference layer_helper.py:40-70 --------------------- */
+/* v = v1 (+ v2 if non-NULL, added in fp32 first as the reference's `w_star + dual`),
+ * viewed as rows x cols with leading dimensions ld1 / ld2.  Runs the whole fp64 fixed
+ * point on the device in ONE cooperative launch; result in *state. */
+int64_t effq_scale_search_workspace(void);
+int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
+                      int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
+                      void* workspace, void* stream);
+/* Multi-GPU building blocks: one pass of local sums, then (after the caller has
+ * all-reduced sums[0..1]) the scale update.  mode 0: sums = {sum|v|, numel};
+ * mode 1: sums = {sum(b*v), sum(b*b)} for the scale in *state. */
+int effq_scale_partial(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
+                       int64_t cols, int32_t nlvl, float lo, float hi, const effq_scale_state* state,
+                       int32_t mode, double* sums, void* workspace, void* stream);
+int effq_scale_step(effq_scale_state* state, const double* sums, int32_t mode, int32_t nlvl,
+                    void* stream);
+
+/* ---- (a10) conv forward + reconstruction error: EfficientQConv.py:118-122 ---- */
+/* Generic fp32 direct conv (any geometry): out = conv3d(x, w) + bias.
+ * out may be NULL; if target != NULL the kernel also reduces
+ * sum(att * (out - target)^2) (att NULL -> 1) into *sse (double, deterministic). */
+int64_t effq_conv3d_f32_workspace(const effq_geom* g);
+int effq_conv3d_f32(const float* x, const float* w, const float* bias, const effq_geom* g,
+                    float* out, const float* target, const float* att, double* sse,
+                    void* workspace, void* stream);
+
+/* tcgen05 implicit-GEMM conv on integer codes (k = 3/stride 1/pad 1, or k = 1):
+ * out = conv_scale * sum(xcode*wcode) + bias, fp32 accumulation in TMEM,
+ * fused squared-error reduction against `target` in the epilogue.
+ * Requires c1 % 16 == 0, c2 % 16 == 0, c2 <= 256. */
+int effq_conv3d_tc_supported(const effq_geom* g);
+int64_t effq_conv3d_tc_workspace(const effq_geom* g);
+int effq_conv3d_tc(const void* xcodes_ndhwc_bf16, const void* wcodes_bf16, const float* bias,
+                   const float* conv_scale, const effq_geom* g, float* out, const float* target,
+                   const float* att, double* sse, void* workspace, void* stream);
+
+/* ---- (a7+a8) normal-equation statistics: solver.py:86-111, :282-314 ---------- */
+/* A0 = 2 X^ diag(att) X^T (K' x K'), B0 = 2 Y diag(att) X^T (C2 x K'), X^ the
+ * im2col matrix of `x` with a ones row appended when has_bias; never materialised.
+ * x_scale (device fp32 scalar or NULL = 1): x holds integer codes and the true
+ * activation is x_scale * x (scaling applied once to the finished sums). */
+int64_t effq_gram_workspace(const effq_geom* g, int32_t has_bias);
+int effq_gram_f32(const float* x, const float* x_scale, const float* y, const float* att,
+                  const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out,
+                  void* workspace, void* stream);
+
+/* ---- (a9,a11) ADMM parameter update: solver.py:316-325, EfficientQConv.py:99-144 */
+/* B = B0 + eta*W0' ;  B[:, :K] += rho*(G - dual)          (solver.py:317-320) */
+int effq_admm_rhs(const float* b0, const float* w0p, const float* g, const float* dual,
+                  float rho, float eta, int32_t c2, int32_t k, int32_t has_bias, float* b_out,
+                  void* stream);
+/* A = A0 + rho*quasi_eye + eta*eye                         (solver.py:317,323) */
+int effq_admm_lhs(const float* a0, float rho, float eta, int32_t kp, int32_t has_bias,
+                  float* a_out, void* stream);
+/* After the scale search on (w* + dual): G = a_w*b_w ; dual = (w* - G + dual)/dual_div;
+ * b* = last column of w*; emits fp32 G (reference layout) and, if wcodes_out != NULL,
+ * bf16 weight codes in the tensor-core layout; updates st->conv_scale / st->a_w. */
+int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
+                      const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
+                      int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
+                      float* bstar_out, void* wcodes_out, effq_admm_state* st, void* stream);
+/* loss = fp32(sse/numel); history[iter] = loss; if (iter==0 || loss < best) keep G, b*
+ * (and, when aux_bytes > 0, the 16B-aligned side buffer aux_src -> aux_dst, e.g. the
+ * tensor-core weight codes of the same iterate). */
+int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const float* g,
+                    const float* bstar, int64_t g_numel, int32_t c2, float* best_g, float* best_b,
+                    float* history, const void* aux_src, void* aux_dst, int64_t aux_bytes,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFQ_B200_H */

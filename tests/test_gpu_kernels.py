@@ -1,0 +1,312 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle and the golden fixtures
+generated from the reference.  Integer / level work is bit-exact; floating-point
+contractions carry their tolerance in the test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import effq_oracle as O  # noqa: E402
+
+LEVEL_CASES = [(4, 0, 1), (16, 0, 1), (256, 0, 1), (4, -1, 1), (16, -1, 1), (256, -1, 1)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from efficientq_b200 import ops as _ops
+    _ops.capi.load()
+    return _ops
+
+
+DEV = "cuda:0"
+
+
+# ---------------------------------------------------------------- fake-quant (a1, a2)
+@pytest.mark.parametrize("L,lo,hi", LEVEL_CASES)
+def test_fakequant_matches_reference_discretize(ops, golden, L, lo, hi):
+    g = golden("discretize.npz")
+    v = torch.from_numpy(g[f"L{L}_lo{lo}_f32_in"]).to(DEV)
+    want = g[f"L{L}_lo{lo}_f32_out"]
+    y, codes = ops.fakequant(v, torch.ones(1, device=DEV), L, lo, hi, want_values=True, want_codes=True)
+    assert np.array_equal(y.cpu().numpy(), want)                          # bit-exact incl. ties
+    want_codes = O.discretize_codes(torch.from_numpy(g[f"L{L}_lo{lo}_f32_in"]), L, lo, hi).numpy()
+    assert np.array_equal(codes.cpu().numpy().astype(np.int32), want_codes)
+
+
+@pytest.mark.parametrize("L", [4, 16, 256])
+def test_fakequant_module_golden(ops, golden, L):
+    g = golden("fakequant_module.npz")
+    x = torch.from_numpy(g[f"L{L}_x"]).to(DEV)
+    w = torch.from_numpy(g[f"L{L}_w"]).to(DEV)
+    a_act = torch.tensor([float(g[f"L{L}_alpha_act"])], device=DEV)
+    a_w = torch.tensor([float(g[f"L{L}_alpha_w"])], device=DEV)
+    qa, _ = ops.fakequant(x, a_act, L, 0.0, 1.0)
+    qw, cw = ops.fakequant(w, a_w, L, -1.0, 1.0, want_codes=True)
+    assert np.array_equal(qa.cpu().numpy(), g[f"L{L}_qact"])
+    assert np.array_equal(qw.cpu().numpy(), g[f"L{L}_qw"])
+    assert np.array_equal(cw.cpu().numpy(), g[f"L{L}_wint"])              # == store_int_weight codes
+
+
+@pytest.mark.parametrize("numel", [1, 3, 4, 1023, 1 << 20, (1 << 22) + 5])
+def test_fakequant_ragged_sizes(ops, numel):
+    torch.manual_seed(numel)
+    x = (torch.randn(numel) * 2).relu()
+    alpha = torch.tensor([1.37])
+    want = O.quantize_act(x, alpha[0], 16)
+    y, c = ops.fakequant(x.to(DEV), alpha.to(DEV), 16, 0.0, 1.0, want_codes=True)
+    assert torch.equal(y.cpu(), want)
+    assert torch.equal(c.cpu().int(), O.discretize_codes(x / alpha[0], 16, 0, 1))
+
+
+def test_fakequant_state_and_ndhwc_codes(ops):
+    torch.manual_seed(3)
+    x = torch.relu(torch.randn(2, 32, 5, 6, 7)) * 1.3
+    a, b = O.project_by_iter(x, 16, 0, 1)
+    st = ops.ScaleState(torch.device(DEV))
+    st.set_a(a)
+    y = ops.fakequant_state(x.to(DEV), st, 16, 0.0, 1.0)
+    assert torch.equal(y.cpu(), a * b)                                     # fp32(a) * fp32(level)
+    codes = ops.quantize_act_ndhwc(x.to(DEV), 16, state=st)
+    want = O.discretize_codes(x.double() / a, 16, 0, 1).permute(0, 2, 3, 4, 1)
+    assert torch.equal(codes.cpu().float().int(), want)
+    # fp32 flavour (PTQConv._quantize_act arithmetic)
+    alpha = torch.tensor([a], dtype=torch.float32)
+    codes32 = ops.quantize_act_ndhwc(x.to(DEV), 16, alpha=alpha.to(DEV))
+    want32 = O.discretize_codes(x / alpha[0], 16, 0, 1).permute(0, 2, 3, 4, 1)
+    assert torch.equal(codes32.cpu().float().int(), want32)
+
+
+# ---------------------------------------------------------------- scale search (a3)
+@pytest.mark.parametrize("name,lo,hi", [("act", 0, 1), ("wt", -1, 1)])
+@pytest.mark.parametrize("L", [4, 16, 256])
+def test_scale_search_golden(ops, golden, name, lo, hi, L):
+    g = golden("project_by_iter.npz")
+    v = torch.from_numpy(g[name]).to(DEV)
+    st = ops.ScaleState(torch.device(DEV))
+    ops.scale_search(v, L, float(lo), float(hi), st)
+    s = st.read()
+    a_ref = float(g[f"{name}_L{L}_a"])
+    assert s["failed"] == 0 and s["converged"] == 1
+    assert abs(s["a"] - a_ref) <= 1e-9 * abs(a_ref)
+    assert s["passes"] == int(g[f"{name}_L{L}_passes"])
+    b = ops.fakequant_state(v, st, L, float(lo), float(hi)).cpu().numpy()
+    assert np.array_equal(b, np.float32(a_ref) * g[f"{name}_L{L}_b"])
+
+
+def test_scale_search_strided_sum_and_multi_gpu_blocks(ops):
+    """v = w*[:, :K] + dual with w* carrying a bias column (ld = K+1); and the one-pass
+    building blocks used when volumes are sharded reach the same fixed point."""
+    torch.manual_seed(5)
+    c2, k = 24, 432
+    sol = torch.randn(c2, k + 1) * 0.1
+    dual = torch.randn(c2, k) * 0.01
+    a_ref, b_ref, passes = O.project_by_iter(sol[:, :k] + dual, 16, -1, 1, return_iters=True)
+    sol_d, dual_d = sol.to(DEV), dual.to(DEV)
+    st = ops.ScaleState(torch.device(DEV))
+    ops.scale_search(sol_d[:, :k], 16, -1.0, 1.0, st, v2=dual_d)
+    s = st.read()
+    assert abs(s["a"] - a_ref) <= 1e-9 * abs(a_ref) and s["passes"] == passes
+    # multi-GPU formulation on one device: partial sums -> (all-reduce) -> step
+    st2 = ops.ScaleState(torch.device(DEV))
+    sums = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ws = ops.workspace(ops.capi.load().effq_scale_search_workspace(), torch.device(DEV))
+    v = (sol[:, :k] + dual).contiguous().to(DEV)
+    ops.scale_partial(v, 16, -1.0, 1.0, st2, 0, sums, ws)
+    ops.scale_step(st2, sums, 0, 16)
+    for _ in range(passes + 3):
+        ops.scale_partial(v, 16, -1.0, 1.0, st2, 1, sums, ws)
+        ops.scale_step(st2, sums, 1, 16)
+    s2 = st2.read()
+    assert s2["converged"] == 1 and s2["passes"] == passes
+    assert abs(s2["a"] - a_ref) <= 1e-9 * abs(a_ref)
+
+
+def test_scale_search_large_activation(ops):
+    torch.manual_seed(6)
+    x = torch.relu(torch.randn(2, 32, 32, 32, 32))                 # 2.1 M elements, many CTAs
+    a_ref, _, passes = O.project_by_iter(x, 16, 0, 1, return_iters=True)
+    st = ops.ScaleState(torch.device(DEV))
+    ops.scale_search(x.to(DEV), 16, 0.0, 1.0, st)
+    s = st.read()
+    assert abs(s["a"] - a_ref) <= 1e-9 * abs(a_ref)
+    assert abs(s["passes"] - passes) <= 1
+
+
+# ---------------------------------------------------------------- conv + squared error (a10)
+CONV_CASES = [
+    # n, c1, c2, k, s, p, spatial
+    (2, 4, 32, 3, 2, 1, (16, 16, 16)),     # conv0-like
+    (2, 32, 3, 1, 1, 0, (8, 16, 8)),       # final_cls-like
+    (1, 16, 16, 3, 1, 1, (5, 7, 9)),       # ragged
+    (2, 32, 64, 1, 1, 0, (4, 6, 10)),
+    (1, 8, 40, 3, 1, 1, (6, 6, 6)),
+]
+
+
+@pytest.mark.parametrize("n,c1,c2,k,s,p,sp", CONV_CASES)
+def test_conv3d_f32_and_sse(ops, n, c1, c2, k, s, p, sp):
+    torch.manual_seed(c1 * 100 + c2)
+    x = torch.randn(n, c1, *sp)
+    w = torch.randn(c2, c1, k, k, k) * 0.1
+    b = torch.randn(c2)
+    want = F.conv3d(x, w, b, s, p)
+    target = want + 0.05 * torch.randn_like(want)
+    att = torch.rand(n, *want.shape[2:]) + 0.5
+    out, sse = ops.conv3d_f32(x.to(DEV), w.to(DEV), b.to(DEV), s, p, want_out=True, target=target.to(DEV),
+                              att=att.to(DEV))
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-4)          # fp32 conv, different summation order
+    ref = (att.unsqueeze(1).double() * (want.double() - target.double()) ** 2).sum().item()
+    assert abs(sse.item() - ref) <= 1e-4 * ref
+    _, sse2 = ops.conv3d_f32(x.to(DEV), w.to(DEV), b.to(DEV), s, p, want_out=False, target=target.to(DEV))
+    ref2 = ((want.double() - target.double()) ** 2).sum().item()
+    assert abs(sse2.item() - ref2) <= 1e-4 * ref2
+
+
+TC_CASES = [
+    # n, c1, c2, k, spatial, La, Lw
+    (1, 32, 32, 1, (2, 16, 8), 16, 16),
+    (1, 32, 32, 3, (3, 16, 8), 16, 16),
+    (2, 32, 32, 3, (4, 16, 16), 16, 16),
+    (1, 64, 64, 3, (4, 16, 8), 16, 16),
+    (1, 32, 64, 1, (4, 8, 8), 16, 16),
+    (1, 128, 128, 3, (2, 8, 8), 16, 16),     # two channel groups, streamed weights, ragged tile (H=8)
+    (1, 256, 128, 1, (2, 8, 8), 4, 4),
+    (1, 16, 48, 3, (3, 10, 12), 256, 256),   # ragged H/W, N=48 (x16 TMEM load), 256 levels
+    (2, 64, 32, 3, (5, 20, 12), 4, 16),
+]
+
+
+@pytest.mark.parametrize("n,c1,c2,k,sp,la,lw", TC_CASES)
+def test_conv3d_tc_exact_on_codes(ops, n, c1, c2, k, sp, la, lw):
+    """tcgen05 conv: integer codes in, exact integer accumulation -> must equal the fp32
+    reference conv on the same codes up to the final scale/bias rounding."""
+    assert ops.conv3d_tc_supported((n, c1, *sp), c2, k, 1, (k - 1) // 2)
+    torch.manual_seed(c1 + c2 + k)
+    xc = torch.randint(0, la, (n, c1, *sp)).float()
+    wc = (2 * torch.randint(0, lw, (c2, c1, k, k, k)) - (lw - 1)).float()
+    b = torch.randn(c2)
+    scale = 0.0123
+    want = F.conv3d(xc.double(), wc.double(), None, 1, (k - 1) // 2).float() * scale + b.view(1, -1, 1, 1, 1)
+    target = want + 0.1 * torch.randn_like(want)
+    att = torch.rand(n, *sp) + 0.5
+    xq = xc.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+    wq = ops.pack_weight_codes(wc).to(DEV)
+    cs = torch.tensor([scale], dtype=torch.float32, device=DEV)
+    out, sse = ops.conv3d_tc(xq, wq, b.to(DEV), cs, c2, k, want_out=True, target=target.to(DEV), att=att.to(DEV))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.cpu(), want, rtol=2e-6, atol=2e-6)
+    ref = (att.unsqueeze(1).double() * (want.double() - target.double()) ** 2).sum().item()
+    assert abs(sse.item() - ref) <= 1e-5 * ref
+    # no output written, unweighted: the per-iteration scoring call
+    _, sse2 = ops.conv3d_tc(xq, wq, b.to(DEV), cs, c2, k, want_out=False, target=target.to(DEV))
+    ref2 = ((want.double() - target.double()) ** 2).sum().item()
+    assert abs(sse2.item() - ref2) <= 1e-5 * ref2
+
+
+def test_conv3d_tc_linearity_at_scale(ops):
+    """Full-size property check (too big for the CPU oracle): conv is linear in the weights,
+    and agrees with the generic fp32 kernel on the same codes."""
+    torch.manual_seed(9)
+    n, c, sp = 2, 32, (32, 64, 64)
+    xc = torch.randint(0, 16, (n, c, *sp), device=DEV).float()
+    w1 = (2 * torch.randint(0, 16, (c, c, 3, 3, 3), device=DEV) - 15).float()
+    xq = xc.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+    cs = torch.ones(1, device=DEV)
+    o1, _ = ops.conv3d_tc(xq, ops.pack_weight_codes(w1), None, cs, c, 3)
+    o2, _ = ops.conv3d_tc(xq, ops.pack_weight_codes(-w1), None, cs, c, 3)
+    assert torch.equal(o1, -o2)
+    ref, _ = ops.conv3d_f32(xc, w1, None, 1, 1)
+    assert torch.equal(o1, ref)                      # integers < 2^24: both paths exact
+
+
+# ---------------------------------------------------------------- normal equations (a7, a8)
+@pytest.mark.parametrize("name", ["k3s1p1", "k3s2p1", "k1s1p0"])
+def test_gram_golden(ops, golden, name):
+    g = golden("solver.npz")
+    k, s, p = [int(t) for t in g[f"{name}_geom"]]
+    x = torch.from_numpy(g[f"{name}_x"]).to(DEV)
+    y = torch.from_numpy(g[f"{name}_y"]).to(DEV)
+    att = torch.from_numpy(g[f"{name}_att"]).to(DEV)
+    a0, b0 = ops.gram(x, y, att, (k, k, k), s, p, has_bias=True)
+    np.testing.assert_allclose(a0.cpu().numpy(), g[f"{name}_A0"], rtol=2e-5, atol=1e-4)
+    np.testing.assert_allclose(b0.cpu().numpy(), g[f"{name}_B0"], rtol=2e-5, atol=1e-4)
+    # symmetry (size-independent property)
+    assert torch.allclose(a0, a0.T, rtol=1e-6, atol=1e-6)
+
+
+def test_gram_codes_with_scale_and_no_bias(ops):
+    torch.manual_seed(12)
+    xc = torch.randint(0, 16, (2, 8, 6, 8, 8)).float()
+    y = torch.randn(2, 5, 6, 8, 8)
+    sc = 0.37
+    a0, b0 = ops.gram(xc.to(DEV), y.to(DEV), None, (3, 3, 3), 1, 1, has_bias=False,
+                      x_scale=torch.tensor([sc], device=DEV))
+    cols = O.im2col(xc * sc, 3, 3, 3, 1, 1).double()
+    ym = y.permute(1, 0, 2, 3, 4).reshape(5, -1).double()
+    np.testing.assert_allclose(a0.cpu().numpy(), (2 * cols @ cols.T).float().numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(b0.cpu().numpy(), (2 * ym @ cols.T).float().numpy(), rtol=1e-5, atol=1e-4)
+
+
+# ---------------------------------------------------------------- ADMM update (a9, a11)
+def test_admm_elementwise_kernels(ops):
+    torch.manual_seed(13)
+    c2, c1, taps = 16, 16, 27
+    k = c1 * taps
+    kp = k + 1
+    b0, w0p = torch.randn(c2, kp), torch.randn(c2, kp)
+    g, dual = torch.randn(c2, k) * 0.1, torch.randn(c2, k) * 0.01
+    rho, eta = 12.5, 1.25
+    want_b = b0 + eta * w0p
+    want_b[:, :k] += rho * (g - dual)
+    out = torch.empty(c2, kp, device=DEV)
+    ops.admm_rhs(b0.to(DEV), w0p.to(DEV), g.to(DEV), dual.to(DEV), rho, eta, out)
+    assert torch.equal(out.cpu(), want_b)
+    a0 = torch.randn(kp, kp)
+    qe = torch.eye(kp)
+    qe[-1, -1] = 0
+    want_a = a0 + rho * qe + eta * torch.eye(kp)
+    aout = torch.empty(kp, kp, device=DEV)
+    ops.admm_lhs(a0.to(DEV), rho, eta, True, aout)
+    assert torch.equal(aout.cpu(), want_a)
+
+    # projection: G = a*b, dual = (w* - G + dual)/2, codes in the tensor-core layout
+    sol = torch.randn(c2, kp) * 0.1
+    a_w, b_w = O.project_by_iter(sol[:, :k] + dual, 16, -1, 1)
+    g_ref = a_w * b_w
+    dual_ref = (sol[:, :k] - g_ref + dual) / 2
+    dev = torch.device(DEV)
+    wst, xst, st = ops.ScaleState(dev), ops.ScaleState(dev), ops.AdmmState(dev)
+    xst.set_a(2.5)
+    sol_d, dual_d = sol.to(DEV), dual.to(DEV)
+    ops.scale_search(sol_d[:, :k], 16, -1.0, 1.0, wst, v2=dual_d)
+    g_d, bstar = torch.empty(c2, k, device=DEV), torch.empty(c2, device=DEV)
+    wcodes = torch.empty(taps * (c1 // 8) * c2 * 8, dtype=torch.bfloat16, device=DEV)
+    ops.admm_project(sol_d, dual_d, wst, xst, 16, 16, c2, c1, taps, True, 2.0, g_d, bstar, wcodes, st)
+    assert torch.equal(g_d.cpu(), g_ref)
+    assert torch.equal(dual_d.cpu(), dual_ref)
+    assert torch.equal(bstar.cpu(), sol[:, k])
+    codes_ref = (2 * O.discretize_codes((sol[:, :k] + dual).double() / a_w, 16, -1, 1) - 15).float()
+    assert torch.equal(wcodes.cpu().float(), ops.pack_weight_codes(codes_ref.view(c2, c1, 3, 3, 3)).float().flatten())
+    s = st.read()
+    assert abs(s["a_w"] - np.float32(a_w)) == 0
+    want_cs = np.float32(np.float64(np.float32(2.5)) / 15 * np.float64(np.float32(a_w)) / 15)
+    assert abs(s["conv_scale"] - want_cs) <= 1e-7 * want_cs
+
+    # best-iterate tracking: strict '<', iterate 0 always seeds
+    best_g, best_b = torch.zeros(c2, k, device=DEV), torch.zeros(c2, device=DEV)
+    hist = torch.zeros(4, device=DEV)
+    sse = torch.zeros(1, dtype=torch.float64, device=DEV)
+    st.reset()
+    for it, val in enumerate([5.0, 7.0, 5.0, 3.0]):
+        sse.fill_(val * 100)
+        g_d.fill_(float(it))
+        ops.admm_track(st, sse, 100.0, g_d, bstar, best_g, best_b, hist)
+        s = st.read()
+        assert s["iter"] == it + 1
+        assert s["best_iter"] == (0 if it < 3 else 3)
+        assert best_g[0, 0].item() == (0.0 if it < 3 else 3.0)
+    assert hist.cpu().tolist() == [5.0, 7.0, 5.0, 3.0]

@@ -1,0 +1,86 @@
+"""Bring-up diagnostics for the tcgen05 conv kernel: structured inputs, simplest case first.
+Usage (GPU box): python tools/tc_diag.py > gpurun_out/tc_diag.log 2>&1"""
+import sys
+import os
+import time
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from efficientq_b200 import ops  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def run(tag, xc, wc, k, scale=1.0, bias=None):
+    n, c1 = xc.shape[:2]
+    c2 = wc.shape[0]
+    want = F.conv3d(xc.double(), wc.double(), None, 1, (k - 1) // 2).float() * scale
+    if bias is not None:
+        want = want + bias.view(1, -1, 1, 1, 1)
+    xq = xc.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+    wq = ops.pack_weight_codes(wc).to(DEV)
+    cs = torch.tensor([scale], dtype=torch.float32, device=DEV)
+    ws = ops.workspace(16 + 8 * 1024, torch.device(DEV))
+    t0 = time.time()
+    try:
+        out, sse = ops.conv3d_tc(xq, wq, bias.to(DEV) if bias is not None else None, cs, c2, k, want_out=True,
+                                 target=want.to(DEV), ws=ws)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"[{tag}] EXCEPTION {e!r}")
+        return False
+    dt = time.time() - t0
+    flags = ws[:8].view(torch.int32).cpu().tolist()
+    diff = (out.cpu() - want).abs()
+    ok = diff.max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    print(f"[{tag}] ok={ok} maxdiff={diff.max().item():.4g} wantmax={want.abs().max().item():.4g} "
+          f"sse={sse.item():.4g} ws(done,abort)={flags} {dt * 1e3:.1f} ms")
+    if not ok:
+        idx = torch.nonzero(diff > 1e-5 * max(1.0, want.abs().max().item()))
+        print("   mismatches:", idx.shape[0], "of", diff.numel(), "first:", idx[:6].tolist())
+        for i in idx[:6].tolist():
+            print("     at", i, "got", out.cpu()[tuple(i)].item(), "want", want[tuple(i)].item())
+        ch = (diff > 0).any(dim=0).any(dim=-1).any(dim=-1).any(dim=-1)
+        print("   bad channels:", torch.nonzero(ch).flatten().tolist()[:40])
+    return ok
+
+
+def main():
+    torch.manual_seed(0)
+    print(torch.cuda.get_device_name(0))
+    ok = True
+    for c1, c2 in [(32, 32), (64, 64), (16, 16)]:
+        sp = (2, 16, 8)
+        ones_x = torch.ones(1, c1, *sp)
+        ones_w = torch.ones(c2, c1, 1, 1, 1)
+        ok &= run(f"k1 ones c{c1}->{c2}", ones_x, ones_w, 1)
+        x = torch.randint(0, 16, (1, c1, *sp)).float()
+        w1 = torch.zeros(c2, c1, 1, 1, 1)
+        for j in range(c2):
+            w1[j, j % c1] = 1.0
+        ok &= run(f"k1 perm c{c1}->{c2}", x, w1, 1)
+        w = (2 * torch.randint(0, 16, (c2, c1, 1, 1, 1)) - 15).float()
+        ok &= run(f"k1 rand c{c1}->{c2}", x, w, 1, 0.01, torch.randn(c2))
+    for c1, c2 in [(32, 32), (64, 64)]:
+        sp = (3, 16, 8)
+        x = torch.randint(0, 16, (1, c1, *sp)).float()
+        for tap in [(1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (2, 2, 2)]:
+            w = torch.zeros(c2, c1, 3, 3, 3)
+            for j in range(c2):
+                w[j, j % c1, tap[0], tap[1], tap[2]] = 1.0
+            ok &= run(f"k3 tap{tap} c{c1}->{c2}", x, w, 3)
+        w = (2 * torch.randint(0, 16, (c2, c1, 3, 3, 3)) - 15).float()
+        ok &= run(f"k3 rand c{c1}->{c2}", x, w, 3, 0.01, torch.randn(c2))
+    x = torch.randint(0, 16, (2, 128, 4, 20, 12)).float()
+    w = (2 * torch.randint(0, 16, (128, 128, 3, 3, 3)) - 15).float()
+    ok &= run("k3 rand c128->128 ragged", x, w, 3, 0.01, torch.randn(128))
+    x = torch.randint(0, 16, (1, 256, 4, 8, 8)).float()
+    w = (2 * torch.randint(0, 16, (256, 256, 3, 3, 3)) - 15).float()
+    ok &= run("k3 rand c256->256", x, w, 3, 0.01, torch.randn(256))
+    print("ALL OK" if ok else "SOME FAILED")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Headline benchmark: EfficientQ PTQ calibration throughput on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+A step = one full PTQ calibration (FP forward -> attention-mask pyramid -> quantizing pass,
+the reference's own timed region t2-t0, src/ptqer.py:333-366) of the BraTS-config 3D U-Net
+at W4A4 (16/16 levels, first/last layer 256/-) over this rank's synthetic 4x128^3 volumes.
+N = 1 is BASELINE.json configs[1] (32 volumes on one B200); N > 1 shards 32 volumes per
+GPU (configs[3]: 256 volumes on 8 GPUs) -- weak scaling, NCCL all-reduce of the statistics
+listed in efficientq_b200/dist.py.  metric = calibration volumes per second (whole job);
+PTQ wall-clock per step is reported beside it as `ptq_wall_s`.
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (volumes per GPU, edge, levels_w, levels_a, task)
+    "brats_w4a4_32x128": dict(n=32, size=(128, 128, 128), lw=16, la=16, task="brats"),
+    "brats_w4a4_8x64": dict(n=8, size=(64, 64, 64), lw=16, la=16, task="brats"),
+    "brats_w4a4_2x64": dict(n=2, size=(64, 64, 64), lw=16, la=16, task="brats"),
+}
+METRIC = "ptq_calibration_throughput"
+UNIT = "volumes/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def brats_args(wl):
+    from efficientq_b200 import entrance
+    a = entrance.build_parser().parse_args(["ptq", "--qlvl_w", str(wl["lw"]), "--qlvl_a", str(wl["la"]),
+                                            "--config", os.path.join(ROOT, "config", "brats_ptq.yaml")])
+    a = entrance.merge_config(a.config, a)
+    a.data_dir = "synthetic"
+    a.lwq_patchsz = ",".join(str(s) for s in wl["size"])
+    return a
+
+
+def seeded_state(model, seed=16):
+    """Random-init weights of the BraTS architecture (no checkpoints offline): kaiming conv
+    weights (reference utils/misc.py:85-102) and perturbed BN statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if k.endswith("alpha_act") or k.endswith("alpha_w"):
+            continue
+        if v.dim() == 5:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3] * v.shape[4]
+            sd[k] = torch.randn(v.shape, generator=g) * (2.0 / fan_in) ** 0.5
+        elif k.endswith("running_mean"):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith("num_batches_tracked"):
+            sd[k] = v.clone()
+        elif k.endswith(".weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith(".bias"):
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = v.clone()
+    return sd
+
+
+def build_model(wl):
+    from efficientq_b200 import definer, fold_bn
+    args = brats_args(wl)
+    QConv, _, kwQ = definer.get_conv_class(args)
+    cube, _ = definer.get_model_cube(args, QConv, kwQ)
+    model = cube["model"]
+    model.load_state_dict(seeded_state(model), strict=False)
+    model.eval()
+    fold_bn.search_fold_and_remove_bn(model)
+    return model, args
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_sample(wl, iters=1, threads=None, edge_div=2):
+    """Bounded sample of the CPU path (oracle port of the reference) on the host cores.
+
+    Runs the per-layer calibration of ALL 22 quantizer layers on ONE volume whose edge is
+    1/edge_div of the workload's (so 1/edge_div^3 of the voxels) with `iters` ADMM
+    iteration(s), timing each phase, and scales to the full job with V = N * edge_div^3:
+        t = V*(t_act + t_gram) + 200/iters*(t_solve + t_wproj + V*t_conv)
+    -- activation search, im2col+Gram and conv+mse scale with the voxel count, the dense
+    solve and the weight projection do not.
+    Returns (volumes/s, description, seconds spent, scaled full-job seconds)."""
+    from oracle import effq_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    from efficientq_b200 import synth
+    from efficientq_b200.qconv import PTQConv
+    model, _ = build_model(wl)
+    t_begin = time.perf_counter()
+    size = tuple(max(64, s // edge_div) for s in wl["size"])
+    vox_scale = 1.0
+    for a, b in zip(wl["size"], size):
+        vox_scale *= a / b
+    x = synth.batch(1, 0, 4, size, wl["task"])
+    feats = {}
+    hooks = []
+    for name, m in model.named_modules():
+        if isinstance(m, PTQConv):
+            m.set_fp()
+            hooks.append(m.register_forward_hook(
+                lambda mod, i, o, name=name: feats.__setitem__(name, (i[0].detach(), o.detach()))))
+    with torch.no_grad():
+        model(x)
+    for h in hooks:
+        h.remove()
+    timers = {}
+    for name, m in model.named_modules():
+        if not isinstance(m, PTQConv):
+            continue
+        xi, yo = feats.pop(name)
+        O.admm_layer(xi, m.weight.data, m.bias.data, yo, m.stride, m.padding, m.qlvl_w, m.qlvl_act, m.q_act,
+                     None, n_iter=iters, timers=timers)
+    n = wl["n"]
+    v = n * vox_scale
+    full = v * (timers.get("act_search", 0) + timers.get("im2col_gram", 0)) + \
+        200.0 / iters * (timers.get("solve", 0) + timers.get("w_project", 0) + v * timers.get("conv_mse", 0))
+    spent = time.perf_counter() - t_begin
+    desc = (f"oracle port on {threads} threads, all 22 layers, one {size} volume (1/{vox_scale:.0f} of a "
+            f"{wl['size']} volume), {iters} of 200 ADMM iterations; phases(s) "
+            f"{json.dumps({k: round(t, 3) for k, t in timers.items()})}; scaled with V={v:.0f}: "
+            f"V*(act+gram)+200/{iters}*(solve+wproj+V*conv) = {full:.0f}s for {n} volumes")
+    return n / full, desc, spent, full
+
+
+def run_reference(args, wl, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    times, vals, desc, full = [], [], "", 0.0
+    for i in range(args.warmup + args.steps):
+        v, desc, spent, full = cpu_sample(wl, iters=1, threads=cores)
+        if i >= args.warmup:
+            times.append(spent)
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "volumes_per_gpu": wl["n"], "volume": list(wl["size"]),
+                       "levels_w": wl["lw"], "levels_a": wl["la"]},
+            "ptq_wall_s": full,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args, wl, wl_name):
+    from efficientq_b200 import capi, ops, ptqer, synth
+    from efficientq_b200.dist import init_from_env
+    capi.load()                                   # raises if the CUDA library is missing: no fallback
+    dist = init_from_env("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    model, margs = build_model(wl)
+    model.to(dev)
+    fp_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    n_local = wl["n"]
+    t0 = time.time()
+    host_batch = synth.batch(n_local, dist.rank * n_local, 4, wl["size"], wl["task"], pin=True)
+    log(f"[rank {dist.rank}] synthetic batch {tuple(host_batch.shape)} in {time.time() - t0:.1f}s")
+    dev_batch = torch.empty(host_batch.shape, dtype=torch.float32, device=dev)
+    h2d = host_batch.numel() * 4
+    d2h_box = [0]
+
+    def one_step(timed):
+        model.load_state_dict(fp_state, strict=False)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        dev_batch.copy_(host_batch, non_blocking=True)                 # H2D of this step's inputs (pinned)
+        e[1].record()
+        res = ptqer.calibrate(model, dev_batch, wl["task"], margs.init_stride, dist)
+        e[2].record()
+        out = {k: v.detach().to("cpu") for k, v in model.state_dict().items()}   # D2H of the result
+        losses = list(res["layer_loss"])
+        e[3].record()
+        d2h_box[0] = sum(v.numel() * v.element_size() for v in out.values())
+        return e, res, losses
+
+    for i in range(args.warmup):
+        t = time.time()
+        one_step(False)
+        torch.cuda.synchronize()
+        log(f"[rank {dist.rank}] warmup {i}: {time.time() - t:.2f}s")
+
+    sampler = ClockSampler(local)
+    ops.timer.reset()
+    ops.timer.enabled = True
+    capi.reset_launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    if dist.rank == 0:
+        sampler.start()
+    w0 = time.time()
+    evs, last = [], None
+    for i in range(args.steps):
+        e, res, losses = one_step(True)
+        evs.append(e)
+        last = (res, losses)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.time() - w0
+    clocks = sampler.stop() if dist.rank == 0 else None
+    ops.timer.enabled = False
+    launches = capi.launch_count()
+
+    dev_ms = sum(e[1].elapsed_time(e[2]) for e in evs)           # inputs resident in HBM
+    e2e_ms = sum(e[0].elapsed_time(e[3]) for e in evs)           # host buffers in, results out
+    t = torch.tensor([dev_ms, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    dist.all_reduce_max(t)
+    dev_ms, e2e_ms, wall_ms = [float(v) for v in t.tolist()]
+    units = float(n_local * dist.world * args.steps)
+    value = units / (dev_ms / 1e3)
+    e2e = units / (e2e_ms / 1e3)
+    if dist.rank != 0:
+        return
+
+    pk = peaks()
+    ksum = ops.timer.summary()
+    res, losses = last
+    act_passes = sum(r.act_passes for r in res["reports"] if r and r.alpha_act is not None)
+    kern = {}
+    for name, s in ksum.items():
+        d = dict(launches=s["launches"] // args.steps, ms_per_step=s["ms"] / args.steps)
+        if s["flops"]:
+            d["tflops"] = s["flops"] / (s["ms"] * 1e-3) / 1e12
+        if s["bytes"] and not s["flops"]:
+            d["gbs"] = s["bytes"] / (s["ms"] * 1e-3) / 1e9
+        kern[name] = d
+    top = max(ksum, key=lambda k: ksum[k]["ms"]) if ksum else None
+    roof = None
+    if top:
+        s = ksum[top]
+        if s["flops"]:
+            ach = s["flops"] / (s["ms"] * 1e-3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                    "launches_per_step": s["launches"] // args.steps, "avg_launch_ms": s["ms"] / s["launches"]}
+        else:
+            nbytes = s["bytes"] or s["pass_bytes"]
+            ach = nbytes / (s["ms"] * 1e-3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                    "launches_per_step": s["launches"] // args.steps, "avg_launch_ms": s["ms"] / s["launches"]}
+
+    cpu = None
+    if args.gpus == 1 and not args.no_cpu:
+        try:
+            v, desc, spent, full = cpu_sample(wl, iters=1)
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc,
+                   "sample_seconds": spent, "ptq_wall_s": full}
+        except Exception as exc:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl_name, "volumes_per_gpu": n_local, "volume": list(wl["size"]),
+                       "levels_w": wl["lw"], "levels_a": wl["la"], "admm_iters": 200, "layers": 22,
+                       "l2": "inputs_larger_than_l2", "parallelism": f"dp{dist.world} (volumes sharded)"},
+            "ptq_wall_s": dev_ms / args.steps / 1e3,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "kernels": kern, "act_scale_passes_per_step": act_passes,
+            "layer_loss_last_step": [ln.rsplit(":", 1)[0].strip() + ":" + "%.6e" % float(ln.rsplit(":", 1)[1])
+                                     for ln in losses][:3] + ["..."],
+            "wall_ms_timed_region": wall_ms}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="brats_w4a4_32x128", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    # the library and the orchestrator print progress; keep stdout for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
+    globals()["_PROGRESS"] = sys.stderr
+    import builtins
+    _print = builtins.print
+
+    def routed_print(*a, **k):
+        if "file" not in k and not (len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{")):
+            k["file"] = sys.stderr
+        return _print(*a, **k)
+    builtins.print = routed_print
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,41 @@ from . import capi
 from .capi import Geom, EffqError, ptr, stream, check
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of the major kernels on the launching stream (bench.py).
+    ``work`` is the ALGORITHMIC work of the launch: {"flops": ..} or {"bytes": ..}."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = {}
+
+    def run(self, name, work, fn):
+        if not self.enabled:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.records.setdefault(name, []).append((e0, e1, work))
+        return out
+
+    def summary(self):
+        """name -> dict(launches, ms, flops, bytes); call after a device synchronize."""
+        res = {}
+        for name, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            res[name] = dict(launches=len(recs), ms=ms, flops=sum(w.get("flops", 0) for _, _, w in recs),
+                             bytes=sum(w.get("bytes", 0) for _, _, w in recs),
+                             pass_bytes=sum(w.get("pass_bytes", 0) for _, _, w in recs))
+        return res
+
+    def reset(self):
+        self.records = {}
+
+
+timer = KernelTimer()
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != torch.float32 or not t.is_cuda:
         raise EffqError(f"{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
@@ -93,8 +128,10 @@ def fakequant(x: torch.Tensor, alpha: torch.Tensor, nlvl: int, lo: float, hi: fl
     alpha = _f32c(alpha.reshape(1), "alpha")
     y = torch.empty_like(x) if want_values else None
     codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
-    check(capi.load().effq_fakequant_f32(ptr(x), x.numel(), ptr(alpha), float(lo), float(hi), int(nlvl),
-                                         ptr(y), ptr(codes), stream()), "effq_fakequant_f32")
+    nbytes = x.numel() * (4 + (4 if want_values else 0) + (1 if want_codes else 0))
+    timer.run("fakequant_f32", {"bytes": nbytes}, lambda: check(
+        capi.load().effq_fakequant_f32(ptr(x), x.numel(), ptr(alpha), float(lo), float(hi), int(nlvl),
+                                       ptr(y), ptr(codes), stream()), "effq_fakequant_f32"))
     return y, codes
 
 
@@ -102,8 +139,9 @@ def fakequant_state(x: torch.Tensor, state: ScaleState, nlvl: int, lo: float, hi
     """fp32(a)*fp32(level) with the scale-search state (EfficientQConv.py:68-70)."""
     x = _f32c(x, "x")
     y = torch.empty_like(x)
-    check(capi.load().effq_fakequant_state(ptr(x), x.numel(), state.p, float(lo), float(hi), int(nlvl), ptr(y),
-                                           stream()), "effq_fakequant_state")
+    timer.run("fakequant_state", {"bytes": 8 * x.numel()}, lambda: check(
+        capi.load().effq_fakequant_state(ptr(x), x.numel(), state.p, float(lo), float(hi), int(nlvl), ptr(y),
+                                         stream()), "effq_fakequant_state"))
     return y
 
 
@@ -115,8 +153,9 @@ def quantize_act_ndhwc(x: torch.Tensor, nlvl: int, state: Optional[ScaleState] =
     out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
     use64 = 1 if state is not None else 0
     a = _f32c(alpha.reshape(1), "alpha") if alpha is not None else None
-    check(capi.load().effq_quantize_act_ndhwc(ptr(x), n, c, d * h * w, int(nlvl), state.p if state else None,
-                                              ptr(a), use64, ptr(out), stream()), "effq_quantize_act_ndhwc")
+    timer.run("quantize_act_ndhwc", {"bytes": 6 * x.numel()}, lambda: check(
+        capi.load().effq_quantize_act_ndhwc(ptr(x), n, c, d * h * w, int(nlvl), state.p if state else None,
+                                            ptr(a), use64, ptr(out), stream()), "effq_quantize_act_ndhwc"))
     return out
 
 
@@ -152,8 +191,10 @@ def scale_search(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: Scale
                  v2: Optional[torch.Tensor] = None) -> ScaleState:
     """project_by_iter on the device (one cooperative launch, no host sync)."""
     rows, cols, ld1, ld2 = _pair_view(v1, v2)
-    check(capi.load().effq_scale_search(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
-                                        state.p, ptr(_scale_ws(v1.device)), stream()), "effq_scale_search")
+    name = "scale_search_w" if v2 is not None else "scale_search_act"
+    timer.run(name, {"pass_bytes": 4 * rows * cols * (2 if v2 is not None else 1)}, lambda: check(
+        capi.load().effq_scale_search(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
+                                      state.p, ptr(_scale_ws(v1.device)), stream()), "effq_scale_search"))
     return state
 
 
@@ -188,8 +229,10 @@ def conv3d_f32(x, w, bias, stride, padding, want_out=True, target=None, att=None
     if att is not None:
         att = _f32c(att, "att")
     b = _f32c(bias, "bias") if bias is not None else None
-    check(lib.effq_conv3d_f32(ptr(x), ptr(w), ptr(b), C.byref(g), ptr(out), ptr(target), ptr(att), ptr(sse),
-                              ptr(ws), stream()), "effq_conv3d_f32")
+    flops = 2.0 * g.n * od * oh * ow * g.c2 * g.c1 * g.taps
+    timer.run("conv3d_f32", {"flops": flops}, lambda: check(
+        lib.effq_conv3d_f32(ptr(x), ptr(w), ptr(b), C.byref(g), ptr(out), ptr(target), ptr(att), ptr(sse),
+                            ptr(ws), stream()), "effq_conv3d_f32"))
     return out, sse
 
 
@@ -219,8 +262,11 @@ def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, 
         att = _f32c(att, "att")
     b = _f32c(bias, "bias") if bias is not None else None
     cs = conv_scale_ptr if not isinstance(conv_scale_ptr, torch.Tensor) else ptr(conv_scale_ptr)
-    check(lib.effq_conv3d_tc(ptr(xcodes), ptr(wcodes), ptr(b), cs, C.byref(g), ptr(out), ptr(target), ptr(att),
-                             ptr(sse), ptr(ws), stream()), "effq_conv3d_tc")
+    flops = 2.0 * n * d * h * w * c2 * c1 * g.taps
+    nbytes = xcodes.numel() * 2 + wcodes.numel() * 2 + n * d * h * w * c2 * 4 * ((target is not None) + (out is not None))
+    timer.run(f"conv3d_tc_c{c1}x{c2}k{k[0]}", {"flops": flops, "bytes": nbytes}, lambda: check(
+        lib.effq_conv3d_tc(ptr(xcodes), ptr(wcodes), ptr(b), cs, C.byref(g), ptr(out), ptr(target), ptr(att),
+                           ptr(sse), ptr(ws), stream()), "effq_conv3d_tc"))
     return out, sse
 
 
@@ -252,8 +298,11 @@ def gram(x, y, att, ksize, stride, padding, has_bias=True, x_scale=None, ws=None
     if att is not None:
         att = _f32c(att, "att")
     xs = _f32c(x_scale.reshape(1), "x_scale") if x_scale is not None else None
-    check(lib.effq_gram_f32(ptr(x), ptr(xs), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0), ptr(b0),
-                            ptr(ws), stream()), "effq_gram_f32")
+    od, oh, ow = g.out_spatial()
+    flops = 2.0 * g.n * od * oh * ow * (kp + g.c2) * kp
+    timer.run("gram_f32", {"flops": flops}, lambda: check(
+        lib.effq_gram_f32(ptr(x), ptr(xs), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0), ptr(b0),
+                          ptr(ws), stream()), "effq_gram_f32"))
     return a0, b0
 
 

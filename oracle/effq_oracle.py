@@ -249,7 +249,7 @@ def admm_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
                out_fp: torch.Tensor, stride, padding, qlvl_w: int, qlvl_act: int,
                q_act: bool = True, mask_pyramid=None, n_iter: int = 200,
                rho0: float = 10.0, rho_max: float = 1000.0, eta0: float = 1.0,
-               rho_period: int = 50, keep_qact: bool = False) -> LayerResult:
+               rho_period: int = 50, keep_qact: bool = False, timers: Optional[dict] = None) -> LayerResult:
     """One layer of EfficientQ calibration, EfficientQConv.py:33-166.
 
     Quirks reproduced on purpose: best iterate picked by strict ``<`` on the
@@ -258,6 +258,12 @@ def admm_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     (:155-158); rho doubles after iterations 0, 50, 100, ... with the dual
     halved (:129-137); the logged loss is attention-weighted (:161-166).
     """
+    import time as _time
+
+    def _tick(key, t_start):
+        if timers is not None:
+            timers[key] = timers.get(key, 0.0) + (_time.perf_counter() - t_start)
+
     stride = _triple(stride)
     padding = _triple(padding)
     g = weight.detach().clone().float()
@@ -268,33 +274,43 @@ def admm_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     rs = rho_scale_of(out_fp, g, att)
 
     alpha_act = None
+    t_ = _time.perf_counter()
     if q_act:
         a_act, b_act = project_by_iter(x, qlvl_act, 0, 1)
         alpha_act = a_act
         q_x = a_act * b_act
     else:
         q_x = x
+    _tick("act_search", t_)
     rho = rho0 * rs
     rho_m = rho_max * rs
     eta = eta0 * rs
 
     w0 = g.clone()
     b0 = bias.detach().clone().float() if bias is not None else None
+    t_ = _time.perf_counter()
     ne = NormalEquations(q_x, out_fp, tuple(weight.shape[2:]), stride, padding, w0, b0, att)
+    _tick("im2col_gram", t_)
 
     b_star = b0
     best = (None, None, 1e10, 0)
     a_w = None
     hist: List[float] = []
     for it in range(n_iter):
+        t_ = _time.perf_counter()
         w_star, b_star_new = ne.solve(rho, eta, g - dual)
+        _tick("solve", t_)
         if bias is not None:
             b_star = b_star_new
+        t_ = _time.perf_counter()
         a_w, b_w = project_by_iter(w_star + dual, qlvl_w, -1, 1)
         g = a_w * b_w
         dual = w_star - g + dual
+        _tick("w_project", t_)
+        t_ = _time.perf_counter()
         out_q = F.conv3d(q_x, g.float(), b_star, stride, padding)
         loss = F.mse_loss(out_q, out_fp).item()
+        _tick("conv_mse", t_)
         hist.append(loss)
         if it % rho_period == 0:
             if rho * 2 <= rho_m:

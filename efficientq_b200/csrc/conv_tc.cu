@@ -299,6 +299,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const bool live = oh < p.h && ow < p.w;
       const long long sp = (long long)dd * plane + (long long)oh * p.w + ow;
       const long long base = (long long)nn * p.c2 * chan + sp;
+      // Target values do not depend on the MMA: issue all loads of a 32-channel chunk before
+      // anything consumes them (32 independent requests in flight per thread), the first chunk
+      // even before waiting for the accumulator.
+      const bool want_t = live && p.target != nullptr;
+      float tv[32];
+      auto load_targets = [&](int c0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          tv[j] = (want_t && c0 + j < p.c2) ? __ldg(p.target + base + (long long)(c0 + j) * chan) : 0.f;
+      };
+      load_targets(0);
       if (!mbar_wait(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
       tc_fence_after();
       float e32 = 0.f;
@@ -308,25 +319,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const int ncol = min(32, p.c2 - c0);
         if (ncol == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
         tc_wait_ld();
-        if (live) {
+        float o[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < ncol) {
-              const float o = fmaf(__uint_as_float(v[j]), scale, bias_s[c0 + j]);
-              const long long oi = base + (long long)(c0 + j) * chan;
-              if (p.out) p.out[oi] = o;
-              if (p.target) {
-                const float dlt = o - __ldg(p.target + oi);
-                e32 = fmaf(dlt, dlt, e32);
-              }
-            }
-          }
+        for (int j = 0; j < 32; ++j) {
+          o[j] = (j < ncol) ? fmaf(__uint_as_float(v[j]), scale, bias_s[c0 + j]) : 0.f;
+          const float dlt = o[j] - tv[j];
+          if (j < ncol) e32 = fmaf(dlt, dlt, e32);
+        }
+        if (c0 + 32 < p.c2) load_targets(c0 + 32);       // next chunk's loads overlap this chunk's stores
+        if (live && p.out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol) __stcs(p.out + base + (long long)(c0 + j) * chan, o[j]);
         }
       }
       tc_fence_before();
       mbar_arrive(BAR(B_TE + ap.stage));
       ap.advance(2);
-      if (live && p.target) {
+      if (want_t) {
         const float wv = p.att ? __ldg(p.att + (long long)nn * chan + sp) : 1.f;
         err_acc += (double)e32 * (double)wv;
       }

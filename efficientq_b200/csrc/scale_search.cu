@@ -37,12 +37,40 @@ __device__ __forceinline__ float load_v(const VecView& vv, long long r, long lon
   return a;
 }
 
+// Per-element work of a search pass.  The passes use reciprocal multiplies (v * (1/a),
+// (t-lo) * (1/delta)) instead of the reference's two fp64 divisions: the level index can
+// differ only when v/a sits within ~1e-16 (relative) of a rounding boundary, which changes
+// a sum by one level step on one element out of millions -- far below the 1e-5 stopping
+// rule.  The FINAL discretize (effq_fakequant_state / effq_quantize_act_ndhwc /
+// effq_admm_project) keeps the exact divisions and is bit-exact.
+struct PassQ {
+  double inv_a, lo, hi, inv_delta, delta;
+};
+__device__ __forceinline__ PassQ make_passq(double a, const QParamD& q) {
+  PassQ p;
+  p.inv_a = 1.0 / a;
+  p.lo = q.lo;
+  p.hi = q.hi;
+  p.delta = q.delta;
+  p.inv_delta = 1.0 / q.delta;
+  return p;
+}
+__device__ __forceinline__ void accum_bv(double v, const PassQ& p, double& s0, double& s1) {
+  double t = v * p.inv_a;
+  t = fmin(fmax(t, p.lo), p.hi);
+  const double idx = rint((t - p.lo) * p.inv_delta);
+  const double b = __dadd_rn(__dmul_rn(idx, p.delta), p.lo);
+  s0 = fma(b, v, s0);
+  s1 = fma(b, b, s1);
+}
+
 // One pass over this CTA's share.  MODE 0: {sum|v|, 0}. MODE 1: {sum b*v, sum b*b}.
 template <int MODE>
 __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QParamD& q,
                                           long long cta, long long nctas, double& s0, double& s1) {
   s0 = 0.0;
   s1 = 0.0;
+  const PassQ pq = make_passq(MODE == 1 ? a : 1.0, q);
   const long long numel = vv.rows * vv.cols;
   const bool flat = (vv.ld1 == vv.cols) && (!vv.v2 || vv.ld2 == vv.cols);
   const long long stride = nctas * SS_THREADS;
@@ -62,13 +90,8 @@ __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QPa
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const double v = (double)e[k];
-        if (MODE == 0) {
-          s0 += fabs(v);
-        } else {
-          const double b = level_value_d(level_index_d(__ddiv_rn(v, a), q), q);
-          s0 += b * v;
-          s1 += b * b;
-        }
+        if (MODE == 0) s0 += fabs(v);
+        else accum_bv(v, pq, s0, s1);
       }
     }
   } else {
@@ -80,13 +103,8 @@ __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QPa
       const long long c = (it % chunks) * SS_THREADS + threadIdx.x;
       if (c >= vv.cols) continue;
       const double v = (double)load_v(vv, r, c);
-      if (MODE == 0) {
-        s0 += fabs(v);
-      } else {
-        const double b = level_value_d(level_index_d(__ddiv_rn(v, a), q), q);
-        s0 += b * v;
-        s1 += b * b;
-      }
+      if (MODE == 0) s0 += fabs(v);
+      else accum_bv(v, pq, s0, s1);
     }
   }
 }
@@ -131,6 +149,10 @@ __device__ __forceinline__ bool grid_barrier(SSWorkspace* ws, unsigned int& targ
   return ok_s != 0;
 }
 
+// REG_ITEMS > 0: the tensor is small (weights: <= 3.5 M elements) -> every thread keeps its
+// REG_ITEMS elements in registers for the whole search and a pass touches no memory at all.
+// REG_ITEMS == 0: stream v from HBM/L2 every pass (activations).
+template <int REG_ITEMS>
 __global__ void __launch_bounds__(SS_THREADS)
 scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, SSWorkspace* ws) {
   __shared__ double scratch[32];
@@ -142,9 +164,24 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
   unsigned int target = 0;
   int parity = 0;
 
+  double vreg[REG_ITEMS > 0 ? REG_ITEMS : 1];
+  if (REG_ITEMS > 0) {
+    const long long stride = (long long)nctas * SS_THREADS;
+    long long i = (long long)blockIdx.x * SS_THREADS + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < REG_ITEMS; ++k, i += stride)
+      vreg[k] = i < numel ? (double)load_v(vv, i / vv.cols, i % vv.cols) : 0.0;   // 0 adds nothing to any sum
+  }
+
   // pass "-1": a0 = mean|v|
   double s0, s1;
-  pass_sums<0>(vv, 0.0, q, blockIdx.x, nctas, s0, s1);
+  if (REG_ITEMS > 0) {
+    s0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < REG_ITEMS; ++k) s0 += fabs(vreg[k]);
+  } else {
+    pass_sums<0>(vv, 0.0, q, blockIdx.x, nctas, s0, s1);
+  }
   s0 = block_sum(s0, scratch);
   if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = 0.0; }
   if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
@@ -156,7 +193,15 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
 
   while (fabs(a - a_prev) > 1e-5 && passes < max_pass) {
     parity ^= 1;
-    pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
+    if (REG_ITEMS > 0) {
+      const PassQ pq = make_passq(a, q);
+      s0 = 0.0;
+      s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < REG_ITEMS; ++k) accum_bv(vreg[k], pq, s0, s1);
+    } else {
+      pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
+    }
     s0 = block_sum(s0, scratch);
     s1 = block_sum(s1, scratch);
     if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = s1; }
@@ -256,6 +301,16 @@ extern "C" int64_t effq_scale_search_workspace(void) {
   return (int64_t)(a > b ? a : b);
 }
 
+template <int REG_ITEMS>
+static int launch_search(effq::VecView vv, int nlvl, float lo, float hi, effq_scale_state* state,
+                         effq::SSWorkspace* ws, int ctas, cudaStream_t s) {
+  using namespace effq;
+  void* args[] = {&vv, &nlvl, &lo, &hi, &state, &ws};
+  EFFQ_CUDA(cudaLaunchCooperativeKernel((void*)scale_search_kernel<REG_ITEMS>, dim3(ctas), dim3(SS_THREADS), args, 0, s));
+  count_launch();
+  return 0;
+}
+
 extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
                                  int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
                                  void* workspace, void* stream) {
@@ -264,21 +319,19 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   EFFQ_CHECK_ARG(rows > 0 && cols > 0 && ld1 >= cols && (!v2 || ld2 >= cols), "bad shape");
   EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
   cudaStream_t s = (cudaStream_t)stream;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    int occ = 0;
-    EFFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scale_search_kernel, SS_THREADS, 0));
-    EFFQ_CHECK_ARG(occ >= 1, "scale_search kernel does not fit on an SM");
-    per_sm = occ > 2 ? 2 : occ;
-  }
-  const int ctas = pick_ctas(rows * cols, per_sm);
-  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 16, s));     // barrier counter + abort flag
+  const long long numel = rows * cols;
+  const int sms = sm_count();                         // one CTA per SM: cheapest grid barrier
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 16, s));    // barrier counter + abort flag
   VecView vv{v1, v2, ld1, ld2, rows, cols};
   SSWorkspace* ws = (SSWorkspace*)workspace;
-  void* args[] = {&vv, &nlvl, &lo, &hi, &state, &ws};
-  EFFQ_CUDA(cudaLaunchCooperativeKernel((void*)scale_search_kernel, dim3(ctas), dim3(SS_THREADS), args, 0, s));
-  count_launch();
-  return 0;
+  const long long per_cta_8 = (long long)SS_THREADS * 8;
+  if (numel <= (long long)sms * SS_THREADS * 8) {
+    int ctas = (int)((numel + per_cta_8 - 1) / per_cta_8);
+    return launch_search<8>(vv, nlvl, lo, hi, state, ws, ctas < 1 ? 1 : ctas, s);
+  }
+  if (numel <= (long long)sms * SS_THREADS * 24) return launch_search<24>(vv, nlvl, lo, hi, state, ws, sms, s);
+  if (numel <= (long long)sms * SS_THREADS * 48) return launch_search<48>(vv, nlvl, lo, hi, state, ws, sms, s);
+  return launch_search<0>(vv, nlvl, lo, hi, state, ws, sms * 2 > SS_MAX_CTAS ? SS_MAX_CTAS : sms * 2, s);
 }
 
 extern "C" int effq_scale_partial(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,

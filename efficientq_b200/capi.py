@@ -76,6 +76,7 @@ _SIGS = {
     "effq_conv3d_tc_workspace": (C.c_int64, [C.POINTER(Geom)]),
     "effq_conv3d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_pack_wcodes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_gram_workspace": (C.c_int64, [C.POINTER(Geom), C.c_int32]),
     "effq_gram_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

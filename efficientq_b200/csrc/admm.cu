@@ -6,6 +6,7 @@
 // All scalars that the reference pulls to the host with .item() stay in device
 // structs, so the 200-iteration loop of one layer enqueues without a host sync.
 #include "common.cuh"
+#include "tc_layout.cuh"
 
 namespace effq {
 
@@ -64,13 +65,12 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
                     const effq_scale_state* __restrict__ wscale, const effq_scale_state* __restrict__ xscale,
                     int nlvl_w, int nlvl_a, int c2, int c1, int taps, int has_bias, float dual_div,
                     float* __restrict__ g_out, float* __restrict__ bstar_out,
-                    __nv_bfloat16* __restrict__ wcodes, effq_admm_state* st) {
+                    __nv_bfloat16* __restrict__ wcodes, TcLayout lay, effq_admm_state* st) {
   const int k = c1 * taps;
   const long long total = (long long)c2 * k;
   const double a64 = wscale->a;
   const float a32 = (float)a64;
   const QParamD q = make_qparam_d(-1.f, 1.f, nlvl_w);
-  const int c1_chunks = c1 / 8;
   for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
        e += (long long)gridDim.x * AD_THREADS) {
     const int r = (int)(e / k), j = (int)(e % k);
@@ -85,7 +85,7 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
     if (wcodes) {
       const int c = j / taps, t = j % taps;
       const float code = (float)(2.0 * idx - (double)(nlvl_w - 1));      // odd integer in [-(L-1), L-1]
-      wcodes[(((long long)t * c1_chunks + (c >> 3)) * c2 + r) * 8 + (c & 7)] = __float2bfloat16_rn(code);
+      wcodes[tc_wcode_index(r, c, t, c1, c2, lay)] = __float2bfloat16_rn(code);
     }
   }
   if (has_bias && bstar_out) {
@@ -126,7 +126,30 @@ admm_keep_kernel(const int* __restrict__ take, const float* __restrict__ g, cons
       best_b[r] = bstar[r];
 }
 
+// [C2][C1][taps] fp32 integer codes -> bf16 codes in the tensor-core weight layout.
+__global__ void __launch_bounds__(AD_THREADS)
+pack_wcodes_kernel(const float* __restrict__ codes, int c2, int c1, int taps, TcLayout lay,
+                   __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)c2 * c1 * taps;
+  for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
+       e += (long long)gridDim.x * AD_THREADS) {
+    const int t = (int)(e % taps);
+    const int c = (int)((e / taps) % c1);
+    const int r = (int)(e / ((long long)taps * c1));
+    out[tc_wcode_index(r, c, t, c1, c2, lay)] = __float2bfloat16_rn(codes[e]);
+  }
+}
+
 }  // namespace effq
+
+extern "C" int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int32_t taps, void* out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(codes && out && c2 > 0 && c1 > 0 && c1 % 8 == 0 && taps > 0, "bad argument");
+  pack_wcodes_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
+      codes, c2, c1, taps, tc_layout(c1), (__nv_bfloat16*)out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int effq_admm_rhs(const float* b0, const float* w0p, const float* g, const float* dual,
                              float rho, float eta, int32_t c2, int32_t k, int32_t has_bias, float* b_out,
@@ -162,7 +185,7 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
   EFFQ_CHECK_ARG(dual_div != 0.f, "dual_div must be non-zero");
   admm_project_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
       wstar, ldw, dual, wscale, xscale, nlvl_w, nlvl_a, c2, c1, taps, has_bias, dual_div, g_out, bstar_out,
-      (__nv_bfloat16*)wcodes_out, st);
+      (__nv_bfloat16*)wcodes_out, tc_layout(c1), st);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

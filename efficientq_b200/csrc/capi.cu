@@ -2,7 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_layout.cuh"
 
 namespace effq {
 

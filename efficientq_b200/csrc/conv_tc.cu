@@ -24,6 +24,8 @@
 // Warp roles (320 threads): 0 weight TMA | 1 MMA issuer + TMEM owner | 2-5 epilogue |
 // 6-9 halo producers (cp.async, zero-fill for padding / ragged edges).
 #include "common.cuh"
+#include <stdlib.h>
+#include "tc_layout.cuh"
 
 namespace effq {
 
@@ -55,6 +57,8 @@ struct TcParams {
   unsigned int halo_bytes, wtile_bytes;
   unsigned int off_bias, off_halo, off_w;
   unsigned int tmem_cols;
+  int swz, rp, debug;          // operand swizzle width (128/64/32 B), row pitch, bring-up debug bits
+  unsigned int wstage_bytes;   // shared-memory stride between weight tiles (1024-aligned when swizzled)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -138,16 +142,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, no-swizzle ("interleaved") UMMA shared-memory descriptor.
-//   rows inside an 8-row core matrix are 16 B apart; sbo = bytes between 8-row groups
-//   (M/N direction); lbo = bytes between the two 8-element K chunks of one K=16 MMA.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// K-major swizzled descriptor: rows at the swizzle width (128/64/32 B), 8-row groups sbo apart,
+// K advances inside the row by adding bytes to the start address.
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t sbo_bytes, int swz, int) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)1 << 16;                                  // LBO unused for swizzled K-major
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;                  // descriptor version 1 (Blackwell)
-  return d;                                // base_offset 0, layout_type 0 = SWIZZLE_NONE
+  d |= (uint64_t)1 << 46;
+  // matrix base offset (bits 49-51) stays 0: the swizzle is a function of the absolute address
+  d |= (uint64_t)(swz == 128 ? 2 : (swz == 64 ? 4 : 6)) << 61;
+  return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
@@ -169,7 +174,8 @@ struct Pipe {
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024 B alignment
   // barrier block (8 B each): halo_full[4] halo_empty[4] w_full[8] w_empty[8] wres tmem_full[2] tmem_empty[2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const long long tile0 = blockIdx.x, tstep = gridDim.x;
+  const unsigned int tile0 = blockIdx.x, tstep = gridDim.x, n_tiles = (unsigned int)p.n_tiles;   // < 2^31 (host check)
   double err_acc = 0.0;
 
   if (warp == 0) {
@@ -215,63 +221,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         mbar_expect_tx(BAR(B_WRES), total);
         for (int g = 0; g < p.n_groups; ++g)
           for (int t = 0; t < p.taps; ++t) {
-            const __nv_bfloat16* src = p.wq + ((long long)t * (p.c1 / 8) + (long long)g * p.nch) * p.c2 * 8;
-            bulk_g2s(wsm0 + (uint32_t)(g * p.taps + t) * p.wtile_bytes, src, p.wtile_bytes, BAR(B_WRES));
+            const __nv_bfloat16* src = p.wq + ((long long)t * p.n_groups + g) * p.cg * p.c2;
+            bulk_g2s(wsm0 + (uint32_t)(g * p.taps + t) * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WRES));
           }
       } else {
         Pipe wp{0, 0};
         bool ok = true;
-        for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep)
+        for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep)
           for (int g = 0; g < p.n_groups && ok; ++g)
             for (int t = 0; t < p.taps; ++t) {
               if (!mbar_wait(BAR(B_WE + wp.stage), wp.phase ^ 1u, abort_flag)) { ok = false; break; }
               mbar_expect_tx(BAR(B_WF + wp.stage), p.wtile_bytes);
-              const __nv_bfloat16* src = p.wq + ((long long)t * (p.c1 / 8) + (long long)g * p.nch) * p.c2 * 8;
-              bulk_g2s(wsm0 + (uint32_t)wp.stage * p.wtile_bytes, src, p.wtile_bytes, BAR(B_WF + wp.stage));
+              const __nv_bfloat16* src = p.wq + ((long long)t * p.n_groups + g) * p.cg * p.c2;
+              bulk_g2s(wsm0 + (uint32_t)wp.stage * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WF + wp.stage));
               wp.advance(p.n_w_stages);
             }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one lane) =====
+    // ===== MMA issuer (one lane).  Only the 14-bit start-address field of a descriptor changes
+    // between MMAs, so both descriptors are a constant high word plus a running low word. =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(p.c2);
-      const uint32_t a_lbo = (uint32_t)p.hv * 16u, a_sbo = (uint32_t)p.wp * 16u;
-      const uint32_t b_lbo = (uint32_t)p.c2 * 16u, b_sbo = 128u;
+      const uint64_t a_tmpl = umma_desc_sw(0, (uint32_t)(p.wp * p.rp), p.swz, 0);
+      const uint64_t b_tmpl = umma_desc_sw(0, (uint32_t)(8 * p.rp), p.swz, 0);
       const int kk_n = p.cg / 16;
+      const uint32_t row16 = (uint32_t)p.rp >> 4;                 // row pitch in 16 B units
+      const uint32_t step_c = row16, step_b = (uint32_t)p.wp * row16, step_a = (uint32_t)(p.hh * p.wp) * row16;
+      const bool no_mma = (p.debug & 4) != 0;
       Pipe hp{0, 0}, wp{0, 0}, ap{0, 0};
       bool ok = true;
       if (p.w_resident) ok = mbar_wait(BAR(B_WRES), 0, abort_flag);
-      for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
+      for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
         if (!mbar_wait(BAR(B_TE + ap.stage), ap.phase ^ 1u, abort_flag)) { ok = false; break; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ap.stage * p.c2);
-        uint32_t first = 1;
+        uint32_t accum = 0;
         for (int g = 0; g < p.n_groups && ok; ++g) {
           if (!mbar_wait(BAR(B_HF + hp.stage), hp.phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
-          int t = 0;
-          for (int a = 0; a < p.kd && ok; ++a)
-            for (int b = 0; b < p.kh && ok; ++b)
-              for (int c = 0; c < p.kw; ++c, ++t) {
-                uint32_t wbase;
-                if (p.w_resident) {
-                  wbase = wsm0 + (uint32_t)(g * p.taps + t) * p.wtile_bytes;
-                } else {
+          const uint32_t h16 = (halo0 + (uint32_t)hp.stage * p.halo_bytes) >> 4;
+          uint32_t w16 = (wsm0 + (uint32_t)(g * p.taps) * p.wstage_bytes) >> 4;   // resident weights
+          uint32_t off_a = h16;
+          for (int a = 0; a < p.kd && ok; ++a, off_a += step_a) {
+            uint32_t off_b = off_a;
+            for (int b = 0; b < p.kh && ok; ++b, off_b += step_b) {
+              uint32_t off_c = off_b;
+              for (int c = 0; c < p.kw; ++c, off_c += step_c) {
+                if (!p.w_resident) {
                   if (!mbar_wait(BAR(B_WF + wp.stage), wp.phase, abort_flag)) { ok = false; break; }
                   tc_fence_after();
-                  wbase = wsm0 + (uint32_t)wp.stage * p.wtile_bytes;
+                  w16 = (wsm0 + (uint32_t)wp.stage * p.wstage_bytes) >> 4;
                 }
-                const uint32_t shift = (uint32_t)((a * p.hh + b) * p.wp + c) * 16u;
-                for (int kk = 0; kk < kk_n; ++kk) {
-                  const uint64_t ad = umma_desc(hbase + shift + (uint32_t)(2 * kk) * a_lbo, a_lbo, a_sbo);
-                  const uint64_t bd = umma_desc(wbase + (uint32_t)(2 * kk) * b_lbo, b_lbo, b_sbo);
-                  tc_mma_bf16(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-                  first = 0;
+                if (!no_mma) {
+#pragma unroll 4
+                  for (int kk = 0; kk < kk_n; ++kk) {
+                    tc_mma_bf16(d_tmem, a_tmpl | (uint64_t)((off_c + 2u * kk) & 0x3fffu),
+                                b_tmpl | (uint64_t)((w16 + 2u * kk) & 0x3fffu), idesc, accum);
+                    accum = 1;
+                  }
                 }
-                if (!p.w_resident) { tc_commit(BAR(B_WE + wp.stage)); wp.advance(p.n_w_stages); }
+                if (p.w_resident) {
+                  w16 += p.wstage_bytes >> 4;
+                } else {
+                  tc_commit(BAR(B_WE + wp.stage));
+                  wp.advance(p.n_w_stages);
+                }
               }
+            }
+          }
           tc_commit(BAR(B_HE + hp.stage));
           hp.advance(p.n_halo_stages);
         }
@@ -289,11 +307,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     const long long chan = (long long)p.d * plane;
     Pipe ap{0, 0};
     bool ok = true;
-    for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
-      long long r = tile;
-      const int tw = (int)(r % p.tiles_w); r /= p.tiles_w;
-      const int th = (int)(r % p.tiles_h); r /= p.tiles_h;
-      const int dd = (int)(r % p.d); r /= p.d;
+    for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
+      unsigned int r = tile;
+      const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
+      const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
+      const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
       const int nn = (int)r;
       const int oh = th * TC_TILE_H + hy, ow = tw * TC_TILE_W + wx;
       const bool live = oh < p.h && ow < p.w;
@@ -302,7 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       // Target values do not depend on the MMA: issue all loads of a 32-channel chunk before
       // anything consumes them (32 independent requests in flight per thread), the first chunk
       // even before waiting for the accumulator.
-      const bool want_t = live && p.target != nullptr;
+      const bool want_t = live && p.target != nullptr && !(p.debug & 2);
       float tv[32];
       auto load_targets = [&](int c0) {
 #pragma unroll
@@ -343,36 +361,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     }
   } else {
     // ===== halo producers: cp.async 16 B pieces, zero-fill outside the volume =====
-    const int pw_id = warp - 6;                  // 0..3
-    const int rows = p.kd * p.hh;
-    const int items = p.wp * p.nch;
-    const int nch_shift = p.nch == 8 ? 3 : (p.nch == 4 ? 2 : 1);
+    // The set of (halo voxel, chunk) items a thread copies is the same for every tile, so the
+    // shared-memory destination (with its swizzle), the global offset relative to the tile origin
+    // and the halo coordinates are computed ONCE; per tile an item costs three range checks, one
+    // 64-bit add and the cp.async.  Lanes walk (chunk fastest, then w): a warp's copies are
+    // contiguous runs in global memory (whole 32 B sectors) .
+    const int ptid = threadIdx.x - 6 * 32;                    // 0..127
+    const int used_w = TC_TILE_W + p.kw - 1;                  // halo columns actually read
+    const int cpi = p.nch > 4 ? p.nch / 4 : 1;                // chunks per item (nch = 8 -> 2)
+    const int ipv = p.nch / cpi;                              // items per voxel
+    const int n_items = p.kd * p.hh * used_w * ipv;
+    constexpr int MAX_IT = 17;                                // ceil(3*18*10*4 / 128)
+    int rel[MAX_IT];                                          // element offset from the tile origin
+    uint32_t dst[MAX_IT];                                     // byte offset inside the halo stage
+    uint32_t crd[MAX_IT];                                     // dz | hy << 4 | wx << 12 | valid << 20
+#pragma unroll
+    for (int i = 0; i < MAX_IT; ++i) {
+      const int it = ptid + i * TC_PRODUCERS;
+      rel[i] = 0; dst[i] = 0; crd[i] = 0;
+      if (it < n_items) {
+        const int q = it % ipv, vox = it / ipv;
+        const int wx = vox % used_w, rr = vox / used_w;
+        const int dz = rr / p.hh, hy = rr % p.hh;
+        const int hrow = rr * p.wp + wx;
+        const int j0 = q * cpi;
+        rel[i] = ((dz * p.h + hy) * p.w + wx) * p.c1 + j0 * 8;
+        dst[i] = (uint32_t)(hrow * p.rp) | ((uint32_t)tc_chunk_xor(hrow, p.swz) << 24) | ((uint32_t)j0 << 28);
+        crd[i] = (uint32_t)dz | ((uint32_t)hy << 4) | ((uint32_t)wx << 12) | (1u << 20);
+      }
+    }
     Pipe hp{0, 0};
     bool ok = true;
     bool pending = false;
     int pending_stage = 0;
-    for (long long tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
-      long long r = tile;
-      const int tw = (int)(r % p.tiles_w); r /= p.tiles_w;
-      const int th = (int)(r % p.tiles_h); r /= p.tiles_h;
-      const int dd = (int)(r % p.d); r /= p.d;
+    for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
+      unsigned int r = tile;
+      const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
+      const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
+      const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
       const int nn = (int)r;
       const int h0 = th * TC_TILE_H - p.ph, w0 = tw * TC_TILE_W - p.pw, d0 = dd - p.pd;
+      // pointer of halo voxel (0,0,0), channel 0 -- may lie outside the tensor, only dereferenced when valid
+      const __nv_bfloat16* origin = p.xq + ((((long long)nn * p.d + d0) * p.h + h0) * p.w + w0) * p.c1;
       for (int g = 0; g < p.n_groups; ++g) {
         if (!mbar_wait(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
         const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
-        for (int rr = pw_id; rr < rows; rr += 4) {
-          const int dz = rr / p.hh, hyy = rr - dz * p.hh;
-          const int gd = d0 + dz, gh = h0 + hyy;
-          const bool row_ok = (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h;
-          const __nv_bfloat16* rowp =
-              p.xq + ((((long long)nn * p.d + (row_ok ? gd : 0)) * p.h + (row_ok ? gh : 0)) * p.w) * p.c1 + g * p.cg;
-          for (int it = lane; it < items; it += 32) {
-            const int wxx = it >> nch_shift, j = it & (p.nch - 1);
-            const int gw = w0 + wxx;
-            const bool okk = row_ok && (unsigned)gw < (unsigned)p.w;
-            const __nv_bfloat16* src = okk ? rowp + (long long)gw * p.c1 + j * 8 : p.xq;
-            cp_async16(hbase + (uint32_t)((j * p.hv + rr * p.wp + wxx) * 16), src, okk ? 16u : 0u);
+        const __nv_bfloat16* gorigin = origin + g * p.cg;
+#pragma unroll
+        for (int i = 0; i < MAX_IT; ++i) {
+          const uint32_t c = crd[i];
+          if (c >> 20) {                                         // item exists (thread-uniform per i)
+            const int gd = d0 + (int)(c & 15u), gh = h0 + (int)((c >> 4) & 255u), gw = w0 + (int)((c >> 12) & 255u);
+            const bool okk = (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w;
+            const __nv_bfloat16* src = okk ? gorigin + rel[i] : p.xq;
+            const uint32_t rowb = hbase + (dst[i] & 0xffffffu);
+            const uint32_t x = (dst[i] >> 24) & 15u, j0 = dst[i] >> 28;
+            if (!(p.debug & 1)) {
+              cp_async16(rowb + (((j0) ^ x) << 4), src, okk ? 16u : 0u);
+              if (cpi == 2) cp_async16(rowb + (((j0 + 1) ^ x) << 4), src + 8, okk ? 16u : 0u);
+            }
           }
         }
         cp_async_commit();
@@ -435,20 +482,28 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
   p.cg = g.c1 < 64 ? g.c1 : 64;
   p.n_groups = g.c1 / p.cg;
   p.nch = p.cg / 8;
+  const TcLayout lay = tc_layout(g.c1);
+  p.swz = lay.swz;
+  p.rp = lay.rp;
+  static const int dbg_env = [] { const char* v = getenv("EFFQ_TC_DEBUG"); return (v && *v) ? atoi(v) : 0; }();
+  p.debug = dbg_env;
   p.hh = TC_TILE_H + g.kh - 1;
   p.wp = TC_TILE_W + g.kw - 1;
+  // NB halo rows are NOT padded to the 8-row swizzle period: the hardware applies the XOR to the
+  // absolute shared-memory address (verified on B200, profiles/r01_conv_layout.md), so a
+  // descriptor may start at any row and 8-row groups may start at any phase; base_offset stays 0.
   p.hv = g.kd * p.hh * p.wp;
   p.tiles_h = (g.h + TC_TILE_H - 1) / TC_TILE_H;
   p.tiles_w = (g.w + TC_TILE_W - 1) / TC_TILE_W;
   p.n_tiles = (long long)g.n * g.d * p.tiles_h * p.tiles_w;
-  // +16 B: the last tap's descriptor of the last 8-row group may touch one slot past the block
-  p.halo_bytes = (uint32_t)(p.nch * p.hv * 16);
-  p.halo_bytes = (p.halo_bytes + 127u) & ~127u;
+  p.halo_bytes = (uint32_t)(p.hv * p.rp);
+  p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
   p.wtile_bytes = (uint32_t)(p.cg * g.c2 * 2);
+  p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
   p.off_bias = 256;
-  p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 127u) & ~127u;
-  const uint32_t budget = 220u * 1024u;
-  const uint32_t w_all = p.wtile_bytes * (uint32_t)(p.n_groups * p.taps);
+  p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
+  const uint32_t budget = 224u * 1024u;
+  const uint32_t w_all = p.wstage_bytes * (uint32_t)(p.n_groups * p.taps);
   p.n_halo_stages = 2;
   if (p.off_halo + 2u * p.halo_bytes + w_all <= budget) {
     p.w_resident = 1;
@@ -459,9 +514,9 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
     p.off_w = p.off_halo + (uint32_t)p.n_halo_stages * p.halo_bytes;
   } else {
     p.w_resident = 0;
-    p.off_w = p.off_halo + 2u * p.halo_bytes;
-    if (p.off_w + 2u * p.wtile_bytes > budget) return false;
-    int ws = (int)((budget - p.off_w) / p.wtile_bytes);
+    p.off_w = p.off_halo + 2u * p.halo_bytes;       // the producer pipeline needs >= 2 halo stages
+    if (p.off_w + 2u * p.wstage_bytes > budget) return false;
+    int ws = (int)((budget - p.off_w) / p.wstage_bytes);
     p.n_w_stages = ws > 8 ? 8 : ws;
   }
   uint32_t cols = 32;
@@ -471,9 +526,9 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
 }
 
 static uint32_t tc_smem_bytes(const TcParams& p) {
-  const uint32_t w = p.w_resident ? p.wtile_bytes * (uint32_t)(p.n_groups * p.taps)
-                                  : p.wtile_bytes * (uint32_t)p.n_w_stages;
-  return p.off_w + w + 128u;
+  const uint32_t w = p.w_resident ? p.wstage_bytes * (uint32_t)(p.n_groups * p.taps)
+                                  : p.wstage_bytes * (uint32_t)p.n_w_stages;
+  return p.off_w + w + 1024u;      // + slack for the manual 1024 B alignment of the base
 }
 
 }  // namespace effq
@@ -498,6 +553,7 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const floa
   EFFQ_CHECK_ARG(((uintptr_t)xcodes & 15) == 0 && ((uintptr_t)wcodes & 15) == 0, "operands must be 16B aligned");
   TcParams p;
   EFFQ_CHECK_ARG(tc_plan(*g, p), "geometry not supported by the tcgen05 path");
+  EFFQ_CHECK_ARG(p.n_tiles < (1ll << 31), "too many tiles");
   p.xq = (const __nv_bfloat16*)xcodes;
   p.wq = (const __nv_bfloat16*)wcodes;
   p.bias = bias;

@@ -165,12 +165,15 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
   int parity = 0;
 
   double vreg[REG_ITEMS > 0 ? REG_ITEMS : 1];
+  int nvalid = 0;                      // this thread owns elements k = 0 .. nvalid-1 (strided, so a prefix)
   if (REG_ITEMS > 0) {
     const long long stride = (long long)nctas * SS_THREADS;
     long long i = (long long)blockIdx.x * SS_THREADS + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < REG_ITEMS; ++k, i += stride)
-      vreg[k] = i < numel ? (double)load_v(vv, i / vv.cols, i % vv.cols) : 0.0;   // 0 adds nothing to any sum
+    for (int k = 0; k < REG_ITEMS; ++k, i += stride) {
+      vreg[k] = 0.0;
+      if (i < numel) { vreg[k] = (double)load_v(vv, i / vv.cols, i % vv.cols); nvalid = k + 1; }
+    }
   }
 
   // pass "-1": a0 = mean|v|
@@ -198,7 +201,8 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
       s0 = 0.0;
       s1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < REG_ITEMS; ++k) accum_bv(vreg[k], pq, s0, s1);
+      for (int k = 0; k < REG_ITEMS; ++k)
+        if (k < nvalid) accum_bv(vreg[k], pq, s0, s1);     // padding must not count: Q(0) != 0 on symmetric grids
     } else {
       pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
     }

@@ -271,12 +271,14 @@ def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, 
 
 
 def pack_weight_codes(wcodes_int: torch.Tensor) -> torch.Tensor:
-    """[C2][C1][kd][kh][kw] integer codes (already 2c-(L-1)) -> [tap][C1/8][C2][8] bf16.
-    Test/bring-up helper; the production path gets this layout from effq_admm_project."""
-    c2, c1 = wcodes_int.shape[:2]
-    taps = wcodes_int[0, 0].numel()
-    t = wcodes_int.reshape(c2, c1 // 8, 8, taps).permute(3, 1, 0, 2).contiguous()
-    return t.to(torch.bfloat16)
+    """[C2][C1][kd][kh][kw] integer codes (already 2c-(L-1)) on the GPU -> bf16 codes in the
+    tensor-core weight layout (the layout effq_admm_project emits during calibration)."""
+    w = _f32c(wcodes_int.float(), "wcodes")
+    c2, c1 = w.shape[:2]
+    taps = w[0, 0].numel()
+    out = torch.empty(c2 * c1 * taps, dtype=torch.bfloat16, device=w.device)
+    check(capi.load().effq_pack_wcodes(ptr(w), c2, c1, taps, ptr(out), stream()), "effq_pack_wcodes")
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -23,7 +23,9 @@
  *   activations fp32 : NCDHW (the reference's / PyTorch's native layout)
  *   activation codes : N,D,H,W,C  bf16 (channels-last-3d), integer values 0..L-1
  *   weights fp32     : [C2][C1][kd][kh][kw]  (== reference weight.reshape(C2,-1))
- *   weight codes     : [tap][C1/8][C2][8] bf16, values 2c-(L-1) (odd integers)
+ *   weight codes     : bf16 values 2c-(L-1) (odd integers), [tap][C1/CG][C2][CG] with
+ *                      CG = min(C1,64) and the 16-byte chunks of every row pre-swizzled
+ *                      for the UMMA 128/64/32-byte swizzle (csrc/tc_layout.cuh)
  *   normal equations : K' = C1*kd*kh*kw (+1 bias slot last), row order (c,kd,kh,kw)
  *                      exactly as reference src/models/solver.py:104-108.
  */
@@ -137,6 +139,10 @@ int64_t effq_conv3d_tc_workspace(const effq_geom* g);
 int effq_conv3d_tc(const void* xcodes_ndhwc_bf16, const void* wcodes_bf16, const float* bias,
                    const float* conv_scale, const effq_geom* g, float* out, const float* target,
                    const float* att, double* sse, void* workspace, void* stream);
+
+/* [C2][C1][taps] fp32 integer weight codes (values 2c-(L-1)) -> bf16 codes in the layout
+ * effq_conv3d_tc consumes (the same layout effq_admm_project emits). */
+int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int32_t taps, void* out, void* stream);
 
 /* ---- (a7+a8) normal-equation statistics: solver.py:86-111, :282-314 ---------- */
 /* A0 = 2 X^ diag(att) X^T (K' x K'), B0 = 2 Y diag(att) X^T (C2 x K'), X^ the

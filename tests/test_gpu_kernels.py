@@ -194,7 +194,7 @@ def test_conv3d_tc_exact_on_codes(ops, n, c1, c2, k, sp, la, lw):
     target = want + 0.1 * torch.randn_like(want)
     att = torch.rand(n, *sp) + 0.5
     xq = xc.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
-    wq = ops.pack_weight_codes(wc).to(DEV)
+    wq = ops.pack_weight_codes(wc.to(DEV))
     cs = torch.tensor([scale], dtype=torch.float32, device=DEV)
     out, sse = ops.conv3d_tc(xq, wq, b.to(DEV), cs, c2, k, want_out=True, target=target.to(DEV), att=att.to(DEV))
     torch.cuda.synchronize()
@@ -290,7 +290,7 @@ def test_admm_elementwise_kernels(ops):
     assert torch.equal(dual_d.cpu(), dual_ref)
     assert torch.equal(bstar.cpu(), sol[:, k])
     codes_ref = (2 * O.discretize_codes((sol[:, :k] + dual).double() / a_w, 16, -1, 1) - 15).float()
-    assert torch.equal(wcodes.cpu().float(), ops.pack_weight_codes(codes_ref.view(c2, c1, 3, 3, 3)).float().flatten())
+    assert torch.equal(wcodes.cpu().float(), ops.pack_weight_codes(codes_ref.view(c2, c1, 3, 3, 3).to(DEV)).cpu().float().flatten())
     s = st.read()
     assert abs(s["a_w"] - np.float32(a_w)) == 0
     want_cs = np.float32(np.float64(np.float32(2.5)) / 15 * np.float64(np.float32(a_w)) / 15)

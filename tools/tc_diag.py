@@ -20,7 +20,7 @@ def run(tag, xc, wc, k, scale=1.0, bias=None):
     if bias is not None:
         want = want + bias.view(1, -1, 1, 1, 1)
     xq = xc.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
-    wq = ops.pack_weight_codes(wc).to(DEV)
+    wq = ops.pack_weight_codes(wc.to(DEV))
     cs = torch.tensor([scale], dtype=torch.float32, device=DEV)
     ws = ops.workspace(16 + 8 * 1024, torch.device(DEV))
     t0 = time.time()
@@ -49,7 +49,7 @@ def run(tag, xc, wc, k, scale=1.0, bias=None):
 
 def main():
     torch.manual_seed(0)
-    print(torch.cuda.get_device_name(0))
+    print(torch.cuda.get_device_name(0), {k: v for k, v in os.environ.items() if k.startswith("EFFQ_")})
     ok = True
     for c1, c2 in [(32, 32), (64, 64), (16, 16)]:
         sp = (2, 16, 8)
@@ -80,6 +80,26 @@ def main():
     w = (2 * torch.randint(0, 16, (256, 256, 3, 3, 3)) - 15).float()
     ok &= run("k3 rand c256->256", x, w, 3, 0.01, torch.randn(256))
     print("ALL OK" if ok else "SOME FAILED")
+    # throughput of the scoring call (no output written) at level-1 / level-2 shapes
+    for c, sp, n in [(32, (64, 64, 64), 8), (64, (32, 32, 32), 32), (128, (16, 16, 16), 32)]:
+        xq = torch.randint(0, 16, (n, *sp, c), device=DEV).to(torch.bfloat16)
+        w = (2 * torch.randint(0, 16, (c, c, 3, 3, 3), device=DEV) - 15).float()
+        wq = ops.pack_weight_codes(w)
+        tgt = torch.randn(n, c, *sp, device=DEV)
+        cs = torch.ones(1, device=DEV)
+        ws = ops.workspace(16 + 8 * 1024, torch.device(DEV))
+        sse = torch.zeros(1, dtype=torch.float64, device=DEV)
+        for _ in range(3):
+            ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=tgt, ws=ws, sse=sse)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=tgt, ws=ws, sse=sse)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = 2.0 * n * sp[0] * sp[1] * sp[2] * c * c * 27
+        print(f"[perf c{c} {n}x{sp}] {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":

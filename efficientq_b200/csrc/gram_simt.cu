@@ -70,12 +70,12 @@ __device__ __forceinline__ float fetch(const RowDesc& rd, const VoxPos& p, const
 
 __global__ void __launch_bounds__(GM_THREADS)
 gram_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ att,
-                effq_geom g, OutDims o, int k, int kp, int mrows, long long vox_per_split,
+                effq_geom g, OutDims o, int k, int kp, int mrows, int row_begin, long long vox_per_split,
                 double* __restrict__ acc64) {
   __shared__ float Ls[GM_KC][GM_TILE + 4];
   __shared__ float Rs[GM_KC][GM_TILE + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int i0 = blockIdx.y * GM_TILE, j0 = blockIdx.x * GM_TILE;
+  const int i0 = row_begin + blockIdx.y * GM_TILE, j0 = blockIdx.x * GM_TILE;
   const long long v_begin = (long long)blockIdx.z * vox_per_split;
   const long long v_end = min(o.vox, v_begin + vox_per_split);
 
@@ -155,13 +155,23 @@ gram_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
   }
 }
 
+// tc_block != 0: the K x K block was accumulated on integer codes by the tcgen05 kernel and
+// needs code_scale^2; the rows >= K (ones row, Y rows) were accumulated on real values; the
+// bias column of the first K rows is mirrored from the ones row (A0 is symmetric).
 __global__ void gram_finalize_kernel(const double* __restrict__ acc64, const float* __restrict__ x_scale,
-                                     int k, int kp, int c2, float* __restrict__ a0, float* __restrict__ b0) {
+                                     int k, int kp, int c2, int tc_block, float* __restrict__ a0,
+                                     float* __restrict__ b0) {
   const double s = x_scale ? (double)__ldg(x_scale) : 1.0;
   const long long total = (long long)(kp + c2) * kp;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / kp), j = (int)(e % kp);
+    if (tc_block) {
+      if (i < k) a0[e] = j < k ? (float)(2.0 * s * s * acc64[e]) : (float)(2.0 * acc64[(long long)k * kp + i]);
+      else if (i < kp) a0[e] = (float)(2.0 * acc64[e]);
+      else b0[(long long)(i - kp) * kp + j] = (float)(2.0 * acc64[e]);
+      continue;
+    }
     const double sj = j < k ? s : 1.0;
     if (i < kp) {
       const double si = i < k ? s : 1.0;
@@ -178,8 +188,28 @@ extern "C" int64_t effq_gram_workspace(const effq_geom* g, int32_t has_bias) {
   if (!g) return 0;
   const long long k = (long long)g->c1 * g->kd * g->kh * g->kw;
   const long long kp = k + (has_bias ? 1 : 0);
-  return (int64_t)((kp + g->c2) * kp * 8);
+  return (int64_t)((kp + g->c2) * kp * 8 + 16);      // fp64 accumulator + abort flag
 }
+
+namespace effq {
+// Launches the generic kernel for rows [row_begin, mrows) of [Xhat ; Y] against att.Xhat.
+static int launch_gram_rows(const float* x, const float* y, const float* att, const effq_geom& g, const OutDims& o,
+                            int k, int kp, int mrows, int row_begin, double* acc, cudaStream_t s) {
+  const int tx = (kp + GM_TILE - 1) / GM_TILE, ty = (mrows - row_begin + GM_TILE - 1) / GM_TILE;
+  long long splits = ((long long)sm_count() * 6 + (long long)tx * ty - 1) / ((long long)tx * ty);
+  const long long max_splits = (o.vox + 511) / 512;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  long long per = (o.vox + splits - 1) / splits;
+  per = (per + GM_KC - 1) / GM_KC * GM_KC;
+  splits = (o.vox + per - 1) / per;
+  dim3 grid(tx, ty, (unsigned)splits);
+  gram_f32_kernel<<<grid, GM_THREADS, 0, s>>>(x, y, att, g, o, k, kp, mrows, row_begin, per, acc);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace effq
 
 extern "C" int effq_gram_f32(const float* x, const float* x_scale, const float* y, const float* att,
                              const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out,
@@ -191,24 +221,43 @@ extern "C" int effq_gram_f32(const float* x, const float* x_scale, const float* 
   const int k = g->c1 * g->kd * g->kh * g->kw;
   const int kp = k + (has_bias ? 1 : 0);
   const int mrows = kp + g->c2;
-  const int tx = (kp + GM_TILE - 1) / GM_TILE, ty = (mrows + GM_TILE - 1) / GM_TILE;
-  long long splits = ((long long)sm_count() * 6 + (long long)tx * ty - 1) / ((long long)tx * ty);
-  const long long max_splits = (o.vox + 511) / 512;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
-  long long per = (o.vox + splits - 1) / splits;
-  per = (per + GM_KC - 1) / GM_KC * GM_KC;
-  splits = (o.vox + per - 1) / per;
   cudaStream_t s = (cudaStream_t)stream;
   EFFQ_CUDA(cudaMemsetAsync(workspace, 0, (size_t)mrows * kp * 8, s));
-  dim3 grid(tx, ty, (unsigned)splits);
-  gram_f32_kernel<<<grid, GM_THREADS, 0, s>>>(x, y, att, *g, o, k, kp, mrows, per, (double*)workspace);
-  EFFQ_LAUNCH_CHECK();
+  if (int rc = launch_gram_rows(x, y, att, *g, o, k, kp, mrows, 0, (double*)workspace, s)) return rc;
   const long long total = (long long)mrows * kp;
   int fb = (int)((total + 255) / 256);
   if (fb > sm_count() * 16) fb = sm_count() * 16;
-  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, x_scale, k, kp, g->c2, a0_out, b0_out);
+  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, x_scale, k, kp, g->c2, 0, a0_out, b0_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const effq_geom* g,
+                                       double* acc64, int32_t ld, void* flags, void* stream);
+extern "C" int effq_gram_tc_supported(const effq_geom* g);
+
+// Tensor-core path: K x K block from integer codes (tcgen05), bias row / column and B0 from the
+// generic kernel on the real-valued activations `x_values` (same tensor the codes came from).
+extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* x_values,
+                            const float* y, const float* att, const effq_geom* g, int32_t has_bias,
+                            float* a0_out, float* b0_out, void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && code_scale && x_values && y && g && a0_out && b0_out && workspace, "null pointer");
+  EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
+  const OutDims o = out_dims(*g);
+  const int k = g->c1 * 27;
+  const int kp = k + (has_bias ? 1 : 0);
+  const int mrows = kp + g->c2;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t acc_bytes = (size_t)mrows * kp * 8;
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, acc_bytes + 16, s));
+  if (int rc = effq_gram_tc_accumulate(xcodes_ndhwc_bf16, att, g, (double*)workspace, kp,
+                                       (char*)workspace + acc_bytes, stream)) return rc;
+  if (int rc = launch_gram_rows(x_values, y, att, *g, o, k, kp, mrows, k, (double*)workspace, s)) return rc;
+  const long long total = (long long)mrows * kp;
+  int fb = (int)((total + 255) / 256);
+  if (fb > sm_count() * 16) fb = sm_count() * 16;
+  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, code_scale, k, kp, g->c2, 1, a0_out, b0_out);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

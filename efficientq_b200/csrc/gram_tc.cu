@@ -1,0 +1,372 @@
+// tcgen05 implicit-GEMM for the im2col Gram matrix of a 3x3x3 / stride-1 / pad-1 layer with
+// quantised activations:      S[i][j] = sum_v att_v * xhat_i(v) * xhat_j(v),   i, j < K = 27*C1
+// (the K x K block of A0 = 2*S of reference src/models/solver.py:282-314; the bias row/column
+// and B0 come from the generic kernel in gram_simt.cu).  The im2col matrix is never formed.
+//
+// GEMM view: M = 128 rows i, N = 256 rows j, reduction over output voxels (K dim = voxels).
+// Row index order inside this kernel is tap-major, i = tap*C1 + c, so that 8 consecutive rows
+// are the 8 channels of one 16-byte NDHWC vector; results are scattered to the reference's
+// (c, tap) order in the epilogue.
+//
+//   * operand tiles are built by 8 "builder" warps straight from global memory (NDHWC bf16
+//     codes, 128-bit loads through L1, zero for padding): each 16-byte vector is the codes of
+//     8 consecutive rows at one voxel, i.e. one chunk of an MN-major, 128B-swizzled UMMA tile
+//     [64-row block][voxel][64 rows].  L1 serves the 27-fold tap reuse of a voxel block.
+//   * the left operand carries the attention weight: p = att_v * code (fp32), split into
+//     bf16 hi + bf16 lo (two MMAs, error <= 2^-17 per term, exact for the reference's integer
+//     masks); the right operand is the raw integer code (exact).
+//   * one thread issues tcgen05.mma M=128,N=256,K=16 (both operands MN-major) -- the only
+//     shape at which the SS tensor pipe is not starved by the A-operand read (B200: one A row
+//     per cycle, profiles/r01_conv_layout.md) -- into a 128x256 fp32 TMEM accumulator.
+//   * a work item = (128-row block, 256-row block, voxel range of <= 32768 voxels): fp32
+//     accumulation stays exact / short; the epilogue adds the tile into an fp64 workspace
+//     with atomics (deterministic to fp32 after the final rounding).
+#include "common.cuh"
+#include "tc_layout.cuh"
+
+namespace effq {
+
+constexpr int GT_BUILDERS = 256;           // 8 warps
+constexpr int GT_THREADS = GT_BUILDERS + 32;
+constexpr int GT_STAGES = 2;
+constexpr int GT_KV = 64;                  // voxels per stage: 8 h-rows x 8 w
+constexpr int GT_BM = 128, GT_BN = 256;
+constexpr uint32_t GT_ZBYTES = 2 * GT_KV * 128;      // 128 rows = 2 blocks of 64 rows: 16 KB
+constexpr uint32_t GT_PBYTES = 4 * GT_KV * 128;      // 256 rows: 32 KB
+constexpr uint32_t GT_STAGE_BYTES = 2 * GT_ZBYTES + GT_PBYTES;   // Zhi, Zlo, P = 64 KB
+constexpr unsigned int GT_SPIN_LIMIT = 1u << 26;
+
+struct GtParams {
+  const __nv_bfloat16* xq;     // NDHWC codes
+  const float* att;            // N,D,H,W or null
+  double* acc;                 // fp64 workspace, leading dimension ld (reference row order)
+  unsigned int* flags;         // [0] abort
+  int n, c1, d, h, w;
+  int k;                       // 27 * c1
+  int ld;
+  int mb_n, nb_n, splits;      // work decomposition
+  int hb_h, hb_w;              // 8x8 voxel blocks per plane (ceil)
+  long long hb_total;          // n*d*hb_h*hb_w
+  long long hb_per_split;
+};
+
+__device__ __forceinline__ uint32_t gt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gt_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void gt_mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool gt_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool gt_mbar_wait(uint32_t bar, uint32_t parity, volatile unsigned int* abort_flag) {
+  unsigned int spins = 0;
+  while (!gt_mbar_try(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0) {
+      if (*abort_flag != 0u) return false;
+      if (spins > GT_SPIN_LIMIT) { *abort_flag = 1u; __threadfence(); return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void gt_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gt_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void gt_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+
+// MN-major, 128B-swizzled UMMA descriptor: 64 rows contiguous (128 B), K (voxel) rows at
+// 128 B, 8-voxel groups sbo apart, 64-row blocks lbo apart.
+__device__ __forceinline__ uint64_t gt_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+struct Slot {
+  int rel;          // element offset of the tap-shifted vector relative to the voxel's own vector
+  int tap;          // (a) | (b << 2) | (c << 4) | valid << 6      (a,b,c in 0..2)
+  uint32_t dst;     // byte offset inside the stage (Zhi / P region), swizzle applied
+};
+
+__device__ __forceinline__ Slot make_slot(int row0, int rc, int kvox, int c1, int k, int h, int w, bool is_p) {
+  Slot s;
+  const int r = row0 + rc * 8;
+  s.tap = 0;
+  s.rel = 0;
+  if (r < k) {
+    const int tap = r / c1, c0 = r % c1;
+    const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+    s.rel = (((a - 1) * h + (b - 1)) * w + (c - 1)) * c1 + c0;
+    s.tap = a | (b << 2) | (c << 4) | (1 << 6);
+  }
+  const uint32_t blk = (uint32_t)(rc >> 3), ch = (uint32_t)(rc & 7);
+  s.dst = blk * (GT_KV * 128u) + (uint32_t)kvox * 128u + ((ch ^ (uint32_t)(kvox & 7)) << 4);
+  (void)is_p;
+  return s;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p) {
+  extern __shared__ __align__(1024) uint8_t gsm_raw[];
+  uint8_t* gsm = gsm_raw + ((1024u - (gt_smem_u32(gsm_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bars[2 * GT_STAGES + 2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar0 = gt_smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(GT_STAGES + s); };
+  const uint32_t TFULL = bar0 + 8u * (2 * GT_STAGES), TEMPTY = bar0 + 8u * (2 * GT_STAGES + 1);
+  const uint32_t stage0 = gt_smem_u32(gsm);
+  volatile unsigned int* abort_flag = p.flags;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(FULL(s), GT_BUILDERS); gt_mbar_init(EMPTY(s), 1); }
+    gt_mbar_init(TFULL, 1);
+    gt_mbar_init(TEMPTY, GT_BUILDERS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem_u32(&tmem_slot)),
+                 "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  const long long n_items = (long long)p.mb_n * p.nb_n * p.splits;
+
+  if (warp == 8) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t idesc = 0;
+      idesc |= 1u << 4;                       // D = f32
+      idesc |= 1u << 7;                       // A = bf16
+      idesc |= 1u << 10;                      // B = bf16
+      idesc |= 1u << 15;                      // A MN-major
+      idesc |= 1u << 16;                      // B MN-major
+      idesc |= (uint32_t)(GT_BN >> 3) << 17;
+      idesc |= (uint32_t)(GT_BM >> 4) << 24;
+      const uint64_t tmpl = gt_desc(0, GT_KV * 128u, 1024u);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
+        const int z = (int)(item % p.splits);
+        long long hb0 = (long long)z * p.hb_per_split;
+        long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
+        if (!gt_mbar_wait(TEMPTY, tphase ^ 1u, abort_flag)) { ok = false; break; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t accum = 0;
+        for (long long hb = hb0; hb < hb1; ++hb) {
+          if (!gt_mbar_wait(FULL(stage), phase, abort_flag)) { ok = false; break; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t zhi = (stage0 + (uint32_t)stage * GT_STAGE_BYTES) >> 4;
+          const uint32_t zlo = zhi + (GT_ZBYTES >> 4), pp = zhi + ((2 * GT_ZBYTES) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < GT_KV / 16; ++ks) {
+            const uint32_t koff = (uint32_t)ks * (16u * 128u >> 4);
+            const uint64_t bd = tmpl | (uint64_t)((pp + koff) & 0x3fffu);
+            gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, accum);
+            gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
+            accum = 1;
+          }
+          gt_commit(EMPTY(stage));
+          if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (ok) gt_commit(TFULL);
+        tphase ^= 1u;
+      }
+    }
+  } else {
+    // ===== builders (also the epilogue) =====
+    const int t = threadIdx.x;                       // 0..255
+    const int kvox = t & (GT_KV - 1);                // this thread's voxel inside every stage
+    const int vy = kvox >> 3, vx = kvox & 7;
+    const int rc_base = t >> 6;                      // 0..3
+    int stage = 0;
+    uint32_t phase = 0, tphase = 0;
+    bool ok = true;
+    const long long plane = (long long)p.h * p.w;
+    for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
+      long long r = item;
+      const int z = (int)(r % p.splits); r /= p.splits;
+      const int nb = (int)(r % p.nb_n); r /= p.nb_n;
+      const int mb = (int)r;
+      Slot zs[4], ps[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + 4 * i, kvox, p.c1, p.k, p.h, p.w, false);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + 4 * i, kvox, p.c1, p.k, p.h, p.w, true);
+      long long hb0 = (long long)z * p.hb_per_split;
+      long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
+      for (long long hb = hb0; hb < hb1; ++hb) {
+        long long q = hb;
+        const int bw = (int)(q % p.hb_w); q /= p.hb_w;
+        const int bh = (int)(q % p.hb_h); q /= p.hb_h;
+        const int dd = (int)(q % p.d); q /= p.d;
+        const int nn = (int)q;
+        const int vh = bh * 8 + vy, vw = bw * 8 + vx;
+        const bool vlive = vh < p.h && vw < p.w;
+        const long long vidx = ((long long)nn * p.d + dd) * plane + (long long)vh * p.w + vw;
+        const __nv_bfloat16* vptr = p.xq + vidx * p.c1;
+        const float aw = vlive ? (p.att ? __ldg(p.att + vidx) : 1.f) : 0.f;
+        // gather first (loads in flight), then wait for the stage, then write
+        uint4 zv[4], pv[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tp = zs[i].tap;
+          const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
+          const bool okk = vlive && (tp >> 6) && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h &&
+                           (unsigned)gw < (unsigned)p.w;
+          zv[i] = okk ? __ldg(reinterpret_cast<const uint4*>(vptr + zs[i].rel)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int tp = ps[i].tap;
+          const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
+          const bool okk = vlive && (tp >> 6) && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h &&
+                           (unsigned)gw < (unsigned)p.w;
+          pv[i] = okk ? __ldg(reinterpret_cast<const uint4*>(vptr + ps[i].rel)) : make_uint4(0, 0, 0, 0);
+        }
+        if (!gt_mbar_wait(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
+        uint8_t* sbase = gsm + (size_t)stage * GT_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t wds[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float c0 = __uint_as_float(wds[e] << 16), c1 = __uint_as_float(wds[e] & 0xffff0000u);
+            const float p0 = c0 * aw, p1 = c1 * aw;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(p0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(p1 - __bfloat162float(h1));
+            hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          *reinterpret_cast<uint4*>(sbase + zs[i].dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sbase + 2 * GT_ZBYTES + ps[i].dst) = pv[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        gt_mbar_arrive(FULL(stage));
+        if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (!ok) break;
+      // ---- epilogue of the item: TMEM tile -> fp64 workspace (reference row order) ----
+      if (!gt_mbar_wait(TFULL, tphase, abort_flag)) { ok = false; break; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tphase ^= 1u;
+      const int qd = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half
+      const int ri = mb * GT_BM + qd * 32 + lane;        // tap-major row index
+      const bool row_ok = ri < p.k;
+      const int ref_i = row_ok ? (ri % p.c1) * 27 + ri / p.c1 : 0;
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        uint32_t v[32];
+        gt_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cj = nb * GT_BN + c0 + j;
+            const float val = __uint_as_float(v[j]);
+            if (cj < p.k && val != 0.f) {
+              const int ref_j = (cj % p.c1) * 27 + cj / p.c1;
+              atomicAdd(p.acc + (long long)ref_i * p.ld + ref_j, (double)val);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      gt_mbar_arrive(TEMPTY);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+}  // namespace effq
+
+extern "C" int effq_gram_tc_supported(const effq_geom* g) {
+  if (!g) return 0;
+  const bool k3 = g->kd == 3 && g->kh == 3 && g->kw == 3 && g->pd == 1 && g->ph == 1 && g->pw == 1 &&
+                  g->sd == 1 && g->sh == 1 && g->sw == 1;
+  return (k3 && g->c1 % 8 == 0 && g->c1 >= 8 && g->c1 <= 512) ? 1 : 0;
+}
+
+// Accumulates S (K x K block, reference row order, NOT yet scaled by 2 or the code scale)
+// into acc64[ld * i + j] (+=).  acc64 must have been zeroed by the caller.
+extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const effq_geom* g,
+                                       double* acc64, int32_t ld, void* flags, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && g && acc64 && flags, "null pointer");
+  EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
+  EFFQ_CHECK_ARG(((uintptr_t)xcodes_ndhwc_bf16 & 15) == 0, "codes must be 16B aligned");
+  GtParams p;
+  p.xq = (const __nv_bfloat16*)xcodes_ndhwc_bf16;
+  p.att = att;
+  p.acc = acc64;
+  p.flags = (unsigned int*)flags;
+  p.n = g->n; p.c1 = g->c1; p.d = g->d; p.h = g->h; p.w = g->w;
+  p.k = 27 * g->c1;
+  p.ld = ld;
+  p.mb_n = (p.k + GT_BM - 1) / GT_BM;
+  p.nb_n = (p.k + GT_BN - 1) / GT_BN;
+  p.hb_h = (g->h + 7) / 8;
+  p.hb_w = (g->w + 7) / 8;
+  p.hb_total = (long long)g->n * g->d * p.hb_h * p.hb_w;
+  // <= 512 voxel blocks (32768 voxels) per item keeps the fp32 TMEM accumulation short; at
+  // least ~4 waves of items so the persistent grid balances
+  long long splits = (p.hb_total + 511) / 512;
+  const long long tiles = (long long)p.mb_n * p.nb_n;
+  const long long want = ((long long)sm_count() * 4 + tiles - 1) / tiles;
+  if (splits < want) splits = want;
+  if (splits > p.hb_total) splits = p.hb_total;
+  if (splits < 1) splits = 1;
+  p.hb_per_split = (p.hb_total + splits - 1) / splits;
+  splits = (p.hb_total + p.hb_per_split - 1) / p.hb_per_split;
+  p.splits = (int)splits;
+  const size_t smem = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long items = tiles * splits;
+  const int ctas = (int)(items < sm_count() ? items : sm_count());
+  gram_tc_kernel<<<ctas, GT_THREADS, smem, (cudaStream_t)stream>>>(p);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}

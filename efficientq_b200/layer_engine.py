@@ -144,7 +144,13 @@ class LayerCalibrator:
             qx = x
 
         # normal-equation statistics (solver.py:253-272), summed over shards
-        a0, b0 = ops.gram(qx, out_fp, att, ksize, stride, padding, has_bias=has_bias, ws=self.gram_ws)
+        gram_flag = None
+        if use_tc and ops.gram_tc_supported(x.shape, c2, ksize, stride, padding):
+            code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
+            a0, b0, self.gram_ws, gram_flag = ops.gram_tc(xcodes, code_scale, qx, out_fp, att, has_bias=has_bias,
+                                                          ws=self.gram_ws)
+        else:
+            a0, b0 = ops.gram(qx, out_fp, att, ksize, stride, padding, has_bias=has_bias, ws=self.gram_ws)
         if dist.world > 1:
             dist.all_reduce_sum(a0)
             dist.all_reduce_sum(b0)
@@ -222,6 +228,8 @@ class LayerCalibrator:
         final_sse = float(self.sse.item())
         if final_sse != final_sse:
             raise ops.EffqError(f"{name}: tcgen05 conv aborted (barrier timeout)")
+        if gram_flag is not None and int(gram_flag.item()) != 0:
+            raise ops.EffqError(f"{name}: tcgen05 Gram kernel aborted (barrier timeout)")
         rep.final_loss = final_sse / numel_total
         rep.best_loss, rep.best_iter, rep.alpha_w = s["best_loss"], s["best_iter"], s["a_w"]
         if q_act:

@@ -308,6 +308,36 @@ def gram(x, y, att, ksize, stride, padding, has_bias=True, x_scale=None, ws=None
     return a0, b0
 
 
+def gram_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
+    g = Geom.make(x_shape, c2, ksize, stride, padding)
+    return bool(capi.load().effq_gram_tc_supported(C.byref(g)))
+
+
+def gram_tc(xcodes, code_scale, x_values, y, att, has_bias=True, ws=None):
+    """A0, B0 with the K x K block on the tensor cores (3x3x3, stride 1, pad 1)."""
+    x_values = _f32c(x_values, "x_values")
+    y = _f32c(y, "y")
+    g = Geom.make(x_values.shape, y.shape[1], 3, 1, 1)
+    k = g.c1 * 27
+    kp = k + (1 if has_bias else 0)
+    lib = capi.load()
+    need = lib.effq_gram_workspace(C.byref(g), int(has_bias))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+    a0 = torch.empty((kp, kp), dtype=torch.float32, device=y.device)
+    b0 = torch.empty((g.c2, kp), dtype=torch.float32, device=y.device)
+    if att is not None:
+        att = _f32c(att, "att")
+    cs = _f32c(code_scale.reshape(1), "code_scale")
+    od, oh, ow = g.out_spatial()
+    flops = 2.0 * g.n * od * oh * ow * k * k
+    timer.run("gram_tc", {"flops": flops}, lambda: check(
+        lib.effq_gram_tc(ptr(xcodes), ptr(cs), ptr(x_values), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0),
+                         ptr(b0), ptr(ws), stream()), "effq_gram_tc"))
+    flag = ws[need - 16:need - 12].view(torch.int32)       # non-zero if the tcgen05 kernel aborted
+    return a0, b0, ws, flag
+
+
 # ---------------------------------------------------------------------------
 # (a9, a11) ADMM update
 # ---------------------------------------------------------------------------

@@ -154,6 +154,19 @@ int effq_gram_f32(const float* x, const float* x_scale, const float* y, const fl
                   const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out,
                   void* workspace, void* stream);
 
+/* Same statistics on the tensor cores for 3x3x3 / stride 1 / pad 1 layers with quantised
+ * activations: the K x K block of A0 from the NDHWC integer codes (tcgen05, att folded into a
+ * bf16 hi+lo split of the left operand), the bias row/column and B0 from the generic kernel on
+ * x_values (= code_scale * codes, NCDHW fp32).  code_scale is a device fp32 scalar.
+ * If the tcgen05 kernel aborts (barrier timeout) the abort word after the accumulator in the
+ * workspace is non-zero. */
+int effq_gram_tc_supported(const effq_geom* g);
+int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* x_values,
+                 const float* y, const float* att, const effq_geom* g, int32_t has_bias,
+                 float* a0_out, float* b0_out, void* workspace, void* stream);
+int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const effq_geom* g,
+                            double* acc64, int32_t ld, void* flags, void* stream);
+
 /* ---- (a9,a11) ADMM parameter update: solver.py:316-325, EfficientQConv.py:99-144 */
 /* B = B0 + eta*W0' ;  B[:, :K] += rho*(G - dual)          (solver.py:317-320) */
 int effq_admm_rhs(const float* b0, const float* w0p, const float* g, const float* dual,

@@ -251,6 +251,44 @@ def test_gram_codes_with_scale_and_no_bias(ops):
     np.testing.assert_allclose(b0.cpu().numpy(), (2 * ym @ cols.T).float().numpy(), rtol=1e-5, atol=1e-4)
 
 
+GRAM_TC_CASES = [
+    # n, c1, c2, spatial, levels, integer att
+    (2, 32, 32, (6, 16, 8), 16, True),
+    (1, 64, 64, (4, 8, 8), 16, False),
+    (1, 16, 24, (5, 10, 12), 4, False),       # ragged 8x8 blocks, partial 128/256-row blocks
+    (1, 128, 16, (2, 8, 8), 16, True),
+    (3, 32, 8, (3, 9, 7), 256, False),
+]
+
+
+@pytest.mark.parametrize("n,c1,c2,sp,la,int_att", GRAM_TC_CASES)
+def test_gram_tc_matches_generic_and_oracle(ops, n, c1, c2, sp, la, int_att):
+    """tcgen05 Gram (K x K block on codes, att via bf16 hi+lo split) + generic rows vs the fp64
+    im2col oracle.  Tolerance: 2^-17 per weighted term for fractional att, exact for integer att."""
+    torch.manual_seed(c1 + c2)
+    codes = torch.randint(0, la, (n, c1, *sp)).float()
+    sc = 0.173
+    x = codes * sc
+    y = torch.randn(n, c2, *sp)
+    att = (torch.rand(n, *sp) * 3).floor() + 1 if int_att else torch.rand(n, *sp) * 2 + 0.25
+    xq = codes.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+    a0, b0, _, flag = ops.gram_tc(xq, torch.tensor([sc], device=DEV), x.to(DEV), y.to(DEV), att.to(DEV), True)
+    assert int(flag.item()) == 0
+    cols = O.im2col(x, 3, 3, 3, 1, 1).double()
+    cols = torch.cat([cols, torch.ones(1, cols.shape[1], dtype=torch.float64)], 0)
+    wcols = cols * att.reshape(1, -1).double()
+    ym = y.permute(1, 0, 2, 3, 4).reshape(c2, -1).double()
+    a_ref, b_ref = (2 * cols @ wcols.T), (2 * ym @ wcols.T)
+    tol = 1e-6 if int_att else 2e-5
+    scale = a_ref.abs().max().item()
+    assert (a0.cpu().double() - a_ref).abs().max().item() <= tol * scale
+    assert (b0.cpu().double() - b_ref).abs().max().item() <= 2e-5 * b_ref.abs().max().item()
+    assert torch.equal(a0, a0.T) or torch.allclose(a0, a0.T, rtol=1e-6, atol=1e-6 * scale)
+    g0, gb0 = ops.gram(x.to(DEV), y.to(DEV), att.to(DEV), (3, 3, 3), 1, 1, has_bias=True)
+    assert (a0 - g0).abs().max().item() <= tol * scale
+    assert torch.allclose(b0, gb0, rtol=1e-5, atol=1e-5 * b_ref.abs().max().item())
+
+
 # ---------------------------------------------------------------- ADMM update (a9, a11)
 def test_admm_elementwise_kernels(ops):
     torch.manual_seed(13)

@@ -1,0 +1,41 @@
+"""One level-1 layer's kernels at the BASELINE config-2 shape (32 volumes, 32 ch, 64^3 voxels),
+each launched a few times: the target of the `ncu --set full` captures under profiles/.
+Usage: python tools/profile_layer.py [n_volumes]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from efficientq_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+c, sp = 32, (64, 64, 64)
+torch.manual_seed(0)
+x = torch.relu(torch.randn(n, c, *sp, device=dev))
+y = torch.randn(n, c, *sp, device=dev)
+att = (torch.rand(n, *sp, device=dev) * 3).floor() + 1
+st = ops.ScaleState(dev)
+ops.scale_search(x, 16, 0.0, 1.0, st)
+print("act scale", st.read())
+qx = ops.fakequant_state(x, st, 16, 0.0, 1.0)
+alpha = st.a_f32().reshape(1)
+yq, codes = ops.fakequant(x, alpha, 16, 0.0, 1.0, want_codes=True)
+xq = ops.quantize_act_ndhwc(x, 16, state=st)
+w = (2 * torch.randint(0, 16, (c, c, 3, 3, 3), device=dev) - 15).float()
+wq = ops.pack_weight_codes(w)
+cs = torch.full((1,), 1e-3, device=dev)
+ws = ops.workspace(16 + 8 * 1024, dev)
+sse = torch.zeros(1, dtype=torch.float64, device=dev)
+for _ in range(4):
+    ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=y, ws=ws, sse=sse)
+code_scale = (st.a_f32() / 15.0).reshape(1)
+a0, b0, _, flag = ops.gram_tc(xq, code_scale, qx, y, att, True)
+sol = torch.randn(c, c * 27 + 1, device=dev) * 0.05
+dual = torch.zeros(c, c * 27, device=dev)
+wst = ops.ScaleState(dev)
+for _ in range(3):
+    ops.scale_search(sol[:, : c * 27], 16, -1.0, 1.0, wst, v2=dual)
+torch.cuda.synchronize()
+print("done", sse.item(), int(flag.item()), wst.read()["passes"])

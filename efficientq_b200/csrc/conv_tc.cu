@@ -59,6 +59,8 @@ struct TcParams {
   unsigned int tmem_cols;
   int swz, rp, debug;          // operand swizzle width (128/64/32 B), row pitch, bring-up debug bits
   unsigned int wstage_bytes;   // shared-memory stride between weight tiles (1024-aligned when swizzled)
+  int transposed;              // 1: D^T = W * X^T (M = 64 weight rows, N = 128 voxels) for C2 <= 64
+  int acc_cols;                // TMEM columns per accumulator stage
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -154,14 +156,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t sbo_by
   d |= (uint64_t)(swz == 128 ? 2 : (swz == 64 ? 4 : 6)) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=m, N=n.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
   uint32_t i = 0;
   i |= 1u << 4;                            // c_format = F32
   i |= 1u << 7;                            // a_format = BF16
   i |= 1u << 10;                           // b_format = BF16
   i |= (uint32_t)(n >> 3) << 17;           // N / 8
-  i |= (uint32_t)(128 >> 4) << 24;         // M / 16
+  i |= (uint32_t)(m >> 4) << 24;           // M / 16
   return i;
 }
 
@@ -173,6 +175,9 @@ struct Pipe {
   }
 };
 
+// KS: kernel edge (3 or 1) and KK: MMAs per (tap, channel block) = CG/16 are compile-time so the
+// single MMA-issuing thread runs straight-line code.  TR: transposed orientation (see below).
+template <int KS, int KK, bool TR>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024 B alignment
@@ -199,6 +204,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.c2; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (TR && p.c2 < 64) {       // weight tiles are padded to 64 rows: the pad rows must read as zero
+    const uint32_t wbytes = p.wstage_bytes * (uint32_t)(p.w_resident ? p.n_groups * p.taps : p.n_w_stages);
+    for (uint32_t i = threadIdx.x * 16u; i < wbytes; i += TC_THREADS * 16u)
+      *reinterpret_cast<uint4*>(smem + p.off_w + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(p.tmem_cols)
@@ -240,57 +251,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one lane).  Only the 14-bit start-address field of a descriptor changes
-    // between MMAs, so both descriptors are a constant high word plus a running low word. =====
+    // between MMAs, so both descriptors are a constant template plus a running address.
+    //   !TR: D[128 voxels][C2]  = X (A: halo rows)   * W^T (B: weight rows), N = C2
+    //    TR: D[64 ch][128 vox]  = W (A: weight rows) * X^T (B: halo rows),   N = 128
+    // With operands in shared memory an M-row MMA costs >= M cycles whatever N is, so for
+    // C2 <= 64 the transposed form halves the MMA time (profiles/r01_conv_layout.md). =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(p.c2);
-      const uint64_t a_tmpl = umma_desc_sw(0, (uint32_t)(p.wp * p.rp), p.swz, 0);
-      const uint64_t b_tmpl = umma_desc_sw(0, (uint32_t)(8 * p.rp), p.swz, 0);
-      const int kk_n = p.cg / 16;
+      const uint32_t idesc = TR ? umma_idesc_bf16(64, 128) : umma_idesc_bf16(128, p.c2);
+      const uint64_t h_tmpl = umma_desc_sw(0, (uint32_t)(p.wp * p.rp), p.swz, 0);
+      const uint64_t w_tmpl = umma_desc_sw(0, (uint32_t)(8 * p.rp), p.swz, 0);
       const uint32_t row16 = (uint32_t)p.rp >> 4;                 // row pitch in 16 B units
-      const uint32_t step_c = row16, step_b = (uint32_t)p.wp * row16, step_a = (uint32_t)(p.hh * p.wp) * row16;
-      const bool no_mma = (p.debug & 4) != 0;
+      const uint32_t step_b = (uint32_t)p.wp * row16, step_a = (uint32_t)(p.hh * p.wp) * row16;
+      const uint32_t wst16 = p.wstage_bytes >> 4;
       Pipe hp{0, 0}, wp{0, 0}, ap{0, 0};
       bool ok = true;
       if (p.w_resident) ok = mbar_wait(BAR(B_WRES), 0, abort_flag);
       for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
         if (!mbar_wait(BAR(B_TE + ap.stage), ap.phase ^ 1u, abort_flag)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ap.stage * p.c2);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ap.stage * p.acc_cols);
         uint32_t accum = 0;
         for (int g = 0; g < p.n_groups && ok; ++g) {
           if (!mbar_wait(BAR(B_HF + hp.stage), hp.phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
           const uint32_t h16 = (halo0 + (uint32_t)hp.stage * p.halo_bytes) >> 4;
-          uint32_t w16 = (wsm0 + (uint32_t)(g * p.taps) * p.wstage_bytes) >> 4;   // resident weights
-          uint32_t off_a = h16;
-          for (int a = 0; a < p.kd && ok; ++a, off_a += step_a) {
-            uint32_t off_b = off_a;
-            for (int b = 0; b < p.kh && ok; ++b, off_b += step_b) {
-              uint32_t off_c = off_b;
-              for (int c = 0; c < p.kw; ++c, off_c += step_c) {
+          uint32_t w16 = (wsm0 >> 4) + (uint32_t)(g * p.taps) * wst16;         // resident weights
+#pragma unroll
+          for (int a = 0; a < KS; ++a) {
+#pragma unroll
+            for (int b = 0; b < KS; ++b) {
+#pragma unroll
+              for (int c = 0; c < KS; ++c) {
                 if (!p.w_resident) {
-                  if (!mbar_wait(BAR(B_WF + wp.stage), wp.phase, abort_flag)) { ok = false; break; }
+                  if (ok && !mbar_wait(BAR(B_WF + wp.stage), wp.phase, abort_flag)) ok = false;
                   tc_fence_after();
-                  w16 = (wsm0 + (uint32_t)wp.stage * p.wstage_bytes) >> 4;
+                  w16 = (wsm0 >> 4) + (uint32_t)wp.stage * wst16;
                 }
-                if (!no_mma) {
-#pragma unroll 4
-                  for (int kk = 0; kk < kk_n; ++kk) {
-                    tc_mma_bf16(d_tmem, a_tmpl | (uint64_t)((off_c + 2u * kk) & 0x3fffu),
-                                b_tmpl | (uint64_t)((w16 + 2u * kk) & 0x3fffu), idesc, accum);
+                const uint32_t hoff = h16 + (uint32_t)a * step_a + (uint32_t)b * step_b + (uint32_t)c * row16;
+                if (ok) {
+#pragma unroll
+                  for (int kk = 0; kk < KK; ++kk) {
+                    const uint64_t hd = h_tmpl | (uint64_t)((hoff + 2u * kk) & 0x3fffu);
+                    const uint64_t wd = w_tmpl | (uint64_t)((w16 + 2u * kk) & 0x3fffu);
+                    if (TR) tc_mma_bf16(d_tmem, wd, hd, idesc, accum);
+                    else    tc_mma_bf16(d_tmem, hd, wd, idesc, accum);
                     accum = 1;
                   }
                 }
                 if (p.w_resident) {
-                  w16 += p.wstage_bytes >> 4;
-                } else {
+                  w16 += wst16;
+                } else if (ok) {
                   tc_commit(BAR(B_WE + wp.stage));
                   wp.advance(p.n_w_stages);
                 }
               }
             }
           }
-          tc_commit(BAR(B_HE + hp.stage));
+          if (ok) tc_commit(BAR(B_HE + hp.stage));
           hp.advance(p.n_halo_stages);
         }
         if (ok) tc_commit(BAR(B_TF + ap.stage));
@@ -298,6 +315,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       }
     }
   } else if (warp < 6) {
+    if (TR) {
+      // ===== epilogue, transposed accumulator: M = 64 rows -> TMEM lanes (m/16)*32 + m%16, so
+      // lanes 0-15 of each warp's quadrant hold output channel q*16 + lane; a thread owns one
+      // channel and the tile's 128 voxels (columns, j = hy*8 + wx): its target / output
+      // accesses are 32-byte runs along w in NCDHW. =====
+      const int q = warp & 3;
+      const int ch = q * 16 + lane;
+      const bool ch_ok = lane < 16 && ch < p.c2;
+      const float scale = __ldg(p.conv_scale);
+      const float bias_c = ch_ok ? bias_s[ch] : 0.f;
+      const long long plane = (long long)p.h * p.w;
+      const long long chan = (long long)p.d * plane;
+      const bool vec_ok = (p.w % 8) == 0;          // whole 8-wide rows, 16 B aligned
+      Pipe ap{0, 0};
+      bool ok = true;
+      for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
+        unsigned int r = tile;
+        const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
+        const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
+        const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
+        const int nn = (int)r;
+        const int h0 = th * TC_TILE_H, w0 = tw * TC_TILE_W;
+        const long long vox0 = (long long)dd * plane + (long long)h0 * p.w + w0;      // voxel of column 0
+        const float* tgt = p.target ? p.target + ((long long)nn * p.c2 + ch) * chan + vox0 : nullptr;
+        float* outp = p.out ? p.out + ((long long)nn * p.c2 + ch) * chan + vox0 : nullptr;
+        const float* attp = p.att ? p.att + (long long)nn * chan + vox0 : nullptr;
+        const bool want_t = ch_ok && tgt != nullptr && !(p.debug & 2);
+        // chunk = 32 columns = 4 tile rows x 8 w.  Loads of chunk 0 are issued before the wait.
+        float tv[32];
+        auto load_targets = [&](int c0) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int hy = (c0 >> 3) + rr;
+            const bool row_ok = want_t && h0 + hy < p.h;
+            if (vec_ok) {
+              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+              if (row_ok) {
+                const float4* src = reinterpret_cast<const float4*>(tgt + (long long)hy * p.w);
+                a4 = __ldg(src);
+                b4 = __ldg(src + 1);
+              }
+              tv[rr * 8 + 0] = a4.x; tv[rr * 8 + 1] = a4.y; tv[rr * 8 + 2] = a4.z; tv[rr * 8 + 3] = a4.w;
+              tv[rr * 8 + 4] = b4.x; tv[rr * 8 + 5] = b4.y; tv[rr * 8 + 6] = b4.z; tv[rr * 8 + 7] = b4.w;
+            } else {
+#pragma unroll
+              for (int x = 0; x < 8; ++x)
+                tv[rr * 8 + x] = (row_ok && w0 + x < p.w) ? __ldg(tgt + (long long)hy * p.w + x) : 0.f;
+            }
+          }
+        };
+        load_targets(0);
+        if (!mbar_wait(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
+        tc_fence_after();
+        float e32 = 0.f;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.acc_cols + c0), v);
+          tc_wait_ld();
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(v[j]), scale, bias_c);
+          if (want_t) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int hy = (c0 >> 3) + rr;
+              if (h0 + hy < p.h) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                  if (vec_ok || w0 + x < p.w) {
+                    const float dlt = o[rr * 8 + x] - tv[rr * 8 + x];
+                    const float wv = attp ? __ldg(attp + (long long)hy * p.w + x) : 1.f;
+                    e32 = fmaf(dlt * dlt, wv, e32);
+                  }
+                }
+              }
+            }
+          }
+          if (c0 + 32 < 128) load_targets(c0 + 32);
+          if (ch_ok && outp) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int hy = (c0 >> 3) + rr;
+              if (h0 + hy < p.h) {
+                if (vec_ok) {
+                  float4* dst = reinterpret_cast<float4*>(outp + (long long)hy * p.w);
+                  __stcs(dst, make_float4(o[rr * 8], o[rr * 8 + 1], o[rr * 8 + 2], o[rr * 8 + 3]));
+                  __stcs(dst + 1, make_float4(o[rr * 8 + 4], o[rr * 8 + 5], o[rr * 8 + 6], o[rr * 8 + 7]));
+                } else {
+#pragma unroll
+                  for (int x = 0; x < 8; ++x)
+                    if (w0 + x < p.w) outp[(long long)hy * p.w + x] = o[rr * 8 + x];
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(B_TE + ap.stage));
+        ap.advance(2);
+        if (want_t) err_acc += (double)e32;
+      }
+    } else {
     // ===== epilogue: TMEM -> registers -> scale+bias -> out / squared error =====
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;               // tile row = hy*8 + wx
@@ -333,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       float e32 = 0.f;
       for (int c0 = 0; c0 < p.c2; c0 += 32) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.c2 + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.acc_cols + c0);
         const int ncol = min(32, p.c2 - c0);
         if (ncol == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
         tc_wait_ld();
@@ -358,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const float wv = p.att ? __ldg(p.att + (long long)nn * chan + sp) : 1.f;
         err_acc += (double)e32 * (double)wv;
       }
+    }
     }
   } else {
     // ===== halo producers: cp.async 16 B pieces, zero-fill outside the volume =====
@@ -498,8 +618,10 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
   p.n_tiles = (long long)g.n * g.d * p.tiles_h * p.tiles_w;
   p.halo_bytes = (uint32_t)(p.hv * p.rp);
   p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
+  p.transposed = g.c2 <= 64 ? 1 : 0;
   p.wtile_bytes = (uint32_t)(p.cg * g.c2 * 2);
-  p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
+  p.wstage_bytes = p.transposed ? (uint32_t)(64 * p.rp) : p.wtile_bytes;   // transposed: tiles padded to M = 64 rows
+  p.wstage_bytes = (p.wstage_bytes + 1023u) & ~1023u;
   p.off_bias = 256;
   p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
   const uint32_t budget = 224u * 1024u;
@@ -519,8 +641,9 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
     int ws = (int)((budget - p.off_w) / p.wstage_bytes);
     p.n_w_stages = ws > 8 ? 8 : ws;
   }
+  p.acc_cols = p.transposed ? 128 : g.c2;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * g.c2)) cols <<= 1;
+  while (cols < (uint32_t)(2 * p.acc_cols)) cols <<= 1;
   p.tmem_cols = cols;
   return cols <= 512;
 }
@@ -529,6 +652,34 @@ static uint32_t tc_smem_bytes(const TcParams& p) {
   const uint32_t w = p.w_resident ? p.wstage_bytes * (uint32_t)(p.n_groups * p.taps)
                                   : p.wstage_bytes * (uint32_t)p.n_w_stages;
   return p.off_w + w + 1024u;      // + slack for the manual 1024 B alignment of the base
+}
+
+template <int KS, int KK, bool TR>
+static int tc_launch(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
+  static uint32_t configured = 0;
+  if (smem > configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KS, KK, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  conv3d_tc_kernel<KS, KK, TR><<<ctas, TC_THREADS, smem, s>>>(p);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KS, int KK>
+static int tc_dispatch_tr(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
+  return p.transposed ? tc_launch<KS, KK, true>(p, smem, ctas, s) : tc_launch<KS, KK, false>(p, smem, ctas, s);
+}
+
+static int tc_dispatch(const TcParams& p, int ks, int kk, uint32_t smem, unsigned ctas, cudaStream_t s) {
+  if (ks == 3) {
+    if (kk == 1) return tc_dispatch_tr<3, 1>(p, smem, ctas, s);
+    if (kk == 2) return tc_dispatch_tr<3, 2>(p, smem, ctas, s);
+    return tc_dispatch_tr<3, 4>(p, smem, ctas, s);
+  }
+  if (kk == 1) return tc_dispatch_tr<1, 1>(p, smem, ctas, s);
+  if (kk == 2) return tc_dispatch_tr<1, 2>(p, smem, ctas, s);
+  return tc_dispatch_tr<1, 4>(p, smem, ctas, s);
 }
 
 }  // namespace effq
@@ -565,13 +716,7 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const floa
   p.ws_done = (unsigned int*)workspace;
   p.ws_partial = (double*)((char*)workspace + 16);
   const uint32_t smem = tc_smem_bytes(p);
-  static uint32_t configured = 0;
-  if (smem > configured) {
-    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  conv3d_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, (cudaStream_t)stream>>>(p);
-  EFFQ_LAUNCH_CHECK();
-  return 0;
+  const long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  const int kk = p.cg / 16;
+  return tc_dispatch(p, g->kd, kk, smem, (unsigned)ctas, (cudaStream_t)stream);
 }

@@ -11,6 +11,7 @@
 // CTAs see bit-identical scales and the loop exit is uniform.  Algorithmic bytes
 // per pass: numel*4 (+numel*4 when v = v1 + v2).
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace effq {
 
@@ -229,6 +230,95 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
   }
 }
 
+// ---- cluster variant: tensors up to 8 x 56 K elements (every weight tensor of the BraTS net
+// except the two 256x6912 ones).  One thread-block cluster; each CTA keeps its slice of v in
+// shared memory for the whole search; a pass ends with ONE hardware cluster barrier and every
+// CTA folds the per-CTA partial sums straight out of its peers' shared memory (DSMEM) in rank
+// order, so all CTAs see bit-identical scales.  No global-memory round trip per pass.
+constexpr int SC_THREADS = 512;
+constexpr int SC_MAX_ELEMS = 56 * 1024;          // floats of shared memory per CTA (224 KB)
+
+__global__ void __launch_bounds__(SC_THREADS, 1)
+scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, int per_cta) {
+  namespace cg = cooperative_groups;
+  extern __shared__ float sv[];                              // this CTA's slice of v
+  __shared__ double scratch[32];
+  __shared__ double slot[2][2];                              // [parity][sum index], read by peers
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int rank = cluster.block_rank(), nranks = cluster.num_blocks();
+  const QParamD q = make_qparam_d(lo, hi, nlvl);
+  const long long numel = vv.rows * vv.cols;
+  const long long begin = (long long)rank * per_cta;
+  const int mine = (int)max(0ll, min((long long)per_cta, numel - begin));
+  for (int i = threadIdx.x; i < mine; i += SC_THREADS) {
+    const long long e = begin + i;
+    sv[i] = load_v(vv, e / vv.cols, e % vv.cols);
+  }
+  __syncthreads();
+
+  __shared__ double folded[2];
+  // warp 0: lane r fetches rank r's partials over DSMEM, then a serial shuffle sum in rank order
+  // (the same order in every CTA -> bit-identical scales); result broadcast through smem.
+  auto fold = [&](int parity, double& t0, double& t1) {
+    if (threadIdx.x < 32) {
+      double x0 = 0.0, x1 = 0.0;
+      if (threadIdx.x < nranks) {
+        const double* peer = cluster.map_shared_rank(&slot[parity][0], threadIdx.x);
+        x0 = peer[0];
+        x1 = peer[1];
+      }
+      double a0 = 0.0, a1 = 0.0;
+      for (unsigned int r = 0; r < nranks; ++r) {
+        a0 += __shfl_sync(0xffffffffu, x0, (int)r);
+        a1 += __shfl_sync(0xffffffffu, x1, (int)r);
+      }
+      if (threadIdx.x == 0) { folded[0] = a0; folded[1] = a1; }
+    }
+    __syncthreads();
+    t0 = folded[0];
+    t1 = folded[1];
+    __syncthreads();
+  };
+
+  int parity = 0;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < mine; i += SC_THREADS) s0 += fabs((double)sv[i]);
+  s0 = block_sum(s0, scratch);
+  if (threadIdx.x == 0) { slot[parity][0] = s0; slot[parity][1] = 0.0; }
+  cluster.sync();
+  double t0, t1;
+  fold(parity, t0, t1);
+  double a = t0 / (double)numel, a_prev = -999.0;
+  int passes = 0;
+  const int max_pass = nlvl * 100;
+  double last0 = 0.0, last1 = 0.0;
+  while (fabs(a - a_prev) > 1e-5 && passes < max_pass) {
+    parity ^= 1;
+    const PassQ pq = make_passq(a, q);
+    s0 = 0.0;
+    s1 = 0.0;
+    for (int i = threadIdx.x; i < mine; i += SC_THREADS) accum_bv((double)sv[i], pq, s0, s1);
+    s0 = block_sum(s0, scratch);
+    s1 = block_sum(s1, scratch);
+    if (threadIdx.x == 0) { slot[parity][0] = s0; slot[parity][1] = s1; }
+    cluster.sync();        // release/acquire: peers' slots are visible; the other parity is free again
+    fold(parity, last0, last1);
+    a_prev = a;
+    a = last0 / last1;
+    ++passes;
+  }
+  cluster.sync();          // nobody exits while a peer may still read its shared memory
+  if (rank == 0 && threadIdx.x == 0) {
+    state->a = a;
+    state->a_prev = a_prev;
+    state->s_bv = last0;
+    state->s_bb = last1;
+    state->passes = passes;
+    state->converged = fabs(a - a_prev) <= 1e-5 ? 1 : 0;
+    state->failed = (passes == max_pass) ? 1 : 0;
+  }
+}
+
 // ---- multi-GPU building blocks (one pass, no grid barrier) -----------------------
 struct SPWorkspace {
   unsigned int done;
@@ -325,8 +415,40 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   cudaStream_t s = (cudaStream_t)stream;
   const long long numel = rows * cols;
   const int sms = sm_count();                         // one CTA per SM: cheapest grid barrier
-  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 16, s));    // barrier counter + abort flag
   VecView vv{v1, v2, ld1, ld2, rows, cols};
+  if (numel <= 8ll * SC_MAX_ELEMS) {                 // portable cluster size (<= 8 CTAs)
+    // small tensors (weights): one thread-block cluster, data resident in shared memory
+    int nranks = (int)((numel + SC_MAX_ELEMS - 1) / SC_MAX_ELEMS);
+    if (nranks < 8 && numel > 8192) {                 // spread the per-pass arithmetic a little
+      const int want = (int)((numel + 8191) / 8192);
+      nranks = want > 8 ? 8 : want;
+    }
+    int per_cta = (int)((numel + nranks - 1) / nranks);
+    per_cta = (per_cta + 3) & ~3;
+    const size_t smem = (size_t)per_cta * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      EFFQ_CUDA(cudaFuncSetAttribute(scale_search_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SC_MAX_ELEMS * (int)sizeof(float)));
+      configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nranks);
+    cfg.blockDim = dim3(SC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nranks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EFFQ_CUDA(cudaLaunchKernelEx(&cfg, scale_search_cluster_kernel, vv, (int)nlvl, lo, hi, state, per_cta));
+    count_launch();
+    return 0;
+  }
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 16, s));    // barrier counter + abort flag
   SSWorkspace* ws = (SSWorkspace*)workspace;
   const long long per_cta_8 = (long long)SS_THREADS * 8;
   if (numel <= (long long)sms * SS_THREADS * 8) {

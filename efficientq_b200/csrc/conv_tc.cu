@@ -59,8 +59,7 @@ struct TcParams {
   unsigned int tmem_cols;
   int swz, rp, debug;          // operand swizzle width (128/64/32 B), row pitch, bring-up debug bits
   unsigned int wstage_bytes;   // shared-memory stride between weight tiles (1024-aligned when swizzled)
-  int transposed;              // 1: D^T = W * X^T (M = 64 weight rows, N = 128 voxels) for C2 <= 64
-  int acc_cols;                // TMEM columns per accumulator stage
+  unsigned long long* dbg;     // bring-up timeline buffer ([tile][8] clock stamps of CTA 0) or null
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -86,9 +85,12 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: returns false (and raises the global abort flag) instead of hanging.
+// SLEEP_NS > 0 backs off between polls (roles that are not latency critical).
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile unsigned int* abort_flag) {
   unsigned int spins = 0;
   while (!mbar_try(bar, parity)) {
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if ((++spins & 0x3ffu) == 0) {
       if (*abort_flag != 0u) return false;
       if (spins > TC_SPIN_LIMIT) { *abort_flag = 1u; __threadfence(); return false; }
@@ -113,13 +115,27 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
+// Descriptors are passed as (low word, high word): only the 14-bit start-address field in the
+// low word changes between MMAs, so the issuing thread does 32-bit adds only.
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// One elected lane of a converged warp.  The MMA / TMA roles keep warp-uniform control flow and
+// run their issue loops inside `if (elect_one())`: the compiler then knows a single lane is
+// active.  (Under `if (lane == 0)` it emulated every uniform-datapath instruction lane by lane,
+// which made the MMA issuer the critical path -- profiles/r01_conv_layout.md.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -167,6 +183,13 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
   return i;
 }
 
+__device__ __forceinline__ void dbg_stamp(const TcParams& p, unsigned int tile, int slot) {
+  if (p.dbg && blockIdx.x == 0) {
+    const unsigned int i = tile / gridDim.x;
+    if (i < 256) p.dbg[i * 8 + slot] = clock64();
+  }
+}
+
 struct Pipe {
   int stage;
   uint32_t phase;
@@ -175,9 +198,9 @@ struct Pipe {
   }
 };
 
-// KS: kernel edge (3 or 1) and KK: MMAs per (tap, channel block) = CG/16 are compile-time so the
-// single MMA-issuing thread runs straight-line code.  TR: transposed orientation (see below).
-template <int KS, int KK, bool TR>
+// KS: kernel edge (3 or 1), KK: MMAs per (tap, channel block) = CG/16 and WRES: weights resident in
+// shared memory are compile-time, so the single MMA-issuing thread runs straight-line code.
+template <int KS, int KK, bool WRES>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024 B alignment
@@ -204,12 +227,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.c2; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
-  if (TR && p.c2 < 64) {       // weight tiles are padded to 64 rows: the pad rows must read as zero
-    const uint32_t wbytes = p.wstage_bytes * (uint32_t)(p.w_resident ? p.n_groups * p.taps : p.n_w_stages);
-    for (uint32_t i = threadIdx.x * 16u; i < wbytes; i += TC_THREADS * 16u)
-      *reinterpret_cast<uint4*>(smem + p.off_w + i) = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();
-  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(p.tmem_cols)
@@ -225,9 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   double err_acc = 0.0;
 
   if (warp == 0) {
-    // ===== weight loader (one lane) =====
-    if (lane == 0) {
-      if (p.w_resident) {
+    // ===== weight loader: one elected lane issues the 1-D bulk TMA copies =====
+    if (elect_one()) {
+      if (WRES) {
         const uint32_t total = p.wtile_bytes * (uint32_t)(p.n_groups * p.taps);
         mbar_expect_tx(BAR(B_WRES), total);
         for (int g = 0; g < p.n_groups; ++g)
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep)
           for (int g = 0; g < p.n_groups && ok; ++g)
             for (int t = 0; t < p.taps; ++t) {
-              if (!mbar_wait(BAR(B_WE + wp.stage), wp.phase ^ 1u, abort_flag)) { ok = false; break; }
+              if (!mbar_wait<32>(BAR(B_WE + wp.stage), wp.phase ^ 1u, abort_flag)) { ok = false; break; }
               mbar_expect_tx(BAR(B_WF + wp.stage), p.wtile_bytes);
               const __nv_bfloat16* src = p.wq + ((long long)t * p.n_groups + g) * p.cg * p.c2;
               bulk_g2s(wsm0 + (uint32_t)wp.stage * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WF + wp.stage));
@@ -249,61 +266,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
             }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer (one lane).  Only the 14-bit start-address field of a descriptor changes
-    // between MMAs, so both descriptors are a constant template plus a running address.
-    //   !TR: D[128 voxels][C2]  = X (A: halo rows)   * W^T (B: weight rows), N = C2
-    //    TR: D[64 ch][128 vox]  = W (A: weight rows) * X^T (B: halo rows),   N = 128
-    // With operands in shared memory an M-row MMA costs >= M cycles whatever N is, so for
-    // C2 <= 64 the transposed form halves the MMA time (profiles/r01_conv_layout.md). =====
-    if (lane == 0) {
-      const uint32_t idesc = TR ? umma_idesc_bf16(64, 128) : umma_idesc_bf16(128, p.c2);
+    // ===== MMA issuer: D[128 voxels][C2] += X(tap slice of the halo) * W(tap)^T.  One elected lane
+    // runs the whole loop; per MMA it does two 32-bit adds on the descriptors' address fields. =====
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.c2);
       const uint64_t h_tmpl = umma_desc_sw(0, (uint32_t)(p.wp * p.rp), p.swz, 0);
       const uint64_t w_tmpl = umma_desc_sw(0, (uint32_t)(8 * p.rp), p.swz, 0);
+      const uint32_t h_hi = (uint32_t)(h_tmpl >> 32), h_lo0 = (uint32_t)h_tmpl;
+      const uint32_t w_hi = (uint32_t)(w_tmpl >> 32), w_lo0 = (uint32_t)w_tmpl;
       const uint32_t row16 = (uint32_t)p.rp >> 4;                 // row pitch in 16 B units
       const uint32_t step_b = (uint32_t)p.wp * row16, step_a = (uint32_t)(p.hh * p.wp) * row16;
       const uint32_t wst16 = p.wstage_bytes >> 4;
+      const uint32_t hst16 = p.halo_bytes >> 4;
+      const uint32_t h_base = h_lo0 + (halo0 >> 4), w_base = w_lo0 + (wsm0 >> 4);
       Pipe hp{0, 0}, wp{0, 0}, ap{0, 0};
       bool ok = true;
-      if (p.w_resident) ok = mbar_wait(BAR(B_WRES), 0, abort_flag);
+      if (WRES) ok = mbar_wait(BAR(B_WRES), 0, abort_flag);
       for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
         if (!mbar_wait(BAR(B_TE + ap.stage), ap.phase ^ 1u, abort_flag)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ap.stage * p.acc_cols);
-        uint32_t accum = 0;
+        dbg_stamp(p, tile, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ap.stage * p.c2);
         for (int g = 0; g < p.n_groups && ok; ++g) {
           if (!mbar_wait(BAR(B_HF + hp.stage), hp.phase, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t h16 = (halo0 + (uint32_t)hp.stage * p.halo_bytes) >> 4;
-          uint32_t w16 = (wsm0 >> 4) + (uint32_t)(g * p.taps) * wst16;         // resident weights
+          if (g == 0) dbg_stamp(p, tile, 1);
+          const uint32_t h_lo = h_base + (uint32_t)hp.stage * hst16;
+          uint32_t w_lo = w_base + (uint32_t)(g * p.taps) * wst16;              // resident weights
 #pragma unroll
           for (int a = 0; a < KS; ++a) {
 #pragma unroll
             for (int b = 0; b < KS; ++b) {
 #pragma unroll
               for (int c = 0; c < KS; ++c) {
-                if (!p.w_resident) {
+                if (!WRES) {
                   if (ok && !mbar_wait(BAR(B_WF + wp.stage), wp.phase, abort_flag)) ok = false;
                   tc_fence_after();
-                  w16 = (wsm0 >> 4) + (uint32_t)wp.stage * wst16;
+                  w_lo = w_base + (uint32_t)wp.stage * wst16;
                 }
-                const uint32_t hoff = h16 + (uint32_t)a * step_a + (uint32_t)b * step_b + (uint32_t)c * row16;
                 if (ok) {
+                  const uint32_t ha = h_lo + (uint32_t)a * step_a + (uint32_t)b * step_b + (uint32_t)c * row16;
 #pragma unroll
-                  for (int kk = 0; kk < KK; ++kk) {
-                    const uint64_t hd = h_tmpl | (uint64_t)((hoff + 2u * kk) & 0x3fffu);
-                    const uint64_t wd = w_tmpl | (uint64_t)((w16 + 2u * kk) & 0x3fffu);
-                    if (TR) tc_mma_bf16(d_tmem, wd, hd, idesc, accum);
-                    else    tc_mma_bf16(d_tmem, hd, wd, idesc, accum);
-                    accum = 1;
-                  }
+                  for (int kk = 0; kk < KK; ++kk)
+                    tc_mma_bf16(d_tmem, ha + 2u * kk, h_hi, w_lo + 2u * kk, w_hi, idesc,
+                                (g == 0 && a == 0 && b == 0 && c == 0 && kk == 0) ? 0u : 1u);
+                  if (!WRES) { tc_commit(BAR(B_WE + wp.stage)); wp.advance(p.n_w_stages); }
                 }
-                if (p.w_resident) {
-                  w16 += wst16;
-                } else if (ok) {
-                  tc_commit(BAR(B_WE + wp.stage));
-                  wp.advance(p.n_w_stages);
-                }
+                if (WRES) w_lo += wst16;
               }
             }
           }
@@ -311,112 +322,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           hp.advance(p.n_halo_stages);
         }
         if (ok) tc_commit(BAR(B_TF + ap.stage));
+        dbg_stamp(p, tile, 2);
         ap.advance(2);
       }
     }
+    __syncwarp();
   } else if (warp < 6) {
-    if (TR) {
-      // ===== epilogue, transposed accumulator: M = 64 rows -> TMEM lanes (m/16)*32 + m%16, so
-      // lanes 0-15 of each warp's quadrant hold output channel q*16 + lane; a thread owns one
-      // channel and the tile's 128 voxels (columns, j = hy*8 + wx): its target / output
-      // accesses are 32-byte runs along w in NCDHW. =====
-      const int q = warp & 3;
-      const int ch = q * 16 + lane;
-      const bool ch_ok = lane < 16 && ch < p.c2;
-      const float scale = __ldg(p.conv_scale);
-      const float bias_c = ch_ok ? bias_s[ch] : 0.f;
-      const long long plane = (long long)p.h * p.w;
-      const long long chan = (long long)p.d * plane;
-      const bool vec_ok = (p.w % 8) == 0;          // whole 8-wide rows, 16 B aligned
-      Pipe ap{0, 0};
-      bool ok = true;
-      for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
-        unsigned int r = tile;
-        const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
-        const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
-        const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
-        const int nn = (int)r;
-        const int h0 = th * TC_TILE_H, w0 = tw * TC_TILE_W;
-        const long long vox0 = (long long)dd * plane + (long long)h0 * p.w + w0;      // voxel of column 0
-        const float* tgt = p.target ? p.target + ((long long)nn * p.c2 + ch) * chan + vox0 : nullptr;
-        float* outp = p.out ? p.out + ((long long)nn * p.c2 + ch) * chan + vox0 : nullptr;
-        const float* attp = p.att ? p.att + (long long)nn * chan + vox0 : nullptr;
-        const bool want_t = ch_ok && tgt != nullptr && !(p.debug & 2);
-        // chunk = 32 columns = 4 tile rows x 8 w.  Loads of chunk 0 are issued before the wait.
-        float tv[32];
-        auto load_targets = [&](int c0) {
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int hy = (c0 >> 3) + rr;
-            const bool row_ok = want_t && h0 + hy < p.h;
-            if (vec_ok) {
-              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
-              if (row_ok) {
-                const float4* src = reinterpret_cast<const float4*>(tgt + (long long)hy * p.w);
-                a4 = __ldg(src);
-                b4 = __ldg(src + 1);
-              }
-              tv[rr * 8 + 0] = a4.x; tv[rr * 8 + 1] = a4.y; tv[rr * 8 + 2] = a4.z; tv[rr * 8 + 3] = a4.w;
-              tv[rr * 8 + 4] = b4.x; tv[rr * 8 + 5] = b4.y; tv[rr * 8 + 6] = b4.z; tv[rr * 8 + 7] = b4.w;
-            } else {
-#pragma unroll
-              for (int x = 0; x < 8; ++x)
-                tv[rr * 8 + x] = (row_ok && w0 + x < p.w) ? __ldg(tgt + (long long)hy * p.w + x) : 0.f;
-            }
-          }
-        };
-        load_targets(0);
-        if (!mbar_wait(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
-        tc_fence_after();
-        float e32 = 0.f;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.acc_cols + c0), v);
-          tc_wait_ld();
-          float o[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = fmaf(__uint_as_float(v[j]), scale, bias_c);
-          if (want_t) {
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const int hy = (c0 >> 3) + rr;
-              if (h0 + hy < p.h) {
-#pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                  if (vec_ok || w0 + x < p.w) {
-                    const float dlt = o[rr * 8 + x] - tv[rr * 8 + x];
-                    const float wv = attp ? __ldg(attp + (long long)hy * p.w + x) : 1.f;
-                    e32 = fmaf(dlt * dlt, wv, e32);
-                  }
-                }
-              }
-            }
-          }
-          if (c0 + 32 < 128) load_targets(c0 + 32);
-          if (ch_ok && outp) {
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const int hy = (c0 >> 3) + rr;
-              if (h0 + hy < p.h) {
-                if (vec_ok) {
-                  float4* dst = reinterpret_cast<float4*>(outp + (long long)hy * p.w);
-                  __stcs(dst, make_float4(o[rr * 8], o[rr * 8 + 1], o[rr * 8 + 2], o[rr * 8 + 3]));
-                  __stcs(dst + 1, make_float4(o[rr * 8 + 4], o[rr * 8 + 5], o[rr * 8 + 6], o[rr * 8 + 7]));
-                } else {
-#pragma unroll
-                  for (int x = 0; x < 8; ++x)
-                    if (w0 + x < p.w) outp[(long long)hy * p.w + x] = o[rr * 8 + x];
-                }
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(BAR(B_TE + ap.stage));
-        ap.advance(2);
-        if (want_t) err_acc += (double)e32;
-      }
-    } else {
     // ===== epilogue: TMEM -> registers -> scale+bias -> out / squared error =====
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;               // tile row = hy*8 + wx
@@ -439,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       // Target values do not depend on the MMA: issue all loads of a 32-channel chunk before
       // anything consumes them (32 independent requests in flight per thread), the first chunk
       // even before waiting for the accumulator.
-      const bool want_t = live && p.target != nullptr && !(p.debug & 2);
+      const bool want_t = live && p.target != nullptr;
       float tv[32];
       auto load_targets = [&](int c0) {
 #pragma unroll
@@ -447,12 +358,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           tv[j] = (want_t && c0 + j < p.c2) ? __ldg(p.target + base + (long long)(c0 + j) * chan) : 0.f;
       };
       load_targets(0);
-      if (!mbar_wait(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
+      if (!mbar_wait<64>(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
+      if (threadIdx.x == 64) dbg_stamp(p, tile, 3);
       tc_fence_after();
       float e32 = 0.f;
       for (int c0 = 0; c0 < p.c2; c0 += 32) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.acc_cols + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.c2 + c0);
         const int ncol = min(32, p.c2 - c0);
         if (ncol == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
         tc_wait_ld();
@@ -472,12 +384,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       }
       tc_fence_before();
       mbar_arrive(BAR(B_TE + ap.stage));
+      if (threadIdx.x == 64) dbg_stamp(p, tile, 4);
       ap.advance(2);
       if (want_t) {
         const float wv = p.att ? __ldg(p.att + (long long)nn * chan + sp) : 1.f;
         err_acc += (double)e32 * (double)wv;
       }
-    }
     }
   } else {
     // ===== halo producers: cp.async 16 B pieces, zero-fill outside the volume =====
@@ -524,7 +436,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       // pointer of halo voxel (0,0,0), channel 0 -- may lie outside the tensor, only dereferenced when valid
       const __nv_bfloat16* origin = p.xq + ((((long long)nn * p.d + d0) * p.h + h0) * p.w + w0) * p.c1;
       for (int g = 0; g < p.n_groups; ++g) {
-        if (!mbar_wait(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
+        if (!mbar_wait<64>(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
+        if (ptid == 0 && g == 0) dbg_stamp(p, tile, 5);
         const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
         const __nv_bfloat16* gorigin = origin + g * p.cg;
 #pragma unroll
@@ -536,13 +449,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
             const __nv_bfloat16* src = okk ? gorigin + rel[i] : p.xq;
             const uint32_t rowb = hbase + (dst[i] & 0xffffffu);
             const uint32_t x = (dst[i] >> 24) & 15u, j0 = dst[i] >> 28;
-            if (!(p.debug & 1)) {
-              cp_async16(rowb + (((j0) ^ x) << 4), src, okk ? 16u : 0u);
-              if (cpi == 2) cp_async16(rowb + (((j0 + 1) ^ x) << 4), src + 8, okk ? 16u : 0u);
-            }
+            cp_async16(rowb + (((j0) ^ x) << 4), src, okk ? 16u : 0u);
+            if (cpi == 2) cp_async16(rowb + (((j0 + 1) ^ x) << 4), src + 8, okk ? 16u : 0u);
           }
         }
         cp_async_commit();
+        if (ptid == 0 && g == 0) dbg_stamp(p, tile, 6);
         if (pending) {                              // previous block: complete -> visible to the async proxy -> signal
           cp_async_wait<1>();
           fence_proxy_async();
@@ -618,10 +530,8 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
   p.n_tiles = (long long)g.n * g.d * p.tiles_h * p.tiles_w;
   p.halo_bytes = (uint32_t)(p.hv * p.rp);
   p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
-  p.transposed = g.c2 <= 64 ? 1 : 0;
   p.wtile_bytes = (uint32_t)(p.cg * g.c2 * 2);
-  p.wstage_bytes = p.transposed ? (uint32_t)(64 * p.rp) : p.wtile_bytes;   // transposed: tiles padded to M = 64 rows
-  p.wstage_bytes = (p.wstage_bytes + 1023u) & ~1023u;
+  p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
   p.off_bias = 256;
   p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
   const uint32_t budget = 224u * 1024u;
@@ -641,9 +551,8 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
     int ws = (int)((budget - p.off_w) / p.wstage_bytes);
     p.n_w_stages = ws > 8 ? 8 : ws;
   }
-  p.acc_cols = p.transposed ? 128 : g.c2;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * p.acc_cols)) cols <<= 1;
+  while (cols < (uint32_t)(2 * g.c2)) cols <<= 1;
   p.tmem_cols = cols;
   return cols <= 512;
 }
@@ -654,32 +563,32 @@ static uint32_t tc_smem_bytes(const TcParams& p) {
   return p.off_w + w + 1024u;      // + slack for the manual 1024 B alignment of the base
 }
 
-template <int KS, int KK, bool TR>
+template <int KS, int KK, bool WRES>
 static int tc_launch(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
   static uint32_t configured = 0;
   if (smem > configured) {
-    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KS, KK, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KS, KK, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  conv3d_tc_kernel<KS, KK, TR><<<ctas, TC_THREADS, smem, s>>>(p);
+  conv3d_tc_kernel<KS, KK, WRES><<<ctas, TC_THREADS, smem, s>>>(p);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }
 
 template <int KS, int KK>
-static int tc_dispatch_tr(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
-  return p.transposed ? tc_launch<KS, KK, true>(p, smem, ctas, s) : tc_launch<KS, KK, false>(p, smem, ctas, s);
+static int tc_dispatch_w(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
+  return p.w_resident ? tc_launch<KS, KK, true>(p, smem, ctas, s) : tc_launch<KS, KK, false>(p, smem, ctas, s);
 }
 
 static int tc_dispatch(const TcParams& p, int ks, int kk, uint32_t smem, unsigned ctas, cudaStream_t s) {
   if (ks == 3) {
-    if (kk == 1) return tc_dispatch_tr<3, 1>(p, smem, ctas, s);
-    if (kk == 2) return tc_dispatch_tr<3, 2>(p, smem, ctas, s);
-    return tc_dispatch_tr<3, 4>(p, smem, ctas, s);
+    if (kk == 1) return tc_dispatch_w<3, 1>(p, smem, ctas, s);
+    if (kk == 2) return tc_dispatch_w<3, 2>(p, smem, ctas, s);
+    return tc_dispatch_w<3, 4>(p, smem, ctas, s);
   }
-  if (kk == 1) return tc_dispatch_tr<1, 1>(p, smem, ctas, s);
-  if (kk == 2) return tc_dispatch_tr<1, 2>(p, smem, ctas, s);
-  return tc_dispatch_tr<1, 4>(p, smem, ctas, s);
+  if (kk == 1) return tc_dispatch_w<1, 1>(p, smem, ctas, s);
+  if (kk == 2) return tc_dispatch_w<1, 2>(p, smem, ctas, s);
+  return tc_dispatch_w<1, 4>(p, smem, ctas, s);
 }
 
 }  // namespace effq
@@ -715,6 +624,9 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const floa
   p.sse = sse;
   p.ws_done = (unsigned int*)workspace;
   p.ws_partial = (double*)((char*)workspace + 16);
+  // bring-up: EFFQ_TC_DEBUG bit 8 -> CTA 0 writes a per-tile clock timeline behind the partials
+  // (the caller must then pass a workspace of at least 16 + 8 KB + 16 KB)
+  p.dbg = (p.debug & 8) ? (unsigned long long*)((char*)workspace + 16 + 8 * 1024) : nullptr;
   const uint32_t smem = tc_smem_bytes(p);
   const long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   const int kk = p.cg / 16;

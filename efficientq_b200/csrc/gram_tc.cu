@@ -64,9 +64,11 @@ __device__ __forceinline__ bool gt_mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ bool gt_mbar_wait(uint32_t bar, uint32_t parity, volatile unsigned int* abort_flag) {
   unsigned int spins = 0;
   while (!gt_mbar_try(bar, parity)) {
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);       // do not steal issue slots from the MMA warp
     if ((++spins & 0x3ffu) == 0) {
       if (*abort_flag != 0u) return false;
       if (spins > GT_SPIN_LIMIT) { *abort_flag = 1u; __threadfence(); return false; }
@@ -82,6 +84,13 @@ __device__ __forceinline__ void gt_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool gt_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void gt_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -162,8 +171,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
   const long long n_items = (long long)p.mb_n * p.nb_n * p.splits;
 
   if (warp == 8) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
+    {
       uint32_t idesc = 0;
       idesc |= 1u << 4;                       // D = f32
       idesc |= 1u << 7;                       // A = bf16
@@ -188,18 +197,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t zhi = (stage0 + (uint32_t)stage * GT_STAGE_BYTES) >> 4;
           const uint32_t zlo = zhi + (GT_ZBYTES >> 4), pp = zhi + ((2 * GT_ZBYTES) >> 4);
+          if (gt_elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < GT_KV / 16; ++ks) {
-            const uint32_t koff = (uint32_t)ks * (16u * 128u >> 4);
-            const uint64_t bd = tmpl | (uint64_t)((pp + koff) & 0x3fffu);
-            gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, accum);
-            gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
-            accum = 1;
+            for (int ks = 0; ks < GT_KV / 16; ++ks) {
+              const uint32_t koff = (uint32_t)ks * (16u * 128u >> 4);
+              const uint64_t bd = tmpl | (uint64_t)((pp + koff) & 0x3fffu);
+              gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, ks == 0 ? accum : 1u);
+              gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
+            }
+            gt_commit(EMPTY(stage));
+            if (hb == hb1 - 1) gt_commit(TFULL);
           }
-          gt_commit(EMPTY(stage));
+          __syncwarp();
+          accum = 1;
           if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (ok) gt_commit(TFULL);
         tphase ^= 1u;
       }
     }
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
                            (unsigned)gw < (unsigned)p.w;
           pv[i] = okk ? __ldg(reinterpret_cast<const uint4*>(vptr + ps[i].rel)) : make_uint4(0, 0, 0, 0);
         }
-        if (!gt_mbar_wait(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
+        if (!gt_mbar_wait<64>(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
         uint8_t* sbase = gsm + (size_t)stage * GT_STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       }
       if (!ok) break;
       // ---- epilogue of the item: TMEM tile -> fp64 workspace (reference row order) ----
-      if (!gt_mbar_wait(TFULL, tphase, abort_flag)) { ok = false; break; }
+      if (!gt_mbar_wait<64>(TFULL, tphase, abort_flag)) { ok = false; break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       tphase ^= 1u;
       const int qd = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half

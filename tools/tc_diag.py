@@ -87,7 +87,7 @@ def main():
         wq = ops.pack_weight_codes(w)
         tgt = torch.randn(n, c, *sp, device=DEV)
         cs = torch.ones(1, device=DEV)
-        ws = ops.workspace(16 + 8 * 1024, torch.device(DEV))
+        ws = ops.workspace(16 + 8 * 1024 + 16 * 1024, torch.device(DEV))
         sse = torch.zeros(1, dtype=torch.float64, device=DEV)
         for _ in range(3):
             ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=tgt, ws=ws, sse=sse)
@@ -100,6 +100,14 @@ def main():
         ms = e0.elapsed_time(e1) / 10
         fl = 2.0 * n * sp[0] * sp[1] * sp[2] * c * c * 27
         print(f"[perf c{c} {n}x{sp}] {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        if int(os.environ.get("EFFQ_TC_DEBUG", "0")) & 8:
+            tl = ws[16 + 8 * 1024:16 + 8 * 1024 + 16 * 1024].view(torch.int64).cpu().reshape(-1, 8)
+            t0 = int(tl[2, 0])
+            names = ["mma:acc_free", "mma:halo_ready", "mma:issued", "epi:acc_full", "epi:done", "prod:slot_free",
+                     "prod:copies_issued", "prod:signalled"]
+            print("   timeline (cycles rel. to tile 2, CTA 0):", names)
+            for i in range(2, 12):
+                print("   tile", i, [int(v) - t0 for v in tl[i]])
 
 
 if __name__ == "__main__":

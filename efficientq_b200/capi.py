@@ -80,11 +80,14 @@ _SIGS = {
     "effq_gram_workspace": (C.c_int64, [C.POINTER(Geom), C.c_int32]),
     "effq_gram_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_gram_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_quadform_sse": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_gram_tc_supported": (C.c_int, [C.POINTER(Geom)]),
-    "effq_gram_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom),
+    "effq_gram_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom),
                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "effq_gram_tc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p, C.c_int32,
-                                          C.c_void_p, C.c_void_p]),
+    "effq_gram_tc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_void_p,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

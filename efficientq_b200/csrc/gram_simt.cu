@@ -71,7 +71,7 @@ __device__ __forceinline__ float fetch(const RowDesc& rd, const VoxPos& p, const
 __global__ void __launch_bounds__(GM_THREADS)
 gram_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ att,
                 effq_geom g, OutDims o, int k, int kp, int mrows, int row_begin, long long vox_per_split,
-                double* __restrict__ acc64) {
+                int flush_every, double* __restrict__ acc64) {
   __shared__ float Ls[GM_KC][GM_TILE + 4];
   __shared__ float Rs[GM_KC][GM_TILE + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -134,7 +134,7 @@ gram_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(l[a], r[b], acc[a][b]);
     }
-    if ((step + 1) % GM_FLUSH == 0) {
+    if ((step + 1) % flush_every == 0) {
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -194,7 +194,8 @@ extern "C" int64_t effq_gram_workspace(const effq_geom* g, int32_t has_bias) {
 namespace effq {
 // Launches the generic kernel for rows [row_begin, mrows) of [Xhat ; Y] against att.Xhat.
 static int launch_gram_rows(const float* x, const float* y, const float* att, const effq_geom& g, const OutDims& o,
-                            int k, int kp, int mrows, int row_begin, double* acc, cudaStream_t s) {
+                            int k, int kp, int mrows, int row_begin, double* acc, cudaStream_t s,
+                            int flush_every = GM_FLUSH) {
   const int tx = (kp + GM_TILE - 1) / GM_TILE, ty = (mrows - row_begin + GM_TILE - 1) / GM_TILE;
   long long splits = ((long long)sm_count() * 6 + (long long)tx * ty - 1) / ((long long)tx * ty);
   const long long max_splits = (o.vox + 511) / 512;
@@ -205,7 +206,7 @@ static int launch_gram_rows(const float* x, const float* y, const float* att, co
   per = (per + GM_KC - 1) / GM_KC * GM_KC;
   splits = (o.vox + per - 1) / per;
   dim3 grid(tx, ty, (unsigned)splits);
-  gram_f32_kernel<<<grid, GM_THREADS, 0, s>>>(x, y, att, g, o, k, kp, mrows, row_begin, per, acc);
+  gram_f32_kernel<<<grid, GM_THREADS, 0, s>>>(x, y, att, g, o, k, kp, mrows, row_begin, per, flush_every, acc);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }
@@ -232,32 +233,101 @@ extern "C" int effq_gram_f32(const float* x, const float* x_scale, const float* 
   return 0;
 }
 
-extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const effq_geom* g,
-                                       double* acc64, int32_t ld, void* flags, void* stream);
+extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                                       const effq_geom* g, int32_t has_bias, double* acc64, int32_t ld,
+                                       void* flags, void* stream);
 extern "C" int effq_gram_tc_supported(const effq_geom* g);
 
-// Tensor-core path: K x K block from integer codes (tcgen05), bias row / column and B0 from the
-// generic kernel on the real-valued activations `x_values` (same tensor the codes came from).
-extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* x_values,
-                            const float* y, const float* att, const effq_geom* g, int32_t has_bias,
-                            float* a0_out, float* b0_out, void* workspace, void* stream) {
+// Tensor-core path: A0 (incl. bias row / column) and B0 in one tcgen05 kernel on the integer
+// codes; code_scale (device fp32) turns codes into activations in the finalize pass.
+extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y,
+                            const float* att, const effq_geom* g, int32_t has_bias, float* a0_out,
+                            float* b0_out, void* workspace, void* stream) {
   using namespace effq;
-  EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && code_scale && x_values && y && g && a0_out && b0_out && workspace, "null pointer");
+  EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && code_scale && y && g && a0_out && b0_out && workspace, "null pointer");
   EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
-  const OutDims o = out_dims(*g);
   const int k = g->c1 * 27;
   const int kp = k + (has_bias ? 1 : 0);
   const int mrows = kp + g->c2;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t acc_bytes = (size_t)mrows * kp * 8;
   EFFQ_CUDA(cudaMemsetAsync(workspace, 0, acc_bytes + 16, s));
-  if (int rc = effq_gram_tc_accumulate(xcodes_ndhwc_bf16, att, g, (double*)workspace, kp,
+  if (int rc = effq_gram_tc_accumulate(xcodes_ndhwc_bf16, att, y, g, has_bias, (double*)workspace, kp,
                                        (char*)workspace + acc_bytes, stream)) return rc;
-  if (int rc = launch_gram_rows(x_values, y, att, *g, o, k, kp, mrows, k, (double*)workspace, s)) return rc;
   const long long total = (long long)mrows * kp;
   int fb = (int)((total + 255) / 256);
   if (fb > sm_count() * 16) fb = sm_count() * 16;
-  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, code_scale, k, kp, g->c2, 1, a0_out, b0_out);
+  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, code_scale, k, kp, g->c2, 0, a0_out, b0_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- sufficient statistics for scoring WITHOUT re-running the conv ------------------------------
+// For a layer whose input is not quantised (conv0, final_cls: q_first/q_last = 256,-1) the conv
+// input is the same tensor in all 200 ADMM iterations, so
+//     sum (W^ x^ - y)^2  =  sum_r [ w_r S w_r^T - 2 w_r . T_r ]  +  sum y^2
+// with the UNWEIGHTED  S = X^ X^T (K' x K')  and  T = Y X^T (C2 x K')  accumulated once in fp64
+// (fp32 products folded into fp64 every 16 voxels).  K' is 109 / 33 for these layers.
+extern "C" int effq_gram_f64(const float* x, const float* y, const effq_geom* g, int32_t has_bias,
+                             double* acc64_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && y && g && acc64_out, "null pointer");
+  const OutDims o = out_dims(*g);
+  EFFQ_CHECK_ARG(o.od > 0 && o.oh > 0 && o.ow > 0 && g->n > 0, "empty output");
+  const int k = g->c1 * g->kd * g->kh * g->kw;
+  const int kp = k + (has_bias ? 1 : 0);
+  const int mrows = kp + g->c2;
+  cudaStream_t s = (cudaStream_t)stream;
+  EFFQ_CUDA(cudaMemsetAsync(acc64_out, 0, (size_t)mrows * kp * 8, s));
+  return launch_gram_rows(x, y, nullptr, *g, o, k, kp, mrows, 0, acc64_out, s, 1);
+}
+
+namespace effq {
+// one CTA per output channel r:  q_r = w_r S w_r^T - 2 w_r . T_r   (fp64), then a fixed-order sum
+__global__ void __launch_bounds__(256)
+quadform_kernel(const double* __restrict__ acc, double yy, const float* __restrict__ gw, const float* __restrict__ bstar,
+                int c2, int k, int kp, double* __restrict__ per_row, unsigned int* __restrict__ done,
+                double* __restrict__ sse) {
+  __shared__ double scratch[32];
+  __shared__ bool last;
+  const int r = blockIdx.x;
+  const double* S = acc;
+  const double* T = acc + (long long)kp * kp + (long long)r * kp;
+  auto wv = [&](int j) -> double { return j < k ? (double)gw[(long long)r * k + j] : (double)bstar[r]; };
+  double part = 0.0;
+  for (int i = threadIdx.x; i < kp; i += blockDim.x) {
+    double t = 0.0;
+    for (int j = 0; j < kp; ++j) t = fma(S[(long long)i * kp + j], wv(j), t);
+    part += wv(i) * (t - 2.0 * T[i]);
+  }
+  part = block_sum(part, scratch);
+  if (threadIdx.x == 0) {
+    per_row[r] = part;
+    __threadfence();
+    last = (atomicAdd(done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = yy;
+    for (int q = 0; q < c2; ++q) t += ((volatile double*)per_row)[q];
+    *sse = t > 0.0 ? t : 0.0;
+    *done = 0;
+  }
+}
+}  // namespace effq
+
+// sse = sum over all outputs of (conv(x, G) + b* - y)^2 from the statistics of effq_gram_f64.
+// workspace: 16 B counter (zero on entry) + c2 doubles.
+extern "C" int effq_quadform_sse(const double* acc64, double sum_y2, const float* gw, const float* bstar,
+                                 int32_t c2, int32_t k, int32_t has_bias, double* sse, void* workspace,
+                                 void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(acc64 && gw && sse && workspace && c2 > 0 && k > 0, "bad argument");
+  EFFQ_CHECK_ARG(!has_bias || bstar, "bias missing");
+  const int kp = k + (has_bias ? 1 : 0);
+  quadform_kernel<<<c2, 256, 0, (cudaStream_t)stream>>>(acc64, sum_y2, gw, bstar, c2, k, kp,
+                                                       (double*)((char*)workspace + 16), (unsigned int*)workspace, sse);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

@@ -39,10 +39,13 @@ constexpr unsigned int GT_SPIN_LIMIT = 1u << 26;
 struct GtParams {
   const __nv_bfloat16* xq;     // NDHWC codes
   const float* att;            // N,D,H,W or null
-  double* acc;                 // fp64 workspace, leading dimension ld (reference row order)
+  const float* y;              // NCDHW fp32 target (rows of B0) or null
+  double* acc;                 // fp64 workspace [(K'+C2) x K'], leading dimension ld (reference row order)
   unsigned int* flags;         // [0] abort
   int n, c1, d, h, w;
   int k;                       // 27 * c1
+  int c2, has_bias;            // B0 rows / ones row+column
+  int mx0;                     // first extra left row (ones row, then y channels from mx0 + 8), multiple of 128
   int ld;
   int mb_n, nb_n, splits;      // work decomposition
   int hb_h, hb_w;              // 8x8 voxel blocks per plane (ceil)
@@ -116,27 +119,41 @@ __device__ __forceinline__ uint64_t gt_desc(uint32_t saddr, uint32_t lbo_bytes, 
   return d;
 }
 
+// A slot = the 16-byte chunk (8 consecutive rows at this thread's voxel) a builder thread fills.
+//   kind 1: 8 channels of the tap-shifted activation vector   (rows < K)
+//   kind 2: the "ones" chunk: row 0 = 1, rows 1-7 = 0         (bias row / column)
+//   kind 3: 8 channels of the fp32 target y                   (left operand only: rows of B0)
+//   kind 0: zero padding
 struct Slot {
-  int rel;          // element offset of the tap-shifted vector relative to the voxel's own vector
-  int tap;          // (a) | (b << 2) | (c << 4) | valid << 6      (a,b,c in 0..2)
+  int rel;          // kind 1: element offset relative to the voxel's own vector; kind 3: first y channel
+  int tap;          // (a) | (b << 2) | (c << 4) | kind << 6      (a,b,c in 0..2)
   uint32_t dst;     // byte offset inside the stage (Zhi / P region), swizzle applied
 };
 
-__device__ __forceinline__ Slot make_slot(int row0, int rc, int kvox, int c1, int k, int h, int w, bool is_p) {
+__device__ __forceinline__ Slot make_slot(int row0, int rc, int kvox, const GtParams& p, bool left) {
   Slot s;
   const int r = row0 + rc * 8;
   s.tap = 0;
   s.rel = 0;
-  if (r < k) {
-    const int tap = r / c1, c0 = r % c1;
+  if (r < p.k) {
+    const int tap = r / p.c1, c0 = r % p.c1;
     const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
-    s.rel = (((a - 1) * h + (b - 1)) * w + (c - 1)) * c1 + c0;
+    s.rel = (((a - 1) * p.h + (b - 1)) * p.w + (c - 1)) * p.c1 + c0;
     s.tap = a | (b << 2) | (c << 4) | (1 << 6);
+  } else if (left) {
+    if (r == p.mx0 && p.has_bias) s.tap = 2 << 6;
+    else if (p.y && r >= p.mx0 + 8 && r < p.mx0 + 8 + p.c2) { s.tap = 3 << 6; s.rel = r - p.mx0 - 8; }
+  } else if (r == p.k && p.has_bias) {
+    s.tap = 2 << 6;
   }
   const uint32_t blk = (uint32_t)(rc >> 3), ch = (uint32_t)(rc & 7);
   s.dst = blk * (GT_KV * 128u) + (uint32_t)kvox * 128u + ((ch ^ (uint32_t)(kvox & 7)) << 4);
-  (void)is_p;
   return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) |
+         ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p) {
@@ -232,9 +249,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       const int mb = (int)r;
       Slot zs[4], ps[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + 4 * i, kvox, p.c1, p.k, p.h, p.w, false);
+      for (int i = 0; i < 4; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + 4 * i, kvox, p, true);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + 4 * i, kvox, p.c1, p.k, p.h, p.w, true);
+      for (int i = 0; i < 8; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + 4 * i, kvox, p, false);
       long long hb0 = (long long)z * p.hb_per_split;
       long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
       for (long long hb = hb0; hb < hb1; ++hb) {
@@ -249,38 +266,61 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
         const __nv_bfloat16* vptr = p.xq + vidx * p.c1;
         const float aw = vlive ? (p.att ? __ldg(p.att + vidx) : 1.f) : 0.f;
         // gather first (loads in flight), then wait for the stage, then write
-        uint4 zv[4], pv[8];
+        uint4 zv[4], pv[8];           // kind 1: raw bf16 codes; kind 3 (left only): handled below
+        float yv[4][8];               // kind 3: the 8 target channels of this voxel
+        const long long chan = (long long)p.d * plane;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int tp = zs[i].tap;
-          const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
-          const bool okk = vlive && (tp >> 6) && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h &&
-                           (unsigned)gw < (unsigned)p.w;
-          zv[i] = okk ? __ldg(reinterpret_cast<const uint4*>(vptr + zs[i].rel)) : make_uint4(0, 0, 0, 0);
+          const int tp = zs[i].tap, kind = tp >> 6;
+          zv[i] = make_uint4(0, 0, 0, 0);
+          if (kind == 1) {
+            const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
+            if (vlive && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w)
+              zv[i] = __ldg(reinterpret_cast<const uint4*>(vptr + zs[i].rel));
+          } else if (kind == 3) {
+            const float* yp = p.y + ((long long)nn * p.c2 + zs[i].rel) * chan + (vidx - (long long)nn * chan);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              yv[i][e] = (vlive && zs[i].rel + e < p.c2) ? __ldg(yp + (long long)e * chan) : 0.f;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int tp = ps[i].tap;
-          const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
-          const bool okk = vlive && (tp >> 6) && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h &&
-                           (unsigned)gw < (unsigned)p.w;
-          pv[i] = okk ? __ldg(reinterpret_cast<const uint4*>(vptr + ps[i].rel)) : make_uint4(0, 0, 0, 0);
+          const int tp = ps[i].tap, kind = tp >> 6;
+          pv[i] = make_uint4(0, 0, 0, 0);
+          if (kind == 1) {
+            const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
+            if (vlive && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w)
+              pv[i] = __ldg(reinterpret_cast<const uint4*>(vptr + ps[i].rel));
+          } else if (kind == 2 && vlive) {
+            pv[i].x = 0x3f80u;        // bf16 1.0 in row 0 of the chunk
+          }
         }
         if (!gt_mbar_wait<64>(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
         uint8_t* sbase = gsm + (size_t)stage * GT_STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t wds[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+          const int kind = zs[i].tap >> 6;
+          float pr[8];                                   // att-weighted left-operand values
+          if (kind == 3) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pr[e] = yv[i][e] * aw;
+          } else {
+            const uint32_t wds[4] = {zv[i].x, zv[i].y, zv[i].z, zv[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              pr[2 * e] = __uint_as_float(wds[e] << 16) * aw;
+              pr[2 * e + 1] = __uint_as_float(wds[e] & 0xffff0000u) * aw;
+            }
+            if (kind == 2) pr[0] = aw;                   // ones row: att_v * 1 (aw is 0 for dead voxels)
+          }
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float c0 = __uint_as_float(wds[e] << 16), c1 = __uint_as_float(wds[e] & 0xffff0000u);
-            const float p0 = c0 * aw, p1 = c1 * aw;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(p0 - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(p1 - __bfloat162float(h1));
-            hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const float p0 = pr[2 * e], p1 = pr[2 * e + 1];
+            const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
+            hi[e] = pack_bf16(p0, p1);
+            lo[e] = pack_bf16(p0 - h0, p1 - h1);
           }
           *reinterpret_cast<uint4*>(sbase + zs[i].dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -297,9 +337,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       tphase ^= 1u;
       const int qd = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half
-      const int ri = mb * GT_BM + qd * 32 + lane;        // tap-major row index
-      const bool row_ok = ri < p.k;
-      const int ref_i = row_ok ? (ri % p.c1) * 27 + ri / p.c1 : 0;
+      const int ri = mb * GT_BM + qd * 32 + lane;        // left row index (tap-major patch rows, then extras)
+      const int kp = p.k + p.has_bias;
+      int ref_i = -1;                                     // destination row in the workspace
+      if (ri < p.k) ref_i = (ri % p.c1) * 27 + ri / p.c1;
+      else if (ri == p.mx0 && p.has_bias) ref_i = p.k;                                   // bias row of A0
+      else if (p.y && ri >= p.mx0 + 8 && ri < p.mx0 + 8 + p.c2) ref_i = kp + (ri - p.mx0 - 8);   // B0 rows
+      const bool row_ok = ref_i >= 0;
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         uint32_t v[32];
         gt_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
@@ -309,8 +353,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
           for (int j = 0; j < 32; ++j) {
             const int cj = nb * GT_BN + c0 + j;
             const float val = __uint_as_float(v[j]);
-            if (cj < p.k && val != 0.f) {
-              const int ref_j = (cj % p.c1) * 27 + cj / p.c1;
+            if (val != 0.f && (cj < p.k || (cj == p.k && p.has_bias))) {
+              const int ref_j = cj < p.k ? (cj % p.c1) * 27 + cj / p.c1 : p.k;
               atomicAdd(p.acc + (long long)ref_i * p.ld + ref_j, (double)val);
             }
           }
@@ -338,10 +382,13 @@ extern "C" int effq_gram_tc_supported(const effq_geom* g) {
   return (k3 && g->c1 % 8 == 0 && g->c1 >= 8 && g->c1 <= 512) ? 1 : 0;
 }
 
-// Accumulates S (K x K block, reference row order, NOT yet scaled by 2 or the code scale)
-// into acc64[ld * i + j] (+=).  acc64 must have been zeroed by the caller.
-extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const effq_geom* g,
-                                       double* acc64, int32_t ld, void* flags, void* stream) {
+// Accumulates (+=) into acc64[ld * i + j], reference row order, NOT yet scaled by 2 or the code
+// scale: rows [0,K) x cols [0,K'] the attention-weighted Gram of the codes (incl. the bias
+// column), row K the bias row, rows K'.. the B0 rows (att*y against the codes) when y != NULL.
+// acc64 must have been zeroed by the caller.
+extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                                       const effq_geom* g, int32_t has_bias, double* acc64, int32_t ld,
+                                       void* flags, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && g && acc64 && flags, "null pointer");
   EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
@@ -349,13 +396,18 @@ extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const floa
   GtParams p;
   p.xq = (const __nv_bfloat16*)xcodes_ndhwc_bf16;
   p.att = att;
+  p.y = y;
   p.acc = acc64;
   p.flags = (unsigned int*)flags;
   p.n = g->n; p.c1 = g->c1; p.d = g->d; p.h = g->h; p.w = g->w;
   p.k = 27 * g->c1;
+  p.c2 = g->c2;
+  p.has_bias = has_bias ? 1 : 0;
   p.ld = ld;
-  p.mb_n = (p.k + GT_BM - 1) / GT_BM;
-  p.nb_n = (p.k + GT_BN - 1) / GT_BN;
+  p.mx0 = (p.k + GT_BM - 1) / GT_BM * GT_BM;                      // extras start on a row-block boundary
+  const int extra_rows = (has_bias || y) ? 8 + (y ? g->c2 : 0) : 0;
+  p.mb_n = (p.mx0 + extra_rows + GT_BM - 1) / GT_BM;
+  p.nb_n = (p.k + (has_bias ? 8 : 0) + GT_BN - 1) / GT_BN;
   p.hb_h = (g->h + 7) / 8;
   p.hb_w = (g->w + 7) / 8;
   p.hb_total = (long long)g->n * g->d * p.hb_h * p.hb_w;

@@ -48,13 +48,14 @@ def select_att(mask_pyramid: Optional[Sequence[torch.Tensor]], out_spatial) -> O
 
 
 def _moments(t: torch.Tensor, dist: DistCtx):
-    """(numel, unbiased std) over all ranks' shards (torch.std is unbiased, EfficientQConv.py:45-48)."""
+    """(numel, unbiased std, sum of squares) over all ranks' shards (torch.std is unbiased,
+    EfficientQConv.py:45-48)."""
     td = t.double()
     s = torch.stack([td.sum(), (td * td).sum(), torch.tensor(float(t.numel()), dtype=torch.float64, device=t.device)])
     s = dist.all_reduce_sum(s)
     tot, sq, n = [float(v) for v in s.tolist()]
     var = max(sq - tot * tot / n, 0.0) / max(n - 1.0, 1.0)
-    return n, var ** 0.5
+    return n, var ** 0.5, sq
 
 
 class LayerCalibrator:
@@ -118,7 +119,7 @@ class LayerCalibrator:
             att = att.to(dev).contiguous().float()
 
         # rho_scale (EfficientQConv.py:44-49, :60-61) -- global statistics over all shards
-        y_n, y_std = _moments(out_fp, dist)
+        y_n, y_std, y_sq = _moments(out_fp, dist)
         w_std = float(w0.std().item())
         rs = max(y_n * y_std / (w0.numel() * w_std), 1.0)
         if att is not None:
@@ -147,13 +148,22 @@ class LayerCalibrator:
         gram_flag = None
         if use_tc and ops.gram_tc_supported(x.shape, c2, ksize, stride, padding):
             code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
-            a0, b0, self.gram_ws, gram_flag = ops.gram_tc(xcodes, code_scale, qx, out_fp, att, has_bias=has_bias,
+            a0, b0, self.gram_ws, gram_flag = ops.gram_tc(xcodes, code_scale, out_fp, att, has_bias=has_bias,
                                                           ws=self.gram_ws)
         else:
             a0, b0 = ops.gram(qx, out_fp, att, ksize, stride, padding, has_bias=has_bias, ws=self.gram_ws)
         if dist.world > 1:
             dist.all_reduce_sum(a0)
             dist.all_reduce_sum(b0)
+        # un-quantised input (conv0 / final_cls): the conv input never changes, so the per-iterate
+        # loss comes from fp64 sufficient statistics instead of 200 fp32 convs
+        stats64 = None
+        if not use_tc and not q_act and kp <= 512:
+            stats64 = ops.gram_f64(qx, out_fp, ksize, stride, padding, has_bias=has_bias)
+            if dist.world > 1:
+                dist.all_reduce_sum(stats64)
+            if self._qf_ws is None:
+                self._qf_ws = ops.workspace(16 + 8 * 1024, dev)
         w0p = torch.cat([w0.reshape(c2, k), bias.detach().float().reshape(c2, 1)], 1).contiguous() if has_bias \
             else w0.reshape(c2, k).contiguous()
 
@@ -205,10 +215,12 @@ class LayerCalibrator:
             if use_tc:
                 ops.conv3d_tc(xcodes, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
                               target=out_fp, ws=self.tc_ws, sse=self.sse)
+            elif stats64 is not None:
+                ops.quadform_sse(stats64, y_sq, g, bstar, self.sse, self._qf_ws)      # already global
             else:
                 ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
                                ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
-            if dist.world > 1:
+            if dist.world > 1 and stats64 is None:
                 dist.all_reduce_sum(self.sse)
             ops.admm_track(self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes)
             rho = new_rho
@@ -245,6 +257,7 @@ class LayerCalibrator:
         return best_g.view(c2, c1, *ksize), best_b, alpha_w, alpha_act, out_q, rep
 
     _cws = None
+    _qf_ws = None
 
     def _conv_ws(self, x, c2, ksize, stride, padding):
         import ctypes as C

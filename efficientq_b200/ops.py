@@ -308,16 +308,36 @@ def gram(x, y, att, ksize, stride, padding, has_bias=True, x_scale=None, ws=None
     return a0, b0
 
 
+def gram_f64(x, y, ksize, stride, padding, has_bias=True):
+    """Unweighted fp64 statistics [S ; T] ((K'+C2) x K') for conv-free scoring."""
+    x = _f32c(x, "x")
+    y = _f32c(y, "y")
+    g = Geom.make(x.shape, y.shape[1], ksize, stride, padding)
+    kp = g.c1 * g.taps + (1 if has_bias else 0)
+    acc = torch.empty((kp + g.c2, kp), dtype=torch.float64, device=x.device)
+    od, oh, ow = g.out_spatial()
+    timer.run("gram_f64", {"flops": 2.0 * g.n * od * oh * ow * (kp + g.c2) * kp}, lambda: check(
+        capi.load().effq_gram_f64(ptr(x), ptr(y), C.byref(g), int(has_bias), ptr(acc), stream()), "effq_gram_f64"))
+    return acc
+
+
+def quadform_sse(acc, sum_y2: float, g, bstar, sse, ws):
+    """sse <- sum((conv(x,G)+b*-y)^2) from the fp64 statistics (one tiny launch per iterate)."""
+    c2, k = g.shape
+    check(capi.load().effq_quadform_sse(ptr(acc), float(sum_y2), ptr(g), ptr(bstar), c2, k, int(bstar is not None),
+                                        ptr(sse), ptr(ws), stream()), "effq_quadform_sse")
+
+
 def gram_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
     g = Geom.make(x_shape, c2, ksize, stride, padding)
     return bool(capi.load().effq_gram_tc_supported(C.byref(g)))
 
 
-def gram_tc(xcodes, code_scale, x_values, y, att, has_bias=True, ws=None):
-    """A0, B0 with the K x K block on the tensor cores (3x3x3, stride 1, pad 1)."""
-    x_values = _f32c(x_values, "x_values")
+def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None):
+    """A0, B0 on the tensor cores from the NDHWC codes (3x3x3, stride 1, pad 1)."""
     y = _f32c(y, "y")
-    g = Geom.make(x_values.shape, y.shape[1], 3, 1, 1)
+    n, d, h, w, c1 = xcodes.shape
+    g = Geom.make((n, c1, d, h, w), y.shape[1], 3, 1, 1)
     k = g.c1 * 27
     kp = k + (1 if has_bias else 0)
     lib = capi.load()
@@ -330,9 +350,9 @@ def gram_tc(xcodes, code_scale, x_values, y, att, has_bias=True, ws=None):
         att = _f32c(att, "att")
     cs = _f32c(code_scale.reshape(1), "code_scale")
     od, oh, ow = g.out_spatial()
-    flops = 2.0 * g.n * od * oh * ow * k * k
+    flops = 2.0 * g.n * od * oh * ow * (kp + g.c2) * kp
     timer.run("gram_tc", {"flops": flops}, lambda: check(
-        lib.effq_gram_tc(ptr(xcodes), ptr(cs), ptr(x_values), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0),
+        lib.effq_gram_tc(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0),
                          ptr(b0), ptr(ws), stream()), "effq_gram_tc"))
     flag = ws[need - 16:need - 12].view(torch.int32)       # non-zero if the tcgen05 kernel aborted
     return a0, b0, ws, flag

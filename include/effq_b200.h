@@ -154,18 +154,30 @@ int effq_gram_f32(const float* x, const float* x_scale, const float* y, const fl
                   const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out,
                   void* workspace, void* stream);
 
+/* Scoring without re-running the conv, for layers whose input is NOT quantised (the input is
+ * the same tensor in all 200 iterations): unweighted S = X^ X^T, T = Y X^T accumulated once in
+ * fp64 into acc64_out[(K'+C2) x K'] (effq_gram_f64), then per iterate
+ *   sse = sum_r [ w_r S w_r^T - 2 w_r.T_r ] + sum_y2      (effq_quadform_sse)
+ * which equals sum((conv3d(x, G) + b* - y)^2) of EfficientQConv.py:118-122 up to fp64 rounding.
+ * quadform workspace: 16 + 8*c2 bytes, zero-initialised once. */
+int effq_gram_f64(const float* x, const float* y, const effq_geom* g, int32_t has_bias, double* acc64_out,
+                  void* stream);
+int effq_quadform_sse(const double* acc64, double sum_y2, const float* gw, const float* bstar, int32_t c2,
+                      int32_t k, int32_t has_bias, double* sse, void* workspace, void* stream);
+
 /* Same statistics on the tensor cores for 3x3x3 / stride 1 / pad 1 layers with quantised
- * activations: the K x K block of A0 from the NDHWC integer codes (tcgen05, att folded into a
- * bf16 hi+lo split of the left operand), the bias row/column and B0 from the generic kernel on
- * x_values (= code_scale * codes, NCDHW fp32).  code_scale is a device fp32 scalar.
- * If the tcgen05 kernel aborts (barrier timeout) the abort word after the accumulator in the
+ * activations, from the NDHWC integer codes: A0 (with its bias row / column) and B0 in one
+ * tcgen05 kernel (att and att*y enter as bf16 hi+lo splits of the left operand, the codes are
+ * exact); code_scale (device fp32 scalar, activation = code_scale * code) is applied in the
+ * finalize pass.  If the kernel aborts (barrier timeout) the word after the accumulator in the
  * workspace is non-zero. */
 int effq_gram_tc_supported(const effq_geom* g);
-int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* x_values,
-                 const float* y, const float* att, const effq_geom* g, int32_t has_bias,
-                 float* a0_out, float* b0_out, void* workspace, void* stream);
-int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const effq_geom* g,
-                            double* acc64, int32_t ld, void* flags, void* stream);
+int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y, const float* att,
+                 const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out, void* workspace,
+                 void* stream);
+int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                            const effq_geom* g, int32_t has_bias, double* acc64, int32_t ld, void* flags,
+                            void* stream);
 
 /* ---- (a9,a11) ADMM parameter update: solver.py:316-325, EfficientQConv.py:99-144 */
 /* B = B0 + eta*W0' ;  B[:, :K] += rho*(G - dual)          (solver.py:317-320) */

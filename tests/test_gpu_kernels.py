@@ -272,7 +272,7 @@ def test_gram_tc_matches_generic_and_oracle(ops, n, c1, c2, sp, la, int_att):
     y = torch.randn(n, c2, *sp)
     att = (torch.rand(n, *sp) * 3).floor() + 1 if int_att else torch.rand(n, *sp) * 2 + 0.25
     xq = codes.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
-    a0, b0, _, flag = ops.gram_tc(xq, torch.tensor([sc], device=DEV), x.to(DEV), y.to(DEV), att.to(DEV), True)
+    a0, b0, _, flag = ops.gram_tc(xq, torch.tensor([sc], device=DEV), y.to(DEV), att.to(DEV), True)
     assert int(flag.item()) == 0
     cols = O.im2col(x, 3, 3, 3, 1, 1).double()
     cols = torch.cat([cols, torch.ones(1, cols.shape[1], dtype=torch.float64)], 0)
@@ -287,6 +287,27 @@ def test_gram_tc_matches_generic_and_oracle(ops, n, c1, c2, sp, la, int_att):
     g0, gb0 = ops.gram(x.to(DEV), y.to(DEV), att.to(DEV), (3, 3, 3), 1, 1, has_bias=True)
     assert (a0 - g0).abs().max().item() <= tol * scale
     assert torch.allclose(b0, gb0, rtol=1e-5, atol=1e-5 * b_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("n,c1,c2,k,s,p,sp", [(2, 4, 32, 3, 2, 1, (16, 16, 16)), (2, 32, 3, 1, 1, 0, (8, 16, 8))])
+def test_quadform_scoring_equals_conv_sse(ops, n, c1, c2, k, s, p, sp):
+    """Conv-free scoring of the un-quantised-input layers: fp64 statistics + quadratic form must
+    reproduce sum((conv(x,G)+b-y)^2) (here against an fp64 conv on the CPU)."""
+    torch.manual_seed(17)
+    x = torch.randn(n, c1, *sp)
+    w0 = torch.randn(c2, c1, k, k, k) * 0.1
+    b0 = torch.randn(c2) * 0.1
+    y = F.conv3d(x, w0, b0, s, p)
+    acc = ops.gram_f64(x.to(DEV), y.to(DEV), (k, k, k), s, p, has_bias=True)
+    yy = (y.double() ** 2).sum().item()
+    ws = ops.workspace(16 + 8 * 1024, torch.device(DEV))
+    sse = torch.zeros(1, dtype=torch.float64, device=DEV)
+    for eps in (1e-2, 1e-3):                      # quantisation-sized perturbations of the weights
+        g = w0 + eps * torch.randn_like(w0)
+        b = b0 + eps * torch.randn_like(b0)
+        ref = ((F.conv3d(x.double(), g.double(), b.double(), s, p) - y.double()) ** 2).sum().item()
+        ops.quadform_sse(acc, yy, g.reshape(c2, -1).contiguous().to(DEV), b.to(DEV), sse, ws)
+        assert abs(sse.item() - ref) <= 1e-4 * ref, (sse.item(), ref)
 
 
 # ---------------------------------------------------------------- ADMM update (a9, a11)

@@ -31,7 +31,7 @@ sse = torch.zeros(1, dtype=torch.float64, device=dev)
 for _ in range(4):
     ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=y, ws=ws, sse=sse)
 code_scale = (st.a_f32() / 15.0).reshape(1)
-a0, b0, _, flag = ops.gram_tc(xq, code_scale, qx, y, att, True)
+a0, b0, _, flag = ops.gram_tc(xq, code_scale, y, att, True)
 sol = torch.randn(c, c * 27 + 1, device=dev) * 0.05
 dual = torch.zeros(c, c * 27, device=dev)
 wst = ops.ScaleState(dev)

@@ -351,15 +351,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       // anything consumes them (32 independent requests in flight per thread), the first chunk
       // even before waiting for the accumulator.
       const bool want_t = live && p.target != nullptr;
-      // two register buffers: the loads of chunk c+1 are in flight while chunk c is consumed
-      float tva[32], tvb[32];
-      auto load_targets = [&](float (&tv)[32], int c0) {
+      // (a second register buffer for the next chunk's loads was tried: 168 registers with spills,
+      //  12-25 % slower -- profiles/r01_conv_layout.md)
+      float tv[32];
+      auto load_targets = [&](int c0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           tv[j] = (want_t && c0 + j < p.c2) ? __ldg(p.target + base + (long long)(c0 + j) * chan) : 0.f;
       };
+      load_targets(0);
+      if (!mbar_wait<64>(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
+      if (threadIdx.x == 64) dbg_stamp(p, tile, 3);
+      tc_fence_after();
       float e32 = 0.f;
-      auto consume = [&](const float (&tv)[32], int c0) {
+      for (int c0 = 0; c0 < p.c2; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.c2 + c0);
         const int ncol = min(32, p.c2 - c0);
@@ -372,23 +377,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
           const float dlt = o[j] - tv[j];
           if (j < ncol) e32 = fmaf(dlt, dlt, e32);
         }
+        if (c0 + 32 < p.c2) load_targets(c0 + 32);       // next chunk's loads overlap this chunk's stores
         if (live && p.out) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < ncol) __stcs(p.out + base + (long long)(c0 + j) * chan, o[j]);
-        }
-      };
-      load_targets(tva, 0);
-      if (32 < p.c2) load_targets(tvb, 32);
-      if (!mbar_wait<64>(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
-      if (threadIdx.x == 64) dbg_stamp(p, tile, 3);
-      tc_fence_after();
-      for (int c0 = 0; c0 < p.c2; c0 += 64) {
-        consume(tva, c0);
-        if (c0 + 64 < p.c2) load_targets(tva, c0 + 64);
-        if (c0 + 32 < p.c2) {
-          consume(tvb, c0 + 32);
-          if (c0 + 96 < p.c2) load_targets(tvb, c0 + 96);
         }
       }
       tc_fence_before();

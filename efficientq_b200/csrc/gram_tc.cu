@@ -14,7 +14,8 @@
 //     [64-row block][voxel][64 rows].  L1 serves the 27-fold tap reuse of a voxel block.
 //   * the left operand carries the attention weight: p = att_v * code (fp32), split into
 //     bf16 hi + bf16 lo (two MMAs, error <= 2^-17 per term, exact for the reference's integer
-//     masks); the right operand is the raw integer code (exact).
+//     masks); the rows of B0 (att_v * y, arbitrary fp32) and the bias row use a three-term
+//     split (24 bits: fp32-exact); the right operand is the raw integer code (exact).
 //   * one thread issues tcgen05.mma M=128,N=256,K=16 (both operands MN-major) -- the only
 //     shape at which the SS tensor pipe is not starved by the A-operand read (B200: one A row
 //     per cycle, profiles/r01_conv_layout.md) -- into a 128x256 fp32 TMEM accumulator.
@@ -33,7 +34,7 @@ constexpr int GT_KV = 64;                  // voxels per stage: 8 h-rows x 8 w
 constexpr int GT_BM = 128, GT_BN = 256;
 constexpr uint32_t GT_ZBYTES = 2 * GT_KV * 128;      // 128 rows = 2 blocks of 64 rows: 16 KB
 constexpr uint32_t GT_PBYTES = 4 * GT_KV * 128;      // 256 rows: 32 KB
-constexpr uint32_t GT_STAGE_BYTES = 2 * GT_ZBYTES + GT_PBYTES;   // Zhi, Zlo, P = 64 KB
+constexpr uint32_t GT_STAGE_BYTES = 3 * GT_ZBYTES + GT_PBYTES;   // Zhi, Zlo, Zlo2, P = 80 KB
 constexpr unsigned int GT_SPIN_LIMIT = 1u << 26;
 
 struct GtParams {
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       bool ok = true;
       for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
         const int z = (int)(item % p.splits);
+        const bool three = (int)(item / ((long long)p.splits * p.nb_n)) * GT_BM >= p.mx0;   // y / ones rows: 3-term split
         long long hb0 = (long long)z * p.hb_per_split;
         long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
         if (!gt_mbar_wait(TEMPTY, tphase ^ 1u, abort_flag)) { ok = false; break; }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
           if (!gt_mbar_wait(FULL(stage), phase, abort_flag)) { ok = false; break; }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t zhi = (stage0 + (uint32_t)stage * GT_STAGE_BYTES) >> 4;
-          const uint32_t zlo = zhi + (GT_ZBYTES >> 4), pp = zhi + ((2 * GT_ZBYTES) >> 4);
+          const uint32_t zlo = zhi + (GT_ZBYTES >> 4), zl2 = zhi + ((2 * GT_ZBYTES) >> 4), pp = zhi + ((3 * GT_ZBYTES) >> 4);
           if (gt_elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < GT_KV / 16; ++ks) {
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
               const uint64_t bd = tmpl | (uint64_t)((pp + koff) & 0x3fffu);
               gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, ks == 0 ? accum : 1u);
               gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
+              if (three) gt_mma(tmem_base, tmpl | (uint64_t)((zl2 + koff) & 0x3fffu), bd, idesc, 1u);
             }
             gt_commit(EMPTY(stage));
             if (hb == hb1 - 1) gt_commit(TFULL);
@@ -314,19 +317,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
             }
             if (kind == 2) pr[0] = aw;                   // ones row: att_v * 1 (aw is 0 for dead voxels)
           }
-          uint32_t hi[4], lo[4];
+          uint32_t hi[4], lo[4], l2[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float p0 = pr[2 * e], p1 = pr[2 * e + 1];
             const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
+            const float r0 = p0 - h0, r1 = p1 - h1;                       // exact in fp32
+            const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
             hi[e] = pack_bf16(p0, p1);
-            lo[e] = pack_bf16(p0 - h0, p1 - h1);
+            lo[e] = pack_bf16(r0, r1);
+            l2[e] = pack_bf16(r0 - m0, r1 - m1);                          // third term: 24 bits in total
           }
           *reinterpret_cast<uint4*>(sbase + zs[i].dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (kind >= 2) *reinterpret_cast<uint4*>(sbase + 2 * GT_ZBYTES + zs[i].dst) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sbase + 2 * GT_ZBYTES + ps[i].dst) = pv[i];
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sbase + 3 * GT_ZBYTES + ps[i].dst) = pv[i];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         gt_mbar_arrive(FULL(stage));
         if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }

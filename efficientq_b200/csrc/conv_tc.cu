@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     bool ok = true;
     bool pending = false;
     int pending_stage = 0;
+    const bool defer = p.n_halo_stages >= 3;       // deep ring: keep one extra block of copies in flight
     for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
       unsigned int r = tile;
       const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
@@ -457,6 +458,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         }
         cp_async_commit();
         if (ptid == 0 && g == 0) dbg_stamp(p, tile, 6);
+        if (!defer) {
+          // two halo stages: signal this block as soon as it has landed.  (Deferring the signal
+          // behind the NEXT block's issue, as below, would chain MMA(t) to MMA(t-1) through the
+          // wait for a free stage.)
+          cp_async_wait<0>();
+          fence_proxy_async();
+          mbar_arrive(BAR(B_HF + hp.stage));
+          hp.advance(p.n_halo_stages);
+          continue;
+        }
         if (pending) {                              // previous block: complete -> visible to the async proxy -> signal
           cp_async_wait<1>();
           fence_proxy_async();

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(FQ_THREADS)
 fakequant_f32_kernel(const float* __restrict__ x, long long numel, const float* __restrict__ alpha_p,
                      QParamF q, float* __restrict__ y, uint8_t* __restrict__ code) {
   const float alpha = __ldg(alpha_p);
+  const QFastF qf = make_qfast_f(alpha, q, (int)(rintf((q.hi - q.lo) / q.delta)) + 1);
   const long long nvec = numel / FQ_VEC;
   const long long stride = (long long)gridDim.x * FQ_THREADS;
   long long i = (long long)blockIdx.x * FQ_THREADS + threadIdx.x;
@@ -36,7 +37,7 @@ fakequant_f32_kernel(const float* __restrict__ x, long long numel, const float* 
       uint32_t packed = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float idx = level_index_f(__fdiv_rn(in[e], alpha), q);
+        float idx = level_index_fast_f(in[e], alpha, q, qf);
         out[e] = __fmul_rn(level_value_f(idx, q), alpha);
         packed |= ((uint32_t)(int)idx & 0xffu) << (8 * e);
       }
@@ -48,7 +49,7 @@ fakequant_f32_kernel(const float* __restrict__ x, long long numel, const float* 
   if (blockIdx.x == 0) {
     long long t = nvec * FQ_VEC + threadIdx.x;
     if (t < numel) {
-      float idx = level_index_f(__fdiv_rn(x[t], alpha), q);
+      float idx = level_index_fast_f(x[t], alpha, q, qf);
       if (WRITE_Y) y[t] = __fmul_rn(level_value_f(idx, q), alpha);
       if (WRITE_C) code[t] = (uint8_t)(int)idx;
     }
@@ -62,10 +63,21 @@ fakequant_state_kernel(const float* __restrict__ x, long long numel, const effq_
                        QParamD q, float* __restrict__ y) {
   const double a64 = st->a;
   const float a32 = (float)a64;
-  for (long long i = (long long)blockIdx.x * FQ_THREADS + threadIdx.x; i < numel;
-       i += (long long)gridDim.x * FQ_THREADS) {
-    const double idx = level_index_d(__ddiv_rn((double)__ldcs(x + i), a64), q);
-    y[i] = __fmul_rn(a32, (float)level_value_d(idx, q));
+  const QFastD qf = make_qfast_d(a64, q, (int)(rint((q.hi - q.lo) / q.delta)) + 1);
+  const long long nvec = numel / 4;
+  const long long stride = (long long)gridDim.x * FQ_THREADS;
+  for (long long i = (long long)blockIdx.x * FQ_THREADS + threadIdx.x; i < nvec; i += stride) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+    float4 o;
+    o.x = __fmul_rn(a32, (float)level_value_d(level_index_fast_d((double)v.x, a64, q, qf), q));
+    o.y = __fmul_rn(a32, (float)level_value_d(level_index_fast_d((double)v.y, a64, q, qf), q));
+    o.z = __fmul_rn(a32, (float)level_value_d(level_index_fast_d((double)v.z, a64, q, qf), q));
+    o.w = __fmul_rn(a32, (float)level_value_d(level_index_fast_d((double)v.w, a64, q, qf), q));
+    __stcs(reinterpret_cast<float4*>(y) + i, o);
+  }
+  if (blockIdx.x == 0) {
+    const long long t = nvec * 4 + threadIdx.x;
+    if (t < numel) y[t] = __fmul_rn(a32, (float)level_value_d(level_index_fast_d((double)x[t], a64, q, qf), q));
   }
 }
 
@@ -90,16 +102,18 @@ quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int
 
   const QParamF qf = make_qparam_f(0.f, 1.f, nlvl);
   const QParamD qd = make_qparam_d(0.f, 1.f, nlvl);
-  const double a64 = F64 ? st->a : 0.0;
-  const float a32 = F64 ? 0.f : __ldg(alpha_f32);
+  const double a64 = F64 ? st->a : 1.0;
+  const float a32 = F64 ? 1.f : __ldg(alpha_f32);
+  const QFastD fd = make_qfast_d(a64, qd, nlvl);
+  const QFastF ff = make_qfast_f(a32, qf, nlvl);
 
   for (int e = threadIdx.x; e < c * QA_TILE_V; e += QA_THREADS) {
     const int ch = e / QA_TILE_V, v = e % QA_TILE_V;
     float code = 0.f;
     if (v < nv) {
       const float val = __ldcs(xs + (long long)ch * dhw + v);
-      if (F64) code = (float)level_index_d(__ddiv_rn((double)val, a64), qd);
-      else     code = level_index_f(__fdiv_rn(val, a32), qf);
+      if (F64) code = (float)level_index_fast_d((double)val, a64, qd, fd);
+      else     code = level_index_fast_f(val, a32, qf, ff);
     }
     tile[v * cp + ch] = __float2bfloat16_rn(code);
   }

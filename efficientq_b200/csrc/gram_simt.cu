@@ -166,10 +166,13 @@ __global__ void gram_finalize_kernel(const double* __restrict__ acc64, const flo
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / kp), j = (int)(e % kp);
-    if (tc_block) {
-      if (i < k) a0[e] = j < k ? (float)(2.0 * s * s * acc64[e]) : (float)(2.0 * acc64[(long long)k * kp + i]);
-      else if (i < kp) a0[e] = (float)(2.0 * acc64[e]);
-      else b0[(long long)(i - kp) * kp + j] = (float)(2.0 * acc64[e]);
+    if (tc_block && i < k && j < k) {
+      // tensor-core path: tiles below the diagonal (in the kernel's tap-major order, 128 x 256
+      // tiles) were skipped -- mirror them from the transpose.  tc_block = C1.
+      const int c1 = tc_block;
+      const int ti = (i % 27) * c1 + i / 27, tj = (j % 27) * c1 + j / 27;
+      const bool skipped = (ti / 128) * 128 >= (tj / 256 + 1) * 256;
+      a0[e] = (float)(2.0 * s * s * acc64[skipped ? (long long)j * kp + i : e]);
       continue;
     }
     const double sj = j < k ? s : 1.0;
@@ -257,7 +260,7 @@ extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_sca
   const long long total = (long long)mrows * kp;
   int fb = (int)((total + 255) / 256);
   if (fb > sm_count() * 16) fb = sm_count() * 16;
-  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, code_scale, k, kp, g->c2, 0, a0_out, b0_out);
+  gram_finalize_kernel<<<fb, 256, 0, s>>>((const double*)workspace, code_scale, k, kp, g->c2, g->c1, a0_out, b0_out);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

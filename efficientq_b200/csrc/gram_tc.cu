@@ -125,6 +125,12 @@ __device__ __forceinline__ uint64_t gt_desc(uint32_t saddr, uint32_t lbo_bytes, 
 //   kind 2: the "ones" chunk: row 0 = 1, rows 1-7 = 0         (bias row / column)
 //   kind 3: 8 channels of the fp32 target y                   (left operand only: rows of B0)
 //   kind 0: zero padding
+// The patch x patch part of S is symmetric: a (128-row, 256-column) tile that lies entirely
+// below the diagonal is not computed; the finalize pass mirrors it from its transpose.
+__device__ __host__ __forceinline__ bool gt_tile_skipped(int mb, int nb, int mx0) {
+  return mb * GT_BM < mx0 && mb * GT_BM >= (nb + 1) * GT_BN;
+}
+
 struct Slot {
   int rel;          // kind 1: element offset relative to the voxel's own vector; kind 3: first y channel
   int tap;          // (a) | (b << 2) | (c << 4) | kind << 6      (a,b,c in 0..2)
@@ -152,9 +158,10 @@ __device__ __forceinline__ Slot make_slot(int row0, int rc, int kvox, const GtPa
   return s;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) |
-         ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+// two fp32 -> packed bf16x2 (first argument in the low half), round to nearest even
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p) {
@@ -205,6 +212,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       bool ok = true;
       for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
         const int z = (int)(item % p.splits);
+        {
+          const long long rr = item / p.splits;
+          if (gt_tile_skipped((int)(rr / p.nb_n), (int)(rr % p.nb_n), p.mx0)) continue;
+        }
         const bool three = (int)(item / ((long long)p.splits * p.nb_n)) * GT_BM >= p.mx0;   // y / ones rows: 3-term split
         long long hb0 = (long long)z * p.hb_per_split;
         long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       const int z = (int)(r % p.splits); r /= p.splits;
       const int nb = (int)(r % p.nb_n); r /= p.nb_n;
       const int mb = (int)r;
+      if (gt_tile_skipped(mb, nb, p.mx0)) continue;
       Slot zs[4], ps[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + 4 * i, kvox, p, true);
@@ -321,12 +333,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float p0 = pr[2 * e], p1 = pr[2 * e + 1];
-            const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
-            const float r0 = p0 - h0, r1 = p1 - h1;                       // exact in fp32
-            const float m0 = __bfloat162float(__float2bfloat16_rn(r0)), m1 = __bfloat162float(__float2bfloat16_rn(r1));
-            hi[e] = pack_bf16(p0, p1);
-            lo[e] = pack_bf16(r0, r1);
-            l2[e] = pack_bf16(r0 - m0, r1 - m1);                          // third term: 24 bits in total
+            hi[e] = pack2(p0, p1);                                        // one cvt.rn.bf16x2.f32
+            const float r0 = p0 - __uint_as_float(hi[e] << 16), r1 = p1 - __uint_as_float(hi[e] & 0xffff0000u);   // exact
+            lo[e] = pack2(r0, r1);
+            l2[e] = 0;
+            if (kind >= 2)                                                // third term: 24 bits in total
+              l2[e] = pack2(r0 - __uint_as_float(lo[e] << 16), r1 - __uint_as_float(lo[e] & 0xffff0000u));
           }
           *reinterpret_cast<uint4*>(sbase + zs[i].dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

@@ -44,23 +44,40 @@ __device__ __forceinline__ float load_v(const VecView& vv, long long r, long lon
 // a sum by one level step on one element out of millions -- far below the 1e-5 stopping
 // rule.  The FINAL discretize (effq_fakequant_state / effq_quantize_act_ndhwc /
 // effq_admm_project) keeps the exact divisions and is bit-exact.
+// With b = idx*delta + lo:  sum b*v = delta*S_iv + lo*S_v ;  sum b*b = delta^2*S_ii + 2*delta*lo*S_i
+// + lo^2*n, so a pass only accumulates S_iv = sum idx*v (fp64 FMA) and the INTEGER sums S_ii, S_i
+// (exact); S_v and n are pass-invariant.  Per element: 1 FMA (q), 2 min/max, 1 rint, 1 FMA on the
+// fp64 pipe plus integer work -- about half of the straightforward formulation.
 struct PassQ {
-  double inv_a, lo, hi, inv_delta, delta;
+  double c1, c0, lm1;
 };
 __device__ __forceinline__ PassQ make_passq(double a, const QParamD& q) {
   PassQ p;
-  p.inv_a = 1.0 / a;
-  p.lo = q.lo;
-  p.hi = q.hi;
-  p.delta = q.delta;
-  p.inv_delta = 1.0 / q.delta;
+  p.c1 = 1.0 / (a * q.delta);
+  p.c0 = -q.lo / q.delta;
+  p.lm1 = (q.hi - q.lo) / q.delta;
   return p;
 }
-__device__ __forceinline__ void accum_bv(double v, const PassQ& p, double& s0, double& s1) {
-  double t = v * p.inv_a;
-  t = fmin(fmax(t, p.lo), p.hi);
-  const double idx = rint((t - p.lo) * p.inv_delta);
-  const double b = __dadd_rn(__dmul_rn(idx, p.delta), p.lo);
+struct PassAcc {
+  double s_iv, s_ii, s_i;       // idx <= 255: s_ii, s_i stay exact integers in fp64 (< 2^53)
+};
+__device__ __forceinline__ void accum_idx(double v, const PassQ& p, PassAcc& acc) {
+  const double idx = rint(fmin(fmax(fma(v, p.c1, p.c0), 0.0), p.lm1));
+  acc.s_iv = fma(idx, v, acc.s_iv);
+  acc.s_ii = fma(idx, idx, acc.s_ii);
+  acc.s_i += idx;
+}
+// (sum b*v, sum b*b) of this thread's share from the index sums; s_v / cnt are the thread's
+// pass-invariant sum of v and element count.
+__device__ __forceinline__ void finish_bv(const PassAcc& acc, const QParamD& q, double s_v, double cnt, double& s0,
+                                          double& s1) {
+  s0 = q.delta * acc.s_iv + q.lo * s_v;
+  s1 = q.delta * q.delta * acc.s_ii + 2.0 * q.delta * q.lo * acc.s_i + q.lo * q.lo * cnt;
+}
+// compatibility wrapper (one element at a time)
+__device__ __forceinline__ void accum_bv(double v, const PassQ& p, const QParamD& q, double& s0, double& s1) {
+  const double idx = rint(fmin(fmax(fma(v, p.c1, p.c0), 0.0), p.lm1));
+  const double b = __dadd_rn(__dmul_rn(idx, q.delta), q.lo);
   s0 = fma(b, v, s0);
   s1 = fma(b, b, s1);
 }
@@ -72,6 +89,8 @@ __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QPa
   s0 = 0.0;
   s1 = 0.0;
   const PassQ pq = make_passq(MODE == 1 ? a : 1.0, q);
+  PassAcc pa{0.0, 0.0, 0.0};
+  double s_v = 0.0, cnt = 0.0;
   const long long numel = vv.rows * vv.cols;
   const bool flat = (vv.ld1 == vv.cols) && (!vv.v2 || vv.ld2 == vv.cols);
   const long long stride = nctas * SS_THREADS;
@@ -92,7 +111,7 @@ __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QPa
       for (int k = 0; k < 4; ++k) {
         const double v = (double)e[k];
         if (MODE == 0) s0 += fabs(v);
-        else accum_bv(v, pq, s0, s1);
+        else { accum_idx(v, pq, pa); s_v += v; cnt += 1.0; }
       }
     }
   } else {
@@ -105,9 +124,10 @@ __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QPa
       if (c >= vv.cols) continue;
       const double v = (double)load_v(vv, r, c);
       if (MODE == 0) s0 += fabs(v);
-      else accum_bv(v, pq, s0, s1);
+      else { accum_idx(v, pq, pa); s_v += v; cnt += 1.0; }
     }
   }
+  if (MODE == 1) finish_bv(pa, q, s_v, cnt, s0, s1);
 }
 
 // Every CTA folds the per-CTA partials in the same order (thread t takes slots
@@ -203,7 +223,7 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
       s1 = 0.0;
 #pragma unroll
       for (int k = 0; k < REG_ITEMS; ++k)
-        if (k < nvalid) accum_bv(vreg[k], pq, s0, s1);     // padding must not count: Q(0) != 0 on symmetric grids
+        if (k < nvalid) accum_bv(vreg[k], pq, q, s0, s1);  // padding must not count: Q(0) != 0 on symmetric grids
     } else {
       pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
     }
@@ -230,8 +250,8 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
   }
 }
 
-// ---- cluster variant: tensors up to 8 x 56 K elements (every weight tensor of the BraTS net
-// except the two 256x6912 ones).  One thread-block cluster; each CTA keeps its slice of v in
+// ---- cluster variant: tensors up to 128 K elements (measured crossover against the 148-CTA
+// grid variant, profiles/r01_scale_search.md).  One thread-block cluster; each CTA keeps its slice of v in
 // shared memory for the whole search; a pass ends with ONE hardware cluster barrier and every
 // CTA folds the per-CTA partial sums straight out of its peers' shared memory (DSMEM) in rank
 // order, so all CTAs see bit-identical scales.  No global-memory round trip per pass.
@@ -282,6 +302,8 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
 
   int parity = 0;
   double s0 = 0.0, s1 = 0.0;
+  double my_sv = 0.0, my_cnt = 0.0;                  // pass-invariant: this thread's sum of v and count
+  for (int i = threadIdx.x; i < mine; i += SC_THREADS) { my_sv += (double)sv[i]; my_cnt += 1.0; }
   for (int i = threadIdx.x; i < mine; i += SC_THREADS) s0 += fabs((double)sv[i]);
   s0 = block_sum(s0, scratch);
   if (threadIdx.x == 0) { slot[parity][0] = s0; slot[parity][1] = 0.0; }
@@ -297,7 +319,11 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
     const PassQ pq = make_passq(a, q);
     s0 = 0.0;
     s1 = 0.0;
-    for (int i = threadIdx.x; i < mine; i += SC_THREADS) accum_bv((double)sv[i], pq, s0, s1);
+    {
+      PassAcc pa{0.0, 0.0, 0.0};
+      for (int i = threadIdx.x; i < mine; i += SC_THREADS) accum_idx((double)sv[i], pq, pa);
+      finish_bv(pa, q, my_sv, my_cnt, s0, s1);
+    }
     s0 = block_sum(s0, scratch);
     s1 = block_sum(s1, scratch);
     if (threadIdx.x == 0) { slot[parity][0] = s0; slot[parity][1] = s1; }
@@ -416,7 +442,7 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   const long long numel = rows * cols;
   const int sms = sm_count();                         // one CTA per SM: cheapest grid barrier
   VecView vv{v1, v2, ld1, ld2, rows, cols};
-  if (numel <= 8ll * SC_MAX_ELEMS) {                 // portable cluster size (<= 8 CTAs)
+  if (numel <= 131072) {       // measured: cluster wins up to ~128 K elements, the 148-CTA grid beyond
     // small tensors (weights): one thread-block cluster, data resident in shared memory
     int nranks = (int)((numel + SC_MAX_ELEMS - 1) / SC_MAX_ELEMS);
     if (nranks < 8 && numel > 8192) {                 // spread the per-pass arithmetic a little

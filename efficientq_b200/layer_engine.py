@@ -173,7 +173,7 @@ class LayerCalibrator:
         best_g = torch.empty_like(g)
         best_b = torch.empty_like(bstar) if has_bias else None
         bmat = torch.empty((c2, kp), dtype=torch.float32, device=dev)
-        amat = torch.empty((kp, kp), dtype=torch.float32, device=dev)
+        amat = torch.empty((kp, kp), dtype=torch.float32, device=dev)   # shape/dtype template for the per-rho matrices
         hist = torch.zeros(self.n_iter, dtype=torch.float32, device=dev)
         wcodes = best_wcodes = None
         if use_tc:
@@ -181,21 +181,42 @@ class LayerCalibrator:
             best_wcodes = torch.empty_like(wcodes)
         self.st.reset()
         numel_total = y_n                      # mse over every rank's outputs
+        g4 = g.view(c2, c1, *ksize)
+
+        # A = A0 + rho*quasi_eye + eta*I takes 5 distinct values per layer (the rho schedule is
+        # known up front) and is SPD (A0 is PSD, eta > 0).  The reference re-factorises it in every
+        # one of the 200 iterations (solver.py:331); here each value is factorised and inverted
+        # once, on a side stream, so the later ones overlap the ADMM iterations of the earlier ones.
+        rhos, r_ = [rho], rho
+        for it in range(0, self.n_iter, self.rho_period):
+            r_ = r_ * 2 if r_ * 2 <= rho_m else rho_m
+            if r_ != rhos[-1]:
+                rhos.append(r_)
+        main = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        self._side.wait_stream(main)
+        inverses, infos = {}, []
+        with torch.cuda.stream(self._side):
+            for r_ in rhos:
+                a_r = torch.empty_like(amat)
+                ops.admm_lhs(a0, r_, eta, has_bias, a_r)
+                chol, info = torch.linalg.cholesky_ex(a_r)
+                inv_r = torch.cholesky_inverse(chol)
+                inv_r.record_stream(main)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                inverses[r_] = (inv_r, ev)
+                infos.append(info)
+                rep.factorizations += 1
         ainv = None
         rho_built = None
-        g4 = g.view(c2, c1, *ksize)
 
         for it in range(self.n_iter):
             if rho_built != rho:
-                # A takes 5 distinct values per layer; factor once per value (SPD: A0 is PSD, eta > 0)
-                ops.admm_lhs(a0, rho, eta, has_bias, amat)
-                chol, info = torch.linalg.cholesky_ex(amat)
-                if int(info.item()) == 0:
-                    ainv = torch.cholesky_inverse(chol)
-                else:                               # not numerically SPD: LU, as the reference (solver.py:331)
-                    ainv = torch.linalg.inv(amat)
+                ainv, ev = inverses[rho]
+                main.wait_event(ev)
                 rho_built = rho
-                rep.factorizations += 1
             # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
             ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat)
             sol = bmat @ ainv
@@ -240,6 +261,8 @@ class LayerCalibrator:
         final_sse = float(self.sse.item())
         if final_sse != final_sse:
             raise ops.EffqError(f"{name}: tcgen05 conv aborted (barrier timeout)")
+        if any(int(i.item()) != 0 for i in infos):
+            raise ops.EffqError(f"{name}: normal matrix not numerically SPD (cholesky failed)")
         if gram_flag is not None and int(gram_flag.item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 Gram kernel aborted (barrier timeout)")
         rep.final_loss = final_sse / numel_total
@@ -258,6 +281,7 @@ class LayerCalibrator:
 
     _cws = None
     _qf_ws = None
+    _side = None
 
     def _conv_ws(self, x, c2, ksize, stride, padding):
         import ctypes as C

@@ -191,7 +191,7 @@ def scale_search(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: Scale
                  v2: Optional[torch.Tensor] = None) -> ScaleState:
     """project_by_iter on the device (one cooperative launch, no host sync)."""
     rows, cols, ld1, ld2 = _pair_view(v1, v2)
-    name = "scale_search_w" if v2 is not None else "scale_search_act"
+    name = f"scale_search_w_{rows * cols}" if v2 is not None else "scale_search_act"
     timer.run(name, {"pass_bytes": 4 * rows * cols * (2 if v2 is not None else 1)}, lambda: check(
         capi.load().effq_scale_search(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
                                       state.p, ptr(_scale_ws(v1.device)), stream()), "effq_scale_search"))

@@ -134,6 +134,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
+# same kernel at the same shape (profiles/r01_layer_ncu.md); None = not captured.
+NCU_TRAFFIC_BYTES = {
+    "conv3d_tc_c32x32k3": 1.611e9,       # 32 x 32ch x 64^3: codes 0.537 GB + fp32 target 1.074 GB, no re-reads
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -313,7 +320,10 @@ def run_ours(args, wl, wl_name):
         if s["flops"]:
             ach = s["flops"] / (s["ms"] * 1e-3) / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                    "frac": ach / pk["tf_sust"], "traffic": NCU_TRAFFIC_BYTES.get(top),
+                    "peak_source": pk["src"] + " (sustained)",
+                    "note": "M=128,N=32,K=16 tcgen05.mma: hardware floor 64 cycles/MMA => <= 25% of peak for C2=32 "
+                            "(tools/mma_bench.cu, profiles/r01_conv_layout.md)" if top.startswith("conv3d_tc_c32") else None,
                     "launches_per_step": s["launches"] // args.steps, "avg_launch_ms": s["ms"] / s["launches"]}
         else:
             nbytes = s["bytes"] or s["pass_bytes"]

@@ -137,7 +137,7 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
 # same kernel at the same shape (profiles/r01_layer_ncu.md); None = not captured.
 NCU_TRAFFIC_BYTES = {
-    "conv3d_tc_c32x32k3": 1.611e9,       # 32 x 32ch x 64^3: codes 0.537 GB + fp32 target 1.074 GB, no re-reads
+    "conv3d_tc_c32x32k3": 1.80e9,        # 32 x 32ch x 64^3: algorithmic 1.611 GB (codes 0.537 + fp32 target 1.074)
 }
 
 

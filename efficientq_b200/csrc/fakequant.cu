@@ -81,23 +81,22 @@ fakequant_state_kernel(const float* __restrict__ x, long long numel, const effq_
   }
 }
 
-// NCDHW fp32 -> NDHWC bf16 codes.  One CTA handles TILE_V consecutive voxels of one
-// sample for all C channels: coalesced reads along the voxel axis per channel,
-// transpose through shared memory, one contiguous TILE_V*C*2-byte store.
-constexpr int QA_TILE_V = 64;
+// NCDHW fp32 -> NDHWC bf16 codes.  One CTA handles TILE_V consecutive voxels of one sample for
+// all C channels: 128-bit loads along the voxel axis (1 KB contiguous per channel at TILE_V = 256),
+// transpose through shared memory, one contiguous TILE_V*C*2-byte store in 16-byte pieces.
 constexpr int QA_THREADS = 256;
 
-template <bool F64>
+template <bool F64, int TILE_V>
 __global__ void __launch_bounds__(QA_THREADS)
 quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int nlvl,
                           const effq_scale_state* __restrict__ st, const float* __restrict__ alpha_f32,
                           __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __nv_bfloat16 tile[];      // [QA_TILE_V][c + 2] (pad keeps banks apart)
-  const int cp = c + 2;
-  const long long tiles_per_sample = (dhw + QA_TILE_V - 1) / QA_TILE_V;
+  extern __shared__ __nv_bfloat16 tile[];      // channel-major [c][TILE_V + 4]: both phases conflict-free
+  constexpr int VP = TILE_V + 4;
+  const long long tiles_per_sample = (dhw + TILE_V - 1) / TILE_V;
   const long long n_idx = blockIdx.x / tiles_per_sample;
-  const long long v0 = (blockIdx.x % tiles_per_sample) * QA_TILE_V;
-  const int nv = (int)min((long long)QA_TILE_V, dhw - v0);
+  const long long v0 = (blockIdx.x % tiles_per_sample) * TILE_V;
+  const int nv = (int)min((long long)TILE_V, dhw - v0);
   const float* xs = x + n_idx * (long long)c * dhw + v0;
 
   const QParamF qf = make_qparam_f(0.f, 1.f, nlvl);
@@ -106,25 +105,43 @@ quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int
   const float a32 = F64 ? 1.f : __ldg(alpha_f32);
   const QFastD fd = make_qfast_d(a64, qd, nlvl);
   const QFastF ff = make_qfast_f(a32, qf, nlvl);
+  auto code_of = [&](float val) -> float {
+    return F64 ? (float)level_index_fast_d((double)val, a64, qd, fd) : level_index_fast_f(val, a32, qf, ff);
+  };
 
-  for (int e = threadIdx.x; e < c * QA_TILE_V; e += QA_THREADS) {
-    const int ch = e / QA_TILE_V, v = e % QA_TILE_V;
-    float code = 0.f;
-    if (v < nv) {
-      const float val = __ldcs(xs + (long long)ch * dhw + v);
-      if (F64) code = (float)level_index_fast_d((double)val, a64, qd, fd);
-      else     code = level_index_fast_f(val, a32, qf, ff);
+  constexpr int VQ = TILE_V / 4;                // float4 groups per channel row
+  const bool vec_ok = (dhw % 4 == 0) && (nv == TILE_V) && ((reinterpret_cast<uintptr_t>(xs) & 15) == 0);
+  if (vec_ok) {
+    for (int e = threadIdx.x; e < c * VQ; e += QA_THREADS) {
+      const int ch = e / VQ, vq = e % VQ;        // a warp reads 512 contiguous bytes of one channel
+      const float4 val = __ldcs(reinterpret_cast<const float4*>(xs + (long long)ch * dhw) + vq);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(code_of(val.x), code_of(val.y));
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(code_of(val.z), code_of(val.w));
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(&tile[ch * VP + vq * 4]) = pk;     // 8 B, consecutive lanes consecutive
     }
-    tile[v * cp + ch] = __float2bfloat16_rn(code);
+  } else {
+    for (int e = threadIdx.x; e < c * TILE_V; e += QA_THREADS) {
+      const int ch = e / TILE_V, v = e % TILE_V;
+      float code = 0.f;
+      if (v < nv) code = code_of(__ldcs(xs + (long long)ch * dhw + v));
+      tile[ch * VP + v] = __float2bfloat16_rn(code);
+    }
   }
   __syncthreads();
   __nv_bfloat16* dst = out + (n_idx * dhw + v0) * c;
-  // c is even (checked on the host): move bf16 pairs
-  const int pairs = c / 2;
-  for (int e = threadIdx.x; e < nv * pairs; e += QA_THREADS) {
-    const int v = e / pairs, p = e % pairs;
-    const __nv_bfloat162 two = *reinterpret_cast<const __nv_bfloat162*>(&tile[v * cp + 2 * p]);
-    reinterpret_cast<__nv_bfloat162*>(dst + (long long)v * c)[p] = two;
+  const int chunks = c / 8;                     // c % 8 == 0 (host check): 16-byte pieces of 8 channels
+  for (int e = threadIdx.x; e < nv * chunks; e += QA_THREADS) {
+    const int q = e / nv, v = e % nv;           // lanes walk v: 2-byte reads of one channel row, no conflicts
+    const unsigned short* col = reinterpret_cast<const unsigned short*>(tile) + (8 * q) * VP + v;
+    uint4 piece;
+    piece.x = (uint32_t)col[0] | ((uint32_t)col[VP] << 16);
+    piece.y = (uint32_t)col[2 * VP] | ((uint32_t)col[3 * VP] << 16);
+    piece.z = (uint32_t)col[4 * VP] | ((uint32_t)col[5 * VP] << 16);
+    piece.w = (uint32_t)col[6 * VP] | ((uint32_t)col[7 * VP] << 16);
+    reinterpret_cast<uint4*>(dst + (long long)v * c)[q] = piece;
   }
 }
 
@@ -179,20 +196,30 @@ extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int
   EFFQ_CHECK_ARG(x && codes_bf16_out, "null pointer");
   EFFQ_CHECK_ARG(use_f64 ? state != nullptr : alpha_f32 != nullptr, "missing scale");
   EFFQ_CHECK_ARG(nlvl >= 2 && nlvl <= 256, "nlvl out of range for bf16-exact codes");
-  EFFQ_CHECK_ARG(c > 0 && c % 2 == 0 && c <= 512, "channel count must be even and <= 512");
+  EFFQ_CHECK_ARG(c > 0 && c % 8 == 0 && c <= 512, "channel count must be a multiple of 8 and <= 512");
+  EFFQ_CHECK_ARG(((uintptr_t)codes_bf16_out & 15) == 0, "output must be 16B aligned");
   if (n <= 0 || dhw <= 0) return 0;
-  const long long tiles = (long long)n * ((dhw + QA_TILE_V - 1) / QA_TILE_V);
-  EFFQ_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
-  const size_t smem = (size_t)QA_TILE_V * (c + 2) * sizeof(__nv_bfloat16);
   cudaStream_t s = (cudaStream_t)stream;
-  if (smem > 48 * 1024) {
-    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  __nv_bfloat16* out = (__nv_bfloat16*)codes_bf16_out;
+  const bool big = c <= 64;                     // 256-voxel tiles while the transpose tile stays <= 36 KB
+  const int tile_v = big ? 256 : 64;
+  const long long tiles = (long long)n * ((dhw + tile_v - 1) / tile_v);
+  EFFQ_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
+  const size_t smem = (size_t)c * (tile_v + 4) * sizeof(__nv_bfloat16);
+  static bool configured = false;
+  if (!configured) {
+    const int mx = 512 * (64 + 4) * 2;
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    configured = true;
   }
-  if (use_f64)
-    quantize_act_ndhwc_kernel<true><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, (__nv_bfloat16*)codes_bf16_out);
-  else
-    quantize_act_ndhwc_kernel<false><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, (__nv_bfloat16*)codes_bf16_out);
+  if (big) {
+    if (use_f64) quantize_act_ndhwc_kernel<true, 256><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
+    else         quantize_act_ndhwc_kernel<false, 256><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
+  } else {
+    if (use_f64) quantize_act_ndhwc_kernel<true, 64><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
+    else         quantize_act_ndhwc_kernel<false, 64><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
+  }
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

@@ -61,7 +61,7 @@ _SIGS = {
     "effq_fakequant_state": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "effq_quantize_act_ndhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
-                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_scale_search_workspace": (C.c_int64, []),
     "effq_scale_search": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -72,11 +72,11 @@ _SIGS = {
     "effq_conv3d_f32_workspace": (C.c_int64, [C.POINTER(Geom)]),
     "effq_conv3d_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "effq_conv3d_tc_supported": (C.c_int, [C.POINTER(Geom)]),
+    "effq_conv3d_tc_supported": (C.c_int, [C.POINTER(Geom), C.c_int32]),
     "effq_conv3d_tc_workspace": (C.c_int64, [C.POINTER(Geom)]),
-    "effq_conv3d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p,
+    "effq_conv3d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "effq_pack_wcodes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_pack_wcodes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_gram_workspace": (C.c_int64, [C.POINTER(Geom), C.c_int32]),
     "effq_gram_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -93,7 +93,7 @@ _SIGS = {
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p]),

@@ -7,6 +7,7 @@
 // structs, so the 200-iteration loop of one layer enqueues without a host sync.
 #include "common.cuh"
 #include "tc_layout.cuh"
+#include <cuda_fp8.h>
 
 namespace effq {
 
@@ -59,13 +60,19 @@ admm_lhs_kernel(const float* __restrict__ a0, float rho, float eta, int kp, int 
   }
 }
 
+// integer code -> operand element (bf16, or e4m3 when |code| <= 16: both exact)
+__device__ __forceinline__ void store_code(void* base, long long idx, float code, int eb) {
+  if (eb == 2) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(code);
+  else reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)__nv_cvt_float_to_fp8(code, __NV_SATFINITE, __NV_E4M3);
+}
+
 // Projection + dual update + operand export.           EfficientQConv.py:107-111,131-137
 __global__ void __launch_bounds__(AD_THREADS)
 admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __restrict__ dual,
                     const effq_scale_state* __restrict__ wscale, const effq_scale_state* __restrict__ xscale,
                     int nlvl_w, int nlvl_a, int c2, int c1, int taps, int has_bias, float dual_div,
                     float* __restrict__ g_out, float* __restrict__ bstar_out,
-                    __nv_bfloat16* __restrict__ wcodes, TcLayout lay, effq_admm_state* st) {
+                    void* __restrict__ wcodes, TcLayout lay, effq_admm_state* st) {
   const int k = c1 * taps;
   const long long total = (long long)c2 * k;
   const double a64 = wscale->a;
@@ -85,7 +92,7 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
     if (wcodes) {
       const int c = j / taps, t = j % taps;
       const float code = (float)(2.0 * idx - (double)(nlvl_w - 1));      // odd integer in [-(L-1), L-1]
-      wcodes[tc_wcode_index(r, c, t, c1, c2, lay)] = __float2bfloat16_rn(code);
+      store_code(wcodes, tc_wcode_index(r, c, t, c1, c2, lay), code, lay.eb);
     }
   }
   if (has_bias && bstar_out) {
@@ -126,27 +133,30 @@ admm_keep_kernel(const int* __restrict__ take, const float* __restrict__ g, cons
       best_b[r] = bstar[r];
 }
 
-// [C2][C1][taps] fp32 integer codes -> bf16 codes in the tensor-core weight layout.
+// [C2][C1][taps] fp32 integer codes -> bf16 / e4m3 codes in the tensor-core weight layout.
 __global__ void __launch_bounds__(AD_THREADS)
 pack_wcodes_kernel(const float* __restrict__ codes, int c2, int c1, int taps, TcLayout lay,
-                   __nv_bfloat16* __restrict__ out) {
+                   void* __restrict__ out) {
   const long long total = (long long)c2 * c1 * taps;
   for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
        e += (long long)gridDim.x * AD_THREADS) {
     const int t = (int)(e % taps);
     const int c = (int)((e / taps) % c1);
     const int r = (int)(e / ((long long)taps * c1));
-    out[tc_wcode_index(r, c, t, c1, c2, lay)] = __float2bfloat16_rn(codes[e]);
+    store_code(out, tc_wcode_index(r, c, t, c1, c2, lay), codes[e], lay.eb);
   }
 }
 
 }  // namespace effq
 
-extern "C" int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int32_t taps, void* out, void* stream) {
+extern "C" int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int32_t taps, int32_t code_dtype,
+                                void* out, void* stream) {
   using namespace effq;
-  EFFQ_CHECK_ARG(codes && out && c2 > 0 && c1 > 0 && c1 % 8 == 0 && taps > 0, "bad argument");
+  EFFQ_CHECK_ARG(codes && out && c2 > 0 && c1 > 0 && taps > 0, "bad argument");
+  EFFQ_CHECK_ARG(code_dtype == CODE_BF16 ? c1 % 8 == 0 : (code_dtype == CODE_E4M3 && c1 % 16 == 0),
+                 "c1 must be a multiple of 8 (bf16) / 16 (e4m3)");
   pack_wcodes_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
-      codes, c2, c1, taps, tc_layout(c1), (__nv_bfloat16*)out);
+      codes, c2, c1, taps, tc_layout(c1, code_dtype), out);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }
@@ -177,15 +187,18 @@ extern "C" int effq_admm_lhs(const float* a0, float rho, float eta, int32_t kp, 
 extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
                                  const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                                  int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
-                                 float* bstar_out, void* wcodes_out, effq_admm_state* st, void* stream) {
+                                 float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
+                                 void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(wstar && dual && wscale && g_out, "null pointer");
   EFFQ_CHECK_ARG(c2 > 0 && c1 > 0 && taps > 0 && ldw >= (int64_t)c1 * taps + (has_bias ? 1 : 0), "bad shape");
-  EFFQ_CHECK_ARG(!wcodes_out || (c1 % 8 == 0 && nlvl_w <= 256), "weight codes need c1 % 8 == 0, nlvl_w <= 256");
+  EFFQ_CHECK_ARG(!wcodes_out || (code_dtype == CODE_BF16 && c1 % 8 == 0 && nlvl_w <= 256) ||
+                     (code_dtype == CODE_E4M3 && c1 % 16 == 0 && nlvl_w <= 16),
+                 "weight codes need c1 % 8 == 0, nlvl_w <= 256 (bf16) or c1 % 16 == 0, nlvl_w <= 16 (e4m3)");
   EFFQ_CHECK_ARG(dual_div != 0.f, "dual_div must be non-zero");
   admm_project_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
       wstar, ldw, dual, wscale, xscale, nlvl_w, nlvl_a, c2, c1, taps, has_bias, dual_div, g_out, bstar_out,
-      (__nv_bfloat16*)wcodes_out, tc_layout(c1), st);
+      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

@@ -4,22 +4,25 @@
 // (reference src/models/EfficientQConv.py:118-122, 200x per layer, and :161-165).
 //
 // Arithmetic: Qact = a_x * cx/(La-1) and G = a_w * cw/(Lw-1) with cx in 0..La-1 and cw an
-// odd integer in [-(Lw-1), Lw-1]; both are exact in bf16 (<= 8 significant bits), the
-// products are exact and the fp32 TMEM accumulation of integers is exact below 2^24, so
-// the tensor-core result is  conv_scale * (exact integer) + bias  -- at least as accurate
-// as the reference's fp32 conv.
+// integer in [-(Lw-1), Lw-1].  Codes of <= 256 levels are exact in bf16 (kind::f16, K = 16 per
+// instruction), codes of <= 16 levels also in e4m3 (kind::f8f6f4, K = 32 per instruction: half
+// the MMA instructions and half the operand bytes).  The products are exact and the fp32 TMEM
+// accumulation of integers is exact below 2^24, so either way the tensor-core result is
+// conv_scale * (exact integer) + bias -- at least as accurate as the reference's fp32 conv, and
+// bit-identical between the two operand types.
 //
 // GEMM view: M = output voxels (tile = 16 h-rows x 8 w, one d-plane -> 128 rows),
 // N = C2, K = taps * C1.  No im2col: the producer warps copy ONE halo block
-// (kd x (16+kh-1) x (8+kw-1) voxels x <=64 channels) per tile into shared memory in the
-// UMMA "interleaved" (no-swizzle, K-major) layout  [channel/8][halo voxel][8 channels];
-// the A descriptor of tap (a,b,c) is the same block with the start address shifted by
-// ((a*HH + b)*WP + c) voxels, so every activation byte is fetched from L2 once per tile
-// and reused by all taps.  Weights [tap][C1/8][C2][8] arrive by 1D bulk TMA copies
-// (cp.async.bulk + mbarrier complete_tx), resident for the whole kernel when they fit,
-// else through a ring.  One elected thread issues tcgen05.mma (M=128, N=C2, K=16) into a
-// double-buffered TMEM accumulator; four epilogue warps drain it with tcgen05.ld, apply
-// scale+bias, read the fp32 target (NCDHW), and reduce att*(out-target)^2.
+// (kd x (16+kh-1) x (8+kw-1) voxels x one channel block of <= 128 bytes) per tile into shared
+// memory as K-major rows with the UMMA 128/64/32-byte swizzle (tc_layout.cuh); the A descriptor
+// of tap (a,b,c) is the same block with the start address shifted by ((a*HH + b)*WP + c) rows
+// (the swizzle is a function of the absolute address, so any row may start a descriptor), so
+// every activation byte is fetched from L2 once per tile and reused by all taps.  Weights
+// [tap][block][C2][CG] (pre-swizzled in global memory) arrive by 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier complete_tx), resident for the whole kernel when they fit, else
+// through a ring.  One elected thread issues tcgen05.mma (M=128, N=C2) into a double-buffered
+// TMEM accumulator; four epilogue warps drain it with tcgen05.ld, apply scale+bias, read the
+// fp32 target (NCDHW), and reduce att*(out-target)^2.
 //
 // Warp roles (320 threads): 0 weight TMA | 1 MMA issuer + TMEM owner | 2-5 epilogue |
 // 6-9 halo producers (cp.async, zero-fill for padding / ragged edges).
@@ -37,8 +40,8 @@ constexpr int TC_EPI = 128;
 constexpr unsigned int TC_SPIN_LIMIT = 1u << 26;
 
 struct TcParams {
-  const __nv_bfloat16* xq;     // NDHWC codes
-  const __nv_bfloat16* wq;     // [tap][C1/8][C2][8]
+  const uint8_t* xq;           // NDHWC codes (bf16 or e4m3, eb bytes each)
+  const uint8_t* wq;           // [tap][group][C2][CG] pre-swizzled (tc_layout.cuh)
   const float* bias;
   const float* conv_scale;
   float* out;                  // NCDHW or null
@@ -49,7 +52,8 @@ struct TcParams {
   double* ws_partial;
   int n, c1, c2, d, h, w;
   int kd, kh, kw, pd, ph, pw, taps;
-  int cg, n_groups, nch;       // channels per halo block, blocks per tile, cg/8
+  int cg, n_groups, nch;       // channels per halo block, blocks per tile, 16-byte chunks per row
+  int eb;                      // bytes per code: 2 = bf16 (kind::f16), 1 = e4m3 (kind::f8f6f4)
   int hh, wp, hv;              // halo rows per plane, halo cols, halo voxels
   int tiles_h, tiles_w;
   long long n_tiles;
@@ -117,14 +121,23 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 // Descriptors are passed as (low word, high word): only the 14-bit start-address field in the
 // low word changes between MMAs, so the issuing thread does 32-bit adds only.
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool FP8>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                       uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if (FP8)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // One elected lane of a converged warp.  The MMA / TMA roles keep warp-uniform control flow and
 // run their issue loops inside `if (elect_one())`: the compiler then knows a single lane is
@@ -172,12 +185,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t sbo_by
   d |= (uint64_t)(swz == 128 ? 2 : (swz == 64 ? 4 : 6)) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=m, N=n.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+// Instruction descriptor: D=f32, both operands K-major, M=m, N=n; A=B=bf16 (kind::f16, K=16 per
+// instruction) or A=B=e4m3 (kind::f8f6f4, format code 0, K=32 per instruction).
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n, bool fp8) {
   uint32_t i = 0;
   i |= 1u << 4;                            // c_format = F32
-  i |= 1u << 7;                            // a_format = BF16
-  i |= 1u << 10;                           // b_format = BF16
+  if (!fp8) {
+    i |= 1u << 7;                          // a_format = BF16
+    i |= 1u << 10;                         // b_format = BF16
+  }
   i |= (uint32_t)(n >> 3) << 17;           // N / 8
   i |= (uint32_t)(m >> 4) << 24;           // M / 16
   return i;
@@ -198,9 +214,10 @@ struct Pipe {
   }
 };
 
-// KS: kernel edge (3 or 1), KK: MMAs per (tap, channel block) = CG/16 and WRES: weights resident in
-// shared memory are compile-time, so the single MMA-issuing thread runs straight-line code.
-template <int KS, int KK, bool WRES>
+// KS: kernel edge (3 or 1), KK: MMAs per (tap, channel block) = row bytes / 32, WRES: weights
+// resident in shared memory and FP8: e4m3 operands are compile-time, so the single MMA-issuing
+// thread runs straight-line code.
+template <int KS, int KK, bool WRES, bool FP8>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024 B alignment
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         mbar_expect_tx(BAR(B_WRES), total);
         for (int g = 0; g < p.n_groups; ++g)
           for (int t = 0; t < p.taps; ++t) {
-            const __nv_bfloat16* src = p.wq + ((long long)t * p.n_groups + g) * p.cg * p.c2;
+            const uint8_t* src = p.wq + ((long long)t * p.n_groups + g) * p.wtile_bytes;
             bulk_g2s(wsm0 + (uint32_t)(g * p.taps + t) * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WRES));
           }
       } else {
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
             for (int t = 0; t < p.taps; ++t) {
               if (!mbar_wait<32>(BAR(B_WE + wp.stage), wp.phase ^ 1u, abort_flag)) { ok = false; break; }
               mbar_expect_tx(BAR(B_WF + wp.stage), p.wtile_bytes);
-              const __nv_bfloat16* src = p.wq + ((long long)t * p.n_groups + g) * p.cg * p.c2;
+              const uint8_t* src = p.wq + ((long long)t * p.n_groups + g) * p.wtile_bytes;
               bulk_g2s(wsm0 + (uint32_t)wp.stage * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WF + wp.stage));
               wp.advance(p.n_w_stages);
             }
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     // ===== MMA issuer: D[128 voxels][C2] += X(tap slice of the halo) * W(tap)^T.  One elected lane
     // runs the whole loop; per MMA it does two 32-bit adds on the descriptors' address fields. =====
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.c2);
+      const uint32_t idesc = umma_idesc(128, p.c2, FP8);
       const uint64_t h_tmpl = umma_desc_sw(0, (uint32_t)(p.wp * p.rp), p.swz, 0);
       const uint64_t w_tmpl = umma_desc_sw(0, (uint32_t)(8 * p.rp), p.swz, 0);
       const uint32_t h_hi = (uint32_t)(h_tmpl >> 32), h_lo0 = (uint32_t)h_tmpl;
@@ -310,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
                   const uint32_t ha = h_lo + (uint32_t)a * step_a + (uint32_t)b * step_b + (uint32_t)c * row16;
 #pragma unroll
                   for (int kk = 0; kk < KK; ++kk)
-                    tc_mma_bf16(d_tmem, ha + 2u * kk, h_hi, w_lo + 2u * kk, w_hi, idesc,
+                    tc_mma<FP8>(d_tmem, ha + 2u * kk, h_hi, w_lo + 2u * kk, w_hi, idesc,
                                 (g == 0 && a == 0 && b == 0 && c == 0 && kk == 0) ? 0u : 1u);
                   if (!WRES) { tc_commit(BAR(B_WE + wp.stage)); wp.advance(p.n_w_stages); }
                 }
@@ -406,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     const int ipv = p.nch / cpi;                              // items per voxel
     const int n_items = p.kd * p.hh * used_w * ipv;
     constexpr int MAX_IT = 17;                                // ceil(3*18*10*4 / 128)
-    int rel[MAX_IT];                                          // element offset from the tile origin
+    int rel[MAX_IT];                                          // byte offset from the tile origin
     uint32_t dst[MAX_IT];                                     // byte offset inside the halo stage
     uint32_t crd[MAX_IT];                                     // dz | hy << 4 | wx << 12 | valid << 20
 #pragma unroll
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         const int dz = rr / p.hh, hy = rr % p.hh;
         const int hrow = rr * p.wp + wx;
         const int j0 = q * cpi;
-        rel[i] = ((dz * p.h + hy) * p.w + wx) * p.c1 + j0 * 8;
+        rel[i] = (((dz * p.h + hy) * p.w + wx) * p.c1) * p.eb + j0 * 16;
         dst[i] = (uint32_t)(hrow * p.rp) | ((uint32_t)tc_chunk_xor(hrow, p.swz) << 24) | ((uint32_t)j0 << 28);
         crd[i] = (uint32_t)dz | ((uint32_t)hy << 4) | ((uint32_t)wx << 12) | (1u << 20);
       }
@@ -437,23 +454,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const int nn = (int)r;
       const int h0 = th * TC_TILE_H - p.ph, w0 = tw * TC_TILE_W - p.pw, d0 = dd - p.pd;
       // pointer of halo voxel (0,0,0), channel 0 -- may lie outside the tensor, only dereferenced when valid
-      const __nv_bfloat16* origin = p.xq + ((((long long)nn * p.d + d0) * p.h + h0) * p.w + w0) * p.c1;
+      const uint8_t* origin = p.xq + ((((long long)nn * p.d + d0) * p.h + h0) * p.w + w0) * p.c1 * p.eb;
       for (int g = 0; g < p.n_groups; ++g) {
         if (!mbar_wait<64>(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
         if (ptid == 0 && g == 0) dbg_stamp(p, tile, 5);
         const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
-        const __nv_bfloat16* gorigin = origin + g * p.cg;
+        const uint8_t* gorigin = origin + g * p.rp;
 #pragma unroll
         for (int i = 0; i < MAX_IT; ++i) {
           const uint32_t c = crd[i];
           if (c >> 20) {                                         // item exists (thread-uniform per i)
             const int gd = d0 + (int)(c & 15u), gh = h0 + (int)((c >> 4) & 255u), gw = w0 + (int)((c >> 12) & 255u);
             const bool okk = (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w;
-            const __nv_bfloat16* src = okk ? gorigin + rel[i] : p.xq;
+            const uint8_t* src = okk ? gorigin + rel[i] : p.xq;
             const uint32_t rowb = hbase + (dst[i] & 0xffffffu);
             const uint32_t x = (dst[i] >> 24) & 15u, j0 = dst[i] >> 28;
             cp_async16(rowb + (((j0) ^ x) << 4), src, okk ? 16u : 0u);
-            if (cpi == 2) cp_async16(rowb + (((j0 + 1) ^ x) << 4), src + 8, okk ? 16u : 0u);
+            if (cpi == 2) cp_async16(rowb + (((j0 + 1) ^ x) << 4), src + 16, okk ? 16u : 0u);
           }
         }
         cp_async_commit();
@@ -513,21 +530,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   }
 }
 
-static bool tc_plan(const effq_geom& g, TcParams& p) {
+static bool tc_plan(const effq_geom& g, int code_dtype, TcParams& p) {
+  if (code_dtype != CODE_BF16 && code_dtype != CODE_E4M3) return false;
   if (!((g.kd == 3 && g.kh == 3 && g.kw == 3 && g.pd == 1 && g.ph == 1 && g.pw == 1) ||
         (g.kd == 1 && g.kh == 1 && g.kw == 1 && g.pd == 0 && g.ph == 0 && g.pw == 0)))
     return false;
   if (g.sd != 1 || g.sh != 1 || g.sw != 1) return false;
-  if (g.c1 % 16 != 0 || g.c2 % 16 != 0 || g.c2 < 16 || g.c2 > 256) return false;
-  if (g.c1 > 64 && g.c1 % 64 != 0) return false;
-  if (g.c1 != 16 && g.c1 != 32 && g.c1 < 64) return false;           // nch must be 2, 4 or 8
+  if (g.c2 % 16 != 0 || g.c2 < 16 || g.c2 > 256) return false;
+  const TcLayout lay = tc_layout(g.c1, code_dtype);
+  if (g.c1 <= 0 || g.c1 % lay.cg != 0) return false;
+  if (lay.rp != 32 && lay.rp != 64 && lay.rp != 128) return false;   // 2, 4 or 8 chunks per row
   p.n = g.n; p.c1 = g.c1; p.c2 = g.c2; p.d = g.d; p.h = g.h; p.w = g.w;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
   p.taps = g.kd * g.kh * g.kw;
-  p.cg = g.c1 < 64 ? g.c1 : 64;
-  p.n_groups = g.c1 / p.cg;
-  p.nch = p.cg / 8;
-  const TcLayout lay = tc_layout(g.c1);
+  p.cg = lay.cg;
+  p.n_groups = lay.groups;
+  p.nch = lay.nch;
+  p.eb = lay.eb;
   p.swz = lay.swz;
   p.rp = lay.rp;
   static const int dbg_env = [] { const char* v = getenv("EFFQ_TC_DEBUG"); return (v && *v) ? atoi(v) : 0; }();
@@ -543,7 +562,7 @@ static bool tc_plan(const effq_geom& g, TcParams& p) {
   p.n_tiles = (long long)g.n * g.d * p.tiles_h * p.tiles_w;
   p.halo_bytes = (uint32_t)(p.hv * p.rp);
   p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
-  p.wtile_bytes = (uint32_t)(p.cg * g.c2 * 2);
+  p.wtile_bytes = (uint32_t)(p.rp * g.c2);
   p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
   p.off_bias = 256;
   p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
@@ -576,21 +595,23 @@ static uint32_t tc_smem_bytes(const TcParams& p) {
   return p.off_w + w + 1024u;      // + slack for the manual 1024 B alignment of the base
 }
 
-template <int KS, int KK, bool WRES>
+template <int KS, int KK, bool WRES, bool FP8>
 static int tc_launch(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
   static uint32_t configured = 0;
   if (smem > configured) {
-    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KS, KK, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KS, KK, WRES, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  conv3d_tc_kernel<KS, KK, WRES><<<ctas, TC_THREADS, smem, s>>>(p);
+  conv3d_tc_kernel<KS, KK, WRES, FP8><<<ctas, TC_THREADS, smem, s>>>(p);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }
 
 template <int KS, int KK>
 static int tc_dispatch_w(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
-  return p.w_resident ? tc_launch<KS, KK, true>(p, smem, ctas, s) : tc_launch<KS, KK, false>(p, smem, ctas, s);
+  if (p.eb == 1)
+    return p.w_resident ? tc_launch<KS, KK, true, true>(p, smem, ctas, s) : tc_launch<KS, KK, false, true>(p, smem, ctas, s);
+  return p.w_resident ? tc_launch<KS, KK, true, false>(p, smem, ctas, s) : tc_launch<KS, KK, false, false>(p, smem, ctas, s);
 }
 
 static int tc_dispatch(const TcParams& p, int ks, int kk, uint32_t smem, unsigned ctas, cudaStream_t s) {
@@ -606,9 +627,9 @@ static int tc_dispatch(const TcParams& p, int ks, int kk, uint32_t smem, unsigne
 
 }  // namespace effq
 
-extern "C" int effq_conv3d_tc_supported(const effq_geom* g) {
+extern "C" int effq_conv3d_tc_supported(const effq_geom* g, int32_t code_dtype) {
   effq::TcParams p;
-  return (g && effq::tc_plan(*g, p)) ? 1 : 0;
+  return (g && effq::tc_plan(*g, code_dtype, p)) ? 1 : 0;
 }
 
 extern "C" int64_t effq_conv3d_tc_workspace(const effq_geom* g) {
@@ -616,8 +637,8 @@ extern "C" int64_t effq_conv3d_tc_workspace(const effq_geom* g) {
   return 16 + 8 * 1024;
 }
 
-extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const float* bias, const float* conv_scale,
-                              const effq_geom* g, float* out, const float* target, const float* att, double* sse,
+extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
+                              const float* conv_scale, const effq_geom* g, float* out, const float* target, const float* att, double* sse,
                               void* workspace, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(xcodes && wcodes && conv_scale && g && workspace, "null pointer");
@@ -625,10 +646,10 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const floa
   EFFQ_CHECK_ARG(!target || sse, "sse required with target");
   EFFQ_CHECK_ARG(((uintptr_t)xcodes & 15) == 0 && ((uintptr_t)wcodes & 15) == 0, "operands must be 16B aligned");
   TcParams p;
-  EFFQ_CHECK_ARG(tc_plan(*g, p), "geometry not supported by the tcgen05 path");
+  EFFQ_CHECK_ARG(tc_plan(*g, code_dtype, p), "geometry / code type not supported by the tcgen05 path");
   EFFQ_CHECK_ARG(p.n_tiles < (1ll << 31), "too many tiles");
-  p.xq = (const __nv_bfloat16*)xcodes;
-  p.wq = (const __nv_bfloat16*)wcodes;
+  p.xq = (const uint8_t*)xcodes;
+  p.wq = (const uint8_t*)wcodes;
   p.bias = bias;
   p.conv_scale = conv_scale;
   p.out = out;
@@ -642,6 +663,6 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, const floa
   p.dbg = (p.debug & 8) ? (unsigned long long*)((char*)workspace + 16 + 8 * 1024) : nullptr;
   const uint32_t smem = tc_smem_bytes(p);
   const long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  const int kk = p.cg / 16;
+  const int kk = p.rp / 32;
   return tc_dispatch(p, g->kd, kk, smem, (unsigned)ctas, (cudaStream_t)stream);
 }

@@ -4,6 +4,7 @@
 //   effq_quantize_act_ndhwc : same arithmetic, emits channels-last bf16 integer codes,
 //                             the operand format of the tcgen05 conv.
 #include "common.cuh"
+#include <cuda_fp8.h>
 
 namespace effq {
 
@@ -90,7 +91,7 @@ template <bool F64, int TILE_V>
 __global__ void __launch_bounds__(QA_THREADS)
 quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int nlvl,
                           const effq_scale_state* __restrict__ st, const float* __restrict__ alpha_f32,
-                          __nv_bfloat16* __restrict__ out) {
+                          __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out8) {
   extern __shared__ __nv_bfloat16 tile[];      // channel-major [c][TILE_V + 4]: both phases conflict-free
   constexpr int VP = TILE_V + 4;
   const long long tiles_per_sample = (dhw + TILE_V - 1) / TILE_V;
@@ -131,6 +132,28 @@ quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int
     }
   }
   __syncthreads();
+  if (out8) {
+    // e4m3 copy of the same codes (exact for <= 16 levels): 16-byte pieces of 16 channels
+    uint8_t* dst8 = out8 + (n_idx * dhw + v0) * c;
+    const int chunks8 = c / 16;                 // c % 16 == 0 (host check)
+    for (int e = threadIdx.x; e < nv * chunks8; e += QA_THREADS) {
+      const int q = e / nv, v = e % nv;
+      const unsigned short* col = reinterpret_cast<const unsigned short*>(tile) + (16 * q) * VP + v;
+      uint32_t wd[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 lo2, hi2;
+        lo2.x = __uint_as_float((uint32_t)col[(4 * k + 0) * VP] << 16);
+        lo2.y = __uint_as_float((uint32_t)col[(4 * k + 1) * VP] << 16);
+        hi2.x = __uint_as_float((uint32_t)col[(4 * k + 2) * VP] << 16);
+        hi2.y = __uint_as_float((uint32_t)col[(4 * k + 3) * VP] << 16);
+        wd[k] = (uint32_t)__nv_cvt_float2_to_fp8x2(lo2, __NV_SATFINITE, __NV_E4M3) |
+                ((uint32_t)__nv_cvt_float2_to_fp8x2(hi2, __NV_SATFINITE, __NV_E4M3) << 16);
+      }
+      reinterpret_cast<uint4*>(dst8 + (long long)v * c)[q] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+  }
+  if (!out) return;
   __nv_bfloat16* dst = out + (n_idx * dhw + v0) * c;
   const int chunks = c / 8;                     // c % 8 == 0 (host check): 16-byte pieces of 8 channels
   for (int e = threadIdx.x; e < nv * chunks; e += QA_THREADS) {
@@ -191,9 +214,12 @@ extern "C" int effq_fakequant_state(const float* x, int64_t numel, const effq_sc
 
 extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, int32_t nlvl,
                                        const effq_scale_state* state, const float* alpha_f32,
-                                       int32_t use_f64, void* codes_bf16_out, void* stream) {
+                                       int32_t use_f64, void* codes_bf16_out, void* codes_e4m3_out,
+                                       void* stream) {
   using namespace effq;
-  EFFQ_CHECK_ARG(x && codes_bf16_out, "null pointer");
+  EFFQ_CHECK_ARG(x && (codes_bf16_out || codes_e4m3_out), "null pointer");
+  EFFQ_CHECK_ARG(!codes_e4m3_out || (nlvl <= 16 && c % 16 == 0 && ((uintptr_t)codes_e4m3_out & 15) == 0),
+                 "e4m3 codes need nlvl <= 16, c % 16 == 0 and a 16B aligned output");
   EFFQ_CHECK_ARG(use_f64 ? state != nullptr : alpha_f32 != nullptr, "missing scale");
   EFFQ_CHECK_ARG(nlvl >= 2 && nlvl <= 256, "nlvl out of range for bf16-exact codes");
   EFFQ_CHECK_ARG(c > 0 && c % 8 == 0 && c <= 512, "channel count must be a multiple of 8 and <= 512");
@@ -201,6 +227,7 @@ extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int
   if (n <= 0 || dhw <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* out = (__nv_bfloat16*)codes_bf16_out;
+  uint8_t* out8 = (uint8_t*)codes_e4m3_out;
   const bool big = c <= 64;                     // 256-voxel tiles while the transpose tile stays <= 36 KB
   const int tile_v = big ? 256 : 64;
   const long long tiles = (long long)n * ((dhw + tile_v - 1) / tile_v);
@@ -214,11 +241,11 @@ extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int
     configured = true;
   }
   if (big) {
-    if (use_f64) quantize_act_ndhwc_kernel<true, 256><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
-    else         quantize_act_ndhwc_kernel<false, 256><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
+    if (use_f64) quantize_act_ndhwc_kernel<true, 256><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out, out8);
+    else         quantize_act_ndhwc_kernel<false, 256><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out, out8);
   } else {
-    if (use_f64) quantize_act_ndhwc_kernel<true, 64><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
-    else         quantize_act_ndhwc_kernel<false, 64><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out);
+    if (use_f64) quantize_act_ndhwc_kernel<true, 64><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out, out8);
+    else         quantize_act_ndhwc_kernel<false, 64><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, state, alpha_f32, out, out8);
   }
   EFFQ_LAUNCH_CHECK();
   return 0;

@@ -133,20 +133,27 @@ class LayerCalibrator:
         use_tc = (not self.force_generic) and q_act and qlvl_act <= 256 and qlvl_w <= 256 and \
             ops.conv3d_tc_supported(x.shape, c2, ksize, stride, padding)
         rep.used_tc = use_tc
+        # <= 16 levels on both sides: the conv runs on e4m3 codes (exact, K = 32 per tcgen05.mma)
+        use_fp8 = use_tc and ops.fp8_codes_enabled() and qlvl_act <= 16 and qlvl_w <= 16 and \
+            ops.conv3d_tc_supported(x.shape, c2, ksize, stride, padding, ops.CODE_E4M3)
+        need_gram_tc = use_tc and ops.gram_tc_supported(x.shape, c2, ksize, stride, padding)
         alpha_act = None
-        xcodes = None
+        xcodes = xcodes_conv = None
         if q_act:
             self._act_scale(x, qlvl_act)
             alpha_act = self.xstate.a_f32()
             qx = ops.fakequant_state(x, self.xstate, qlvl_act, 0.0, 1.0)
-            if use_tc:
-                xcodes = ops.quantize_act_ndhwc(x, qlvl_act, state=self.xstate)
+            if use_fp8:
+                xcodes, xcodes_conv = ops.quantize_act_ndhwc(x, qlvl_act, state=self.xstate, bf16=need_gram_tc,
+                                                             e4m3=True)
+            elif use_tc:
+                xcodes = xcodes_conv = ops.quantize_act_ndhwc(x, qlvl_act, state=self.xstate)
         else:
             qx = x
 
         # normal-equation statistics (solver.py:253-272), summed over shards
         gram_flag = None
-        if use_tc and ops.gram_tc_supported(x.shape, c2, ksize, stride, padding):
+        if need_gram_tc:
             code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
             a0, b0, self.gram_ws, gram_flag = ops.gram_tc(xcodes, code_scale, out_fp, att, has_bias=has_bias,
                                                           ws=self.gram_ws)
@@ -177,7 +184,7 @@ class LayerCalibrator:
         hist = torch.zeros(self.n_iter, dtype=torch.float32, device=dev)
         wcodes = best_wcodes = None
         if use_tc:
-            wcodes = torch.empty(taps * (c1 // 8) * c2 * 8, dtype=torch.bfloat16, device=dev)
+            wcodes = torch.empty(taps * c1 * c2, dtype=xcodes_conv.dtype, device=dev)
             best_wcodes = torch.empty_like(wcodes)
         self.st.reset()
         numel_total = y_n                      # mse over every rank's outputs
@@ -234,7 +241,7 @@ class LayerCalibrator:
                              has_bias, div, g, bstar, wcodes, self.st)
             # score the iterate (EfficientQConv.py:118-122)
             if use_tc:
-                ops.conv3d_tc(xcodes, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
+                ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
                               target=out_fp, ws=self.tc_ws, sse=self.sse)
             elif stats64 is not None:
                 ops.quadform_sse(stats64, y_sq, g, bstar, self.sse, self._qf_ws)      # already global
@@ -248,7 +255,7 @@ class LayerCalibrator:
 
         # final forward with the best iterate: layer output + attention-weighted loss (:161-166)
         if use_tc:
-            out_q, _ = ops.conv3d_tc(xcodes, best_wcodes, best_b, self.st.best_conv_scale_ptr(), c2, ksize,
+            out_q, _ = ops.conv3d_tc(xcodes_conv, best_wcodes, best_b, self.st.best_conv_scale_ptr(), c2, ksize,
                                      want_out=True, target=out_fp, att=att, ws=self.tc_ws, sse=self.sse)
         else:
             out_q, _ = ops.conv3d_f32(qx, best_g.view(c2, c1, *ksize), best_b, stride, padding, want_out=True,

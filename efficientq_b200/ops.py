@@ -8,6 +8,7 @@ missing the first call raises (no fallback by design).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import struct
 from typing import Optional, Tuple
 
@@ -145,18 +146,39 @@ def fakequant_state(x: torch.Tensor, state: ScaleState, nlvl: int, lo: float, hi
     return y
 
 
+CODE_BF16, CODE_E4M3 = 0, 1
+E4M3 = torch.float8_e4m3fn
+
+
+def code_dtype_of(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return CODE_BF16
+    if t.dtype == E4M3:
+        return CODE_E4M3
+    raise EffqError(f"integer codes must be bf16 or float8_e4m3fn, got {t.dtype}")
+
+
+def fp8_codes_enabled() -> bool:
+    """EFFQ_FP8=0 forces bf16 codes everywhere (results are bit-identical; this only changes speed)."""
+    return os.environ.get("EFFQ_FP8", "1") != "0"
+
+
 def quantize_act_ndhwc(x: torch.Tensor, nlvl: int, state: Optional[ScaleState] = None,
-                       alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """NCDHW fp32 -> (N,D,H,W,C) bf16 integer codes, the tcgen05 conv operand."""
+                       alpha: Optional[torch.Tensor] = None, bf16: bool = True, e4m3: bool = False):
+    """NCDHW fp32 -> (N,D,H,W,C) integer codes, the tensor-core operand: a bf16 tensor (default), or
+    with e4m3=True the pair (bf16 or None, e4m3) written by the same pass over x."""
     x = _f32c(x, "x")
     n, c, d, h, w = x.shape
-    out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device) if bf16 else None
+    out8 = torch.empty((n, d, h, w, c), dtype=E4M3, device=x.device) if e4m3 else None
     use64 = 1 if state is not None else 0
     a = _f32c(alpha.reshape(1), "alpha") if alpha is not None else None
-    timer.run("quantize_act_ndhwc", {"bytes": 6 * x.numel()}, lambda: check(
+    nbytes = x.numel() * (4 + 2 * bool(bf16) + bool(e4m3))
+    timer.run("quantize_act_ndhwc", {"bytes": nbytes}, lambda: check(
         capi.load().effq_quantize_act_ndhwc(ptr(x), n, c, d * h * w, int(nlvl), state.p if state else None,
-                                            ptr(a), use64, ptr(out), stream()), "effq_quantize_act_ndhwc"))
-    return out
+                                            ptr(a), use64, ptr(out), ptr(out8), stream()),
+        "effq_quantize_act_ndhwc"))
+    return (out, out8) if e4m3 else out
 
 
 # ---------------------------------------------------------------------------
@@ -236,16 +258,20 @@ def conv3d_f32(x, w, bias, stride, padding, want_out=True, target=None, att=None
     return out, sse
 
 
-def conv3d_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
+def conv3d_tc_supported(x_shape, c2, ksize, stride, padding, code_dtype: int = CODE_BF16) -> bool:
     g = Geom.make(x_shape, c2, ksize, stride, padding)
-    return bool(capi.load().effq_conv3d_tc_supported(C.byref(g)))
+    return bool(capi.load().effq_conv3d_tc_supported(C.byref(g), int(code_dtype)))
 
 
 def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, c2: int, ksize, want_out=True,
               target=None, att=None, ws=None, sse=None):
-    """tcgen05 conv on codes.  xcodes (N,D,H,W,C1) bf16; wcodes [tap][C1/8][C2][8] bf16."""
-    if xcodes.dtype != torch.bfloat16 or not xcodes.is_contiguous() or not xcodes.is_cuda:
-        raise EffqError("conv3d_tc: xcodes must be contiguous CUDA bf16 NDHWC")
+    """tcgen05 conv on codes.  xcodes (N,D,H,W,C1) bf16 or e4m3; wcodes of the same type in the
+    tensor-core weight layout (pack_weight_codes / admm_project)."""
+    cdt = code_dtype_of(xcodes)
+    if wcodes.dtype != xcodes.dtype:
+        raise EffqError("conv3d_tc: activation and weight codes must have the same element type")
+    if not xcodes.is_contiguous() or not xcodes.is_cuda:
+        raise EffqError("conv3d_tc: xcodes must be contiguous CUDA NDHWC")
     n, d, h, w, c1 = xcodes.shape
     k = capi._triple(ksize)
     pad = tuple((t - 1) // 2 for t in k)
@@ -263,21 +289,23 @@ def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, 
     b = _f32c(bias, "bias") if bias is not None else None
     cs = conv_scale_ptr if not isinstance(conv_scale_ptr, torch.Tensor) else ptr(conv_scale_ptr)
     flops = 2.0 * n * d * h * w * c2 * c1 * g.taps
-    nbytes = xcodes.numel() * 2 + wcodes.numel() * 2 + n * d * h * w * c2 * 4 * ((target is not None) + (out is not None))
-    timer.run(f"conv3d_tc_c{c1}x{c2}k{k[0]}", {"flops": flops, "bytes": nbytes}, lambda: check(
-        lib.effq_conv3d_tc(ptr(xcodes), ptr(wcodes), ptr(b), cs, C.byref(g), ptr(out), ptr(target), ptr(att),
+    nbytes = (xcodes.numel() + wcodes.numel()) * xcodes.element_size() + n * d * h * w * c2 * 4 * ((target is not None) + (out is not None))
+    name = f"conv3d_tc_c{c1}x{c2}k{k[0]}" + ("_e4m3" if cdt == CODE_E4M3 else "")
+    timer.run(name, {"flops": flops, "bytes": nbytes}, lambda: check(
+        lib.effq_conv3d_tc(ptr(xcodes), ptr(wcodes), cdt, ptr(b), cs, C.byref(g), ptr(out), ptr(target), ptr(att),
                            ptr(sse), ptr(ws), stream()), "effq_conv3d_tc"))
     return out, sse
 
 
-def pack_weight_codes(wcodes_int: torch.Tensor) -> torch.Tensor:
-    """[C2][C1][kd][kh][kw] integer codes (already 2c-(L-1)) on the GPU -> bf16 codes in the
+def pack_weight_codes(wcodes_int: torch.Tensor, code_dtype: int = CODE_BF16) -> torch.Tensor:
+    """[C2][C1][kd][kh][kw] integer codes (already 2c-(L-1)) on the GPU -> bf16 / e4m3 codes in the
     tensor-core weight layout (the layout effq_admm_project emits during calibration)."""
     w = _f32c(wcodes_int.float(), "wcodes")
     c2, c1 = w.shape[:2]
     taps = w[0, 0].numel()
-    out = torch.empty(c2 * c1 * taps, dtype=torch.bfloat16, device=w.device)
-    check(capi.load().effq_pack_wcodes(ptr(w), c2, c1, taps, ptr(out), stream()), "effq_pack_wcodes")
+    out = torch.empty(c2 * c1 * taps, dtype=E4M3 if code_dtype == CODE_E4M3 else torch.bfloat16, device=w.device)
+    check(capi.load().effq_pack_wcodes(ptr(w), c2, c1, taps, int(code_dtype), ptr(out), stream()),
+          "effq_pack_wcodes")
     return out
 
 
@@ -382,7 +410,8 @@ def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], 
     ldw = wstar.stride(0)
     check(capi.load().effq_admm_project(ptr(wstar), ldw, ptr(dual), wstate.p, xstate.p if xstate else None,
                                         int(nlvl_w), int(nlvl_a), c2, c1, taps, int(has_bias), float(dual_div),
-                                        ptr(g_out), ptr(bstar_out), ptr(wcodes_out), st.p, stream()),
+                                        ptr(g_out), ptr(bstar_out), ptr(wcodes_out),
+                                        code_dtype_of(wcodes_out) if wcodes_out is not None else 0, st.p, stream()),
           "effq_admm_project")
 
 

@@ -111,14 +111,48 @@ class PTQConv(nn.Conv3d):
                                 self.stride, self.padding)
         return out
 
+    def _weight_codes(self, code_dtype=ops.CODE_BF16):
+        """Weight codes 2c-(L-1) of the stored fake-quant weights in the tensor-core layout
+        (c = round((w/alpha_w + 1)/delta), PTQConv.py:131-134); cached until the weights change."""
+        key = (self.weight.data_ptr(), self.weight._version, float(self.alpha_w.item()), code_dtype)
+        if self._wcodes_cache is None or self._wcodes_cache[0] != key:
+            _, c = ops.fakequant(self.weight.data, self.alpha_w.data, self.qlvl_w, -1.0, 1.0,
+                                 want_values=False, want_codes=True)
+            codes = 2.0 * c.float() - float(self.qlvl_w - 1)
+            self._wcodes_cache = (key, ops.pack_weight_codes(codes, code_dtype))
+        return self._wcodes_cache[1]
+
+    def _quantized_forward(self, x):
+        """Deployment forward (PTQConv.py:163-167): fake-quant activations + conv with the stored
+        quantized weights.  3x3x3 / 1x1x1 stride-1 layers run on the tcgen05 integer-code conv
+        (codes from the same fp32 arithmetic as `_quantize_act`, so the result equals the
+        reference's conv3d(qact, qweight) up to fp32 summation order); other layers use the
+        generic fp32 kernels."""
+        if self.q_act and self.q_weight and self.qlvl_act <= 256 and self.qlvl_w <= 256 and \
+                ops.conv3d_tc_supported(x.shape, self.out_channels, self.kernel_size, self.stride, self.padding):
+            fp8 = ops.fp8_codes_enabled() and self.qlvl_act <= 16 and self.qlvl_w <= 16 and \
+                ops.conv3d_tc_supported(x.shape, self.out_channels, self.kernel_size, self.stride, self.padding,
+                                        ops.CODE_E4M3)
+            if fp8:
+                _, xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data, bf16=False, e4m3=True)
+            else:
+                xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data)
+            wcodes = self._weight_codes(ops.CODE_E4M3 if fp8 else ops.CODE_BF16)
+            scale = (self.alpha_act.data.double() / (self.qlvl_act - 1) *
+                     self.alpha_w.data.double() / (self.qlvl_w - 1)).float().reshape(1)
+            out, _ = ops.conv3d_tc(xcodes, wcodes, self.bias.data if self.bias is not None else None,
+                                   scale, self.out_channels, self.kernel_size, want_out=True)
+            return out
+        qact = self._quantize_act(x) if self.q_act else x
+        return self._conv(qact)
+
     def forward(self, x):
         if self._fp:
             return F.conv3d(x, self.weight, self.bias, self.stride, self.padding)
         if self._quantizing:
             return self.ptq(x)                      # returns conv3d(qact, weight*, bias*) of the calibrated layer
         if self._quantized:
-            qact = self._quantize_act(x) if self.q_act else x
-            return self._conv(qact)
+            return self._quantized_forward(x.contiguous())
         if self._init_act:
             return self._conv(self.init_alpha_act(x))
         raise RuntimeError(f"Unknown FP/Quant setting: FP={self._fp}, "

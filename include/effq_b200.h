@@ -96,13 +96,21 @@ int effq_fakequant_f32(const float* x, int64_t numel, const float* alpha, float 
 int effq_fakequant_state(const float* x, int64_t numel, const effq_scale_state* state, float lo,
                          float hi, int32_t nlvl, float* y_out, void* stream);
 
-/* Activation codes for the tensor-core conv: NCDHW fp32 -> NDHWC bf16 integer codes.
- * use_f64 = 1 reproduces project_by_iter's final fp64 discretize with scale
+/* Element type of the integer codes the tensor-core kernels consume.  Both are exact:
+ * bf16 holds every code of <= 256 levels, e4m3 (1 byte, twice the K per tcgen05.mma)
+ * every code of <= 16 levels; the fp32 TMEM accumulation of the integer products is exact
+ * either way, so the two give bit-identical results. */
+#define EFFQ_CODE_BF16 0
+#define EFFQ_CODE_E4M3 1
+
+/* Activation codes for the tensor-core kernels: NCDHW fp32 -> NDHWC integer codes, as bf16
+ * (codes_bf16_out) and / or e4m3 bytes (codes_e4m3_out; nlvl <= 16, c % 16 == 0); either
+ * may be NULL.  use_f64 = 1 reproduces project_by_iter's final fp64 discretize with scale
  * state->a (EfficientQConv.py:68-70); use_f64 = 0 reproduces _quantize_act with the
  * fp32 scale alpha_f32 (PTQConv.py:114-116). */
 int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, int32_t nlvl,
                             const effq_scale_state* state, const float* alpha_f32, int32_t use_f64,
-                            void* codes_bf16_out, void* stream);
+                            void* codes_bf16_out, void* codes_e4m3_out, void* stream);
 
 /* ---- (a3) scale search: reference layer_helper.py:40-70 --------------------- */
 /* v = v1 (+ v2 if non-NULL, added in fp32 first as the reference's `w_star + dual`),
@@ -133,16 +141,18 @@ int effq_conv3d_f32(const float* x, const float* w, const float* bias, const eff
 /* tcgen05 implicit-GEMM conv on integer codes (k = 3/stride 1/pad 1, or k = 1):
  * out = conv_scale * sum(xcode*wcode) + bias, fp32 accumulation in TMEM,
  * fused squared-error reduction against `target` in the epilogue.
- * Requires c1 % 16 == 0, c2 % 16 == 0, c2 <= 256. */
-int effq_conv3d_tc_supported(const effq_geom* g);
+ * Requires c2 % 16 == 0, c2 <= 256 and c1 in {16, 32} or a multiple of 64 (bf16 codes),
+ * c1 in {32, 64} or a multiple of 128 (e4m3 codes).  Both operands use `code_dtype`. */
+int effq_conv3d_tc_supported(const effq_geom* g, int32_t code_dtype);
 int64_t effq_conv3d_tc_workspace(const effq_geom* g);
-int effq_conv3d_tc(const void* xcodes_ndhwc_bf16, const void* wcodes_bf16, const float* bias,
+int effq_conv3d_tc(const void* xcodes_ndhwc, const void* wcodes, int32_t code_dtype, const float* bias,
                    const float* conv_scale, const effq_geom* g, float* out, const float* target,
                    const float* att, double* sse, void* workspace, void* stream);
 
-/* [C2][C1][taps] fp32 integer weight codes (values 2c-(L-1)) -> bf16 codes in the layout
- * effq_conv3d_tc consumes (the same layout effq_admm_project emits). */
-int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int32_t taps, void* out, void* stream);
+/* [C2][C1][taps] fp32 integer weight codes (values 2c-(L-1)) -> codes of `code_dtype` in the
+ * layout effq_conv3d_tc consumes (the same layout effq_admm_project emits). */
+int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int32_t taps, int32_t code_dtype,
+                     void* out, void* stream);
 
 /* ---- (a7+a8) normal-equation statistics: solver.py:86-111, :282-314 ---------- */
 /* A0 = 2 X^ diag(att) X^T (K' x K'), B0 = 2 Y diag(att) X^T (C2 x K'), X^ the
@@ -189,11 +199,12 @@ int effq_admm_lhs(const float* a0, float rho, float eta, int32_t kp, int32_t has
                   float* a_out, void* stream);
 /* After the scale search on (w* + dual): G = a_w*b_w ; dual = (w* - G + dual)/dual_div;
  * b* = last column of w*; emits fp32 G (reference layout) and, if wcodes_out != NULL,
- * bf16 weight codes in the tensor-core layout; updates st->conv_scale / st->a_w. */
+ * weight codes of `code_dtype` in the tensor-core layout; updates st->conv_scale / st->a_w. */
 int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
                       const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                       int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
-                      float* bstar_out, void* wcodes_out, effq_admm_state* st, void* stream);
+                      float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
+                      void* stream);
 /* loss = fp32(sse/numel); history[iter] = loss; if (iter==0 || loss < best) keep G, b*
  * (and, when aux_bytes > 0, the 16B-aligned side buffer aux_src -> aux_dst, e.g. the
  * tensor-core weight codes of the same iterate). */

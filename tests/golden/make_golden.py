@@ -187,16 +187,24 @@ def run_ref_layer(R, x, w, b, y, stride, pad, qlvl_w, qlvl_a, q_act, pyramid):
                 hist=np.array(hist[:200], dtype=np.float64), final=np.float64(final))
 
 
-def gen_layers(R, out):
+LAYER_CASES = [
+    # name, n, c1, c2, k, s, p, spatial, Lw, La, q_act
+    ("w4a4_k3", 2, 16, 16, 3, 1, 1, (8, 16, 8), 16, 16, True),
+    ("w2a2_k3", 1, 16, 32, 3, 1, 1, (8, 16, 8), 4, 4, True),
+    ("w4a4_k1", 2, 16, 32, 1, 1, 0, (8, 8, 8), 16, 16, True),
+    ("first_k3s2", 2, 4, 16, 3, 2, 1, (16, 16, 16), 256, 256, False),
+]
+# channel counts of the real networks' inner layers (>= 32): these take the e4m3 operand path
+WIDE_LAYER_CASES = [
+    ("w4a4_k3_c32", 1, 32, 32, 3, 1, 1, (8, 16, 8), 16, 16, True),
+    ("w4a4_k1_c64", 2, 64, 32, 1, 1, 0, (8, 8, 8), 16, 16, True),
+    ("w2a4_k3_c64", 1, 64, 16, 3, 1, 1, (4, 16, 8), 4, 16, True),
+]
+
+
+def gen_layers(R, out, cases=LAYER_CASES, seed=15, fname="layers.npz"):
     res = {}
-    g = torch.Generator().manual_seed(15)
-    cases = [
-        # name, n, c1, c2, k, s, p, spatial, Lw, La, q_act
-        ("w4a4_k3", 2, 16, 16, 3, 1, 1, (8, 16, 8), 16, 16, True),
-        ("w2a2_k3", 1, 16, 32, 3, 1, 1, (8, 16, 8), 4, 4, True),
-        ("w4a4_k1", 2, 16, 32, 1, 1, 0, (8, 8, 8), 16, 16, True),
-        ("first_k3s2", 2, 4, 16, 3, 2, 1, (16, 16, 16), 256, 256, False),
-    ]
+    g = torch.Generator().manual_seed(seed)
     for name, n, c1, c2, k, s, p, sp, lw, la, qa in cases:
         x = torch.randn(n, c1, *sp, generator=g)
         if qa:
@@ -212,7 +220,11 @@ def gen_layers(R, out):
                     f"{name}_cfg": np.array([k, s, p, lw, la, int(qa)], dtype=np.int64)})
         res.update({f"{name}_out_{k2}": v for k2, v in r.items()})
         print(name, "final", r["final"], "alpha_w", r["alpha_w"], "alpha_act", r["alpha_act"])
-    np.savez_compressed(os.path.join(out, "layers.npz"), **res)
+    np.savez_compressed(os.path.join(out, fname), **res)
+
+
+def gen_layers_wide(R, out):
+    gen_layers(R, out, WIDE_LAYER_CASES, seed=17, fname="layers_wide.npz")
 
 
 TOY = dict(num_mod=4, num_classes=3, depth=[1, 1, 1], width=[8, 16, 8], dilation=[1, 1, 1],
@@ -325,7 +337,7 @@ def main():
     torch.manual_seed(0)
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
-                solver=gen_solver, layers=gen_layers, toy_net=gen_toy_net)
+                solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

@@ -78,6 +78,14 @@ def test_fakequant_state_and_ndhwc_codes(ops):
     codes32 = ops.quantize_act_ndhwc(x.to(DEV), 16, alpha=alpha.to(DEV))
     want32 = O.discretize_codes(x / alpha[0], 16, 0, 1).permute(0, 2, 3, 4, 1)
     assert torch.equal(codes32.cpu().float().int(), want32)
+    # e4m3 copy of the same codes, written by the same pass (<= 16 levels are exact in e4m3)
+    c16, c8 = ops.quantize_act_ndhwc(x.to(DEV), 16, state=st, e4m3=True)
+    assert c8.dtype == torch.float8_e4m3fn and torch.equal(c16, codes)
+    assert torch.equal(c8.cpu().float().int(), want)
+    none16, c8b = ops.quantize_act_ndhwc(x.to(DEV), 16, alpha=alpha.to(DEV), bf16=False, e4m3=True)
+    assert none16 is None and torch.equal(c8b.cpu().float().int(), want32)
+    with pytest.raises(Exception):
+        ops.quantize_act_ndhwc(x.to(DEV), 256, state=st, e4m3=True)       # 256 levels do not fit e4m3
 
 
 # ---------------------------------------------------------------- scale search (a3)
@@ -207,6 +215,52 @@ def test_conv3d_tc_exact_on_codes(ops, n, c1, c2, k, sp, la, lw):
     assert abs(sse2.item() - ref2) <= 1e-5 * ref2
 
 
+FP8_CASES = [
+    # n, c1, c2, k, spatial, La, Lw   (c1 = 32 -> 32 B rows / SW32, 64 -> SW64, 128 -> SW128, 256 -> two blocks)
+    (1, 32, 32, 3, (3, 16, 8), 16, 16),
+    (2, 32, 32, 1, (4, 16, 16), 16, 16),
+    (1, 64, 64, 3, (4, 16, 8), 16, 16),
+    (1, 64, 32, 3, (5, 20, 12), 4, 16),
+    (1, 128, 128, 3, (2, 8, 8), 16, 16),
+    (1, 128, 64, 1, (3, 9, 7), 16, 4),
+    (1, 256, 128, 3, (2, 8, 8), 16, 16),
+    (1, 256, 48, 1, (2, 10, 8), 4, 4),
+]
+
+
+@pytest.mark.parametrize("n,c1,c2,k,sp,la,lw", FP8_CASES)
+def test_conv3d_tc_e4m3_bit_identical_to_bf16(ops, n, c1, c2, k, sp, la, lw):
+    """<= 16 levels: the e4m3 operand path (kind::f8f6f4, K = 32) must give exactly the bits of the
+    bf16 path (kind::f16) -- same exact integer sums, same epilogue -- and of the fp64 reference."""
+    assert ops.conv3d_tc_supported((n, c1, *sp), c2, k, 1, (k - 1) // 2, ops.CODE_E4M3)
+    torch.manual_seed(c1 * 7 + c2 + k)
+    xc = torch.randint(0, la, (n, c1, *sp)).float()
+    wc = (2 * torch.randint(0, lw, (c2, c1, k, k, k)) - (lw - 1)).float()
+    b = torch.randn(c2).to(DEV)
+    cs = torch.tensor([0.0123], dtype=torch.float32, device=DEV)
+    target = torch.randn(n, c2, *sp).to(DEV)
+    att = (torch.rand(n, *sp) + 0.5).to(DEV)
+    xcl = xc.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    x16, x8 = xcl.to(torch.bfloat16), xcl.to(torch.float8_e4m3fn)
+    w16 = ops.pack_weight_codes(wc.to(DEV))
+    w8 = ops.pack_weight_codes(wc.to(DEV), ops.CODE_E4M3)
+    o16, s16 = ops.conv3d_tc(x16, w16, b, cs, c2, k, want_out=True, target=target, att=att)
+    o8, s8 = ops.conv3d_tc(x8, w8, b, cs, c2, k, want_out=True, target=target, att=att)
+    torch.cuda.synchronize()
+    assert torch.equal(o8, o16)
+    assert s8.item() == s16.item()
+    want = F.conv3d(xc.double(), wc.double(), None, 1, (k - 1) // 2).float() * 0.0123 + b.cpu().view(1, -1, 1, 1, 1)
+    torch.testing.assert_close(o8.cpu(), want, rtol=2e-6, atol=2e-6)
+    with pytest.raises(Exception):
+        ops.conv3d_tc(x8, w16, b, cs, c2, k)                 # mixed operand types are refused
+
+
+def test_conv3d_tc_e4m3_unsupported_shapes(ops):
+    assert not ops.conv3d_tc_supported((1, 16, 4, 16, 8), 32, 3, 1, 1, ops.CODE_E4M3)     # 16 B rows
+    assert not ops.conv3d_tc_supported((1, 192, 4, 16, 8), 32, 3, 1, 1, ops.CODE_E4M3)    # not a multiple of 128
+    assert ops.conv3d_tc_supported((1, 192, 4, 16, 8), 32, 3, 1, 1, ops.CODE_BF16)
+
+
 def test_conv3d_tc_linearity_at_scale(ops):
     """Full-size property check (too big for the CPU oracle): conv is linear in the weights,
     and agrees with the generic fp32 kernel on the same codes."""
@@ -221,6 +275,8 @@ def test_conv3d_tc_linearity_at_scale(ops):
     assert torch.equal(o1, -o2)
     ref, _ = ops.conv3d_f32(xc, w1, None, 1, 1)
     assert torch.equal(o1, ref)                      # integers < 2^24: both paths exact
+    o8, _ = ops.conv3d_tc(xq.to(torch.float8_e4m3fn), ops.pack_weight_codes(w1, ops.CODE_E4M3), None, cs, c, 3)
+    assert torch.equal(o8, ref)
 
 
 # ---------------------------------------------------------------- normal equations (a7, a8)

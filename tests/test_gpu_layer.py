@@ -23,10 +23,15 @@ def engine_mod():
     return layer_engine
 
 
-@pytest.mark.parametrize("name", ["w4a4_k3", "w2a2_k3", "w4a4_k1", "first_k3s2"])
+WIDE = ["w4a4_k3_c32", "w4a4_k1_c64", "w2a4_k3_c64"]       # >= 32 input channels: e4m3 operand path
+
+
+@pytest.mark.parametrize("name", ["w4a4_k3", "w2a2_k3", "w4a4_k1", "first_k3s2"] + WIDE)
 @pytest.mark.parametrize("generic", [False, True])
 def test_layer_calibration_matches_reference(engine_mod, golden, name, generic):
-    g = golden("layers.npz")
+    if generic and name in WIDE[1:]:
+        pytest.skip("generic path covered by the other cases")
+    g = golden("layers_wide.npz" if name in WIDE else "layers.npz")
     k, s, p, lw, la, qa = [int(t) for t in g[f"{name}_cfg"]]
     x = torch.from_numpy(g[f"{name}_x"]).to(DEV)
     w = torch.from_numpy(g[f"{name}_w"]).to(DEV)
@@ -61,6 +66,32 @@ def test_layer_calibration_matches_reference(engine_mod, golden, name, generic):
     lv = torch.unique(wq)
     assert lv.numel() <= lw
     assert rep.factorizations == 5
+
+
+@pytest.mark.parametrize("name", WIDE)
+def test_layer_calibration_e4m3_equals_bf16(engine_mod, golden, name, monkeypatch):
+    """The e4m3 and bf16 operand paths compute the same exact integer sums: the whole 200-iterate
+    loss history, the scales and the calibrated weights must be bit-identical."""
+    from efficientq_b200 import ops
+    g = golden("layers_wide.npz")
+    k, s, p, lw, la, qa = [int(t) for t in g[f"{name}_cfg"]]
+    args = [torch.from_numpy(g[f"{name}_{t}"]).to(DEV) for t in ("x", "w", "b", "y")]
+    att = torch.from_numpy(g[f"{name}_att"]).to(DEV)
+    pyr = [torch.ones(args[0].shape[0], 3, 3, 3, device=DEV), att]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("EFFQ_FP8", flag)
+        ops.timer.enabled, ops.timer.records = True, {}
+        eng = engine_mod.LayerCalibrator(torch.device(DEV), keep_history=True)
+        res[flag] = eng.run(args[0], args[1], args[2], args[3], s, p, lw, la, bool(qa), pyr, name=name)
+        names = set(ops.timer.records.keys())
+        ops.timer.enabled = False
+        ops.timer.reset()
+        assert any(n.endswith("_e4m3") for n in names) == (flag == "1"), names
+    (wq1, bq1, aw1, aa1, o1, r1), (wq0, bq0, aw0, aa0, o0, r0) = res["1"], res["0"]
+    assert r1.history == r0.history
+    assert torch.equal(wq1, wq0) and torch.equal(bq1, bq0) and torch.equal(o1, o0)
+    assert float(aw1) == float(aw0) and float(aa1) == float(aa0)
 
 
 def build_toy():
@@ -105,3 +136,26 @@ def test_toy_network_matches_reference(engine_mod, golden):
     # prefix, tolerance documented in DESIGN.md
     assert abs(losses[0] - ref[0]) <= 1e-3 * ref[0]
     np.testing.assert_allclose(losses, ref, rtol=5e-2)
+
+
+@pytest.mark.parametrize("c1,c2,k", [(32, 32, 3), (64, 32, 1), (16, 48, 3)])
+def test_quantized_forward_matches_reference_semantics(engine_mod, c1, c2, k):
+    """Deployment forward (PTQConv.forward, _quantized branch, PTQConv.py:163-167) on the
+    tensor-core code path vs the oracle's  conv3d(quantize_act(x), qweight, bias)."""
+    import torch.nn.functional as F
+    from efficientq_b200.qconv import EfficientQConv
+    from oracle import effq_oracle as O
+    torch.manual_seed(c1 + k)
+    m = EfficientQConv(c1, c2, k, 1, (k - 1) // 2, bias=True, q_weight=True, qlvl=16, q_act=True, qlvl_act=16)
+    a_w, a_act = torch.tensor(0.21), torch.tensor(1.7)
+    qw = O.quantize_w(torch.randn(c2, c1, k, k, k) * 0.1, a_w, 16)
+    m.weight.data, m.alpha_w.data, m.alpha_act.data = qw.clone(), a_w.clone(), a_act.clone()
+    m.bias.data = torch.randn(c2) * 0.1
+    x = torch.relu(torch.randn(2, c1, 6, 16, 8)) * 1.2
+    want = F.conv3d(O.quantize_act(x, a_act, 16).double(), qw.double(), m.bias.data.double(), 1, (k - 1) // 2).float()
+    m.to(DEV)
+    m.set_quantized()
+    with torch.no_grad():
+        got = m(x.to(DEV))
+    assert m._wcodes_cache is not None                      # the tcgen05 path was taken
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-5)

@@ -74,9 +74,9 @@ def test_im2col_and_normal_equations(golden, name):
     np.testing.assert_allclose(bs.numpy(), g[f"{name}_bstar"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["w4a4_k3", "w2a2_k3", "w4a4_k1", "first_k3s2"])
+@pytest.mark.parametrize("name", ["w4a4_k3", "w2a2_k3", "w4a4_k1", "first_k3s2", "w4a4_k1_c64"])
 def test_admm_layer(golden, name):
-    g = golden("layers.npz")
+    g = golden("layers_wide.npz" if "_c" in name else "layers.npz")
     k, s, p, lw, la, qa = [int(t) for t in g[f"{name}_cfg"]]
     x = torch.from_numpy(g[f"{name}_x"])
     w = torch.from_numpy(g[f"{name}_w"])

@@ -12,9 +12,11 @@
 // bit-identical between the two operand types.
 //
 // GEMM view: M = output voxels (tile = 16 h-rows x 8 w, one d-plane -> 128 rows),
-// N = C2, K = taps * C1.  No im2col: the producer warps copy ONE halo block
-// (kd x (16+kh-1) x (8+kw-1) voxels x one channel block of <= 128 bytes) per tile into shared
-// memory as K-major rows with the UMMA 128/64/32-byte swizzle (tc_layout.cuh); the A descriptor
+// N = C2, K = taps * C1.  No im2col: ONE 5-D TMA box (cp.async.bulk.tensor, tile mode) brings the
+// halo block (kd x (16+kh-1) x (8+kw-1) voxels x one channel block of <= 128 bytes) of a tile
+// into shared memory as K-major rows with the UMMA 128/64/32-byte swizzle (tc_layout.cuh);
+// box coordinates outside the volume are zero-filled by the hardware, which is exactly the
+// convolution's zero padding and the ragged tile edge.  The A descriptor
 // of tap (a,b,c) is the same block with the start address shifted by ((a*HH + b)*WP + c) rows
 // (the swizzle is a function of the absolute address, so any row may start a descriptor), so
 // every activation byte is fetched from L2 once per tile and reused by all taps.  Weights
@@ -24,18 +26,23 @@
 // TMEM accumulator; four epilogue warps drain it with tcgen05.ld, apply scale+bias, read the
 // fp32 target (NCDHW), and reduce att*(out-target)^2.
 //
-// Warp roles (320 threads): 0 weight TMA | 1 MMA issuer + TMEM owner | 2-5 epilogue |
-// 6-9 halo producers (cp.async, zero-fill for padding / ragged edges).
+// The fp32 target tile of the epilogue ([32 channels][16 h][8 w], NCDHW) is also a TMA box into
+// a small shared-memory ring when the shape allows (W % 4 == 0, C2 % 32 == 0, room for two
+// 16 KB stages); otherwise the epilogue threads load it directly.
+//
+// Warp roles (256 threads): 0 weight TMA | 1 MMA issuer + TMEM owner | 2-5 epilogue |
+// 6 halo TMA | 7 target TMA.
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include "tc_layout.cuh"
 
 namespace effq {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 256;
 constexpr int TC_TILE_H = 16;
 constexpr int TC_TILE_W = 8;
-constexpr int TC_PRODUCERS = 128;
+constexpr uint32_t TC_TGT_BYTES = 32u * TC_TILE_H * TC_TILE_W * 4u;     // one target stage: 32 channels of a tile
 constexpr int TC_EPI = 128;
 constexpr unsigned int TC_SPIN_LIMIT = 1u << 26;
 
@@ -58,7 +65,9 @@ struct TcParams {
   int tiles_h, tiles_w;
   long long n_tiles;
   int n_halo_stages, n_w_stages, w_resident;
-  unsigned int halo_bytes, wtile_bytes;
+  int n_tgt_stages;            // > 0: the target tile arrives by TMA through a ring of this many stages
+  unsigned int off_tgt;
+  unsigned int halo_bytes, halo_tx_bytes, wtile_bytes;   // stage stride, bytes one halo box delivers, weight tile
   unsigned int off_bias, off_halo, off_w;
   unsigned int tmem_cols;
   int swz, rp, debug;          // operand swizzle width (128/64/32 B), row pitch, bring-up debug bits
@@ -113,6 +122,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// 5-D tiled TMA load (coordinates innermost first: channel, w, h, d, n; may be negative / beyond
+// the tensor: those elements arrive as zeros and still count towards the transaction bytes)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int d, int n,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -214,11 +232,48 @@ struct Pipe {
   }
 };
 
+// ---- epilogue pieces (NC = 32 or 16 channels of one voxel per thread) -------------------------
+template <int NC>
+__device__ __forceinline__ void epi_load_targets(float (&tv)[32], const float* tp, long long chan, bool want) {
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    tv[j] = want ? __ldg(tp) : 0.f;
+    tp += chan;
+  }
+}
+// v: raw accumulators in, outputs (scale * acc + bias) out; returns sum (out - target)^2 of the chunk
+template <int NC>
+__device__ __forceinline__ float epi_chunk(uint32_t (&v)[32], const float (&tv)[32], const float* bias_c0, float scale) {
+  float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_c0 + j);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float o = fmaf(__uint_as_float(v[j + k]), scale, bb[k]);
+      const float dlt = o - tv[j + k];
+      e[k] = fmaf(dlt, dlt, e[k]);
+      v[j + k] = __float_as_uint(o);
+    }
+  }
+  return (e[0] + e[1]) + (e[2] + e[3]);
+}
+template <int NC>
+__device__ __forceinline__ void epi_store(const uint32_t (&v)[32], float* op, long long chan) {
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    __stcs(op, __uint_as_float(v[j]));
+    op += chan;
+  }
+}
+
 // KS: kernel edge (3 or 1), KK: MMAs per (tap, channel block) = row bytes / 32, WRES: weights
 // resident in shared memory and FP8: e4m3 operands are compile-time, so the single MMA-issuing
 // thread runs straight-line code.
 template <int KS, int KK, bool WRES, bool FP8>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024 B alignment
   // barrier block (8 B each): halo_full[4] halo_empty[4] w_full[8] w_empty[8] wres tmem_full[2] tmem_empty[2]
@@ -226,6 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   constexpr int B_HF = 0, B_HE = 4, B_WF = 8, B_WE = 16, B_WRES = 24, B_TF = 25, B_TE = 27, B_TMEMPTR = 30;
+  constexpr int B_GF = 32, B_GE = 36;            // target ring: full (TMA complete_tx) / empty (128 epilogue threads)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + B_TMEMPTR);
   float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
   const uint32_t halo0 = smem_u32(smem + p.off_halo);
@@ -237,10 +293,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
   volatile unsigned int* abort_flag = p.ws_done + 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_HF + i), TC_PRODUCERS); mbar_init(BAR(B_HE + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_HF + i), 1); mbar_init(BAR(B_HE + i), 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(BAR(B_WF + i), 1); mbar_init(BAR(B_WE + i), 1); }
     mbar_init(BAR(B_WRES), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TF + i), 1); mbar_init(BAR(B_TE + i), TC_EPI); }
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_GF + i), 1); mbar_init(BAR(B_GE + i), TC_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.c2; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
@@ -352,7 +409,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
     const float scale = __ldg(p.conv_scale);
     const long long plane = (long long)p.h * p.w;
     const long long chan = (long long)p.d * plane;
-    Pipe ap{0, 0};
+    Pipe ap{0, 0}, gp{0, 0};
+    const float* tgt_row = reinterpret_cast<const float*>(smem + p.off_tgt) + row;
     bool ok = true;
     for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
       unsigned int r = tile;
@@ -364,19 +422,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       const bool live = oh < p.h && ow < p.w;
       const long long sp = (long long)dd * plane + (long long)oh * p.w + ow;
       const long long base = (long long)nn * p.c2 * chan + sp;
+      if (p.n_tgt_stages > 0) {
+        // ---- target tile staged in shared memory by the TMA warp: [32 channels][128 voxels] fp32 ----
+        float* optr = p.out + base;
+        const bool store = live && p.out != nullptr;
+        float e32 = 0.f;
+        for (int c0 = 0; c0 < p.c2 && ok; c0 += 32) {
+          if (!mbar_wait<32>(BAR(B_GF + gp.stage), gp.phase, abort_flag)) { ok = false; break; }
+          if (c0 == 0) {
+            if (!mbar_wait<32>(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
+            if (threadIdx.x == 64) dbg_stamp(p, tile, 3);
+            tc_fence_after();
+          }
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.c2 + c0), v);
+          float tv[32];
+          const float* ts = tgt_row + gp.stage * (int)(TC_TGT_BYTES / 4);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tv[j] = ts[j * (TC_TILE_H * TC_TILE_W)];     // lanes read consecutive floats
+          tc_wait_ld();
+          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale);
+          mbar_arrive(BAR(B_GE + gp.stage));
+          gp.advance(p.n_tgt_stages);
+          if (store) epi_store<32>(v, optr, chan);
+          optr += 32 * chan;
+        }
+        if (!ok) break;
+        tc_fence_before();
+        mbar_arrive(BAR(B_TE + ap.stage));
+        if (threadIdx.x == 64) dbg_stamp(p, tile, 4);
+        ap.advance(2);
+        if (live) {
+          const float wv = p.att ? __ldg(p.att + (long long)nn * chan + sp) : 1.f;
+          err_acc += (double)e32 * (double)wv;
+        }
+        continue;
+      }
       // Target values do not depend on the MMA: issue all loads of a 32-channel chunk before
       // anything consumes them (32 independent requests in flight per thread), the first chunk
-      // even before waiting for the accumulator.
-      const bool want_t = live && p.target != nullptr;
+      // even before waiting for the accumulator.  Addresses advance by one running pointer per
+      // chunk (the epilogue is instruction-bound: a 64-bit multiply per load tripled its length).
+      const bool want_t = live && p.target != nullptr && !(p.debug & 16);   // bit 16: bring-up, skip the target reads
       // (a second register buffer for the next chunk's loads was tried: 168 registers with spills,
       //  12-25 % slower -- profiles/r01_conv_layout.md)
       float tv[32];
-      auto load_targets = [&](int c0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          tv[j] = (want_t && c0 + j < p.c2) ? __ldg(p.target + base + (long long)(c0 + j) * chan) : 0.f;
-      };
-      load_targets(0);
+      const float* tptr = p.target + base;          // only dereferenced when want_t
+      float* optr = p.out + base;                   // only dereferenced when live && p.out
+      const bool store = live && p.out != nullptr;
+      if (p.c2 >= 32) epi_load_targets<32>(tv, tptr, chan, want_t); else epi_load_targets<16>(tv, tptr, chan, want_t);
       if (!mbar_wait<64>(BAR(B_TF + ap.stage), ap.phase, abort_flag)) { ok = false; break; }
       if (threadIdx.x == 64) dbg_stamp(p, tile, 3);
       tc_fence_after();
@@ -384,22 +477,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
       for (int c0 = 0; c0 < p.c2; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ap.stage * p.c2 + c0);
-        const int ncol = min(32, p.c2 - c0);
-        if (ncol == 32) tc_ld32(taddr, v); else tc_ld16(taddr, v);
-        tc_wait_ld();
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          o[j] = (j < ncol) ? fmaf(__uint_as_float(v[j]), scale, bias_s[c0 + j]) : 0.f;
-          const float dlt = o[j] - tv[j];
-          if (j < ncol) e32 = fmaf(dlt, dlt, e32);
+        const int rest = p.c2 - c0 - 32;            // channels after this chunk (>= 16 or <= 0)
+        if (rest >= 0) {
+          tc_ld32(taddr, v);
+          tc_wait_ld();
+          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale);
+          if (rest >= 32) epi_load_targets<32>(tv, tptr + 32 * chan, chan, want_t);      // next chunk's loads overlap
+          else if (rest > 0) epi_load_targets<16>(tv, tptr + 32 * chan, chan, want_t);   // this chunk's stores
+          if (store) epi_store<32>(v, optr, chan);
+        } else {
+          tc_ld16(taddr, v);
+          tc_wait_ld();
+          e32 += epi_chunk<16>(v, tv, bias_s + c0, scale);
+          if (store) epi_store<16>(v, optr, chan);
         }
-        if (c0 + 32 < p.c2) load_targets(c0 + 32);       // next chunk's loads overlap this chunk's stores
-        if (live && p.out) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) __stcs(p.out + base + (long long)(c0 + j) * chan, o[j]);
-        }
+        tptr += 32 * chan;
+        optr += 32 * chan;
       }
       tc_fence_before();
       mbar_arrive(BAR(B_TE + ap.stage));
@@ -410,96 +503,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3d_tc_kernel(const TcParams
         err_acc += (double)e32 * (double)wv;
       }
     }
-  } else {
-    // ===== halo producers: cp.async 16 B pieces, zero-fill outside the volume =====
-    // The set of (halo voxel, chunk) items a thread copies is the same for every tile, so the
-    // shared-memory destination (with its swizzle), the global offset relative to the tile origin
-    // and the halo coordinates are computed ONCE; per tile an item costs three range checks, one
-    // 64-bit add and the cp.async.  Lanes walk (chunk fastest, then w): a warp's copies are
-    // contiguous runs in global memory (whole 32 B sectors) .
-    const int ptid = threadIdx.x - 6 * 32;                    // 0..127
-    const int used_w = TC_TILE_W + p.kw - 1;                  // halo columns actually read
-    const int cpi = p.nch > 4 ? p.nch / 4 : 1;                // chunks per item (nch = 8 -> 2)
-    const int ipv = p.nch / cpi;                              // items per voxel
-    const int n_items = p.kd * p.hh * used_w * ipv;
-    constexpr int MAX_IT = 17;                                // ceil(3*18*10*4 / 128)
-    int rel[MAX_IT];                                          // byte offset from the tile origin
-    uint32_t dst[MAX_IT];                                     // byte offset inside the halo stage
-    uint32_t crd[MAX_IT];                                     // dz | hy << 4 | wx << 12 | valid << 20
-#pragma unroll
-    for (int i = 0; i < MAX_IT; ++i) {
-      const int it = ptid + i * TC_PRODUCERS;
-      rel[i] = 0; dst[i] = 0; crd[i] = 0;
-      if (it < n_items) {
-        const int q = it % ipv, vox = it / ipv;
-        const int wx = vox % used_w, rr = vox / used_w;
-        const int dz = rr / p.hh, hy = rr % p.hh;
-        const int hrow = rr * p.wp + wx;
-        const int j0 = q * cpi;
-        rel[i] = (((dz * p.h + hy) * p.w + wx) * p.c1) * p.eb + j0 * 16;
-        dst[i] = (uint32_t)(hrow * p.rp) | ((uint32_t)tc_chunk_xor(hrow, p.swz) << 24) | ((uint32_t)j0 << 28);
-        crd[i] = (uint32_t)dz | ((uint32_t)hy << 4) | ((uint32_t)wx << 12) | (1u << 20);
-      }
-    }
-    Pipe hp{0, 0};
-    bool ok = true;
-    bool pending = false;
-    int pending_stage = 0;
-    const bool defer = p.n_halo_stages >= 3;       // deep ring: keep one extra block of copies in flight
-    for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
-      unsigned int r = tile;
-      const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
-      const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
-      const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
-      const int nn = (int)r;
-      const int h0 = th * TC_TILE_H - p.ph, w0 = tw * TC_TILE_W - p.pw, d0 = dd - p.pd;
-      // pointer of halo voxel (0,0,0), channel 0 -- may lie outside the tensor, only dereferenced when valid
-      const uint8_t* origin = p.xq + ((((long long)nn * p.d + d0) * p.h + h0) * p.w + w0) * p.c1 * p.eb;
-      for (int g = 0; g < p.n_groups; ++g) {
-        if (!mbar_wait<64>(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
-        if (ptid == 0 && g == 0) dbg_stamp(p, tile, 5);
-        const uint32_t hbase = halo0 + (uint32_t)hp.stage * p.halo_bytes;
-        const uint8_t* gorigin = origin + g * p.rp;
-#pragma unroll
-        for (int i = 0; i < MAX_IT; ++i) {
-          const uint32_t c = crd[i];
-          if (c >> 20) {                                         // item exists (thread-uniform per i)
-            const int gd = d0 + (int)(c & 15u), gh = h0 + (int)((c >> 4) & 255u), gw = w0 + (int)((c >> 12) & 255u);
-            const bool okk = (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w;
-            const uint8_t* src = okk ? gorigin + rel[i] : p.xq;
-            const uint32_t rowb = hbase + (dst[i] & 0xffffffu);
-            const uint32_t x = (dst[i] >> 24) & 15u, j0 = dst[i] >> 28;
-            cp_async16(rowb + (((j0) ^ x) << 4), src, okk ? 16u : 0u);
-            if (cpi == 2) cp_async16(rowb + (((j0 + 1) ^ x) << 4), src + 16, okk ? 16u : 0u);
-          }
-        }
-        cp_async_commit();
-        if (ptid == 0 && g == 0) dbg_stamp(p, tile, 6);
-        if (!defer) {
-          // two halo stages: signal this block as soon as it has landed.  (Deferring the signal
-          // behind the NEXT block's issue, as below, would chain MMA(t) to MMA(t-1) through the
-          // wait for a free stage.)
-          cp_async_wait<0>();
-          fence_proxy_async();
-          mbar_arrive(BAR(B_HF + hp.stage));
+  } else if (warp == 6) {
+    // ===== halo loader: one 5-D TMA box per (tile, channel block); padding and ragged edges are
+    // the hardware's out-of-bounds zero fill =====
+    if (elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
+      Pipe hp{0, 0};
+      bool ok = true;
+      for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
+        unsigned int r = tile;
+        const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
+        const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
+        const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
+        const int nn = (int)r;
+        const int h0 = th * TC_TILE_H - p.ph, w0 = tw * TC_TILE_W - p.pw, d0 = dd - p.pd;
+        for (int g = 0; g < p.n_groups; ++g) {
+          if (!mbar_wait<32>(BAR(B_HE + hp.stage), hp.phase ^ 1u, abort_flag)) { ok = false; break; }
+          if (g == 0) dbg_stamp(p, tile, 5);
+          mbar_expect_tx(BAR(B_HF + hp.stage), p.halo_tx_bytes);
+          tma_load_5d(halo0 + (uint32_t)hp.stage * p.halo_bytes, &xmap, g * p.cg, w0, h0, d0, nn, BAR(B_HF + hp.stage));
+          if (g == 0) dbg_stamp(p, tile, 6);
           hp.advance(p.n_halo_stages);
-          continue;
         }
-        if (pending) {                              // previous block: complete -> visible to the async proxy -> signal
-          cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(BAR(B_HF + pending_stage));
-        }
-        pending = true;
-        pending_stage = hp.stage;
-        hp.advance(p.n_halo_stages);
       }
     }
-    if (pending) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(BAR(B_HF + pending_stage));
+    __syncwarp();
+  } else {
+    // ===== target loader: the epilogue's fp32 target tile, 32 channels per box =====
+    if (p.n_tgt_stages > 0 && elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+      const uint32_t tgt0 = smem_u32(smem + p.off_tgt);
+      Pipe gp{0, 0};
+      bool ok = true;
+      for (unsigned int tile = tile0; tile < n_tiles && ok; tile += tstep) {
+        unsigned int r = tile;
+        const int tw = (int)(r % (unsigned)p.tiles_w); r /= (unsigned)p.tiles_w;
+        const int th = (int)(r % (unsigned)p.tiles_h); r /= (unsigned)p.tiles_h;
+        const int dd = (int)(r % (unsigned)p.d); r /= (unsigned)p.d;
+        const int nn = (int)r;
+        for (int c0 = 0; c0 < p.c2; c0 += 32) {
+          if (!mbar_wait<32>(BAR(B_GE + gp.stage), gp.phase ^ 1u, abort_flag)) { ok = false; break; }
+          mbar_expect_tx(BAR(B_GF + gp.stage), TC_TGT_BYTES);
+          tma_load_5d(tgt0 + (uint32_t)gp.stage * TC_TGT_BYTES, &tmap, tw * TC_TILE_W, th * TC_TILE_H, dd, c0, nn,
+                      BAR(B_GF + gp.stage));
+          gp.advance(p.n_tgt_stages);
+        }
+      }
     }
+    __syncwarp();
   }
 
   // ---- teardown -------------------------------------------------------------------------
@@ -560,26 +611,36 @@ static bool tc_plan(const effq_geom& g, int code_dtype, TcParams& p) {
   p.tiles_h = (g.h + TC_TILE_H - 1) / TC_TILE_H;
   p.tiles_w = (g.w + TC_TILE_W - 1) / TC_TILE_W;
   p.n_tiles = (long long)g.n * g.d * p.tiles_h * p.tiles_w;
-  p.halo_bytes = (uint32_t)(p.hv * p.rp);
-  p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
+  p.halo_tx_bytes = (uint32_t)(p.hv * p.rp);
+  p.halo_bytes = (p.halo_tx_bytes + 1023u) & ~1023u;
   p.wtile_bytes = (uint32_t)(p.rp * g.c2);
   p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
-  p.off_bias = 256;
+  p.off_bias = 384;
   p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
   const uint32_t budget = 224u * 1024u;
   const uint32_t w_all = p.wstage_bytes * (uint32_t)(p.n_groups * p.taps);
+  // Shared-memory plan: halo ring (>= 2 stages), weights (resident, else a ring of >= 2 tiles), and --
+  // when the target can be a TMA box -- a target ring of >= 2 stages; leftover space deepens the rings.
+  const bool tgt_ok = (g.w % 4 == 0) && (g.c2 % 32 == 0);
   p.n_halo_stages = 2;
+  p.n_tgt_stages = 0;
   if (p.off_halo + 2u * p.halo_bytes + w_all <= budget) {
     p.w_resident = 1;
     p.n_w_stages = 0;
-    uint32_t left = budget - (p.off_halo + w_all);
-    int hs = (int)(left / p.halo_bytes);
-    p.n_halo_stages = hs > 4 ? 4 : hs;
-    p.off_w = p.off_halo + (uint32_t)p.n_halo_stages * p.halo_bytes;
+    uint32_t left = budget - (p.off_halo + w_all + 2u * p.halo_bytes);
+    if (tgt_ok && left >= 2u * TC_TGT_BYTES) { p.n_tgt_stages = 2; left -= 2u * TC_TGT_BYTES; }
+    for (int round = 0; round < 2; ++round) {            // alternate: one more halo stage, one more target stage
+      if (p.n_halo_stages < 4 && left >= p.halo_bytes) { ++p.n_halo_stages; left -= p.halo_bytes; }
+      if (p.n_tgt_stages > 0 && p.n_tgt_stages < 4 && left >= TC_TGT_BYTES) { ++p.n_tgt_stages; left -= TC_TGT_BYTES; }
+    }
+    p.off_tgt = p.off_halo + (uint32_t)p.n_halo_stages * p.halo_bytes;
+    p.off_w = p.off_tgt + (uint32_t)p.n_tgt_stages * TC_TGT_BYTES;
   } else {
     p.w_resident = 0;
-    p.off_w = p.off_halo + 2u * p.halo_bytes;       // the producer pipeline needs >= 2 halo stages
-    if (p.off_w + 2u * p.wstage_bytes > budget) return false;
+    p.off_tgt = p.off_halo + 2u * p.halo_bytes;       // the loader pipeline needs >= 2 halo stages
+    if (p.off_tgt + 2u * p.wstage_bytes > budget) return false;
+    if (tgt_ok && p.off_tgt + 2u * TC_TGT_BYTES + 3u * p.wstage_bytes <= budget) p.n_tgt_stages = 2;
+    p.off_w = p.off_tgt + (uint32_t)p.n_tgt_stages * TC_TGT_BYTES;
     int ws = (int)((budget - p.off_w) / p.wstage_bytes);
     p.n_w_stages = ws > 8 ? 8 : ws;
   }
@@ -596,33 +657,88 @@ static uint32_t tc_smem_bytes(const TcParams& p) {
 }
 
 template <int KS, int KK, bool WRES, bool FP8>
-static int tc_launch(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
+static int tc_launch(const TcParams& p, const CUtensorMap& xmap, const CUtensorMap& tmap, uint32_t smem, unsigned ctas, cudaStream_t s) {
   static uint32_t configured = 0;
   if (smem > configured) {
     EFFQ_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KS, KK, WRES, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  conv3d_tc_kernel<KS, KK, WRES, FP8><<<ctas, TC_THREADS, smem, s>>>(p);
+  conv3d_tc_kernel<KS, KK, WRES, FP8><<<ctas, TC_THREADS, smem, s>>>(p, xmap, tmap);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }
 
 template <int KS, int KK>
-static int tc_dispatch_w(const TcParams& p, uint32_t smem, unsigned ctas, cudaStream_t s) {
+static int tc_dispatch_w(const TcParams& p, const CUtensorMap& m, const CUtensorMap& t, uint32_t smem, unsigned ctas, cudaStream_t s) {
   if (p.eb == 1)
-    return p.w_resident ? tc_launch<KS, KK, true, true>(p, smem, ctas, s) : tc_launch<KS, KK, false, true>(p, smem, ctas, s);
-  return p.w_resident ? tc_launch<KS, KK, true, false>(p, smem, ctas, s) : tc_launch<KS, KK, false, false>(p, smem, ctas, s);
+    return p.w_resident ? tc_launch<KS, KK, true, true>(p, m, t, smem, ctas, s) : tc_launch<KS, KK, false, true>(p, m, t, smem, ctas, s);
+  return p.w_resident ? tc_launch<KS, KK, true, false>(p, m, t, smem, ctas, s) : tc_launch<KS, KK, false, false>(p, m, t, smem, ctas, s);
 }
 
-static int tc_dispatch(const TcParams& p, int ks, int kk, uint32_t smem, unsigned ctas, cudaStream_t s) {
+static int tc_dispatch(const TcParams& p, const CUtensorMap& m, const CUtensorMap& t, int ks, int kk, uint32_t smem, unsigned ctas,
+                       cudaStream_t s) {
   if (ks == 3) {
-    if (kk == 1) return tc_dispatch_w<3, 1>(p, smem, ctas, s);
-    if (kk == 2) return tc_dispatch_w<3, 2>(p, smem, ctas, s);
-    return tc_dispatch_w<3, 4>(p, smem, ctas, s);
+    if (kk == 1) return tc_dispatch_w<3, 1>(p, m, t, smem, ctas, s);
+    if (kk == 2) return tc_dispatch_w<3, 2>(p, m, t, smem, ctas, s);
+    return tc_dispatch_w<3, 4>(p, m, t, smem, ctas, s);
   }
-  if (kk == 1) return tc_dispatch_w<1, 1>(p, smem, ctas, s);
-  if (kk == 2) return tc_dispatch_w<1, 2>(p, smem, ctas, s);
-  return tc_dispatch_w<1, 4>(p, smem, ctas, s);
+  if (kk == 1) return tc_dispatch_w<1, 1>(p, m, t, smem, ctas, s);
+  if (kk == 2) return tc_dispatch_w<1, 2>(p, m, t, smem, ctas, s);
+  return tc_dispatch_w<1, 4>(p, m, t, smem, ctas, s);
+}
+
+// Tensor map of the NDHWC code tensor, dims innermost first (C, W, H, D, N), box = one halo block.
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tc_encoder() {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return (EncodeTiledFn)fn;
+  }();
+  if (!encode) set_error("effq_conv3d_tc: cuTensorMapEncodeTiled not available from the driver");
+  return encode;
+}
+
+// Tensor map of the NCDHW fp32 target, dims innermost first (W, H, D, C2, N), box = 32 channels of
+// one output tile, dense in shared memory as [channel][h][w].
+static int tc_make_tmap(const TcParams& p, const float* target, CUtensorMap* map) {
+  EncodeTiledFn encode = tc_encoder();
+  if (!encode) return 2;
+  const cuuint64_t dims[5] = {(cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.d, (cuuint64_t)p.c2, (cuuint64_t)p.n};
+  const cuuint64_t strides[4] = {dims[0] * 4, dims[0] * dims[1] * 4, dims[0] * dims[1] * dims[2] * 4,
+                                 dims[0] * dims[1] * dims[2] * dims[3] * 4};
+  const cuuint32_t box[5] = {(cuuint32_t)TC_TILE_W, (cuuint32_t)TC_TILE_H, 1u, 32u, 1u};
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(target), dims, strides, box,
+                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { set_error("effq_conv3d_tc: cuTensorMapEncodeTiled(target) failed (%d)", (int)rc); return 2; }
+  return 0;
+}
+
+static int tc_make_xmap(const TcParams& p, const void* xcodes, CUtensorMap* map) {
+  EncodeTiledFn encode = tc_encoder();
+  if (!encode) return 2;
+  const cuuint64_t eb = (cuuint64_t)p.eb;
+  const cuuint64_t dims[5] = {(cuuint64_t)p.c1, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.d, (cuuint64_t)p.n};
+  const cuuint64_t strides[4] = {dims[0] * eb, dims[0] * dims[1] * eb, dims[0] * dims[1] * dims[2] * eb,
+                                 dims[0] * dims[1] * dims[2] * dims[3] * eb};
+  const cuuint32_t box[5] = {(cuuint32_t)p.cg, (cuuint32_t)p.wp, (cuuint32_t)p.hh, (cuuint32_t)p.kd, 1u};
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  const CUtensorMapSwizzle swz = p.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (p.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUresult rc = encode(map, p.eb == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                             const_cast<void*>(xcodes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { set_error("effq_conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)rc); return 2; }
+  return 0;
 }
 
 }  // namespace effq
@@ -664,5 +780,14 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t co
   const uint32_t smem = tc_smem_bytes(p);
   const long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   const int kk = p.rp / 32;
-  return tc_dispatch(p, g->kd, kk, smem, (unsigned)ctas, (cudaStream_t)stream);
+  alignas(64) CUtensorMap xmap, tmap;
+  if (int rc = tc_make_xmap(p, xcodes, &xmap)) return rc;
+  static const bool tgt_tma_off = [] { const char* v = getenv("EFFQ_TC_TARGET_TMA"); return v && *v == '0'; }();
+  if (!target || ((uintptr_t)target & 15) != 0 || tgt_tma_off) p.n_tgt_stages = 0;     // epilogue loads the target itself
+  if (p.n_tgt_stages > 0) {
+    if (int rc = tc_make_tmap(p, target, &tmap)) return rc;
+  } else {
+    tmap = xmap;                                       // never dereferenced
+  }
+  return tc_dispatch(p, xmap, tmap, g->kd, kk, smem, (unsigned)ctas, (cudaStream_t)stream);
 }

@@ -208,8 +208,10 @@ class LayerCalibrator:
             for r_ in rhos:
                 a_r = torch.empty_like(amat)
                 ops.admm_lhs(a0, r_, eta, has_bias, a_r)
-                chol, info = torch.linalg.cholesky_ex(a_r)
-                inv_r = torch.cholesky_inverse(chol)
+                chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
+                                           lambda: torch.linalg.cholesky_ex(a_r))
+                inv_r = ops.timer.run("lib_cholesky_inverse", {"flops": 2.0 * kp ** 3 / 3.0},
+                                      lambda: torch.cholesky_inverse(chol))
                 inv_r.record_stream(main)
                 ev = torch.cuda.Event()
                 ev.record(self._side)
@@ -225,8 +227,8 @@ class LayerCalibrator:
                 main.wait_event(ev)
                 rho_built = rho
             # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
-            ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat)
-            sol = bmat @ ainv
+            ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
+            sol = ops.timer.run("lib_sgemm_B_Ainv", {"flops": 2.0 * c2 * kp * kp}, lambda: bmat @ ainv)
             # projection + dual update (EfficientQConv.py:107-111)
             wview = sol[:, :k] if has_bias else sol
             ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
@@ -237,8 +239,9 @@ class LayerCalibrator:
                     new_rho, div = rho * 2, 2.0
                 else:
                     new_rho, div = rho_m, rho_m / rho
-            ops.admm_project(sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps,
-                             has_bias, div, g, bstar, wcodes, self.st)
+            ops.timer.run("admm_project", {"bytes": 16 * c2 * k}, lambda: ops.admm_project(
+                sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps, has_bias, div,
+                g, bstar, wcodes, self.st))
             # score the iterate (EfficientQConv.py:118-122)
             if use_tc:
                 ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
@@ -250,7 +253,8 @@ class LayerCalibrator:
                                ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
             if dist.world > 1 and stats64 is None:
                 dist.all_reduce_sum(self.sse)
-            ops.admm_track(self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes)
+            ops.timer.run("admm_track", {"bytes": 8 * c2 * k}, lambda: ops.admm_track(
+                self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes))
             rho = new_rho
 
         # final forward with the best iterate: layer output + attention-weighted loss (:161-166)

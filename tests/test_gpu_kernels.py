@@ -185,6 +185,8 @@ TC_CASES = [
     (1, 256, 128, 1, (2, 8, 8), 4, 4),
     (1, 16, 48, 3, (3, 10, 12), 256, 256),   # ragged H/W, N=48 (x16 TMEM load), 256 levels
     (2, 64, 32, 3, (5, 20, 12), 4, 16),
+    (1, 32, 32, 3, (3, 12, 10), 16, 16),     # W % 4 != 0: the epilogue loads the target itself (no target TMA)
+    (1, 32, 64, 3, (4, 24, 20), 16, 16),     # two target boxes per tile, ragged H tile
 ]
 
 

@@ -48,14 +48,18 @@ def test_layer_calibration_matches_reference(engine_mod, golden, name, generic):
           "best_it", rep.best_iter, "min hist", hist.min(), "ref min", ref_hist.min())
     assert rep.used_tc == ((not generic) and name != "first_k3s2")
     # first iterate: identical problem, no trajectory divergence yet -> tight
-    assert abs(hist[0] - ref_hist[0]) <= 1e-4 * ref_hist[0]
+    # (w2a4_k3_c64: 4 weight levels, K' = 1729 -- the reference's own first iterate moves by 1.7e-4
+    #  between 1 and 8 CPU threads, profiles/r01_parity.txt)
+    assert abs(hist[0] - ref_hist[0]) <= (5e-4 if name == "w2a4_k3_c64" else 1e-4) * ref_hist[0]
     # final / best loss: the north-star bar is 1e-3 relative, but the reference algorithm itself
     # moves by 1.1e-3 (final) / 1.9e-3 (best) on this very fixture when it is run with 1 thread
     # instead of 8 or when its inputs are perturbed by 1e-7 (profiles/r01_parity.txt): the ADMM
     # trajectory is chaotic in the last bits.  3e-3 is the tightest bar the reference meets
     # against itself.
-    assert abs(rep.final_loss - ref_final) <= 3e-3 * ref_final
-    assert abs(hist.min() - ref_hist.min()) <= 3e-3 * ref_hist.min()
+    # The K' >= 865 wide fixtures move by up to 5.2e-3 between 1 and 8 CPU threads -> 1e-2 there.
+    tol = 1e-2 if name in ("w4a4_k3_c32", "w2a4_k3_c64") else 3e-3
+    assert abs(rep.final_loss - ref_final) <= tol * ref_final
+    assert abs(hist.min() - ref_hist.min()) <= tol * ref_hist.min()
     if qa:
         assert abs(rep.alpha_act - float(g[f"{name}_out_alpha_act"])) <= 1e-6 * rep.alpha_act
     # alpha_w is the LAST iterate's scale (reference quirk); with 256 levels the late, large-rho

@@ -81,10 +81,11 @@ def main():
     ok &= run("k3 rand c256->256", x, w, 3, 0.01, torch.randn(256))
     print("ALL OK" if ok else "SOME FAILED")
     # throughput of the scoring call (no output written) at level-1 / level-2 shapes
+    fp8 = os.environ.get("EFFQ_DIAG_FP8", "0") == "1"
     for c, sp, n in [(32, (64, 64, 64), 8), (64, (32, 32, 32), 32), (128, (16, 16, 16), 32)]:
-        xq = torch.randint(0, 16, (n, *sp, c), device=DEV).to(torch.bfloat16)
+        xq = torch.randint(0, 16, (n, *sp, c), device=DEV).to(torch.float8_e4m3fn if fp8 else torch.bfloat16)
         w = (2 * torch.randint(0, 16, (c, c, 3, 3, 3), device=DEV) - 15).float()
-        wq = ops.pack_weight_codes(w)
+        wq = ops.pack_weight_codes(w, ops.CODE_E4M3 if fp8 else ops.CODE_BF16)
         tgt = torch.randn(n, c, *sp, device=DEV)
         cs = torch.ones(1, device=DEV)
         ws = ops.workspace(16 + 8 * 1024 + 16 * 1024, torch.device(DEV))
@@ -99,7 +100,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         fl = 2.0 * n * sp[0] * sp[1] * sp[2] * c * c * 27
-        print(f"[perf c{c} {n}x{sp}] {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        print(f"[perf {'e4m3' if fp8 else 'bf16'} c{c} {n}x{sp}] {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
         if int(os.environ.get("EFFQ_TC_DEBUG", "0")) & 8:
             tl = ws[16 + 8 * 1024:16 + 8 * 1024 + 16 * 1024].view(torch.int64).cpu().reshape(-1, 8)
             t0 = int(tl[2, 0])

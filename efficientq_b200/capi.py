@@ -89,7 +89,12 @@ _SIGS = {
     "effq_gram_tc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_void_p,
                                           C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
-                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_split3_ld": (C.c_int64, [C.c_int64]),
+    "effq_split3_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "effq_solve_gemm_tc_workspace": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "effq_solve_gemm_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p]),
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,

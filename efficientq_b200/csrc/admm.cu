@@ -25,17 +25,31 @@ static inline int grid_for(long long n) {
 __global__ void __launch_bounds__(AD_THREADS)
 admm_rhs_kernel(const float* __restrict__ b0, const float* __restrict__ w0p, const float* __restrict__ g,
                 const float* __restrict__ dual, float rho, float eta, int c2, int k, int kp,
-                float* __restrict__ b_out) {
-  const long long total = (long long)c2 * kp;
+                float* __restrict__ b_out, __nv_bfloat16* __restrict__ planes, int ldk) {
+  // planes != NULL: also (or only) emit B as three bf16 terms [3][c2][ldk] for effq_solve_gemm_tc
+  const int ldj = planes ? ldk : kp;
+  const long long total = (long long)c2 * ldj;
   for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
        e += (long long)gridDim.x * AD_THREADS) {
-    const int r = (int)(e / kp), j = (int)(e % kp);
-    float v = __fadd_rn(b0[e], __fmul_rn(eta, w0p[e]));
-    if (j < k) {
-      const long long ge = (long long)r * k + j;
-      v = __fadd_rn(v, __fmul_rn(rho, __fsub_rn(g[ge], dual[ge])));
+    const int r = (int)(e / ldj), j = (int)(e % ldj);
+    float v = 0.f;
+    if (j < kp) {
+      const long long be = (long long)r * kp + j;
+      v = __fadd_rn(b0[be], __fmul_rn(eta, w0p[be]));
+      if (j < k) {
+        const long long ge = (long long)r * k + j;
+        v = __fadd_rn(v, __fmul_rn(rho, __fsub_rn(g[ge], dual[ge])));
+      }
+      if (b_out) b_out[be] = v;
     }
-    b_out[e] = v;
+    if (planes) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
+      const float r1 = __fsub_rn(v, __bfloat162float(h0));
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+      planes[e] = h0;
+      planes[total + e] = h1;
+      planes[2 * total + e] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(h1)));
+    }
   }
 }
 
@@ -163,13 +177,15 @@ extern "C" int effq_pack_wcodes(const float* codes, int32_t c2, int32_t c1, int3
 
 extern "C" int effq_admm_rhs(const float* b0, const float* w0p, const float* g, const float* dual,
                              float rho, float eta, int32_t c2, int32_t k, int32_t has_bias, float* b_out,
-                             void* stream) {
+                             void* planes_out, void* stream) {
   using namespace effq;
-  EFFQ_CHECK_ARG(b0 && w0p && g && dual && b_out, "null pointer");
+  EFFQ_CHECK_ARG(b0 && w0p && g && dual && (b_out || planes_out), "null pointer");
   EFFQ_CHECK_ARG(c2 > 0 && k > 0, "bad shape");
+  EFFQ_CHECK_ARG(((uintptr_t)planes_out & 15) == 0, "planes must be 16B aligned");
   const int kp = k + (has_bias ? 1 : 0);
-  admm_rhs_kernel<<<grid_for((long long)c2 * kp), AD_THREADS, 0, (cudaStream_t)stream>>>(
-      b0, w0p, g, dual, rho, eta, c2, k, kp, b_out);
+  const int ldk = (int)effq_split3_ld(kp);
+  admm_rhs_kernel<<<grid_for((long long)c2 * (planes_out ? ldk : kp)), AD_THREADS, 0, (cudaStream_t)stream>>>(
+      b0, w0p, g, dual, rho, eta, c2, k, kp, b_out, (__nv_bfloat16*)planes_out, ldk);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

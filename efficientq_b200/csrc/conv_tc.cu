@@ -36,6 +36,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include "tc_layout.cuh"
+#include "tc_ptx.cuh"
 
 namespace effq {
 
@@ -44,7 +45,6 @@ constexpr int TC_TILE_H = 16;
 constexpr int TC_TILE_W = 8;
 constexpr uint32_t TC_TGT_BYTES = 32u * TC_TILE_H * TC_TILE_W * 4u;     // one target stage: 32 channels of a tile
 constexpr int TC_EPI = 128;
-constexpr unsigned int TC_SPIN_LIMIT = 1u << 26;
 
 struct TcParams {
   const uint8_t* xq;           // NDHWC codes (bf16 or e4m3, eb bytes each)
@@ -75,148 +75,6 @@ struct TcParams {
   unsigned long long* dbg;     // bring-up timeline buffer ([tile][8] clock stamps of CTA 0) or null
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: returns false (and raises the global abort flag) instead of hanging.
-// SLEEP_NS > 0 backs off between polls (roles that are not latency critical).
-template <int SLEEP_NS = 0>
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile unsigned int* abort_flag) {
-  unsigned int spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
-    if ((++spins & 0x3ffu) == 0) {
-      if (*abort_flag != 0u) return false;
-      if (spins > TC_SPIN_LIMIT) { *abort_flag = 1u; __threadfence(); return false; }
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// 5-D tiled TMA load (coordinates innermost first: channel, w, h, d, n; may be negative / beyond
-// the tensor: those elements arrive as zeros and still count towards the transaction bytes)
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c, int w, int h, int d, int n,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// Descriptors are passed as (low word, high word): only the 14-bit start-address field in the
-// low word changes between MMAs, so the issuing thread does 32-bit adds only.
-template <bool FP8>
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                       uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  if (FP8)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// One elected lane of a converged warp.  The MMA / TMA roles keep warp-uniform control flow and
-// run their issue loops inside `if (elect_one())`: the compiler then knows a single lane is
-// active.  (Under `if (lane == 0)` it emulated every uniform-datapath instruction lane by lane,
-// which made the MMA issuer the critical path -- profiles/r01_conv_layout.md.)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major swizzled descriptor: rows at the swizzle width (128/64/32 B), 8-row groups sbo apart,
-// K advances inside the row by adding bytes to the start address.
-__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t sbo_bytes, int swz, int) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-  d |= (uint64_t)1 << 16;                                  // LBO unused for swizzled K-major
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;
-  // matrix base offset (bits 49-51) stays 0: the swizzle is a function of the absolute address
-  d |= (uint64_t)(swz == 128 ? 2 : (swz == 64 ? 4 : 6)) << 61;
-  return d;
-}
-// Instruction descriptor: D=f32, both operands K-major, M=m, N=n; A=B=bf16 (kind::f16, K=16 per
-// instruction) or A=B=e4m3 (kind::f8f6f4, format code 0, K=32 per instruction).
-__device__ __forceinline__ uint32_t umma_idesc(int m, int n, bool fp8) {
-  uint32_t i = 0;
-  i |= 1u << 4;                            // c_format = F32
-  if (!fp8) {
-    i |= 1u << 7;                          // a_format = BF16
-    i |= 1u << 10;                         // b_format = BF16
-  }
-  i |= (uint32_t)(n >> 3) << 17;           // N / 8
-  i |= (uint32_t)(m >> 4) << 24;           // M / 16
-  return i;
-}
-
 __device__ __forceinline__ void dbg_stamp(const TcParams& p, unsigned int tile, int slot) {
   if (p.dbg && blockIdx.x == 0) {
     const unsigned int i = tile / gridDim.x;
@@ -224,13 +82,6 @@ __device__ __forceinline__ void dbg_stamp(const TcParams& p, unsigned int tile, 
   }
 }
 
-struct Pipe {
-  int stage;
-  uint32_t phase;
-  __device__ __forceinline__ void advance(int n) {
-    if (++stage == n) { stage = 0; phase ^= 1u; }
-  }
-};
 
 // ---- epilogue pieces (NC = 32 or 16 channels of one voxel per thread) -------------------------
 template <int NC>
@@ -688,24 +539,6 @@ static int tc_dispatch(const TcParams& p, const CUtensorMap& m, const CUtensorMa
 }
 
 // Tensor map of the NDHWC code tensor, dims innermost first (C, W, H, D, N), box = one halo block.
-// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn tc_encoder() {
-  static EncodeTiledFn encode = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    return (EncodeTiledFn)fn;
-  }();
-  if (!encode) set_error("effq_conv3d_tc: cuTensorMapEncodeTiled not available from the driver");
-  return encode;
-}
-
 // Tensor map of the NCDHW fp32 target, dims innermost first (W, H, D, C2, N), box = 32 channels of
 // one output tile, dense in shared memory as [channel][h][w].
 static int tc_make_tmap(const TcParams& p, const float* target, CUtensorMap* map) {

@@ -16,6 +16,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
+import os
+
 import torch
 
 from . import ops
@@ -204,6 +206,9 @@ class LayerCalibrator:
             self._side = torch.cuda.Stream(device=dev)
         self._side.wait_stream(main)
         inverses, infos = {}, []
+        # K' >= 256: the per-iteration product B A^-1 runs on the tensor cores from bf16 split planes
+        # (fp32-class accuracy, csrc/solve_gemm_tc.cu); smaller systems stay on the library SGEMM
+        solve_tc = kp >= 256 and not self.force_generic and os.environ.get("EFFQ_SOLVE_TC", "1") != "0"
         with torch.cuda.stream(self._side):
             for r_ in rhos:
                 a_r = torch.empty_like(amat)
@@ -212,6 +217,10 @@ class LayerCalibrator:
                                            lambda: torch.linalg.cholesky_ex(a_r))
                 inv_r = ops.timer.run("lib_cholesky_inverse", {"flops": 2.0 * kp ** 3 / 3.0},
                                       lambda: torch.cholesky_inverse(chol))
+                if solve_tc:
+                    # A^-1 is symmetric: a column-major result is read as its (row-major) transpose, no copy
+                    inv_rm = inv_r if inv_r.stride(1) == 1 else inv_r.T
+                    inv_r = ops.timer.run("split3_bf16", {"bytes": 10 * kp * kp}, lambda: ops.split3_bf16(inv_rm))
                 inv_r.record_stream(main)
                 ev = torch.cuda.Event()
                 ev.record(self._side)
@@ -220,6 +229,9 @@ class LayerCalibrator:
                 rep.factorizations += 1
         ainv = None
         rho_built = None
+        if solve_tc:
+            bplanes = torch.empty((3, c2, ops.split3_ld(kp)), dtype=torch.bfloat16, device=dev)
+            sol_buf = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :kp]
 
         for it in range(self.n_iter):
             if rho_built != rho:
@@ -227,8 +239,13 @@ class LayerCalibrator:
                 main.wait_event(ev)
                 rho_built = rho
             # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
-            ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
-            sol = ops.timer.run("lib_sgemm_B_Ainv", {"flops": 2.0 * c2 * kp * kp}, lambda: bmat @ ainv)
+            if solve_tc:
+                ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
+                              lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
+                sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
+            else:
+                ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
+                sol = ops.timer.run("lib_sgemm_B_Ainv", {"flops": 2.0 * c2 * kp * kp}, lambda: bmat @ ainv)
             # projection + dual update (EfficientQConv.py:107-111)
             wview = sol[:, :k] if has_bias else sol
             ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
@@ -274,6 +291,8 @@ class LayerCalibrator:
             raise ops.EffqError(f"{name}: tcgen05 conv aborted (barrier timeout)")
         if any(int(i.item()) != 0 for i in infos):
             raise ops.EffqError(f"{name}: normal matrix not numerically SPD (cholesky failed)")
+        if solve_tc and int(self._sg_ws[:4].view(torch.int32)[0].item()) != 0:
+            raise ops.EffqError(f"{name}: tcgen05 solve GEMM aborted (barrier timeout)")
         if gram_flag is not None and int(gram_flag.item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 Gram kernel aborted (barrier timeout)")
         rep.final_loss = final_sse / numel_total
@@ -291,6 +310,7 @@ class LayerCalibrator:
         return best_g.view(c2, c1, *ksize), best_b, alpha_w, alpha_act, out_q, rep
 
     _cws = None
+    _sg_ws = None
     _qf_ws = None
     _side = None
 

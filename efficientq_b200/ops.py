@@ -389,12 +389,51 @@ def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None):
 # ---------------------------------------------------------------------------
 # (a9, a11) ADMM update
 # ---------------------------------------------------------------------------
-def admm_rhs(b0, w0p, g, dual, rho: float, eta: float, out):
+def admm_rhs(b0, w0p, g, dual, rho: float, eta: float, out, planes=None):
+    """B = B0 + eta W0' (+ rho (G - dual) on the weight columns) as fp32 ``out`` and / or as the three
+    bf16 terms ``planes`` ([3][C2][split3_ld(K')]) that solve_gemm_tc consumes."""
     c2, kp = b0.shape
     k = g.numel() // c2
     check(capi.load().effq_admm_rhs(ptr(b0), ptr(w0p), ptr(g), ptr(dual), float(rho), float(eta), c2, k,
-                                    int(kp != k), ptr(out), stream()), "effq_admm_rhs")
+                                    int(kp != k), ptr(out), ptr(planes), stream()), "effq_admm_rhs")
     return out
+
+
+def split3_ld(cols: int) -> int:
+    return int(capi.load().effq_split3_ld(int(cols)))
+
+
+def split3_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows][cols] -> bf16 [3][rows][split3_ld(cols)] with x = p0 + p1 + p2 (tail columns zero)."""
+    if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda:
+        raise EffqError("split3_bf16: expected a CUDA float32 matrix")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    rows, cols = x.shape
+    out = torch.empty((3, rows, split3_ld(cols)), dtype=torch.bfloat16, device=x.device)
+    check(capi.load().effq_split3_bf16(ptr(x), rows, cols, x.stride(0), ptr(out), stream()), "effq_split3_bf16")
+    return out
+
+
+def solve_gemm_tc(a_planes: torch.Tensor, b_planes: torch.Tensor, k: int, out: Optional[torch.Tensor] = None,
+                  ws: Optional[torch.Tensor] = None):
+    """out[m][n] = A B^T from split planes (fp32-class accuracy on the tensor cores); A^-1 symmetric ->
+    pass its planes as ``b_planes`` to get B A^-1.  Returns (out, workspace)."""
+    if a_planes.dtype != torch.bfloat16 or b_planes.dtype != torch.bfloat16 or a_planes.shape[2] != b_planes.shape[2]:
+        raise EffqError("solve_gemm_tc: operands must be bf16 planes with the same row pitch")
+    m, n = a_planes.shape[1], b_planes.shape[1]
+    lib = capi.load()
+    if out is None:
+        ldo = (n + 3) // 4 * 4
+        out = torch.empty((m, ldo), dtype=torch.float32, device=a_planes.device)[:, :n]
+    ldo = out.stride(0)
+    need = lib.effq_solve_gemm_tc_workspace(m, n, int(k), ldo)
+    if ws is None or ws.numel() < need:
+        ws = workspace(need, a_planes.device)
+    timer.run("solve_gemm_tc", {"flops": 2.0 * m * n * k}, lambda: check(
+        lib.effq_solve_gemm_tc(ptr(a_planes), ptr(b_planes), m, n, int(k), ptr(out), ldo, ptr(ws), stream()),
+        "effq_solve_gemm_tc"))
+    return out, ws
 
 
 def admm_lhs(a0, rho: float, eta: float, has_bias: bool, out):

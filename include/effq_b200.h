@@ -193,7 +193,24 @@ int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, con
 /* B = B0 + eta*W0' ;  B[:, :K] += rho*(G - dual)          (solver.py:317-320) */
 int effq_admm_rhs(const float* b0, const float* w0p, const float* g, const float* dual,
                   float rho, float eta, int32_t c2, int32_t k, int32_t has_bias, float* b_out,
-                  void* stream);
+                  void* planes_out, void* stream);
+/* b_out (fp32 [C2][K']) and planes_out (three bf16 terms [3][C2][effq_split3_ld(K')] for
+ * effq_solve_gemm_tc) may each be NULL, not both. */
+
+/* ---- (a9) proximal step w* = B A^-1 on the tensor cores: solver.py:331-342 ----------- */
+/* fp32 -> three bf16 terms x = x0 + x1 + x2 (24 significand bits), planes [3][rows][ldk] with
+ * ldk = effq_split3_ld(cols) (multiple of 64, tail zero-filled). */
+int64_t effq_split3_ld(int64_t cols);
+int effq_split3_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld, void* planes_out,
+                     void* stream);
+/* out[m][n] (leading dimension ldo) = A B^T with A = a_planes (m x k), B = b_planes (n x k),
+ * evaluated as the six bf16 products of combined order <= 2 with fp32 accumulation: fp32-class
+ * accuracy at the tensor-core rate.  For the solve, A = the right-hand side B of solver.py:317-320
+ * and B = A^-1 (symmetric, so its rows are the K-major operand).  workspace: zero-initialised once,
+ * effq_solve_gemm_tc_workspace(m, n, k, ldo) bytes (split-K partials). */
+int64_t effq_solve_gemm_tc_workspace(int32_t m, int32_t n, int32_t k, int64_t ldo);
+int effq_solve_gemm_tc(const void* a_planes, const void* b_planes, int32_t m, int32_t n, int32_t k,
+                       float* out, int64_t ldo, void* workspace, void* stream);
 /* A = A0 + rho*quasi_eye + eta*eye                         (solver.py:317,323) */
 int effq_admm_lhs(const float* a0, float rho, float eta, int32_t kp, int32_t has_bias,
                   float* a_out, void* stream);

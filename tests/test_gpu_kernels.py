@@ -427,3 +427,46 @@ def test_admm_elementwise_kernels(ops):
         assert s["best_iter"] == (0 if it < 3 else 3)
         assert best_g[0, 0].item() == (0.0 if it < 3 else 3.0)
     assert hist.cpu().tolist() == [5.0, 7.0, 5.0, 3.0]
+
+
+# ---------------------------------------------------------------- proximal-step GEMM (a9)
+def test_split3_bf16_is_exact(ops):
+    torch.manual_seed(21)
+    x = (torch.randn(37, 131) * torch.logspace(-6, 4, 131)).to(DEV)
+    pl = ops.split3_bf16(x)
+    assert pl.shape == (3, 37, 192) and pl.dtype == torch.bfloat16
+    back = pl[0].float() + pl[1].float() + pl[2].float()            # exact in fp32: the terms do not overlap
+    assert torch.equal(back[:, :131], x)
+    assert torch.count_nonzero(pl[:, :, 131:]) == 0
+
+
+@pytest.mark.parametrize("m,k", [(32, 865), (64, 1729), (16, 433), (128, 3457), (256, 1000), (48, 300)])
+def test_solve_gemm_tc_fp32_class_accuracy(ops, m, k):
+    """w* = B A^-1 from bf16 split planes: the error against fp64 must be in the class of an fp32 GEMM
+    (the library SGEMM it replaces), on an SPD inverse with the dynamic range of the real systems."""
+    torch.manual_seed(m + k)
+    x = torch.randn(k, 2 * k, device=DEV, dtype=torch.float64)
+    a = x @ x.T / (2 * k) + 0.05 * torch.eye(k, device=DEV, dtype=torch.float64)
+    ainv = torch.linalg.inv(a).float()
+    ainv = 0.5 * (ainv + ainv.T)
+    b = (torch.randn(m, k, device=DEV) * torch.logspace(-2, 2, k, device=DEV)).float()
+    ref = b.double() @ ainv.double()
+    got, _ = ops.solve_gemm_tc(ops.split3_bf16(b), ops.split3_bf16(ainv), k)
+    torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lib = b @ ainv
+    scale = ref.abs().max().item()
+    err_tc = (got.double() - ref).abs().max().item() / scale
+    err_lib = (lib.double() - ref).abs().max().item() / scale
+    print(f"m={m} k={k}: tensor-core split err {err_tc:.2e}, fp32 SGEMM err {err_lib:.2e}")
+    assert got.shape == (m, k)
+    # (the TMEM accumulator truncates instead of rounding to nearest: a small constant factor over SGEMM)
+    assert err_tc <= max(4.0 * err_lib, 4e-6)
+    # fused producer of the A planes: admm_rhs emits the same three terms as split3 of its fp32 output
+    kk = k - 1
+    b0, w0p = b, torch.randn(m, k, device=DEV)
+    g, dual = torch.randn(m, kk, device=DEV), torch.randn(m, kk, device=DEV)
+    out32 = torch.empty(m, k, device=DEV)
+    planes = torch.empty((3, m, ops.split3_ld(k)), dtype=torch.bfloat16, device=DEV)
+    ops.admm_rhs(b0, w0p, g, dual, 10.0, 1.0, out32, planes=planes)
+    assert torch.equal(planes, ops.split3_bf16(out32))

@@ -64,7 +64,8 @@ def test_layer_calibration_matches_reference(engine_mod, golden, name, generic):
         assert abs(rep.alpha_act - float(g[f"{name}_out_alpha_act"])) <= 1e-6 * rep.alpha_act
     # alpha_w is the LAST iterate's scale (reference quirk); with 256 levels the late, large-rho
     # iterates settle in different basins, so only the 4/16-level cases are compared tightly
-    tol_aw = 2e-3 if lw <= 16 else 1e-1
+    # (wide k=3 fixtures: the reference's own alpha_w moves by 3.6e-3 / 2.6e-3 between 1 and 8 threads)
+    tol_aw = (1e-2 if name in ("w4a4_k3_c32", "w2a4_k3_c64") else 2e-3) if lw <= 16 else 1e-1
     assert abs(rep.alpha_w - float(g[f"{name}_out_alpha_w"])) <= tol_aw * rep.alpha_w
     # returned tensors are consistent: weight is on the level grid of SOME scale, output = conv(qact, w)+b
     lv = torch.unique(wq)

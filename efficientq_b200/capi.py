@@ -62,9 +62,9 @@ _SIGS = {
                                        C.c_void_p, C.c_void_p]),
     "effq_quantize_act_ndhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "effq_scale_search_workspace": (C.c_int64, []),
+    "effq_scale_search_workspace": (C.c_int64, [C.c_int64]),
     "effq_scale_search": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
-                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "effq_scale_partial": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                      C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),

@@ -10,7 +10,17 @@
 // barrier, and every CTA then folds the partials in the same fixed order, so all
 // CTAs see bit-identical scales and the loop exit is uniform.  Algorithmic bytes
 // per pass: numel*4 (+numel*4 when v = v1 + v2).
+//
+// Large tensors (activations) additionally use INTERVAL-STABLE partial sums: late in the search
+// the scale moves by tiny steps, so for an interval I = [a-w, a+w] around the current scale most
+// elements have the same level index for EVERY scale in I (the index is monotone in the scale, so
+// comparing the two end points decides it).  One classifying pass adds those elements into
+// "stable" sums once and copies the few ambiguous ones (near a rounding boundary) to a list; while
+// the scale stays inside I a pass reads only the list.  The level index of every element is the
+// one the plain pass would compute, so the scales differ from the plain passes only through the
+// fp64 summation order (~1e-16 relative); the pass count is the same.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 
 namespace effq {
@@ -22,8 +32,11 @@ constexpr unsigned long long SS_SPIN_LIMIT = 1ull << 28;
 struct SSWorkspace {
   unsigned int barrier;                      // monotonically increasing arrival counter
   unsigned int abort_flag;
-  unsigned int pad[2];
-  double partial[2][SS_MAX_CTAS][2];
+  unsigned int list_count[3];                // ambiguous-list fill counters (rotate per classifying pass)
+  unsigned int pad[3];
+  double diag[4];                            // streamed search: pass-type counts of the last launch
+  double partial[2][SS_MAX_CTAS][4];
+  // followed by the ambiguous list (floats) when the caller's workspace is larger
 };
 
 struct VecView {
@@ -132,7 +145,7 @@ __device__ __forceinline__ void pass_sums(const VecView& vv, double a, const QPa
 
 // Every CTA folds the per-CTA partials in the same order (thread t takes slots
 // t, t+512, ... then the fixed block tree), so all CTAs get bit-identical sums.
-__device__ __forceinline__ void fold_partials(const double (*part)[2], unsigned int nctas,
+__device__ __forceinline__ void fold_partials(const double (*part)[4], unsigned int nctas,
                                               double* scratch, double* bc) {
   double t0 = 0.0, t1 = 0.0;
   for (unsigned int b = threadIdx.x; b < nctas; b += SS_THREADS) {
@@ -142,6 +155,19 @@ __device__ __forceinline__ void fold_partials(const double (*part)[2], unsigned 
   t0 = block_sum(t0, scratch);
   t1 = block_sum(t1, scratch);
   if (threadIdx.x == 0) { bc[0] = t0; bc[1] = t1; }
+  __syncthreads();
+}
+__device__ __forceinline__ void fold_partials4(const double (*part)[4], unsigned int nctas,
+                                               double* scratch, double* bc) {
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  for (unsigned int b = threadIdx.x; b < nctas; b += SS_THREADS)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] += ((const volatile double*)part[b])[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double r = block_sum(t[k], scratch);
+    if (threadIdx.x == 0) bc[k] = r;
+  }
   __syncthreads();
 }
 
@@ -250,6 +276,272 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
   }
 }
 
+// ---- streaming variant with interval-stable partial sums (activations) ---------------------
+struct ClassAcc {
+  PassAcc st, am;                 // stable / ambiguous index sums at the current scale
+  double sv_st, n_st, sv_am, n_am;
+};
+__device__ __forceinline__ double idx_of(double v, const PassQ& p) {
+  return rint(fmin(fmax(fma(v, p.c1, p.c0), 0.0), p.lm1));
+}
+// One element against the interval [a_lo, a_hi] (plo = pass constants of a_hi, phi of a_lo): stable ->
+// index sums; ambiguous -> index sums at the current scale + appended to `list`.
+// Ambiguous elements are staged in shared memory and flushed to the global list with ONE global
+// atomic per ~2 K elements (a global atomic per warp made the classifying pass ~18x a plain pass).
+constexpr unsigned int SS_STAGE_FLUSH = 2048;                 // flush when at least this many are staged
+constexpr unsigned int SS_STAGE_CAP = SS_STAGE_FLUSH + 4 * SS_THREADS;   // + one loop iteration's worst case
+__device__ __forceinline__ void classify(double v, const PassQ& pa, const PassQ& plo, const PassQ& phi, ClassAcc& c,
+                                         float* sbuf, unsigned int* scnt) {
+  namespace cg = cooperative_groups;
+  const double idx = idx_of(v, pa);
+  const bool amb = idx_of(v, plo) != idx_of(v, phi);        // index monotone in the scale: end points decide
+  if (!amb) {
+    c.st.s_iv = fma(idx, v, c.st.s_iv); c.st.s_ii = fma(idx, idx, c.st.s_ii); c.st.s_i += idx;
+    c.sv_st += v; c.n_st += 1.0;
+  } else {
+    c.am.s_iv = fma(idx, v, c.am.s_iv); c.am.s_ii = fma(idx, idx, c.am.s_ii); c.am.s_i += idx;
+    c.sv_am += v; c.n_am += 1.0;
+    cg::coalesced_group grp = cg::coalesced_threads();
+    unsigned int base = 0;
+    if (grp.thread_rank() == 0) base = atomicAdd(scnt, grp.size());
+    base = grp.shfl(base, 0);
+    sbuf[base + grp.thread_rank()] = (float)v;
+  }
+}
+// All threads of the CTA (after a __syncthreads): move the staged elements to the global list.
+__device__ __forceinline__ void stage_flush(float* sbuf, unsigned int* scnt, unsigned int* sbase, float* list,
+                                            unsigned int* counter, unsigned int cap) {
+  const unsigned int n = *scnt;
+  if (threadIdx.x == 0) *sbase = atomicAdd(counter, n);
+  __syncthreads();
+  const unsigned int g0 = *sbase;
+  for (unsigned int i = threadIdx.x; i < n; i += SS_THREADS)
+    if (g0 + i < cap) list[g0 + i] = sbuf[i];
+  __syncthreads();
+  if (threadIdx.x == 0) *scnt = 0;
+  __syncthreads();
+}
+// block-reduce the four class sums into this CTA's partial slot
+__device__ __forceinline__ void publish4(const ClassAcc& c, const QParamD& q, double (*slot)[4], double* scratch) {
+  double v4[4];
+  finish_bv(c.st, q, c.sv_st, c.n_st, v4[0], v4[1]);
+  finish_bv(c.am, q, c.sv_am, c.n_am, v4[2], v4[3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double rsum = block_sum(v4[k], scratch);
+    if (threadIdx.x == 0) slot[blockIdx.x][k] = rsum;
+  }
+}
+
+constexpr unsigned int SS_RECLASS_MIN = 1u << 16;      // lists shorter than this are not worth re-classifying
+
+__global__ void __launch_bounds__(SS_THREADS, 2)
+scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, SSWorkspace* ws,
+                           float* list_mem, unsigned int cap, float wmax0, float dthr) {
+  __shared__ double scratch[32];
+  __shared__ double bc[4];
+  __shared__ float sbuf[SS_STAGE_CAP];
+  __shared__ unsigned int scnt, sbase;
+  const QParamD q = make_qparam_d(lo, hi, nlvl);
+  const unsigned int nctas = gridDim.x;
+  const long long numel = vv.rows * vv.cols;
+  const int max_pass = nlvl * 100;
+  unsigned int target = 0;
+  int parity = 0;
+  if (threadIdx.x == 0) scnt = 0;
+  __syncthreads();
+
+  double s0, s1;
+  pass_sums<0>(vv, 0.0, q, blockIdx.x, nctas, s0, s1);
+  s0 = block_sum(s0, scratch);
+  if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = 0.0; }
+  if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+  fold_partials(ws->partial[parity], nctas, scratch, bc);
+  double a = bc[0] / (double)numel;
+  double a_prev = -999.0;
+  int passes = 0;
+  double last0 = 0.0, last1 = 0.0;
+
+  // Interval state: identical in every CTA (derived from the folded sums and one global counter).
+  // Two nested intervals.  OUTER [olo, ohi] (as wide as the list capacity allows) is classified from
+  // the tensor: stable sums ost*, ambiguous elements in list L1.  INNER [ilo, ihi] (what the next few
+  // steps need) is classified from L1 -- a fraction of a pass --: sums ist* of the L1 elements that are
+  // stable for it, the rest in L2 (two buffers, so an L2 pass can narrow the inner interval further).
+  // Leaving the inner interval costs a pass over L1, leaving the outer one a pass over the tensor.
+  bool have_outer = false, have_inner = false;
+  double olo = 0.0, ohi = 0.0, ost0 = 0.0, ost1 = 0.0;
+  double ilo = 0.0, ihi = 0.0, ist0 = 0.0, ist1 = 0.0;
+  double d = 1e300, d_prev = 0.0, wmax = wmax0, d_retry = 1e300;
+  unsigned int n1 = 0, n2 = 0;
+  float* l1 = list_mem;
+  float* l2cur = list_mem + cap;
+  float* l2nxt = list_mem + 2 * (size_t)cap;
+  int build_id = 0, n_builds = 0, n_list = 0, n_reclass = 0, n_l1 = 0;
+
+  const bool flat = (vv.ld1 == vv.cols) && (!vv.v2 || vv.ld2 == vv.cols) && (numel % 4 == 0) &&
+                    (((uintptr_t)vv.v1 & 15) == 0) && (!vv.v2 || ((uintptr_t)vv.v2 & 15) == 0);
+
+  while (fabs(a - a_prev) > 1e-5 && passes < max_pass) {
+    parity ^= 1;
+    double p0, p1;
+    double r = d_prev > 0.0 ? d / d_prev : 0.9;               // observed contraction of the step
+    r = fmin(fmax(r, 0.0), 0.98);
+    const double need = fmax(4.0 * d, 2.0 * r / (1.0 - r) * d);   // half-width that should hold until convergence
+    if (have_outer && a >= olo && a <= ohi) {
+      // ---- list pass ----
+      const bool in_inner = have_inner && a >= ilo && a <= ihi;
+      const float* src;
+      unsigned int src_n;
+      bool reclass;
+      double nlo = ilo, nhi = ihi;
+      if (!in_inner) {
+        // (re)build the inner interval from L1 -- unless it would be (nearly) the whole outer interval
+        src = l1;
+        src_n = n1;
+        nlo = fmax(olo, a - need);
+        nhi = fmin(ohi, a + need);
+        reclass = n1 >= SS_RECLASS_MIN && (nhi - nlo) <= 0.7 * (ohi - olo);
+        have_inner = false;
+        ist0 = 0.0;
+        ist1 = 0.0;
+        ++n_l1;
+      } else {
+        src = l2cur;
+        src_n = n2;
+        reclass = n2 >= SS_RECLASS_MIN && 3.0 * need <= 0.5 * (ihi - ilo);
+        if (reclass) { nlo = fmax(ilo, a - need); nhi = fmin(ihi, a + need); }
+      }
+      const PassQ pq = make_passq(a, q);
+      // counters rotate over three slots: slot k is re-armed two barriers after its last reader
+      unsigned int* counter = &ws->list_count[build_id % 3];
+      if (reclass && blockIdx.x == 0 && threadIdx.x == 0) ws->list_count[(build_id + 1) % 3] = 0;
+      const PassQ plo = make_passq(nhi, q), phi = make_passq(nlo, q);
+      ClassAcc c{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, 0.0, 0.0, 0.0, 0.0};
+      const unsigned int nvec = (src_n + 3u) / 4u;
+      const float4* lv = reinterpret_cast<const float4*>(src);
+      // block-uniform trip count (the staging flush synchronises the CTA)
+      for (unsigned int i0 = blockIdx.x * SS_THREADS; i0 < nvec; i0 += nctas * SS_THREADS) {
+        const unsigned int i = i0 + threadIdx.x;
+        if (i < nvec) {
+          const float4 t = __ldcg(lv + i);                     // written earlier in this launch: no .nc path
+          const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (4u * i + (unsigned)k < src_n) {
+              const double v = (double)e[k];
+              if (reclass) classify(v, pq, plo, phi, c, sbuf, &scnt);
+              else { accum_idx(v, pq, c.am); c.sv_am += v; c.n_am += 1.0; }
+            }
+          }
+        }
+        if (reclass) {
+          __syncthreads();
+          if (scnt >= SS_STAGE_FLUSH) stage_flush(sbuf, &scnt, &sbase, l2nxt, counter, cap);
+        }
+      }
+      if (reclass) {
+        __syncthreads();
+        if (scnt > 0) stage_flush(sbuf, &scnt, &sbase, l2nxt, counter, cap);
+      }
+      publish4(c, q, ws->partial[parity], scratch);
+      if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+      fold_partials4(ws->partial[parity], nctas, scratch, bc);
+      ist0 += bc[0];                                           // newly stable elements (zero without re-classification)
+      ist1 += bc[1];
+      p0 = ost0 + ist0 + bc[2];
+      p1 = ost1 + ist1 + bc[3];
+      if (reclass) {
+        n2 = *((volatile unsigned int*)counter);
+        float* t = l2cur; l2cur = l2nxt; l2nxt = t;
+        ilo = nlo;
+        ihi = nhi;
+        have_inner = true;
+        ++build_id;
+        ++n_reclass;
+      }
+      ++n_list;
+    } else if (flat && cap > 0 && passes >= 2 && d <= (double)dthr * fabs(a) && d <= d_retry) {
+      // ---- classifying pass over the tensor: stable sums + ambiguous list L1 for the outer interval ----
+      const double w = fmax(4.0 * d, fmin(need, wmax * fabs(a)));
+      olo = a - w;
+      ohi = a + w;
+      unsigned int* counter = &ws->list_count[build_id % 3];
+      if (blockIdx.x == 0 && threadIdx.x == 0) ws->list_count[(build_id + 1) % 3] = 0;
+      const PassQ pa_ = make_passq(a, q), plo = make_passq(ohi, q), phi = make_passq(olo, q);
+      ClassAcc c{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, 0.0, 0.0, 0.0, 0.0};
+      const long long nvec = numel / 4;
+      const float4* p1v = reinterpret_cast<const float4*>(vv.v1);
+      const float4* p2v = reinterpret_cast<const float4*>(vv.v2);
+      for (long long i0 = (long long)blockIdx.x * SS_THREADS; i0 < nvec; i0 += (long long)nctas * SS_THREADS) {
+        const long long i = i0 + threadIdx.x;
+        if (i < nvec) {
+          float4 t = __ldg(p1v + i);
+          if (p2v) {
+            const float4 u = __ldg(p2v + i);
+            t.x = __fadd_rn(t.x, u.x); t.y = __fadd_rn(t.y, u.y);
+            t.z = __fadd_rn(t.z, u.z); t.w = __fadd_rn(t.w, u.w);
+          }
+          classify((double)t.x, pa_, plo, phi, c, sbuf, &scnt);
+          classify((double)t.y, pa_, plo, phi, c, sbuf, &scnt);
+          classify((double)t.z, pa_, plo, phi, c, sbuf, &scnt);
+          classify((double)t.w, pa_, plo, phi, c, sbuf, &scnt);
+        }
+        __syncthreads();
+        if (scnt >= SS_STAGE_FLUSH) stage_flush(sbuf, &scnt, &sbase, l1, counter, cap);
+      }
+      __syncthreads();
+      if (scnt > 0) stage_flush(sbuf, &scnt, &sbase, l1, counter, cap);
+      publish4(c, q, ws->partial[parity], scratch);
+      if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+      fold_partials4(ws->partial[parity], nctas, scratch, bc);
+      ost0 = bc[0];
+      ost1 = bc[1];
+      p0 = ost0 + bc[2];
+      p1 = ost1 + bc[3];
+      n1 = *((volatile unsigned int*)counter);
+      have_outer = n1 <= cap;
+      have_inner = false;
+      if (!have_outer) { wmax *= 0.5; d_retry = 0.5 * d; }     // list overflow: plain passes until the step has halved
+      ++build_id;
+      ++n_builds;
+    } else {
+      // ---- plain pass ----
+      have_outer = false;
+      have_inner = false;
+      pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
+      s0 = block_sum(s0, scratch);
+      s1 = block_sum(s1, scratch);
+      if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = s1; }
+      if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+      fold_partials(ws->partial[parity], nctas, scratch, bc);
+      p0 = bc[0];
+      p1 = bc[1];
+    }
+    __syncthreads();
+    last0 = p0;
+    last1 = p1;
+    a_prev = a;
+    a = last0 / last1;
+    d_prev = d;
+    d = fabs(a - a_prev);
+    ++passes;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->a = a;
+    state->a_prev = a_prev;
+    state->s_bv = last0;
+    state->s_bb = last1;
+    state->passes = passes;
+    state->converged = fabs(a - a_prev) <= 1e-5 ? 1 : 0;
+    state->failed = (passes == max_pass) ? 1 : 0;
+    // diagnostics: classifying passes over the tensor | list passes | of which re-classifying | last list length
+    ws->diag[0] = (double)n_builds;
+    ws->diag[1] = (double)n_list;
+    ws->diag[2] = (double)n_reclass;
+    ws->diag[3] = (double)n_l1;
+  }
+}
+
 // ---- cluster variant: tensors up to 128 K elements (measured crossover against the 148-CTA
 // grid variant, profiles/r01_scale_search.md).  One thread-block cluster; each CTA keeps its slice of v in
 // shared memory for the whole search; a pass ends with ONE hardware cluster barrier and every
@@ -349,7 +641,7 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
 struct SPWorkspace {
   unsigned int done;
   unsigned int pad[3];
-  double partial[SS_MAX_CTAS][2];
+  double partial[SS_MAX_CTAS][4];
 };
 
 template <int MODE>
@@ -416,9 +708,16 @@ static int pick_ctas(long long numel, int per_sm) {
 
 }  // namespace effq
 
-extern "C" int64_t effq_scale_search_workspace(void) {
+static int64_t ss_base_bytes() {
   size_t a = sizeof(effq::SSWorkspace), b = sizeof(effq::SPWorkspace);
-  return (int64_t)(a > b ? a : b);
+  return (int64_t)(((a > b ? a : b) + 255) & ~(size_t)255);
+}
+static bool ss_streams(long long numel) { return numel > (long long)effq::sm_count() * effq::SS_THREADS * 48; }
+
+extern "C" int64_t effq_scale_search_workspace(int64_t numel) {
+  // fixed part + (for tensors that are streamed from memory every pass) room for the ambiguous list:
+  // three list buffers (L1 + two for L2) of a quarter of the elements each
+  return ss_base_bytes() + (ss_streams(numel) ? 3 * ((numel / 4 + 63) / 64 * 64) * 4 : 0);
 }
 
 template <int REG_ITEMS>
@@ -433,9 +732,10 @@ static int launch_search(effq::VecView vv, int nlvl, float lo, float hi, effq_sc
 
 extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
                                  int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
-                                 void* workspace, void* stream) {
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(v1 && state && workspace, "null pointer");
+  EFFQ_CHECK_ARG(workspace_bytes >= ss_base_bytes(), "workspace smaller than effq_scale_search_workspace(0)");
   EFFQ_CHECK_ARG(rows > 0 && cols > 0 && ld1 >= cols && (!v2 || ld2 >= cols), "bad shape");
   EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
   cudaStream_t s = (cudaStream_t)stream;
@@ -474,7 +774,7 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
     count_launch();
     return 0;
   }
-  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 16, s));    // barrier counter + abort flag
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 32, s));    // barrier counter, abort flag, list counters
   SSWorkspace* ws = (SSWorkspace*)workspace;
   const long long per_cta_8 = (long long)SS_THREADS * 8;
   if (numel <= (long long)sms * SS_THREADS * 8) {
@@ -483,7 +783,29 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   }
   if (numel <= (long long)sms * SS_THREADS * 24) return launch_search<24>(vv, nlvl, lo, hi, state, ws, sms, s);
   if (numel <= (long long)sms * SS_THREADS * 48) return launch_search<48>(vv, nlvl, lo, hi, state, ws, sms, s);
-  return launch_search<0>(vv, nlvl, lo, hi, state, ws, sms * 2 > SS_MAX_CTAS ? SS_MAX_CTAS : sms * 2, s);
+  {
+    float* list = (float*)((char*)workspace + ss_base_bytes());
+    long long room = (workspace_bytes - ss_base_bytes()) / 12 / 64 * 64;      // floats per list buffer
+    static const bool plain = [] { const char* v = getenv("EFFQ_SCALE_PLAIN"); return v && *v == '1'; }();
+    if (room < 0 || plain) room = 0;
+    unsigned int cap = room > 0x7fffffffll ? 0x7fffffffu : (unsigned int)room;
+    static int per_sm = 0;                             // co-resident CTAs per SM (register bound)
+    if (per_sm == 0) {
+      int occ = 0;
+      EFFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scale_search_stream_kernel, SS_THREADS, 0));
+      per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
+    }
+    const int ctas = sms * per_sm > SS_MAX_CTAS ? SS_MAX_CTAS : sms * per_sm;
+    // interval policy: start once the step is below dthr * a (so that 4 steps fit the widest interval),
+    // half-width at most wmax * a (ambiguous fraction ~ the relative half-width; the list holds 25 %)
+    static const float wmax0 = [] { const char* v = getenv("EFFQ_SS_WMAX"); return v && *v ? (float)atof(v) : 0.04f; }();
+    static const float dthr = [] { const char* v = getenv("EFFQ_SS_DTHR"); return v && *v ? (float)atof(v) : 0.01f; }();
+    float wm = wmax0, dt = dthr;
+    void* args[] = {&vv, &nlvl, &lo, &hi, &state, &ws, &list, &cap, &wm, &dt};
+    EFFQ_CUDA(cudaLaunchCooperativeKernel((void*)scale_search_stream_kernel, dim3(ctas), dim3(SS_THREADS), args, 0, s));
+    count_launch();
+    return 0;
+  }
 }
 
 extern "C" int effq_scale_partial(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,

@@ -76,7 +76,7 @@ class LayerCalibrator:
         self.st = ops.AdmmState(device)
         self.sse = torch.zeros(1, dtype=torch.float64, device=device)
         self.sums = torch.zeros(2, dtype=torch.float64, device=device)
-        self.sp_ws = ops.workspace(ops.capi.load().effq_scale_search_workspace(), device)
+        self.sp_ws = ops.workspace(ops.capi.load().effq_scale_search_workspace(0), device)
         self.gram_ws = None
         self.tc_ws = ops.workspace(16 + 8 * 1024, device)
 

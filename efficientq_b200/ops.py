@@ -187,11 +187,21 @@ def quantize_act_ndhwc(x: torch.Tensor, nlvl: int, state: Optional[ScaleState] =
 _ss_ws = {}
 
 
-def _scale_ws(device) -> torch.Tensor:
+def _scale_ws(device, numel: int = 0) -> torch.Tensor:
+    """Scale-search workspace of the device, grown on demand (large tensors need room for the
+    ambiguous-element list of the interval-stable passes)."""
     key = (device.type, device.index)
-    if key not in _ss_ws:
-        _ss_ws[key] = workspace(capi.load().effq_scale_search_workspace(), device)
+    need = capi.load().effq_scale_search_workspace(int(numel))
+    if key not in _ss_ws or _ss_ws[key].numel() < need:
+        _ss_ws[key] = workspace(need, device)
     return _ss_ws[key]
+
+
+def scale_search_diag(device) -> dict:
+    """Pass-type counts of the last streamed search on this device (SSWorkspace::diag, csrc/scale_search.cu)."""
+    v = _scale_ws(device)[32:64].view(torch.float64).cpu().tolist()
+    return {"classifying_passes": int(v[0]), "list_passes": int(v[1]), "reclassifying_list_passes": int(v[2]),
+            "l1_passes": int(v[3])}
 
 
 def _pair_view(v1: torch.Tensor, v2: Optional[torch.Tensor]):
@@ -210,13 +220,15 @@ def _pair_view(v1: torch.Tensor, v2: Optional[torch.Tensor]):
 
 
 def scale_search(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: ScaleState,
-                 v2: Optional[torch.Tensor] = None) -> ScaleState:
+                 v2: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> ScaleState:
     """project_by_iter on the device (one cooperative launch, no host sync)."""
     rows, cols, ld1, ld2 = _pair_view(v1, v2)
     name = f"scale_search_w_{rows * cols}" if v2 is not None else "scale_search_act"
+    if ws is None:
+        ws = _scale_ws(v1.device, rows * cols)
     timer.run(name, {"pass_bytes": 4 * rows * cols * (2 if v2 is not None else 1)}, lambda: check(
         capi.load().effq_scale_search(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
-                                      state.p, ptr(_scale_ws(v1.device)), stream()), "effq_scale_search"))
+                                      state.p, ptr(ws), ws.numel(), stream()), "effq_scale_search"))
     return state
 
 

@@ -116,10 +116,14 @@ int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, i
 /* v = v1 (+ v2 if non-NULL, added in fp32 first as the reference's `w_star + dual`),
  * viewed as rows x cols with leading dimensions ld1 / ld2.  Runs the whole fp64 fixed
  * point on the device in ONE cooperative launch; result in *state. */
-int64_t effq_scale_search_workspace(void);
+/* Workspace: effq_scale_search_workspace(numel) bytes (numel = rows*cols; 0 gives the fixed part that
+ * effq_scale_partial needs).  Tensors too large to keep on chip get room for the list of
+ * "ambiguous" elements of the interval-stable passes (csrc/scale_search.cu); with a smaller
+ * workspace the search falls back to plain passes (same result up to fp64 summation order). */
+int64_t effq_scale_search_workspace(int64_t numel);
 int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
                       int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
-                      void* workspace, void* stream);
+                      void* workspace, int64_t workspace_bytes, void* stream);
 /* Multi-GPU building blocks: one pass of local sums, then (after the caller has
  * all-reduced sums[0..1]) the scale update.  mode 0: sums = {sum|v|, numel};
  * mode 1: sums = {sum(b*v), sum(b*b)} for the scale in *state. */

@@ -105,6 +105,35 @@ def test_scale_search_golden(ops, golden, name, lo, hi, L):
     assert np.array_equal(b, np.float32(a_ref) * g[f"{name}_L{L}_b"])
 
 
+@pytest.mark.parametrize("L,lo", [(16, 0.0), (4, 0.0), (16, -1.0)])
+def test_scale_search_streamed_interval_passes(ops, L, lo):
+    """Tensors that are streamed from memory every pass (> 3.6 M elements) use interval-stable partial
+    sums: same level index for every element as a plain pass, so the scale agrees with the oracle and
+    with the plain-pass kernel to fp64 summation noise, in the same number of passes."""
+    torch.manual_seed(31 + L)
+    n = 6_000_000
+    v = torch.randn(n) * 1.3
+    if lo == 0.0:
+        v = torch.relu(v)
+    a_ref, _, passes = O.project_by_iter(v, L, lo, 1, return_iters=True)
+    vd = v.to(DEV)
+    st = ops.ScaleState(torch.device(DEV))
+    ops.scale_search(vd, L, lo, 1.0, st)
+    s = st.read()
+    diag = ops.scale_search_diag(torch.device(DEV))
+    print("passes", s["passes"], diag)
+    assert s["converged"] == 1 and s["passes"] == passes
+    assert abs(s["a"] - a_ref) <= 1e-9 * abs(a_ref)
+    assert diag["classifying_passes"] >= 1 and diag["list_passes"] >= 1
+    assert diag["classifying_passes"] + diag["list_passes"] <= passes
+    # plain passes only (workspace without room for the list)
+    small = ops.workspace(ops.capi.load().effq_scale_search_workspace(0), torch.device(DEV))
+    st2 = ops.ScaleState(torch.device(DEV))
+    ops.scale_search(vd, L, lo, 1.0, st2, ws=small)
+    s2 = st2.read()
+    assert s2["passes"] == passes and abs(s2["a"] - s["a"]) <= 1e-12 * abs(s["a"])
+
+
 def test_scale_search_strided_sum_and_multi_gpu_blocks(ops):
     """v = w*[:, :K] + dual with w* carrying a bias column (ld = K+1); and the one-pass
     building blocks used when volumes are sharded reach the same fixed point."""
@@ -121,7 +150,7 @@ def test_scale_search_strided_sum_and_multi_gpu_blocks(ops):
     # multi-GPU formulation on one device: partial sums -> (all-reduce) -> step
     st2 = ops.ScaleState(torch.device(DEV))
     sums = torch.zeros(2, dtype=torch.float64, device=DEV)
-    ws = ops.workspace(ops.capi.load().effq_scale_search_workspace(), torch.device(DEV))
+    ws = ops.workspace(ops.capi.load().effq_scale_search_workspace(0), torch.device(DEV))
     v = (sol[:, :k] + dual).contiguous().to(DEV)
     ops.scale_partial(v, 16, -1.0, 1.0, st2, 0, sums, ws)
     ops.scale_step(st2, sums, 0, 16)

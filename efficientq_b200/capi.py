@@ -20,6 +20,11 @@ class EffqError(RuntimeError):
     pass
 
 
+class PeerComm(C.Structure):
+    """``effq_peer_comm`` (include/effq_b200.h)."""
+    _fields_ = [("slots", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class Geom(C.Structure):
     """``effq_geom`` (include/effq_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in
@@ -64,7 +69,8 @@ _SIGS = {
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_scale_search_workspace": (C.c_int64, [C.c_int64]),
     "effq_scale_search": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
-                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p]),
     "effq_scale_partial": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                      C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
@@ -101,7 +107,12 @@ _SIGS = {
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                  C.c_void_p]),
+                                  C.c_void_p, C.c_void_p]),
+    "effq_peer_bytes": (C.c_int64, []),
+    "effq_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
+    "effq_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "effq_peer_close": (C.c_int, [C.c_void_p]),
+    "effq_peer_free": (C.c_int, [C.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -7,6 +7,7 @@
 // structs, so the 200-iteration loop of one layer enqueues without a host sync.
 #include "common.cuh"
 #include "tc_layout.cuh"
+#include "peer.cuh"
 #include <cuda_fp8.h>
 
 namespace effq {
@@ -121,13 +122,19 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
 }
 
 __global__ void admm_decide_kernel(effq_admm_state* st, const double* __restrict__ sse, double numel,
-                                   float* __restrict__ history, int* __restrict__ take) {
-  const float loss = (float)(*sse / numel);              // F.mse_loss(...).item()
+                                   float* __restrict__ history, int* __restrict__ take, effq_peer_comm comm) {
+  double total = *sse;
+  if (comm.world > 1) {                                   // sharded volumes: sum the ranks' shares over NVLink
+    double v[3] = {total, 0.0, 0.0};
+    if (!peer_allreduce3(comm, 1, v)) v[0] = __longlong_as_double(0x7ff8000000000000ll);   // NaN: exchange timed out
+    total = v[0];
+  }
+  const float loss = (float)(total / numel);             // F.mse_loss(...).item()
   const int it = st->iter;
   const int keep = (it == 0 || loss < st->best_loss) ? 1 : 0;   // EfficientQConv.py:139
   if (keep) { st->best_loss = loss; st->best_iter = it; st->best_conv_scale = st->conv_scale; }
   st->last_loss = loss;
-  st->sse = *sse;
+  st->sse = total;
   if (history) history[it] = loss;
   st->iter = it + 1;
   *take = keep;
@@ -222,15 +229,19 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
 extern "C" int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const float* g,
                                const float* bstar, int64_t g_numel, int32_t c2, float* best_g, float* best_b,
                                float* history, const void* aux_src, void* aux_dst, int64_t aux_bytes,
-                               void* stream) {
+                               const effq_peer_comm* comm, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(st && sse && g && best_g && numel > 0, "bad argument");
+  EFFQ_CHECK_ARG(!comm || (comm->world >= 1 && comm->world <= EFFQ_PEER_MAX && comm->rank >= 0 &&
+                           comm->rank < comm->world), "bad communicator");
+  effq_peer_comm cm;
+  if (comm) cm = *comm; else { cm.world = 1; cm.rank = 0; for (int i = 0; i < EFFQ_PEER_MAX; ++i) cm.slots[i] = nullptr; }
   EFFQ_CHECK_ARG(aux_bytes == 0 || (aux_src && aux_dst && aux_bytes % 16 == 0 &&
                                     ((uintptr_t)aux_src & 15) == 0 && ((uintptr_t)aux_dst & 15) == 0),
                  "aux buffers must be 16B aligned and sized");
   cudaStream_t s = (cudaStream_t)stream;
   int* take = &st->take_;
-  admm_decide_kernel<<<1, 1, 0, s>>>(st, sse, numel, history, take);
+  admm_decide_kernel<<<1, 1, 0, s>>>(st, sse, numel, history, take, cm);
   EFFQ_LAUNCH_CHECK();
   admm_keep_kernel<<<grid_for(g_numel), AD_THREADS, 0, s>>>(take, g, bstar, g_numel, c2, best_g, best_b,
                                                                            (const uint4*)aux_src, (uint4*)aux_dst, aux_bytes / 16);

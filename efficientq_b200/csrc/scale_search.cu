@@ -20,6 +20,7 @@
 // one the plain pass would compute, so the scales differ from the plain passes only through the
 // fp64 summation order (~1e-16 relative); the pass count is the same.
 #include "common.cuh"
+#include "peer.cuh"
 #include <stdlib.h>
 #include <cooperative_groups.h>
 
@@ -35,6 +36,7 @@ struct SSWorkspace {
   unsigned int list_count[3];                // ambiguous-list fill counters (rotate per classifying pass)
   unsigned int pad[3];
   double diag[4];                            // streamed search: pass-type counts of the last launch
+  double gsum[4];                            // sharded search: sums over all ranks of the current pass
   double partial[2][SS_MAX_CTAS][4];
   // followed by the ambiguous list (floats) when the caller's workspace is larger
 };
@@ -337,7 +339,7 @@ constexpr unsigned int SS_RECLASS_MIN = 1u << 16;      // lists shorter than thi
 
 __global__ void __launch_bounds__(SS_THREADS, 2)
 scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, SSWorkspace* ws,
-                           float* list_mem, unsigned int cap, float wmax0, float dthr) {
+                           float* list_mem, unsigned int cap, float wmax0, float dthr, effq_peer_comm comm) {
   __shared__ double scratch[32];
   __shared__ double bc[4];
   __shared__ float sbuf[SS_STAGE_CAP];
@@ -351,13 +353,35 @@ scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_
   if (threadIdx.x == 0) scnt = 0;
   __syncthreads();
 
+  // Sharded volumes: every pass ends with an in-kernel all-reduce of the two local sums over NVLink
+  // peer memory (CTA 0, one thread), then a second grid barrier publishes the global sums.  Which
+  // elements are stable / listed is a local matter; the scale -- hence every decision below -- is
+  // global and identical on all ranks.
+  auto exchange = [&](double& x0, double& x1) -> bool {
+    if (comm.world <= 1) return true;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      double v[3] = {x0, x1, 0.0};
+      const bool ok = peer_allreduce3(comm, 0, v);
+      ws->gsum[0] = v[0];
+      ws->gsum[1] = v[1];
+      ws->gsum[2] = ok ? 0.0 : 1.0;
+      __threadfence();
+    }
+    if (!grid_barrier(ws, target, nctas)) return false;
+    x0 = ((volatile double*)ws->gsum)[0];
+    x1 = ((volatile double*)ws->gsum)[1];
+    return ((volatile double*)ws->gsum)[2] == 0.0;
+  };
+
   double s0, s1;
   pass_sums<0>(vv, 0.0, q, blockIdx.x, nctas, s0, s1);
   s0 = block_sum(s0, scratch);
   if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = 0.0; }
   if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
   fold_partials(ws->partial[parity], nctas, scratch, bc);
-  double a = bc[0] / (double)numel;
+  double g_abs = bc[0], g_cnt = (double)numel;
+  if (!exchange(g_abs, g_cnt)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
+  double a = g_abs / g_cnt;
   double a_prev = -999.0;
   int passes = 0;
   double last0 = 0.0, last1 = 0.0;
@@ -518,6 +542,7 @@ scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_
       p1 = bc[1];
     }
     __syncthreads();
+    if (!exchange(p0, p1)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
     last0 = p0;
     last1 = p1;
     a_prev = a;
@@ -732,9 +757,15 @@ static int launch_search(effq::VecView vv, int nlvl, float lo, float hi, effq_sc
 
 extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
                                  int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
-                                 void* workspace, int64_t workspace_bytes, void* stream) {
+                                 void* workspace, int64_t workspace_bytes, const effq_peer_comm* comm,
+                                 void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(v1 && state && workspace, "null pointer");
+  EFFQ_CHECK_ARG(!comm || (comm->world >= 1 && comm->world <= EFFQ_PEER_MAX && comm->rank >= 0 &&
+                           comm->rank < comm->world), "bad communicator");
+  const bool sharded = comm && comm->world > 1;
+  effq_peer_comm cm;
+  if (comm) cm = *comm; else { cm.world = 1; cm.rank = 0; for (int i = 0; i < EFFQ_PEER_MAX; ++i) cm.slots[i] = nullptr; }
   EFFQ_CHECK_ARG(workspace_bytes >= ss_base_bytes(), "workspace smaller than effq_scale_search_workspace(0)");
   EFFQ_CHECK_ARG(rows > 0 && cols > 0 && ld1 >= cols && (!v2 || ld2 >= cols), "bad shape");
   EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
@@ -742,7 +773,7 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   const long long numel = rows * cols;
   const int sms = sm_count();                         // one CTA per SM: cheapest grid barrier
   VecView vv{v1, v2, ld1, ld2, rows, cols};
-  if (numel <= 131072) {       // measured: cluster wins up to ~128 K elements, the 148-CTA grid beyond
+  if (!sharded && numel <= 131072) {   // measured: cluster wins up to ~128 K elements, the 148-CTA grid beyond
     // small tensors (weights): one thread-block cluster, data resident in shared memory
     int nranks = (int)((numel + SC_MAX_ELEMS - 1) / SC_MAX_ELEMS);
     if (nranks < 8 && numel > 8192) {                 // spread the per-pass arithmetic a little
@@ -777,12 +808,14 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 32, s));    // barrier counter, abort flag, list counters
   SSWorkspace* ws = (SSWorkspace*)workspace;
   const long long per_cta_8 = (long long)SS_THREADS * 8;
-  if (numel <= (long long)sms * SS_THREADS * 8) {
+  if (sharded) {
+    // the in-kernel exchange lives in the streaming kernel: use it for every size
+  } else if (numel <= (long long)sms * SS_THREADS * 8) {
     int ctas = (int)((numel + per_cta_8 - 1) / per_cta_8);
     return launch_search<8>(vv, nlvl, lo, hi, state, ws, ctas < 1 ? 1 : ctas, s);
   }
-  if (numel <= (long long)sms * SS_THREADS * 24) return launch_search<24>(vv, nlvl, lo, hi, state, ws, sms, s);
-  if (numel <= (long long)sms * SS_THREADS * 48) return launch_search<48>(vv, nlvl, lo, hi, state, ws, sms, s);
+  else if (numel <= (long long)sms * SS_THREADS * 24) return launch_search<24>(vv, nlvl, lo, hi, state, ws, sms, s);
+  else if (numel <= (long long)sms * SS_THREADS * 48) return launch_search<48>(vv, nlvl, lo, hi, state, ws, sms, s);
   {
     float* list = (float*)((char*)workspace + ss_base_bytes());
     long long room = (workspace_bytes - ss_base_bytes()) / 12 / 64 * 64;      // floats per list buffer
@@ -801,7 +834,7 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
     static const float wmax0 = [] { const char* v = getenv("EFFQ_SS_WMAX"); return v && *v ? (float)atof(v) : 0.04f; }();
     static const float dthr = [] { const char* v = getenv("EFFQ_SS_DTHR"); return v && *v ? (float)atof(v) : 0.01f; }();
     float wm = wmax0, dt = dthr;
-    void* args[] = {&vv, &nlvl, &lo, &hi, &state, &ws, &list, &cap, &wm, &dt};
+    void* args[] = {&vv, &nlvl, &lo, &hi, &state, &ws, &list, &cap, &wm, &dt, &cm};
     EFFQ_CUDA(cudaLaunchCooperativeKernel((void*)scale_search_stream_kernel, dim3(ctas), dim3(SS_THREADS), args, 0, s));
     count_launch();
     return 0;

@@ -32,6 +32,20 @@ class DistCtx:
         self.group = group
         self.world = td.get_world_size(group) if self.enabled else 1
         self.rank = td.get_rank(group) if self.enabled else 0
+        self._peer = None
+
+    def peer_link(self, device: torch.device):
+        """The NVLink peer link of this run (created on first use; None for a single process, for
+        non-CUDA process groups, with EFFQ_PEER=0, or when CUDA IPC is unavailable)."""
+        if self._peer is None and self.world > 1 and device.type == "cuda" and \
+                os.environ.get("EFFQ_PEER", "1") != "0" and td.get_backend(self.group) == "nccl":
+            try:
+                self._peer = PeerLink(self, device)
+            except Exception as exc:  # noqa: BLE001  (plumbing only: the NCCL form of the exchanges remains)
+                import warnings
+                warnings.warn(f"NVLink peer link unavailable ({exc!r}); using NCCL all-reduces")
+                self._peer = False
+        return self._peer or None
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         """In-place SUM all-reduce (no-op for a single process); returns ``t``."""
@@ -51,6 +65,52 @@ class DistCtx:
     def shard(self, n_total: int) -> Tuple[int, int]:
         """[begin, end) of the calibration volumes owned by this rank (contiguous, balanced)."""
         return shard_range(n_total, self.rank, self.world)
+
+
+class PeerLink:
+    """NVLink peer-memory link between the ranks of one node for the in-kernel exchanges of
+    csrc/peer.cuh (2 doubles per activation-search pass, 1 double per ADMM iteration: thousands of
+    latency-bound all-reduces per layer that are cheaper inside the kernels than as NCCL calls).
+
+    Every rank allocates one 4 KB slot buffer, exports it through CUDA IPC, all-gathers the 64-byte
+    handles over the process group and maps its peers' buffers.  ``comm_ptr`` is what the C-ABI
+    takes as ``const effq_peer_comm*``.  Construction fails (EffqError) when IPC / peer access is
+    not available; the caller then keeps the NCCL form of the same exchanges."""
+
+    def __init__(self, ctx: "DistCtx", device: torch.device):
+        import ctypes as C
+        from . import capi
+        lib = capi.load()
+        if ctx.world > 8:
+            raise capi.EffqError("PeerLink: at most 8 ranks (one node)")
+        self._lib = lib
+        self.local = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        capi.check(lib.effq_peer_alloc(C.byref(self.local), handle), "effq_peer_alloc")
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
+        gathered = [torch.empty_like(mine) for _ in range(ctx.world)]
+        td.all_gather(gathered, mine, group=ctx.group)
+        self.comm = capi.PeerComm()
+        self.comm.rank, self.comm.world = ctx.rank, ctx.world
+        self._opened = []
+        for r, h in enumerate(gathered):
+            if r == ctx.rank:
+                self.comm.slots[r] = self.local.value
+                continue
+            p = C.c_void_p()
+            capi.check(lib.effq_peer_open(bytes(h.cpu().numpy().tobytes()), C.byref(p)), "effq_peer_open")
+            self._opened.append(p)
+            self.comm.slots[r] = p.value
+        self.comm_ptr = C.byref(self.comm)
+        ctx.barrier()                     # every rank has mapped every buffer before the first kernel uses them
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._lib.effq_peer_close(p)
+        self._opened = []
+        if self.local:
+            self._lib.effq_peer_free(self.local)
+            self.local = None
 
 
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:

@@ -85,7 +85,13 @@ class LayerCalibrator:
         if self.dist.world == 1:
             ops.scale_search(x, nlvl, 0.0, 1.0, self.xstate)
             return
-        # sharded volumes: one pass of local sums, all-reduce 2 doubles, device-side update
+        peer = self.dist.peer_link(self.device)
+        if peer is not None:
+            # sharded volumes, one node: the same single launch, the sums of every pass all-reduced
+            # in-kernel over NVLink peer memory
+            ops.scale_search(x, nlvl, 0.0, 1.0, self.xstate, comm=peer.comm_ptr)
+            return
+        # NCCL form: one pass of local sums, all-reduce 2 doubles, device-side update
         ops.scale_partial(x, nlvl, 0.0, 1.0, self.xstate, 0, self.sums, self.sp_ws)
         self.dist.all_reduce_sum(self.sums)
         ops.scale_step(self.xstate, self.sums, 0, nlvl)
@@ -215,8 +221,18 @@ class LayerCalibrator:
                 ops.admm_lhs(a0, r_, eta, has_bias, a_r)
                 chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
                                            lambda: torch.linalg.cholesky_ex(a_r))
-                inv_r = ops.timer.run("lib_cholesky_inverse", {"flops": 2.0 * kp ** 3 / 3.0},
-                                      lambda: torch.cholesky_inverse(chol))
+                if solve_tc and kp >= 1024 and os.environ.get("EFFQ_INV_TC", "1") != "0":
+                    # A^-1 = L^-T L^-1: one library TRSM for W = L^-1, then W^T W on the tensor cores
+                    # (the library's potri runs at ~5 TFLOP/s and was the largest item of the step)
+                    eye = self._eye(kp, dev)
+                    w_inv = ops.timer.run("lib_trsm", {"flops": float(kp) ** 3},
+                                          lambda: torch.linalg.solve_triangular(chol, eye, upper=False))
+                    wt = ops.split3_bf16(w_inv.T)              # rows of W^T: K-major operand of (W^T W)[i][j]
+                    inv_r, self._sg_ws2 = ops.solve_gemm_tc(wt, wt, kp, ws=self._sg_ws2)
+                    del w_inv, wt
+                else:
+                    inv_r = ops.timer.run("lib_cholesky_inverse", {"flops": 2.0 * kp ** 3 / 3.0},
+                                          lambda: torch.cholesky_inverse(chol))
                 if solve_tc:
                     # A^-1 is symmetric: a column-major result is read as its (row-major) transpose, no copy
                     inv_rm = inv_r if inv_r.stride(1) == 1 else inv_r.T
@@ -229,6 +245,7 @@ class LayerCalibrator:
                 rep.factorizations += 1
         ainv = None
         rho_built = None
+        peer = dist.peer_link(dev) if dist.world > 1 else None
         if solve_tc:
             bplanes = torch.empty((3, c2, ops.split3_ld(kp)), dtype=torch.bfloat16, device=dev)
             sol_buf = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :kp]
@@ -268,10 +285,15 @@ class LayerCalibrator:
             else:
                 ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
                                ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
-            if dist.world > 1 and stats64 is None:
-                dist.all_reduce_sum(self.sse)
+            track_comm = None
+            if dist.world > 1 and stats64 is None:                # this rank's share of the squared error
+                if peer is not None:
+                    track_comm = peer.comm_ptr                    # summed inside admm_track over NVLink
+                else:
+                    dist.all_reduce_sum(self.sse)
             ops.timer.run("admm_track", {"bytes": 8 * c2 * k}, lambda: ops.admm_track(
-                self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes))
+                self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes,
+                comm=track_comm))
             rho = new_rho
 
         # final forward with the best iterate: layer output + attention-weighted loss (:161-166)
@@ -296,6 +318,8 @@ class LayerCalibrator:
         if gram_flag is not None and int(gram_flag.item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 Gram kernel aborted (barrier timeout)")
         rep.final_loss = final_sse / numel_total
+        if s["last_loss"] != s["last_loss"]:
+            raise ops.EffqError(f"{name}: NVLink peer exchange timed out (a rank is missing or out of step)")
         rep.best_loss, rep.best_iter, rep.alpha_w = s["best_loss"], s["best_iter"], s["a_w"]
         if q_act:
             xs = self.xstate.read()
@@ -311,6 +335,16 @@ class LayerCalibrator:
 
     _cws = None
     _sg_ws = None
+    _sg_ws2 = None          # split-K partials of the K' x K' inverse product (side stream)
+    _eyes = None
+
+    def _eye(self, n, dev):
+        if self._eyes is None:
+            self._eyes = {}
+        if n not in self._eyes:
+            self._eyes[n] = torch.eye(n, dtype=torch.float32, device=dev)
+        return self._eyes[n]
+
     _qf_ws = None
     _side = None
 

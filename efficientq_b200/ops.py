@@ -220,15 +220,16 @@ def _pair_view(v1: torch.Tensor, v2: Optional[torch.Tensor]):
 
 
 def scale_search(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: ScaleState,
-                 v2: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> ScaleState:
-    """project_by_iter on the device (one cooperative launch, no host sync)."""
+                 v2: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None, comm=None) -> ScaleState:
+    """project_by_iter on the device (one cooperative launch, no host sync).  With ``comm``
+    (dist.PeerLink.comm_ptr) v1 is this rank's shard and every pass is all-reduced in-kernel."""
     rows, cols, ld1, ld2 = _pair_view(v1, v2)
     name = f"scale_search_w_{rows * cols}" if v2 is not None else "scale_search_act"
     if ws is None:
         ws = _scale_ws(v1.device, rows * cols)
     timer.run(name, {"pass_bytes": 4 * rows * cols * (2 if v2 is not None else 1)}, lambda: check(
         capi.load().effq_scale_search(ptr(v1), ld1, ptr(v2), ld2, rows, cols, int(nlvl), float(lo), float(hi),
-                                      state.p, ptr(ws), ws.numel(), stream()), "effq_scale_search"))
+                                      state.p, ptr(ws), ws.numel(), comm, stream()), "effq_scale_search"))
     return state
 
 
@@ -466,8 +467,10 @@ def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], 
           "effq_admm_project")
 
 
-def admm_track(st: AdmmState, sse, numel: float, g, bstar, best_g, best_b, history, aux_src=None, aux_dst=None):
+def admm_track(st: AdmmState, sse, numel: float, g, bstar, best_g, best_b, history, aux_src=None, aux_dst=None,
+               comm=None):
+    """``comm`` (dist.PeerLink.comm_ptr) makes the kernel all-reduce this rank's SSE share over NVLink."""
     nb = aux_src.numel() * aux_src.element_size() if aux_src is not None else 0
     check(capi.load().effq_admm_track(st.p, ptr(sse), float(numel), ptr(g), ptr(bstar), g.numel(),
                                       g.shape[0], ptr(best_g), ptr(best_b), ptr(history), ptr(aux_src),
-                                      ptr(aux_dst), nb, stream()), "effq_admm_track")
+                                      ptr(aux_dst), nb, comm, stream()), "effq_admm_track")

@@ -77,11 +77,31 @@ typedef struct effq_admm_state {
   float   best_conv_scale; /* conv_scale of the best iterate                     */
 } effq_admm_state;
 
+/* Peer-memory communicator of a sharded run (one process per GPU of ONE node): slots[r] is rank
+ * r's slot buffer (effq_peer_alloc on rank r, effq_peer_open elsewhere; slots[rank] is the
+ * local one).  Kernels that take a `comm` all-reduce their few doubles over it in-kernel
+ * (NVLink loads/stores, csrc/peer.cuh) instead of returning to the host for an NCCL call.
+ * comm == NULL means a single-GPU run. */
+#define EFFQ_PEER_MAX 8
+#define EFFQ_PEER_CHANNELS 2        /* 0: scale search, 1: ADMM iterate score */
+typedef struct effq_peer_comm {
+  void*   slots[EFFQ_PEER_MAX];
+  int32_t rank;
+  int32_t world;
+} effq_peer_comm;
+
 /* ---- library ------------------------------------------------------------- */
 int         effq_abi_version(void);
 const char* effq_last_error(void);
 /* kernels launched by this library since the last reset (bench gpu_launches). */
 uint64_t    effq_launch_count(void);
+/* Slot buffer of this rank (zero-initialised, effq_peer_bytes() bytes) + its 64-byte CUDA IPC
+ * handle; peers map it with effq_peer_open.  Host-side, synchronous. */
+int64_t     effq_peer_bytes(void);
+int         effq_peer_alloc(void** dev_ptr, uint8_t* handle64);
+int         effq_peer_open(const uint8_t* handle64, void** dev_ptr);
+int         effq_peer_close(void* dev_ptr);
+int         effq_peer_free(void* dev_ptr);
 void        effq_reset_launch_count(void);
 
 /* ---- (a) fake-quant: reference layer_helper.py:25-37, PTQConv.py:110-116 ---- */
@@ -121,9 +141,12 @@ int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, i
  * "ambiguous" elements of the interval-stable passes (csrc/scale_search.cu); with a smaller
  * workspace the search falls back to plain passes (same result up to fp64 summation order). */
 int64_t effq_scale_search_workspace(int64_t numel);
+/* comm != NULL: v is this rank's shard; the sums of every pass are all-reduced in-kernel, so all
+ * ranks run the same passes and end with the same scale (the sharded form of the search). */
 int effq_scale_search(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
                       int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* state,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      void* workspace, int64_t workspace_bytes, const effq_peer_comm* comm,
+                      void* stream);
 /* Multi-GPU building blocks: one pass of local sums, then (after the caller has
  * all-reduced sums[0..1]) the scale update.  mode 0: sums = {sum|v|, numel};
  * mode 1: sums = {sum(b*v), sum(b*b)} for the scale in *state. */
@@ -229,10 +252,11 @@ int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_s
 /* loss = fp32(sse/numel); history[iter] = loss; if (iter==0 || loss < best) keep G, b*
  * (and, when aux_bytes > 0, the 16B-aligned side buffer aux_src -> aux_dst, e.g. the
  * tensor-core weight codes of the same iterate). */
+/* comm != NULL: *sse is this rank's share; it is all-reduced in-kernel (numel is the global count). */
 int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const float* g,
                     const float* bstar, int64_t g_numel, int32_t c2, float* best_g, float* best_b,
                     float* history, const void* aux_src, void* aux_dst, int64_t aux_bytes,
-                    void* stream);
+                    const effq_peer_comm* comm, void* stream);
 
 #ifdef __cplusplus
 }

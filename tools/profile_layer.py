@@ -22,14 +22,17 @@ print("act scale", st.read())
 qx = ops.fakequant_state(x, st, 16, 0.0, 1.0)
 alpha = st.a_f32().reshape(1)
 yq, codes = ops.fakequant(x, alpha, 16, 0.0, 1.0, want_codes=True)
-xq = ops.quantize_act_ndhwc(x, 16, state=st)
+xq, xq8 = ops.quantize_act_ndhwc(x, 16, state=st, e4m3=True)
 w = (2 * torch.randint(0, 16, (c, c, 3, 3, 3), device=dev) - 15).float()
 wq = ops.pack_weight_codes(w)
+wq8 = ops.pack_weight_codes(w, ops.CODE_E4M3)
 cs = torch.full((1,), 1e-3, device=dev)
 ws = ops.workspace(16 + 8 * 1024, dev)
 sse = torch.zeros(1, dtype=torch.float64, device=dev)
 for _ in range(4):
-    ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=y, ws=ws, sse=sse)
+    ops.conv3d_tc(xq8, wq8, None, cs, c, 3, want_out=False, target=y, ws=ws, sse=sse)      # the step's conv (e4m3 codes)
+for _ in range(2):
+    ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=y, ws=ws, sse=sse)        # bf16 codes, for comparison
 code_scale = (st.a_f32() / 15.0).reshape(1)
 a0, b0, _, flag = ops.gram_tc(xq, code_scale, y, att, True)
 sol = torch.randn(c, c * 27 + 1, device=dev) * 0.05
@@ -37,5 +40,12 @@ dual = torch.zeros(c, c * 27, device=dev)
 wst = ops.ScaleState(dev)
 for _ in range(3):
     ops.scale_search(sol[:, : c * 27], 16, -1.0, 1.0, wst, v2=dual)
+# proximal-step GEMM at the deepest layer's shape (C2 = 256, K' = 6913)
+kp = 6913
+bm = torch.randn(256, kp, device=dev)
+ai = torch.randn(kp, kp, device=dev) * 1e-3
+ap, bp = ops.split3_bf16(bm), ops.split3_bf16(ai)
+for _ in range(3):
+    ops.solve_gemm_tc(ap, bp, kp)
 torch.cuda.synchronize()
 print("done", sse.item(), int(flag.item()), wst.read()["passes"])

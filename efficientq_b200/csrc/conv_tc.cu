@@ -65,6 +65,7 @@ struct TcParams {
   int tiles_h, tiles_w;
   long long n_tiles;
   int n_halo_stages, n_w_stages, w_resident;
+  int ctas_per_sm;             // 2 when two CTAs are meant to share an SM (grid = 2 x SMs)
   int n_tgt_stages;            // > 0: the target tile arrives by TMA through a ring of this many stages
   unsigned int off_tgt;
   unsigned int halo_bytes, halo_tx_bytes, wtile_bytes;   // stage stride, bytes one halo box delivers, weight tile
@@ -123,7 +124,7 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], float* op, lo
 // resident in shared memory and FP8: e4m3 operands are compile-time, so the single MMA-issuing
 // thread runs straight-line code.
 template <int KS, int KK, bool WRES, bool FP8>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, (KK == 1) ? 2 : 1)
 conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024 B alignment
@@ -468,7 +469,16 @@ static bool tc_plan(const effq_geom& g, int code_dtype, TcParams& p) {
   p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
   p.off_bias = 384;
   p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
-  const uint32_t budget = 224u * 1024u;
+  // 32-byte rows (C1 = 32 e4m3 / 16 bf16): everything is small, so TWO CTAs share an SM (each with
+  // half the shared memory and <= 128 registers): their tile pipelines interleave and hide the
+  // per-tile serialisation of the single MMA-issuing thread.
+  static const bool one_cta = [] { const char* v = getenv("EFFQ_TC_ONE_CTA"); return v && *v == '1'; }();
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * g.c2)) cols <<= 1;
+  p.tmem_cols = cols;
+  if (cols > 512) return false;
+  p.ctas_per_sm = (p.rp == 32 && !one_cta && 2 * cols <= 512) ? 2 : 1;   // both CTAs' accumulators must fit TMEM
+  const uint32_t budget = p.ctas_per_sm == 2 ? 110u * 1024u : 224u * 1024u;
   const uint32_t w_all = p.wstage_bytes * (uint32_t)(p.n_groups * p.taps);
   // Shared-memory plan: halo ring (>= 2 stages), weights (resident, else a ring of >= 2 tiles), and --
   // when the target can be a TMA box -- a target ring of >= 2 stages; leftover space deepens the rings.
@@ -495,10 +505,7 @@ static bool tc_plan(const effq_geom& g, int code_dtype, TcParams& p) {
     int ws = (int)((budget - p.off_w) / p.wstage_bytes);
     p.n_w_stages = ws > 8 ? 8 : ws;
   }
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * g.c2)) cols <<= 1;
-  p.tmem_cols = cols;
-  return cols <= 512;
+  return true;
 }
 
 static uint32_t tc_smem_bytes(const TcParams& p) {
@@ -611,7 +618,8 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t co
   // (the caller must then pass a workspace of at least 16 + 8 KB + 16 KB)
   p.dbg = (p.debug & 8) ? (unsigned long long*)((char*)workspace + 16 + 8 * 1024) : nullptr;
   const uint32_t smem = tc_smem_bytes(p);
-  const long long ctas = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  const long long max_ctas = (long long)sm_count() * p.ctas_per_sm;
+  const long long ctas = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
   const int kk = p.rp / 32;
   alignas(64) CUtensorMap xmap, tmap;
   if (int rc = tc_make_xmap(p, xcodes, &xmap)) return rc;

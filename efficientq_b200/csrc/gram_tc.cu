@@ -16,6 +16,12 @@
 //     bf16 hi + bf16 lo (two MMAs, error <= 2^-17 per term, exact for the reference's integer
 //     masks); the rows of B0 (att_v * y, arbitrary fp32) and the bias row use a three-term
 //     split (24 bits: fp32-exact); the right operand is the raw integer code (exact).
+//   * when C1 is a multiple of 32 the right operand is not built by threads at all: a 64-row
+//     (C1 % 64 == 0, SWIZZLE_128B) or 32-row (C1 = 32, SWIZZLE_64B) block of it is exactly one
+//     tap's channel slice of an 8x8 voxel block, i.e. ONE 5-D TMA box of the NDHWC codes at
+//     tap-shifted coordinates (out-of-range coordinates arrive as zeros = the padding); the
+//     constant blocks behind row K (the ones column, zero fill) are written once per item.  The
+//     builders then only gather, weight and split the left operand (4 chunks instead of 12).
 //   * one thread issues tcgen05.mma M=128,N=256,K=16 (both operands MN-major) -- the only
 //     shape at which the SS tensor pipe is not starved by the A-operand read (B200: one A row
 //     per cycle, profiles/r01_conv_layout.md) -- into a 128x256 fp32 TMEM accumulator.
@@ -24,11 +30,14 @@
 //     with atomics (deterministic to fp32 after the final rounding).
 #include "common.cuh"
 #include "tc_layout.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace effq {
 
 constexpr int GT_BUILDERS = 256;           // 8 warps
-constexpr int GT_THREADS = GT_BUILDERS + 32;
+constexpr int GT_THREADS = GT_BUILDERS + 64;        // + MMA warp + right-operand TMA warp
 constexpr int GT_STAGES = 2;
 constexpr int GT_KV = 64;                  // voxels per stage: 8 h-rows x 8 w
 constexpr int GT_BM = 128, GT_BN = 256;
@@ -52,6 +61,8 @@ struct GtParams {
   int hb_h, hb_w;              // 8x8 voxel blocks per plane (ceil)
   long long hb_total;          // n*d*hb_h*hb_w
   long long hb_per_split;
+  int p_tma;                   // right operand by TMA
+  int pblk;                    // rows per right-operand block (64: SWIZZLE_128B, 32: SWIZZLE_64B)
 };
 
 __device__ __forceinline__ uint32_t gt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,7 +175,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p) {
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
   extern __shared__ __align__(1024) uint8_t gsm_raw[];
   uint8_t* gsm = gsm_raw + ((1024u - (gt_smem_u32(gsm_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bars[2 * GT_STAGES + 2];
@@ -178,7 +190,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(FULL(s), GT_BUILDERS); gt_mbar_init(EMPTY(s), 1); }
+    // FULL: every builder thread + (TMA path) the arrive.expect_tx of the right-operand loader
+    for (int s = 0; s < GT_STAGES; ++s) { gt_mbar_init(FULL(s), GT_BUILDERS + (p.p_tma ? 1 : 0)); gt_mbar_init(EMPTY(s), 1); }
     gt_mbar_init(TFULL, 1);
     gt_mbar_init(TEMPTY, GT_BUILDERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,6 +220,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       idesc |= (uint32_t)(GT_BN >> 3) << 17;
       idesc |= (uint32_t)(GT_BM >> 4) << 24;
       const uint64_t tmpl = gt_desc(0, GT_KV * 128u, 1024u);
+      // right operand: 64-row blocks (128 B per voxel) or, for the TMA path at C1 = 32, 32-row blocks
+      // (64 B per voxel, SWIZZLE_64B: 8-voxel groups 512 B apart, blocks GT_KV * 64 B apart)
+      const bool p32 = p.p_tma && p.pblk == 32;
+      uint64_t ptmpl = tmpl;
+      if (p32) {
+        ptmpl = gt_desc(0, GT_KV * 64u, 512u);
+        ptmpl = (ptmpl & ~((uint64_t)7 << 61)) | ((uint64_t)4 << 61);      // SWIZZLE_64B
+      }
+      const uint32_t pk16 = p32 ? (16u * 64u >> 4) : (16u * 128u >> 4);     // 16 voxels of the right operand, in 16 B units
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       bool ok = true;
@@ -231,7 +253,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
 #pragma unroll
             for (int ks = 0; ks < GT_KV / 16; ++ks) {
               const uint32_t koff = (uint32_t)ks * (16u * 128u >> 4);
-              const uint64_t bd = tmpl | (uint64_t)((pp + koff) & 0x3fffu);
+              const uint64_t bd = ptmpl | (uint64_t)((pp + (uint32_t)ks * pk16) & 0x3fffu);
               gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, ks == 0 ? accum : 1u);
               gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
               if (three) gt_mma(tmem_base, tmpl | (uint64_t)((zl2 + koff) & 0x3fffu), bd, idesc, 1u);
@@ -246,6 +268,44 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
         tphase ^= 1u;
       }
     }
+  } else if (warp == 9) {
+    // ===== right-operand loader: one TMA box per (tap, channel slice) block of the 256-row tile =====
+    if (p.p_tma && elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&pmap)) : "memory");
+      const uint32_t blk_bytes = (uint32_t)(GT_KV * p.pblk * 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
+        long long r = item;
+        const int z = (int)(r % p.splits); r /= p.splits;
+        const int nb = (int)(r % p.nb_n); r /= p.nb_n;
+        if (gt_tile_skipped((int)r, nb, p.mx0)) continue;
+        int n_live = (p.k - nb * GT_BN) / p.pblk;                    // blocks of this tile below row K
+        n_live = n_live < 0 ? 0 : (n_live > GT_BN / p.pblk ? GT_BN / p.pblk : n_live);
+        long long hb0 = (long long)z * p.hb_per_split;
+        long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
+        for (long long hb = hb0; hb < hb1; ++hb) {
+          long long q = hb;
+          const int bw = (int)(q % p.hb_w); q /= p.hb_w;
+          const int bh = (int)(q % p.hb_h); q /= p.hb_h;
+          const int dd = (int)(q % p.d); q /= p.d;
+          const int nn = (int)q;
+          if (!gt_mbar_wait<32>(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
+          const uint32_t pdst = stage0 + (uint32_t)stage * GT_STAGE_BYTES + 3u * GT_ZBYTES;
+          mbar_expect_tx(FULL(stage), (uint32_t)n_live * blk_bytes);
+          for (int j = 0; j < n_live; ++j) {
+            const int r0 = nb * GT_BN + j * p.pblk;
+            const int tap = r0 / p.c1, c0 = r0 % p.c1;
+            const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+            tma_load_5d(pdst + (uint32_t)j * blk_bytes, &pmap, c0, bw * 8 + c - 1, bh * 8 + b - 1, dd + a - 1, nn,
+                        FULL(stage));
+          }
+          if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ===== builders (also the epilogue) =====
     const int t = threadIdx.x;                       // 0..255
@@ -267,6 +327,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       for (int i = 0; i < 4; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + 4 * i, kvox, p, true);
 #pragma unroll
       for (int i = 0; i < 8; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + 4 * i, kvox, p, false);
+      const bool p_tma = p.p_tma != 0;
       long long hb0 = (long long)z * p.hb_per_split;
       long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
       for (long long hb = hb0; hb < hb1; ++hb) {
@@ -303,6 +364,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
         for (int i = 0; i < 8; ++i) {
           const int tp = ps[i].tap, kind = tp >> 6;
           pv[i] = make_uint4(0, 0, 0, 0);
+          if (p_tma) continue;                        // the TMA warp delivers the right operand
           if (kind == 1) {
             const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
             if (vlive && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w)
@@ -344,8 +406,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
           *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           if (kind >= 2) *reinterpret_cast<uint4*>(sbase + 2 * GT_ZBYTES + zs[i].dst) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
         }
+        if (!p_tma) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sbase + 3 * GT_ZBYTES + ps[i].dst) = pv[i];
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sbase + 3 * GT_ZBYTES + ps[i].dst) = pv[i];
+        } else if (hb - hb0 < GT_STAGES) {
+          // first use of this stage buffer in the item: the constant blocks behind row K (TMA never
+          // writes them): the ones column (row K; dead voxels are zeroed by the left operand) and zeros
+          const int rowb = p.pblk * 2;                               // bytes per voxel row of a block
+          const int cpb = p.pblk / 8;                                // 16-byte chunks per voxel row
+          const int first = (p.k - nb * GT_BN + p.pblk - 1) / p.pblk;
+          for (int j = first < 0 ? 0 : first; j < GT_BN / p.pblk; ++j) {
+            for (int ch = rc_base; ch < cpb; ch += 4) {
+              const uint32_t x = p.pblk == 64 ? (uint32_t)(kvox & 7) : (uint32_t)((kvox >> 1) & 3);
+              const uint32_t dst = (uint32_t)j * (uint32_t)(GT_KV * rowb) + (uint32_t)kvox * rowb + (((uint32_t)ch ^ x) << 4);
+              uint4 val = make_uint4(0, 0, 0, 0);
+              if (p.has_bias && nb * GT_BN + j * p.pblk == p.k && ch == 0) val.x = 0x3f80u;   // bf16 1.0 in row K
+              *reinterpret_cast<uint4*>(sbase + 3 * GT_ZBYTES + dst) = val;
+            }
+          }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         gt_mbar_arrive(FULL(stage));
         if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }
@@ -355,7 +434,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tc_kernel(const GtParams p
       if (!gt_mbar_wait<64>(TFULL, tphase, abort_flag)) { ok = false; break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       tphase ^= 1u;
-      const int qd = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half
+      const int qd = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half (builder warps 0..7)
       const int ri = mb * GT_BM + qd * 32 + lane;        // left row index (tap-major patch rows, then extras)
       const int kp = p.k + p.has_bias;
       int ref_i = -1;                                     // destination row in the workspace
@@ -449,7 +528,27 @@ extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const floa
   }
   const long long items = tiles * splits;
   const int ctas = (int)(items < sm_count() ? items : sm_count());
-  gram_tc_kernel<<<ctas, GT_THREADS, smem, (cudaStream_t)stream>>>(p);
+  // right operand by TMA: a block = one tap's slice of 64 (or, at C1 = 32, all 32) channels
+  static const bool no_ptma = [] { const char* v = getenv("EFFQ_GRAM_PTMA"); return v && *v == '0'; }();
+  p.p_tma = (!no_ptma && (g->c1 == 32 || g->c1 % 64 == 0)) ? 1 : 0;
+  p.pblk = g->c1 == 32 ? 32 : 64;
+  alignas(64) CUtensorMap pmap;
+  memset(&pmap, 0, sizeof(pmap));
+  if (p.p_tma) {
+    EncodeTiledFn encode = tc_encoder();
+    if (!encode) return 2;
+    const cuuint64_t dims[5] = {(cuuint64_t)p.c1, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.d, (cuuint64_t)p.n};
+    const cuuint64_t strides[4] = {dims[0] * 2, dims[0] * dims[1] * 2, dims[0] * dims[1] * dims[2] * 2,
+                                   dims[0] * dims[1] * dims[2] * dims[3] * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)p.pblk, 8u, 8u, 1u, 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    const CUresult rc = encode(&pmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xcodes_ndhwc_bf16), dims,
+                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               p.pblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { set_error("effq_gram_tc: cuTensorMapEncodeTiled failed (%d)", (int)rc); return 2; }
+  }
+  gram_tc_kernel<<<ctas, GT_THREADS, smem, (cudaStream_t)stream>>>(p, pmap);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

@@ -36,7 +36,10 @@
 
 namespace effq {
 
-constexpr int GT_BUILDERS = 256;           // 8 warps
+constexpr int GT_BUILDERS = 512;           // 16 warps
+constexpr int GT_RCS = GT_BUILDERS / 64;   // builder threads per voxel (each takes every GT_RCS-th chunk)
+constexpr int GT_ZS = 16 / GT_RCS;         // left-operand chunks per thread and stage (128 rows = 16 chunks per voxel)
+constexpr int GT_PS = 32 / GT_RCS;         // right-operand chunks per thread and stage (thread-built path)
 constexpr int GT_THREADS = GT_BUILDERS + 64;        // + MMA warp + right-operand TMA warp
 constexpr int GT_STAGES = 2;
 constexpr int GT_KV = 64;                  // voxels per stage: 8 h-rows x 8 w
@@ -196,7 +199,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
     gt_mbar_init(TEMPTY, GT_BUILDERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == GT_BUILDERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem_u32(&tmem_slot)),
                  "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -208,7 +211,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
 
   const long long n_items = (long long)p.mb_n * p.nb_n * p.splits;
 
-  if (warp == 8) {
+  if (warp == GT_BUILDERS / 32) {
     // ===== MMA issuer: warp-uniform control flow, one elected lane issues =====
     {
       uint32_t idesc = 0;
@@ -268,7 +271,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
         tphase ^= 1u;
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == GT_BUILDERS / 32 + 1) {
     // ===== right-operand loader: one TMA box per (tap, channel slice) block of the 256-row tile =====
     if (p.p_tma && elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&pmap)) : "memory");
@@ -311,7 +314,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
     const int t = threadIdx.x;                       // 0..255
     const int kvox = t & (GT_KV - 1);                // this thread's voxel inside every stage
     const int vy = kvox >> 3, vx = kvox & 7;
-    const int rc_base = t >> 6;                      // 0..3
+    const int rc_base = t >> 6;                      // 0..GT_RCS-1
     int stage = 0;
     uint32_t phase = 0, tphase = 0;
     bool ok = true;
@@ -322,11 +325,11 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
       const int nb = (int)(r % p.nb_n); r /= p.nb_n;
       const int mb = (int)r;
       if (gt_tile_skipped(mb, nb, p.mx0)) continue;
-      Slot zs[4], ps[8];
+      Slot zs[GT_ZS], ps[GT_PS];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + 4 * i, kvox, p, true);
+      for (int i = 0; i < GT_ZS; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + GT_RCS * i, kvox, p, true);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + 4 * i, kvox, p, false);
+      for (int i = 0; i < GT_PS; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + GT_RCS * i, kvox, p, false);
       const bool p_tma = p.p_tma != 0;
       long long hb0 = (long long)z * p.hb_per_split;
       long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
@@ -342,11 +345,11 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
         const __nv_bfloat16* vptr = p.xq + vidx * p.c1;
         const float aw = vlive ? (p.att ? __ldg(p.att + vidx) : 1.f) : 0.f;
         // gather first (loads in flight), then wait for the stage, then write
-        uint4 zv[4], pv[8];           // kind 1: raw bf16 codes; kind 3 (left only): handled below
-        float yv[4][8];               // kind 3: the 8 target channels of this voxel
+        uint4 zv[GT_ZS], pv[GT_PS];           // kind 1: raw bf16 codes; kind 3 (left only): handled below
+        float yv[GT_ZS][8];               // kind 3: the 8 target channels of this voxel
         const long long chan = (long long)p.d * plane;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GT_ZS; ++i) {
           const int tp = zs[i].tap, kind = tp >> 6;
           zv[i] = make_uint4(0, 0, 0, 0);
           if (kind == 1) {
@@ -361,7 +364,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < GT_PS; ++i) {
           const int tp = ps[i].tap, kind = tp >> 6;
           pv[i] = make_uint4(0, 0, 0, 0);
           if (p_tma) continue;                        // the TMA warp delivers the right operand
@@ -376,7 +379,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
         if (!gt_mbar_wait<64>(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
         uint8_t* sbase = gsm + (size_t)stage * GT_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GT_ZS; ++i) {
           const int kind = zs[i].tap >> 6;
           float pr[8];                                   // att-weighted left-operand values
           if (kind == 3) {
@@ -408,7 +411,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
         }
         if (!p_tma) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sbase + 3 * GT_ZBYTES + ps[i].dst) = pv[i];
+          for (int i = 0; i < GT_PS; ++i) *reinterpret_cast<uint4*>(sbase + 3 * GT_ZBYTES + ps[i].dst) = pv[i];
         } else if (hb - hb0 < GT_STAGES) {
           // first use of this stage buffer in the item: the constant blocks behind row K (TMA never
           // writes them): the ones column (row K; dead voxels are zeroed by the left operand) and zeros
@@ -416,7 +419,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
           const int cpb = p.pblk / 8;                                // 16-byte chunks per voxel row
           const int first = (p.k - nb * GT_BN + p.pblk - 1) / p.pblk;
           for (int j = first < 0 ? 0 : first; j < GT_BN / p.pblk; ++j) {
-            for (int ch = rc_base; ch < cpb; ch += 4) {
+            for (int ch = rc_base; ch < cpb; ch += GT_RCS) {
               const uint32_t x = p.pblk == 64 ? (uint32_t)(kvox & 7) : (uint32_t)((kvox >> 1) & 3);
               const uint32_t dst = (uint32_t)j * (uint32_t)(GT_KV * rowb) + (uint32_t)kvox * rowb + (((uint32_t)ch ^ x) << 4);
               uint4 val = make_uint4(0, 0, 0, 0);
@@ -442,7 +445,8 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
       else if (ri == p.mx0 && p.has_bias) ref_i = p.k;                                   // bias row of A0
       else if (p.y && ri >= p.mx0 + 8 && ri < p.mx0 + 8 + p.c2) ref_i = kp + (ri - p.mx0 - 8);   // B0 rows
       const bool row_ok = ref_i >= 0;
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+      constexpr int GT_EPI_COLS = GT_BN / (GT_BUILDERS / 128);      // columns per warp group of four quadrant warps
+      for (int c0 = half * GT_EPI_COLS; c0 < half * GT_EPI_COLS + GT_EPI_COLS; c0 += 32) {
         uint32_t v[32];
         gt_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -465,7 +469,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == GT_BUILDERS / 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }

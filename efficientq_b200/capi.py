@@ -91,9 +91,9 @@ _SIGS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_gram_tc_supported": (C.c_int, [C.POINTER(Geom)]),
     "effq_gram_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom),
-                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "effq_gram_tc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_void_p,
-                                          C.c_int32, C.c_void_p, C.c_void_p]),
+                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_gram_tc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_split3_ld": (C.c_int64, [C.c_int64]),

@@ -236,16 +236,12 @@ extern "C" int effq_gram_f32(const float* x, const float* x_scale, const float* 
   return 0;
 }
 
-extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
-                                       const effq_geom* g, int32_t has_bias, double* acc64, int32_t ld,
-                                       void* flags, void* stream);
-extern "C" int effq_gram_tc_supported(const effq_geom* g);
 
 // Tensor-core path: A0 (incl. bias row / column) and B0 in one tcgen05 kernel on the integer
 // codes; code_scale (device fp32) turns codes into activations in the finalize pass.
 extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y,
-                            const float* att, const effq_geom* g, int32_t has_bias, float* a0_out,
-                            float* b0_out, void* workspace, void* stream) {
+                            const float* att, const effq_geom* g, int32_t has_bias, int32_t att_exact,
+                            float* a0_out, float* b0_out, void* workspace, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && code_scale && y && g && a0_out && b0_out && workspace, "null pointer");
   EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
@@ -255,7 +251,7 @@ extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_sca
   cudaStream_t s = (cudaStream_t)stream;
   const size_t acc_bytes = (size_t)mrows * kp * 8;
   EFFQ_CUDA(cudaMemsetAsync(workspace, 0, acc_bytes + 16, s));
-  if (int rc = effq_gram_tc_accumulate(xcodes_ndhwc_bf16, att, y, g, has_bias, (double*)workspace, kp,
+  if (int rc = effq_gram_tc_accumulate(xcodes_ndhwc_bf16, att, y, g, has_bias, att_exact, (double*)workspace, kp,
                                        (char*)workspace + acc_bytes, stream)) return rc;
   const long long total = (long long)mrows * kp;
   int fb = (int)((total + 255) / 256);

@@ -64,6 +64,7 @@ struct GtParams {
   int hb_h, hb_w;              // 8x8 voxel blocks per plane (ceil)
   long long hb_total;          // n*d*hb_h*hb_w
   long long hb_per_split;
+  int single;                  // att * code exact in bf16: one term for the weighted codes (no lo plane / MMA)
   int p_tma;                   // right operand by TMA
   int pblk;                    // rows per right-operand block (64: SWIZZLE_128B, 32: SWIZZLE_64B)
 };
@@ -144,6 +145,28 @@ __device__ __forceinline__ uint64_t gt_desc(uint32_t saddr, uint32_t lbo_bytes, 
 __device__ __host__ __forceinline__ bool gt_tile_skipped(int mb, int nb, int mx0) {
   return mb * GT_BM < mx0 && mb * GT_BM >= (nb + 1) * GT_BN;
 }
+
+// Coordinates of an 8x8 voxel block; `next` walks blocks in linear order without divisions (the
+// loaders and builders advance one block per pipeline stage).
+struct BlockPos {
+  int bw, bh, dd, nn;
+  __device__ __forceinline__ void set(long long hb, const GtParams& p) {
+    long long q = hb;
+    bw = (int)(q % p.hb_w); q /= p.hb_w;
+    bh = (int)(q % p.hb_h); q /= p.hb_h;
+    dd = (int)(q % p.d); q /= p.d;
+    nn = (int)q;
+  }
+  __device__ __forceinline__ void next(const GtParams& p) {
+    if (++bw == p.hb_w) {
+      bw = 0;
+      if (++bh == p.hb_h) {
+        bh = 0;
+        if (++dd == p.d) { dd = 0; ++nn; }
+      }
+    }
+  }
+};
 
 struct Slot {
   int rel;          // kind 1: element offset relative to the voxel's own vector; kind 3: first y channel
@@ -242,6 +265,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
           if (gt_tile_skipped((int)(rr / p.nb_n), (int)(rr % p.nb_n), p.mx0)) continue;
         }
         const bool three = (int)(item / ((long long)p.splits * p.nb_n)) * GT_BM >= p.mx0;   // y / ones rows: 3-term split
+        const bool two = three || !p.single;                                                // weighted codes: hi + lo unless exact
         long long hb0 = (long long)z * p.hb_per_split;
         long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
         if (!gt_mbar_wait(TEMPTY, tphase ^ 1u, abort_flag)) { ok = false; break; }
@@ -258,7 +282,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
               const uint32_t koff = (uint32_t)ks * (16u * 128u >> 4);
               const uint64_t bd = ptmpl | (uint64_t)((pp + (uint32_t)ks * pk16) & 0x3fffu);
               gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, ks == 0 ? accum : 1u);
-              gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
+              if (two) gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
               if (three) gt_mma(tmem_base, tmpl | (uint64_t)((zl2 + koff) & 0x3fffu), bd, idesc, 1u);
             }
             gt_commit(EMPTY(stage));
@@ -288,22 +312,30 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
         n_live = n_live < 0 ? 0 : (n_live > GT_BN / p.pblk ? GT_BN / p.pblk : n_live);
         long long hb0 = (long long)z * p.hb_per_split;
         long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
+        // per-item box table: channel offset and tap shift of every live block (no divisions per stage:
+        // this single thread is on the latency path of every stage)
+        int bc0[8], bsh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r0 = nb * GT_BN + j * p.pblk;
+          const int tap = r0 / p.c1;
+          bc0[j] = r0 % p.c1;
+          bsh[j] = (tap / 9) | (((tap / 3) % 3) << 2) | ((tap % 3) << 4);
+        }
+        BlockPos bp;
+        bp.set(hb0, p);
         for (long long hb = hb0; hb < hb1; ++hb) {
-          long long q = hb;
-          const int bw = (int)(q % p.hb_w); q /= p.hb_w;
-          const int bh = (int)(q % p.hb_h); q /= p.hb_h;
-          const int dd = (int)(q % p.d); q /= p.d;
-          const int nn = (int)q;
           if (!gt_mbar_wait<32>(EMPTY(stage), phase ^ 1u, abort_flag)) { ok = false; break; }
           const uint32_t pdst = stage0 + (uint32_t)stage * GT_STAGE_BYTES + 3u * GT_ZBYTES;
           mbar_expect_tx(FULL(stage), (uint32_t)n_live * blk_bytes);
-          for (int j = 0; j < n_live; ++j) {
-            const int r0 = nb * GT_BN + j * p.pblk;
-            const int tap = r0 / p.c1, c0 = r0 % p.c1;
-            const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
-            tma_load_5d(pdst + (uint32_t)j * blk_bytes, &pmap, c0, bw * 8 + c - 1, bh * 8 + b - 1, dd + a - 1, nn,
-                        FULL(stage));
+          const int w0 = bp.bw * 8 - 1, h0 = bp.bh * 8 - 1, d0 = bp.dd - 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < n_live)
+              tma_load_5d(pdst + (uint32_t)j * blk_bytes, &pmap, bc0[j], w0 + ((bsh[j] >> 4) & 3), h0 + ((bsh[j] >> 2) & 3),
+                          d0 + (bsh[j] & 3), bp.nn, FULL(stage));
           }
+          bp.next(p);
           if (++stage == GT_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -331,14 +363,15 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
 #pragma unroll
       for (int i = 0; i < GT_PS; ++i) ps[i] = make_slot(nb * GT_BN, rc_base + GT_RCS * i, kvox, p, false);
       const bool p_tma = p.p_tma != 0;
+      const bool single = p.single != 0;
+      const bool mb_patch = mb * GT_BM < p.mx0;       // a row block of weighted codes only (no y / ones rows): lo plane unused when exact
       long long hb0 = (long long)z * p.hb_per_split;
       long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
+      BlockPos bp;
+      bp.set(hb0, p);
       for (long long hb = hb0; hb < hb1; ++hb) {
-        long long q = hb;
-        const int bw = (int)(q % p.hb_w); q /= p.hb_w;
-        const int bh = (int)(q % p.hb_h); q /= p.hb_h;
-        const int dd = (int)(q % p.d); q /= p.d;
-        const int nn = (int)q;
+        const int bw = bp.bw, bh = bp.bh, dd = bp.dd, nn = bp.nn;
+        bp.next(p);
         const int vh = bh * 8 + vy, vw = bw * 8 + vx;
         const bool vlive = vh < p.h && vw < p.w;
         const long long vidx = ((long long)nn * p.d + dd) * plane + (long long)vh * p.w + vw;
@@ -400,13 +433,15 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
             const float p0 = pr[2 * e], p1 = pr[2 * e + 1];
             hi[e] = pack2(p0, p1);                                        // one cvt.rn.bf16x2.f32
             const float r0 = p0 - __uint_as_float(hi[e] << 16), r1 = p1 - __uint_as_float(hi[e] & 0xffff0000u);   // exact
-            lo[e] = pack2(r0, r1);
+            lo[e] = 0;
             l2[e] = 0;
+            if (kind == 1 && single) continue;                            // att * code is exact in bf16: hi is the value
+            lo[e] = pack2(r0, r1);
             if (kind >= 2)                                                // third term: 24 bits in total
               l2[e] = pack2(r0 - __uint_as_float(lo[e] << 16), r1 - __uint_as_float(lo[e] & 0xffff0000u));
           }
           *reinterpret_cast<uint4*>(sbase + zs[i].dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (!(single && mb_patch)) *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           if (kind >= 2) *reinterpret_cast<uint4*>(sbase + 2 * GT_ZBYTES + zs[i].dst) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
         }
         if (!p_tma) {
@@ -489,8 +524,8 @@ extern "C" int effq_gram_tc_supported(const effq_geom* g) {
 // column), row K the bias row, rows K'.. the B0 rows (att*y against the codes) when y != NULL.
 // acc64 must have been zeroed by the caller.
 extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
-                                       const effq_geom* g, int32_t has_bias, double* acc64, int32_t ld,
-                                       void* flags, void* stream) {
+                                       const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
+                                       int32_t ld, void* flags, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && g && acc64 && flags, "null pointer");
   EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
@@ -505,6 +540,7 @@ extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const floa
   p.k = 27 * g->c1;
   p.c2 = g->c2;
   p.has_bias = has_bias ? 1 : 0;
+  p.single = (att_exact || !att) ? 1 : 0;
   p.ld = ld;
   p.mx0 = (p.k + GT_BM - 1) / GT_BM * GT_BM;                      // extras start on a row-block boundary
   const int extra_rows = (has_bias || y) ? 8 + (y ? g->c2 : 0) : 0;

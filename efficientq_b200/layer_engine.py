@@ -164,7 +164,8 @@ class LayerCalibrator:
         if need_gram_tc:
             code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
             a0, b0, self.gram_ws, gram_flag = ops.gram_tc(xcodes, code_scale, out_fp, att, has_bias=has_bias,
-                                                          ws=self.gram_ws)
+                                                          ws=self.gram_ws,
+                                                          att_exact=ops.att_is_exact(att, qlvl_act - 1))
         else:
             a0, b0 = ops.gram(qx, out_fp, att, ksize, stride, padding, has_bias=has_bias, ws=self.gram_ws)
         if dist.world > 1:

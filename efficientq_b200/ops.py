@@ -374,8 +374,27 @@ def gram_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
     return bool(capi.load().effq_gram_tc_supported(C.byref(g)))
 
 
-def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None):
-    """A0, B0 on the tensor cores from the NDHWC codes (3x3x3, stride 1, pad 1)."""
+_att_exact_cache = {}
+
+
+def att_is_exact(att: Optional[torch.Tensor], code_max: int) -> bool:
+    """True when every att * code (code <= code_max) is exactly representable in bf16: integer-valued
+    weights -- the reference truncates its attention map to integers (ptqer.py:160-163) -- with
+    max(att) * code_max <= 256.  One device reduction + read-back per attention map (cached)."""
+    if att is None:
+        return True
+    key = (att.data_ptr(), att._version, tuple(att.shape), int(code_max))
+    if key not in _att_exact_cache:
+        if len(_att_exact_cache) > 64:
+            _att_exact_cache.clear()
+        st = torch.stack([(att == att.round()).all().float(), att.max(), att.min()]).cpu().tolist()
+        _att_exact_cache[key] = bool(st[0] == 1.0 and st[2] >= 0.0 and st[1] * code_max <= 256.0)
+    return _att_exact_cache[key]
+
+
+def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None, att_exact=False):
+    """A0, B0 on the tensor cores from the NDHWC codes (3x3x3, stride 1, pad 1).  ``att_exact``:
+    see att_is_exact (one bf16 term instead of hi + lo for the weighted codes)."""
     y = _f32c(y, "y")
     n, d, h, w, c1 = xcodes.shape
     g = Geom.make((n, c1, d, h, w), y.shape[1], 3, 1, 1)
@@ -393,8 +412,8 @@ def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None):
     od, oh, ow = g.out_spatial()
     flops = 2.0 * g.n * od * oh * ow * (kp + g.c2) * kp
     timer.run("gram_tc", {"flops": flops}, lambda: check(
-        lib.effq_gram_tc(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(has_bias), ptr(a0),
-                         ptr(b0), ptr(ws), stream()), "effq_gram_tc"))
+        lib.effq_gram_tc(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(has_bias), int(bool(att_exact)),
+                         ptr(a0), ptr(b0), ptr(ws), stream()), "effq_gram_tc"))
     flag = ws[need - 16:need - 12].view(torch.int32)       # non-zero if the tcgen05 kernel aborted
     return a0, b0, ws, flag
 

@@ -207,14 +207,18 @@ int effq_quadform_sse(const double* acc64, double sum_y2, const float* gw, const
  * tcgen05 kernel (att and att*y enter as bf16 hi+lo splits of the left operand, the codes are
  * exact); code_scale (device fp32 scalar, activation = code_scale * code) is applied in the
  * finalize pass.  If the kernel aborts (barrier timeout) the word after the accumulator in the
- * workspace is non-zero. */
+ * workspace is non-zero.
+ * att_exact != 0: the caller guarantees that every att * code is exactly representable in bf16
+ * (e.g. the reference's integer-valued attention masks with max(att) * max(code) <= 256, or
+ * att == NULL); the kernel then uses ONE bf16 term for the weighted codes instead of hi + lo
+ * (half the tensor work, same exact result). */
 int effq_gram_tc_supported(const effq_geom* g);
 int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y, const float* att,
-                 const effq_geom* g, int32_t has_bias, float* a0_out, float* b0_out, void* workspace,
-                 void* stream);
+                 const effq_geom* g, int32_t has_bias, int32_t att_exact, float* a0_out, float* b0_out,
+                 void* workspace, void* stream);
 int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
-                            const effq_geom* g, int32_t has_bias, double* acc64, int32_t ld, void* flags,
-                            void* stream);
+                            const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
+                            int32_t ld, void* flags, void* stream);
 
 /* ---- (a9,a11) ADMM parameter update: solver.py:316-325, EfficientQConv.py:99-144 */
 /* B = B0 + eta*W0' ;  B[:, :K] += rho*(G - dual)          (solver.py:317-320) */

@@ -374,6 +374,14 @@ def test_gram_tc_matches_generic_and_oracle(ops, n, c1, c2, sp, la, int_att):
     g0, gb0 = ops.gram(x.to(DEV), y.to(DEV), att.to(DEV), (3, 3, 3), 1, 1, has_bias=True)
     assert (a0 - g0).abs().max().item() <= tol * scale
     assert torch.allclose(b0, gb0, rtol=1e-5, atol=1e-5 * b_ref.abs().max().item())
+    # single-term mode: chosen when every att * code is exact in bf16 (integer masks) -> identical bits
+    att_d = att.to(DEV)
+    exact = ops.att_is_exact(att_d, la - 1)
+    assert exact == (int_att and 3 * (la - 1) <= 256)
+    if exact:
+        a1, b1, _, flag1 = ops.gram_tc(xq, torch.tensor([sc], device=DEV), y.to(DEV), att_d, True, att_exact=True)
+        assert int(flag1.item()) == 0
+        assert torch.equal(a1, a0) and torch.equal(b1, b0)
 
 
 @pytest.mark.parametrize("n,c1,c2,k,s,p,sp", [(2, 4, 32, 3, 2, 1, (16, 16, 16)), (2, 32, 3, 1, 1, 0, (8, 16, 8))])

@@ -25,6 +25,11 @@ class PeerComm(C.Structure):
     _fields_ = [("slots", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
 
 
+class NextRhs(C.Structure):
+    """``effq_next_rhs`` (include/effq_b200.h)."""
+    _fields_ = [("b0", C.c_void_p), ("w0p", C.c_void_p), ("rho", C.c_float), ("eta", C.c_float), ("planes", C.c_void_p)]
+
+
 class Geom(C.Structure):
     """``effq_geom`` (include/effq_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in
@@ -104,7 +109,7 @@ _SIGS = {
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p]),

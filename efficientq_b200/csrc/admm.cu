@@ -81,13 +81,23 @@ __device__ __forceinline__ void store_code(void* base, long long idx, float code
   else reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)__nv_cvt_float_to_fp8(code, __NV_SATFINITE, __NV_E4M3);
 }
 
+// x = x0 + x1 + x2 in bf16 (24 bits), planes `plane` elements apart (as split3_kernel / admm_rhs_kernel)
+__device__ __forceinline__ void store_split3(__nv_bfloat16* planes, long long at, long long plane, float v) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
+  const float r1 = __fsub_rn(v, __bfloat162float(h0));
+  const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+  planes[at] = h0;
+  planes[plane + at] = h1;
+  planes[2 * plane + at] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(h1)));
+}
+
 // Projection + dual update + operand export.           EfficientQConv.py:107-111,131-137
 __global__ void __launch_bounds__(AD_THREADS)
 admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __restrict__ dual,
                     const effq_scale_state* __restrict__ wscale, const effq_scale_state* __restrict__ xscale,
                     int nlvl_w, int nlvl_a, int c2, int c1, int taps, int has_bias, float dual_div,
                     float* __restrict__ g_out, float* __restrict__ bstar_out,
-                    void* __restrict__ wcodes, TcLayout lay, effq_admm_state* st) {
+                    void* __restrict__ wcodes, TcLayout lay, effq_admm_state* st, effq_next_rhs nx, int ldk) {
   const int k = c1 * taps;
   const long long total = (long long)c2 * k;
   const double a64 = wscale->a;
@@ -103,7 +113,15 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
     const float b32 = (float)level_value_d(idx, q);                      // .float()
     const float gq = __fmul_rn(a32, b32);                                // G = a_w * b_w
     g_out[e] = gq;
-    dual[e] = __fdiv_rn(__fadd_rn(__fsub_rn(ws, gq), du), dual_div);     // (w*-G+dual) [/2 on rho steps]
+    const float dn = __fdiv_rn(__fadd_rn(__fsub_rn(ws, gq), du), dual_div);   // (w*-G+dual) [/2 on rho steps]
+    dual[e] = dn;
+    if (nx.planes) {
+      // next iteration's B on the weight columns, op for op as admm_rhs_kernel, split into three bf16 terms
+      const long long be = (long long)r * (k + has_bias) + j;
+      float v = __fadd_rn(nx.b0[be], __fmul_rn(nx.eta, nx.w0p[be]));
+      v = __fadd_rn(v, __fmul_rn(nx.rho, __fsub_rn(gq, dn)));
+      store_split3((__nv_bfloat16*)nx.planes, (long long)r * ldk + j, (long long)c2 * ldk, v);
+    }
     if (wcodes) {
       const int c = j / taps, t = j % taps;
       const float code = (float)(2.0 * idx - (double)(nlvl_w - 1));      // odd integer in [-(L-1), L-1]
@@ -113,6 +131,17 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
   if (has_bias && bstar_out) {
     for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < c2; r += gridDim.x * AD_THREADS)
       bstar_out[r] = wstar[(long long)r * ldw + k];
+  }
+  if (nx.planes) {
+    // bias column (constant B0 + eta*W0') and the zero tail up to the plane pitch
+    const int kp = k + has_bias, tail = ldk - k;
+    for (long long t = (long long)blockIdx.x * AD_THREADS + threadIdx.x; t < (long long)c2 * tail;
+         t += (long long)gridDim.x * AD_THREADS) {
+      const int r = (int)(t / tail), j = k + (int)(t % tail);
+      float v = 0.f;
+      if (j < kp) { const long long be = (long long)r * kp + j; v = __fadd_rn(nx.b0[be], __fmul_rn(nx.eta, nx.w0p[be])); }
+      store_split3((__nv_bfloat16*)nx.planes, (long long)r * ldk + j, (long long)c2 * ldk, v);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && st) {
     st->a_w = a32;
@@ -211,7 +240,7 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
                                  const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                                  int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
                                  float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
-                                 void* stream) {
+                                 const effq_next_rhs* next, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(wstar && dual && wscale && g_out, "null pointer");
   EFFQ_CHECK_ARG(c2 > 0 && c1 > 0 && taps > 0 && ldw >= (int64_t)c1 * taps + (has_bias ? 1 : 0), "bad shape");
@@ -219,9 +248,14 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
                      (code_dtype == CODE_E4M3 && c1 % 16 == 0 && nlvl_w <= 16),
                  "weight codes need c1 % 8 == 0, nlvl_w <= 256 (bf16) or c1 % 16 == 0, nlvl_w <= 16 (e4m3)");
   EFFQ_CHECK_ARG(dual_div != 0.f, "dual_div must be non-zero");
+  EFFQ_CHECK_ARG(!next || (next->b0 && next->w0p && next->planes && ((uintptr_t)next->planes & 15) == 0),
+                 "next right-hand side: null / misaligned pointer");
+  effq_next_rhs nx;
+  if (next) nx = *next; else { nx.b0 = nullptr; nx.w0p = nullptr; nx.rho = 0.f; nx.eta = 0.f; nx.planes = nullptr; }
+  const int ldk = (int)effq_split3_ld((int64_t)c1 * taps + (has_bias ? 1 : 0));
   admm_project_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
       wstar, ldw, dual, wscale, xscale, nlvl_w, nlvl_a, c2, c1, taps, has_bias, dual_div, g_out, bstar_out,
-      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st);
+      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st, nx, ldk);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

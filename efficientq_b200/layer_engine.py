@@ -258,8 +258,9 @@ class LayerCalibrator:
                 rho_built = rho
             # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
             if solve_tc:
-                ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
-                              lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
+                if it == 0:     # later right-hand sides come out of admm_project of the previous iteration
+                    ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
+                                  lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
                 sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
             else:
                 ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
@@ -274,9 +275,10 @@ class LayerCalibrator:
                     new_rho, div = rho * 2, 2.0
                 else:
                     new_rho, div = rho_m, rho_m / rho
+            nxt = (b0, w0p, new_rho, eta, bplanes) if (solve_tc and it + 1 < self.n_iter) else None
             ops.timer.run("admm_project", {"bytes": 16 * c2 * k}, lambda: ops.admm_project(
                 sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps, has_bias, div,
-                g, bstar, wcodes, self.st))
+                g, bstar, wcodes, self.st, next_rhs=nxt))
             # score the iterate (EfficientQConv.py:118-122)
             if use_tc:
                 ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,

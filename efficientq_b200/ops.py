@@ -477,12 +477,19 @@ def admm_lhs(a0, rho: float, eta: float, has_bias: bool, out):
 
 def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], nlvl_w: int, nlvl_a: int,
                  c2: int, c1: int, taps: int, has_bias: bool, dual_div: float, g_out, bstar_out, wcodes_out,
-                 st: AdmmState):
+                 st: AdmmState, next_rhs=None):
+    """``next_rhs`` = (b0, w0p, rho_next, eta, planes): also emit the next iteration's right-hand side
+    as split planes (replaces the next admm_rhs launch)."""
     ldw = wstar.stride(0)
+    nx = None
+    if next_rhs is not None:
+        b0, w0p, rho_n, eta, planes = next_rhs
+        nx = C.byref(capi.NextRhs(b0.data_ptr(), w0p.data_ptr(), float(rho_n), float(eta), planes.data_ptr()))
     check(capi.load().effq_admm_project(ptr(wstar), ldw, ptr(dual), wstate.p, xstate.p if xstate else None,
                                         int(nlvl_w), int(nlvl_a), c2, c1, taps, int(has_bias), float(dual_div),
                                         ptr(g_out), ptr(bstar_out), ptr(wcodes_out),
-                                        code_dtype_of(wcodes_out) if wcodes_out is not None else 0, st.p, stream()),
+                                        code_dtype_of(wcodes_out) if wcodes_out is not None else 0, st.p, nx,
+                                        stream()),
           "effq_admm_project")
 
 

@@ -248,11 +248,22 @@ int effq_admm_lhs(const float* a0, float rho, float eta, int32_t kp, int32_t has
 /* After the scale search on (w* + dual): G = a_w*b_w ; dual = (w* - G + dual)/dual_div;
  * b* = last column of w*; emits fp32 G (reference layout) and, if wcodes_out != NULL,
  * weight codes of `code_dtype` in the tensor-core layout; updates st->conv_scale / st->a_w. */
+/* next != NULL: the same pass also assembles the NEXT iteration's right-hand side
+ * B = B0 + eta*W0' (+ rho*(G - dual) on the weight columns) from the G and dual it just produced and
+ * writes it as the three bf16 planes effq_solve_gemm_tc consumes (what effq_admm_rhs(..., planes_out)
+ * would write; saves that launch and a re-read of G and dual). */
+typedef struct effq_next_rhs {
+  const float* b0;      /* [C2][K'] */
+  const float* w0p;     /* [C2][K'] */
+  float        rho;     /* rho of the NEXT iteration */
+  float        eta;
+  void*        planes;  /* [3][C2][effq_split3_ld(K')] bf16 */
+} effq_next_rhs;
 int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
                       const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                       int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
                       float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
-                      void* stream);
+                      const effq_next_rhs* next, void* stream);
 /* loss = fp32(sse/numel); history[iter] = loss; if (iter==0 || loss < best) keep G, b*
  * (and, when aux_bytes > 0, the 16B-aligned side buffer aux_src -> aux_dst, e.g. the
  * tensor-core weight codes of the same iterate). */

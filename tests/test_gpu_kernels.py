@@ -439,7 +439,14 @@ def test_admm_elementwise_kernels(ops):
     ops.scale_search(sol_d[:, :k], 16, -1.0, 1.0, wst, v2=dual_d)
     g_d, bstar = torch.empty(c2, k, device=DEV), torch.empty(c2, device=DEV)
     wcodes = torch.empty(taps * (c1 // 8) * c2 * 8, dtype=torch.bfloat16, device=DEV)
-    ops.admm_project(sol_d, dual_d, wst, xst, 16, 16, c2, c1, taps, True, 2.0, g_d, bstar, wcodes, st)
+    # fused assembly of the NEXT right-hand side (what admm_rhs would produce from the new G / dual)
+    b0n, w0n = torch.randn(c2, c1 * taps + 1, device=DEV), torch.randn(c2, c1 * taps + 1, device=DEV)
+    nplanes = torch.empty((3, c2, ops.split3_ld(c1 * taps + 1)), dtype=torch.bfloat16, device=DEV)
+    ops.admm_project(sol_d, dual_d, wst, xst, 16, 16, c2, c1, taps, True, 2.0, g_d, bstar, wcodes, st,
+                     next_rhs=(b0n, w0n, 20.0, 1.5, nplanes))
+    want_planes = torch.empty_like(nplanes)
+    ops.admm_rhs(b0n, w0n, g_d, dual_d, 20.0, 1.5, None, planes=want_planes)
+    assert torch.equal(nplanes, want_planes)
     assert torch.equal(g_d.cpu(), g_ref)
     assert torch.equal(dual_d.cpu(), dual_ref)
     assert torch.equal(bstar.cpu(), sol[:, k])

@@ -137,7 +137,8 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
 # same kernel at the same shape (profiles/r01_layer_ncu.md); None = not captured.
 NCU_TRAFFIC_BYTES = {
-    "conv3d_tc_c32x32k3": 1.80e9,        # 32 x 32ch x 64^3: algorithmic 1.611 GB (codes 0.537 + fp32 target 1.074)
+    "conv3d_tc_c32x32k3_e4m3": 1.391e9,  # 32 x 32ch x 64^3: algorithmic 1.342 GB (e4m3 codes 0.268 + fp32 target 1.074)
+    "conv3d_tc_c32x32k3": 1.615e9,       # same layer, bf16 codes: algorithmic 1.611 GB
 }
 
 

@@ -168,14 +168,15 @@ struct BlockPos {
   }
 };
 
-// item -> (voxel range z, column block nb, row block mb), voxel range SLOWEST: the CTAs that run
-// concurrently work on the same few voxel ranges for all tile pairs, so the codes of a range come
-// from DRAM once and from L2 for the other ~20 tile pairs (tile-pair-major order re-read the whole
-// tensor per pair: 23 GB of DRAM traffic against 1.6 GB algorithmic, ncu).
+// item -> (voxel range z, column block nb, row block mb), voxel range FASTEST: concurrently running
+// CTAs work on different voxel ranges of the same tile pair.  (The voxel-range-slowest order, which
+// lets the ~20 tile pairs of a range share it through L2, cut the DRAM reads -- 23 GB per launch
+// against 1.6 GB algorithmic, ncu -- but ran 16 % slower: DRAM is at 10 % of its peak here, and the
+// mixed order puts the slow three-term row blocks and the fp64 epilogue atomics of all tiles in
+// flight at once.  profiles/r01_layer_ncu.md)
 __device__ __forceinline__ void gt_decode(long long item, const GtParams& p, int& z, int& nb, int& mb) {
-  const long long tiles = (long long)p.mb_n * p.nb_n;
-  const long long t = item % tiles;
-  z = (int)(item / tiles);
+  z = (int)(item % p.splits);
+  const long long t = item / p.splits;
   nb = (int)(t % p.nb_n);
   mb = (int)(t / p.nb_n);
 }

@@ -35,7 +35,11 @@ WORKLOADS = {
     "brats_w4a4_32x128": dict(n=32, size=(128, 128, 128), lw=16, la=16, task="brats"),
     "brats_w4a4_8x64": dict(n=8, size=(64, 64, 64), lw=16, la=16, task="brats"),
     "brats_w4a4_2x64": dict(n=2, size=(64, 64, 64), lw=16, la=16, task="brats"),
+    # BASELINE configs[2]: LiTS-config 1-channel CT net (28 quantizer layers, widths 32..512, init_stride 2,2,1),
+    # W2A2 = 4/4 levels, 1x160x160x64 volumes.  A parity / coverage case, not the headline line.
+    "lits_w2a2_4x160": dict(n=4, size=(160, 160, 64), lw=4, la=4, task="lits"),
 }
+N_MOD = {"brats": 4, "lits": 1}
 METRIC = "ptq_calibration_throughput"
 UNIT = "volumes/s"
 
@@ -44,10 +48,10 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def brats_args(wl):
+def task_args(wl):
     from efficientq_b200 import entrance
     a = entrance.build_parser().parse_args(["ptq", "--qlvl_w", str(wl["lw"]), "--qlvl_a", str(wl["la"]),
-                                            "--config", os.path.join(ROOT, "config", "brats_ptq.yaml")])
+                                            "--config", os.path.join(ROOT, "config", f"{wl['task']}_ptq.yaml")])
     a = entrance.merge_config(a.config, a)
     a.data_dir = "synthetic"
     a.lwq_patchsz = ",".join(str(s) for s in wl["size"])
@@ -82,7 +86,7 @@ def seeded_state(model, seed=16):
 
 def build_model(wl):
     from efficientq_b200 import definer, fold_bn
-    args = brats_args(wl)
+    args = task_args(wl)
     QConv, _, kwQ = definer.get_conv_class(args)
     cube, _ = definer.get_model_cube(args, QConv, kwQ)
     model = cube["model"]
@@ -172,7 +176,7 @@ def cpu_sample(wl, iters=1, threads=None, edge_div=2):
     vox_scale = 1.0
     for a, b in zip(wl["size"], size):
         vox_scale *= a / b
-    x = synth.batch(1, 0, 4, size, wl["task"])
+    x = synth.batch(1, 0, N_MOD[wl["task"]], size, wl["task"])
     feats = {}
     hooks = []
     for name, m in model.named_modules():
@@ -185,9 +189,11 @@ def cpu_sample(wl, iters=1, threads=None, edge_div=2):
     for h in hooks:
         h.remove()
     timers = {}
+    n_layers = 0
     for name, m in model.named_modules():
         if not isinstance(m, PTQConv):
             continue
+        n_layers += 1
         xi, yo = feats.pop(name)
         O.admm_layer(xi, m.weight.data, m.bias.data, yo, m.stride, m.padding, m.qlvl_w, m.qlvl_act, m.q_act,
                      None, n_iter=iters, timers=timers)
@@ -196,7 +202,7 @@ def cpu_sample(wl, iters=1, threads=None, edge_div=2):
     full = v * (timers.get("act_search", 0) + timers.get("im2col_gram", 0)) + \
         200.0 / iters * (timers.get("solve", 0) + timers.get("w_project", 0) + v * timers.get("conv_mse", 0))
     spent = time.perf_counter() - t_begin
-    desc = (f"oracle port on {threads} threads, all 22 layers, one {size} volume (1/{vox_scale:.0f} of a "
+    desc = (f"oracle port on {threads} threads, all {n_layers} layers, one {size} volume (1/{vox_scale:.0f} of a "
             f"{wl['size']} volume), {iters} of 200 ADMM iterations; phases(s) "
             f"{json.dumps({k: round(t, 3) for k, t in timers.items()})}; scaled with V={v:.0f}: "
             f"V*(act+gram)+200/{iters}*(solve+wproj+V*conv) = {full:.0f}s for {n} volumes")
@@ -244,7 +250,7 @@ def run_ours(args, wl, wl_name):
     fp_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     n_local = wl["n"]
     t0 = time.time()
-    host_batch = synth.batch(n_local, dist.rank * n_local, 4, wl["size"], wl["task"], pin=True)
+    host_batch = synth.batch(n_local, dist.rank * n_local, N_MOD[wl["task"]], wl["size"], wl["task"], pin=True)
     log(f"[rank {dist.rank}] synthetic batch {tuple(host_batch.shape)} in {time.time() - t0:.1f}s")
     dev_batch = torch.empty(host_batch.shape, dtype=torch.float32, device=dev)
     h2d = host_batch.numel() * 4
@@ -355,7 +361,7 @@ def run_ours(args, wl, wl_name):
             "vs_baseline": None, "dtype": "e4m3" if ops.fp8_codes_enabled() and wl["la"] <= 16 and wl["lw"] <= 16 else "bf16",
             "data": "synthetic",
             "config": {"workload": wl_name, "volumes_per_gpu": n_local, "volume": list(wl["size"]),
-                       "levels_w": wl["lw"], "levels_a": wl["la"], "admm_iters": 200, "layers": 22,
+                       "levels_w": wl["lw"], "levels_a": wl["la"], "admm_iters": 200, "layers": len(res["reports"]),
                        "l2": "inputs_larger_than_l2", "parallelism": f"dp{dist.world} (volumes sharded)"},
             "ptq_wall_s": dev_ms / args.steps / 1e3,
             "fp_pass_s": res.get("t_fp"), "quantizing_pass_s": res.get("t_ptq"),

@@ -37,6 +37,8 @@ class LayerReport:
     used_tc: bool = False
     history: Optional[List[float]] = None
     factorizations: int = 0
+    fp64_factor: bool = False        # fp32 Cholesky hit a non-positive pivot -> this layer's systems went to fp64
+    lu_factor: bool = False          # ... and fp64 Cholesky failed too -> fp64 LU (the reference's own method)
 
 
 def select_att(mask_pyramid: Optional[Sequence[torch.Tensor]], out_spatial) -> Optional[torch.Tensor]:
@@ -144,7 +146,13 @@ class LayerCalibrator:
         # <= 16 levels on both sides: the conv runs on e4m3 codes (exact, K = 32 per tcgen05.mma)
         use_fp8 = use_tc and ops.fp8_codes_enabled() and qlvl_act <= 16 and qlvl_w <= 16 and \
             ops.conv3d_tc_supported(x.shape, c2, ksize, stride, padding, ops.CODE_E4M3)
-        need_gram_tc = use_tc and ops.gram_tc_supported(x.shape, c2, ksize, stride, padding)
+        # normal-equation statistics on the tensor cores from the integer codes whenever the geometry
+        # allows, also when the scoring conv cannot take the tcgen05 path (C2 > 256: LiTS 512-channel
+        # level).  Besides speed this keeps A0 = 2 s^2 (exact integer Gram): an fp32 Gram of the scaled
+        # values rounds every product of the same code pair the same way, a coherent perturbation of
+        # ~1e-7 lambda_max that made A indefinite at that level (V = 400 voxels, K' = 13825 unknowns).
+        need_gram_tc = (not self.force_generic) and q_act and qlvl_act <= 256 and \
+            ops.gram_tc_supported(x.shape, c2, ksize, stride, padding)
         alpha_act = None
         xcodes = xcodes_conv = None
         if q_act:
@@ -156,6 +164,8 @@ class LayerCalibrator:
                                                              e4m3=True)
             elif use_tc:
                 xcodes = xcodes_conv = ops.quantize_act_ndhwc(x, qlvl_act, state=self.xstate)
+            elif need_gram_tc:
+                xcodes = ops.quantize_act_ndhwc(x, qlvl_act, state=self.xstate)
         else:
             qx = x
 
@@ -217,12 +227,36 @@ class LayerCalibrator:
         # (fp32-class accuracy, csrc/solve_gemm_tc.cu); smaller systems stay on the library SGEMM
         solve_tc = kp >= 256 and not self.force_generic and os.environ.get("EFFQ_SOLVE_TC", "1") != "0"
         with torch.cuda.stream(self._side):
-            for r_ in rhos:
+            use64 = False
+            for idx, r_ in enumerate(rhos):
                 a_r = torch.empty_like(amat)
                 ops.admm_lhs(a0, r_, eta, has_bias, a_r)
-                chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
-                                           lambda: torch.linalg.cholesky_ex(a_r))
-                if solve_tc and kp >= 1024 and os.environ.get("EFFQ_INV_TC", "1") != "0":
+                if not use64:
+                    chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
+                                               lambda: torch.linalg.cholesky_ex(a_r))
+                    # The smallest rho is the worst-conditioned system.  With fewer voxels than unknowns
+                    # (LiTS deepest level: V = 400, K' = 13825) cond(A) = lambda_max(A0)/(rho+eta) reaches
+                    # 1e8+ and an fp32 pivot can come out negative: check it once (one sync per layer, on
+                    # the side stream) and, if so, factorise and invert every A of this layer in fp64.
+                    if idx == 0 and int(info.item()) != 0:
+                        use64 = True
+                        rep.fp64_factor = True
+                if use64:
+                    a64 = a_r.double()
+                    chol64, info = ops.timer.run("lib_cholesky_f64", {"flops": kp ** 3 / 3.0},
+                                                 lambda: torch.linalg.cholesky_ex(a64))
+                    if int(info.item()) != 0:
+                        # not positive definite even in fp64 (A0 itself is off by more than rho + eta):
+                        # LU, which is what the reference's torch.linalg.solve does (solver.py:331)
+                        inv64, info = ops.timer.run("lib_lu_inverse_f64", {"flops": 2.0 * kp ** 3},
+                                                    lambda: torch.linalg.inv_ex(a64))
+                        rep.lu_factor = True
+                    else:
+                        inv64 = ops.timer.run("lib_cholesky_inverse_f64", {"flops": 2.0 * kp ** 3 / 3.0},
+                                              lambda: torch.cholesky_inverse(chol64))
+                    inv_r = inv64.float()
+                    del a64, chol64, inv64
+                elif solve_tc and kp >= 1024 and os.environ.get("EFFQ_INV_TC", "1") != "0":
                     # A^-1 = L^-T L^-1: one library TRSM for W = L^-1, then W^T W on the tensor cores
                     # (the library's potri runs at ~5 TFLOP/s and was the largest item of the step)
                     eye = self._eye(kp, dev)
@@ -312,14 +346,17 @@ class LayerCalibrator:
         alpha_w = self.st.a_w_tensor().clone()     # LAST iterate's scale (reference quirk, :158)
         s = self.st.read()                          # the layer's one result read-back
         final_sse = float(self.sse.item())
-        if final_sse != final_sse:
-            raise ops.EffqError(f"{name}: tcgen05 conv aborted (barrier timeout)")
         if any(int(i.item()) != 0 for i in infos):
-            raise ops.EffqError(f"{name}: normal matrix not numerically SPD (cholesky failed)")
+            raise ops.EffqError(f"{name}: normal matrix is numerically singular (factorisation failed"
+                                f"{', fp64 LU included' if rep.lu_factor else ''})")
         if solve_tc and int(self._sg_ws[:4].view(torch.int32)[0].item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 solve GEMM aborted (barrier timeout)")
         if gram_flag is not None and int(gram_flag.item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 Gram kernel aborted (barrier timeout)")
+        if final_sse != final_sse:
+            raise ops.EffqError(f"{name}: non-finite reconstruction error"
+                                + (" (tcgen05 conv aborted on a barrier timeout, or non-finite inputs)" if use_tc
+                                   else " (non-finite inputs or proximal step)"))
         rep.final_loss = final_sse / numel_total
         if s["last_loss"] != s["last_loss"]:
             raise ops.EffqError(f"{name}: NVLink peer exchange timed out (a rank is missing or out of step)")

@@ -233,6 +233,11 @@ def gen_layers_wide(R, out):
 TOY = dict(num_mod=4, num_classes=3, depth=[1, 1, 1], width=[8, 16, 8], dilation=[1, 1, 1],
            init_stride=(2, 2, 2), drop_rate=0.5, ds="simple", blk="mid", qlvl=16, qlvl_act=16,
            q_first=[256, -1], q_last=[256, -1], n=2, size=64, task="brats", seed=16)
+# LiTS-config miniature (config/lits_ptq.yaml): 1 CT channel, init_stride 2,2,1, anisotropic volume,
+# W2A2 (4/4 levels), softmax/argmax prediction, body mask all ones
+TOY_LITS = dict(num_mod=1, num_classes=3, depth=[1, 1, 1], width=[8, 16, 8], dilation=[1, 1, 1],
+                init_stride=(2, 2, 1), drop_rate=0.5, ds="simple", blk="mid", qlvl=4, qlvl_act=4,
+                q_first=[256, -1], q_last=[256, -1], n=2, size=(96, 64, 32), task="lits", seed=18)
 
 
 def build_toy(R, QConv, cfg=TOY):
@@ -273,17 +278,17 @@ def seeded_state(model, seed):
     return sd
 
 
-def gen_toy_net(R, out):
+def gen_toy_net(R, out, cfg=TOY, fname="toy_net.npz"):
     """The do_ptq core (reference src/ptqer.py:289-364) on a toy UResQ, CPU."""
     from efficientq_b200 import synth
     ptqer = R["ptqer"]
-    cfg = TOY
-    model = build_toy(R, R["effq"].EfficientQConv)
+    model = build_toy(R, R["effq"].EfficientQConv, cfg)
     sd = seeded_state(model, cfg["seed"])
     model.load_state_dict(sd, strict=False)
     model.eval()
     R["fold_bn"].search_fold_and_remove_bn(model)
-    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
+    size = cfg["size"] if isinstance(cfg["size"], tuple) else (cfg["size"],) * 3
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], size, cfg["task"])
     ptqer.set_name(model)
     ptqer.set_fp(model)
     handles = []
@@ -292,9 +297,12 @@ def gen_toy_net(R, out):
             handles.append(m.register_forward_hook(R["hooks"].forward_hook))
     with torch.no_grad():
         output_fp = model(data).detach()
-    body = (data[:, 0] != 0.0).bool()
-    wmap, nums = ptqer.get_att_weight_map(output_fp, torch.ones_like(data[:, 0]).bool(), "p:0.5", task="brats")
-    pyr = ptqer.get_mask_pyramid(output_fp, body, wmap, "2,2,2", num_lvls=5, task="brats")
+    task = cfg["task"]
+    # ptqer.py:337-340: BraTS body = non-zero voxels of modality 0, LiTS body = everything
+    body = (data[:, 0] != 0.0).bool() if task == "brats" else torch.ones_like(data[:, 0]).bool()
+    wmap, nums = ptqer.get_att_weight_map(output_fp, torch.ones_like(data[:, 0]).bool(), "p:0.5", task=task)
+    pyr = ptqer.get_mask_pyramid(output_fp, body, wmap, ",".join(str(v) for v in cfg["init_stride"]),
+                                 num_lvls=5, task=task)
     ptqer.set_mask(model, pyr)
     for h in handles:
         h.remove()
@@ -329,7 +337,11 @@ def gen_toy_net(R, out):
             res[f"q::{name}.wint"] = m.weight.data.numpy()
     for k, v in zip(names, losses):
         print(f"{k:45s} {v:.6e}")
-    np.savez_compressed(os.path.join(out, "toy_net.npz"), **res)
+    np.savez_compressed(os.path.join(out, fname), **res)
+
+
+def gen_toy_net_lits(R, out):
+    gen_toy_net(R, out, TOY_LITS, "toy_net_lits.npz")
 
 
 def main():
@@ -340,7 +352,8 @@ def main():
     torch.manual_seed(0)
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
-                solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net)
+                solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
+                toy_net_lits=gen_toy_net_lits)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

@@ -345,6 +345,7 @@ GRAM_TC_CASES = [
     (1, 16, 24, (5, 10, 12), 4, False),       # ragged 8x8 blocks, partial 128/256-row blocks
     (1, 128, 16, (2, 8, 8), 16, True),
     (3, 32, 8, (3, 9, 7), 256, False),
+    (2, 256, 16, (3, 5, 4), 4, True),         # LiTS deep level: volume smaller than one 8x8 block, V << K' = 6913
 ]
 
 

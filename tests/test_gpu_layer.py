@@ -99,9 +99,10 @@ def test_layer_calibration_e4m3_equals_bf16(engine_mod, golden, name, monkeypatc
     assert float(aw1) == float(aw0) and float(aa1) == float(aa0)
 
 
-def build_toy():
+def build_toy(task="brats"):
     from efficientq_b200 import model_blk, qconv
-    from tests.golden.make_golden import TOY as cfg
+    from tests.golden.make_golden import TOY, TOY_LITS
+    cfg = TOY if task == "brats" else TOY_LITS
     hetero = {"drop_cut_thres": 128, "ds_depth_limit": 3, "aniso_pool_depth": 9999, "aniso_pool_stride": (2, 2, 1)}
     return model_blk.UResQ(qconv.EfficientQConv, cfg["num_mod"], cfg["num_classes"], depth_config=cfg["depth"],
                            width_config=cfg["width"], dilation_config=cfg["dilation"], init_stride=cfg["init_stride"],
@@ -111,20 +112,24 @@ def build_toy():
                            hetero_param=hetero, fuse_bn=True, save_mem=True, init_kernel=3), cfg
 
 
-def test_toy_network_matches_reference(engine_mod, golden):
+@pytest.mark.parametrize("task", ["brats", "lits"])
+def test_toy_network_matches_reference(engine_mod, golden, task):
+    """do_ptq core on a miniature of the BraTS config (4 modalities, cubic, W4A4) and of the LiTS config
+    (1 CT channel, init_stride 2,2,1, anisotropic volume, W2A2, softmax prediction, all-ones body mask)."""
     from efficientq_b200 import fold_bn, ptqer, synth
-    g = golden("toy_net.npz")
-    model, cfg = build_toy()
+    g = golden("toy_net.npz" if task == "brats" else "toy_net_lits.npz")
+    model, cfg = build_toy(task)
     sd = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}
     model.load_state_dict(sd, strict=False)
     model.eval()
     fold_bn.search_fold_and_remove_bn(model)
     model.to(DEV)
-    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
+    size = cfg["size"] if isinstance(cfg["size"], tuple) else (cfg["size"],) * 3
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], size, cfg["task"])
     assert abs(data.double().sum().item() - float(g["data_checksum"])) < 1e-6
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    res = ptqer.calibrate(model, data.to(DEV), "brats", "2,2,2")
+    res = ptqer.calibrate(model, data.to(DEV), task, ",".join(str(v) for v in cfg["init_stride"]))
     assert res["class_nums"] == [int(v) for v in g["class_nums"]]
     np.testing.assert_allclose([p.mean().item() for p in res["pyramid"]], g["pyr_means"], rtol=1e-6)
     names = [ln.rsplit(":", 1)[0].strip() for ln in res["layer_loss"]]
@@ -135,12 +140,21 @@ def test_toy_network_matches_reference(engine_mod, golden):
     print("\n".join(lines))
     import os
     if os.path.isdir("gpurun_out"):
-        with open("gpurun_out/toy_net_parity.txt", "w") as fid:
+        with open("gpurun_out/toy_net_parity.txt" if task == "brats" else "gpurun_out/toy_net_lits_parity.txt", "w") as fid:
             fid.write("\n".join(lines) + f"\nt_fp {res['t_fp']:.3f}s t_ptq {res['t_ptq']:.3f}s\n")
     # layer 1 sees identical inputs -> 1e-3; later layers inherit the (chaotic) quantised
     # prefix, tolerance documented in DESIGN.md
     assert abs(losses[0] - ref[0]) <= 1e-3 * ref[0]
-    np.testing.assert_allclose(losses, ref, rtol=5e-2)
+    if task == "brats":
+        np.testing.assert_allclose(losses, ref, rtol=5e-2)
+    else:
+        # W2A2: 4-level codes make the trajectory far more sensitive to one flipped code.  The REFERENCE run
+        # with 1 CPU thread instead of 8 reproduces layers 1-4 to 8e-6 and then moves by 5.7e-3, 8.1e-3,
+        # 4.5e-3, 3.9e-3, 2.7e-2, 6.5e-2 on layers 5-10 (profiles/r01_parity.txt, "LiTS miniature").
+        # Bars: layers 1-4 tight, 5-6 at 2e-2, the rest at ~3x the reference's own two-run spread.
+        np.testing.assert_allclose(losses[:4], ref[:4], rtol=1e-4)
+        np.testing.assert_allclose(losses[4:6], ref[4:6], rtol=2e-2)
+        np.testing.assert_allclose(losses[6:], ref[6:], rtol=0.25)
 
 
 @pytest.mark.parametrize("c1,c2,k", [(32, 32, 3), (64, 32, 1), (16, 48, 3)])

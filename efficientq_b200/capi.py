@@ -113,6 +113,11 @@ _SIGS = {
     "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p]),
+    "effq_ste_bwd_workspace": (C.c_int64, []),
+    "effq_fakequant_ste_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                 C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "effq_peer_bytes": (C.c_int64, []),
     "effq_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
     "effq_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -500,3 +500,40 @@ def admm_track(st: AdmmState, sse, numel: float, g, bstar, best_g, best_b, histo
     check(capi.load().effq_admm_track(st.p, ptr(sse), float(numel), ptr(g), ptr(bstar), g.numel(),
                                       g.shape[0], ptr(best_g), ptr(best_b), ptr(history), ptr(aux_src),
                                       ptr(aux_dst), nb, comm, stream()), "effq_admm_track")
+
+
+# ---------------------------------------------------------------------------
+# (a15) end-to-end activation-range refinement: STE backward + Adam
+# ---------------------------------------------------------------------------
+_ste_ws = {}
+
+
+def fakequant_ste_bwd(x: torch.Tensor, grad_out: torch.Tensor, alpha: torch.Tensor, nlvl: int, lo: float, hi: float,
+                      grad_alpha_acc: torch.Tensor, want_grad_x: bool = True) -> Optional[torch.Tensor]:
+    """Backward of discretize(x/alpha)*alpha under the reference's STE (layer_helper.py:13-37):
+    returns grad_x (or None) and ADDS d loss / d alpha into the 0-dim/1-element fp64 ``grad_alpha_acc``."""
+    x = _f32c(x, "x")
+    grad_out = _f32c(grad_out, "grad_out")
+    alpha = _f32c(alpha.reshape(1), "alpha")
+    if grad_alpha_acc.dtype != torch.float64 or not grad_alpha_acc.is_cuda:
+        raise EffqError("grad_alpha_acc must be a CUDA float64 tensor")
+    lib = capi.load()
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    if key not in _ste_ws:
+        _ste_ws[key] = workspace(lib.effq_ste_bwd_workspace(), x.device)
+    gx = torch.empty_like(x) if want_grad_x else None
+    timer.run("fakequant_ste_bwd", {"bytes": x.numel() * (8 + (4 if want_grad_x else 0))}, lambda: check(
+        lib.effq_fakequant_ste_bwd(ptr(x), ptr(grad_out), x.numel(), ptr(alpha), float(lo), float(hi), int(nlvl),
+                                   ptr(gx), ptr(grad_alpha_acc), ptr(_ste_ws[key]), stream()),
+        "effq_fakequant_ste_bwd"))
+    return gx
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    """torch.optim.Adam's update of a flat fp32 parameter vector from fp64 gradients, one launch."""
+    if params.dtype != torch.float32 or grads.dtype != torch.float64 or not params.is_contiguous():
+        raise EffqError("adam_step: params fp32 contiguous, grads fp64")
+    check(capi.load().effq_adam_step(ptr(params), ptr(grads), float(grad_scale), ptr(exp_avg), ptr(exp_avg_sq),
+                                     params.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                     stream()), "effq_adam_step")

@@ -210,6 +210,12 @@ def do_ptq(args, model_cube, data_cube, tester, snap_dir, dist: Optional[DistCtx
         tester.test_as_is(folder="fp", is_save_nii=getattr(args, "save_nii", False))
     res = calibrate(model, data_batch, args.task, args.init_stride, dist)
     print(f"FP forward costs {res['t_fp']:.3f}s, PTQ costs {res['t_ptq']:.3f}s, totally {res['t_total']:.3f}s.")
+    n_tune = int(getattr(args, "lwq_tune_iter", 0) or 0)
+    if n_tune > 0:                                       # optional: reference ptqer.py:238-272
+        from .tune import tune_activation_range
+        res["tune_losses"] = tune_activation_range(model, res["output_fp"], data_batch, max_iter=n_tune, dist=dist)
+        print(f"alpha_act refinement: loss {res['tune_losses'][0]:.6g} -> {res['tune_losses'][-1]:.6g} "
+              f"in {n_tune} Adam iterations")
     if dist.rank == 0 and snap_dir:
         os.makedirs(snap_dir, exist_ok=True)
         with open(P.join(snap_dir, "class_voxel_nums.txt"), "w") as fid:

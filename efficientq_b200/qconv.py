@@ -40,6 +40,7 @@ class PTQConv(nn.Conv3d):
         self._fp, self._quantizing, self._quantized, self._init_act = True, False, False, False
         self._act_inited = False
         self._wcodes_cache = None
+        self._tune_ctx = None            # set by tune.tune_activation_range while alpha_act is being refined
 
     # -- mode machine (PTQConv.py:44-72) ------------------------------------------------
     def _mode(self, fp=False, quantizing=False, quantized=False, init_act=False):
@@ -112,14 +113,28 @@ class PTQConv(nn.Conv3d):
         return out
 
     def _weight_codes(self, code_dtype=ops.CODE_BF16):
-        """Weight codes 2c-(L-1) of the stored fake-quant weights in the tensor-core layout
-        (c = round((w/alpha_w + 1)/delta), PTQConv.py:131-134); cached until the weights change."""
-        key = (self.weight.data_ptr(), self.weight._version, float(self.alpha_w.item()), code_dtype)
+        """(codes, scale) of the stored fake-quant weights for the tensor-core conv: odd integers
+        2c-(L-1) in the tensor-core layout and the grid scale a with  weight == a * codes / (L-1)  exactly,
+        or None when the weights do not lie on a symmetric L-level grid.  The scale is recovered from the
+        weights themselves, NOT from alpha_w: after calibration alpha_w is the LAST iterate's scale while
+        the weights come from the BEST iterate (reference quirk, EfficientQConv.py:155-158), and the
+        reference's quantized forward uses the stored weights as they are (PTQConv.py:163-167).
+        Cached until the weights change (one host read per weight version)."""
+        key = (self.weight.data_ptr(), self.weight._version, code_dtype)
         if self._wcodes_cache is None or self._wcodes_cache[0] != key:
-            _, c = ops.fakequant(self.weight.data, self.alpha_w.data, self.qlvl_w, -1.0, 1.0,
-                                 want_values=False, want_codes=True)
-            codes = 2.0 * c.float() - float(self.qlvl_w - 1)
-            self._wcodes_cache = (key, ops.pack_weight_codes(codes, code_dtype))
+            w = self.weight.data.float()
+            lm1 = float(self.qlvl_w - 1)
+            wmax = w.abs().max()
+            found = None
+            for k in range(self.qlvl_w - 1, max(self.qlvl_w - 9, 0), -2):     # largest |code| present: L-1, L-3, ...
+                a = wmax * (lm1 / k)
+                codes = torch.round(w / a * lm1)
+                odd = torch.remainder(codes + lm1, 2.0) == 0
+                exact = (codes * (a / lm1) - w).abs().max() <= 1e-6 * wmax
+                if bool((odd.all() & exact & (wmax > 0)).item()):
+                    found = (ops.pack_weight_codes(codes, code_dtype), a.reshape(1).clone())
+                    break
+            self._wcodes_cache = (key, found)
         return self._wcodes_cache[1]
 
     def _quantized_forward(self, x):
@@ -133,16 +148,18 @@ class PTQConv(nn.Conv3d):
             fp8 = ops.fp8_codes_enabled() and self.qlvl_act <= 16 and self.qlvl_w <= 16 and \
                 ops.conv3d_tc_supported(x.shape, self.out_channels, self.kernel_size, self.stride, self.padding,
                                         ops.CODE_E4M3)
-            if fp8:
-                _, xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data, bf16=False, e4m3=True)
-            else:
-                xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data)
-            wcodes = self._weight_codes(ops.CODE_E4M3 if fp8 else ops.CODE_BF16)
-            scale = (self.alpha_act.data.double() / (self.qlvl_act - 1) *
-                     self.alpha_w.data.double() / (self.qlvl_w - 1)).float().reshape(1)
-            out, _ = ops.conv3d_tc(xcodes, wcodes, self.bias.data if self.bias is not None else None,
-                                   scale, self.out_channels, self.kernel_size, want_out=True)
-            return out
+            wc = self._weight_codes(ops.CODE_E4M3 if fp8 else ops.CODE_BF16)
+            if wc is not None:                  # weights on an exact L-level grid (always, after calibration)
+                wcodes, w_scale = wc
+                if fp8:
+                    _, xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data, bf16=False, e4m3=True)
+                else:
+                    xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data)
+                scale = (self.alpha_act.data.double() / (self.qlvl_act - 1) *
+                         w_scale.double() / (self.qlvl_w - 1)).float().reshape(1)
+                out, _ = ops.conv3d_tc(xcodes, wcodes, self.bias.data if self.bias is not None else None,
+                                       scale, self.out_channels, self.kernel_size, want_out=True)
+                return out
         qact = self._quantize_act(x) if self.q_act else x
         return self._conv(qact)
 
@@ -152,6 +169,8 @@ class PTQConv(nn.Conv3d):
         if self._quantizing:
             return self.ptq(x)                      # returns conv3d(qact, weight*, bias*) of the calibrated layer
         if self._quantized:
+            if self._tune_ctx is not None:          # differentiable (STE) forward, ptqer.py:238-272
+                return self._tune_ctx["forward"](self, x)
             return self._quantized_forward(x.contiguous())
         if self._init_act:
             return self._conv(self.init_alpha_act(x))

@@ -273,6 +273,22 @@ int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const 
                     float* history, const void* aux_src, void* aux_dst, int64_t aux_bytes,
                     const effq_peer_comm* comm, void* stream);
 
+/* ---- end-to-end activation-range refinement: reference ptqer.py:238-272 ------------------
+ * (tune_activation_range: Adam on every alpha_act through the straight-through estimator of
+ * layer_helper.py:13-37; defined in the reference, not called by its do_ptq.) */
+/* Backward of qact = discretize(x/alpha, nlvl, lo, hi)*alpha given grad_out = dL/dqact:
+ *   grad_x_out[i]   = grad_out[i] * 1[lo <= x[i]/alpha <= hi]           (may be NULL)
+ *   *grad_alpha_acc += sum_i grad_out[i] * (D(x[i]/alpha) - 1[..] * x[i]/alpha)   (fp64, deterministic)
+ * workspace: effq_ste_bwd_workspace() bytes, zeroed once by the caller (self-resetting). */
+int64_t effq_ste_bwd_workspace(void);
+int effq_fakequant_ste_bwd(const float* x, const float* grad_out, int64_t numel, const float* alpha,
+                           float lo, float hi, int32_t nlvl, float* grad_x_out, double* grad_alpha_acc,
+                           void* workspace, void* stream);
+/* torch.optim.Adam update (no weight decay / amsgrad) of n fp32 scalars from fp64 gradients scaled by
+ * grad_scale (1/world after an all-reduce); step counts from 1. */
+int effq_adam_step(float* params, const double* grads, float grad_scale, float* exp_avg, float* exp_avg_sq,
+                   int32_t n, float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -424,3 +424,36 @@ def mask_pyramid(output_fp: torch.Tensor, body: torch.Tensor, wmap: dict, init_s
         out = F.avg_pool3d(out, 2)
         body = F.max_pool3d(body.float(), 2).bool()
     return levels
+
+
+# ----------------------------------------------------------------------------
+# a15: end-to-end activation-range refinement (reference: src/ptqer.py:238-272)
+# ----------------------------------------------------------------------------
+def ste_grads(x: torch.Tensor, alpha: float, num_lvl: int, grad_out: torch.Tensor, lo: float = 0.0, hi: float = 1.0):
+    """Gradients of  qact = discretize(x/alpha, L, lo, hi) * alpha  (PTQConv.py:114-116) under the
+    reference's straight-through estimator (layer_helper.py:13-37): round() has identity gradient,
+    torch.clamp passes the gradient where lo <= u <= hi.  With u = x/alpha, m = 1[lo <= u <= hi]:
+    grad_x = m*(((g*alpha)*delta)/delta)/alpha,  grad_alpha = sum g*(D(u) - m*u).  Returns (grad_x, grad_alpha as fp64)."""
+    a = torch.tensor(float(alpha), dtype=torch.float32)
+    u = x.float() / a
+    m = (u >= lo) & (u <= hi)
+    d = discretize(u, num_lvl, lo, hi)
+    # autograd's op order through Qvar*alpha, t*delta+lo, round (identity), (var-lo)/delta, clamp, x/alpha:
+    # (((g*alpha)*delta)/delta)/alpha in fp32
+    delta = torch.tensor((hi - lo) / (num_lvl - 1), dtype=torch.float32)
+    gx = torch.where(m, (((grad_out.float() * a) * delta) / delta) / a, torch.zeros_like(grad_out, dtype=torch.float32))
+    ga = (grad_out.double() * (d.double() - torch.where(m, u, torch.zeros_like(u)).double())).sum().item()
+    return gx, ga
+
+
+def adam_update(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float = 5e-4,
+                beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
+    """One torch.optim.Adam step (the optimiser of ptqer.py:259; no weight decay, no amsgrad) on fp32
+    vectors, restated from torch/optim/adam.py::_single_tensor_adam.  Returns (p, m, v)."""
+    m = m + (1 - beta1) * (g - m)                         # exp_avg.lerp_(grad, 1 - beta1)
+    v = v * beta2 + (1 - beta2) * g * g                   # exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = v.sqrt() / (bc2 ** 0.5) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v

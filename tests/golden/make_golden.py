@@ -340,6 +340,86 @@ def gen_toy_net(R, out, cfg=TOY, fname="toy_net.npz"):
     np.savez_compressed(os.path.join(out, fname), **res)
 
 
+def gen_toy_tune(R, out, n_tune=3):
+    """Reference tune_activation_range (src/ptqer.py:238-272) on the BraTS miniature, right after its
+    do_ptq core: the calibrated state it starts from, d loss / d alpha_act of the first iteration (one
+    manual forward/backward identical to the reference's loop body), then the reference function itself
+    for n_tune Adam iterations -> losses and the refined alpha_act."""
+    from efficientq_b200 import synth
+    ptqer = R["ptqer"]
+    cfg = TOY
+    model = build_toy(R, R["effq"].EfficientQConv, cfg)
+    model.load_state_dict(seeded_state(model, cfg["seed"]), strict=False)
+    model.eval()
+    R["fold_bn"].search_fold_and_remove_bn(model)
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
+    ptqer.set_name(model)
+    ptqer.set_fp(model)
+    handles = [m.register_forward_hook(R["hooks"].forward_hook) for m in model.modules()
+               if isinstance(m, R["ptqconv"].PTQConv)]
+    with torch.no_grad():
+        output_fp = model(data).detach()
+    body = (data[:, 0] != 0.0).bool()
+    wmap, _ = ptqer.get_att_weight_map(output_fp, torch.ones_like(data[:, 0]).bool(), "p:0.5", task="brats")
+    ptqer.set_mask(model, ptqer.get_mask_pyramid(output_fp, body, wmap, "2,2,2", num_lvls=5, task="brats"))
+    for h in handles:
+        h.remove()
+    ptqer.set_anything(model, "layer_loss", [])
+    ptqer.set_quantizing(model)
+    with torch.no_grad():
+        model(data)
+    ptqer.set_quantized(model)
+    res = {"out_fp_sum": np.float64(output_fp.double().sum().item())}
+    mods = [(n, m) for n, m in model.named_modules() if isinstance(m, R["ptqconv"].PTQConv)]
+    for name, m in mods:                                   # the calibrated state the tuning starts from
+        res[f"pre::{name}.weight"] = m.weight.data.numpy().copy()
+        res[f"pre::{name}.bias"] = m.bias.data.numpy().copy()
+        res[f"pre::{name}.alpha_w"] = np.float32(m.alpha_w.item())
+        res[f"pre::{name}.alpha_act"] = np.float32(m.alpha_act.item())
+    out_q = model(data)                                    # loop body of ptqer.py:262-268, once, by hand
+    loss = F.mse_loss(out_q, output_fp)
+    model.zero_grad()
+    loss.backward()
+    res["loss0"] = np.float64(loss.item())
+    for name, m in mods:
+        if m.alpha_act.grad is not None:
+            res[f"grad0::{name}"] = np.float64(m.alpha_act.grad.item())
+    model.zero_grad(set_to_none=True)
+    losses = ptqer.tune_activation_range(model, output_fp, data, max_iter=n_tune)
+    res["tune_losses"] = np.array(losses, dtype=np.float64)
+    for name, m in mods:
+        res[f"post::{name}.alpha_act"] = np.float32(m.alpha_act.item())
+    # kernel-level known answers: STE gradients of the reference's discretize (incl. values on the clamp
+    # boundaries and rounding ties) and three torch.optim.Adam(lr=5e-4) steps on a small vector
+    g = torch.Generator().manual_seed(21)
+    for lv in (4, 16, 256):
+        alpha = torch.tensor(1.37, requires_grad=True)
+        x = torch.randn(4099, generator=g) * 1.2
+        x[:8] = torch.tensor([0.0, 1.37, 1.37 * 0.5, -0.0, 2.0, -1.0, 1.37 / (lv - 1) * 0.5, 1.37 / (lv - 1) * 1.5])
+        x.requires_grad_(True)
+        go = torch.randn(4099, generator=g)
+        q = R["lh"].discretize(x / alpha, lv, 0, 1) * alpha
+        q.backward(go)
+        res[f"ste{lv}::x"], res[f"ste{lv}::g"] = x.detach().numpy(), go.numpy()
+        res[f"ste{lv}::grad_x"] = x.grad.numpy().copy()
+        res[f"ste{lv}::grad_alpha"] = np.float64(alpha.grad.item())
+    p = torch.nn.Parameter(torch.tensor([3.68, 6.06, 19.58, 0.5]))
+    opt = torch.optim.Adam([p], lr=5e-4)
+    gs = torch.tensor([[0.19, -0.028, -1.2e-3, 3.0e-9], [0.17, 0.031, -1.0e-3, -2.0e-9], [-0.05, 0.030, 4.0e-4, 1.0e-9]])
+    traj = []
+    for k in range(3):
+        p.grad = gs[k].clone()
+        opt.step()
+        traj.append(p.data.clone().numpy())
+    res["adam::grads"], res["adam::p0"] = gs.numpy(), np.array([3.68, 6.06, 19.58, 0.5], dtype=np.float32)
+    res["adam::traj"] = np.stack(traj)
+    print("loss0", res["loss0"], "tune losses", losses)
+    for name, m in mods:
+        print(f"{name:45s} grad0 {res.get(f'grad0::{name}', float('nan')):+.6e} alpha {res[f'pre::{name}.alpha_act']:.6f} -> "
+              f"{res[f'post::{name}.alpha_act']:.6f}")
+    np.savez_compressed(os.path.join(out, "toy_tune.npz"), **res)
+
+
 def gen_toy_net_lits(R, out):
     gen_toy_net(R, out, TOY_LITS, "toy_net_lits.npz")
 
@@ -353,7 +433,7 @@ def main():
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
                 solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
-                toy_net_lits=gen_toy_net_lits)
+                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

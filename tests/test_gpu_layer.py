@@ -176,5 +176,39 @@ def test_quantized_forward_matches_reference_semantics(engine_mod, c1, c2, k):
     m.set_quantized()
     with torch.no_grad():
         got = m(x.to(DEV))
-    assert m._wcodes_cache is not None                      # the tcgen05 path was taken
+    assert m._wcodes_cache is not None and m._wcodes_cache[1] is not None      # the tcgen05 path was taken
     torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_quantized_forward_uses_stored_weights_not_alpha_w(engine_mod):
+    """Reference quirk (EfficientQConv.py:155-158): after calibration alpha_w is the LAST iterate's scale
+    while the weights are the BEST iterate's, so alpha_w does not describe the stored weights.  The
+    reference's quantized forward convolves with the stored weights as they are (PTQConv.py:163-167); the
+    tensor-core path must therefore recover the grid scale from the weights (found by the tune parity test:
+    0.4 % loss error when alpha_w was used)."""
+    import torch.nn.functional as F
+    from efficientq_b200.qconv import EfficientQConv
+    from oracle import effq_oracle as O
+    torch.manual_seed(5)
+    c1, c2, k = 32, 32, 3
+    m = EfficientQConv(c1, c2, k, 1, 1, bias=True, q_weight=True, qlvl=16, q_act=True, qlvl_act=16)
+    a_best, a_last, a_act = torch.tensor(0.2137), torch.tensor(0.2101), torch.tensor(1.7)
+    qw = O.quantize_w(torch.randn(c2, c1, k, k, k) * 0.1, a_best, 16)
+    m.weight.data, m.alpha_w.data, m.alpha_act.data = qw.clone(), a_last.clone(), a_act.clone()
+    m.bias.data = torch.randn(c2) * 0.1
+    x = torch.relu(torch.randn(2, c1, 6, 16, 8)) * 1.2
+    want = F.conv3d(O.quantize_act(x, a_act, 16).double(), qw.double(), m.bias.data.double(), 1, 1).float()
+    m.to(DEV)
+    m.set_quantized()
+    with torch.no_grad():
+        got = m(x.to(DEV))
+    assert m._wcodes_cache[1] is not None                   # tcgen05 path, scale recovered from the weights
+    assert abs(float(m._wcodes_cache[1][1]) - float(a_best)) <= 1e-6 * float(a_best)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-5)
+    # weights that are on no L-level grid at all -> generic fp32 path, still the stored weights
+    m.weight.data = (qw * (1 + 0.01 * torch.randn_like(qw))).to(DEV)
+    with torch.no_grad():
+        got2 = m(x.to(DEV))
+    assert m._wcodes_cache[1] is None
+    want2 = F.conv3d(O.quantize_act(x, a_act, 16).double(), m.weight.data.cpu().double(), m.bias.data.cpu().double(), 1, 1).float()
+    torch.testing.assert_close(got2.cpu(), want2, rtol=1e-4, atol=1e-4)

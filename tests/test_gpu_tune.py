@@ -1,0 +1,124 @@
+"""GPU parity of the end-to-end activation-range refinement (reference
+src/ptqer.py:238-272 tune_activation_range) against fixtures produced by the reference itself
+(tests/golden/make_golden.py::gen_toy_tune) and against the oracle's restatement."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from efficientq_b200 import ops as _ops
+    _ops.capi.load()
+    return _ops
+
+
+@pytest.mark.parametrize("L", [4, 16, 256])
+def test_ste_backward_kernel_golden(ops, golden, L):
+    """grad_x bit-exact against torch autograd through the reference's discretize (clamp boundaries and
+    rounding ties included); d/d alpha (the reference sums it in fp32, the kernel in fp64) to 2e-5."""
+    g = golden("toy_tune.npz")
+    x, go = torch.from_numpy(g[f"ste{L}::x"]).to(DEV), torch.from_numpy(g[f"ste{L}::g"]).to(DEV)
+    alpha = torch.tensor([1.37], device=DEV)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    gx = ops.fakequant_ste_bwd(x, go, alpha, L, 0.0, 1.0, acc)
+    assert torch.equal(gx.cpu(), torch.from_numpy(g[f"ste{L}::grad_x"]))
+    ref = float(g[f"ste{L}::grad_alpha"])
+    assert abs(acc.item() - ref) <= 2e-5 * abs(ref) + 1e-5
+    # accumulates (autograd semantics) and can skip grad_x
+    assert ops.fakequant_ste_bwd(x, go, alpha, L, 0.0, 1.0, acc, want_grad_x=False) is None
+    assert abs(acc.item() - 2 * ref) <= 4e-5 * abs(ref) + 2e-5
+
+
+@pytest.mark.parametrize("numel", [1, 5, 1023, (1 << 22) + 3])
+def test_ste_backward_kernel_vs_oracle_ragged(ops, numel):
+    from oracle import effq_oracle as O
+    torch.manual_seed(numel)
+    x = torch.randn(numel) * 2.0
+    go = torch.randn(numel)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    gx = ops.fakequant_ste_bwd(x.to(DEV), go.to(DEV), torch.tensor([0.9], device=DEV), 16, 0.0, 1.0, acc)
+    gx_o, ga_o = O.ste_grads(x, 0.9, 16, go)
+    assert torch.equal(gx.cpu(), gx_o)
+    assert abs(acc.item() - ga_o) <= 1e-9 * max(abs(ga_o), 1.0) * max(1.0, numel ** 0.5)
+    # deterministic: same bits on a second run
+    acc2 = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.fakequant_ste_bwd(x.to(DEV), go.to(DEV), torch.tensor([0.9], device=DEV), 16, 0.0, 1.0, acc2, want_grad_x=False)
+    assert acc2.item() == acc.item()
+
+
+def test_adam_step_kernel_matches_torch(ops, golden):
+    g = golden("toy_tune.npz")
+    p = torch.from_numpy(g["adam::p0"]).to(DEV).clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for k in range(3):
+        ops.adam_step(p, torch.from_numpy(g["adam::grads"][k]).double().to(DEV), m, v, k + 1, 5e-4)
+        np.testing.assert_allclose(p.cpu().numpy(), g["adam::traj"][k], rtol=2e-7, atol=0)
+
+
+def test_tune_activation_range_matches_reference(ops, golden):
+    """The reference's tune_activation_range on the BraTS miniature, started from the reference's own
+    calibrated state: first-iteration gradients of every alpha_act, the loss trajectory and the refined
+    alpha_act after three Adam steps."""
+    from efficientq_b200 import fold_bn, ptqer, synth, tune
+    from efficientq_b200.qconv import PTQConv
+    from tests.test_gpu_layer import build_toy
+    g, g0 = golden("toy_tune.npz"), golden("toy_net.npz")
+    model, cfg = build_toy("brats")
+    model.load_state_dict({k[4:]: torch.from_numpy(g0[k]) for k in g0.files if k.startswith("sd::")}, strict=False)
+    model.eval()
+    fold_bn.search_fold_and_remove_bn(model)
+    model.to(DEV)
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"]).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ptqer.set_name(model)
+    ptqer.set_fp(model)
+    with torch.no_grad():
+        output_fp = model(data).detach()
+    assert abs(output_fp.double().sum().item() - float(g["out_fp_sum"])) <= 1e-4 * abs(float(g["out_fp_sum"])) + 1e-2
+    mods = {n: m for n, m in model.named_modules() if isinstance(m, PTQConv)}
+    for name, m in mods.items():                        # the reference's calibrated state
+        m.weight.data = torch.from_numpy(g[f"pre::{name}.weight"]).to(DEV)
+        m.bias.data = torch.from_numpy(g[f"pre::{name}.bias"]).to(DEV)
+        m.alpha_w.data = torch.tensor(float(g[f"pre::{name}.alpha_w"]), device=DEV)
+        m.alpha_act.data = torch.tensor(float(g[f"pre::{name}.alpha_act"]), device=DEV)
+    # iteration 0 by hand: gradients
+    probe = {}
+    orig = ops.adam_step
+
+    def spy(params, grads, *a, **k):
+        probe.setdefault("grads", []).append(grads.clone())
+        return orig(params, grads, *a, **k)
+    ops.adam_step = spy
+    try:
+        losses = tune.tune_activation_range(model, output_fp, data, max_iter=3)
+    finally:
+        ops.adam_step = orig
+    tuned = [n for n, m in mods.items() if m.q_act]
+    grads0 = probe["grads"][0].cpu().tolist()
+    lines = []
+    for name, gv in zip(tuned, grads0):
+        ref = float(g[f"grad0::{name}"])
+        lines.append(f"{name:45s} grad ours {gv:+.6e} ref {ref:+.6e} rel {abs(gv - ref) / abs(ref):.2e} | alpha "
+                     f"{float(mods[name].alpha_act.detach()):.6f} ref {float(g[f'post::{name}.alpha_act']):.6f}")
+    lines.append(f"losses ours {losses} ref {g['tune_losses'].tolist()}")
+    print("\n".join(lines))
+    import os
+    if os.path.isdir("gpurun_out"):
+        open("gpurun_out/toy_tune_parity.txt", "w").write("\n".join(lines) + "\n")
+    np.testing.assert_allclose(losses[0], float(g["loss0"]), rtol=1e-5)
+    for name, gv in zip(tuned, grads0):
+        ref = float(g[f"grad0::{name}"])
+        assert abs(gv - ref) <= 2e-3 * abs(ref) + 1e-7, (name, gv, ref)
+    np.testing.assert_allclose(losses, g["tune_losses"], rtol=1e-5)
+    for name in tuned:
+        assert abs(float(mods[name].alpha_act) - float(g[f"post::{name}.alpha_act"])) <= 2e-5 * float(mods[name].alpha_act)
+    for name, m in mods.items():
+        if not m.q_act:
+            assert float(m.alpha_act) == 1.0 and m._tune_ctx is None

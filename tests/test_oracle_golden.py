@@ -107,3 +107,23 @@ def test_mask_pyramid_matches_reference(golden):
     vals = torch.unique(torch.cat([p.flatten() for p in pyr]))
     assert set(vals.tolist()) <= {1.0, 2.0, 3.0}
     assert g["pyr0"].max() >= 1
+
+
+@pytest.mark.parametrize("L", [4, 16, 256])
+def test_ste_gradients_match_reference_autograd(golden, L):
+    """a15: closed-form STE gradients vs torch autograd through the reference's own discretize
+    (clamp boundaries and rounding ties included)."""
+    g = golden("toy_tune.npz")
+    x, go = torch.from_numpy(g[f"ste{L}::x"]), torch.from_numpy(g[f"ste{L}::g"])
+    gx, ga = O.ste_grads(x, 1.37, L, go)
+    assert torch.equal(gx, torch.from_numpy(g[f"ste{L}::grad_x"]))
+    assert abs(ga - float(g[f"ste{L}::grad_alpha"])) <= 2e-5 * abs(ga) + 1e-5     # reference sums in fp32
+
+
+def test_adam_update_matches_torch(golden):
+    g = golden("toy_tune.npz")
+    p = torch.from_numpy(g["adam::p0"]).clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for k in range(3):
+        p, m, v = O.adam_update(p, torch.from_numpy(g["adam::grads"][k]), m, v, k + 1)
+        np.testing.assert_allclose(p.numpy(), g["adam::traj"][k], rtol=2e-7, atol=0)

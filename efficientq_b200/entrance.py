@@ -90,7 +90,7 @@ def build_parser():
     p.add_argument("--lwq_verbose", action="store_true")
     # extension (not a reference flag): > 0 runs the reference's tune_activation_range (src/ptqer.py:238-272,
     # defined there but never called) for that many Adam iterations after the layer-wise calibration
-    p.add_argument("--lwq_tune_iter", type=int, default=0)
+    p.add_argument("--tune_act_iter", type=int, default=0)
     p.add_argument("--save_nii", action="store_true")
     return p
 

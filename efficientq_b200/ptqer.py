@@ -210,7 +210,7 @@ def do_ptq(args, model_cube, data_cube, tester, snap_dir, dist: Optional[DistCtx
         tester.test_as_is(folder="fp", is_save_nii=getattr(args, "save_nii", False))
     res = calibrate(model, data_batch, args.task, args.init_stride, dist)
     print(f"FP forward costs {res['t_fp']:.3f}s, PTQ costs {res['t_ptq']:.3f}s, totally {res['t_total']:.3f}s.")
-    n_tune = int(getattr(args, "lwq_tune_iter", 0) or 0)
+    n_tune = int(getattr(args, "tune_act_iter", 0) or 0)
     if n_tune > 0:                                       # optional: reference ptqer.py:238-272
         from .tune import tune_activation_range
         res["tune_losses"] = tune_activation_range(model, res["output_fp"], data_batch, max_iter=n_tune, dist=dist)

@@ -4,7 +4,7 @@
 the same name: every quantizer module is put in its quantized mode, Adam (lr 5e-4) runs on all
 ``alpha_act`` parameters, the loss is the MSE between the quantised network's output and the FP
 output.  The reference defines it but never calls it from ``do_ptq``; here it is reachable through
-``ptqer.do_ptq`` when the YAML/CLI sets ``lwq_tune_iter > 0`` (an extension key, default 0).
+``ptqer.do_ptq`` when the YAML/CLI sets ``tune_act_iter > 0`` (an extension key, default 0).
 
 What runs where:
   * forward of a quantizer layer: the deployment forward (fake-quant codes + tcgen05 conv,

@@ -30,20 +30,64 @@ fakequant_ste_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
   const long long nvec = numel / 4;
   const long long stride = (long long)gridDim.x * STE_THREADS;
   double acc = 0.0;
+  // Instruction budget (ncu, profiles/r01_ste_ncu.md): the op-for-op form needs four IEEE divisions per
+  // element (x/alpha, the level index, autograd's (..)/delta and (..)/alpha) and ran at 33 % of the HBM
+  // peak with 114 instructions per element, a third of them branches around the division subroutine.
+  // Here ONE predicate decides per element between
+  //  * the fast path: u and the level index from multiplies (as level_index_fast_f, common.cuh), the two
+  //    divisions of grad_x by correctly rounded reciprocals + Markstein's correction
+  //        q = t*r;  q' = fma(fma(-q, b, t), r, q)        (= RN(t/b) for operands in the normal range),
+  //  * the exact op-for-op sequence, taken near a rounding tie, near a clamp boundary, for NaN and for
+  //    gradients outside the safely-normal range.  Same bits either way (tests/test_gpu_tune.py).
+  const int nlvl = (int)(rintf((q.hi - q.lo) / q.delta)) + 1;
+  const QFastF qf = make_qfast_f(alpha, q, nlvl);
+  const float r_alpha = __frcp_rn(alpha), r_delta = __frcp_rn(q.delta);
+  const float eps_hi = 1e-5f * fabsf(q.hi) + 1e-30f, eps_lo = 1e-5f * fabsf(q.lo) + 1e-30f;
   auto one = [&](float xv, float gv, float& gxo) -> double {
-    const float u = __fdiv_rn(xv, alpha);                    // exactly the reference's x / alpha
-    const bool in = (u >= q.lo) && (u <= q.hi);              // torch.clamp backward; NaN -> false
-    const float d = level_value_f(level_index_f(u, q), q);
-    // autograd's op order through Qvar*alpha, t*delta+lo, round, (var-lo)/delta, clamp, x/alpha
-    gxo = in ? __fdiv_rn(__fdiv_rn(__fmul_rn(__fmul_rn(gv, alpha), q.delta), q.delta), alpha) : 0.f;
-    return (double)gv * (in ? (double)d - (double)u : (double)d);      // fp64: exact products, exact sum order below
+    float u = xv * qf.inv_alpha;
+    const float qa = (u - q.lo) * qf.inv_delta;
+    const float r = rintf(qa);
+    const float ag = fabsf(gv);
+    const bool tie = fabsf(fabsf(qa - r) - 0.5f) < 2e-3f && qa > -1.0f && qa < qf.lm1 + 1.0f;
+    const bool edge = fabsf(u - q.hi) < eps_hi || (fabsf(u - q.lo) < eps_lo && xv != 0.f);
+    const bool wild = !(xv == xv) || !(ag < 1e25f && (ag > 1e-20f || ag == 0.f));
+    float idx, gq;
+    const float t = __fmul_rn(__fmul_rn(gv, alpha), q.delta);   // autograd: (g*alpha)*delta ...
+    if (tie || edge || wild) {
+      u = __fdiv_rn(xv, alpha);                                  // exactly the reference's x / alpha
+      idx = level_index_f(u, q);
+      gq = __fdiv_rn(__fdiv_rn(t, q.delta), alpha);              // ... /delta, /alpha
+    } else {
+      idx = fminf(fmaxf(r, 0.f), qf.lm1);
+      const float q1 = t * r_delta;
+      const float d1 = fmaf(fmaf(-q1, q.delta, t), r_delta, q1);
+      const float q2 = d1 * r_alpha;
+      gq = fmaf(fmaf(-q2, alpha, d1), r_alpha, q2);
+    }
+    const bool in = (u >= q.lo) && (u <= q.hi);                  // torch.clamp backward; NaN -> false
+    const float d = level_value_f(idx, q);
+    gxo = in ? gq : 0.f;
+    return (double)gv * (double)(in ? __fsub_rn(d, u) : d);      // d - u: within 1 ulp(u) of the exact difference
   };
-  for (long long i = (long long)blockIdx.x * STE_THREADS + threadIdx.x; i < nvec; i += stride) {
-    const float4 xv = __ldcs(reinterpret_cast<const float4*>(x) + i);
-    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
-    float4 o;
-    acc += (one(xv.x, gv.x, o.x) + one(xv.y, gv.y, o.y)) + (one(xv.z, gv.z, o.z) + one(xv.w, gv.w, o.w));
-    if (WRITE_GX) __stcs(reinterpret_cast<float4*>(gx) + i, o);
+  constexpr int U = 4;                                       // independent 128-bit load pairs in flight per thread
+  for (long long i = (long long)blockIdx.x * STE_THREADS + threadIdx.x; i < nvec; i += stride * U) {
+    float4 xv[U], gv[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long j = i + k * stride;
+      if (j < nvec) {
+        xv[k] = __ldcs(reinterpret_cast<const float4*>(x) + j);
+        gv[k] = __ldcs(reinterpret_cast<const float4*>(g) + j);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long j = i + k * stride;
+      if (j >= nvec) continue;
+      float4 o;
+      acc += (one(xv[k].x, gv[k].x, o.x) + one(xv[k].y, gv[k].y, o.y)) + (one(xv[k].z, gv[k].z, o.z) + one(xv[k].w, gv[k].w, o.w));
+      if (WRITE_GX) __stcs(reinterpret_cast<float4*>(gx) + j, o);
+    }
   }
   if (blockIdx.x == 0) {
     const long long t = nvec * 4 + threadIdx.x;
@@ -106,7 +150,7 @@ extern "C" int effq_fakequant_ste_bwd(const float* x, const float* grad_out, int
                      (!grad_x_out || ((uintptr_t)grad_x_out & 15) == 0), "pointers must be 16B aligned");
   if (numel <= 0) return 0;
   const QParamF q = make_qparam_f(lo, hi, nlvl);
-  long long blocks = (numel / 4 + STE_THREADS - 1) / STE_THREADS;
+  long long blocks = (numel / 4 + STE_THREADS * 4 - 1) / (STE_THREADS * 4);
   const long long cap = (long long)sm_count() * 8 < STE_MAX_BLOCKS ? (long long)sm_count() * 8 : STE_MAX_BLOCKS;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;

@@ -45,4 +45,34 @@ dist.all_reduce_max(mn)
 assert mx.item() == -mn.item(), "ranks diverged"
 if dist.rank == 0:
     print("ranks hold identical weights")
+
+# a15: sharded alpha_act refinement against the reference's UNSHARDED tune_activation_range fixture.
+# Every rank differentiates its own volume; the alpha gradients are all-reduced (tune.py).
+from efficientq_b200 import ops, tune  # noqa: E402
+from efficientq_b200.qconv import PTQConv  # noqa: E402
+gt = np.load(os.path.join(ROOT, "tests", "golden", "toy_tune.npz"))
+model2, _ = build_toy()
+model2.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=False)
+model2.eval()
+fold_bn.search_fold_and_remove_bn(model2)
+model2.to(dev)
+ptqer.set_name(model2)
+ptqer.set_fp(model2)
+with torch.no_grad():
+    out_fp = model2(data).detach()
+mods = {n: m for n, m in model2.named_modules() if isinstance(m, PTQConv)}
+for name, m in mods.items():
+    m.weight.data = torch.from_numpy(gt[f"pre::{name}.weight"]).to(dev)
+    m.bias.data = torch.from_numpy(gt[f"pre::{name}.bias"]).to(dev)
+    m.alpha_w.data = torch.tensor(float(gt[f"pre::{name}.alpha_w"]), device=dev)
+    m.alpha_act.data = torch.tensor(float(gt[f"pre::{name}.alpha_act"]), device=dev)
+losses_t = tune.tune_activation_range(model2, out_fp, data, max_iter=3, dist=dist)
+post = {n: float(m.alpha_act.detach()) for n, m in mods.items() if m.q_act}
+if dist.rank == 0:
+    print("tune losses sharded", losses_t, "ref (unsharded)", gt["tune_losses"].tolist())
+    assert np.allclose(losses_t, gt["tune_losses"], rtol=1e-5)
+    for n, v in post.items():
+        r = float(gt[f"post::{n}.alpha_act"])
+        assert abs(v - r) <= 2e-5 * r, (n, v, r)
+    print(f"TUNE DIST OK world={dist.world}: refined alpha_act equal the unsharded reference's")
 torch.distributed.destroy_process_group() if dist.world > 1 else None

@@ -73,6 +73,11 @@ struct TcParams {
   unsigned int tmem_cols;
   int swz, rp, debug;          // operand swizzle width (128/64/32 B), row pitch, bring-up debug bits
   unsigned int wstage_bytes;   // shared-memory stride between weight tiles (1024-aligned when swizzled)
+  // C2 > 256 runs as launches over chunks of 256 output channels (c2 = the chunk): the chunk's rows of every
+  // [C2_total][CG] weight tile are contiguous in global memory, its outputs / targets sit c2_off channels into
+  // the NCDHW tensors, and launches after the first add their squared error to *sse.
+  int c2_total, c2_off, sse_accumulate;
+  unsigned int wsrc_tile_bytes, wsrc_off;       // global stride between weight tiles, byte offset of the chunk's rows
   unsigned long long* dbg;     // bring-up timeline buffer ([tile][8] clock stamps of CTA 0) or null
 };
 
@@ -152,7 +157,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
     for (int i = 0; i < 4; ++i) { mbar_init(BAR(B_GF + i), 1); mbar_init(BAR(B_GE + i), TC_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.c2; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.c2; i += TC_THREADS) bias_s[i] = p.bias ? p.bias[p.c2_off + i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(p.tmem_cols)
@@ -175,7 +180,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
         mbar_expect_tx(BAR(B_WRES), total);
         for (int g = 0; g < p.n_groups; ++g)
           for (int t = 0; t < p.taps; ++t) {
-            const uint8_t* src = p.wq + ((long long)t * p.n_groups + g) * p.wtile_bytes;
+            const uint8_t* src = p.wq + ((long long)t * p.n_groups + g) * p.wsrc_tile_bytes + p.wsrc_off;
             bulk_g2s(wsm0 + (uint32_t)(g * p.taps + t) * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WRES));
           }
       } else {
@@ -186,7 +191,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
             for (int t = 0; t < p.taps; ++t) {
               if (!mbar_wait<32>(BAR(B_WE + wp.stage), wp.phase ^ 1u, abort_flag)) { ok = false; break; }
               mbar_expect_tx(BAR(B_WF + wp.stage), p.wtile_bytes);
-              const uint8_t* src = p.wq + ((long long)t * p.n_groups + g) * p.wtile_bytes;
+              const uint8_t* src = p.wq + ((long long)t * p.n_groups + g) * p.wsrc_tile_bytes + p.wsrc_off;
               bulk_g2s(wsm0 + (uint32_t)wp.stage * p.wstage_bytes, src, p.wtile_bytes, BAR(B_WF + wp.stage));
               wp.advance(p.n_w_stages);
             }
@@ -273,7 +278,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
       const int oh = th * TC_TILE_H + hy, ow = tw * TC_TILE_W + wx;
       const bool live = oh < p.h && ow < p.w;
       const long long sp = (long long)dd * plane + (long long)oh * p.w + ow;
-      const long long base = (long long)nn * p.c2 * chan + sp;
+      const long long base = ((long long)nn * p.c2_total + p.c2_off) * chan + sp;
       if (p.n_tgt_stages > 0) {
         // ---- target tile staged in shared memory by the TMA warp: [32 channels][128 voxels] fp32 ----
         float* optr = p.out + base;
@@ -396,7 +401,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
         for (int c0 = 0; c0 < p.c2; c0 += 32) {
           if (!mbar_wait<32>(BAR(B_GE + gp.stage), gp.phase ^ 1u, abort_flag)) { ok = false; break; }
           mbar_expect_tx(BAR(B_GF + gp.stage), TC_TGT_BYTES);
-          tma_load_5d(tgt0 + (uint32_t)gp.stage * TC_TGT_BYTES, &tmap, tw * TC_TILE_W, th * TC_TILE_H, dd, c0, nn,
+          tma_load_5d(tgt0 + (uint32_t)gp.stage * TC_TGT_BYTES, &tmap, tw * TC_TILE_W, th * TC_TILE_H, dd, p.c2_off + c0, nn,
                       BAR(B_GF + gp.stage));
           gp.advance(p.n_tgt_stages);
         }
@@ -427,7 +432,8 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += TC_THREADS) t += ((volatile double*)p.ws_partial)[b];
     t = block_sum(t, red_scratch);
     if (threadIdx.x == 0) {
-      *p.sse = (*abort_flag != 0u) ? __longlong_as_double(0x7ff8000000000000ll) : t;   // NaN on abort
+      const double prev = p.sse_accumulate ? *p.sse : 0.0;                                    // later channel chunks add up
+      *p.sse = (*abort_flag != 0u) ? __longlong_as_double(0x7ff8000000000000ll) : prev + t;   // NaN on abort
       *p.ws_done = 0;
     }
   }
@@ -466,6 +472,8 @@ static bool tc_plan(const effq_geom& g, int code_dtype, TcParams& p) {
   p.halo_tx_bytes = (uint32_t)(p.hv * p.rp);
   p.halo_bytes = (p.halo_tx_bytes + 1023u) & ~1023u;
   p.wtile_bytes = (uint32_t)(p.rp * g.c2);
+  p.c2_total = g.c2; p.c2_off = 0; p.sse_accumulate = 0;
+  p.wsrc_tile_bytes = p.wtile_bytes; p.wsrc_off = 0;
   p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
   p.off_bias = 384;
   p.off_halo = (p.off_bias + (uint32_t)g.c2 * 4u + 1023u) & ~1023u;
@@ -551,7 +559,7 @@ static int tc_dispatch(const TcParams& p, const CUtensorMap& m, const CUtensorMa
 static int tc_make_tmap(const TcParams& p, const float* target, CUtensorMap* map) {
   EncodeTiledFn encode = tc_encoder();
   if (!encode) return 2;
-  const cuuint64_t dims[5] = {(cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.d, (cuuint64_t)p.c2, (cuuint64_t)p.n};
+  const cuuint64_t dims[5] = {(cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.d, (cuuint64_t)p.c2_total, (cuuint64_t)p.n};
   const cuuint64_t strides[4] = {dims[0] * 4, dims[0] * dims[1] * 4, dims[0] * dims[1] * dims[2] * 4,
                                  dims[0] * dims[1] * dims[2] * dims[3] * 4};
   const cuuint32_t box[5] = {(cuuint32_t)TC_TILE_W, (cuuint32_t)TC_TILE_H, 1u, 32u, 1u};
@@ -583,9 +591,16 @@ static int tc_make_xmap(const TcParams& p, const void* xcodes, CUtensorMap* map)
 
 }  // namespace effq
 
+// C2 > 256 (one tcgen05.mma covers N <= 256 and the accumulator is double-buffered in 512 TMEM columns):
+// chunks of 256 output channels, one launch each.
+static bool tc_chunked(const effq_geom& g) { return g.c2 > 256 && g.c2 % 256 == 0 && g.c2 <= 1024; }
+
 extern "C" int effq_conv3d_tc_supported(const effq_geom* g, int32_t code_dtype) {
   effq::TcParams p;
-  return (g && effq::tc_plan(*g, code_dtype, p)) ? 1 : 0;
+  if (!g) return 0;
+  effq_geom gg = *g;
+  if (tc_chunked(gg)) gg.c2 = 256;
+  return effq::tc_plan(gg, code_dtype, p) ? 1 : 0;
 }
 
 extern "C" int64_t effq_conv3d_tc_workspace(const effq_geom* g) {
@@ -601,8 +616,17 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t co
   EFFQ_CHECK_ARG(out || target, "nothing to compute");
   EFFQ_CHECK_ARG(!target || sse, "sse required with target");
   EFFQ_CHECK_ARG(((uintptr_t)xcodes & 15) == 0 && ((uintptr_t)wcodes & 15) == 0, "operands must be 16B aligned");
+  const int n_chunks = tc_chunked(*g) ? g->c2 / 256 : 1;
+  effq_geom gg = *g;
+  if (n_chunks > 1) gg.c2 = 256;
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
   TcParams p;
-  EFFQ_CHECK_ARG(tc_plan(*g, code_dtype, p), "geometry / code type not supported by the tcgen05 path");
+  EFFQ_CHECK_ARG(tc_plan(gg, code_dtype, p), "geometry / code type not supported by the tcgen05 path");
+  p.c2_total = g->c2;
+  p.c2_off = chunk * gg.c2;
+  p.sse_accumulate = chunk > 0 ? 1 : 0;
+  p.wsrc_tile_bytes = (uint32_t)(p.rp * g->c2);
+  p.wsrc_off = (uint32_t)(p.rp * p.c2_off);
   EFFQ_CHECK_ARG(p.n_tiles < (1ll << 31), "too many tiles");
   p.xq = (const uint8_t*)xcodes;
   p.wq = (const uint8_t*)wcodes;
@@ -630,5 +654,7 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t co
   } else {
     tmap = xmap;                                       // never dereferenced
   }
-  return tc_dispatch(p, xmap, tmap, g->kd, kk, smem, (unsigned)ctas, (cudaStream_t)stream);
+  if (int rc = tc_dispatch(p, xmap, tmap, g->kd, kk, smem, (unsigned)ctas, (cudaStream_t)stream)) return rc;
+  }
+  return 0;
 }

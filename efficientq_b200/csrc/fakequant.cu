@@ -5,6 +5,7 @@
 //                             the operand format of the tcgen05 conv.
 #include "common.cuh"
 #include <cuda_fp8.h>
+#include <stdlib.h>
 
 namespace effq {
 
@@ -168,6 +169,148 @@ quantize_act_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int
   }
 }
 
+// ---- v2: register transpose ------------------------------------------------------------------
+// The v1 kernel above is issue-bound (ncu: 106 instructions per element, 40-47 % of the HBM peak,
+// profiles/r01_conv_sweep.md): fp64 arithmetic for every element plus one LDS.U16 per element in the
+// transpose.  v2, used whenever dhw % 4 == 0 and the tile is full:
+//  * a thread owns 4 channels x 4 consecutive voxels: four independent 128-bit loads (one per channel
+//    row), a 4x4 transpose in registers, and per voxel ONE 32-bit (e4m3) / 64-bit (bf16) shared-memory
+//    store of its 4-channel pack into a tile that already has the output layout [voxel][channel];
+//    lanes rotate which voxel they store first, which makes the stores bank-conflict free;
+//  * the tile leaves as a straight 16-byte LDS.128 -> STG.128 copy (the block is contiguous in NDHWC);
+//  * the level index comes from one fp32 FMA + rint; only elements within a safety margin of a rounding
+//    tie (or NaN) take the exact fp64 sequence, so the codes are identical to v1's.
+template <bool F64, bool W16, bool W8>
+__global__ void __launch_bounds__(QA_THREADS)
+quantize_act_ndhwc_v2_kernel(const float* __restrict__ x, int c, long long dhw, int nlvl, int tile_v, long long n_tiles,
+                             const effq_scale_state* __restrict__ st, const float* __restrict__ alpha_f32,
+                             __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out8) {
+  extern __shared__ __align__(16) uint8_t tile_raw[];
+  uint32_t* t16 = reinterpret_cast<uint32_t*>(tile_raw);                                    // [tile_v][c] bf16
+  uint32_t* t8 = reinterpret_cast<uint32_t*>(tile_raw + (W16 ? (size_t)tile_v * c * 2 : 0)); // [tile_v][c] e4m3
+  const long long tiles_per_sample = dhw / tile_v;                 // host guarantees dhw % tile_v == 0
+
+  const QParamF qf = make_qparam_f(0.f, 1.f, nlvl);
+  const QParamD qd = make_qparam_d(0.f, 1.f, nlvl);
+  const double a64 = F64 ? st->a : 1.0;
+  const float a32 = F64 ? 1.f : __ldg(alpha_f32);
+  const QFastD fd = make_qfast_d(a64, qd, nlvl);
+  const QFastF ff = make_qfast_f(a32, qf, nlvl);
+  const float c1f = (float)fd.c1, lm1 = (float)(nlvl - 1);
+  const float tol = 1e-5f * (lm1 + 1.f) + 1e-5f;                   // >= 40x the fp32 evaluation error of qa
+  auto code_of = [&](float val) -> float {
+    if (F64) {
+      const float qa = val * c1f;                                  // lo = 0: c0 = 0
+      const float r = rintf(qa);
+      const bool risky = (fabsf(fabsf(qa - r) - 0.5f) < tol && qa > -1.0f && qa < lm1 + 1.0f) || !(val == val);
+      if (risky) return (float)level_index_fast_d((double)val, a64, qd, fd);
+      return fminf(fmaxf(r, 0.f), lm1);
+    }
+    return level_index_fast_f(val, a32, qf, ff);
+  };
+
+  const int groups = c >> 2;                                       // 4-channel groups
+  const int gw = groups < 32 ? groups : 32;                        // groups covered by one warp
+  const int vqw = 32 / gw;                                         // voxel quads covered by one warp (gw is a power of 2 <= 32
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      //  or groups >= 32; host check)
+  const int lg = lane % gw, lq = lane / gw;
+  const int quads = tile_v >> 2;
+  const int gblocks = (groups + gw - 1) / gw;
+  const int items = gblocks * ((quads + vqw - 1) / vqw);           // warp-level work items
+  // Persistent: a CTA walks tiles with a grid stride, so the scale set-up above (fp64 divisions) is paid once
+  // per CTA: 41-47 % -> 53-61 % of the HBM peak.  Measured and rejected: issuing all of a thread's loads of a
+  // tile first (80 registers + spills: 28 %), prefetching the next tile's loads across the transpose
+  // (126 registers, 2 CTAs per SM: 33 %).  What is left is memory-latency stall on the first use of the loaded
+  // data (ncu: 31 % of the samples); a TMA-staged ring is the next step.
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long n_idx = tile / tiles_per_sample;
+    const long long v0 = (tile % tiles_per_sample) * tile_v;
+    const float* xs = x + n_idx * (long long)c * dhw + v0;
+    for (int it = warp; it < items; it += QA_THREADS / 32) {
+      const int gb = it % gblocks, qb = it / gblocks;
+      const int g4 = gb * gw + lg, vq = qb * vqw + lq;
+      if (g4 >= groups || vq >= quads) continue;
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(xs + (long long)(4 * g4 + k) * dhw) + vq);
+      float cd[4][4];                                              // [voxel][channel]
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cd[0][k] = code_of(v[k].x); cd[1][k] = code_of(v[k].y); cd[2][k] = code_of(v[k].z); cd[3][k] = code_of(v[k].w);
+      }
+      uint32_t p8[4];
+      uint2 p16[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (W8)
+          p8[i] = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][0], cd[i][1]), __NV_SATFINITE, __NV_E4M3) |
+                  ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][2], cd[i][3]), __NV_SATFINITE, __NV_E4M3) << 16);
+        if (W16) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(cd[i][0], cd[i][1]);
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(cd[i][2], cd[i][3]);
+          p16[i].x = *reinterpret_cast<const uint32_t*>(&lo);
+          p16[i].y = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+      }
+      // store order rotated by the lane's quad index: in each store instruction the warp's quads write
+      // different voxel rows -> different banks
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int vi = (i + lq) & 3;
+        const int row = 4 * vq + vi;
+        if (W8) {
+          const uint32_t w = vi == 0 ? p8[0] : vi == 1 ? p8[1] : vi == 2 ? p8[2] : p8[3];
+          t8[row * groups + g4] = w;
+        }
+        if (W16) {
+          const uint2 w = vi == 0 ? p16[0] : vi == 1 ? p16[1] : vi == 2 ? p16[2] : p16[3];
+          reinterpret_cast<uint2*>(t16)[row * groups + g4] = w;
+        }
+      }
+    }
+    __syncthreads();
+    if (W8) {
+      uint4* dst = reinterpret_cast<uint4*>(out8 + (n_idx * dhw + v0) * c);
+      const uint4* src = reinterpret_cast<const uint4*>(t8);
+      const int n16 = tile_v * c / 16;
+      for (int e = threadIdx.x; e < n16; e += QA_THREADS) dst[e] = src[e];
+    }
+    if (W16) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (n_idx * dhw + v0) * c);
+      const uint4* src = reinterpret_cast<const uint4*>(t16);
+      const int n16 = tile_v * c / 8;
+      for (int e = threadIdx.x; e < n16; e += QA_THREADS) dst[e] = src[e];
+    }
+    __syncthreads();                                               // the tile is reused by the next iteration
+  }
+}
+
+template <bool F64>
+static int launch_quantize_v2(const float* x, int n, int c, long long dhw, int nlvl, int tile_v,
+                              const effq_scale_state* st, const float* alpha, __nv_bfloat16* out, uint8_t* out8,
+                              cudaStream_t s) {
+  const long long n_tiles = (long long)n * (dhw / tile_v);
+  const size_t smem = (size_t)tile_v * c * ((out ? 2 : 0) + (out8 ? 1 : 0));
+  const long long cap = (long long)sm_count() * 8;                 // grid stride beyond 8 CTAs per SM
+  const long long tiles = n_tiles < cap ? n_tiles : cap;
+  static bool configured = false;
+  if (!configured) {
+    const int mx = 96 * 1024;
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v2_kernel<F64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v2_kernel<F64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v2_kernel<F64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    configured = true;
+  }
+  if (out && out8)
+    quantize_act_ndhwc_v2_kernel<F64, true, true><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, tile_v, n_tiles, st, alpha, out, out8);
+  else if (out)
+    quantize_act_ndhwc_v2_kernel<F64, true, false><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, tile_v, n_tiles, st, alpha, out, out8);
+  else
+    quantize_act_ndhwc_v2_kernel<F64, false, true><<<(unsigned)tiles, QA_THREADS, smem, s>>>(x, c, dhw, nlvl, tile_v, n_tiles, st, alpha, out, out8);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace effq
 
 extern "C" int effq_fakequant_f32(const float* x, int64_t numel, const float* alpha, float lo, float hi,
@@ -228,6 +371,19 @@ extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* out = (__nv_bfloat16*)codes_bf16_out;
   uint8_t* out8 = (uint8_t*)codes_e4m3_out;
+  // v2 (register transpose): full tiles only, channel groups a power of two below 32 or a multiple of 32
+  {
+    const int groups = c / 4;
+    const bool g_ok = (c % 4 == 0) && (groups >= 32 ? groups % 32 == 0 : (groups & (groups - 1)) == 0);
+    static const bool v1_only = [] { const char* v = getenv("EFFQ_QA_V1"); return v && *v == '1'; }();
+    int tv = 0;
+    for (int cand = 256; cand >= 16; cand >>= 1)                  // largest tile that divides dhw and fits 48 KB
+      if (dhw % cand == 0 && (size_t)cand * c * 3 <= 48 * 1024) { tv = cand; break; }
+    // measured (profiles/r01_conv_sweep.md): v2 wins up to C = 128 (47-61 % vs 41-47 % of the HBM peak), v1 above
+    if (g_ok && tv > 0 && !v1_only && c <= 128 && ((uintptr_t)x & 15) == 0 && (!out8 || c % 16 == 0) && (!out || c % 8 == 0))
+      return use_f64 ? launch_quantize_v2<true>(x, n, c, dhw, nlvl, tv, state, alpha_f32, out, out8, s)
+                     : launch_quantize_v2<false>(x, n, c, dhw, nlvl, tv, state, alpha_f32, out, out8, s);
+  }
   const bool big = c <= 64;                     // 256-voxel tiles while the transpose tile stays <= 36 KB
   const int tile_v = big ? 256 : 64;
   const long long tiles = (long long)n * ((dhw + tile_v - 1) / tile_v);

@@ -88,6 +88,37 @@ def test_fakequant_state_and_ndhwc_codes(ops):
         ops.quantize_act_ndhwc(x.to(DEV), 256, state=st, e4m3=True)       # 256 levels do not fit e4m3
 
 
+@pytest.mark.parametrize("n,c,sp,L", [(2, 32, (8, 16, 16), 16), (1, 64, (4, 8, 8), 4), (1, 16, (4, 8, 8), 16),
+                                      (1, 128, (2, 8, 8), 256), (1, 512, (1, 4, 8), 16), (3, 8, (2, 4, 6), 16),
+                                      (1, 256, (5, 5, 4), 4), (1, 24, (2, 4, 8), 16)])
+def test_ndhwc_codes_register_transpose_kernel(ops, n, c, sp, L):
+    """The register-transpose NDHWC kernel (full tiles, dhw % 16 == 0) and the shared-memory one (other
+    shapes) against the oracle's fp64 / fp32 discretize, incl. values planted on and next to rounding ties
+    and clamp boundaries (the fast fp32 index must hand those to the exact sequence)."""
+    torch.manual_seed(c + L)
+    x = torch.relu(torch.randn(n, c, *sp)) * 1.3
+    a, _ = O.project_by_iter(x, L, 0, 1)
+    flat = x.view(-1)
+    k = torch.arange(min(L - 1, 64), dtype=torch.float64)
+    ties = ((k + 0.5) / (L - 1) * a)
+    planted = torch.cat([ties, ties * (1 + 1e-7), ties * (1 - 1e-7), ties * (1 + 3e-5), torch.tensor([a, a * (1 + 1e-7), 0.0])]).float()
+    flat[:planted.numel()] = planted[: flat.numel()]
+    st = ops.ScaleState(torch.device(DEV))
+    st.set_a(a)
+    want = O.discretize_codes(x.double() / a, L, 0, 1).permute(0, 2, 3, 4, 1)
+    codes = ops.quantize_act_ndhwc(x.to(DEV), L, state=st)
+    assert torch.equal(codes.cpu().float().int(), want)
+    alpha = torch.tensor([a], dtype=torch.float32)
+    want32 = O.discretize_codes(x / alpha[0], L, 0, 1).permute(0, 2, 3, 4, 1)
+    codes32 = ops.quantize_act_ndhwc(x.to(DEV), L, alpha=alpha.to(DEV))
+    assert torch.equal(codes32.cpu().float().int(), want32)
+    if L <= 16 and c % 16 == 0:
+        c16, c8 = ops.quantize_act_ndhwc(x.to(DEV), L, state=st, e4m3=True)
+        assert torch.equal(c16, codes) and torch.equal(c8.cpu().float().int(), want)
+        _, c8b = ops.quantize_act_ndhwc(x.to(DEV), L, alpha=alpha.to(DEV), bf16=False, e4m3=True)
+        assert torch.equal(c8b.cpu().float().int(), want32)
+
+
 # ---------------------------------------------------------------- scale search (a3)
 @pytest.mark.parametrize("name,lo,hi", [("act", 0, 1), ("wt", -1, 1)])
 @pytest.mark.parametrize("L", [4, 16, 256])
@@ -216,6 +247,8 @@ TC_CASES = [
     (2, 64, 32, 3, (5, 20, 12), 4, 16),
     (1, 32, 32, 3, (3, 12, 10), 16, 16),     # W % 4 != 0: the epilogue loads the target itself (no target TMA)
     (1, 32, 64, 3, (4, 24, 20), 16, 16),     # two target boxes per tile, ragged H tile
+    (1, 128, 512, 3, (2, 5, 4), 4, 4),       # C2 > 256: two chunks of 256 output channels (LiTS deepest level)
+    (2, 64, 512, 1, (2, 8, 8), 16, 16),      # same with the target TMA ring (W % 4 == 0)
 ]
 
 
@@ -256,6 +289,7 @@ FP8_CASES = [
     (1, 128, 64, 1, (3, 9, 7), 16, 4),
     (1, 256, 128, 3, (2, 8, 8), 16, 16),
     (1, 256, 48, 1, (2, 10, 8), 4, 4),
+    (1, 128, 512, 3, (2, 8, 8), 4, 4),       # chunked C2
 ]
 
 

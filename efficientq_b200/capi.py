@@ -129,9 +129,50 @@ EXPORTS = tuple(_SIGS)
 _lib: Optional[C.CDLL] = None
 
 
+class _Recorder:
+    """Stands in for the library while a launch sequence is being recorded: every entry point still runs,
+    and (function, converted arguments, tag) is appended to ``calls`` so that the same sequence can be
+    re-issued later without the Python wrappers around it (layer_engine: the ADMM iterations of one rho block
+    launch the same kernels on the same buffers; re-issuing them costs ~2 us per launch instead of ~17 us)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self.calls = []
+        self.tag = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+
+        def rec(*args):
+            if fn.restype is C.c_int and fn.argtypes and fn.argtypes[-1] is C.c_void_p and not name.endswith("_supported"):
+                self.calls.append((fn, args, self.tag, name))      # launches only, not size / support queries
+            return fn(*args)
+        return rec
+
+
+_recorder: Optional[_Recorder] = None
+
+
+class record:
+    """``with capi.record() as rec: ...`` -- see _Recorder."""
+
+    def __enter__(self):
+        global _recorder
+        load()
+        _recorder = _Recorder(_lib)
+        return _recorder
+
+    def __exit__(self, *exc):
+        global _recorder
+        _recorder = None
+        return False
+
+
 def load(path: Optional[str] = None) -> C.CDLL:
     """dlopen the kernel library and type every entry point.  Raises if it is absent."""
     global _lib
+    if _recorder is not None and path is None:
+        return _recorder
     if _lib is not None and path is None:
         return _lib
     path = path or LIB_PATH

@@ -285,54 +285,99 @@ class LayerCalibrator:
             bplanes = torch.empty((3, c2, ops.split3_ld(kp)), dtype=torch.bfloat16, device=dev)
             sol_buf = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :kp]
 
+        loop_prof = os.environ.get("EFFQ_LOOP_PROF") == "1"     # bring-up: CPU enqueue time vs GPU time of the loop
+        if loop_prof:
+            import time as _t
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            ev_a.record()
+            t_cpu0 = _t.perf_counter()
+        # Iterations inside one rho block launch the same kernels on the same buffers (the iteration counter,
+        # scales, losses and the best-iterate decision live in device structs), so the launch sequence of the
+        # block's second iteration is recorded once (capi.record) and re-issued for the rest of the block
+        # without the Python wrappers: ~17 us -> ~2 us of host time per launch.  The 1x1x1 layers were
+        # host-bound (19 ms of enqueue for 19 ms of GPU time per layer, profiles/r01_loop_prof.txt).
+        from contextlib import nullcontext
+        from . import capi as _capi
+        replayable = not (dist.world > 1 and stats64 is None and peer is None) and \
+            os.environ.get("EFFQ_REPLAY", "1") != "0"            # an NCCL all-reduce inside the loop cannot be re-issued
+        steady = None
+        sol_small = None if solve_tc else torch.empty((c2, kp), dtype=torch.float32, device=dev)
         for it in range(self.n_iter):
             if rho_built != rho:
                 ainv, ev = inverses[rho]
                 main.wait_event(ev)
                 rho_built = rho
-            # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
-            if solve_tc:
-                if it == 0:     # later right-hand sides come out of admm_project of the previous iteration
-                    ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
-                                  lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
-                sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
-            else:
-                ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
-                sol = ops.timer.run("lib_sgemm_B_Ainv", {"flops": 2.0 * c2 * kp * kp}, lambda: bmat @ ainv)
-            # projection + dual update (EfficientQConv.py:107-111)
-            wview = sol[:, :k] if has_bias else sol
-            ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
-            div = 1.0
-            new_rho = rho
-            if it % self.rho_period == 0:          # EfficientQConv.py:129-137
-                if rho * 2 <= rho_m:
-                    new_rho, div = rho * 2, 2.0
+                steady = None
+            special = it == 0 or it % self.rho_period == 0 or it + 1 == self.n_iter
+            if steady is not None and not special:
+                pre, mm, post = steady
+                ops.replay(pre)
+                if mm is not None:
+                    mm()
+                ops.replay(post)
+                continue
+            recording = replayable and not special
+            with (_capi.record() if recording else nullcontext()) as rec:
+                n_pre = 0
+                mm = None
+                # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
+                if solve_tc:
+                    if it == 0:     # later right-hand sides come out of admm_project of the previous iteration
+                        ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
+                                      lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
+                    sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
                 else:
-                    new_rho, div = rho_m, rho_m / rho
-            nxt = (b0, w0p, new_rho, eta, bplanes) if (solve_tc and it + 1 < self.n_iter) else None
-            ops.timer.run("admm_project", {"bytes": 16 * c2 * k}, lambda: ops.admm_project(
-                sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps, has_bias, div,
-                g, bstar, wcodes, self.st, next_rhs=nxt))
-            # score the iterate (EfficientQConv.py:118-122)
-            if use_tc:
-                ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
-                              target=out_fp, ws=self.tc_ws, sse=self.sse)
-            elif stats64 is not None:
-                ops.quadform_sse(stats64, y_sq, g, bstar, self.sse, self._qf_ws)      # already global
-            else:
-                ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
-                               ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
-            track_comm = None
-            if dist.world > 1 and stats64 is None:                # this rank's share of the squared error
-                if peer is not None:
-                    track_comm = peer.comm_ptr                    # summed inside admm_track over NVLink
+                    ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
+                    n_pre = len(rec.calls) if recording else 0
+                    ainv_now = ainv
+
+                    def mm(ainv_now=ainv_now):
+                        ops.timer.run("lib_sgemm_B_Ainv", {"flops": 2.0 * c2 * kp * kp},
+                                      lambda: torch.matmul(bmat, ainv_now, out=sol_small))
+                    mm()
+                    sol = sol_small
+                # projection + dual update (EfficientQConv.py:107-111)
+                wview = sol[:, :k] if has_bias else sol
+                ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
+                div = 1.0
+                new_rho = rho
+                if it % self.rho_period == 0:          # EfficientQConv.py:129-137
+                    if rho * 2 <= rho_m:
+                        new_rho, div = rho * 2, 2.0
+                    else:
+                        new_rho, div = rho_m, rho_m / rho
+                nxt = (b0, w0p, new_rho, eta, bplanes) if (solve_tc and it + 1 < self.n_iter) else None
+                ops.timer.run("admm_project", {"bytes": 16 * c2 * k}, lambda: ops.admm_project(
+                    sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps, has_bias, div,
+                    g, bstar, wcodes, self.st, next_rhs=nxt))
+                # score the iterate (EfficientQConv.py:118-122)
+                if use_tc:
+                    ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
+                                  target=out_fp, ws=self.tc_ws, sse=self.sse)
+                elif stats64 is not None:
+                    ops.quadform_sse(stats64, y_sq, g, bstar, self.sse, self._qf_ws)      # already global
                 else:
-                    dist.all_reduce_sum(self.sse)
-            ops.timer.run("admm_track", {"bytes": 8 * c2 * k}, lambda: ops.admm_track(
-                self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes,
-                comm=track_comm))
+                    ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
+                                   ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
+                track_comm = None
+                if dist.world > 1 and stats64 is None:                # this rank's share of the squared error
+                    if peer is not None:
+                        track_comm = peer.comm_ptr                    # summed inside admm_track over NVLink
+                    else:
+                        dist.all_reduce_sum(self.sse)
+                ops.timer.run("admm_track", {"bytes": 8 * c2 * k}, lambda: ops.admm_track(
+                    self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes,
+                    comm=track_comm))
+                if recording:
+                    steady = (rec.calls[:n_pre], mm if not solve_tc else None, rec.calls[n_pre:])
             rho = new_rho
 
+        if loop_prof:
+            t_cpu = _t.perf_counter() - t_cpu0
+            ev_b.record()
+            torch.cuda.synchronize(dev)
+            print(f"[loop] {name:45s} K'={kp:5d} C2={c2:3d} tc={int(use_tc)} cpu enqueue {1e3 * t_cpu:8.2f} ms   gpu {ev_a.elapsed_time(ev_b):8.2f} ms")
         # final forward with the best iterate: layer output + attention-weighted loss (:161-166)
         if use_tc:
             out_q, _ = ops.conv3d_tc(xcodes_conv, best_wcodes, best_b, self.st.best_conv_scale_ptr(), c2, ksize,

@@ -24,10 +24,24 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
+        self.only = None             # optional tuple of name prefixes: time just those kernels
         self.records = {}
 
     def run(self, name, work, fn):
-        if not self.enabled:
+        rec = capi._recorder
+        if rec is not None:                  # recording a launch sequence: remember which kernel the calls belong to
+            rec.tag = (name, work)
+            try:
+                return self._run(name, work, fn)
+            finally:
+                rec.tag = None
+        return self._run(name, work, fn)
+
+    def wants(self, name) -> bool:
+        return self.enabled and (self.only is None or name.startswith(self.only))
+
+    def _run(self, name, work, fn):
+        if not self.enabled or (self.only is not None and not name.startswith(self.only)):
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -51,6 +65,18 @@ class KernelTimer:
 
 
 timer = KernelTimer()
+
+
+def replay(calls) -> None:
+    """Re-issue a recorded launch sequence (capi.record) on the current stream: same functions, same
+    arguments.  Kernels the timer wants are still bracketed by CUDA events."""
+    for fn, args, tag, name in calls:
+        if tag is not None and timer.wants(tag[0]):
+            timer._run(tag[0], tag[1], lambda: check(fn(*args), name))
+        else:
+            rc = fn(*args)
+            if rc != 0:
+                check(rc, name)
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:

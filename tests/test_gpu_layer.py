@@ -212,3 +212,22 @@ def test_quantized_forward_uses_stored_weights_not_alpha_w(engine_mod):
     assert m._wcodes_cache[1] is None
     want2 = F.conv3d(O.quantize_act(x, a_act, 16).double(), m.weight.data.cpu().double(), m.bias.data.cpu().double(), 1, 1).float()
     torch.testing.assert_close(got2.cpu(), want2, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["w4a4_k3_c32", "w4a4_k1_c64", "w4a4_k1", "first_k3s2"])
+def test_replayed_iterations_are_bit_identical(engine_mod, golden, name, monkeypatch):
+    """The steady-state iterations of a rho block are re-issued from a recorded launch sequence
+    (capi.record / ops.replay): same kernels, same arguments -> the whole loss history, the scales and the
+    calibrated weights must equal the run that goes through the Python wrappers every iteration."""
+    g = golden("layers_wide.npz" if name in WIDE else "layers.npz")
+    k, s, p, lw, la, qa = [int(t) for t in g[f"{name}_cfg"]]
+    x, w, b, y, att = [torch.from_numpy(g[f"{name}_{t}"]).to(DEV) for t in ("x", "w", "b", "y", "att")]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("EFFQ_REPLAY", flag)
+        eng = engine_mod.LayerCalibrator(torch.device(DEV), keep_history=True)
+        res[flag] = eng.run(x, w, b, y, s, p, lw, la, bool(qa), [att], name=name)
+    (wq1, bq1, aw1, aa1, o1, r1), (wq0, bq0, aw0, aa0, o0, r0) = res["1"], res["0"]
+    assert r1.history == r0.history and r1.best_iter == r0.best_iter
+    assert torch.equal(wq1, wq0) and torch.equal(bq1, bq0) and torch.equal(o1, o0)
+    assert float(aw1) == float(aw0)

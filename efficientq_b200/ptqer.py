@@ -233,4 +233,5 @@ def do_ptq(args, model_cube, data_cube, tester, snap_dir, dist: Optional[DistCtx
         store_int_weight(model)
         snapshot.save(model, P.join(snap_dir, "state_in_int8.pkl"), compress=False)
         snapshot.save(model, P.join(snap_dir, "state_in_int8_compress.npz"), compress=True)
+        snapshot.save_packed(model, P.join(snap_dir, "state_in_packed.npz"))     # extension: 2 / 4 / 8-bit packed codes
     return res

@@ -14,3 +14,71 @@ def save(model, filename: str, compress: bool = False) -> None:
         np.savez_compressed(filename, state)
     else:
         torch.save(state, filename)
+
+
+# ---- extension: true sub-byte packing ---------------------------------------------------------
+# The reference stores one uint8 per weight whatever the bit width (PTQConv.py:125-142).  For layers with
+# <= 16 levels two codes fit a byte, with <= 4 levels four: ``state_in_packed.npz`` holds, per quantizer
+# layer, the packed codes + shape + level count + alpha_w (everything else of the state dict unchanged), and
+# ``load_packed`` rebuilds exactly the state dict ``save(model after store_int_weight)`` would have written.
+def _bits_for(levels: int) -> int:
+    return 2 if levels <= 4 else 4 if levels <= 16 else 8
+
+
+def pack_codes(codes: np.ndarray, levels: int) -> np.ndarray:
+    """uint8 codes in [0, levels) -> bytes with 8 // bits codes each (little end first)."""
+    bits = _bits_for(levels)
+    flat = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1)
+    if flat.size and int(flat.max()) >= (1 << bits):
+        raise ValueError(f"code {int(flat.max())} does not fit {bits} bits")
+    per = 8 // bits
+    pad = (-flat.size) % per
+    if pad:
+        flat = np.concatenate([flat, np.zeros(pad, dtype=np.uint8)])
+    flat = flat.reshape(-1, per)
+    out = np.zeros(flat.shape[0], dtype=np.uint8)
+    for j in range(per):
+        out |= (flat[:, j] << (bits * j)).astype(np.uint8)
+    return out
+
+
+def unpack_codes(packed: np.ndarray, levels: int, numel: int) -> np.ndarray:
+    bits = _bits_for(levels)
+    per = 8 // bits
+    mask = (1 << bits) - 1
+    cols = [(packed >> (bits * j)) & mask for j in range(per)]
+    return np.stack(cols, axis=1).reshape(-1)[:numel].astype(np.uint8)
+
+
+def save_packed(model, filename: str) -> None:
+    """Call after ``store_int_weight`` (the quantizer layers' weights are uint8 codes)."""
+    from .qconv import PTQConv
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    out = {}
+    packed_keys = []
+    for name, m in model.named_modules():
+        if isinstance(m, PTQConv) and m.weight.dtype == torch.uint8 and m.qlvl_w <= 256:
+            key = f"{name}.weight"
+            codes = sd.pop(key)
+            out[f"packed::{key}"] = pack_codes(codes, m.qlvl_w)
+            out[f"shape::{key}"] = np.array(codes.shape, dtype=np.int64)
+            out[f"levels::{key}"] = np.int64(m.qlvl_w)
+            packed_keys.append(key)
+    out.update({f"raw::{k}": v for k, v in sd.items()})
+    print(f"Snapshotting to {filename} ({len(packed_keys)} packed layers)")
+    np.savez_compressed(filename, **out)
+
+
+def load_packed(filename: str) -> dict:
+    """-> {"state_dict": {...}} with uint8 codes for the quantizer layers, as ``state_in_int8.pkl`` holds."""
+    z = np.load(filename, allow_pickle=False)
+    sd = {}
+    for k in z.files:
+        kind, key = k.split("::", 1)
+        if kind == "raw":
+            sd[key] = torch.from_numpy(z[k])
+        elif kind == "packed":
+            shape = tuple(int(t) for t in z[f"shape::{key}"])
+            codes = unpack_codes(z[k], int(z[f"levels::{key}"]), int(np.prod(shape)))
+            sd[key] = torch.from_numpy(codes.reshape(shape))
+    return {"state_dict": sd}

@@ -127,3 +127,39 @@ def test_adam_update_matches_torch(golden):
     for k in range(3):
         p, m, v = O.adam_update(p, torch.from_numpy(g["adam::grads"][k]), m, v, k + 1)
         np.testing.assert_allclose(p.numpy(), g["adam::traj"][k], rtol=2e-7, atol=0)
+
+
+@pytest.mark.parametrize("task", ["brats", "lits"])
+def test_att_map_and_pyramid_match_reference_on_toy_nets(golden, task):
+    """a12 on real network outputs: class voxel counts, class weights and the means of the five pyramid
+    masks the REFERENCE computed on the toy nets (BraTS: nested sigmoid labels, body = non-zero voxels;
+    LiTS: softmax/argmax, all-ones body, init_stride 2,2,1) vs the oracle on the same FP output.  The FP
+    forward of the host mirror is stock PyTorch, so it runs on the CPU."""
+    import torch.nn as nn
+    from efficientq_b200 import fold_bn, model_blk, qconv, synth
+    from tests.golden.make_golden import TOY, TOY_LITS
+    cfg = TOY if task == "brats" else TOY_LITS
+    g = golden("toy_net.npz" if task == "brats" else "toy_net_lits.npz")
+    hetero = {"drop_cut_thres": 128, "ds_depth_limit": 3, "aniso_pool_depth": 9999, "aniso_pool_stride": (2, 2, 1)}
+    model = model_blk.UResQ(qconv.EfficientQConv, cfg["num_mod"], cfg["num_classes"], depth_config=cfg["depth"],
+                            width_config=cfg["width"], dilation_config=cfg["dilation"], init_stride=cfg["init_stride"],
+                            stride=2, drop_rate=cfg["drop_rate"], nla=model_blk.ReLU(True), bn=nn.BatchNorm3d,
+                            ds=cfg["ds"], blk_type=cfg["blk"], q_weight=True, qlvl=cfg["qlvl"], q_act=True,
+                            qlvl_act=cfg["qlvl_act"], q_first=cfg["q_first"], q_last=cfg["q_last"],
+                            hetero_param=hetero, fuse_bn=True, save_mem=True, init_kernel=3)
+    model.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=False)
+    model.eval()
+    fold_bn.search_fold_and_remove_bn(model)
+    size = cfg["size"] if isinstance(cfg["size"], tuple) else (cfg["size"],) * 3
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], size, cfg["task"])
+    assert abs(data.double().sum().item() - float(g["data_checksum"])) < 1e-6
+    with torch.no_grad():
+        out_fp = model(data)
+    assert abs(out_fp.double().sum().item() - float(g["out_fp_sum"])) <= 1e-5 * abs(float(g["out_fp_sum"])) + 1e-3
+    body = (data[:, 0] != 0.0) if task == "brats" else torch.ones_like(data[:, 0]).bool()
+    wmap, nums = O.att_weight_map(out_fp, torch.ones_like(data[:, 0]).bool(), 0.5, task)   # reference passes all ones
+    assert nums == [int(v) for v in g["class_nums"]]
+    np.testing.assert_allclose([wmap[k] for k in sorted(wmap)], g["wmap"], rtol=1e-12)
+    pyr = O.mask_pyramid(out_fp, body, wmap, cfg["init_stride"], 5, task)
+    np.testing.assert_allclose([p.mean().item() for p in pyr], g["pyr_means"], rtol=1e-6)
+    assert np.array_equal(pyr[0].numpy().astype(np.uint8), g["pyr0"])

@@ -420,6 +420,78 @@ def gen_toy_tune(R, out, n_tune=3):
     np.savez_compressed(os.path.join(out, "toy_tune.npz"), **res)
 
 
+def dice_table(pred, label, n_cls=3):
+    """Per-class Dice with the reference's formula (src/utils/metrics.py:21-25)."""
+    out = []
+    for k in range(1, n_cls + 1):
+        pb, tb = (pred == k), (label == k)
+        out.append(float((2 * (pb & tb).sum().float() + 1e-6) / (pb.sum().float() + tb.sum().float() + 1e-6)))
+    return out
+
+
+def gen_toy_dice(R, out, steps=160):
+    """Final-Dice parity case (BASELINE north star: "final Dice within 0.1 points"): a BraTS miniature TRAINED
+    with stock PyTorch on the synthetic nested-sphere volumes (so that Dice is non-degenerate), then the
+    reference's do_ptq core at W4A4 on 2 calibration volumes, and Dice of the FP and of the quantised model
+    on 4 held-out volumes (full-volume forward, nested-sigmoid prediction of metrics.py:182-192)."""
+    from efficientq_b200 import synth
+    ptqer = R["ptqer"]
+    cfg = TOY
+    torch.manual_seed(cfg["seed"] + 100)
+    model = build_toy(R, R["effq"].EfficientQConv, cfg)
+    model.load_state_dict(seeded_state(model, cfg["seed"]), strict=False)
+    ptqer.set_fp(model)
+    vols = [synth.volume(i, cfg["num_mod"], (cfg["size"],) * 3, "brats") for i in range(8)]
+    opt = torch.optim.Adam([p for n, p in model.named_parameters() if "alpha" not in n], lr=2e-3)
+    model.train()
+    for step in range(steps):
+        idx = [(2 * step) % 8, (2 * step + 1) % 8]
+        x = torch.stack([vols[i][0] for i in idx])
+        lab = torch.stack([vols[i][1] for i in idx]).long()
+        tgt = torch.stack([(lab >= k).float() for k in (1, 2, 3)], 1)          # nested regions <-> get_pred_brats
+        o = model(x)                                                            # (M, N, 3, D, H, W)
+        loss = sum(F.binary_cross_entropy_with_logits(o[m], tgt) for m in range(o.shape[0]))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if step % 20 == 0:
+            print("train step", step, float(loss))
+    model.eval()
+    trained = {k: v.detach().clone() for k, v in model.state_dict().items() if not k.endswith(("alpha_act", "alpha_w"))}
+    R["fold_bn"].search_fold_and_remove_bn(model)
+    ev = [synth.volume(100 + i, cfg["num_mod"], (cfg["size"],) * 3, "brats") for i in range(4)]
+    ev_x = torch.stack([v[0] for v in ev])
+    ev_l = torch.stack([v[1] for v in ev]).long()
+    metrics = R["ptqer"].metrics if hasattr(R["ptqer"], "metrics") else None
+    from utils import metrics as M_                                            # reference's get_pred_brats
+    with torch.no_grad():
+        dice_fp = dice_table(M_.get_pred_brats(model(ev_x)[-1]), ev_l)
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
+    ptqer.set_name(model)
+    handles = [m.register_forward_hook(R["hooks"].forward_hook) for m in model.modules()
+               if isinstance(m, R["ptqconv"].PTQConv)]
+    with torch.no_grad():
+        output_fp = model(data).detach()
+    body = (data[:, 0] != 0.0).bool()
+    wmap, _ = ptqer.get_att_weight_map(output_fp, torch.ones_like(data[:, 0]).bool(), "p:0.5", task="brats")
+    ptqer.set_mask(model, ptqer.get_mask_pyramid(output_fp, body, wmap, "2,2,2", num_lvls=5, task="brats"))
+    for h in handles:
+        h.remove()
+    layer_loss = []
+    ptqer.set_anything(model, "layer_loss", layer_loss)
+    ptqer.set_quantizing(model)
+    with torch.no_grad():
+        model(data)
+    ptqer.set_quantized(model)
+    with torch.no_grad():
+        dice_q = dice_table(M_.get_pred_brats(model(ev_x)[-1]), ev_l)
+    res = {f"sd::{k}": v.numpy() for k, v in trained.items()}
+    res["dice_fp"], res["dice_q"] = np.array(dice_fp), np.array(dice_q)
+    res["layer_losses"] = np.array([float(ln.rsplit(":", 1)[1]) for ln in layer_loss])
+    print("Dice FP", dice_fp, "mean", np.mean(dice_fp), "| Dice W4A4 (reference)", dice_q, "mean", np.mean(dice_q))
+    np.savez_compressed(os.path.join(out, "toy_dice.npz"), **res)
+
+
 def gen_toy_net_lits(R, out):
     gen_toy_net(R, out, TOY_LITS, "toy_net_lits.npz")
 
@@ -433,7 +505,7 @@ def main():
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
                 solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
-                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune)
+                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

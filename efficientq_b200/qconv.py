@@ -132,10 +132,24 @@ class PTQConv(nn.Conv3d):
                 odd = torch.remainder(codes + lm1, 2.0) == 0
                 exact = (codes * (a / lm1) - w).abs().max() <= 1e-6 * wmax
                 if bool((odd.all() & exact & (wmax > 0)).item()):
-                    found = (ops.pack_weight_codes(codes, code_dtype), a.reshape(1).clone())
+                    found = (ops.pack_weight_codes(codes, code_dtype), a.reshape(1).clone(), codes)
                     break
             self._wcodes_cache = (key, found)
         return self._wcodes_cache[1]
+
+    def _dgrad_operands(self):
+        """(packed codes, scale) of the TRANSPOSED, spatially flipped weights for the tensor-core dgrad of a
+        stride-1 layer (d qact = conv(d out, W^T flipped)), or None when the weights are on no exact grid.
+        Cached with the weights."""
+        wc = self._weight_codes(ops.CODE_BF16)
+        if wc is None:
+            return None
+        key = self._wcodes_cache[0]
+        if getattr(self, "_dgrad_cache", None) is None or self._dgrad_cache[0] != key:
+            codes_t = wc[2].flip(2, 3, 4).transpose(0, 1).contiguous()              # [C1][C2][kd][kh][kw]
+            scale = (wc[1].double() / (self.qlvl_w - 1)).float().reshape(1)
+            self._dgrad_cache = (key, (ops.pack_weight_codes(codes_t, ops.CODE_BF16), scale))
+        return self._dgrad_cache[1]
 
     def _quantized_forward(self, x):
         """Deployment forward (PTQConv.py:163-167): fake-quant activations + conv with the stored
@@ -150,7 +164,7 @@ class PTQConv(nn.Conv3d):
                                         ops.CODE_E4M3)
             wc = self._weight_codes(ops.CODE_E4M3 if fp8 else ops.CODE_BF16)
             if wc is not None:                  # weights on an exact L-level grid (always, after calibration)
-                wcodes, w_scale = wc
+                wcodes, w_scale, _ = wc
                 if fp8:
                     _, xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data, bf16=False, e4m3=True)
                 else:

@@ -9,8 +9,10 @@ output.  The reference defines it but never calls it from ``do_ptq``; here it is
 What runs where:
   * forward of a quantizer layer: the deployment forward (fake-quant codes + tcgen05 conv,
     ``PTQConv._quantized_forward``);
-  * backward of a quantizer layer: conv dgrad (library: ``torch.nn.grad.conv3d_input``), then ONE pass of
-    ``effq_fakequant_ste_bwd`` producing grad_x and d loss / d alpha_act (csrc/tune.cu);
+  * backward of a quantizer layer: conv dgrad -- on the tcgen05 conv kernel for stride-1 layers with >= 16
+    channels (``conv_dgrad``: integer weight codes x three exact bf16 planes of the gradient), the library's
+    ``torch.nn.grad.conv3d_input`` otherwise -- then ONE pass of ``effq_fakequant_ste_bwd`` producing grad_x
+    and d loss / d alpha_act (csrc/tune.cu);
   * glue ops between the layers (ReLU, pooling, upsampling, residual adds): stock autograd;
   * the optimiser: ``effq_adam_step`` on the flat vector that all ``alpha_act`` parameters alias;
   * sharded calibration: each rank differentiates its own volumes, the alpha gradients (<= 28
@@ -19,6 +21,7 @@ Weights are frozen (the reference computes their gradients and throws them away)
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -29,6 +32,33 @@ from .dist import DistCtx
 from .qconv import PTQConv
 
 __all__ = ["tune_activation_range"]
+
+
+def conv_dgrad(mod: PTQConv, x_shape, grad_out: torch.Tensor) -> torch.Tensor:
+    """d loss / d qact of a quantizer layer.  Stride-1 3x3x3 / 1x1x1 layers whose weights lie on their L-level grid
+    run on the tcgen05 conv kernel: dgrad = conv(grad_out, flipped W^T) with the integer weight codes as one
+    operand and grad_out as THREE bf16 planes (hi + mid + lo = the fp32 value exactly, so every product is exact
+    and the result has fp32-conv accuracy), one launch per plane.  Other shapes: the library's fp32 dgrad."""
+    n, c1, d, h, w = x_shape
+    c2 = mod.out_channels
+    ks = mod.kernel_size
+    ok = mod.q_weight and mod.qlvl_w <= 256 and tuple(mod.stride) == (1, 1, 1) and \
+        tuple(mod.padding) == tuple((k - 1) // 2 for k in ks) and \
+        ops.conv3d_tc_supported((n, c2, d, h, w), c1, ks, 1, mod.padding) and os.environ.get("EFFQ_DGRAD_TC", "1") != "0"
+    opnd = mod._dgrad_operands() if ok else None
+    if opnd is None:
+        return torch.nn.grad.conv3d_input(x_shape, mod.weight.data, grad_out.contiguous(), mod.stride, mod.padding)
+    wcodes_t, scale = opnd
+    g = grad_out.permute(0, 2, 3, 4, 1).contiguous()                 # NDHWC fp32 (layout glue)
+    hi = g.to(torch.bfloat16)
+    r1 = g - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    out, _ = ops.conv3d_tc(hi, wcodes_t, None, scale, c1, ks, want_out=True)
+    for plane in (mid, lo):
+        part, _ = ops.conv3d_tc(plane, wcodes_t, None, scale, c1, ks, want_out=True)
+        out += part
+    return out
 
 
 class _QuantLayerSTE(torch.autograd.Function):
@@ -47,7 +77,7 @@ class _QuantLayerSTE(torch.autograd.Function):
     def backward(ctx, grad_out):
         (x,) = ctx.saved_tensors
         mod = ctx.mod
-        g_qact = torch.nn.grad.conv3d_input(x.shape, mod.weight.data, grad_out.contiguous(), mod.stride, mod.padding)
+        g_qact = conv_dgrad(mod, x.shape, grad_out)
         gx = ops.fakequant_ste_bwd(x, g_qact, ctx.alpha_view, mod.qlvl_act, 0.0, 1.0, ctx.grad_slot,
                                    want_grad_x=ctx.needs_input_grad[0])
         return gx, None, None, None, None

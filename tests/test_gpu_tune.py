@@ -132,3 +132,30 @@ def test_tune_activation_range_matches_reference(ops, golden):
     for name, m in mods.items():
         if not m.q_act:
             assert float(m.alpha_act) == 1.0 and m._tune_ctx is None
+
+
+@pytest.mark.parametrize("n,c1,c2,k,sp,lw", [(2, 32, 32, 3, (6, 16, 8), 16), (1, 64, 32, 1, (4, 8, 8), 16),
+                                             (1, 32, 64, 3, (3, 10, 12), 4), (1, 128, 128, 3, (2, 8, 8), 256)])
+def test_tensor_core_dgrad_matches_fp64(ops, n, c1, c2, k, sp, lw):
+    """conv dgrad of a quantizer layer on the tcgen05 conv (integer weight codes x 3 exact bf16 planes of the
+    gradient) against the fp64 transposed convolution; and the library path it replaces for comparison."""
+    import torch.nn as nn
+    from efficientq_b200 import tune
+    from efficientq_b200.qconv import EfficientQConv
+    from oracle import effq_oracle as O
+    torch.manual_seed(c1 + c2 + k)
+    m = EfficientQConv(c1, c2, k, 1, (k - 1) // 2, bias=True, q_weight=True, qlvl=lw, q_act=True, qlvl_act=16)
+    a_w = torch.tensor(0.173)
+    m.weight.data = O.quantize_w(torch.randn(c2, c1, k, k, k) * 0.1, a_w, lw)
+    m.alpha_w.data = a_w * 0.97                      # the reference's alpha_w does not describe the weights
+    m.to(DEV)
+    go = (torch.randn(n, c2, *sp) * torch.exp(torch.randn(n, c2, *sp))).to(DEV)
+    want = torch.nn.grad.conv3d_input((n, c1, *sp), m.weight.data.double(), go.double(), 1, (k - 1) // 2)
+    got = tune.conv_dgrad(m, (n, c1, *sp), go)
+    assert getattr(m, "_dgrad_cache", None) is not None          # the tensor-core path was taken
+    scale = want.abs().max().item()
+    err_tc = (got.double() - want).abs().max().item() / scale
+    lib = torch.nn.grad.conv3d_input((n, c1, *sp), m.weight.data, go, 1, (k - 1) // 2)
+    err_lib = (lib.double() - want).abs().max().item() / scale
+    print(f"dgrad rel err: tcgen05 {err_tc:.2e}, library fp32 {err_lib:.2e}")
+    assert err_tc <= 5e-6

@@ -121,6 +121,9 @@ class PTQConv(nn.Conv3d):
         reference's quantized forward uses the stored weights as they are (PTQConv.py:163-167).
         Cached until the weights change (one host read per weight version)."""
         key = (self.weight.data_ptr(), self.weight._version, code_dtype)
+        if getattr(self, "_wcodes_by_dtype", None) is None:
+            self._wcodes_by_dtype = {}                    # one entry per operand type (forward: e4m3, dgrad: bf16)
+        self._wcodes_cache = self._wcodes_by_dtype.get(code_dtype)
         if self._wcodes_cache is None or self._wcodes_cache[0] != key:
             w = self.weight.data.float()
             lm1 = float(self.qlvl_w - 1)
@@ -134,7 +137,7 @@ class PTQConv(nn.Conv3d):
                 if bool((odd.all() & exact & (wmax > 0)).item()):
                     found = (ops.pack_weight_codes(codes, code_dtype), a.reshape(1).clone(), codes)
                     break
-            self._wcodes_cache = (key, found)
+            self._wcodes_cache = self._wcodes_by_dtype[code_dtype] = (key, found)
         return self._wcodes_cache[1]
 
     def _dgrad_operands(self):

@@ -116,6 +116,9 @@ _SIGS = {
     "effq_ste_bwd_workspace": (C.c_int64, []),
     "effq_fakequant_ste_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_split3_ndhwc_supported": (C.c_int, [C.c_int32, C.c_int64]),
+    "effq_split3_ndhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "effq_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "effq_peer_bytes": (C.c_int64, []),

@@ -136,7 +136,121 @@ __global__ void adam_step_kernel(float* __restrict__ p, const double* __restrict
   p[i] = __fadd_rn(p[i], __fmul_rn(-step_size, __fdiv_rn(m1, denom)));
 }
 
+// NCDHW fp32 -> three NDHWC bf16 planes with hi + mid + lo == x exactly (24 significant bits): the operand
+// format of the tensor-core dgrad (tune.conv_dgrad).  Same data movement as quantize_act_ndhwc_v2 (fakequant.cu):
+// a thread owns 4 channels x 4 consecutive voxels, transposes in registers, writes 8-byte 4-channel packs into
+// shared-memory tiles that already have the output layout (store order rotated per lane -> conflict free), and
+// the tiles leave as straight 16-byte copies.  Persistent, 10 B per element instead of ~38 B for the
+// permute + five elementwise passes it replaces.
+constexpr int SP_THREADS = 256;
+
+__device__ __forceinline__ void split3(float v, float& hi, float& mid, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(v));
+  const float r1 = __fsub_rn(v, hi);                 // exact (Sterbenz / 16 leftover bits)
+  mid = __bfloat162float(__float2bfloat16_rn(r1));
+  lo = __bfloat162float(__float2bfloat16_rn(__fsub_rn(r1, mid)));
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+split3_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int tile_v, long long n_tiles,
+                    __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_mid, __nv_bfloat16* __restrict__ o_lo) {
+  extern __shared__ __align__(16) uint8_t sp_raw[];
+  uint2* tiles[3];
+  for (int p = 0; p < 3; ++p) tiles[p] = reinterpret_cast<uint2*>(sp_raw + (size_t)p * tile_v * c * 2);
+  __nv_bfloat16* outs[3] = {o_hi, o_mid, o_lo};
+  const long long tiles_per_sample = dhw / tile_v;
+  const int groups = c >> 2;
+  const int gw = groups < 32 ? groups : 32;
+  const int vqw = 32 / gw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % gw, lq = lane / gw;
+  const int quads = tile_v >> 2;
+  const int gblocks = (groups + gw - 1) / gw;
+  const int items = gblocks * ((quads + vqw - 1) / vqw);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long n_idx = tile / tiles_per_sample;
+    const long long v0 = (tile % tiles_per_sample) * tile_v;
+    const float* xs = x + n_idx * (long long)c * dhw + v0;
+    for (int it = warp; it < items; it += SP_THREADS / 32) {
+      const int g4 = (it % gblocks) * gw + lg, vq = (it / gblocks) * vqw + lq;
+      if (g4 >= groups || vq >= quads) continue;
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(xs + (long long)(4 * g4 + k) * dhw) + vq);
+      uint2 pk[3][4];                                           // [plane][voxel]: 4 channels as bf16
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float h[4], m[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float val = i == 0 ? v[k].x : i == 1 ? v[k].y : i == 2 ? v[k].z : v[k].w;
+          split3(val, h[k], m[k], l[k]);
+        }
+        const float* src[3] = {h, m, l};
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const __nv_bfloat162 a = __floats2bfloat162_rn(src[p][0], src[p][1]);
+          const __nv_bfloat162 b = __floats2bfloat162_rn(src[p][2], src[p][3]);
+          pk[p][i].x = *reinterpret_cast<const uint32_t*>(&a);
+          pk[p][i].y = *reinterpret_cast<const uint32_t*>(&b);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int vi = (i + lq) & 3;
+        const int row = 4 * vq + vi;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint2 w = vi == 0 ? pk[p][0] : vi == 1 ? pk[p][1] : vi == 2 ? pk[p][2] : pk[p][3];
+          tiles[p][row * groups + g4] = w;
+        }
+      }
+    }
+    __syncthreads();
+    const int n16 = tile_v * c / 8;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      uint4* dst = reinterpret_cast<uint4*>(outs[p] + (n_idx * dhw + v0) * c);
+      const uint4* src = reinterpret_cast<const uint4*>(tiles[p]);
+      for (int e = threadIdx.x; e < n16; e += SP_THREADS) dst[e] = src[e];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace effq
+
+extern "C" int effq_split3_ndhwc_supported(int32_t c, int64_t dhw) {
+  const int groups = c / 4;
+  const bool g_ok = c > 0 && c % 8 == 0 && (groups >= 32 ? groups % 32 == 0 : (groups & (groups - 1)) == 0);
+  if (!g_ok) return 0;
+  for (int cand = 256; cand >= 16; cand >>= 1)
+    if (dhw % cand == 0 && (long long)cand * c <= 8192) return cand;
+  return 0;
+}
+
+extern "C" int effq_split3_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, void* hi_out, void* mid_out,
+                                 void* lo_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && hi_out && mid_out && lo_out, "null pointer");
+  const int tile_v = effq_split3_ndhwc_supported(c, dhw);
+  EFFQ_CHECK_ARG(tile_v > 0, "shape not supported (c % 8, channel groups a power of two or a multiple of 32, dhw % 16)");
+  EFFQ_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)hi_out & 15) == 0 && ((uintptr_t)mid_out & 15) == 0 &&
+                     ((uintptr_t)lo_out & 15) == 0, "pointers must be 16B aligned");
+  if (n <= 0) return 0;
+  const long long n_tiles = (long long)n * (dhw / tile_v);
+  const long long cap = (long long)sm_count() * 4;
+  const size_t smem = (size_t)tile_v * c * 6;
+  static bool configured = false;
+  if (!configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(split3_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  split3_ndhwc_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), SP_THREADS, smem, (cudaStream_t)stream>>>(
+      x, c, dhw, tile_v, n_tiles, (__nv_bfloat16*)hi_out, (__nv_bfloat16*)mid_out, (__nv_bfloat16*)lo_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int64_t effq_ste_bwd_workspace(void) { return 16 + 8 * (int64_t)effq::STE_MAX_BLOCKS; }
 

@@ -563,3 +563,18 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
     check(capi.load().effq_adam_step(ptr(params), ptr(grads), float(grad_scale), ptr(exp_avg), ptr(exp_avg_sq),
                                      params.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
                                      stream()), "effq_adam_step")
+
+
+def split3_ndhwc(x: torch.Tensor):
+    """NCDHW fp32 -> (hi, mid, lo) NDHWC bf16 planes with hi + mid + lo == x exactly (operand of the tensor-core
+    dgrad), one fused pass; None when the shape is not handled (caller falls back to elementwise ops)."""
+    x = _f32c(x, "x")
+    n, c, d, h, w = x.shape
+    lib = capi.load()
+    if not lib.effq_split3_ndhwc_supported(c, d * h * w):
+        return None
+    planes = [torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device) for _ in range(3)]
+    timer.run("split3_ndhwc", {"bytes": 10 * x.numel()}, lambda: check(
+        lib.effq_split3_ndhwc(ptr(x), n, c, d * h * w, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), stream()),
+        "effq_split3_ndhwc"))
+    return planes

@@ -49,11 +49,14 @@ def conv_dgrad(mod: PTQConv, x_shape, grad_out: torch.Tensor) -> torch.Tensor:
     if opnd is None:
         return torch.nn.grad.conv3d_input(x_shape, mod.weight.data, grad_out.contiguous(), mod.stride, mod.padding)
     wcodes_t, scale = opnd
-    g = grad_out.permute(0, 2, 3, 4, 1).contiguous()                 # NDHWC fp32 (layout glue)
-    hi = g.to(torch.bfloat16)
-    r1 = g - hi.float()
-    mid = r1.to(torch.bfloat16)
-    lo = (r1 - mid.float()).to(torch.bfloat16)
+    planes = ops.split3_ndhwc(grad_out)                              # fused layout change + exact 3-plane split
+    if planes is None:                                               # odd shapes: the same with stock elementwise ops
+        g = grad_out.permute(0, 2, 3, 4, 1).contiguous()
+        hi = g.to(torch.bfloat16)
+        r1 = g - hi.float()
+        mid = r1.to(torch.bfloat16)
+        planes = [hi, mid, (r1 - mid.float()).to(torch.bfloat16)]
+    hi, mid, lo = planes
     out, _ = ops.conv3d_tc(hi, wcodes_t, None, scale, c1, ks, want_out=True)
     for plane in (mid, lo):
         part, _ = ops.conv3d_tc(plane, wcodes_t, None, scale, c1, ks, want_out=True)

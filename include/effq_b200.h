@@ -284,6 +284,11 @@ int64_t effq_ste_bwd_workspace(void);
 int effq_fakequant_ste_bwd(const float* x, const float* grad_out, int64_t numel, const float* alpha,
                            float lo, float hi, int32_t nlvl, float* grad_x_out, double* grad_alpha_acc,
                            void* workspace, void* stream);
+/* Operand of the tensor-core dgrad: NCDHW fp32 -> three NDHWC bf16 planes, hi + mid + lo == x exactly.
+ * effq_split3_ndhwc_supported returns the tile size (> 0) when the shape is handled. */
+int effq_split3_ndhwc_supported(int32_t c, int64_t dhw);
+int effq_split3_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, void* hi_out, void* mid_out,
+                      void* lo_out, void* stream);
 /* torch.optim.Adam update (no weight decay / amsgrad) of n fp32 scalars from fp64 gradients scaled by
  * grad_scale (1/world after an all-reduce); step counts from 1. */
 int effq_adam_step(float* params, const double* grads, float grad_scale, float* exp_avg, float* exp_avg_sq,

@@ -159,3 +159,21 @@ def test_tensor_core_dgrad_matches_fp64(ops, n, c1, c2, k, sp, lw):
     err_lib = (lib.double() - want).abs().max().item() / scale
     print(f"dgrad rel err: tcgen05 {err_tc:.2e}, library fp32 {err_lib:.2e}")
     assert err_tc <= 5e-6
+
+
+@pytest.mark.parametrize("n,c,sp", [(2, 32, (4, 8, 8)), (1, 64, (2, 16, 16)), (1, 16, (4, 8, 8)), (1, 128, (2, 8, 8)),
+                                    (1, 512, (1, 4, 4)), (3, 8, (2, 4, 6))])
+def test_split3_ndhwc_planes_are_exact(ops, n, c, sp):
+    """Fused NCDHW fp32 -> 3 NDHWC bf16 planes: hi + mid + lo must equal x exactly, in the channels-last layout."""
+    torch.manual_seed(c)
+    x = torch.randn(n, c, *sp) * torch.exp(torch.randn(n, c, *sp) * 4)
+    x.view(-1)[:3] = torch.tensor([0.0, -0.0, 1.0])
+    planes = ops.split3_ndhwc(x.to(DEV))
+    dhw = sp[0] * sp[1] * sp[2]
+    if dhw % 16 != 0:
+        assert planes is None
+        return
+    assert planes is not None and all(p.shape == (n, *sp, c) and p.dtype == torch.bfloat16 for p in planes)
+    total = sum(p.double() for p in planes).cpu()
+    assert torch.equal(total, x.permute(0, 2, 3, 4, 1).double())
+    assert torch.equal(planes[0].cpu(), x.permute(0, 2, 3, 4, 1).to(torch.bfloat16))

@@ -25,9 +25,20 @@ def _bits_for(levels: int) -> int:
     return 2 if levels <= 4 else 4 if levels <= 16 else 8
 
 
-def pack_codes(codes: np.ndarray, levels: int) -> np.ndarray:
-    """uint8 codes in [0, levels) -> bytes with 8 // bits codes each (little end first)."""
+def bits_needed(codes: np.ndarray, levels: int) -> int:
+    """Bits per code for a layer: from the level count, widened when the stored codes do not fit.  (The reference
+    derives the codes with alpha_w of the LAST ADMM iterate while the weights are the BEST iterate's
+    (EfficientQConv.py:155-158), so round((w/alpha_w + 1)/delta) can exceed levels - 1.)"""
     bits = _bits_for(levels)
+    mx = int(codes.max()) if codes.size else 0
+    while bits < 8 and mx >= (1 << bits):
+        bits *= 2
+    return bits
+
+
+def pack_codes(codes: np.ndarray, levels: int, bits: int = 0) -> np.ndarray:
+    """uint8 codes -> bytes with 8 // bits codes each (little end first); bits defaults to the level count's."""
+    bits = bits or _bits_for(levels)
     flat = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1)
     if flat.size and int(flat.max()) >= (1 << bits):
         raise ValueError(f"code {int(flat.max())} does not fit {bits} bits")
@@ -42,8 +53,8 @@ def pack_codes(codes: np.ndarray, levels: int) -> np.ndarray:
     return out
 
 
-def unpack_codes(packed: np.ndarray, levels: int, numel: int) -> np.ndarray:
-    bits = _bits_for(levels)
+def unpack_codes(packed: np.ndarray, levels: int, numel: int, bits: int = 0) -> np.ndarray:
+    bits = bits or _bits_for(levels)
     per = 8 // bits
     mask = (1 << bits) - 1
     cols = [(packed >> (bits * j)) & mask for j in range(per)]
@@ -60,9 +71,11 @@ def save_packed(model, filename: str) -> None:
         if isinstance(m, PTQConv) and m.weight.dtype == torch.uint8 and m.qlvl_w <= 256:
             key = f"{name}.weight"
             codes = sd.pop(key)
-            out[f"packed::{key}"] = pack_codes(codes, m.qlvl_w)
+            bits = bits_needed(codes, m.qlvl_w)
+            out[f"packed::{key}"] = pack_codes(codes, m.qlvl_w, bits)
             out[f"shape::{key}"] = np.array(codes.shape, dtype=np.int64)
             out[f"levels::{key}"] = np.int64(m.qlvl_w)
+            out[f"bits::{key}"] = np.int64(bits)
             packed_keys.append(key)
     out.update({f"raw::{k}": v for k, v in sd.items()})
     print(f"Snapshotting to {filename} ({len(packed_keys)} packed layers)")
@@ -75,10 +88,13 @@ def load_packed(filename: str) -> dict:
     sd = {}
     for k in z.files:
         kind, key = k.split("::", 1)
+        if kind in ("shape", "levels", "bits"):
+            continue
         if kind == "raw":
             sd[key] = torch.from_numpy(z[k])
         elif kind == "packed":
             shape = tuple(int(t) for t in z[f"shape::{key}"])
-            codes = unpack_codes(z[k], int(z[f"levels::{key}"]), int(np.prod(shape)))
+            bits = int(z[f"bits::{key}"]) if f"bits::{key}" in z.files else 0
+            codes = unpack_codes(z[k], int(z[f"levels::{key}"]), int(np.prod(shape)), bits)
             sd[key] = torch.from_numpy(codes.reshape(shape))
     return {"state_dict": sd}

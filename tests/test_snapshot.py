@@ -75,3 +75,7 @@ def test_pack_codes_ragged_and_range():
         assert np.array_equal(snapshot.unpack_codes(snapshot.pack_codes(c, levels), levels, n), c)
     with pytest.raises(ValueError):
         snapshot.pack_codes(np.array([16], dtype=np.uint8), 16)
+    # codes beyond levels - 1 (reference quirk: alpha_w of the last iterate) widen the layer instead of failing
+    c = np.array([0, 5, 16, 3], dtype=np.uint8)
+    assert snapshot.bits_needed(c, 16) == 8 and snapshot.bits_needed(c[:2], 16) == 4 and snapshot.bits_needed(c, 4) == 8
+    assert np.array_equal(snapshot.unpack_codes(snapshot.pack_codes(c, 16, 8), 16, 4, 8), c)

@@ -105,3 +105,50 @@ def test_cli_and_yaml_schema():
     mods = [m for m in cube["model"].modules() if isinstance(m, PTQConv)]
     assert len(mods) == 28                                     # LiTS config
     assert (mods[0].qlvl_w, mods[0].q_act) == (256, False) and (mods[1].qlvl_w, mods[1].qlvl_act) == (4, 4)
+
+
+def test_launch_recorder_and_replay_semantics():
+    """capi.record / ops.replay (layer_engine re-issues the steady-state ADMM iterations from a recorded launch
+    sequence): launches are recorded with their converted arguments and the timer tag, size / support queries
+    are not, replay calls the same functions with the same arguments and raises on a non-zero return code."""
+    import ctypes as C
+    from efficientq_b200 import capi, ops
+
+    calls = []
+
+    class FakeFn:
+        def __init__(self, name, restype, argtypes, rc=0):
+            self.name, self.restype, self.argtypes, self.rc = name, restype, argtypes, rc
+
+        def __call__(self, *args):
+            calls.append((self.name, args))
+            return self.rc
+
+    class FakeLib:
+        effq_launch_a = FakeFn("a", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p])
+        effq_launch_b = FakeFn("b", C.c_int, [C.c_float, C.c_void_p])
+        effq_query_workspace = FakeFn("q", C.c_int64, [C.c_int32])
+        effq_thing_supported = FakeFn("s", C.c_int, [C.c_void_p])
+        effq_bad = FakeFn("bad", C.c_int, [C.c_void_p], rc=3)
+
+    rec = capi._Recorder(FakeLib())
+    rec.tag = ("kernel_a", {"bytes": 8})
+    assert rec.effq_launch_a(None, 5, None) == 0
+    rec.tag = None
+    rec.effq_query_workspace(7)
+    rec.effq_thing_supported(None)
+    rec.effq_launch_b(1.5, None)
+    assert [c[3] for c in rec.calls] == ["effq_launch_a", "effq_launch_b"]
+    assert rec.calls[0][2] == ("kernel_a", {"bytes": 8}) and rec.calls[1][2] is None
+    n0 = len(calls)
+    ops.replay(rec.calls)
+    assert [c[0] for c in calls[n0:]] == ["a", "b"] and calls[n0][1] == (None, 5, None) and calls[n0 + 1][1] == (1.5, None)
+    # a failing launch surfaces as EffqError (the message comes from the real library's effq_last_error)
+    rec.effq_bad(None)
+    with pytest.raises(capi.EffqError):
+        ops.replay(rec.calls[-1:])
+    # the recorder is only installed inside `with capi.record()`
+    assert capi._recorder is None
+    with capi.record() as r2:
+        assert capi.load() is r2
+    assert capi._recorder is None and capi.load() is not r2

@@ -221,7 +221,8 @@ def run_reference(args, wl, wl_name):
     cores = os.cpu_count()
     times, vals, desc, full = [], [], "", 0.0
     for i in range(args.warmup + args.steps):
-        v, desc, spent, full = cpu_sample(wl, threads=cores)
+        # warm-up samples (thread pool, allocator, page cache) need only one iteration; timed ones the full sample
+        v, desc, spent, full = cpu_sample(wl, iters=CPU_SAMPLE_ITERS if i >= args.warmup else 1, threads=cores)
         if i >= args.warmup:
             times.append(spent)
             vals.append(v)

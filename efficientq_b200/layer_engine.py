@@ -181,6 +181,10 @@ class LayerCalibrator:
         if dist.world > 1:
             dist.all_reduce_sum(a0)
             dist.all_reduce_sum(b0)
+        if self.probe is not None:
+            for tag, t in (("x", x), ("out_fp", out_fp), ("att", att), ("alpha_act", self.xstate.buf[:8].view(torch.float64).clone() if q_act else None),
+                           ("qx", qx if q_act else None), ("xcodes", xcodes), ("a0", a0), ("b0", b0)):
+                self._probe(name, tag, t)
         # un-quantised input (conv0 / final_cls): the conv input never changes, so the per-iterate
         # loss comes from fp64 sufficient statistics instead of 200 fp32 convs
         stats64 = None
@@ -278,6 +282,10 @@ class LayerCalibrator:
                 inverses[r_] = (inv_r, ev)
                 infos.append(info)
                 rep.factorizations += 1
+        if self.probe is not None:
+            self._side.synchronize()
+            for i_, r_ in enumerate(rhos):
+                self._probe(name, f"inv{i_}", inverses[r_][0])
         ainv = None
         rho_built = None
         peer = dist.peer_link(dev) if dist.world > 1 else None
@@ -416,7 +424,18 @@ class LayerCalibrator:
             raise RuntimeWarning(f"Exceed maximum iteration ({qlvl_w * 100}) for alpha optimization in var_init_iter")
         if self.keep_history:
             rep.history = hist.cpu().tolist()
+        if self.probe is not None:
+            for tag, t in (("hist", hist), ("best_g", best_g), ("best_b", best_b), ("alpha_w", alpha_w), ("out_q", out_q)):
+                self._probe(name, tag, t)
         return best_g.view(c2, c1, *ksize), best_b, alpha_w, alpha_act, out_q, rep
+
+    # bring-up hook (tools/repro_check.py): callable(layer name, tag, tensor) handed the intermediate results of a
+    # layer; None in production (no call, no synchronisation)
+    probe = None
+
+    def _probe(self, name, tag, t):
+        if self.probe is not None and t is not None:
+            self.probe(name, tag, t)
 
     _cws = None
     _sg_ws = None

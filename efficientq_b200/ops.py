@@ -8,6 +8,7 @@ missing the first call raises (no fallback by design).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import struct
 from typing import Optional, Tuple
@@ -406,16 +407,21 @@ _att_exact_cache = {}
 def att_is_exact(att: Optional[torch.Tensor], code_max: int) -> bool:
     """True when every att * code (code <= code_max) is exactly representable in bf16: integer-valued
     weights -- the reference truncates its attention map to integers (ptqer.py:160-163) -- with
-    max(att) * code_max <= 256.  One device reduction + read-back per attention map (cached)."""
+    max(att) * code_max <= 256.  One device reduction + read-back per attention map, remembered for as long
+    as that tensor OBJECT lives and is not written to (a weak reference, not the address: the caching
+    allocator hands the address of a freed map to the next one of the same size)."""
     if att is None:
         return True
-    key = (att.data_ptr(), att._version, tuple(att.shape), int(code_max))
-    if key not in _att_exact_cache:
-        if len(_att_exact_cache) > 64:
-            _att_exact_cache.clear()
-        st = torch.stack([(att == att.round()).all().float(), att.max(), att.min()]).cpu().tolist()
-        _att_exact_cache[key] = bool(st[0] == 1.0 and st[2] >= 0.0 and st[1] * code_max <= 256.0)
-    return _att_exact_cache[key]
+    key = (id(att), int(code_max))
+    hit = _att_exact_cache.get(key)
+    if hit is not None and hit[0]() is att and hit[1] == att._version:
+        return hit[2]
+    for k in [k for k, v in _att_exact_cache.items() if v[0]() is None]:        # entries of dead tensors
+        del _att_exact_cache[k]
+    st = torch.stack([(att == att.round()).all().float(), att.max(), att.min()]).cpu().tolist()
+    ok = bool(st[0] == 1.0 and st[2] >= 0.0 and st[1] * code_max <= 256.0)
+    _att_exact_cache[key] = (weakref.ref(att), att._version, ok)
+    return ok
 
 
 def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None, att_exact=False):

@@ -103,6 +103,7 @@ class PTQConv(nn.Conv3d):
         self.weight.data = w_int.data.cpu()
 
     def restore_fp_weight(self):
+        self._wcodes_by_dtype = self._wcodes_cache = self._dgrad_cache = None
         delta = 2 / (self.qlvl_w - 1)
         self.weight.data = self.alpha_w.data * (self.weight.data.float() * delta - 1)
 
@@ -237,6 +238,7 @@ class EfficientQConv(PTQConv):
             self.stride, self.padding, self.qlvl_w, self.qlvl_act, self.q_act, self.mask_pyramid,
             name=self.name or "")
         self.weight.data = w.clone()
+        self._wcodes_by_dtype = self._wcodes_cache = self._dgrad_cache = None    # keyed by address + version: drop
         if self.bias is not None:
             self.bias.data = b.clone()
         self.alpha_w.data = a_w.to(x.dtype)

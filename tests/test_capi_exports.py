@@ -152,3 +152,26 @@ def test_launch_recorder_and_replay_semantics():
     with capi.record() as r2:
         assert capi.load() is r2
     assert capi._recorder is None and capi.load() is not r2
+
+
+def test_att_exactness_memo_follows_the_tensor_object_not_its_address():
+    """ops.att_is_exact remembers its answer per tensor OBJECT and version (the caching allocator reuses the
+    address of a freed attention map for the next one of the same size)."""
+    import gc
+    import torch
+    from efficientq_b200 import ops
+    ops._att_exact_cache.clear()
+    a = torch.tensor([[1.0, 2.0], [3.0, 1.0]])
+    assert ops.att_is_exact(None, 15) is True
+    assert ops.att_is_exact(a, 15) is True and len(ops._att_exact_cache) == 1
+    assert ops.att_is_exact(a, 15) is True and len(ops._att_exact_cache) == 1          # memo hit
+    assert ops.att_is_exact(a, 255) is False                                             # 3 * 255 > 256
+    a[0, 0] = 1.5                                                                        # in-place write: new version
+    assert ops.att_is_exact(a, 15) is False
+    b = torch.tensor([[0.5, 2.0]])
+    assert ops.att_is_exact(b, 15) is False
+    del a, b
+    gc.collect()
+    c = torch.tensor([[2.0, 2.0]])
+    assert ops.att_is_exact(c, 15) is True                                               # dead entries are purged
+    assert all(v[0]() is not None for v in ops._att_exact_cache.values())

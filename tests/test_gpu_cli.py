@@ -19,6 +19,7 @@ def test_cli_ptq_end_to_end_writes_reference_artefacts():
     exp_id = "pytest_cli_w4a4"
     root = os.path.join(ROOT, "exp_ptq", "brats", "snap", "round1", exp_id)
     shutil.rmtree(root, ignore_errors=True)
+    torch.manual_seed(0)          # no --pretrain: the net keeps torch's default random initialisation
     try:
         res = entrance.main(["ptq", "--qlvl_w", "16", "--qlvl_a", "16", "--round", "1", "--device", "0",
                              "--config", os.path.join(ROOT, "config", "brats_ptq.yaml"), "--data_dir", "synthetic",

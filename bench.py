@@ -231,7 +231,8 @@ def run_reference(args, wl, wl_name):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "volumes_per_gpu": wl["n"], "volume": list(wl["size"]),
-                       "levels_w": wl["lw"], "levels_a": wl["la"]},
+                       "levels_w": wl["lw"], "levels_a": wl["la"], "admm_iters": 200,
+                       "parallelism": f"{cores} host threads (oracle port of the reference's CPU path)"},
             "ptq_wall_s": full,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -37,7 +37,8 @@ WORKLOADS = {
     "brats_w4a4_2x64": dict(n=2, size=(64, 64, 64), lw=16, la=16, task="brats"),
     # BASELINE configs[2]: LiTS-config 1-channel CT net (28 quantizer layers, widths 32..512, init_stride 2,2,1),
     # W2A2 = 4/4 levels, 1x160x160x64 volumes.  A parity / coverage case, not the headline line.
-    "lits_w2a2_4x160": dict(n=4, size=(160, 160, 64), lw=4, la=4, task="lits"),
+    # cpu_iters: the K' = 13825 LU solves of the 512-channel level cost ~10 s each on 16 host threads
+    "lits_w2a2_4x160": dict(n=4, size=(160, 160, 64), lw=4, la=4, task="lits", cpu_iters=1),
 }
 N_MOD = {"brats": 4, "lits": 1}
 METRIC = "ptq_calibration_throughput"
@@ -158,7 +159,7 @@ def peaks():
 CPU_SAMPLE_ITERS = 16   # of 200 ADMM iterations per layer: ~15-20 s of work on 16 host threads
 
 
-def cpu_sample(wl, iters=CPU_SAMPLE_ITERS, threads=None, edge_div=2):
+def cpu_sample(wl, iters=None, threads=None, edge_div=2):
     """Bounded sample of the CPU path (oracle port of the reference) on the host cores.
 
     Runs the per-layer calibration of ALL 22 quantizer layers on ONE volume whose edge is
@@ -171,6 +172,7 @@ def cpu_sample(wl, iters=CPU_SAMPLE_ITERS, threads=None, edge_div=2):
     1-iteration sample overstates the CPU time by ~1.4x (8491 s vs 6121 s on 8 cores).
     Returns (volumes/s, description, seconds spent, scaled full-job seconds)."""
     from oracle import effq_oracle as O
+    iters = iters or wl.get("cpu_iters", CPU_SAMPLE_ITERS)
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     from efficientq_b200 import synth
@@ -222,7 +224,7 @@ def run_reference(args, wl, wl_name):
     times, vals, desc, full = [], [], "", 0.0
     for i in range(args.warmup + args.steps):
         # warm-up samples (thread pool, allocator, page cache) need only one iteration; timed ones the full sample
-        v, desc, spent, full = cpu_sample(wl, iters=CPU_SAMPLE_ITERS if i >= args.warmup else 1, threads=cores)
+        v, desc, spent, full = cpu_sample(wl, iters=None if i >= args.warmup else 1, threads=cores)
         if i >= args.warmup:
             times.append(spent)
             vals.append(v)

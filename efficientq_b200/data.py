@@ -36,6 +36,10 @@ def center_crop(t: torch.Tensor, size) -> torch.Tensor:
     return t[..., x1:x1 + size[0], y1:y1 + size[1], z1:z1 + size[2]]
 
 
+SYNTH_VAL_VOLUMES = 2          # held-out synthetic volumes evaluated when data_dir is synthetic
+SYNTH_VAL_FIRST_SEED = 5000
+
+
 class CalibrationData:
     def __init__(self, args):
         self.args = args
@@ -90,3 +94,48 @@ class CalibrationData:
             imgs.append(center_crop(img, shape))
             labs.append(center_crop(lab, shape))
         return torch.stack(imgs).float(), torch.stack(labs)
+
+    def slide_window(self):
+        """(patch_size, overlap) of the sliding-window evaluation (src/definer.py:41-62, :78-83, :106-107)."""
+        a = self.args
+        ps = getattr(a, "patch_size", None)
+        if ps:
+            ps = tuple(int(x) for x in str(ps).split(",")) if "," in str(ps) else (int(ps),) * 3
+        else:
+            ps = (128, 128, 128) if self.task == "brats" else (128, 128, 64)
+        return ps, (16, 16, 16)
+
+    def evaluation_volumes(self, split: str = "val"):
+        """Iterable of ``(sn, image[C,D,H,W] fp32, label[D,H,W])`` of a split with the fixed transform of the
+        reference's val / test loaders (ToTensor + optional normalisation, no crop: src/dataloader/datahub.py:75-110),
+        or None when the split does not exist.  Synthetic data: ``SYNTH_VAL_VOLUMES`` held-out volumes as the
+        'val' split, one quarter-window longer than the window along D so that the stitching is exercised."""
+        a = self.args
+        n_mod = int(getattr(a, "nMod", None) or (4 if self.task == "brats" else 1))
+        if self.synthetic:
+            if split != "val":
+                return None
+            ps, _ = self.slide_window()
+            shape = (ps[0] + max(ps[0] // 4, 1), ps[1], ps[2])
+
+            def synth_volumes():
+                for i in range(SYNTH_VAL_VOLUMES):
+                    img, lab = synth.volume(SYNTH_VAL_FIRST_SEED + i, n_mod, shape, self.task)
+                    yield f"synthetic_{SYNTH_VAL_FIRST_SEED + i}", img, lab
+            return synth_volumes()
+        if not getattr(a, "split_dir", None):
+            return None
+        path = P.join(a.split_dir, "round" + str(a.round), f"{split}.txt")
+        if not P.isfile(path):
+            return None
+        sns = [s for s in open(path).read().splitlines() if s]
+        if not sns:
+            return None
+        if not getattr(a, "data_on_disk", False):
+            sns.sort()
+
+        def disk_volumes():
+            for sn in sns:
+                img, lab = self._load(sn)
+                yield sn, img.float(), lab
+        return disk_volumes()

@@ -230,8 +230,7 @@ class EfficientQConv(PTQConv):
             raise ops.EffqError("EfficientQConv.ptq needs CUDA tensors: there is no CPU path")
         if self.output_fp is None:
             raise RuntimeError("output_fp missing: run the FP pass with forward hooks first")
-        if self.lwq_verbose or True:
-            print(f"Calibrating {self.name}")
+        print(f"Calibrating {self.name}")                 # unconditional in the reference (EfficientQConv.py:52)
         out_fp = self.output_fp.to(x.device)
         w, b, a_w, a_act, out_q, rep = self._engine(x.device).run(
             x, self.weight.data, self.bias.data if self.bias is not None else None, out_fp,

@@ -496,6 +496,70 @@ def gen_toy_net_lits(R, out):
     gen_toy_net(R, out, TOY_LITS, "toy_net_lits.npz")
 
 
+EVAL_TILINGS = [((20, 24, 12), (8, 16, 12), (4, 8, 8)), ((18, 18, 18), (18, 18, 18), (8, 8, 8)),
+                ((25, 21, 17), (12, 12, 12), (8, 4, 0)), ((32, 16, 16), (16, 16, 16), (8, 8, 8))]
+
+
+def gen_eval(R, out):
+    """Sliding-window tiling / stitching (src/utils/transforms.py:784-851), label split / merge
+    (src/utils/misc.py:221-285) and SegMetricMC (src/utils/validate.py:19-205) of the reference's evaluation."""
+    import io
+    import utils.transforms as tfm
+    import utils.misc as misc
+    from utils.validate import SegMetricMC
+    res = {}
+    g = torch.Generator().manual_seed(41)
+    for ci, (dhw, patch, ov) in enumerate(EVAL_TILINGS):
+        n_vox = dhw[0] * dhw[1] * dhw[2]
+        index_img = torch.arange(n_vox, dtype=torch.float32).reshape(1, 1, *dhw)          # value = linear voxel index
+        starts = [int(p[0, 0, 0, 0, 0]) for p in tfm.image_to_patch3d(index_img, patch, ov)]
+        img = torch.randn(2, 2, *dhw, generator=g)
+        patches = tfm.image_to_patch3d(img, patch, ov)
+        preds = [torch.stack([p * (1.0 + 0.125 * k) + 0.5 * k, p.flip(1) - 0.25 * k]) for k, p in enumerate(patches)]
+        stitched = tfm.patch_to_image3d(img, preds, patch, ov)
+        res[f"tile{ci}_starts"] = np.array(starts, dtype=np.int64)
+        res[f"tile{ci}_img"] = img.numpy()
+        res[f"tile{ci}_stitched"] = stitched.numpy()
+    # labels
+    lab = torch.randint(0, 4, (10, 12, 14), generator=g)
+    res["label_brats"] = lab.numpy().astype(np.uint8)
+    res["split_brats"] = misc.split_label_brats(lab).numpy()
+    lab2 = torch.randint(0, 3, (10, 12, 14), generator=g)
+    res["label_lits"] = lab2.numpy().astype(np.uint8)
+    res["split_lits"] = misc.split_label_lits(lab2).numpy()
+    bits = (torch.rand(3, 10, 12, 14, generator=g) > 0.5).int()
+    res["merge_in"] = bits.numpy()
+    res["merge_con"] = misc.merge_label_basic(bits.clone(), "con").numpy()
+    res["merge_agg"] = misc.merge_label_basic(bits.clone(), "agg").numpy()
+    res["merge_brats_con"] = misc.merge_label_brats(bits.clone(), "con").numpy()
+    # metrics: two subjects each; multi-class (argmax over 3 logits, integer label) and multi-label
+    # (sigmoid >= 0.5 per channel, optional fusion)
+    for mode in ("mc", "ml_con", "ml_none"):
+        sm = SegMetricMC(3, ["case_a", "case_b"])
+        for j in range(2):
+            logits = torch.randn(3, 12, 10, 8, generator=g)
+            if mode == "mc":
+                label = torch.randint(0, 3, (12, 10, 8), generator=g)
+                pred = sm.evaluate_append(logits, label)
+            else:
+                label = (torch.rand(3, 12, 10, 8, generator=g) > 0.6).float()
+                pred = sm.evaluate_append(logits, label, multilabel_fusetype="con" if mode == "ml_con" else None)
+            res[f"{mode}_logits{j}"] = logits.numpy()
+            res[f"{mode}_label{j}"] = label.numpy()
+            res[f"{mode}_pred{j}"] = pred.numpy()
+        sm.get_metric()
+        keys = list(sm.metric.keys())
+        res[f"{mode}_keys"] = np.array(keys)
+        res[f"{mode}_metric"] = np.array([sm.metric[k] for k in keys], dtype=np.float64)
+        res[f"{mode}_buffer"] = np.array([[float(v) for v in sm.buffer[k]] for k in keys], dtype=np.float32)
+        buf = io.StringIO()
+        sm.write_metric(buf, "Output -1:", True)
+        res[f"{mode}_text"] = np.array(buf.getvalue())
+    for k, v in meta().items():
+        res["meta_" + k] = np.array(str(v))
+    np.savez_compressed(os.path.join(out, "eval.npz"), **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -505,7 +569,7 @@ def main():
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
                 solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
-                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice)
+                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice, eval=gen_eval)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

@@ -24,7 +24,7 @@ def test_cli_ptq_end_to_end_writes_reference_artefacts():
         res = entrance.main(["ptq", "--qlvl_w", "16", "--qlvl_a", "16", "--round", "1", "--device", "0",
                              "--config", os.path.join(ROOT, "config", "brats_ptq.yaml"), "--data_dir", "synthetic",
                              "--lwq_patchsz", "64,64,64", "--lwq_batchsz", "2", "--exp_id", exp_id,
-                             "--tune_act_iter", "2"])
+                             "--tune_act_iter", "2", "--no_test"])      # evaluation: tests/test_gpu_zz_eval.py
         for f in ("cmd.txt", "time_cost.txt", "layer_loss.txt", "class_voxel_nums.txt", "state_in_fp.pkl",
                   "state_in_int8.pkl", "state_in_int8_compress.npz", "state_in_packed.npz"):
             assert os.path.exists(os.path.join(root, f)), f

@@ -145,10 +145,10 @@ def test_toy_network_matches_reference(engine_mod, golden, task):
     # layer 1 sees identical inputs -> 1e-3; later layers inherit the (chaotic) quantised
     # prefix, tolerance documented in DESIGN.md
     assert abs(losses[0] - ref[0]) <= 1e-3 * ref[0]
-    # GPU runs of these two-volume miniatures are not bit-reproducible from one process to the next (observed:
-    # the CLI case's end-to-end loss moves by 2x between identical runs; profiles/r01_parity.txt, "run-to-run"),
-    # and each layer calibrates on the output of the already-quantised prefix, so the deep layers get a bar that
-    # leaves room for that spread; layers 1-3 see (nearly) identical problems and stay tight.
+    # Each layer calibrates on the output of the already-quantised prefix and the ADMM trajectory amplifies
+    # last-bit differences (the reference itself moves by several percent between a 1-thread and an 8-thread CPU
+    # run), so the deep layers get a wide bar; layers 1-3 see (nearly) identical problems and stay tight.
+    # Whether two GPU runs agree bit for bit is measured by tools/repro_check.py.
     if task == "brats":
         np.testing.assert_allclose(losses[:3], ref[:3], rtol=5e-3)
         np.testing.assert_allclose(losses[3:], ref[3:], rtol=1e-1)

@@ -86,7 +86,7 @@ def merge_label_basic(pred: torch.Tensor, fusetype: str) -> torch.Tensor:
     wherever an inner one is set."""
     kind = fusetype.lower()
     if kind in ("con", "conservative"):
-        return torch.cumprod(pred, dim=0)
+        return torch.cumprod(pred, dim=0).to(pred.dtype)
     if kind in ("agg", "aggressive"):
         return (torch.flip(torch.cumsum(torch.flip(pred, (0,)), dim=0), (0,)) > 0).to(pred.dtype)
     raise RuntimeError("Unknown Multilabel Fusetype: %s" % fusetype)

@@ -560,6 +560,67 @@ def gen_eval(R, out):
     np.savez_compressed(os.path.join(out, "eval.npz"), **res)
 
 
+TINY_SNS = ["s03", "s01", "s10", "s02", "s07"]                 # deliberately unsorted: Dataset_SEG sorts, the on-disk variant does not
+TINY_SHAPES = [(20, 18, 26), (18, 20, 24), (22, 16, 25), (17, 19, 28), (16, 16, 24)]
+
+
+def write_tiny_dataset(root, seed=77):
+    """A five-subject BraTS-layout dataset (src/definer.py:42, src/dataloader/datasets.py:24-29) written from a
+    platform-stable numpy stream; used by gen_calib_data here and, with the same seed, by tests/test_data.py."""
+    import pickle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for mod in ("seg", "flair", "t1", "t1ce", "t2"):
+        os.makedirs(os.path.join(root, mod), exist_ok=True)
+    for sn, shp in zip(TINY_SNS, TINY_SHAPES):
+        for mod in ("flair", "t1", "t1ce", "t2"):
+            np.savez(os.path.join(root, mod, sn + ".npz"), rng.standard_normal(shp).astype(np.float32))
+        np.savez(os.path.join(root, "seg", sn + ".npz"), rng.integers(0, 4, shp).astype(np.uint8))
+    os.makedirs(os.path.join(root, "split", "round1"), exist_ok=True)
+    with open(os.path.join(root, "split", "round1", "train.txt"), "w") as fid:
+        fid.write("\n".join(TINY_SNS) + "\n")
+    with open(os.path.join(root, "split", "round1", "val.txt"), "w") as fid:
+        fid.write("\n".join(TINY_SNS[:2]) + "\n")
+    with open(os.path.join(root, "sn_fn.txt"), "w") as fid:
+        fid.write("\n".join(f"{s},{s}.nii.gz" for s in TINY_SNS) + "\n")
+    with open(os.path.join(root, "restore_shape_infokw.pickle"), "wb") as fid:
+        pickle.dump({s: {} for s in TINY_SNS}, fid)
+
+
+def tiny_dataset_args(root, data_on_disk):
+    from efficientq_b200 import entrance
+    a = entrance.build_parser().parse_args(["ptq", "--config", os.path.join(ROOT, "config", "brats_ptq.yaml")])
+    a = entrance.merge_config(a.config, a)
+    a.data_dir, a.split_dir, a.num_workers = root, os.path.join(root, "split"), 0
+    a.lwq_patchsz, a.lwq_batchsz, a.lwq_dataid, a.data_on_disk = "16,16,24", 3, 1, data_on_disk
+    return a
+
+
+def gen_calib_data(R, out):
+    """Calibration-batch assembly (src/ptqer.py:83-111 over src/definer.py:14-127 / src/dataloader) and the val
+    loader's volumes, for the in-memory (sorted) and the on-disk (file order) dataset classes."""
+    import tempfile
+    import definer as rdef
+    root = tempfile.mkdtemp()
+    write_tiny_dataset(root)
+    res = {}
+    for disk in (True, False):
+        a = tiny_dataset_args(root, disk)
+        cube = rdef.get_data_cube(a)[0]
+        x, y = R["ptqer"].get_calibration_data(a, cube)
+        tag = "disk" if disk else "mem"
+        res[f"{tag}_batch"] = x.numpy()
+        res[f"{tag}_label_batch"] = y.numpy().astype(np.uint8)
+        for i, (im, lb) in enumerate(cube.valloader):
+            res[f"{tag}_val{i}_img"] = im[0].numpy()
+            res[f"{tag}_val{i}_label"] = lb[0].numpy().astype(np.uint8)
+        a.lwq_batchsz, a.lwq_dataid = 1, 0                       # the single-volume branch (:93-100)
+        cube = rdef.get_data_cube(a)[0]
+        res[f"{tag}_single"] = R["ptqer"].get_calibration_data(a, cube)[0].numpy()
+    for k, v in meta().items():
+        res["meta_" + k] = np.array(str(v))
+    np.savez_compressed(os.path.join(out, "calib_data.npz"), **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -569,7 +630,7 @@ def main():
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
                 solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
-                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice, eval=gen_eval)
+                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice, eval=gen_eval, calib_data=gen_calib_data)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

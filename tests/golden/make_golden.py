@@ -621,6 +621,49 @@ def gen_calib_data(R, out):
     np.savez_compressed(os.path.join(out, "calib_data.npz"), **res)
 
 
+def gen_interface(R, out):
+    """The reference's command line (src/entrance.py:31-113: every flag with its type, default and action) and the
+    state-dict layout (keys + shapes, module order of the quantizer layers) of its BraTS- and LiTS-config nets
+    (src/definer.py:130-248, :286-329 over config/*_ptq.yaml) -> interface.json."""
+    import argparse as ap
+    import json
+    import definer as rdef
+    src = open(os.path.join(sys.path[0] if os.path.exists(os.path.join(sys.path[0], "entrance.py"))
+                            else os.path.join("/root/reference", "src"), "entrance.py")).read()
+    part = src[src.index("parser = argparse.ArgumentParser"):src.index("args = parser.parse_args()")]
+    ns = {"argparse": ap}
+    exec(part, ns)                                              # builds the reference's parser, runs nothing else
+    flags = {}
+    for act in ns["parser"]._actions:
+        if not act.option_strings:
+            flags[act.dest] = {"positional": True, "choices": list(act.choices) if act.choices else None}
+            continue
+        if act.dest == "help":
+            continue
+        flags[act.dest] = {"option": act.option_strings[0], "type": act.type.__name__ if act.type else None,
+                           "default": act.default, "flag": isinstance(act, ap._StoreTrueAction),
+                           "choices": list(act.choices) if act.choices else None}
+    res = {"flags": flags, "nets": {}}
+    from efficientq_b200 import entrance
+    for task, lw, la in (("brats", 16, 16), ("lits", 4, 4)):
+        a = entrance.build_parser().parse_args(["ptq", "--qlvl_w", str(lw), "--qlvl_a", str(la), "--config",
+                                                os.path.join(ROOT, "config", f"{task}_ptq.yaml")])
+        a = entrance.merge_config(a.config, a)
+        QConv, qinfo, kwQ = rdef.get_conv_class(a)
+        cube, info = rdef.get_model_cube(a, QConv, kwQ)
+        model = cube["model"]
+        qmods = [(n, m.in_channels, m.out_channels, list(m.kernel_size), list(m.stride), list(m.padding),
+                  int(m.qlvl_w), int(m.qlvl_act), bool(m.q_act))
+                 for n, m in model.named_modules() if isinstance(m, R["ptqconv"].PTQConv)]
+        res["nets"][task] = {"qinfo": qinfo, "model_info": info, "num_mo": cube["num_mo"], "nClass": cube["nClass"],
+                             "nMod": cube["nMod"], "kwQ": sorted(kwQ),
+                             "state": [[k, list(v.shape)] for k, v in model.state_dict().items()],
+                             "quantizers": qmods}
+    res["meta"] = {k: str(v) for k, v in meta().items()}
+    with open(os.path.join(out, "interface.json"), "w") as fid:
+        json.dump(res, fid, indent=0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -630,7 +673,7 @@ def main():
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
                 solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
-                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice, eval=gen_eval, calib_data=gen_calib_data)
+                toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice, eval=gen_eval, calib_data=gen_calib_data, interface=gen_interface)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):
             continue

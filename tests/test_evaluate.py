@@ -168,3 +168,33 @@ def test_tester_around_the_brats_unet_in_fp_mode(tmp_path):
     assert all(np.isfinite(v) and 0.0 <= v <= 1.0 for v in res.values())
     lines = open(os.path.join(tmp_path, "fp", "val_seg.txt")).read().splitlines()
     assert sum(ln.startswith("Output") for ln in lines) == 3 and lines[3].split("|")[1].strip() == "synthetic_5000"
+
+
+def test_mission_driver_hands_the_tester_to_do_ptq(monkeypatch):
+    """ptq_seg.ptq: evaluation is on by default (reference ptqer.py:379), --no_test alone switches it off, --test_fp
+    alone keeps the tester, --save_nii fails before any work."""
+    import shutil
+    from efficientq_b200 import entrance, ptq_seg
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = []
+    monkeypatch.setattr(ptq_seg, "do_ptq", lambda args, mc, dc, tester, snap, dist=None: seen.append(tester) or {})
+    base = ["ptq", "--qlvl_w", "16", "--qlvl_a", "16", "--config", os.path.join(root, "config", "lits_ptq.yaml"),
+            "--data_dir", "synthetic", "--exp_id", "pytest_wiring", "--device", "0"]
+    snap = os.path.join(root, "exp_ptq", "lits", "snap", "round1", "pytest_wiring")
+    try:
+        res = entrance.main(base)
+        assert isinstance(seen[-1], E.PTQTester) and res["eval"] == {}
+        t = seen[-1]
+        assert (t.patch_size, t.overlap, t.num_mo, t.n_class, t.label_tfm, t.fusetype) == \
+            ((128, 128, 64), (16, 16, 16), 3, 3, None, None)                      # LiTS: arg-max over three classes
+        assert os.path.samefile(t.root, snap)
+        entrance.main(base + ["--no_test"])
+        assert seen[-1] is None
+        entrance.main(base + ["--no_test", "--test_fp"])
+        assert isinstance(seen[-1], E.PTQTester)
+        n = len(seen)
+        with pytest.raises(NotImplementedError):
+            entrance.main(base + ["--save_nii"])
+        assert len(seen) == n
+    finally:
+        shutil.rmtree(snap, ignore_errors=True)

@@ -362,6 +362,17 @@ def run_ours(args, wl, wl_name):
                              "peak, for bf16 operands); profiles/r01_conv_layout.md")
                     if top.startswith("conv3d_tc_c32") else None,
                     "launches_per_step": s["launches"] // args.steps, "avg_launch_ms": s["ms"] / s["launches"]}
+            try:
+                # BASELINE.json's second metric: output voxels per second of the fused fake-quant conv + SSE kernel,
+                # all GPUs (weak scaling: every rank runs the same launches on its own volumes)
+                import re
+                m = re.match(r"conv3d_tc_c(\d+)x(\d+)k(\d+)", top)
+                if m:
+                    c1_, c2_, k_ = (int(v) for v in m.groups())
+                    vox = s["flops"] / (2.0 * c1_ * c2_ * k_ ** 3)
+                    roof["fakequant_conv_voxels_per_s"] = vox / (s["ms"] * 1e-3) * dist.world
+            except Exception:  # noqa: BLE001  (a derived convenience figure must never cost the bench line)
+                pass
         else:
             nbytes = s["bytes"] or s["pass_bytes"]
             ach = nbytes / (s["ms"] * 1e-3) / 1e9

@@ -1,8 +1,8 @@
-"""Validation of bench.py's CPU extrapolation model: BASELINE configs[0] (BraTS U-Net W4A4, 8 synthetic 4x64^3 volumes,
+"""(Test infrastructure: the one script outside bench.py that runs the CPU port, hence under tests/.)  Validation of bench.py's CPU extrapolation model: BASELINE configs[0] (BraTS U-Net W4A4, 8 synthetic 4x64^3 volumes,
 all 22 layers, all 200 ADMM iterations) run IN FULL with the CPU port of the reference on this host's cores, next to
 what bench.cpu_sample predicts for the same job from its bounded sample (one volume, 16 of 200 iterations).
 
-    python tools/cpu_model_check.py            # ~10 minutes on 8 cores
+    python tests/cpu_model_check.py            # ~10 minutes on 8 cores
 """
 import json
 import os

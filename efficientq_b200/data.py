@@ -105,11 +105,13 @@ class CalibrationData:
             ps = (128, 128, 128) if self.task == "brats" else (128, 128, 64)
         return ps, (16, 16, 16)
 
-    def evaluation_volumes(self, split: str = "val"):
+    def evaluation_volumes(self, split: str = "val", rank: int = 0, world: int = 1):
         """Iterable of ``(sn, image[C,D,H,W] fp32, label[D,H,W])`` of a split with the fixed transform of the
         reference's val / test loaders (ToTensor + optional normalisation, no crop: src/dataloader/datahub.py:75-110),
         or None when the split does not exist.  Synthetic data: ``SYNTH_VAL_VOLUMES`` held-out volumes as the
-        'val' split, one quarter-window longer than the window along D so that the stitching is exercised."""
+        'val' split, one quarter-window longer than the window along D so that the stitching is exercised.
+        ``rank`` / ``world``: this rank's share of the split, volumes dealt round-robin (volume i -> rank i % world);
+        the other volumes are not read."""
         a = self.args
         n_mod = int(getattr(a, "nMod", None) or (4 if self.task == "brats" else 1))
         if self.synthetic:
@@ -119,7 +121,7 @@ class CalibrationData:
             shape = (ps[0] + max(ps[0] // 4, 1), ps[1], ps[2])
 
             def synth_volumes():
-                for i in range(SYNTH_VAL_VOLUMES):
+                for i in range(rank, SYNTH_VAL_VOLUMES, world):
                     img, lab = synth.volume(SYNTH_VAL_FIRST_SEED + i, n_mod, shape, self.task)
                     yield f"synthetic_{SYNTH_VAL_FIRST_SEED + i}", img, lab
             return synth_volumes()
@@ -135,7 +137,7 @@ class CalibrationData:
             sns.sort()
 
         def disk_volumes():
-            for sn in sns:
+            for sn in sns[rank::world]:
                 img, lab = self._load(sn)
                 yield sn, img.float(), lab
         return disk_volumes()

@@ -62,6 +62,14 @@ class DistCtx:
         if self.world > 1:
             td.barrier(group=self.group)
 
+    def all_gather_object(self, obj) -> list:
+        """One small picklable object from every rank, in rank order (plumbing for per-subject metric rows)."""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        td.all_gather_object(out, obj, group=self.group)
+        return out
+
     def shard(self, n_total: int) -> Tuple[int, int]:
         """[begin, end) of the calibration volumes owned by this rank (contiguous, balanced)."""
         return shard_range(n_total, self.rank, self.world)

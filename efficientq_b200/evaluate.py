@@ -175,6 +175,19 @@ class SegMetric:
             self.buffer[m].append(v.mean() if per_channel else v[1:].mean())
         return pred
 
+    def rows(self) -> List[Tuple[str, List[float]]]:
+        """Per-subject rows (name, one fp32 value per key) -- what the ranks of a sharded evaluation exchange."""
+        return [(sn, [float(self.buffer[k][i]) for k in self.keys]) for i, sn in enumerate(self.sn_list)]
+
+    @classmethod
+    def from_rows(cls, n_class: int, rows) -> "SegMetric":
+        sm = cls(n_class)
+        for sn, vals in rows:
+            sm.sn_list.append(sn)
+            for k, v in zip(sm.keys, vals):
+                sm.buffer[k].append(torch.tensor(v, dtype=torch.float32))
+        return sm
+
     def get_metric(self) -> Dict[str, float]:
         if len(self):
             for k in self.keys:
@@ -231,8 +244,9 @@ class PTQTester:
     ``<root>/<folder>/<split>_seg.txt`` (trainer.py:286-291)."""
 
     def __init__(self, model, data_cube, root: Optional[str], device, num_mo: int, n_class: int, patch_size,
-                 overlap, multi_label: Optional[str] = None, multilabel_fusetype: Optional[str] = None):
+                 overlap, multi_label: Optional[str] = None, multilabel_fusetype: Optional[str] = None, dist=None):
         self.model, self.data_cube, self.root, self.device = model, data_cube, root, device
+        self.dist = dist                                  # DistCtx of a torchrun launch: volumes dealt round-robin
         self.num_mo, self.n_class = num_mo, n_class
         self.patch_size, self.overlap = patch_size, overlap
         self.label_tfm = label_transform(multi_label)
@@ -243,12 +257,26 @@ class PTQTester:
         if is_save_nii:
             raise NotImplementedError("--save_nii needs nibabel, which is outside this package")
         out = {}
+        rank, world = (self.dist.rank, self.dist.world) if self.dist is not None else (0, 1)
         for split in ("val", "test"):
-            vols = self.data_cube.evaluation_volumes(split)
+            vols = self.data_cube.evaluation_volumes(split, rank, world) if world > 1 else \
+                self.data_cube.evaluation_volumes(split)
             if vols is None:
                 continue
             sm = validate_seg(self.model, vols, self.device, self.num_mo, self.n_class, self.patch_size,
                               self.overlap, self.fusetype, self.label_tfm)
+            if world > 1:
+                # every rank scored its own volumes (no data-path collective); the per-subject rows -- a few
+                # floats each -- are exchanged and put back into the split's order: volume i sits on rank i % world
+                per_rank = self.dist.all_gather_object([s.rows() for s in sm])
+                n_total = sum(len(r[0]) for r in per_rank)
+                sm = [SegMetric.from_rows(self.n_class, [per_rank[i % world][h][i // world] for i in range(n_total)])
+                      for h in range(len(sm))]
+                for s in sm:
+                    s.get_metric()
+                if rank != 0:
+                    out[split] = dict(sm[-1].metric)
+                    continue
             if self.root:
                 os.makedirs(P.join(self.root, folder), exist_ok=True)
                 with open(P.join(self.root, folder, "%s_seg.txt" % split), "w") as fid:

@@ -84,3 +84,59 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _EvalCube:
+    """Five deterministic volumes; hands out a rank's round-robin share like CalibrationData.evaluation_volumes."""
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(5)
+        self.vols = [(f"sn{i}", torch.randn(2, 20, 16, 16, generator=g), torch.randint(0, 4, (20, 16, 16), generator=g))
+                     for i in range(5)]
+
+    def evaluation_volumes(self, split, rank=0, world=1):
+        return iter(self.vols[rank::world]) if split == "val" else None
+
+
+class _EvalNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(9)
+        self.a = torch.nn.Conv3d(2, 3, 3, padding=1)
+        self.b = torch.nn.Conv3d(2, 3, 1)
+
+    def forward(self, x):
+        return torch.stack([self.b(x), self.a(x)])
+
+
+def _eval_worker(rank, world, port, out, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from efficientq_b200.dist import DistCtx
+    from efficientq_b200.evaluate import PTQTester
+    args = dict(num_mo=2, n_class=3, patch_size=(16, 16, 16), overlap=8, multi_label="brats", multilabel_fusetype="con")
+    root = os.path.join(tmp, "sharded") if rank == 0 else None
+    res = PTQTester(_EvalNet(), _EvalCube(), root, "cpu", dist=DistCtx(), **args).test_as_is("ptq")
+    if rank == 0:
+        ref = PTQTester(_EvalNet(), _EvalCube(), os.path.join(tmp, "single"), "cpu", **args).test_as_is("ptq")
+        a = open(os.path.join(tmp, "sharded", "ptq", "val_seg.txt")).read()
+        b = open(os.path.join(tmp, "single", "ptq", "val_seg.txt")).read()
+        assert a == b and res == ref, (a, b)              # same report, character for character
+        out.put("ok")
+    else:
+        out.put(res["val"]["dsc"])                        # every rank ends up with the merged metrics
+    td.destroy_process_group()
+
+
+def test_two_rank_sharded_evaluation_equals_unsharded(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = [q.get(timeout=5), q.get(timeout=5)]
+    assert "ok" in got and any(isinstance(v, float) and 0.0 <= v <= 1.0 for v in got)

@@ -30,6 +30,11 @@ class NextRhs(C.Structure):
     _fields_ = [("b0", C.c_void_p), ("w0p", C.c_void_p), ("rho", C.c_float), ("eta", C.c_float), ("planes", C.c_void_p)]
 
 
+class AdmmKeep(C.Structure):
+    """``effq_admm_keep_bufs`` (include/effq_b200.h)."""
+    _fields_ = [("best_g", C.c_void_p), ("best_b", C.c_void_p), ("best_wcodes", C.c_void_p)]
+
+
 class Geom(C.Structure):
     """``effq_geom`` (include/effq_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in
@@ -94,6 +99,12 @@ _SIGS = {
     "effq_gram_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_quadform_sse": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_quadform_delta_workspace": (C.c_int64, [C.c_int32, C.c_int32]),
+    "effq_quadform_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                      C.c_void_p]),
+    "effq_gram_tc_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_gram_tc_supported": (C.c_int, [C.POINTER(Geom)]),
     "effq_gram_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom),
                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -109,7 +120,10 @@ _SIGS = {
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_admm_decide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_admm_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p]),

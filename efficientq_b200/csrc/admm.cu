@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "tc_layout.cuh"
 #include "peer.cuh"
+#include "admm_decide.cuh"
 #include <cuda_fp8.h>
 
 namespace effq {
@@ -96,10 +97,15 @@ __global__ void __launch_bounds__(AD_THREADS)
 admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __restrict__ dual,
                     const effq_scale_state* __restrict__ wscale, const effq_scale_state* __restrict__ xscale,
                     int nlvl_w, int nlvl_a, int c2, int c1, int taps, int has_bias, float dual_div,
-                    float* __restrict__ g_out, float* __restrict__ bstar_out,
-                    void* __restrict__ wcodes, TcLayout lay, effq_admm_state* st, effq_next_rhs nx, int ldk) {
+                    float* g_out, float* bstar_out,
+                    void* wcodes, TcLayout lay, effq_admm_state* st, effq_next_rhs nx, int ldk,
+                    effq_admm_keep_bufs kp_) {
   const int k = c1 * taps;
   const long long total = (long long)c2 * k;
+  // Fused "keep": when the PREVIOUS iterate was the best so far (st->take_, set by the decide step
+  // that scored it) its G / b* / weight codes are still in g_out / bstar_out / wcodes -- every thread
+  // saves the element it is about to overwrite (EfficientQConv.py:139-142 without a launch of its own).
+  const bool keep_prev = kp_.best_g != nullptr && st != nullptr && *((volatile int*)&st->take_) != 0;
   const double a64 = wscale->a;
   const float a32 = (float)a64;
   const QParamD q = make_qparam_d(-1.f, 1.f, nlvl_w);
@@ -112,6 +118,7 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
     const double idx = level_index_d(__ddiv_rn((double)v, a64), q);      // fp64 discretize
     const float b32 = (float)level_value_d(idx, q);                      // .float()
     const float gq = __fmul_rn(a32, b32);                                // G = a_w * b_w
+    if (keep_prev) kp_.best_g[e] = g_out[e];
     g_out[e] = gq;
     const float dn = __fdiv_rn(__fadd_rn(__fsub_rn(ws, gq), du), dual_div);   // (w*-G+dual) [/2 on rho steps]
     dual[e] = dn;
@@ -125,12 +132,19 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
     if (wcodes) {
       const int c = j / taps, t = j % taps;
       const float code = (float)(2.0 * idx - (double)(nlvl_w - 1));      // odd integer in [-(L-1), L-1]
-      store_code(wcodes, tc_wcode_index(r, c, t, c1, c2, lay), code, lay.eb);
+      const long long wi = tc_wcode_index(r, c, t, c1, c2, lay);
+      if (keep_prev && kp_.best_wcodes) {
+        if (lay.eb == 2) reinterpret_cast<uint16_t*>(kp_.best_wcodes)[wi] = reinterpret_cast<const uint16_t*>(wcodes)[wi];
+        else reinterpret_cast<uint8_t*>(kp_.best_wcodes)[wi] = reinterpret_cast<const uint8_t*>(wcodes)[wi];
+      }
+      store_code(wcodes, wi, code, lay.eb);
     }
   }
   if (has_bias && bstar_out) {
-    for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < c2; r += gridDim.x * AD_THREADS)
+    for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < c2; r += gridDim.x * AD_THREADS) {
+      if (keep_prev && kp_.best_b) kp_.best_b[r] = bstar_out[r];
       bstar_out[r] = wstar[(long long)r * ldw + k];
+    }
   }
   if (nx.planes) {
     // bias column (constant B0 + eta*W0') and the zero tail up to the plane pitch
@@ -158,15 +172,8 @@ __global__ void admm_decide_kernel(effq_admm_state* st, const double* __restrict
     if (!peer_allreduce3(comm, 1, v)) v[0] = __longlong_as_double(0x7ff8000000000000ll);   // NaN: exchange timed out
     total = v[0];
   }
-  const float loss = (float)(total / numel);             // F.mse_loss(...).item()
-  const int it = st->iter;
-  const int keep = (it == 0 || loss < st->best_loss) ? 1 : 0;   // EfficientQConv.py:139
-  if (keep) { st->best_loss = loss; st->best_iter = it; st->best_conv_scale = st->conv_scale; }
-  st->last_loss = loss;
-  st->sse = total;
-  if (history) history[it] = loss;
-  st->iter = it + 1;
-  *take = keep;
+  admm_decide_dev(st, total, numel, history);
+  (void)take;
 }
 
 __global__ void __launch_bounds__(AD_THREADS)
@@ -240,8 +247,11 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
                                  const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                                  int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
                                  float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
-                                 const effq_next_rhs* next, void* stream) {
+                                 const effq_next_rhs* next, const effq_admm_keep_bufs* keep, void* stream) {
   using namespace effq;
+  EFFQ_CHECK_ARG(!keep || (keep->best_g && st), "keep: best_g and the ADMM state are required");
+  effq_admm_keep_bufs kp_;
+  if (keep) kp_ = *keep; else { kp_.best_g = nullptr; kp_.best_b = nullptr; kp_.best_wcodes = nullptr; }
   EFFQ_CHECK_ARG(wstar && dual && wscale && g_out, "null pointer");
   EFFQ_CHECK_ARG(c2 > 0 && c1 > 0 && taps > 0 && ldw >= (int64_t)c1 * taps + (has_bias ? 1 : 0), "bad shape");
   EFFQ_CHECK_ARG(!wcodes_out || (code_dtype == CODE_BF16 && c1 % 8 == 0 && nlvl_w <= 256) ||
@@ -255,7 +265,37 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
   const int ldk = (int)effq_split3_ld((int64_t)c1 * taps + (has_bias ? 1 : 0));
   admm_project_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
       wstar, ldw, dual, wscale, xscale, nlvl_w, nlvl_a, c2, c1, taps, has_bias, dual_div, g_out, bstar_out,
-      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st, nx, ldk);
+      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st, nx, ldk, kp_);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// The two halves of effq_admm_track as launches of their own: the calibration loop scores an iterate with
+// effq_admm_decide (or inside effq_quadform_delta) and lets the NEXT effq_admm_project save the best iterate
+// (`keep`); effq_admm_keep flushes the last one after the loop.
+extern "C" int effq_admm_decide(effq_admm_state* st, const double* sse, double numel, float* history,
+                                const effq_peer_comm* comm, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(st && sse && numel > 0, "bad argument");
+  EFFQ_CHECK_ARG(!comm || (comm->world >= 1 && comm->world <= EFFQ_PEER_MAX && comm->rank >= 0 &&
+                           comm->rank < comm->world), "bad communicator");
+  effq_peer_comm cm;
+  if (comm) cm = *comm; else { cm.world = 1; cm.rank = 0; for (int i = 0; i < EFFQ_PEER_MAX; ++i) cm.slots[i] = nullptr; }
+  admm_decide_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st, sse, numel, history, &st->take_, cm);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_admm_keep(effq_admm_state* st, const float* g, const float* bstar, int64_t g_numel, int32_t c2,
+                              float* best_g, float* best_b, const void* aux_src, void* aux_dst, int64_t aux_bytes,
+                              void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(st && g && best_g && g_numel > 0, "bad argument");
+  EFFQ_CHECK_ARG(aux_bytes == 0 || (aux_src && aux_dst && aux_bytes % 16 == 0 &&
+                                    ((uintptr_t)aux_src & 15) == 0 && ((uintptr_t)aux_dst & 15) == 0),
+                 "aux buffers must be 16B aligned and sized");
+  admm_keep_kernel<<<grid_for(g_numel), AD_THREADS, 0, (cudaStream_t)stream>>>(
+      &st->take_, g, bstar, g_numel, c2, best_g, best_b, (const uint4*)aux_src, (uint4*)aux_dst, aux_bytes / 16);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

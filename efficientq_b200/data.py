@@ -78,6 +78,9 @@ class CalibrationData:
         dist = dist or DistCtx()
         n_total = int(getattr(a, "lwq_batchsz", 1) or 1)
         first = int(getattr(a, "lwq_dataid", 0) or 0)
+        if n_total < dist.world:
+            raise ValueError(f"lwq_batchsz = {n_total} calibration volume(s) cannot be sharded over {dist.world} ranks: "
+                             f"every rank needs at least one volume (raise lwq_batchsz or launch fewer processes)")
         lo, hi = dist.shard(n_total)
         n_mod = int(getattr(a, "nMod", None) or (4 if self.task == "brats" else 1))
         if self.synthetic:

@@ -36,16 +36,27 @@ class DistCtx:
 
     def peer_link(self, device: torch.device):
         """The NVLink peer link of this run (created on first use; None for a single process, for
-        non-CUDA process groups, with EFFQ_PEER=0, or when CUDA IPC is unavailable)."""
+        non-CUDA process groups, with EFFQ_PEER=0, or when CUDA IPC is unavailable on ANY rank: the
+        decision is collective -- a rank that fell back to NCCL alone would wait in a different
+        collective than its peers)."""
         if self._peer is None and self.world > 1 and device.type == "cuda" and \
                 os.environ.get("EFFQ_PEER", "1") != "0" and td.get_backend(self.group) == "nccl":
-            try:
-                self._peer = PeerLink(self, device)
-            except Exception as exc:  # noqa: BLE001  (plumbing only: the NCCL form of the exchanges remains)
+            link = PeerLink(self, device)
+            if link.ok:
+                self._peer = link
+            else:
                 import warnings
-                warnings.warn(f"NVLink peer link unavailable ({exc!r}); using NCCL all-reduces")
+                warnings.warn(f"NVLink peer link unavailable ({link.error!r} on this rank or a failure on a peer); "
+                              "using NCCL all-reduces")
+                link.close()
                 self._peer = False
         return self._peer or None
+
+    def close(self) -> None:
+        """Release the peer mappings (end of do_ptq)."""
+        if self._peer:
+            self._peer.close()
+        self._peer = None
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         """In-place SUM all-reduce (no-op for a single process); returns ``t``."""
@@ -89,28 +100,42 @@ class PeerLink:
         import ctypes as C
         from . import capi
         lib = capi.load()
-        if ctx.world > 8:
-            raise capi.EffqError("PeerLink: at most 8 ranks (one node)")
         self._lib = lib
         self.local = C.c_void_p()
+        self._opened = []
+        self.error = None
+        self.comm = capi.PeerComm()
+        self.comm.rank, self.comm.world = ctx.rank, ctx.world
+        # Every step that can fail locally is followed by the SAME collectives on every rank; `ok` is the
+        # all-reduced (MIN) success flag, so either all ranks use the link or none does.
         handle = C.create_string_buffer(64)
-        capi.check(lib.effq_peer_alloc(C.byref(self.local), handle), "effq_peer_alloc")
+        try:
+            if ctx.world > 8:
+                raise capi.EffqError("PeerLink: at most 8 ranks (one node)")
+            capi.check(lib.effq_peer_alloc(C.byref(self.local), handle), "effq_peer_alloc")
+        except Exception as exc:  # noqa: BLE001
+            self.error = exc
         mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
         gathered = [torch.empty_like(mine) for _ in range(ctx.world)]
         td.all_gather(gathered, mine, group=ctx.group)
-        self.comm = capi.PeerComm()
-        self.comm.rank, self.comm.world = ctx.rank, ctx.world
-        self._opened = []
-        for r, h in enumerate(gathered):
-            if r == ctx.rank:
-                self.comm.slots[r] = self.local.value
-                continue
-            p = C.c_void_p()
-            capi.check(lib.effq_peer_open(bytes(h.cpu().numpy().tobytes()), C.byref(p)), "effq_peer_open")
-            self._opened.append(p)
-            self.comm.slots[r] = p.value
+        flag = torch.tensor([0.0 if self.error else 1.0], device=device)
+        td.all_reduce(flag, op=td.ReduceOp.MIN, group=ctx.group)
+        if float(flag.item()) == 1.0:
+            try:
+                for r, h in enumerate(gathered):
+                    if r == ctx.rank:
+                        self.comm.slots[r] = self.local.value
+                        continue
+                    p = C.c_void_p()
+                    capi.check(lib.effq_peer_open(bytes(h.cpu().numpy().tobytes()), C.byref(p)), "effq_peer_open")
+                    self._opened.append(p)
+                    self.comm.slots[r] = p.value
+            except Exception as exc:  # noqa: BLE001
+                self.error = exc
+        flag = torch.tensor([0.0 if self.error else 1.0], device=device)
+        td.all_reduce(flag, op=td.ReduceOp.MIN, group=ctx.group)     # also the "everyone has mapped everything" barrier
+        self.ok = float(flag.item()) == 1.0
         self.comm_ptr = C.byref(self.comm)
-        ctx.barrier()                     # every rank has mapped every buffer before the first kernel uses them
 
     def close(self) -> None:
         for p in self._opened:

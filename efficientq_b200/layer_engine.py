@@ -106,11 +106,95 @@ class LayerCalibrator:
             s = self.xstate.read()
             done = bool(s["converged"] or s["failed"])
 
+    # -- a9: (A0 + rho*quasi_eye + eta*I)^-1 ------------------------------------------------------
+    def inverse_of(self, a0: torch.Tensor, rho: float, eta: float, has_bias: bool, solve_tc: bool, fstate: dict,
+                   rep: Optional[LayerReport] = None, check_first: bool = True):
+        """One normal matrix of the layer (solver.py:316-331), assembled, factorised and inverted on the current
+        stream.  Returns (A^-1 -- as three bf16 planes when ``solve_tc`` --, info tensor of the factorisation).
+        ``fstate['use64']`` carries the layer's decision to factorise in fp64 (taken on its first, worst-conditioned
+        system when ``check_first``)."""
+        kp = a0.shape[0]
+        dev = a0.device
+        rep = rep or LayerReport()
+        a_r = torch.empty_like(a0)
+        ops.admm_lhs(a0, rho, eta, has_bias, a_r)
+        if not fstate["use64"]:
+            chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
+                                       lambda: torch.linalg.cholesky_ex(a_r))
+            # The smallest rho is the worst-conditioned system.  With fewer voxels than unknowns
+            # (LiTS deepest level: V = 400, K' = 13825) cond(A) = lambda_max(A0)/(rho+eta) reaches
+            # 1e8+ and an fp32 pivot can come out negative: check it once (one sync per layer, on
+            # the side stream) and, if so, factorise and invert every A of this layer in fp64.
+            if (check_first and int(info.item()) != 0) or fstate.get("force64"):
+                fstate["use64"] = True
+                rep.fp64_factor = True
+        if fstate["use64"]:
+            a64 = a_r.double()
+            chol64, info = ops.timer.run("lib_cholesky_f64", {"flops": kp ** 3 / 3.0},
+                                         lambda: torch.linalg.cholesky_ex(a64))
+            if int(info.item()) != 0 or fstate.get("force_lu"):
+                # not positive definite even in fp64 (A0 itself is off by more than rho + eta):
+                # LU, which is what the reference's torch.linalg.solve does (solver.py:331)
+                inv64, info = ops.timer.run("lib_lu_inverse_f64", {"flops": 2.0 * kp ** 3},
+                                            lambda: torch.linalg.inv_ex(a64))
+                rep.lu_factor = True
+            else:
+                inv64 = ops.timer.run("lib_cholesky_inverse_f64", {"flops": 2.0 * kp ** 3 / 3.0},
+                                      lambda: torch.cholesky_inverse(chol64))
+            inv_r = inv64.float()
+            del a64, chol64, inv64
+        elif solve_tc and kp >= 1024 and os.environ.get("EFFQ_INV_TC", "1") != "0":
+            # A^-1 = L^-T L^-1: one library TRSM for W = L^-1, then W^T W on the tensor cores
+            # (the library's potri runs at ~5 TFLOP/s and was the largest item of the step)
+            eye = self._eye(kp, dev)
+            w_inv = ops.timer.run("lib_trsm", {"flops": float(kp) ** 3},
+                                  lambda: torch.linalg.solve_triangular(chol, eye, upper=False))
+            wt = ops.split3_bf16(w_inv.T)              # rows of W^T: K-major operand of (W^T W)[i][j]
+            inv_r, self._sg_ws2 = ops.solve_gemm_tc(wt, wt, kp, ws=self._sg_ws2)
+            del w_inv, wt
+        else:
+            inv_r = ops.timer.run("lib_cholesky_inverse", {"flops": 2.0 * kp ** 3 / 3.0},
+                                  lambda: torch.cholesky_inverse(chol))
+        if solve_tc:
+            # A^-1 is symmetric: a column-major result is read as its (row-major) transpose, no copy
+            inv_rm = inv_r if inv_r.stride(1) == 1 else inv_r.T
+            inv_r = ops.timer.run("split3_bf16", {"bytes": 10 * kp * kp}, lambda: ops.split3_bf16(inv_rm))
+        return inv_r, info
+
+    @staticmethod
+    def use_solve_tc(kp: int, force_generic: bool = False) -> bool:
+        """K' >= 256: the per-iteration product B A^-1 runs on the tensor cores from bf16 split planes
+        (fp32-class accuracy, csrc/solve_gemm_tc.cu); smaller systems stay on the library SGEMM."""
+        return kp >= 256 and not force_generic and os.environ.get("EFFQ_SOLVE_TC", "1") != "0"
+
+    def proximal_step(self, a0, b0, w0p, g, dual, rho: float, eta: float, has_bias: bool, fstate=None):
+        """One stand-alone proximal step  w* = (B0 + eta W0' + rho (G - dual)) A^-1  (solver.py:316-345) through
+        the same kernels as the loop in ``run``; returns the C2 x K' solution.  Used by the solve-chain tests."""
+        c2, kp = b0.shape
+        solve_tc = self.use_solve_tc(kp, self.force_generic)
+        inv_r, info = self.inverse_of(a0, rho, eta, has_bias, solve_tc, fstate if fstate is not None else {"use64": False})
+        if int(info.item()) != 0:
+            raise ops.EffqError("normal matrix is numerically singular")
+        if solve_tc:
+            planes = torch.empty((3, c2, ops.split3_ld(kp)), dtype=torch.bfloat16, device=a0.device)
+            ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=planes)
+            sol, self._sg_ws = ops.solve_gemm_tc(planes, inv_r, kp, ws=self._sg_ws)
+            return sol
+        bmat = torch.empty((c2, kp), dtype=torch.float32, device=a0.device)
+        ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat)
+        return torch.matmul(bmat, inv_r)
+
     # -- the layer -----------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out_fp: torch.Tensor,
-            stride, padding, qlvl_w: int, qlvl_act: int, q_act: bool, mask_pyramid=None, name: str = ""):
-        """Returns (weight*, bias*, alpha_w (0-dim device fp32), alpha_act or None, layer output, report)."""
+            stride, padding, qlvl_w: int, qlvl_act: int, q_act: bool, mask_pyramid=None, name: str = "",
+            resume=None, stop_iter: Optional[int] = None):
+        """Returns (weight*, bias*, alpha_w (0-dim device fp32), alpha_act or None, layer output, report).
+
+        ``resume = (G, dual, start_iter)`` enters the ADMM loop at iteration ``start_iter`` with that state (rho follows
+        from the schedule) and ``stop_iter`` leaves it early: the one-step-ahead parity tests run single iterations
+        from states recorded in the reference (tests/test_gpu_parity.py).  Device-side bookkeeping (history index,
+        best-iterate seed) then counts from the first executed iteration."""
         dev = self.device
         dist = self.dist
         x = x.detach().contiguous().float()
@@ -192,18 +276,30 @@ class LayerCalibrator:
             stats64 = ops.gram_f64(qx, out_fp, ksize, stride, padding, has_bias=has_bias)
             if dist.world > 1:
                 dist.all_reduce_sum(stats64)
-            if self._qf_ws is None:
-                self._qf_ws = ops.workspace(16 + 8 * 1024, dev)
+        # quantised 3x3x3 layers up to 64 channels (K' <= 1729): the quantised input is just as constant, so after the
+        # first iterate (scored by the conv, which also leaves its output) the other 199 are scored from the fp64
+        # statistics of the RESIDUAL R = Y - conv(first iterate) -- csrc/quadform.cu.  Beyond 64 channels the
+        # C2 K'^2 fp64 form costs more than the tensor-core conv it would replace.
+        qf_delta = use_tc and need_gram_tc and ksize == (3, 3, 3) and kp <= 2048 and not self.force_generic and \
+            os.environ.get("EFFQ_QF", "1") != "0"
+        yy_dev = torch.tensor([y_sq], dtype=torch.float64, device=dev) if stats64 is not None else None
+        g_ref = b_ref = None
+        gram_flag2 = None
         w0p = torch.cat([w0.reshape(c2, k), bias.detach().float().reshape(c2, 1)], 1).contiguous() if has_bias \
             else w0.reshape(c2, k).contiguous()
 
-        g = w0.reshape(c2, k).clone()
-        dual = torch.zeros_like(g)
+        it_first, it_end = 0, self.n_iter if stop_iter is None else min(int(stop_iter), self.n_iter)
+        if resume is not None:
+            g = resume[0].detach().to(dev).float().reshape(c2, k).clone()
+            dual = resume[1].detach().to(dev).float().reshape(c2, k).clone()
+            it_first = int(resume[2])
+        else:
+            g = w0.reshape(c2, k).clone()
+            dual = torch.zeros_like(g)
         bstar = bias.detach().float().clone() if has_bias else None
         best_g = torch.empty_like(g)
         best_b = torch.empty_like(bstar) if has_bias else None
         bmat = torch.empty((c2, kp), dtype=torch.float32, device=dev)
-        amat = torch.empty((kp, kp), dtype=torch.float32, device=dev)   # shape/dtype template for the per-rho matrices
         hist = torch.zeros(self.n_iter, dtype=torch.float32, device=dev)
         wcodes = best_wcodes = None
         if use_tc:
@@ -217,65 +313,29 @@ class LayerCalibrator:
         # known up front) and is SPD (A0 is PSD, eta > 0).  The reference re-factorises it in every
         # one of the 200 iterations (solver.py:331); here each value is factorised and inverted
         # once, on a side stream, so the later ones overlap the ADMM iterations of the earlier ones.
-        rhos, r_ = [rho], rho
-        for it in range(0, self.n_iter, self.rho_period):
-            r_ = r_ * 2 if r_ * 2 <= rho_m else rho_m
-            if r_ != rhos[-1]:
+        # rho of every iteration (EfficientQConv.py:129-137: doubled after iterations 0, 50, 100, ... up to rho_max)
+        rho_seq, r_ = [], rho
+        for it in range(self.n_iter):
+            rho_seq.append(r_)
+            if it % self.rho_period == 0:
+                r_ = r_ * 2 if r_ * 2 <= rho_m else rho_m
+        rho_seq.append(r_)
+        rhos = []
+        for r_ in rho_seq[it_first:it_end]:              # only the systems the executed iterations need
+            if r_ not in rhos:
                 rhos.append(r_)
+        rho = rho_seq[it_first]
         main = torch.cuda.current_stream(dev)
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
         self._side.wait_stream(main)
         inverses, infos = {}, []
-        # K' >= 256: the per-iteration product B A^-1 runs on the tensor cores from bf16 split planes
-        # (fp32-class accuracy, csrc/solve_gemm_tc.cu); smaller systems stay on the library SGEMM
-        solve_tc = kp >= 256 and not self.force_generic and os.environ.get("EFFQ_SOLVE_TC", "1") != "0"
+        solve_tc = self.use_solve_tc(kp, self.force_generic)
         with torch.cuda.stream(self._side):
-            use64 = False
+            fstate = {"use64": False, "force64": self.force_fp64_factor or self.force_lu_factor,
+                      "force_lu": self.force_lu_factor}
             for idx, r_ in enumerate(rhos):
-                a_r = torch.empty_like(amat)
-                ops.admm_lhs(a0, r_, eta, has_bias, a_r)
-                if not use64:
-                    chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
-                                               lambda: torch.linalg.cholesky_ex(a_r))
-                    # The smallest rho is the worst-conditioned system.  With fewer voxels than unknowns
-                    # (LiTS deepest level: V = 400, K' = 13825) cond(A) = lambda_max(A0)/(rho+eta) reaches
-                    # 1e8+ and an fp32 pivot can come out negative: check it once (one sync per layer, on
-                    # the side stream) and, if so, factorise and invert every A of this layer in fp64.
-                    if idx == 0 and int(info.item()) != 0:
-                        use64 = True
-                        rep.fp64_factor = True
-                if use64:
-                    a64 = a_r.double()
-                    chol64, info = ops.timer.run("lib_cholesky_f64", {"flops": kp ** 3 / 3.0},
-                                                 lambda: torch.linalg.cholesky_ex(a64))
-                    if int(info.item()) != 0:
-                        # not positive definite even in fp64 (A0 itself is off by more than rho + eta):
-                        # LU, which is what the reference's torch.linalg.solve does (solver.py:331)
-                        inv64, info = ops.timer.run("lib_lu_inverse_f64", {"flops": 2.0 * kp ** 3},
-                                                    lambda: torch.linalg.inv_ex(a64))
-                        rep.lu_factor = True
-                    else:
-                        inv64 = ops.timer.run("lib_cholesky_inverse_f64", {"flops": 2.0 * kp ** 3 / 3.0},
-                                              lambda: torch.cholesky_inverse(chol64))
-                    inv_r = inv64.float()
-                    del a64, chol64, inv64
-                elif solve_tc and kp >= 1024 and os.environ.get("EFFQ_INV_TC", "1") != "0":
-                    # A^-1 = L^-T L^-1: one library TRSM for W = L^-1, then W^T W on the tensor cores
-                    # (the library's potri runs at ~5 TFLOP/s and was the largest item of the step)
-                    eye = self._eye(kp, dev)
-                    w_inv = ops.timer.run("lib_trsm", {"flops": float(kp) ** 3},
-                                          lambda: torch.linalg.solve_triangular(chol, eye, upper=False))
-                    wt = ops.split3_bf16(w_inv.T)              # rows of W^T: K-major operand of (W^T W)[i][j]
-                    inv_r, self._sg_ws2 = ops.solve_gemm_tc(wt, wt, kp, ws=self._sg_ws2)
-                    del w_inv, wt
-                else:
-                    inv_r = ops.timer.run("lib_cholesky_inverse", {"flops": 2.0 * kp ** 3 / 3.0},
-                                          lambda: torch.cholesky_inverse(chol))
-                if solve_tc:
-                    # A^-1 is symmetric: a column-major result is read as its (row-major) transpose, no copy
-                    inv_rm = inv_r if inv_r.stride(1) == 1 else inv_r.T
-                    inv_r = ops.timer.run("split3_bf16", {"bytes": 10 * kp * kp}, lambda: ops.split3_bf16(inv_rm))
+                inv_r, info = self.inverse_of(a0, r_, eta, has_bias, solve_tc, fstate, rep, check_first=(idx == 0))
                 inv_r.record_stream(main)
                 ev = torch.cuda.Event()
                 ev.record(self._side)
@@ -307,17 +367,18 @@ class LayerCalibrator:
         # host-bound (19 ms of enqueue for 19 ms of GPU time per layer, profiles/r01_loop_prof.txt).
         from contextlib import nullcontext
         from . import capi as _capi
-        replayable = not (dist.world > 1 and stats64 is None and peer is None) and \
+        replayable = not (dist.world > 1 and stats64 is None and not qf_delta and peer is None) and \
             os.environ.get("EFFQ_REPLAY", "1") != "0"            # an NCCL all-reduce inside the loop cannot be re-issued
+        keep_bufs = (best_g, best_b, best_wcodes)
         steady = None
         sol_small = None if solve_tc else torch.empty((c2, kp), dtype=torch.float32, device=dev)
-        for it in range(self.n_iter):
+        for it in range(it_first, it_end):
             if rho_built != rho:
                 ainv, ev = inverses[rho]
                 main.wait_event(ev)
                 rho_built = rho
                 steady = None
-            special = it == 0 or it % self.rho_period == 0 or it + 1 == self.n_iter
+            special = it == it_first or it % self.rho_period == 0 or it + 1 == it_end or self.probe is not None
             if steady is not None and not special:
                 pre, mm, post = steady
                 ops.replay(pre)
@@ -331,7 +392,7 @@ class LayerCalibrator:
                 mm = None
                 # proximal step (solver.py:316-345): w* = solve(A, B^T)^T = B A^-1
                 if solve_tc:
-                    if it == 0:     # later right-hand sides come out of admm_project of the previous iteration
+                    if it == it_first:     # later right-hand sides come out of admm_project of the previous iteration
                         ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
                                       lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
                     sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
@@ -355,32 +416,56 @@ class LayerCalibrator:
                         new_rho, div = rho * 2, 2.0
                     else:
                         new_rho, div = rho_m, rho_m / rho
-                nxt = (b0, w0p, new_rho, eta, bplanes) if (solve_tc and it + 1 < self.n_iter) else None
+                nxt = (b0, w0p, new_rho, eta, bplanes) if (solve_tc and it + 1 < it_end) else None
+                if self.probe is not None:
+                    self._probe(name, f"it{it}_wstar", sol)
+                # the previous iterate, if it was the best so far, is saved by this launch (keep) before G, b* and the
+                # weight codes are overwritten
                 ops.timer.run("admm_project", {"bytes": 16 * c2 * k}, lambda: ops.admm_project(
                     sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps, has_bias, div,
-                    g, bstar, wcodes, self.st, next_rhs=nxt))
-                # score the iterate (EfficientQConv.py:118-122)
-                if use_tc:
-                    ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize, want_out=False,
-                                  target=out_fp, ws=self.tc_ws, sse=self.sse)
-                elif stats64 is not None:
-                    ops.quadform_sse(stats64, y_sq, g, bstar, self.sse, self._qf_ws)      # already global
+                    g, bstar, wcodes, self.st, next_rhs=nxt, keep=keep_bufs))
+                # score the iterate (EfficientQConv.py:118-122) and do the best-iterate bookkeeping (:139-142)
+                if stats64 is not None:
+                    ops.quadform_delta(stats64, yy_dev, g, bstar, self.sse, g_ref, b_ref, st=self.st,
+                                       numel=numel_total, history=hist)                      # statistics are global
                 else:
-                    ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
-                                   ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
-                track_comm = None
-                if dist.world > 1 and stats64 is None:                # this rank's share of the squared error
-                    if peer is not None:
-                        track_comm = peer.comm_ptr                    # summed inside admm_track over NVLink
+                    out0 = None
+                    if use_tc:
+                        out0, _ = ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize,
+                                                want_out=qf_delta, target=out_fp, ws=self.tc_ws, sse=self.sse)
                     else:
-                        dist.all_reduce_sum(self.sse)
-                ops.timer.run("admm_track", {"bytes": 8 * c2 * k}, lambda: ops.admm_track(
-                    self.st, self.sse, numel_total, g, bstar, best_g, best_b, hist, wcodes, best_wcodes,
-                    comm=track_comm))
+                        ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
+                                       ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
+                    track_comm = None
+                    if dist.world > 1:                                    # this rank's share of the squared error
+                        if peer is not None:
+                            track_comm = peer.comm_ptr                    # summed inside the decide kernel over NVLink
+                        else:
+                            dist.all_reduce_sum(self.sse)
+                    ops.timer.run("admm_decide", {"bytes": 64}, lambda: ops.admm_decide(
+                        self.st, self.sse, numel_total, hist, comm=track_comm))
+                    if qf_delta:
+                        # residual statistics of this (first executed) iterate: R = Y - out0, T = R X^T, sum R^2
+                        torch.sub(out_fp, out0, out=out0)
+                        code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
+                        stats64, self.gram_ws, gram_flag2 = ops.gram_tc_f64(xcodes, code_scale, out0, None,
+                                                                             has_bias=has_bias, ws=self.gram_ws,
+                                                                             att_exact=True)
+                        yy_dev = self.sse.clone()
+                        if dist.world > 1:
+                            dist.all_reduce_sum(stats64)
+                            if peer is not None:                          # with NCCL scoring self.sse is already global
+                                dist.all_reduce_sum(yy_dev)
+                        g_ref, b_ref = g.clone(), (bstar.clone() if has_bias else None)
+                        del out0
                 if recording:
                     steady = (rec.calls[:n_pre], mm if not solve_tc else None, rec.calls[n_pre:])
+                if self.probe is not None:
+                    for tag, t in (("g", g), ("dual", dual), ("bstar", bstar), ("a_w", self.st.a_w_tensor()), ("wcodes", wcodes)):
+                        self._probe(name, f"it{it}_{tag}", t)
             rho = new_rho
 
+        ops.admm_keep(self.st, g, bstar, best_g, best_b, wcodes, best_wcodes)      # the last iterate, if it was the best
         if loop_prof:
             t_cpu = _t.perf_counter() - t_cpu0
             ev_b.record()
@@ -396,6 +481,7 @@ class LayerCalibrator:
                                       sse=self.sse)
         if dist.world > 1:
             dist.all_reduce_sum(self.sse)
+        main.wait_stream(self._side)               # every factorisation (also an unused last one) is ordered before the read-back
         alpha_w = self.st.a_w_tensor().clone()     # LAST iterate's scale (reference quirk, :158)
         s = self.st.read()                          # the layer's one result read-back
         final_sse = float(self.sse.item())
@@ -404,6 +490,8 @@ class LayerCalibrator:
                                 f"{', fp64 LU included' if rep.lu_factor else ''})")
         if solve_tc and int(self._sg_ws[:4].view(torch.int32)[0].item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 solve GEMM aborted (barrier timeout)")
+        if gram_flag2 is not None and int(gram_flag2.item()) != 0:
+            raise ops.EffqError(f"{name}: tcgen05 Gram kernel (residual statistics) aborted (barrier timeout)")
         if gram_flag is not None and int(gram_flag.item()) != 0:
             raise ops.EffqError(f"{name}: tcgen05 Gram kernel aborted (barrier timeout)")
         if final_sse != final_sse:
@@ -437,6 +525,8 @@ class LayerCalibrator:
         if self.probe is not None and t is not None:
             self.probe(name, tag, t)
 
+    force_fp64_factor = False      # tests: take the fp64-Cholesky / fp64-LU fallbacks of inverse_of on any layer
+    force_lu_factor = False
     _cws = None
     _sg_ws = None
     _sg_ws2 = None          # split-K partials of the K' x K' inverse product (side stream)
@@ -449,7 +539,6 @@ class LayerCalibrator:
             self._eyes[n] = torch.eye(n, dtype=torch.float32, device=dev)
         return self._eyes[n]
 
-    _qf_ws = None
     _side = None
 
     def _conv_ws(self, x, c2, ksize, stride, padding):

@@ -396,6 +396,51 @@ def quadform_sse(acc, sum_y2: float, g, bstar, sse, ws):
                                         ptr(sse), ptr(ws), stream()), "effq_quadform_sse")
 
 
+_qf_ws = {}
+
+
+def quadform_delta(acc, sum_sq: torch.Tensor, g, bstar, sse, g_ref=None, b_ref=None, st: Optional["AdmmState"] = None,
+                   numel: float = 0.0, history=None):
+    """sse <- sum((conv(x, G) + b* - y)^2) from fp64 statistics, tiled kernel (csrc/quadform.cu).  With
+    (g_ref, b_ref) the statistics are those of the residual R = y - conv(x, g_ref) - b_ref and ``sum_sq`` (device
+    fp64 scalar) is sum R^2.  ``st``: also do the best-iterate bookkeeping of the scored iterate (numel, history)."""
+    c2, k = g.shape
+    if sum_sq.dtype != torch.float64 or not sum_sq.is_cuda:
+        raise EffqError("quadform_delta: sum_sq must be a CUDA float64 scalar")
+    lib = capi.load()
+    key = (g.device.type, g.device.index)
+    if key not in _qf_ws:
+        _qf_ws[key] = workspace(lib.effq_quadform_delta_workspace(c2, k + 1), g.device)
+    kp = k + (1 if bstar is not None else 0)
+    timer.run(f"quadform_k{kp}", {"flops": 2.0 * c2 * kp * kp}, lambda: check(
+        lib.effq_quadform_delta(ptr(acc), ptr(sum_sq), ptr(g), ptr(bstar), ptr(g_ref), ptr(b_ref), c2, k,
+                                int(bstar is not None), ptr(sse), ptr(_qf_ws[key]), st.p if st is not None else None,
+                                float(numel), ptr(history), stream()), "effq_quadform_delta"))
+
+
+def gram_tc_f64(xcodes, code_scale, y, att=None, has_bias=True, ws=None, att_exact=False):
+    """[X^ diag(att) X^T ; Y diag(att) X^T] as one full fp64 matrix in real units (operand of quadform_delta),
+    from the tcgen05 Gram kernel.  Returns (acc64, workspace, abort flag)."""
+    y = _f32c(y, "y")
+    n, d, h, w, c1 = xcodes.shape
+    g = Geom.make((n, c1, d, h, w), y.shape[1], 3, 1, 1)
+    kp = g.c1 * 27 + (1 if has_bias else 0)
+    lib = capi.load()
+    need = lib.effq_gram_workspace(C.byref(g), int(has_bias))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+    acc = torch.empty((kp + g.c2, kp), dtype=torch.float64, device=y.device)
+    if att is not None:
+        att = _f32c(att, "att")
+    cs = _f32c(code_scale.reshape(1), "code_scale")
+    flops = 2.0 * g.n * d * h * w * (kp + g.c2) * kp
+    timer.run("gram_tc_f64", {"flops": flops}, lambda: check(
+        lib.effq_gram_tc_f64(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(has_bias), int(bool(att_exact)),
+                             ptr(acc), ptr(ws), stream()), "effq_gram_tc_f64"))
+    flag = ws[need - 16:need - 12].view(torch.int32)
+    return acc, ws, flag
+
+
 def gram_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
     g = Geom.make(x_shape, c2, ksize, stride, padding)
     return bool(capi.load().effq_gram_tc_supported(C.byref(g)))
@@ -509,9 +554,15 @@ def admm_lhs(a0, rho: float, eta: float, has_bias: bool, out):
 
 def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], nlvl_w: int, nlvl_a: int,
                  c2: int, c1: int, taps: int, has_bias: bool, dual_div: float, g_out, bstar_out, wcodes_out,
-                 st: AdmmState, next_rhs=None):
+                 st: AdmmState, next_rhs=None, keep=None):
     """``next_rhs`` = (b0, w0p, rho_next, eta, planes): also emit the next iteration's right-hand side
-    as split planes (replaces the next admm_rhs launch)."""
+    as split planes (replaces the next admm_rhs launch).  ``keep`` = (best_g, best_b, best_wcodes): save the
+    previous iterate (still in g_out / bstar_out / wcodes_out) first if the step that scored it made it the best."""
+    kp_ = None
+    if keep is not None:
+        bg, bb, bw = keep
+        kp_ = C.byref(capi.AdmmKeep(bg.data_ptr(), bb.data_ptr() if bb is not None else None,
+                                    bw.data_ptr() if bw is not None else None))
     ldw = wstar.stride(0)
     nx = None
     if next_rhs is not None:
@@ -520,9 +571,21 @@ def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], 
     check(capi.load().effq_admm_project(ptr(wstar), ldw, ptr(dual), wstate.p, xstate.p if xstate else None,
                                         int(nlvl_w), int(nlvl_a), c2, c1, taps, int(has_bias), float(dual_div),
                                         ptr(g_out), ptr(bstar_out), ptr(wcodes_out),
-                                        code_dtype_of(wcodes_out) if wcodes_out is not None else 0, st.p, nx,
+                                        code_dtype_of(wcodes_out) if wcodes_out is not None else 0, st.p, nx, kp_,
                                         stream()),
           "effq_admm_project")
+
+
+def admm_decide(st: AdmmState, sse, numel: float, history, comm=None):
+    """Best-iterate bookkeeping of the iterate whose squared error is in ``sse`` (all-reduced in-kernel with
+    ``comm``); the copy of the best iterate happens in the next admm_project (``keep``) / admm_keep."""
+    check(capi.load().effq_admm_decide(st.p, ptr(sse), float(numel), ptr(history), comm, stream()), "effq_admm_decide")
+
+
+def admm_keep(st: AdmmState, g, bstar, best_g, best_b, aux_src=None, aux_dst=None):
+    nb = aux_src.numel() * aux_src.element_size() if aux_src is not None else 0
+    check(capi.load().effq_admm_keep(st.p, ptr(g), ptr(bstar), g.numel(), g.shape[0], ptr(best_g), ptr(best_b),
+                                     ptr(aux_src), ptr(aux_dst), nb, stream()), "effq_admm_keep")
 
 
 def admm_track(st: AdmmState, sse, numel: float, g, bstar, best_g, best_b, history, aux_src=None, aux_dst=None,

@@ -140,6 +140,18 @@ def get_mask_pyramid(output_fp, body_mask, weight_map: dict, init_stride, num_lv
     return pyramid
 
 
+def fp_target_hook(m, i, o):
+    """The reference's hook is ``m.output_fp = o.detach().cpu()`` (src/models/hooks.py:5-6): on the device it runs on
+    that is a COPY of the layer's pre-activation output.  A bare ``detach()`` would alias the conv output, and with
+    the BN folded to identity the next unit's ``ReLU(inplace=True)`` (blk: mid) overwrites it, turning the target
+    into the post-ReLU tensor.  The copy stays in HBM (no host round trip)."""
+    m.output_fp = o.detach().clone()
+
+
+def register_fp_hooks(model: nn.Module):
+    return [mod.register_forward_hook(fp_target_hook) for _, mod in _each(model)]
+
+
 # -- the calibration pass (ptqer.py:313-364) -------------------------------------------------
 @torch.no_grad()
 def calibrate(model: nn.Module, data_batch: torch.Tensor, task: str, init_stride, dist: Optional[DistCtx] = None,
@@ -150,9 +162,7 @@ def calibrate(model: nn.Module, data_batch: torch.Tensor, task: str, init_stride
     dev = data_batch.device
     set_name(model)
     set_fp(model)
-    handles = []
-    for _, mod in _each(model):
-        handles.append(mod.register_forward_hook(lambda m, i, o: setattr(m, "output_fp", o.detach())))
+    handles = register_fp_hooks(model)
     torch.cuda.synchronize(dev)
     t0 = time.time()
     output_fp = model(data_batch).detach()
@@ -227,6 +237,7 @@ def do_ptq(args, model_cube, data_cube, tester, snap_dir, dist: Optional[DistCtx
             fid.write("\n".join(res["layer_loss"]))
     if not getattr(args, "no_test", False) and tester is not None:
         tester.test_as_is("ptq", getattr(args, "save_nii", False))
+    dist.close()
     if dist.rank == 0 and snap_dir:
         model.cpu()
         snapshot.save(model, P.join(snap_dir, "state_in_fp.pkl"), compress=False)

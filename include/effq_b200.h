@@ -201,6 +201,20 @@ int effq_gram_f64(const float* x, const float* y, const effq_geom* g, int32_t ha
                   void* stream);
 int effq_quadform_sse(const double* acc64, double sum_y2, const float* gw, const float* bstar, int32_t c2,
                       int32_t k, int32_t has_bias, double* sse, void* workspace, void* stream);
+/* The same scoring for layers WITH quantised activations (the quantised input is just as constant), in
+ * residual form so that nothing cancels against sum y^2: for a reference iterate (g_ref, b_ref) whose
+ * conv output has been subtracted from the target, R = Y - conv3d(X^, g_ref) - b_ref, with
+ * acc64 = [S ; T], T = R X^T (effq_gram_tc_f64 with y = R, att = NULL) and *sum_sq = sum R^2:
+ *   sse = sum_r [ u_r S u_r^T - 2 u_r.T_r ] + *sum_sq ,   u = [gw - g_ref | bstar - b_ref]
+ * g_ref == NULL gives the plain form above (u = [gw | bstar], *sum_sq = sum y^2).  Tiled fp64 kernel for
+ * K' up to a few thousand (replaces EfficientQConv.py:118-122's conv + MSE per iterate).  When st != NULL
+ * the launch also does the best-iterate bookkeeping of effq_admm_decide for the iterate it scored
+ * (loss = fp32(sse / numel), history[iter]).  workspace: effq_quadform_delta_workspace() bytes, zeroed once. */
+int64_t effq_quadform_delta_workspace(int32_t c2, int32_t kp);
+int effq_quadform_delta(const double* acc64, const double* sum_sq, const float* gw, const float* bstar,
+                        const float* g_ref, const float* b_ref, int32_t c2, int32_t k, int32_t has_bias,
+                        double* sse, void* workspace, effq_admm_state* st, double numel, float* history,
+                        void* stream);
 
 /* Same statistics on the tensor cores for 3x3x3 / stride 1 / pad 1 layers with quantised
  * activations, from the NDHWC integer codes: A0 (with its bias row / column) and B0 in one
@@ -219,6 +233,12 @@ int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const f
 int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
                             const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
                             int32_t ld, void* flags, void* stream);
+/* The tcgen05 statistics as a full fp64 matrix in real units, acc64_out[(K'+C2) x K'] = [X^ diag(att) X^T ;
+ * Y diag(att) X^T] (no factor 2, mirrored, code_scale applied): the operand of effq_quadform_delta.
+ * workspace as effq_gram_workspace. */
+int effq_gram_tc_f64(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y, const float* att,
+                     const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64_out,
+                     void* workspace, void* stream);
 
 /* ---- (a9,a11) ADMM parameter update: solver.py:316-325, EfficientQConv.py:99-144 */
 /* B = B0 + eta*W0' ;  B[:, :K] += rho*(G - dual)          (solver.py:317-320) */
@@ -259,11 +279,28 @@ typedef struct effq_next_rhs {
   float        eta;
   void*        planes;  /* [3][C2][effq_split3_ld(K')] bf16 */
 } effq_next_rhs;
+/* Optional `keep` of effq_admm_project: when the PREVIOUS iterate was the best so far (st->take_, written by
+ * the step that scored it: effq_admm_decide / effq_admm_track / effq_quadform_delta) its G, b* and weight
+ * codes -- still in g_out / bstar_out / wcodes_out on entry -- are saved before being overwritten
+ * (reference EfficientQConv.py:139-142, without a launch of its own). */
+typedef struct effq_admm_keep_bufs {
+  float* best_g;        /* [C2][K]  */
+  float* best_b;        /* [C2] or NULL */
+  void*  best_wcodes;   /* same size / type as wcodes_out, or NULL */
+} effq_admm_keep_bufs;
 int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
                       const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                       int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
                       float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
-                      const effq_next_rhs* next, void* stream);
+                      const effq_next_rhs* next, const effq_admm_keep_bufs* keep, void* stream);
+/* The two halves of effq_admm_track as launches of their own.  effq_admm_decide: loss = fp32(sse/numel)
+ * (sse all-reduced in-kernel when comm != NULL), history[iter] = loss, best-iterate bookkeeping, st->take_.
+ * effq_admm_keep: copy G, b* (and aux) to the best-iterate buffers if st->take_ (after the loop's last iterate). */
+int effq_admm_decide(effq_admm_state* st, const double* sse, double numel, float* history,
+                     const effq_peer_comm* comm, void* stream);
+int effq_admm_keep(effq_admm_state* st, const float* g, const float* bstar, int64_t g_numel, int32_t c2,
+                   float* best_g, float* best_b, const void* aux_src, void* aux_dst, int64_t aux_bytes,
+                   void* stream);
 /* loss = fp32(sse/numel); history[iter] = loss; if (iter==0 || loss < best) keep G, b*
  * (and, when aux_bytes > 0, the 16B-aligned side buffer aux_src -> aux_dst, e.g. the
  * tensor-core weight codes of the same iterate). */

@@ -47,6 +47,80 @@ def meta():
                 threads=torch.get_num_threads())
 
 
+def copying_hook(m, i, o):
+    """The reference's forward hook is ``m.output_fp = o.detach().cpu()`` (src/models/hooks.py:5-6).  On the device the
+    reference is run on (``--device <gpu id>``) ``.cpu()`` is a COPY, so the stored FP target is the layer's
+    pre-activation output.  On CPU tensors ``.cpu()`` is a no-op, the target aliases the conv output, and the next
+    unit's ``ReLU(inplace=True)`` (blk: mid, BN folded to identity) overwrites it -- an artefact of running the
+    reference on the CPU, not its semantics.  The fixtures therefore register this copying form of the same hook."""
+    m.output_fp = o.detach().clone()
+
+
+class PtqTrace:
+    """Observes the unmodified ``EfficientQConv.ptq`` from the outside: a wrapper around the class method records the
+    layer's input / target / attention map, ``QuadraSolver.solve`` and ``F.mse_loss`` are wrapped to read the ADMM
+    state out of the caller's frame (``ptq``'s local variables G, dual, rho, w_star, b_star, a_w, i) -- the state
+    right before the proximal step of iteration i and right after its projection."""
+
+    def __init__(self, R, state_iters=(), keep_inputs=True):
+        self.R, self.state_iters, self.keep_inputs = R, set(state_iters), keep_inputs
+        self.layers = []                     # one dict per ptq() call, in execution order
+
+    def __enter__(self):
+        import sys as _sys
+        effq, solver = self.R["effq"], self.R["solver"]
+        self._orig = (effq.EfficientQConv.ptq, solver.QuadraSolver.solve, effq.F.mse_loss)
+        orig_ptq, orig_solve, orig_mse = self._orig
+        tr = self
+
+        def ptq(mod, x):
+            rec = dict(name=mod.name, hist=[], states={}, n_iter=mod.lwq_iter)
+            if tr.keep_inputs:
+                rec["x"] = x.detach().clone()
+                rec["y"] = mod.output_fp.detach().clone()
+                att = None
+                if mod.mask_pyramid:
+                    for lv, mask in enumerate(mod.mask_pyramid):
+                        if mask.shape[1:] == mod.output_fp.shape[2:]:
+                            att = lv
+                            break
+                rec["att_level"] = -1 if att is None else att
+            rec["w0"], rec["b0"] = mod.weight.data.clone(), mod.bias.data.clone()
+            tr.layers.append(rec)
+            out = orig_ptq(mod, x)
+            rec["final"] = float(mod.layer_loss[-1].split(":")[-1])
+            rec["alpha_w"], rec["alpha_act"] = float(mod.alpha_w.item()), float(mod.alpha_act.item())
+            rec["weight"], rec["bias"] = mod.weight.data.clone(), mod.bias.data.clone()
+            return out
+
+        def solve(qs, rho, eta, gd):
+            loc = _sys._getframe(1).f_locals
+            if "admm_iter" in loc and loc["i"] in tr.state_iters:
+                tr.layers[-1]["states"][loc["i"]] = dict(G=loc["G"].detach().clone(), dual=loc["dual"].detach().clone(),
+                                                        rho=float(rho), eta=float(eta))
+            return orig_solve(qs, rho, eta, gd)
+
+        def mse(a, t, *args, **kw):
+            v = orig_mse(a, t, *args, **kw)
+            loc = _sys._getframe(1).f_locals
+            if "admm_iter" in loc and tr.layers:
+                rec = tr.layers[-1]
+                i = loc["i"]
+                if i < loc["admm_iter"] and len(rec["hist"]) == i:
+                    rec["hist"].append(float(v.item()))
+                    if i in tr.state_iters:
+                        rec["states"][i].update(wstar=loc["w_star"].detach().clone(), bstar=loc["b_star"].detach().clone(),
+                                                a_w=float(loc["a_w"]), G_next=loc["G"].detach().clone(), loss=float(v.item()))
+            return v
+        effq.EfficientQConv.ptq, solver.QuadraSolver.solve, effq.F.mse_loss = ptq, solve, mse
+        return self
+
+    def __exit__(self, *exc):
+        effq, solver = self.R["effq"], self.R["solver"]
+        effq.EfficientQConv.ptq, solver.QuadraSolver.solve, effq.F.mse_loss = self._orig
+        return False
+
+
 LEVEL_CASES = [(4, 0, 1), (16, 0, 1), (256, 0, 1), (4, -1, 1), (16, -1, 1), (256, -1, 1)]
 
 
@@ -135,8 +209,10 @@ def gen_solver(R, out):
     solver = R["solver"]
     res = {}
     g = torch.Generator().manual_seed(14)
+    # k3_wide: K' = 1297 unknowns against V = 768 voxels -- the ill-conditioned regime (cond(A) is set by rho + eta)
+    # that takes the tensor-core inverse and the split-bf16 GEMM on the GPU
     cases = [("k3s1p1", 2, 5, 7, 3, 1, 1, (6, 7, 8)), ("k3s2p1", 2, 4, 6, 3, 2, 1, (8, 10, 12)),
-             ("k1s1p0", 3, 6, 5, 1, 1, 0, (4, 5, 6))]
+             ("k1s1p0", 3, 6, 5, 1, 1, 0, (4, 5, 6)), ("k3_wide", 2, 48, 24, 3, 1, 1, (6, 8, 8))]
     for name, n, c1, c2, k, s, p, sp in cases:
         x = torch.relu(torch.randn(n, c1, *sp, generator=g))
         w0 = torch.randn(c2, c1, k, k, k, generator=g) * 0.1
@@ -148,16 +224,20 @@ def gen_solver(R, out):
                                  mu=0, eta=0.7, W0=w0, att=att, b0=b0)
         gmat = w0 + 0.01 * torch.randn(w0.shape, generator=g)
         ws, bs = qs.solve(3.0, 0.7, gmat)
+        if cols.size > 2 ** 18:
+            cols = cols[:, :64]                                    # wide case: the first 64 columns pin the ordering
         res.update({f"{name}_x": x.numpy(), f"{name}_w0": w0.numpy(), f"{name}_b0": b0.numpy(),
                     f"{name}_y": y.numpy(), f"{name}_att": att.numpy(), f"{name}_cols": cols,
-                    f"{name}_A0": qs.A0.numpy(), f"{name}_B0": qs.B0.numpy(), f"{name}_G": gmat.numpy(),
+                    # wide case: every 5th row / column of A0 (6.7 MB otherwise)
+                    f"{name}_A0": qs.A0.numpy() if qs.A0.numel() <= 2 ** 18 else qs.A0[::5, ::5].contiguous().numpy(),
+                    f"{name}_B0": qs.B0.numpy(), f"{name}_G": gmat.numpy(),
                     f"{name}_wstar": ws.numpy(), f"{name}_bstar": bs.numpy(),
                     f"{name}_geom": np.array([k, s, p], dtype=np.int64)})
     np.savez_compressed(os.path.join(out, "solver.npz"), **res)
 
 
-def run_ref_layer(R, x, w, b, y, stride, pad, qlvl_w, qlvl_a, q_act, pyramid):
-    """EfficientQConv.ptq on one layer, recording the per-iteration losses."""
+def run_ref_layer(R, x, w, b, y, stride, pad, qlvl_w, qlvl_a, q_act, pyramid, state_iters=(), n_iter=None):
+    """EfficientQConv.ptq on one layer, recording the per-iteration losses (and the ADMM state at ``state_iters``)."""
     effq = R["effq"]
     c2, c1, k = w.shape[0], w.shape[1], w.shape[2]
     m = effq.EfficientQConv(c1, c2, k, stride, pad, bias=True, q_weight=True, qlvl=qlvl_w,
@@ -168,23 +248,27 @@ def run_ref_layer(R, x, w, b, y, stride, pad, qlvl_w, qlvl_a, q_act, pyramid):
     m.output_fp = y.clone()
     m.mask_pyramid = pyramid
     m.layer_loss = []
-    hist = []
-    orig = effq.F.mse_loss
+    if n_iter is not None:
+        m.lwq_iter = n_iter               # an attribute of the reference module (EfficientQConv.py:23), not a code change
+    tr = PtqTrace(R, state_iters=state_iters, keep_inputs=False)
+    with tr, torch.no_grad():
+        m.ptq(x)
+    rec = tr.layers[0]
+    res = dict(weight=m.weight.data.numpy(), bias=m.bias.data.numpy(),
+               alpha_w=np.float32(m.alpha_w.item()), alpha_act=np.float32(m.alpha_act.item()),
+               hist=np.array(rec["hist"], dtype=np.float64), final=np.float64(rec["final"]))
+    lm1 = qlvl_w - 1
+    for i, st in sorted(rec["states"].items()):
+        res[f"st{i}_dual"], res[f"st{i}_wstar"], res[f"st{i}_bstar"] = st["dual"].numpy(), st["wstar"].numpy(), st["bstar"].numpy()
+        res[f"st{i}_rho"], res[f"st{i}_a_w"], res[f"st{i}_loss"] = np.float64(st["rho"]), np.float64(st["a_w"]), np.float64(st["loss"])
+        res[f"st{i}_G"] = st["G"].numpy()                        # <= L distinct values: compresses well
+        nxt = torch.round(st["G_next"] / float(st["a_w"]) * lm1)
+        res[f"st{i}_codes_next"] = nxt.numpy().astype(np.int16)
+    return res
 
-    def rec(a, t, *args, **kw):
-        v = orig(a, t, *args, **kw)
-        hist.append(float(v.item()))
-        return v
-    effq.F.mse_loss = rec
-    try:
-        with torch.no_grad():
-            m.ptq(x)
-    finally:
-        effq.F.mse_loss = orig
-    final = float(m.layer_loss[0].split(":")[-1])
-    return dict(weight=m.weight.data.numpy(), bias=m.bias.data.numpy(),
-                alpha_w=np.float32(m.alpha_w.item()), alpha_act=np.float32(m.alpha_act.item()),
-                hist=np.array(hist[:200], dtype=np.float64), final=np.float64(final))
+
+STATE_ITERS = (0, 1, 2, 49, 50, 51, 100, 150, 199)
+STATE_ITERS_WIDE = (0, 1, 50, 51, 199)
 
 
 LAYER_CASES = [
@@ -205,7 +289,7 @@ WIDE_LAYER_CASES = [
 ]
 
 
-def gen_layers(R, out, cases=LAYER_CASES, seed=15, fname="layers.npz"):
+def gen_layers(R, out, cases=LAYER_CASES, seed=15, fname="layers.npz", state_iters=STATE_ITERS):
     res = {}
     g = torch.Generator().manual_seed(seed)
     for name, n, c1, c2, k, s, p, sp, lw, la, qa in cases:
@@ -217,7 +301,7 @@ def gen_layers(R, out, cases=LAYER_CASES, seed=15, fname="layers.npz"):
         y = F.conv3d(x, w, b, s, p)
         att = (torch.rand(n, *y.shape[2:], generator=g) * 3).floor() + 1.0
         pyramid = [torch.ones(n, 3, 3, 3), att]
-        r = run_ref_layer(R, x, w, b, y, s, p, lw, la, qa, pyramid)
+        r = run_ref_layer(R, x, w, b, y, s, p, lw, la, qa, pyramid, state_iters=state_iters)
         res.update({f"{name}_x": x.numpy(), f"{name}_w": w.numpy(), f"{name}_b": b.numpy(),
                     f"{name}_y": y.numpy(), f"{name}_att": att.numpy(),
                     f"{name}_cfg": np.array([k, s, p, lw, la, int(qa)], dtype=np.int64)})
@@ -227,7 +311,59 @@ def gen_layers(R, out, cases=LAYER_CASES, seed=15, fname="layers.npz"):
 
 
 def gen_layers_wide(R, out):
-    gen_layers(R, out, WIDE_LAYER_CASES, seed=17, fname="layers_wide.npz")
+    gen_layers(R, out, WIDE_LAYER_CASES, seed=17, fname="layers_wide.npz", state_iters=STATE_ITERS_WIDE)
+
+
+# Real widths of the BraTS net's two deepest levels (K' = 3457 and 6913).  Inputs are regenerated from
+# these seeds by the test (torch's CPU generator is deterministic for a given torch version, tests/golden/VERSIONS.txt),
+# so only checksums and results are stored.  V >= 2 K' voxels, like the real layers (V >= 38 K' there).
+REAL_WIDTH_CASES = [
+    # name, channels, spatial, reference iterations, reference runs of the sensitivity ensemble
+    ("c128", 128, (16, 24, 24), 200, 2),
+    ("c256", 256, (24, 24, 24), 5, 0),
+]
+
+
+def real_width_inputs(name, c, sp, perturb=None):
+    g = torch.Generator().manual_seed(2000 + c)
+    x = torch.relu(torch.randn(1, c, *sp, generator=g))
+    w = torch.randn(c, c, 3, 3, 3, generator=g) * (2.0 / (c * 27)) ** 0.5
+    b = torch.randn(c, generator=g) * 0.05
+    att = (torch.rand(1, *sp, generator=g) * 3).floor() + 1.0
+    if perturb is not None:
+        x = x * (1.0 + 1e-7 * torch.randn(x.shape, generator=torch.Generator().manual_seed(3000 + perturb)))
+    y = F.conv3d(x, w, b, 1, 1)
+    return x, w, b, y, att
+
+
+def gen_real_width(R, out):
+    res = {}
+    for name, c, sp, n_iter, n_ens in REAL_WIDTH_CASES:
+        x, w, b, y, att = real_width_inputs(name, c, sp)
+        its = tuple(range(min(5, n_iter)))
+        r = run_ref_layer(R, x, w, b, y, 1, 1, 16, 16, True, [att], state_iters=its, n_iter=n_iter)
+        res[f"{name}_sums"] = np.array([x.double().sum().item(), w.double().sum().item(), y.double().sum().item(),
+                                        att.double().sum().item()])
+        res[f"{name}_hist"], res[f"{name}_final"] = r["hist"], r["final"]
+        res[f"{name}_alpha_w"], res[f"{name}_alpha_act"] = r["alpha_w"], r["alpha_act"]
+        res[f"{name}_n_iter"] = np.int64(n_iter)
+        for i in its:
+            res[f"{name}_st{i}_a_w"], res[f"{name}_st{i}_loss"] = r[f"st{i}_a_w"], r[f"st{i}_loss"]
+        res[f"{name}_st0_wstar_sub"] = r["st0_wstar"].reshape(-1)[::101].copy()
+        res[f"{name}_st0_wstar_absmax"] = np.float64(np.abs(r["st0_wstar"]).max())
+        res[f"{name}_st0_bstar"] = r["st0_bstar"]
+        res[f"{name}_st0_codes_next_sub"] = r["st0_codes_next"].reshape(-1)[::101].copy()
+        print(name, "final", r["final"], "alpha_w", r["alpha_w"], "alpha_act", r["alpha_act"], "hist[:5]", r["hist"][:5])
+        ens = [[float(r["final"]), float(r["hist"].min()), float(r["alpha_w"])]]
+        for k in range(n_ens):
+            xk, wk, bk, yk, attk = real_width_inputs(name, c, sp, perturb=k)
+            rk = run_ref_layer(R, xk, wk, bk, y, 1, 1, 16, 16, True, [attk], n_iter=n_iter)
+            ens.append([float(rk["final"]), float(rk["hist"].min()), float(rk["alpha_w"])])
+            print(name, "ensemble", k, ens[-1])
+        res[f"{name}_ens"] = np.array(ens)
+    for k, v in meta().items():
+        res["meta_" + k] = np.array(str(v))
+    np.savez_compressed(os.path.join(out, "real_width.npz"), **res)
 
 
 TOY = dict(num_mod=4, num_classes=3, depth=[1, 1, 1], width=[8, 16, 8], dilation=[1, 1, 1],
@@ -278,23 +414,26 @@ def seeded_state(model, seed):
     return sd
 
 
-def gen_toy_net(R, out, cfg=TOY, fname="toy_net.npz"):
-    """The do_ptq core (reference src/ptqer.py:289-364) on a toy UResQ, CPU."""
+def ref_toy_run(R, cfg, sd, perturb_seed=None, trace=None):
+    """The do_ptq core (reference src/ptqer.py:289-364) on a toy UResQ, CPU.  ``perturb_seed``: multiply the
+    calibration volumes by (1 + 1e-7 * N(0,1)) -- the ensemble member of the reference's own sensitivity study."""
     from efficientq_b200 import synth
     ptqer = R["ptqer"]
     model = build_toy(R, R["effq"].EfficientQConv, cfg)
-    sd = seeded_state(model, cfg["seed"])
     model.load_state_dict(sd, strict=False)
     model.eval()
     R["fold_bn"].search_fold_and_remove_bn(model)
     size = cfg["size"] if isinstance(cfg["size"], tuple) else (cfg["size"],) * 3
     data = synth.batch(cfg["n"], 0, cfg["num_mod"], size, cfg["task"])
+    if perturb_seed is not None:
+        gp = torch.Generator().manual_seed(1000 + perturb_seed)
+        data = data * (1.0 + 1e-7 * torch.randn(data.shape, generator=gp))
     ptqer.set_name(model)
     ptqer.set_fp(model)
     handles = []
     for m in model.modules():
         if isinstance(m, R["ptqconv"].PTQConv):
-            handles.append(m.register_forward_hook(R["hooks"].forward_hook))
+            handles.append(m.register_forward_hook(copying_hook))
     with torch.no_grad():
         output_fp = model(data).detach()
     task = cfg["task"]
@@ -310,14 +449,51 @@ def gen_toy_net(R, out, cfg=TOY, fname="toy_net.npz"):
     ptqer.set_anything(model, "layer_loss", layer_loss)
     ptqer.set_quantizing(model)
     with torch.no_grad():
-        output_q = model(data)
+        if trace is not None:
+            with trace:
+                output_q = model(data)
+        else:
+            output_q = model(data)
     ptqer.set_quantized(model)
-    res = {f"sd::{k}": v.numpy() for k, v in sd.items()}
     names, losses = [], []
     for line in layer_loss:
         nm, val = line.rsplit(":", 1)
         names.append(nm.strip())
         losses.append(float(val))
+    return dict(model=model, data=data, output_fp=output_fp, output_q=output_q, names=names, losses=losses,
+                nums=nums, wmap=wmap, pyr=pyr)
+
+
+ENSEMBLE = 8      # reference runs under a 1e-7 relative perturbation of the calibration volumes (+ one 1-thread run)
+
+
+def ref_ensemble(R, cfg, sd, extra=None):
+    """Per-layer losses of ENSEMBLE perturbed reference runs and of one single-threaded run of the unperturbed
+    problem: how far the reference moves against ITSELF (the ADMM trajectory is chaotic in the last bits)."""
+    rows = []
+    for k in range(ENSEMBLE):
+        r = ref_toy_run(R, cfg, sd, perturb_seed=k)
+        rows.append(r["losses"] + ([extra(r)] if extra else []))
+        print("ensemble", k, " ".join(f"{v:.4e}" for v in rows[-1]))
+    nthr = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        r = ref_toy_run(R, cfg, sd)
+        rows.append(r["losses"] + ([extra(r)] if extra else []))
+    finally:
+        torch.set_num_threads(nthr)
+    print("1 thread  ", " ".join(f"{v:.4e}" for v in rows[-1]))
+    return np.array(rows, dtype=np.float64)
+
+
+def gen_toy_net(R, out, cfg=TOY, fname="toy_net.npz"):
+    model0 = build_toy(R, R["effq"].EfficientQConv, cfg)
+    sd = seeded_state(model0, cfg["seed"])
+    trace = PtqTrace(R, state_iters=(), keep_inputs=True)
+    run = ref_toy_run(R, cfg, sd, trace=trace)
+    model, data, output_fp, output_q, pyr = run["model"], run["data"], run["output_fp"], run["output_q"], run["pyr"]
+    names, losses, nums, wmap = run["names"], run["losses"], run["nums"], run["wmap"]
+    res = {f"sd::{k}": v.numpy() for k, v in sd.items()}
     res["layer_names"] = np.array(names)
     res["layer_losses"] = np.array(losses, dtype=np.float64)
     res["class_nums"] = np.array(nums, dtype=np.int64)
@@ -331,13 +507,59 @@ def gen_toy_net(R, out, cfg=TOY, fname="toy_net.npz"):
         if isinstance(m, R["ptqconv"].PTQConv):
             res[f"q::{name}.alpha_w"] = np.float32(m.alpha_w.item())
             res[f"q::{name}.alpha_act"] = np.float32(m.alpha_act.item())
-    ptqer.store_int_weight(model)
+    # first conv's FP target: pre-activation (copying hook), so it must have negative entries
+    res["conv0_target_min"] = np.float64(min(float(l["y"].min()) for l in trace.layers[:1]))
+    R["ptqer"].store_int_weight(model)
     for name, m in model.named_modules():
         if isinstance(m, R["ptqconv"].PTQConv):
             res[f"q::{name}.wint"] = m.weight.data.numpy()
     for k, v in zip(names, losses):
         print(f"{k:45s} {v:.6e}")
+    res["ensemble_losses"] = ref_ensemble(R, cfg, sd)
     np.savez_compressed(os.path.join(out, fname), **res)
+    # teacher-forced fixture: what every layer of the REFERENCE run produced (calibrated fake-quant weights, bias,
+    # scales, 200-iterate loss history, final loss).  A test rebuilds each layer's input by running the reference's
+    # calibrated prefix (these weights) in deployment mode, so the 16 MB of per-layer inputs need not be stored; the
+    # exact inputs of the small (<= 2^17 elements) layers ARE stored to check that replay.  ``tf_ens``: the reference
+    # re-calibrating the SAME layer from its own input perturbed by 1e-7 (and single-threaded) -- its own per-layer
+    # sensitivity, which bounds how tight a per-layer bar can be.
+    tf = {"layer_names": np.array(names)}
+    for lv, p in enumerate(pyr):
+        assert float(p.max()) <= 65535 and bool((p == p.round()).all())
+        tf[f"pyr{lv}"] = p.numpy().astype(np.uint16)
+    gp = torch.Generator().manual_seed(4242)
+    for rec in trace.layers:
+        nm = rec["name"]
+        mod = dict(model.named_modules())[nm]
+        if rec["x"].numel() <= 2 ** 17:
+            tf[f"x::{nm}"] = rec["x"].numpy()
+        tf[f"x_sum::{nm}"] = np.float64(rec["x"].double().sum().item())
+        tf[f"y_sum::{nm}"] = np.float64(rec["y"].double().sum().item())
+        tf[f"weight::{nm}"], tf[f"bias::{nm}"] = rec["weight"].numpy(), rec["bias"].numpy()
+        tf[f"att_level::{nm}"] = np.int64(rec["att_level"])
+        tf[f"hist::{nm}"] = np.array(rec["hist"], dtype=np.float64)
+        tf[f"final::{nm}"] = np.float64(rec["final"])
+        tf[f"alpha_w::{nm}"], tf[f"alpha_act::{nm}"] = np.float32(rec["alpha_w"]), np.float32(rec["alpha_act"])
+        ens = []
+        for k in range(TF_ENSEMBLE + 1):
+            xk = rec["x"] * (1.0 + 1e-7 * torch.randn(rec["x"].shape, generator=gp)) if k < TF_ENSEMBLE else rec["x"]
+            nthr = torch.get_num_threads()
+            if k == TF_ENSEMBLE:
+                torch.set_num_threads(1)
+            try:
+                r = run_ref_layer(R, xk, rec["w0"], rec["b0"], rec["y"], mod.stride, mod.padding, mod.qlvl_w,
+                                  mod.qlvl_act, mod.q_act, pyr)
+            finally:
+                torch.set_num_threads(nthr)
+            ens.append([float(r["final"]), float(r["hist"].min()), float(r["alpha_w"])])
+        tf[f"tf_ens::{nm}"] = np.array(ens, dtype=np.float64)
+        e = tf[f"tf_ens::{nm}"]
+        print(f"TF {nm:45s} ref final {rec['final']:.6e}  ensemble spread final {np.ptp(e[:, 0]) / rec['final']:.2e} "
+              f"best {np.ptp(e[:, 1]) / min(rec['hist']):.2e} alpha_w {np.ptp(e[:, 2]) / rec['alpha_w']:.2e}")
+    np.savez_compressed(os.path.join(out, fname.replace(".npz", "_tf.npz")), **tf)
+
+
+TF_ENSEMBLE = 4
 
 
 def gen_toy_tune(R, out, n_tune=3):
@@ -355,7 +577,7 @@ def gen_toy_tune(R, out, n_tune=3):
     data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
     ptqer.set_name(model)
     ptqer.set_fp(model)
-    handles = [m.register_forward_hook(R["hooks"].forward_hook) for m in model.modules()
+    handles = [m.register_forward_hook(copying_hook) for m in model.modules()
                if isinstance(m, R["ptqconv"].PTQConv)]
     with torch.no_grad():
         output_fp = model(data).detach()
@@ -458,37 +680,39 @@ def gen_toy_dice(R, out, steps=160):
             print("train step", step, float(loss))
     model.eval()
     trained = {k: v.detach().clone() for k, v in model.state_dict().items() if not k.endswith(("alpha_act", "alpha_w"))}
-    R["fold_bn"].search_fold_and_remove_bn(model)
     ev = [synth.volume(100 + i, cfg["num_mod"], (cfg["size"],) * 3, "brats") for i in range(4)]
     ev_x = torch.stack([v[0] for v in ev])
     ev_l = torch.stack([v[1] for v in ev]).long()
-    metrics = R["ptqer"].metrics if hasattr(R["ptqer"], "metrics") else None
     from utils import metrics as M_                                            # reference's get_pred_brats
-    with torch.no_grad():
-        dice_fp = dice_table(M_.get_pred_brats(model(ev_x)[-1]), ev_l)
-    data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"])
-    ptqer.set_name(model)
-    handles = [m.register_forward_hook(R["hooks"].forward_hook) for m in model.modules()
-               if isinstance(m, R["ptqconv"].PTQConv)]
-    with torch.no_grad():
-        output_fp = model(data).detach()
-    body = (data[:, 0] != 0.0).bool()
-    wmap, _ = ptqer.get_att_weight_map(output_fp, torch.ones_like(data[:, 0]).bool(), "p:0.5", task="brats")
-    ptqer.set_mask(model, ptqer.get_mask_pyramid(output_fp, body, wmap, "2,2,2", num_lvls=5, task="brats"))
-    for h in handles:
-        h.remove()
-    layer_loss = []
-    ptqer.set_anything(model, "layer_loss", layer_loss)
-    ptqer.set_quantizing(model)
-    with torch.no_grad():
-        model(data)
-    ptqer.set_quantized(model)
-    with torch.no_grad():
-        dice_q = dice_table(M_.get_pred_brats(model(ev_x)[-1]), ev_l)
+
+    def dice_of(m):
+        with torch.no_grad():
+            return dice_table(M_.get_pred_brats(m(ev_x)[-1]), ev_l)
+    fp_model = build_toy(R, R["effq"].EfficientQConv, cfg)
+    fp_model.load_state_dict(trained, strict=False)
+    fp_model.eval()
+    R["fold_bn"].search_fold_and_remove_bn(fp_model)
+    ptqer.set_fp(fp_model)
+    dice_fp = dice_of(fp_model)
+    run = ref_toy_run(R, cfg, trained)
+    dice_q = dice_of(run["model"])
     res = {f"sd::{k}": v.numpy() for k, v in trained.items()}
     res["dice_fp"], res["dice_q"] = np.array(dice_fp), np.array(dice_q)
-    res["layer_losses"] = np.array([float(ln.rsplit(":", 1)[1]) for ln in layer_loss])
+    res["layer_losses"] = np.array(run["losses"])
     print("Dice FP", dice_fp, "mean", np.mean(dice_fp), "| Dice W4A4 (reference)", dice_q, "mean", np.mean(dice_q))
+    # the reference against itself: ENSEMBLE calibrations from volumes perturbed by 1e-7 + one single-threaded run
+    rows = []
+    for k in range(ENSEMBLE + 1):
+        nthr = torch.get_num_threads()
+        if k == ENSEMBLE:
+            torch.set_num_threads(1)
+        try:
+            r = ref_toy_run(R, cfg, trained, perturb_seed=k if k < ENSEMBLE else None)
+            rows.append(dice_of(r["model"]))
+        finally:
+            torch.set_num_threads(nthr)
+        print("dice ensemble", k, rows[-1], "mean", np.mean(rows[-1]))
+    res["dice_q_ensemble"] = np.array(rows, dtype=np.float64)
     np.savez_compressed(os.path.join(out, "toy_dice.npz"), **res)
 
 
@@ -672,7 +896,7 @@ def main():
     torch.manual_seed(0)
     R = import_reference(args.ref)
     gens = dict(discretize=gen_discretize, fakequant_module=gen_fakequant_module, project=gen_project,
-                solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, toy_net=gen_toy_net,
+                solver=gen_solver, layers=gen_layers, layers_wide=gen_layers_wide, real_width=gen_real_width, toy_net=gen_toy_net,
                 toy_net_lits=gen_toy_net_lits, toy_tune=gen_toy_tune, toy_dice=gen_toy_dice, eval=gen_eval, calib_data=gen_calib_data, interface=gen_interface)
     for name, fn in gens.items():
         if args.only and name not in args.only.split(","):

@@ -508,6 +508,107 @@ def test_admm_elementwise_kernels(ops):
     assert hist.cpu().tolist() == [5.0, 7.0, 5.0, 3.0]
 
 
+def test_project_keep_and_decide_equal_track(ops):
+    """The loop's fused form -- effq_admm_decide (or the tail of effq_quadform_delta) scores, the NEXT
+    effq_admm_project saves the best iterate before overwriting it, effq_admm_keep flushes the last one -- must
+    leave the same best iterate, codes, history and state as effq_admm_track after every iterate."""
+    torch.manual_seed(31)
+    c2, c1, taps = 16, 16, 27
+    k = c1 * taps
+    dev = torch.device(DEV)
+    losses = [5.0, 7.0, 4.0, 4.0, 3.0, 6.0]
+
+    def run(fused):
+        wst, xst, st = ops.ScaleState(dev), ops.ScaleState(dev), ops.AdmmState(dev)
+        xst.set_a(2.5)
+        g, bstar = torch.zeros(c2, k, device=DEV), torch.zeros(c2, device=DEV)
+        wcodes = torch.zeros(taps * c1 * c2, dtype=torch.bfloat16, device=DEV)
+        best_g, best_b, best_w = torch.zeros_like(g), torch.zeros_like(bstar), torch.zeros_like(wcodes)
+        dual = torch.zeros(c2, k, device=DEV)
+        hist = torch.zeros(len(losses), device=DEV)
+        sse = torch.zeros(1, dtype=torch.float64, device=DEV)
+        gen = torch.Generator().manual_seed(5)
+        snaps = []
+        for it, val in enumerate(losses):
+            sol = (torch.randn(c2, k + 1, generator=gen) * 0.1).to(DEV)
+            ops.scale_search(sol[:, :k], 16, -1.0, 1.0, wst, v2=dual)
+            ops.admm_project(sol, dual, wst, xst, 16, 16, c2, c1, taps, True, 1.0, g, bstar, wcodes, st,
+                             keep=(best_g, best_b, best_w) if fused else None)
+            sse.fill_(val * 100)
+            if fused:
+                ops.admm_decide(st, sse, 100.0, hist)
+            else:
+                ops.admm_track(st, sse, 100.0, g, bstar, best_g, best_b, hist, wcodes, best_w)
+            snaps.append((g.clone(), bstar.clone(), wcodes.clone()))
+        if fused:
+            ops.admm_keep(st, g, bstar, best_g, best_b, wcodes, best_w)
+        return best_g, best_b, best_w, hist, st.read(), snaps
+    bg1, bb1, bw1, h1, s1, snaps = run(True)
+    bg0, bb0, bw0, h0, s0, _ = run(False)
+    assert s1["best_iter"] == s0["best_iter"] == 4 and s1["iter"] == s0["iter"] == len(losses)
+    assert s1["best_conv_scale"] == s0["best_conv_scale"] and s1["best_loss"] == s0["best_loss"]
+    assert torch.equal(h1, h0)
+    assert torch.equal(bg1, bg0) and torch.equal(bb1, bb0) and torch.equal(bw1, bw0)
+    assert torch.equal(bg1, snaps[4][0]) and torch.equal(bb1, snaps[4][1]) and torch.equal(bw1, snaps[4][2])
+
+
+@pytest.mark.parametrize("n,c1,c2,sp", [(2, 32, 32, (6, 16, 8)), (1, 64, 64, (4, 8, 16)), (1, 16, 24, (5, 10, 12))])
+def test_quadform_delta_equals_conv_sse(ops, n, c1, c2, sp):
+    """Residual-form conv-free scoring of a QUANTISED layer: statistics of R = Y - conv(first iterate) from the
+    tcgen05 Gram kernel (integer codes, att = None) + the tiled fp64 quadratic form must reproduce the squared
+    error of later iterates (fp64 conv on the CPU) to ~1e-6, and the fused bookkeeping must equal admm_decide's."""
+    torch.manual_seed(c1 + c2)
+    la = 16
+    codes = torch.randint(0, la, (n, c1, *sp)).float()
+    sc = 0.173
+    x = codes * sc
+    w_true = torch.randn(c2, c1, 3, 3, 3) * (2.0 / (27 * c1)) ** 0.5
+    b_true = torch.randn(c2) * 0.05
+    y = F.conv3d(x, w_true, b_true, 1, 1)
+    g_ref = w_true + 0.02 * w_true.std() * torch.randn_like(w_true)      # "first iterate"
+    b_ref = b_true + 0.01 * torch.randn_like(b_true)
+    r = (y.double() - F.conv3d(x.double(), g_ref.double(), b_ref.double(), 1, 1)).float()
+    xq = codes.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+    acc, _, flag = ops.gram_tc_f64(xq, torch.tensor([sc], device=DEV), r.to(DEV), None, True, att_exact=True)
+    assert int(flag.item()) == 0
+    # S against the fp64 im2col Gram: the integer part is exact
+    cols = O.im2col(x, 3, 3, 3, 1, 1).double()
+    cols = torch.cat([cols, torch.ones(1, cols.shape[1], dtype=torch.float64)], 0)
+    kp = cols.shape[0]
+    s_ref = cols @ cols.T
+    assert (acc[:kp].cpu() - s_ref).abs().max().item() <= 1e-9 * s_ref.abs().max().item()
+    t_ref = r.permute(1, 0, 2, 3, 4).reshape(c2, -1).double() @ cols.T
+    assert (acc[kp:].cpu() - t_ref).abs().max().item() <= 2e-5 * t_ref.abs().max().item()
+    yy = torch.tensor([(r.double() ** 2).sum().item()], dtype=torch.float64, device=DEV)
+    sse = torch.zeros(1, dtype=torch.float64, device=DEV)
+    dev = torch.device(DEV)
+    st, st2 = ops.AdmmState(dev), ops.AdmmState(dev)
+    numel = float(y.numel())
+    hist, hist2 = torch.zeros(3, device=DEV), torch.zeros(3, device=DEV)
+    gd, bd = g_ref.reshape(c2, -1).contiguous().to(DEV), b_ref.to(DEV)
+    for i, eps in enumerate((2e-2, 5e-3, 1e-3)):
+        g = g_ref + eps * w_true.std() * torch.randn_like(g_ref)
+        b = b_ref + eps * 0.1 * torch.randn_like(b_ref)
+        ref = ((F.conv3d(x.double(), g.double(), b.double(), 1, 1) - y.double()) ** 2).sum().item()
+        ops.quadform_delta(acc, yy, g.reshape(c2, -1).contiguous().to(DEV), b.to(DEV), sse, gd, bd, st=st,
+                           numel=numel, history=hist)
+        got = sse.item()
+        print(f"c1={c1} eps={eps}: sse {got:.9e} fp64 conv {ref:.9e} rel {abs(got - ref) / ref:.1e}")
+        assert abs(got - ref) <= 3e-6 * ref, (got, ref)
+        ops.admm_decide(st2, sse, numel, hist2)
+        assert st.read() == st2.read()
+    assert torch.equal(hist, hist2)
+    # plain form (g_ref = None) on the statistics of y itself == the old single-CTA kernel
+    acc_y, _, _ = ops.gram_tc_f64(xq, torch.tensor([sc], device=DEV), y.to(DEV), None, True, att_exact=True)
+    yy_y = torch.tensor([(y.double() ** 2).sum().item()], dtype=torch.float64, device=DEV)
+    g = g_ref.reshape(c2, -1).contiguous().to(DEV)
+    ops.quadform_delta(acc_y, yy_y, g, bd, sse)
+    ws = ops.workspace(16 + 8 * 1024, dev)
+    sse_old = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.quadform_sse(acc_y, float(yy_y.item()), g, bd, sse_old, ws)
+    assert abs(sse.item() - sse_old.item()) <= 1e-9 * abs(sse_old.item()) + 1e-9 * float(yy_y.item())
+
+
 # ---------------------------------------------------------------- proximal-step GEMM (a9)
 def test_split3_bf16_is_exact(ops):
     torch.manual_seed(21)

@@ -99,6 +99,32 @@ def test_layer_calibration_e4m3_equals_bf16(engine_mod, golden, name, monkeypatc
     assert float(aw1) == float(aw0) and float(aa1) == float(aa0)
 
 
+@pytest.mark.parametrize("name", ["w4a4_k3_c32", "w2a4_k3_c64", "w4a4_k3"])
+def test_conv_free_scoring_matches_conv_scoring(engine_mod, golden, name, monkeypatch):
+    """Quantised 3x3x3 layers score iterates 1..199 from the residual statistics (csrc/quadform.cu) instead of a
+    conv per iterate: the loss history must agree with the conv-scored run to fp32-loss accuracy and the same
+    iterate must win (so weights, scales and the final loss are identical)."""
+    g = golden("layers_wide.npz" if name in WIDE else "layers.npz")
+    k, s, p, lw, la, qa = [int(t) for t in g[f"{name}_cfg"]]
+    x, w, b, y, att = [torch.from_numpy(g[f"{name}_{t}"]).to(DEV) for t in ("x", "w", "b", "y", "att")]
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("EFFQ_QF", flag)
+        eng = engine_mod.LayerCalibrator(torch.device(DEV), keep_history=True)
+        res[flag] = eng.run(x, w, b, y, s, p, lw, la, bool(qa), [att], name=name)
+    (wq1, bq1, aw1, _, o1, r1), (wq0, bq0, aw0, _, o0, r0) = res["1"], res["0"]
+    h1, h0 = np.array(r1.history), np.array(r0.history)
+    rel = np.abs(h1 - h0) / h0
+    print(name, "max rel diff of the loss history", rel.max(), "best iter", r1.best_iter, r0.best_iter)
+    assert h1[0] == h0[0]                              # iterate 0 is conv-scored in both
+    assert rel.max() <= 2e-6
+    assert r1.best_iter == r0.best_iter or abs(h0[r1.best_iter] - h0[r0.best_iter]) <= 2e-6 * h0.min()
+    if r1.best_iter == r0.best_iter:
+        assert torch.equal(wq1, wq0) and torch.equal(bq1, bq0) and torch.equal(o1, o0)
+        assert r1.final_loss == r0.final_loss
+    assert float(aw1) == float(aw0)
+
+
 def build_toy(task="brats"):
     from efficientq_b200 import model_blk, qconv
     from tests.golden.make_golden import TOY, TOY_LITS
@@ -142,24 +168,21 @@ def test_toy_network_matches_reference(engine_mod, golden, task):
     if os.path.isdir("gpurun_out"):
         with open("gpurun_out/toy_net_parity.txt" if task == "brats" else "gpurun_out/toy_net_lits_parity.txt", "w") as fid:
             fid.write("\n".join(lines) + f"\nt_fp {res['t_fp']:.3f}s t_ptq {res['t_ptq']:.3f}s\n")
-    # layer 1 sees identical inputs -> 1e-3; later layers inherit the (chaotic) quantised
-    # prefix, tolerance documented in DESIGN.md
+    # Each layer calibrates on the output of the already-quantised prefix, and the ADMM trajectory amplifies
+    # last-bit differences, so differences compound through the network (per-layer parity WITHOUT the compounding
+    # is tests/test_gpu_parity.py::test_teacher_forced_layer_parity, at 1e-3).  Here the bar is the reference
+    # against ITSELF: 8 reference runs from volumes perturbed by 1e-7 and one single-threaded run
+    # (``ensemble_losses``); the GPU result must lie within the ensemble's range widened by one range on either
+    # side (a ninth sample of the same distribution falls outside the bare range of eight 2 times out of 9),
+    # and within 1e-3 wherever the reference does not move at all.
+    ens = np.concatenate([g["ensemble_losses"], ref[None]], 0)
+    lo, hi = ens.min(0), ens.max(0)
+    width = hi - lo
+    ok = (losses >= lo - width - 1e-3 * ref) & (losses <= hi + width + 1e-3 * ref)
+    for nm, a, l_, h_, o in zip(names, losses, lo, hi, ok):
+        print(f"{nm:45s} ours {a:.6e} reference ensemble [{l_:.6e}, {h_:.6e}] {'ok' if o else 'OUTSIDE'}")
     assert abs(losses[0] - ref[0]) <= 1e-3 * ref[0]
-    # Each layer calibrates on the output of the already-quantised prefix and the ADMM trajectory amplifies
-    # last-bit differences (the reference itself moves by several percent between a 1-thread and an 8-thread CPU
-    # run), so the deep layers get a wide bar; layers 1-3 see (nearly) identical problems and stay tight.
-    # Whether two GPU runs agree bit for bit is measured by tools/repro_check.py.
-    if task == "brats":
-        np.testing.assert_allclose(losses[:3], ref[:3], rtol=5e-3)
-        np.testing.assert_allclose(losses[3:], ref[3:], rtol=1e-1)
-    else:
-        # W2A2: 4-level codes make the trajectory far more sensitive to one flipped code.  The REFERENCE run
-        # with 1 CPU thread instead of 8 reproduces layers 1-4 to 8e-6 and then moves by 5.7e-3, 8.1e-3,
-        # 4.5e-3, 3.9e-3, 2.7e-2, 6.5e-2 on layers 5-10 (profiles/r01_parity.txt, "LiTS miniature").
-        # Bars: layers 1-4 tight, 5-6 at 2e-2, the rest at 0.5 (observed on the GPU: 0.18 and 0.22 on final_cls in two runs).
-        np.testing.assert_allclose(losses[:4], ref[:4], rtol=1e-4)
-        np.testing.assert_allclose(losses[4:6], ref[4:6], rtol=2e-2)
-        np.testing.assert_allclose(losses[6:], ref[6:], rtol=0.5)
+    assert ok.all(), [n for n, o in zip(names, ok) if not o]
 
 
 @pytest.mark.parametrize("c1,c2,k", [(32, 32, 3), (64, 32, 1), (16, 48, 3)])
@@ -243,7 +266,7 @@ def test_final_dice_on_trained_miniature(engine_mod, golden):
     nested-sphere volumes (tests/golden/make_golden.py::gen_toy_dice), calibrated at W4A4 on 2 volumes, Dice of
     the quantised model on 4 held-out volumes (deployment forward on the tcgen05 code path).  The REFERENCE's own
     quantised Dice moves by 0.7 points (foreground mean) / 2.0 points (class 3) between a 1-thread and an 8-thread
-    CPU run from the same trained state (profiles/r01_parity.txt), so the bars are 1.5 / 3 points (measured: 0.31 / 0.94; GPU runs are bit-reproducible, profiles/r01_repro_check.txt); the FP Dice
+    CPU run from the same trained state, so the bar is the reference's own ensemble (below); the FP Dice
     (no calibration involved) must agree to 0.01 points."""
     from efficientq_b200 import fold_bn, ptqer, synth
     from tests.golden.make_golden import dice_table
@@ -273,6 +296,13 @@ def test_final_dice_on_trained_miniature(engine_mod, golden):
     import os
     if os.path.isdir("gpurun_out"):
         open("gpurun_out/toy_dice_parity.txt", "w").write(line + "\n")
-    assert abs(np.mean(dice_q) - np.mean(g["dice_q"])) <= 0.015
-    np.testing.assert_allclose(dice_q, g["dice_q"], atol=0.03)
+    # the reference against itself (8 perturbed runs + 1 single-threaded, tests/golden/make_golden.py::gen_toy_dice):
+    # ours must lie in the ensemble's range widened by one range on either side, per class and for the mean
+    ens = np.concatenate([g["dice_q_ensemble"], g["dice_q"][None]], 0)
+    ens = np.concatenate([ens, ens.mean(1, keepdims=True)], 1)
+    ours = np.array(list(dice_q) + [np.mean(dice_q)])
+    lo, hi = ens.min(0), ens.max(0)
+    width = hi - lo
+    print("reference ensemble Dice range", np.round(lo, 4).tolist(), np.round(hi, 4).tolist())
+    assert ((ours >= lo - width - 1e-3) & (ours <= hi + width + 1e-3)).all(), (ours, lo, hi)
     np.testing.assert_allclose([float(ln.rsplit(":", 1)[1]) for ln in res["layer_loss"]][:1], g["layer_losses"][:1], rtol=1e-3)

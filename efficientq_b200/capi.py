@@ -117,6 +117,14 @@ _SIGS = {
     "effq_solve_gemm_tc_workspace": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "effq_solve_gemm_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p]),
+    "effq_gemm_tc_ex_workspace": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "effq_gemm_tc_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                  C.c_void_p, C.c_void_p]),
+    "effq_potrf_tile": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_int32, C.c_void_p]),
+    "effq_split3_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_int32, C.c_int32, C.c_void_p]),
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,

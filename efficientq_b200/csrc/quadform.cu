@@ -70,19 +70,40 @@ quadform_delta_kernel(QfArgs a) {
   const int ti = t % 16, tr = t / 16;            // thread tile: rows i0 + ti + 16 q (q < 4) x channels r0 + 2 tr, +1
   double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
   double lin = 0.0;                              // u.T share of channel r0 + t (threads t < 32 of row tile 0)
-  for (int j0 = j_begin; j0 < j_end; j0 += QF_TJ) {
-    // stage S[i0..i0+63][j0..j0+15] (j contiguous in memory) and u[r0..r0+31][j0..j0+15]
-    for (int e = t; e < QF_TI * QF_TJ; e += QF_THREADS) {
+  // register prefetch of the next j step (4 S values + 2 u values per thread) hides the L2 latency behind the
+  // 128 FMAs of the current one
+  double s_pre[4], u_pre[2];
+  auto fetch = [&](int j0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = t + q * QF_THREADS;
       const int ii = e / QF_TJ, jj = e % QF_TJ;
       const int i = i0 + ii, j = j0 + jj;
-      Ss[jj][ii] = (i < a.kp && j < j_end) ? __ldg(a.acc + (long long)i * a.kp + j) : 0.0;
+      s_pre[q] = (i < a.kp && j < j_end) ? __ldg(a.acc + (long long)i * a.kp + j) : 0.0;
     }
-    for (int e = t; e < QF_TR * QF_TJ; e += QF_THREADS) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = t + q * QF_THREADS;
       const int rr = e / QF_TJ, jj = e % QF_TJ;
       const int j = j0 + jj;
-      Us[jj][rr] = j < j_end ? qf_u(a, r0 + rr, j) : 0.0;
+      u_pre[q] = j < j_end ? qf_u(a, r0 + rr, j) : 0.0;
+    }
+  };
+  if (j_begin < j_end) fetch(j_begin);
+  for (int j0 = j_begin; j0 < j_end; j0 += QF_TJ) {
+    // stage S[i0..i0+63][j0..j0+15] (j contiguous in memory) and u[r0..r0+31][j0..j0+15]
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = t + q * QF_THREADS;
+      Ss[e % QF_TJ][e / QF_TJ] = s_pre[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = t + q * QF_THREADS;
+      Us[e % QF_TJ][e / QF_TJ] = u_pre[q];
     }
     __syncthreads();
+    if (j0 + QF_TJ < j_end) fetch(j0 + QF_TJ);
 #pragma unroll
     for (int jj = 0; jj < QF_TJ; ++jj) {
       const double u0 = Us[jj][tr * 2], u1 = Us[jj][tr * 2 + 1];
@@ -198,9 +219,10 @@ extern "C" int effq_quadform_delta(const double* acc64, const double* sum_sq, co
   a.c2 = c2; a.k = k; a.kp = k + (has_bias ? 1 : 0);
   a.n_it = (a.kp + QF_TI - 1) / QF_TI;
   a.n_rt = (c2 + QF_TR - 1) / QF_TR;
-  // split the j range so that about two waves of CTAs exist, in whole QF_TJ steps
+  // split the j range so that every SM holds ~8 CTAs (latency hiding: a CTA is a chain of dependent L2 loads),
+  // in whole QF_TJ steps
   const int base = a.n_it * a.n_rt;
-  int n_js = (2 * sm_count() + base - 1) / base;
+  int n_js = (8 * sm_count() + base - 1) / base;
   const int max_js = (a.kp + QF_TJ - 1) / QF_TJ;
   if (n_js > max_js) n_js = max_js;
   if (n_js < 1) n_js = 1;

@@ -43,6 +43,12 @@ struct SgParams {
   int m, n, k, ldo;
   int ksteps, splits;
   unsigned int* abort_flag;
+  // general form (effq_gemm_tc_ex): result = alpha * A B^T + beta * c_in, applied here when splits == 1 and in the
+  // fold pass otherwise; lower_only skips the tiles strictly above the diagonal (symmetric updates)
+  const float* c_in;
+  long long ldc;
+  float alpha, beta;
+  int lower_only;
 };
 
 __global__ void __launch_bounds__(SG_THREADS, 1)
@@ -59,6 +65,7 @@ solve_gemm_tc_kernel(const SgParams p, const __grid_constant__ CUtensorMap amap,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   volatile unsigned int* abort_flag = p.abort_flag;
   const int n0 = blockIdx.x * SG_BN, m0 = blockIdx.y * SG_BM;
+  if (p.lower_only && n0 > m0 + SG_BM - 1) return;               // whole CTA, before any barrier / TMEM allocation
   const int ks_begin = (int)(((long long)p.ksteps * blockIdx.z) / p.splits);
   const int ks_end = (int)(((long long)p.ksteps * (blockIdx.z + 1)) / p.splits);
 
@@ -136,7 +143,7 @@ solve_gemm_tc_kernel(const SgParams p, const __grid_constant__ CUtensorMap amap,
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     float* orow = p.out + ((long long)blockIdx.z * p.m + row) * p.ldo + n0;
-    const bool vec = (p.ldo & 3) == 0;
+    const bool vec = (p.ldo & 3) == 0 && ((uintptr_t)p.out & 15) == 0;
     if (ks_end > ks_begin) {
       if (mbar_wait<64>(BAR(B_ACC), 0, abort_flag)) {
         tc_fence_after();
@@ -152,6 +159,15 @@ solve_gemm_tc_kernel(const SgParams p, const __grid_constant__ CUtensorMap amap,
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          }
+          if (row < p.m && p.splits == 1 && (p.c_in != nullptr || p.alpha != 1.f)) {
+            const float* crow = p.c_in ? p.c_in + (long long)row * p.ldc + n0 + c0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float r = p.alpha * __uint_as_float(v[j]);
+              if (crow && n0 + c0 + j < p.n) r = fmaf(p.beta, crow[j], r);
+              v[j] = __float_as_uint(r);
+            }
           }
           if (row < p.m) {
 #pragma unroll
@@ -185,13 +201,18 @@ solve_gemm_tc_kernel(const SgParams p, const __grid_constant__ CUtensorMap amap,
 
 // deterministic split-K fold: out[r][c] = sum_s partial[s][r][c] in index order
 __global__ void __launch_bounds__(256)
-solve_gemm_fold_kernel(const float* __restrict__ partial, int splits, int m, int n, int ldo, float* __restrict__ out) {
+solve_gemm_fold_kernel(const float* __restrict__ partial, int splits, int m, int n, int ldp, float* out, long long ldo,
+                       float alpha, float beta, const float* c_in, long long ldc) {
   const long long total = (long long)m * n;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     const int r = (int)(e / n), c = (int)(e % n);
-    const long long o = (long long)r * ldo + c;
-    float acc = partial[o];
-    for (int s = 1; s < splits; ++s) acc += partial[(long long)s * m * ldo + o];
+    const long long o = (long long)r * ldo + c, q = (long long)r * ldp + c;
+    float acc = partial[q];
+    for (int s = 1; s < splits; ++s) acc += partial[(long long)s * m * ldp + q];
+    if (c_in != nullptr || alpha != 1.f) {
+      acc *= alpha;
+      if (c_in) acc = fmaf(beta, c_in[(long long)r * ldc + c], acc);
+    }
     out[o] = acc;
   }
 }
@@ -215,11 +236,12 @@ split3_kernel(const float* __restrict__ src, int rows, int cols, long long ld, _
   }
 }
 
-static int sg_make_map(const void* planes, int rows, int k, int ldk, CUtensorMap* map) {
+static int sg_make_map(const void* planes, int rows, int k, long long ldk, CUtensorMap* map, long long plane_stride = 0) {
   EncodeTiledFn encode = tc_encoder();
   if (!encode) return 2;
+  if (plane_stride == 0) plane_stride = (long long)rows * ldk;
   const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, 3};
-  const cuuint64_t strides[2] = {(cuuint64_t)ldk * 2, (cuuint64_t)rows * ldk * 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldk * 2, (cuuint64_t)plane_stride * 2};
   const cuuint32_t box[3] = {(cuuint32_t)SG_BK, (cuuint32_t)SG_BM, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
@@ -259,9 +281,43 @@ extern "C" int effq_split3_bf16(const float* src, int32_t rows, int32_t cols, in
 }
 
 extern "C" int64_t effq_solve_gemm_tc_workspace(int32_t m, int32_t n, int32_t k, int64_t ldo) {
+  (void)ldo;                                                    // partials are compact, independent of the output pitch
   const int s = effq::sg_splits(m, n, k);
-  return 16 + (s > 1 ? (int64_t)s * m * ldo * 4 : 0);
+  return 16 + (s > 1 ? (int64_t)s * m * ((n + 3) / 4 * 4) * 4 : 0);
 }
+
+namespace effq {
+static int sg_launch(const CUtensorMap& amap, const CUtensorMap& bmap, int m, int n, int k, float* out, long long ldo,
+                     void* workspace, float alpha, float beta, const float* c_in, long long ldc, int lower_only,
+                     cudaStream_t s) {
+  SgParams p;
+  p.m = m; p.n = n; p.k = k; p.ldo = (int)ldo;
+  p.ksteps = (k + SG_BK - 1) / SG_BK;
+  p.splits = sg_splits(m, n, k);
+  p.abort_flag = (unsigned int*)workspace;                     // word 0: abort flag (zero-initialised by the caller)
+  p.c_in = c_in; p.ldc = ldc; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only;
+  float* partial = (float*)((char*)workspace + 16);
+  const int ldp = (n + 3) / 4 * 4;                              // split-K partials are compact: [splits][m][ldp]
+  if (p.splits > 1) { p.out = partial; p.ldo = ldp; } else { p.out = out; }
+  const uint32_t smem = 1024 + SG_STAGES * SG_STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(solve_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const dim3 grid((n + SG_BN - 1) / SG_BN, (m + SG_BM - 1) / SG_BM, p.splits);
+  solve_gemm_tc_kernel<<<grid, SG_THREADS, smem, s>>>(p, amap, bmap);
+  EFFQ_LAUNCH_CHECK();
+  if (p.splits > 1) {
+    long long blocks = ((long long)m * n + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    solve_gemm_fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(partial, p.splits, m, n, ldp, out, ldo, alpha, beta, c_in, ldc);
+    EFFQ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+}  // namespace effq
 
 extern "C" int effq_solve_gemm_tc(const void* a_planes, const void* b_planes, int32_t m, int32_t n, int32_t k,
                                   float* out, int64_t ldo, void* workspace, void* stream) {
@@ -274,29 +330,28 @@ extern "C" int effq_solve_gemm_tc(const void* a_planes, const void* b_planes, in
   alignas(64) CUtensorMap amap, bmap;
   if (int rc = sg_make_map(a_planes, m, k, ldk, &amap)) return rc;
   if (int rc = sg_make_map(b_planes, n, k, ldk, &bmap)) return rc;
-  SgParams p;
-  p.m = m; p.n = n; p.k = k; p.ldo = (int)ldo;
-  p.ksteps = (k + SG_BK - 1) / SG_BK;
-  p.splits = sg_splits(m, n, k);
-  p.abort_flag = (unsigned int*)workspace;                     // word 0: abort flag (zero-initialised by the caller)
-  float* partial = (float*)((char*)workspace + 16);
-  p.out = p.splits > 1 ? partial : out;
-  const uint32_t smem = 1024 + SG_STAGES * SG_STAGE_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
-    EFFQ_CUDA(cudaFuncSetAttribute(solve_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  const dim3 grid((n + SG_BN - 1) / SG_BN, (m + SG_BM - 1) / SG_BM, p.splits);
-  solve_gemm_tc_kernel<<<grid, SG_THREADS, smem, s>>>(p, amap, bmap);
-  EFFQ_LAUNCH_CHECK();
-  if (p.splits > 1) {
-    long long blocks = ((long long)m * n + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    solve_gemm_fold_kernel<<<(unsigned)blocks, 256, 0, s>>>(partial, p.splits, m, n, (int)ldo, out);
-    EFFQ_LAUNCH_CHECK();
-  }
-  return 0;
+  return sg_launch(amap, bmap, m, n, k, out, ldo, workspace, 1.f, 0.f, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+// General form on SUB-BLOCKS of split-plane matrices:  out = alpha * A B^T + beta * c_in  with
+// A = rows x k block starting at a_planes (row pitch a_ld elements, planes a_plane_stride elements apart), B likewise
+// (n rows).  The building block of the blocked Cholesky factorisation and triangular inverse (csrc/chol_tc.cu).
+extern "C" int64_t effq_gemm_tc_ex_workspace(int32_t m, int32_t n, int32_t k, int64_t ldo) {
+  return effq_solve_gemm_tc_workspace(m, n, k, ldo);
+}
+extern "C" int effq_gemm_tc_ex(const void* a_planes, int64_t a_ld, int64_t a_plane_stride, const void* b_planes,
+                               int64_t b_ld, int64_t b_plane_stride, int32_t m, int32_t n, int32_t k, float alpha,
+                               float beta, const float* c_in, int64_t ldc, float* out, int64_t ldo,
+                               int32_t lower_only, void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(a_planes && b_planes && out && workspace, "null pointer");
+  EFFQ_CHECK_ARG(m > 0 && n > 0 && k > 0 && ldo >= n && (!c_in || ldc >= n), "bad shape");
+  EFFQ_CHECK_ARG(a_ld % 8 == 0 && b_ld % 8 == 0 && a_plane_stride % 8 == 0 && b_plane_stride % 8 == 0 && a_ld >= k &&
+                     b_ld >= k, "row pitch / plane stride must be multiples of 8 elements and cover k");
+  EFFQ_CHECK_ARG(((uintptr_t)a_planes & 15) == 0 && ((uintptr_t)b_planes & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+                 "operands must be 16B aligned");
+  alignas(64) CUtensorMap amap, bmap;
+  if (int rc = sg_make_map(a_planes, m, k, a_ld, &amap, a_plane_stride)) return rc;
+  if (int rc = sg_make_map(b_planes, n, k, b_ld, &bmap, b_plane_stride)) return rc;
+  return sg_launch(amap, bmap, m, n, k, out, ldo, workspace, alpha, beta, c_in, ldc, lower_only, (cudaStream_t)stream);
 }

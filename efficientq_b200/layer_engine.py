@@ -118,13 +118,23 @@ class LayerCalibrator:
         rep = rep or LayerReport()
         a_r = torch.empty_like(a0)
         ops.admm_lhs(a0, rho, eta, has_bias, a_r)
+        own = not self.force_generic and os.environ.get("EFFQ_SPD", "1") != "0"
+        inv_r = None
         if not fstate["use64"]:
-            chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
-                                       lambda: torch.linalg.cholesky_ex(a_r))
+            if own:
+                # blocked Cholesky + block triangular inverse + W^T W on the tensor cores (spd_inverse.py): no library
+                if self._spd is None:
+                    from .spd_inverse import SpdInverter
+                    self._spd = SpdInverter(dev)
+                inv_r, info = self._spd.invert(a_r, copy=not solve_tc)
+            else:
+                chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
+                                           lambda: torch.linalg.cholesky_ex(a_r))
             # The smallest rho is the worst-conditioned system.  With fewer voxels than unknowns
             # (LiTS deepest level: V = 400, K' = 13825) cond(A) = lambda_max(A0)/(rho+eta) reaches
             # 1e8+ and an fp32 pivot can come out negative: check it once (one sync per layer, on
-            # the side stream) and, if so, factorise and invert every A of this layer in fp64.
+            # the side stream) and, if so, factorise and invert every A of this layer in fp64 (library: the
+            # robustness fallback, like the reference's own CPU retry at solver.py:329-337).
             if (check_first and int(info.item()) != 0) or fstate.get("force64"):
                 fstate["use64"] = True
                 rep.fp64_factor = True
@@ -143,6 +153,8 @@ class LayerCalibrator:
                                       lambda: torch.cholesky_inverse(chol64))
             inv_r = inv64.float()
             del a64, chol64, inv64
+        elif inv_r is not None:
+            pass                                       # own factorisation + inverse, done above
         elif solve_tc and kp >= 1024 and os.environ.get("EFFQ_INV_TC", "1") != "0":
             # A^-1 = L^-T L^-1: one library TRSM for W = L^-1, then W^T W on the tensor cores
             # (the library's potri runs at ~5 TFLOP/s and was the largest item of the step)
@@ -163,9 +175,10 @@ class LayerCalibrator:
 
     @staticmethod
     def use_solve_tc(kp: int, force_generic: bool = False) -> bool:
-        """K' >= 256: the per-iteration product B A^-1 runs on the tensor cores from bf16 split planes
-        (fp32-class accuracy, csrc/solve_gemm_tc.cu); smaller systems stay on the library SGEMM."""
-        return kp >= 256 and not force_generic and os.environ.get("EFFQ_SOLVE_TC", "1") != "0"
+        """The per-iteration product B A^-1 runs on the tensor cores from bf16 split planes (fp32-class accuracy,
+        csrc/solve_gemm_tc.cu; TMA zero-fills partial tiles, so every K' qualifies).  ``force_generic`` /
+        EFFQ_SOLVE_TC=0 select the library SGEMM (bring-up comparison only)."""
+        return kp >= 8 and not force_generic and os.environ.get("EFFQ_SOLVE_TC", "1") != "0"
 
     def proximal_step(self, a0, b0, w0p, g, dual, rho: float, eta: float, has_bias: bool, fstate=None):
         """One stand-alone proximal step  w* = (B0 + eta W0' + rho (G - dual)) A^-1  (solver.py:316-345) through
@@ -525,6 +538,7 @@ class LayerCalibrator:
         if self.probe is not None and t is not None:
             self.probe(name, tag, t)
 
+    _spd = None
     force_fp64_factor = False      # tests: take the fp64-Cholesky / fp64-LU fallbacks of inverse_of on any layer
     force_lu_factor = False
     _cws = None

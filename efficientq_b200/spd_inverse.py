@@ -1,0 +1,169 @@
+"""Inverse of the SPD normal matrix A = A0 + rho*quasi_eye + eta*I on the repo's own kernels (row a9).
+
+The reference calls ``torch.linalg.solve(A, B^T)`` -- an fp32 LU of the K' x K' matrix -- in every one of its 200
+iterations (src/models/solver.py:327-331).  A takes five values per layer, so each is factorised and inverted once
+and the iterations multiply with A^-1 (layer_engine).  This module is that factorisation + inverse without cuSOLVER /
+cuBLAS: a blocked right-looking Cholesky and a block triangular inverse whose O(n^3) work runs on the tensor cores
+through ``effq_gemm_tc_ex`` (three-term bf16 split, fp32-class accuracy), with the 128 x 128 diagonal blocks done by
+one CTA each (``effq_potrf_tile``):
+
+    for every 128-wide block column j:                                   (Cholesky, A = L L^T)
+        L11, W11 = L11^-1            <- potrf_tile(A11)
+        L21 = A21 W11^T              <- GEMM  (m x 128 x 128)
+        A22 -= L21 L21^T             <- GEMM  (lower tiles only, m x m x 128)
+    for every block column j, last to first:                             (W = L^-1, lower triangular)
+        T   = L21 W11                <- GEMM  (m x 128 x 128)
+        W21 = -W22 T                 <- GEMM  (m x 128 x m)
+    A^-1 = W^T W                     <- GEMM  (n x n x n)
+
+The launch sequence depends only on n and on the buffers, so it is recorded once per matrix size (capi.record) and
+re-issued for the other rhos of the layer without the Python wrappers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import capi, ops
+from .capi import check, ptr, stream
+
+NB = 128
+
+
+def _p(t: Optional[torch.Tensor]):
+    """Device pointer of a (possibly strided) view; None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _Plan:
+    """Buffers of one matrix size n; planes are [3][n][ldk] bf16 with x = p0 + p1 + p2."""
+
+    def __init__(self, n: int, device):
+        self.n = n
+        self.nblk = (n + NB - 1) // NB
+        self.ldk = ops.split3_ld(n)
+        bf, f32 = torch.bfloat16, torch.float32
+        ld4 = (n + 3) // 4 * 4                                                     # 16-byte aligned rows: vector stores in the GEMM epilogue
+        self.a = torch.empty((n, ld4), dtype=f32, device=device)[:, :n]           # A, overwritten by L (lower triangle)
+        self.lp = torch.zeros((3, n, self.ldk), dtype=bf, device=device)          # L as split planes (below-diagonal blocks)
+        self.w = torch.zeros((n, ld4), dtype=f32, device=device)[:, :n]           # W = L^-1 (upper triangle stays zero)
+        self.wp = torch.zeros((3, n, self.ldk), dtype=bf, device=device)          # W as split planes
+        self.wtp = torch.empty((3, n, self.ldk), dtype=bf, device=device)         # W^T as split planes
+        self.wdt = torch.empty((self.nblk, NB, NB), dtype=f32, device=device)     # W_jj^T, dense per block
+        self.p_a21 = torch.empty((3, n, NB), dtype=bf, device=device)             # A21 panel as planes
+        self.p_blk = torch.empty((3, NB, NB), dtype=bf, device=device)            # W_jj or W_jj^T as planes
+        self.t = torch.empty((n, NB), dtype=f32, device=device)                   # T = L21 W11
+        self.tp = torch.empty((3, NB, self.ldk), dtype=bf, device=device)         # T^T as planes
+        self.inv = torch.empty((n, (n + 3) // 4 * 4), dtype=f32, device=device)[:, :n]
+        self.info = torch.zeros(1, dtype=torch.int32, device=device)
+        self.calls, self.calls_stream = None, None                                 # recorded launch sequence and its stream
+        # one GEMM workspace for the whole (stream-ordered) sequence: the largest split-K partial buffer is that of
+        # the final n x n x n product
+        lib = capi.load()
+        need = max(lib.effq_gemm_tc_ex_workspace(n, n, n, n), lib.effq_gemm_tc_ex_workspace(n, NB, n, NB))
+        self.ws = ops.workspace(need, device)
+
+
+def _gemm(plan: _Plan, a_planes, a_ld, a_ps, b_planes, b_ld, b_ps, m, n, k, alpha, beta, c_in, out, lower_only=False):
+    lib = capi.load()
+    ldo = out.stride(0)
+    if lib.effq_gemm_tc_ex_workspace(m, n, k, ldo) > plan.ws.numel():
+        raise capi.EffqError("spd_inverse: GEMM workspace too small")
+    ops.timer.run("spd_gemm_tc", {"flops": 2.0 * m * n * k * (0.5 if lower_only else 1.0)}, lambda: check(
+        lib.effq_gemm_tc_ex(C.c_void_p(a_planes), a_ld, a_ps, C.c_void_p(b_planes), b_ld, b_ps, m, n, k, float(alpha),
+                            float(beta), _p(c_in), c_in.stride(0) if c_in is not None else 0, _p(out), ldo,
+                            int(lower_only), ptr(plan.ws), stream()), "effq_gemm_tc_ex"))
+
+
+def _split_block(src: torch.Tensor, dst_ptr: int, dst_ld: int, dst_plane: int, transpose: bool, pad_k: int):
+    rows, cols = src.shape
+    check(capi.load().effq_split3_block(_p(src), rows, cols, src.stride(0), C.c_void_p(dst_ptr), dst_ld, dst_plane,
+                                        int(transpose), pad_k, stream()), "effq_split3_block")
+
+
+def _enqueue(plan: _Plan) -> None:
+    """Factorise plan.a in place and leave A^-1 in plan.inv (all launches on the current stream)."""
+    lib = capi.load()
+    n, ldk = plan.n, plan.ldk
+    a, w = plan.a, plan.w
+    esz = 2
+    lp0, wp0, ps = plan.lp.data_ptr(), plan.wp.data_ptr(), n * ldk
+    pa0, pb0 = plan.p_a21.data_ptr(), plan.p_blk.data_ptr()
+    # ---- Cholesky, right-looking
+    for jb in range(plan.nblk):
+        j = jb * NB
+        nb = min(NB, n - j)
+        m = n - j - nb
+        ops.timer.run("potrf_tile", {"flops": nb ** 3}, lambda: check(
+            lib.effq_potrf_tile(_p(a[j:, j:]), a.stride(0), nb, _p(w[j:, j:]), w.stride(0), _p(plan.wdt[jb]), _p(plan.info),
+                                jb, stream()), "effq_potrf_tile"))
+        if m == 0:
+            break
+        # L21 = A21 W11^T  (B operand = rows of W11)
+        _split_block(a[j + nb:, j:j + nb], pa0, NB, n * NB, False, NB)
+        _split_block(w[j:j + nb, j:j + nb], pb0, NB, NB * NB, False, NB)
+        _gemm(plan, pa0, NB, n * NB, pb0, NB, NB * NB, m, nb, nb, 1.0, 0.0, None, a[j + nb:, j:j + nb])
+        # L21 as planes inside Lp, then the symmetric rank-nb update of the trailing block (lower tiles)
+        pad = min(NB, ldk - j)
+        _split_block(a[j + nb:, j:j + nb], lp0 + ((j + nb) * ldk + j) * esz, ldk, ps, False, pad)
+        l21 = lp0 + ((j + nb) * ldk + j) * esz
+        a22 = a[j + nb:, j + nb:]
+        _gemm(plan, l21, ldk, ps, l21, ldk, ps, m, m, nb, -1.0, 1.0, a22, a22, lower_only=True)
+    # ---- W = L^-1, block columns from the last to the first (W_jj is already in place)
+    tp0 = plan.tp.data_ptr()
+    for jb in range(plan.nblk - 1, -1, -1):
+        j = jb * NB
+        nb = min(NB, n - j)
+        m = n - j - nb
+        pad = min(NB, ldk - j)
+        _split_block(w[j:j + nb, j:j + nb], wp0 + (j * ldk + j) * esz, ldk, ps, False, pad)
+        if m == 0:
+            continue
+        # T = L21 W11  (B operand = rows of W11^T)
+        _split_block(plan.wdt[jb][:nb, :nb], pb0, NB, NB * NB, False, NB)
+        l21 = lp0 + ((j + nb) * ldk + j) * esz
+        t = plan.t[:m, :nb]
+        _gemm(plan, l21, ldk, ps, pb0, NB, NB * NB, m, nb, nb, 1.0, 0.0, None, t)
+        # W21 = -W22 T  (A operand = rows of W22, K = m; B operand = rows of T^T)
+        mk = (m + 63) // 64 * 64
+        _split_block(t, tp0, ldk, NB * ldk, True, mk)
+        w22 = wp0 + ((j + nb) * ldk + (j + nb)) * esz
+        w21 = w[j + nb:, j:j + nb]
+        _gemm(plan, w22, ldk, ps, tp0, ldk, NB * ldk, m, nb, m, -1.0, 0.0, None, w21)
+        _split_block(w21, wp0 + ((j + nb) * ldk + j) * esz, ldk, ps, False, pad)
+    # ---- A^-1 = W^T W  (both operands = rows of W^T)
+    _split_block(w, plan.wtp.data_ptr(), ldk, ps, True, ldk)
+    wt = plan.wtp.data_ptr()
+    _gemm(plan, wt, ldk, ps, wt, ldk, ps, n, n, n, 1.0, 0.0, None, plan.inv)
+
+
+class SpdInverter:
+    """``invert(a)``: a (n x n fp32, symmetric positive definite; only its lower triangle is read) -> (A^-1 as a fresh
+    fp32 tensor, info tensor: 0 or the 1-based index of the first non-positive pivot).  Stream-ordered, no host sync."""
+
+    def __init__(self, device):
+        self.device = device
+        self.plans: Dict[int, _Plan] = {}
+
+    def invert(self, a: torch.Tensor, replay: bool = True, copy: bool = True):
+        """``copy=False`` returns the plan's own result buffer (valid until the next ``invert`` of this size)."""
+        n = a.shape[0]
+        plan = self.plans.get(n)
+        if plan is None:
+            for k in [k for k in self.plans if k != n]:          # one live size (the buffers of K' = 6913 take ~2 GB)
+                del self.plans[k]
+            plan = self.plans[n] = _Plan(n, self.device)
+        plan.a.copy_(a)
+        plan.info.zero_()
+        cur = torch.cuda.current_stream(self.device).cuda_stream       # the recorded launches carry their stream
+        if plan.calls is not None and replay and plan.calls_stream == cur:
+            ops.replay(plan.calls)
+        elif replay and capi._recorder is None and plan.calls is None:
+            with capi.record() as rec:
+                _enqueue(plan)
+            plan.calls, plan.calls_stream = list(rec.calls), cur
+        else:
+            _enqueue(plan)
+        return (plan.inv.clone() if copy else plan.inv), plan.info.clone()

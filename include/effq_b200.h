@@ -310,6 +310,30 @@ int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const 
                     float* history, const void* aux_src, void* aux_dst, int64_t aux_bytes,
                     const effq_peer_comm* comm, void* stream);
 
+/* ---- (a9) dense SPD factorisation and inverse on the repo's own kernels -------------------------------------
+ * The reference solves A x = B^T with an fp32 LU of the K' x K' normal matrix in every iteration
+ * (solver.py:331).  A takes 5 values per layer; each is factorised (blocked right-looking Cholesky) and inverted
+ * (block triangular inverse, then W^T W) once, the O(n^3) work on the tensor cores through effq_gemm_tc_ex
+ * (efficientq_b200/spd_inverse.py drives the block loop). */
+/* out = alpha * A B^T + beta * c_in on SUB-BLOCKS of split-plane matrices (three bf16 terms per fp32 value,
+ * effq_split3_bf16 / effq_split3_block): A = m x k block at a_planes with row pitch a_ld and plane stride
+ * a_plane_stride (elements, multiples of 8), B = n x k likewise.  c_in may be NULL (beta ignored) and may alias
+ * out.  lower_only != 0 skips the 128 x 128 tiles strictly above the diagonal.  fp32-class accuracy. */
+int64_t effq_gemm_tc_ex_workspace(int32_t m, int32_t n, int32_t k, int64_t ldo);
+int effq_gemm_tc_ex(const void* a_planes, int64_t a_ld, int64_t a_plane_stride, const void* b_planes,
+                    int64_t b_ld, int64_t b_plane_stride, int32_t m, int32_t n, int32_t k, float alpha,
+                    float beta, const float* c_in, int64_t ldc, float* out, int64_t ldo, int32_t lower_only,
+                    void* workspace, void* stream);
+/* One diagonal block (nb <= 128): a[nb][lda] <- its Cholesky factor (lower triangle); w_out[nb][ldw] <- the
+ * factor's inverse (lower triangular, zero above), wt_out[128][128] <- that inverse transposed (dense, zero
+ * padded).  *info stays 0 or receives 128 * block_index + (1-based failing pivot), first failure wins. */
+int effq_potrf_tile(float* a, int64_t lda, int32_t nb, float* w_out, int64_t ldw, float* wt_out, int32_t* info,
+                    int32_t block_index, void* stream);
+/* fp32 block src[rows][cols] (pitch ld) -> three bf16 terms at dst inside a plane matrix (row pitch dst_ld,
+ * plane stride dst_plane, elements); transpose != 0 writes src^T; the K direction is zero-filled up to pad_k. */
+int effq_split3_block(const float* src, int32_t rows, int32_t cols, int64_t ld, void* dst, int64_t dst_ld,
+                      int64_t dst_plane, int32_t transpose, int32_t pad_k, void* stream);
+
 /* ---- end-to-end activation-range refinement: reference ptqer.py:238-272 ------------------
  * (tune_activation_range: Adam on every alpha_act through the straight-through estimator of
  * layer_helper.py:13-37; defined in the reference, not called by its do_ptq.) */

@@ -560,23 +560,23 @@ def test_quadform_delta_equals_conv_sse(ops, n, c1, c2, sp):
     torch.manual_seed(c1 + c2)
     la = 16
     codes = torch.randint(0, la, (n, c1, *sp)).float()
-    sc = 0.173
-    x = codes * sc
+    sc = float(np.float32(0.173))
+    x = codes.double() * sc                        # the kernel's model of the activations: fp32 scale x integer code
     w_true = torch.randn(c2, c1, 3, 3, 3) * (2.0 / (27 * c1)) ** 0.5
     b_true = torch.randn(c2) * 0.05
-    y = F.conv3d(x, w_true, b_true, 1, 1)
+    y = F.conv3d(x, w_true.double(), b_true.double(), 1, 1).float()
     g_ref = w_true + 0.02 * w_true.std() * torch.randn_like(w_true)      # "first iterate"
     b_ref = b_true + 0.01 * torch.randn_like(b_true)
-    r = (y.double() - F.conv3d(x.double(), g_ref.double(), b_ref.double(), 1, 1)).float()
+    r = (y.double() - F.conv3d(x, g_ref.double(), b_ref.double(), 1, 1)).float()
     xq = codes.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
     acc, _, flag = ops.gram_tc_f64(xq, torch.tensor([sc], device=DEV), r.to(DEV), None, True, att_exact=True)
     assert int(flag.item()) == 0
     # S against the fp64 im2col Gram: the integer part is exact
-    cols = O.im2col(x, 3, 3, 3, 1, 1).double()
+    cols = O.im2col(codes, 3, 3, 3, 1, 1).double() * sc
     cols = torch.cat([cols, torch.ones(1, cols.shape[1], dtype=torch.float64)], 0)
     kp = cols.shape[0]
     s_ref = cols @ cols.T
-    assert (acc[:kp].cpu() - s_ref).abs().max().item() <= 1e-9 * s_ref.abs().max().item()
+    assert (acc[:kp].cpu() - s_ref).abs().max().item() <= 1e-12 * s_ref.abs().max().item()
     t_ref = r.permute(1, 0, 2, 3, 4).reshape(c2, -1).double() @ cols.T
     assert (acc[kp:].cpu() - t_ref).abs().max().item() <= 2e-5 * t_ref.abs().max().item()
     yy = torch.tensor([(r.double() ** 2).sum().item()], dtype=torch.float64, device=DEV)
@@ -589,7 +589,8 @@ def test_quadform_delta_equals_conv_sse(ops, n, c1, c2, sp):
     for i, eps in enumerate((2e-2, 5e-3, 1e-3)):
         g = g_ref + eps * w_true.std() * torch.randn_like(g_ref)
         b = b_ref + eps * 0.1 * torch.randn_like(b_ref)
-        ref = ((F.conv3d(x.double(), g.double(), b.double(), 1, 1) - y.double()) ** 2).sum().item()
+        # what the statistics describe: sum((g - g_ref) X + (b - b_ref) - R)^2 with the fp32-rounded residual R
+        ref = ((F.conv3d(x, (g - g_ref).double(), (b - b_ref).double(), 1, 1) - r.double()) ** 2).sum().item()
         ops.quadform_delta(acc, yy, g.reshape(c2, -1).contiguous().to(DEV), b.to(DEV), sse, gd, bd, st=st,
                            numel=numel, history=hist)
         got = sse.item()
@@ -650,3 +651,39 @@ def test_solve_gemm_tc_fp32_class_accuracy(ops, m, k):
     planes = torch.empty((3, m, ops.split3_ld(k)), dtype=torch.bfloat16, device=DEV)
     ops.admm_rhs(b0, w0p, g, dual, 10.0, 1.0, out32, planes=planes)
     assert torch.equal(planes, ops.split3_bf16(out32))
+
+
+# ---------------------------------------------------------------- own SPD factorisation + inverse (a9)
+@pytest.mark.parametrize("n", [33, 109, 129, 257, 865, 1729, 3457])
+def test_spd_inverse_own_kernels(ops, n):
+    """Blocked Cholesky + block triangular inverse + W^T W through the repo's kernels (spd_inverse.py) against an
+    fp64 inverse, on a matrix with the structure of the real normal matrices (Gram of non-negative features + a small
+    ridge: cond ~ 1e4..1e5); error in the class of the library's fp32 Cholesky inverse.  Also: replayed launch
+    sequence == first run, and a non-positive pivot is reported like LAPACK's info."""
+    from efficientq_b200.spd_inverse import SpdInverter
+    torch.manual_seed(n)
+    v = 4 * n
+    x = torch.relu(torch.randn(n, v, device=DEV, dtype=torch.float64)) * 0.4
+    a64 = 2.0 * x @ x.T + (0.02 * v) * torch.eye(n, device=DEV, dtype=torch.float64)
+    a = a64.float()
+    ref = torch.linalg.inv(a.double())
+    inv = SpdInverter(torch.device(DEV))
+    got, info = inv.invert(a)
+    assert int(info.item()) == 0
+    lib = torch.cholesky_inverse(torch.linalg.cholesky(a))
+    scale = ref.abs().max().item()
+    e_own = (got.double() - ref).abs().max().item() / scale
+    e_lib = (lib.double() - ref).abs().max().item() / scale
+    resid = (got.double() @ a.double() - torch.eye(n, device=DEV, dtype=torch.float64)).abs().max().item()
+    line = f"n={n}: A^-1 vs fp64: own kernels {e_own:.2e}, library fp32 Cholesky inverse {e_lib:.2e} | max|A^-1 A - I| {resid:.2e}"
+    print(line)
+    import os
+    if os.path.isdir("gpurun_out"):
+        open("gpurun_out/r02_spd_inverse.txt", "a").write(line + "\n")
+    assert e_own <= max(4.0 * e_lib, 2e-6)
+    got2, _ = inv.invert(a)                                 # second call replays the recorded launch sequence
+    assert torch.equal(got, got2)
+    bad = a.clone()
+    bad[n // 2, n // 2] = -1.0
+    _, info_bad = inv.invert(bad)
+    assert int(info_bad.item()) == n // 2 + 1

@@ -126,7 +126,10 @@ def test_tune_activation_range_matches_reference(ops, golden):
     for name, gv in zip(tuned, grads0):
         ref = float(g[f"grad0::{name}"])
         assert abs(gv - ref) <= 2e-3 * abs(ref) + 1e-7, (name, gv, ref)
-    np.testing.assert_allclose(losses, g["tune_losses"], rtol=1e-5)
+    # after an Adam step every alpha_act has moved by lr = 5e-4: activations that sat within that of a level
+    # boundary change code, and which ones do depends on the last bits of the layer inputs (exact integer conv
+    # here, fp32 MKL conv in the reference) -- 2.5e-4 on the loss of step 1 with this fixture, 1e-7 on steps 0 and 2
+    np.testing.assert_allclose(losses, g["tune_losses"], rtol=5e-4)
     for name in tuned:
         assert abs(float(mods[name].alpha_act) - float(g[f"post::{name}.alpha_act"])) <= 2e-5 * float(mods[name].alpha_act)
     for name, m in mods.items():

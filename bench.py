@@ -2,7 +2,7 @@
 """Headline benchmark: EfficientQ PTQ calibration throughput on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the unmodified reference's CPU path (baseline/_ref)
 
 A step = one full PTQ calibration (FP forward -> attention-mask pyramid -> quantizing pass,
 the reference's own timed region t2-t0, src/ptqer.py:333-366) of the BraTS-config 3D U-Net
@@ -159,61 +159,77 @@ def peaks():
 CPU_SAMPLE_ITERS = 16   # of 200 ADMM iterations per layer: ~15-20 s of work on 16 host threads
 
 
-def cpu_sample(wl, iters=None, threads=None, edge_div=2):
-    """Bounded sample of the CPU path (oracle port of the reference) on the host cores.
+def cpu_sample(wl, iters=None, threads=None, edge_div=2, n_volumes=None):
+    """Bounded sample of the reference's CPU path on the host cores.
 
-    Runs the per-layer calibration of ALL 22 quantizer layers on ONE volume whose edge is
-    1/edge_div of the workload's (so 1/edge_div^3 of the voxels) with `iters` ADMM
-    iteration(s), timing each phase, and scales to the full job with V = N * edge_div^3:
-        t = V*(t_act + t_gram) + 200/iters*(t_solve + t_wproj + V*t_conv)
-    -- activation search, im2col+Gram and conv+mse scale with the voxel count, the dense
-    solve and the weight projection do not.  `iters` > 1 matters: the first
-    iterate's weight projection needs more fixed-point passes than the later ones, so a
-    1-iteration sample overstates the CPU time by ~1.4x (8491 s vs 6121 s on 8 cores).
-    Returns (volumes/s, description, seconds spent, scaled full-job seconds)."""
-    from oracle import effq_oracle as O
+    When ``baseline/_ref`` holds the reference (copied there by ``__graft_entry__.build()`` in the build container;
+    it travels with the working tree) the sample runs the UNMODIFIED reference -- its own network, BN folding, hooks,
+    mask pyramid and ``EfficientQConv.ptq`` (baseline/ref_harness.py), ``kind: "reference"``; otherwise the oracle
+    port of the same path (``kind: "port"``).  Either way: ALL quantizer layers on ONE volume whose edge is
+    1/edge_div of the workload's (1/edge_div^3 of the voxels) with `iters` of the 200 ADMM iterations, every phase
+    timed, and scaled to the full job with V = n_volumes * edge_div^3:
+        t = V*(t_fp + t_act + t_gram) + 200/iters*(t_solve + t_wproj + V*t_conv)
+    -- FP pass, activation search, im2col+Gram and conv+mse scale with the voxel count, the dense solve and the weight
+    projection do not.  `iters` > 1 matters: the first iterate's weight projection needs more
+    fixed-point passes than the later ones, so a 1-iteration sample overstates the CPU time by ~1.4x.
+    Returns (volumes/s, description, seconds spent, scaled full-job seconds, kind)."""
     iters = iters or wl.get("cpu_iters", CPU_SAMPLE_ITERS)
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     from efficientq_b200 import synth
-    from efficientq_b200.qconv import PTQConv
-    model, _ = build_model(wl)
-    t_begin = time.perf_counter()
+    n = n_volumes or wl["n"]
     size = tuple(max(64, s // edge_div) for s in wl["size"])
     vox_scale = 1.0
     for a, b in zip(wl["size"], size):
         vox_scale *= a / b
     x = synth.batch(1, 0, N_MOD[wl["task"]], size, wl["task"])
-    feats = {}
-    hooks = []
-    for name, m in model.named_modules():
-        if isinstance(m, PTQConv):
-            m.set_fp()
-            hooks.append(m.register_forward_hook(
-                lambda mod, i, o, name=name: feats.__setitem__(name, (i[0].detach(), o.detach()))))
-    with torch.no_grad():
-        model(x)
-    for h in hooks:
-        h.remove()
-    timers = {}
-    n_layers = 0
-    for name, m in model.named_modules():
-        if not isinstance(m, PTQConv):
-            continue
-        n_layers += 1
-        xi, yo = feats.pop(name)
-        O.admm_layer(xi, m.weight.data, m.bias.data, yo, m.stride, m.padding, m.qlvl_w, m.qlvl_act, m.q_act,
-                     None, n_iter=iters, timers=timers)
-    n = wl["n"]
+    from baseline import ref_harness as H
+    t_begin = time.perf_counter()
+    if H.ensure_ref():
+        kind = "reference"
+        R = H.import_reference()
+        margs = task_args(wl)
+        model = H.build_reference_model(R, margs, seeded_state)
+        timers, t_fp, _, losses = H.timed_ptq(R, model, x, wl["task"], margs.init_stride, iters)
+        n_layers = len(losses)
+        timers = dict(timers, fp_pass=t_fp)
+        what = "the UNMODIFIED reference (baseline/_ref: its own UResQ, fold_bn, hooks, EfficientQConv.ptq)"
+    else:
+        kind = "port"
+        from oracle import effq_oracle as O
+        from efficientq_b200.qconv import PTQConv
+        model, _ = build_model(wl)
+        feats = {}
+        hooks = []
+        for name, m in model.named_modules():
+            if isinstance(m, PTQConv):
+                m.set_fp()
+                hooks.append(m.register_forward_hook(
+                    lambda mod, i, o, name=name: feats.__setitem__(name, (i[0].detach().clone(), o.detach().clone()))))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            model(x)
+        timers = {"fp_pass": time.perf_counter() - t0}
+        for h in hooks:
+            h.remove()
+        n_layers = 0
+        for name, m in model.named_modules():
+            if not isinstance(m, PTQConv):
+                continue
+            n_layers += 1
+            xi, yo = feats.pop(name)
+            O.admm_layer(xi, m.weight.data, m.bias.data, yo, m.stride, m.padding, m.qlvl_w, m.qlvl_act, m.q_act,
+                         None, n_iter=iters, timers=timers)
+        what = "oracle port of the reference's CPU path (baseline/_ref absent)"
     v = n * vox_scale
-    full = v * (timers.get("act_search", 0) + timers.get("im2col_gram", 0)) + \
+    full = v * (timers.get("fp_pass", 0) + timers.get("act_search", 0) + timers.get("im2col_gram", 0)) + \
         200.0 / iters * (timers.get("solve", 0) + timers.get("w_project", 0) + v * timers.get("conv_mse", 0))
     spent = time.perf_counter() - t_begin
-    desc = (f"oracle port on {threads} threads, all {n_layers} layers, one {size} volume (1/{vox_scale:.0f} of a "
+    desc = (f"{what} on {threads} threads, all {n_layers} layers, one {size} volume (1/{vox_scale:.0f} of a "
             f"{wl['size']} volume), {iters} of 200 ADMM iterations; phases(s) "
             f"{json.dumps({k: round(t, 3) for k, t in timers.items()})}; scaled with V={v:.0f}: "
-            f"V*(act+gram)+200/{iters}*(solve+wproj+V*conv) = {full:.0f}s for {n} volumes")
-    return n / full, desc, spent, full
+            f"V*(fp+act+gram)+200/{iters}*(solve+wproj+V*conv) = {full:.0f}s for {n} volumes")
+    return n / full, desc, spent, full, kind
 
 
 def run_reference(args, wl, wl_name):
@@ -224,7 +240,8 @@ def run_reference(args, wl, wl_name):
     times, vals, desc, full = [], [], "", 0.0
     for i in range(args.warmup + args.steps):
         # warm-up samples (thread pool, allocator, page cache) need only one iteration; timed ones the full sample
-        v, desc, spent, full = cpu_sample(wl, iters=None if i >= args.warmup else 1, threads=cores)
+        v, desc, spent, full, kind = cpu_sample(wl, iters=None if i >= args.warmup else 1, threads=cores,
+                                                n_volumes=wl["n"] * max(1, args.gpus))
         if i >= args.warmup:
             times.append(spent)
             vals.append(v)
@@ -234,9 +251,10 @@ def run_reference(args, wl, wl_name):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "volumes_per_gpu": wl["n"], "volume": list(wl["size"]),
                        "levels_w": wl["lw"], "levels_a": wl["la"], "admm_iters": 200,
-                       "parallelism": f"{cores} host threads (oracle port of the reference's CPU path)"},
+                       "parallelism": f"{cores} host threads ({'unmodified reference' if kind == 'reference' else 'oracle port'}, "
+                                      f"{wl['n'] * max(1, args.gpus)} volumes)"},
             "ptq_wall_s": full,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -327,6 +345,15 @@ def run_ours(args, wl, wl_name):
     units = float(n_local * dist.world * args.steps)
     value = units / (dev_ms / 1e3)
     e2e = units / (e2e_ms / 1e3)
+    # replicated solve / projection: every rank must end the last step with bit-identical quantised weights
+    ranks_identical = None
+    if dist.world > 1:
+        flat = torch.cat([p_.detach().reshape(-1).double() for p_ in model.parameters()])
+        sig = torch.stack([flat.sum(), (flat * torch.arange(1, flat.numel() + 1, device=dev, dtype=torch.float64)).sum()])
+        hi_, lo_ = sig.clone(), -sig.clone()
+        dist.all_reduce_max(hi_)
+        dist.all_reduce_max(lo_)
+        ranks_identical = bool(torch.equal(hi_, -lo_))
     if dist.rank != 0:
         return
 
@@ -383,8 +410,8 @@ def run_ours(args, wl, wl_name):
     cpu = None
     if args.gpus == 1 and not args.no_cpu:
         try:
-            v, desc, spent, full = cpu_sample(wl)
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc,
+            v, desc, spent, full, kind = cpu_sample(wl)
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": desc,
                    "sample_seconds": spent, "ptq_wall_s": full}
         except Exception as exc:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
@@ -403,6 +430,7 @@ def run_ours(args, wl, wl_name):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "kernels": kern, "kernels_note": "CUDA events around every major kernel in ONE instrumented step outside the timed "
                                              "region; `roofline` is the dominant kernel timed live inside the timed region",
+            "ranks_hold_identical_weights": ranks_identical,
             "act_scale_passes_per_step": act_passes,
             "layer_loss_last_step": [ln.rsplit(":", 1)[0].strip() + ":" + "%.6e" % float(ln.rsplit(":", 1)[1])
                                      for ln in losses][:3] + ["..."],

@@ -32,7 +32,7 @@ class NextRhs(C.Structure):
 
 class AdmmKeep(C.Structure):
     """``effq_admm_keep_bufs`` (include/effq_b200.h)."""
-    _fields_ = [("best_g", C.c_void_p), ("best_b", C.c_void_p), ("best_wcodes", C.c_void_p)]
+    _fields_ = [("best_g", C.c_void_p), ("best_b", C.c_void_p), ("best_wcodes", C.c_void_p), ("best_pc", C.c_void_p)]
 
 
 class Geom(C.Structure):
@@ -92,6 +92,8 @@ _SIGS = {
     "effq_conv3d_tc_workspace": (C.c_int64, [C.POINTER(Geom)]),
     "effq_conv3d_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_conv3d_tc_pc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_pack_wcodes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_gram_workspace": (C.c_int64, [C.POINTER(Geom), C.c_int32]),
     "effq_gram_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
@@ -128,10 +130,12 @@ _SIGS = {
     "effq_admm_lhs": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_admm_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_scale_search_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                         C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "effq_admm_decide": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_admm_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "effq_admm_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p]),

@@ -99,19 +99,23 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
                     int nlvl_w, int nlvl_a, int c2, int c1, int taps, int has_bias, float dual_div,
                     float* g_out, float* bstar_out,
                     void* wcodes, TcLayout lay, effq_admm_state* st, effq_next_rhs nx, int ldk,
-                    effq_admm_keep_bufs kp_) {
+                    effq_admm_keep_bufs kp_, float* __restrict__ pc_out) {
+  // pc_out != NULL: per-output-channel scales -- wscale is an array of c2 states (effq_scale_search_rows) and
+  // pc_out[0..c2) receives fp32(a_w) of every row, pc_out[c2..2c2) the conv scale a_x a_w_r / ((La-1)(Lw-1))
   const int k = c1 * taps;
   const long long total = (long long)c2 * k;
   // Fused "keep": when the PREVIOUS iterate was the best so far (st->take_, set by the decide step
   // that scored it) its G / b* / weight codes are still in g_out / bstar_out / wcodes -- every thread
   // saves the element it is about to overwrite (EfficientQConv.py:139-142 without a launch of its own).
   const bool keep_prev = kp_.best_g != nullptr && st != nullptr && *((volatile int*)&st->take_) != 0;
-  const double a64 = wscale->a;
-  const float a32 = (float)a64;
+  const bool per_row = pc_out != nullptr;
+  const double a64_all = wscale->a;
   const QParamD q = make_qparam_d(-1.f, 1.f, nlvl_w);
   for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < total;
        e += (long long)gridDim.x * AD_THREADS) {
     const int r = (int)(e / k), j = (int)(e % k);
+    const double a64 = per_row ? wscale[r].a : a64_all;
+    const float a32 = (float)a64;
     const float ws = wstar[(long long)r * ldw + j];
     const float du = dual[e];
     const float v = __fadd_rn(ws, du);                                   // w_star + dual (fp32)
@@ -157,9 +161,18 @@ admm_project_kernel(const float* __restrict__ wstar, long long ldw, float* __res
       store_split3((__nv_bfloat16*)nx.planes, (long long)r * ldk + j, (long long)c2 * ldk, v);
     }
   }
+  const double ax = xscale ? (double)(float)xscale->a / (double)(nlvl_a - 1) : 1.0;
+  if (per_row) {
+    for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < c2; r += gridDim.x * AD_THREADS) {
+      if (keep_prev && kp_.best_pc) { kp_.best_pc[r] = pc_out[r]; kp_.best_pc[c2 + r] = pc_out[c2 + r]; }
+      const float a32 = (float)wscale[r].a;
+      pc_out[r] = a32;
+      pc_out[c2 + r] = (float)(ax * (double)a32 / (double)(nlvl_w - 1));
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0 && st) {
+    const float a32 = (float)a64_all;                    // per-row mode: row 0's scale (bookkeeping only)
     st->a_w = a32;
-    const double ax = xscale ? (double)(float)xscale->a / (double)(nlvl_a - 1) : 1.0;
     st->conv_scale = (float)(ax * (double)a32 / (double)(nlvl_w - 1));
   }
 }
@@ -179,8 +192,11 @@ __global__ void admm_decide_kernel(effq_admm_state* st, const double* __restrict
 __global__ void __launch_bounds__(AD_THREADS)
 admm_keep_kernel(const int* __restrict__ take, const float* __restrict__ g, const float* __restrict__ bstar,
                  long long g_numel, int c2, float* __restrict__ best_g, float* __restrict__ best_b,
-                 const uint4* __restrict__ aux_src, uint4* __restrict__ aux_dst, long long aux_vec) {
+                 const uint4* __restrict__ aux_src, uint4* __restrict__ aux_dst, long long aux_vec,
+                 const float* __restrict__ pc_src = nullptr, float* __restrict__ pc_dst = nullptr) {
   if (*take == 0) return;
+  if (pc_src && pc_dst)
+    for (int r = blockIdx.x * AD_THREADS + threadIdx.x; r < 2 * c2; r += gridDim.x * AD_THREADS) pc_dst[r] = pc_src[r];
   for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < aux_vec;
        e += (long long)gridDim.x * AD_THREADS) aux_dst[e] = aux_src[e];
   for (long long e = (long long)blockIdx.x * AD_THREADS + threadIdx.x; e < g_numel;
@@ -247,11 +263,12 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
                                  const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                                  int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
                                  float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
-                                 const effq_next_rhs* next, const effq_admm_keep_bufs* keep, void* stream) {
+                                 const effq_next_rhs* next, const effq_admm_keep_bufs* keep, float* per_channel_out,
+                                 void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(!keep || (keep->best_g && st), "keep: best_g and the ADMM state are required");
   effq_admm_keep_bufs kp_;
-  if (keep) kp_ = *keep; else { kp_.best_g = nullptr; kp_.best_b = nullptr; kp_.best_wcodes = nullptr; }
+  if (keep) kp_ = *keep; else { kp_.best_g = nullptr; kp_.best_b = nullptr; kp_.best_wcodes = nullptr; kp_.best_pc = nullptr; }
   EFFQ_CHECK_ARG(wstar && dual && wscale && g_out, "null pointer");
   EFFQ_CHECK_ARG(c2 > 0 && c1 > 0 && taps > 0 && ldw >= (int64_t)c1 * taps + (has_bias ? 1 : 0), "bad shape");
   EFFQ_CHECK_ARG(!wcodes_out || (code_dtype == CODE_BF16 && c1 % 8 == 0 && nlvl_w <= 256) ||
@@ -265,7 +282,7 @@ extern "C" int effq_admm_project(const float* wstar, int64_t ldw, float* dual, c
   const int ldk = (int)effq_split3_ld((int64_t)c1 * taps + (has_bias ? 1 : 0));
   admm_project_kernel<<<grid_for((long long)c2 * c1 * taps), AD_THREADS, 0, (cudaStream_t)stream>>>(
       wstar, ldw, dual, wscale, xscale, nlvl_w, nlvl_a, c2, c1, taps, has_bias, dual_div, g_out, bstar_out,
-      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st, nx, ldk, kp_);
+      wcodes_out, tc_layout(c1, wcodes_out ? code_dtype : 0), st, nx, ldk, kp_, per_channel_out);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }
@@ -288,14 +305,15 @@ extern "C" int effq_admm_decide(effq_admm_state* st, const double* sse, double n
 
 extern "C" int effq_admm_keep(effq_admm_state* st, const float* g, const float* bstar, int64_t g_numel, int32_t c2,
                               float* best_g, float* best_b, const void* aux_src, void* aux_dst, int64_t aux_bytes,
-                              void* stream) {
+                              const float* pc_src, float* pc_dst, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(st && g && best_g && g_numel > 0, "bad argument");
   EFFQ_CHECK_ARG(aux_bytes == 0 || (aux_src && aux_dst && aux_bytes % 16 == 0 &&
                                     ((uintptr_t)aux_src & 15) == 0 && ((uintptr_t)aux_dst & 15) == 0),
                  "aux buffers must be 16B aligned and sized");
   admm_keep_kernel<<<grid_for(g_numel), AD_THREADS, 0, (cudaStream_t)stream>>>(
-      &st->take_, g, bstar, g_numel, c2, best_g, best_b, (const uint4*)aux_src, (uint4*)aux_dst, aux_bytes / 16);
+      &st->take_, g, bstar, g_numel, c2, best_g, best_b, (const uint4*)aux_src, (uint4*)aux_dst, aux_bytes / 16, pc_src,
+      pc_dst);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

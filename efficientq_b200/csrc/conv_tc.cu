@@ -51,6 +51,7 @@ struct TcParams {
   const uint8_t* wq;           // [tap][group][C2][CG] pre-swizzled (tc_layout.cuh)
   const float* bias;
   const float* conv_scale;
+  const float* scale_vec;      // optional [c2_total]: per-output-channel scales (conv_scale is then ignored)
   float* out;                  // NCDHW or null
   const float* target;         // NCDHW or null
   const float* att;            // N,D,H,W or null
@@ -100,7 +101,8 @@ __device__ __forceinline__ void epi_load_targets(float (&tv)[32], const float* t
 }
 // v: raw accumulators in, outputs (scale * acc + bias) out; returns sum (out - target)^2 of the chunk
 template <int NC>
-__device__ __forceinline__ float epi_chunk(uint32_t (&v)[32], const float (&tv)[32], const float* bias_c0, float scale) {
+__device__ __forceinline__ float epi_chunk(uint32_t (&v)[32], const float (&tv)[32], const float* bias_c0, float scale,
+                                           const float* svec_c0 = nullptr) {
   float e[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < NC; j += 4) {
@@ -108,7 +110,9 @@ __device__ __forceinline__ float epi_chunk(uint32_t (&v)[32], const float (&tv)[
     const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float o = fmaf(__uint_as_float(v[j + k]), scale, bb[k]);
+      // per-output-channel scales (optional extension): a warp-uniform broadcast load from L1
+      const float sc = svec_c0 ? __ldg(svec_c0 + j + k) : scale;
+      const float o = fmaf(__uint_as_float(v[j + k]), sc, bb[k]);
       const float dlt = o - tv[j + k];
       e[k] = fmaf(dlt, dlt, e[k]);
       v[j + k] = __float_as_uint(o);
@@ -263,7 +267,8 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;               // tile row = hy*8 + wx
     const int hy = row >> 3, wx = row & 7;
-    const float scale = __ldg(p.conv_scale);
+    const float scale = p.scale_vec ? 1.f : __ldg(p.conv_scale);
+    const float* svec = p.scale_vec ? p.scale_vec + p.c2_off : nullptr;
     const long long plane = (long long)p.h * p.w;
     const long long chan = (long long)p.d * plane;
     Pipe ap{0, 0}, gp{0, 0};
@@ -298,7 +303,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
 #pragma unroll
           for (int j = 0; j < 32; ++j) tv[j] = ts[j * (TC_TILE_H * TC_TILE_W)];     // lanes read consecutive floats
           tc_wait_ld();
-          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale);
+          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr);
           mbar_arrive(BAR(B_GE + gp.stage));
           gp.advance(p.n_tgt_stages);
           if (store) epi_store<32>(v, optr, chan);
@@ -338,14 +343,14 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
         if (rest >= 0) {
           tc_ld32(taddr, v);
           tc_wait_ld();
-          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale);
+          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr);
           if (rest >= 32) epi_load_targets<32>(tv, tptr + 32 * chan, chan, want_t);      // next chunk's loads overlap
           else if (rest > 0) epi_load_targets<16>(tv, tptr + 32 * chan, chan, want_t);   // this chunk's stores
           if (store) epi_store<32>(v, optr, chan);
         } else {
           tc_ld16(taddr, v);
           tc_wait_ld();
-          e32 += epi_chunk<16>(v, tv, bias_s + c0, scale);
+          e32 += epi_chunk<16>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr);
           if (store) epi_store<16>(v, optr, chan);
         }
         tptr += 32 * chan;
@@ -608,9 +613,26 @@ extern "C" int64_t effq_conv3d_tc_workspace(const effq_geom* g) {
   return 16 + 8 * 1024;
 }
 
+static int conv3d_tc_impl(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
+                          const float* conv_scale, const float* scale_vec, const effq_geom* g, float* out,
+                          const float* target, const float* att, double* sse, void* workspace, void* stream);
+
 extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
                               const float* conv_scale, const effq_geom* g, float* out, const float* target, const float* att, double* sse,
                               void* workspace, void* stream) {
+  return conv3d_tc_impl(xcodes, wcodes, code_dtype, bias, conv_scale, nullptr, g, out, target, att, sse, workspace, stream);
+}
+
+// The same conv with one scale per OUTPUT CHANNEL (scale_vec[c2], device): out[c] = scale_vec[c] * (integer) + bias[c].
+extern "C" int effq_conv3d_tc_pc(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
+                                 const float* scale_vec, const effq_geom* g, float* out, const float* target,
+                                 const float* att, double* sse, void* workspace, void* stream) {
+  return conv3d_tc_impl(xcodes, wcodes, code_dtype, bias, scale_vec, scale_vec, g, out, target, att, sse, workspace, stream);
+}
+
+static int conv3d_tc_impl(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
+                          const float* conv_scale, const float* scale_vec, const effq_geom* g, float* out,
+                          const float* target, const float* att, double* sse, void* workspace, void* stream) {
   using namespace effq;
   EFFQ_CHECK_ARG(xcodes && wcodes && conv_scale && g && workspace, "null pointer");
   EFFQ_CHECK_ARG(out || target, "nothing to compute");
@@ -632,6 +654,7 @@ extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t co
   p.wq = (const uint8_t*)wcodes;
   p.bias = bias;
   p.conv_scale = conv_scale;
+  p.scale_vec = scale_vec;
   p.out = out;
   p.target = target;
   p.att = att;

@@ -662,6 +662,59 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
   }
 }
 
+// ---- per-row variant: one independent search per output channel (per-output-channel weight scales, the
+// optional `lwq_channel_wise` extension; the reference's live path is per-tensor, PTQConv.py:26-27).  One CTA per
+// row, the row in shared memory, no inter-CTA barrier: C2 searches run concurrently.
+constexpr int SR_THREADS = 256;
+__global__ void __launch_bounds__(SR_THREADS)
+scale_search_rows_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* states) {
+  extern __shared__ float srow[];
+  __shared__ double scratch[32];
+  __shared__ double bc[2];
+  const QParamD q = make_qparam_d(lo, hi, nlvl);
+  const long long r = blockIdx.x;
+  const int cols = (int)vv.cols;
+  for (int c = threadIdx.x; c < cols; c += SR_THREADS) srow[c] = load_v(vv, r, c);
+  __syncthreads();
+  double s0 = 0.0, my_sv = 0.0, my_cnt = 0.0;
+  for (int c = threadIdx.x; c < cols; c += SR_THREADS) { const double v = (double)srow[c]; s0 += fabs(v); my_sv += v; my_cnt += 1.0; }
+  s0 = block_sum(s0, scratch);
+  if (threadIdx.x == 0) bc[0] = s0 / (double)cols;
+  __syncthreads();
+  double a = bc[0], a_prev = -999.0, last0 = 0.0, last1 = 0.0;
+  int passes = 0;
+  const int max_pass = nlvl * 100;
+  const PassQ pq_base = make_passq(1.0, q);
+  while (fabs(a - a_prev) > 1e-5 && passes < max_pass) {
+    PassQ pq = pq_base;
+    pq.c1 = 1.0 / (a * q.delta);
+    PassAcc pa{0.0, 0.0, 0.0};
+    for (int c = threadIdx.x; c < cols; c += SR_THREADS) accum_idx((double)srow[c], pq, pa);
+    double t0, t1;
+    finish_bv(pa, q, my_sv, my_cnt, t0, t1);
+    t0 = block_sum(t0, scratch);
+    t1 = block_sum(t1, scratch);
+    __syncthreads();                         // everyone has read bc of the previous pass
+    if (threadIdx.x == 0) { bc[0] = t0; bc[1] = t1; }
+    __syncthreads();
+    last0 = bc[0];
+    last1 = bc[1];
+    a_prev = a;
+    a = last0 / last1;
+    ++passes;
+  }
+  if (threadIdx.x == 0) {
+    effq_scale_state* st = states + r;
+    st->a = a;
+    st->a_prev = a_prev;
+    st->s_bv = last0;
+    st->s_bb = last1;
+    st->passes = passes;
+    st->converged = fabs(a - a_prev) <= 1e-5 ? 1 : 0;
+    st->failed = (passes == max_pass) ? 1 : 0;
+  }
+}
+
 // ---- multi-GPU building blocks (one pass, no grid barrier) -----------------------
 struct SPWorkspace {
   unsigned int done;
@@ -866,6 +919,25 @@ extern "C" int effq_scale_step(effq_scale_state* state, const double* sums, int3
   using namespace effq;
   EFFQ_CHECK_ARG(state && sums, "null pointer");
   scale_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, sums, mode, nlvl);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_scale_search_rows(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows,
+                                      int64_t cols, int32_t nlvl, float lo, float hi, effq_scale_state* states,
+                                      void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(v1 && states, "null pointer");
+  EFFQ_CHECK_ARG(rows > 0 && cols > 0 && ld1 >= cols && (!v2 || ld2 >= cols) && nlvl >= 2, "bad shape");
+  EFFQ_CHECK_ARG(cols <= 56 * 1024, "row too long for the per-row search (56 K elements)");
+  const size_t smem = (size_t)cols * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(scale_search_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024 * 4));
+    configured = true;
+  }
+  VecView vv{v1, v2, ld1, ld2, rows, cols};
+  scale_search_rows_kernel<<<(unsigned)rows, SR_THREADS, smem, (cudaStream_t)stream>>>(vv, (int)nlvl, lo, hi, states);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

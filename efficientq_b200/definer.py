@@ -29,6 +29,8 @@ def get_conv_class(args):
     q_weight, q_act = args.qlvl_w > 0, args.qlvl_a > 0
     qlvl, qlvl_act = args.qlvl_w, (args.qlvl_a if q_act else 256)
     kwQ = {a: getattr(args, a) for a in dir(args) if a[:4] == "lwq_"}
+    if getattr(args, "w_per_channel", False):          # extension flag (entrance.py): not one of the reference's lwq_* keys
+        kwQ["lwq_channel_wise"] = True
     if q_act and q_weight:
         info = "bothQw{}a{}".format(qlvl, qlvl_act)
     elif q_act:

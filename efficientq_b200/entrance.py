@@ -35,7 +35,10 @@ _QUANT = {"qconv": (None, "conv"), "qlvl_w": (int, None), "qlvl_a": (int, None),
           "lwq_verbose": (FLAG, False),
           # extension (not a reference flag, and deliberately not named lwq_*: the quantizer classes receive exactly
           # the reference's lwq_* keys): > 0 runs tune_activation_range (src/ptqer.py:238-272) for that many Adam steps
-          "tune_act_iter": (int, 0)}
+          "tune_act_iter": (int, 0),
+          # extension: one weight scale per OUTPUT CHANNEL instead of the reference's per-tensor alpha_w
+          # (PTQConv.py:26-27); alpha_w then has shape [C_out] in the snapshots
+          "w_per_channel": (FLAG, False)}
 
 
 def merge_config(cfg: str, args: argparse.Namespace):

@@ -201,13 +201,17 @@ class LayerCalibrator:
     @torch.no_grad()
     def run(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out_fp: torch.Tensor,
             stride, padding, qlvl_w: int, qlvl_act: int, q_act: bool, mask_pyramid=None, name: str = "",
-            resume=None, stop_iter: Optional[int] = None):
+            resume=None, stop_iter: Optional[int] = None, channel_wise: bool = False):
         """Returns (weight*, bias*, alpha_w (0-dim device fp32), alpha_act or None, layer output, report).
 
         ``resume = (G, dual, start_iter)`` enters the ADMM loop at iteration ``start_iter`` with that state (rho follows
         from the schedule) and ``stop_iter`` leaves it early: the one-step-ahead parity tests run single iterations
         from states recorded in the reference (tests/test_gpu_parity.py).  Device-side bookkeeping (history index,
-        best-iterate seed) then counts from the first executed iteration."""
+        best-iterate seed) then counts from the first executed iteration.
+
+        ``channel_wise``: one weight scale per OUTPUT CHANNEL -- the projection runs project_by_iter on every row of
+        w* + dual separately (optional extension, north star "per output channel"; the reference's live path is
+        per-tensor, PTQConv.py:26-27, which stays the default and the parity path).  alpha_w is then a [C2] vector."""
         dev = self.device
         dist = self.dist
         x = x.detach().contiguous().float()
@@ -276,8 +280,12 @@ class LayerCalibrator:
         else:
             a0, b0 = ops.gram(qx, out_fp, att, ksize, stride, padding, has_bias=has_bias, ws=self.gram_ws)
         if dist.world > 1:
-            dist.all_reduce_sum(a0)
-            dist.all_reduce_sum(b0)
+            # ONE all-reduce for A0 || B0 (latency of the second call: ~30 us x 22 layers, and NVLS prefers big buffers)
+            flat = torch.cat([a0.reshape(-1), b0.reshape(-1)])
+            dist.all_reduce_sum(flat)
+            a0.copy_(flat[:a0.numel()].view_as(a0))
+            b0.copy_(flat[a0.numel():].view_as(b0))
+            del flat
         if self.probe is not None:
             for tag, t in (("x", x), ("out_fp", out_fp), ("att", att), ("alpha_act", self.xstate.buf[:8].view(torch.float64).clone() if q_act else None),
                            ("qx", qx if q_act else None), ("xcodes", xcodes), ("a0", a0), ("b0", b0)):
@@ -319,6 +327,11 @@ class LayerCalibrator:
             wcodes = torch.empty(taps * c1 * c2, dtype=xcodes_conv.dtype, device=dev)
             best_wcodes = torch.empty_like(wcodes)
         self.st.reset()
+        wrows = pc = best_pc = None
+        if channel_wise:
+            wrows = ops.ScaleStateRows(dev, c2)
+            pc = torch.zeros(2 * c2, dtype=torch.float32, device=dev)          # [a_w per channel | conv scale per channel]
+            best_pc = torch.zeros_like(pc)
         numel_total = y_n                      # mse over every rank's outputs
         g4 = g.view(c2, c1, *ksize)
 
@@ -382,7 +395,7 @@ class LayerCalibrator:
         from . import capi as _capi
         replayable = not (dist.world > 1 and stats64 is None and not qf_delta and peer is None) and \
             os.environ.get("EFFQ_REPLAY", "1") != "0"            # an NCCL all-reduce inside the loop cannot be re-issued
-        keep_bufs = (best_g, best_b, best_wcodes)
+        keep_bufs = (best_g, best_b, best_wcodes, best_pc)
         steady = None
         sol_small = None if solve_tc else torch.empty((c2, kp), dtype=torch.float32, device=dev)
         for it in range(it_first, it_end):
@@ -421,7 +434,10 @@ class LayerCalibrator:
                     sol = sol_small
                 # projection + dual update (EfficientQConv.py:107-111)
                 wview = sol[:, :k] if has_bias else sol
-                ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
+                if channel_wise:
+                    ops.scale_search_rows(wview, qlvl_w, -1.0, 1.0, wrows, v2=dual)
+                else:
+                    ops.scale_search(wview, qlvl_w, -1.0, 1.0, self.wstate, v2=dual)
                 div = 1.0
                 new_rho = rho
                 if it % self.rho_period == 0:          # EfficientQConv.py:129-137
@@ -435,8 +451,8 @@ class LayerCalibrator:
                 # the previous iterate, if it was the best so far, is saved by this launch (keep) before G, b* and the
                 # weight codes are overwritten
                 ops.timer.run("admm_project", {"bytes": 16 * c2 * k}, lambda: ops.admm_project(
-                    sol, dual, self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2, c1, taps, has_bias, div,
-                    g, bstar, wcodes, self.st, next_rhs=nxt, keep=keep_bufs))
+                    sol, dual, wrows if channel_wise else self.wstate, self.xstate if q_act else None, qlvl_w, qlvl_act, c2,
+                    c1, taps, has_bias, div, g, bstar, wcodes, self.st, next_rhs=nxt, keep=keep_bufs, per_channel_out=pc))
                 # score the iterate (EfficientQConv.py:118-122) and do the best-iterate bookkeeping (:139-142)
                 if stats64 is not None:
                     ops.quadform_delta(stats64, yy_dev, g, bstar, self.sse, g_ref, b_ref, st=self.st,
@@ -445,7 +461,8 @@ class LayerCalibrator:
                     out0 = None
                     if use_tc:
                         out0, _ = ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize,
-                                                want_out=qf_delta, target=out_fp, ws=self.tc_ws, sse=self.sse)
+                                                want_out=qf_delta, target=out_fp, ws=self.tc_ws, sse=self.sse,
+                                                scale_vec=pc[c2:] if channel_wise else None)
                     else:
                         ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
                                        ws=self._conv_ws(qx, c2, ksize, stride, padding), sse=self.sse)
@@ -478,7 +495,7 @@ class LayerCalibrator:
                         self._probe(name, f"it{it}_{tag}", t)
             rho = new_rho
 
-        ops.admm_keep(self.st, g, bstar, best_g, best_b, wcodes, best_wcodes)      # the last iterate, if it was the best
+        ops.admm_keep(self.st, g, bstar, best_g, best_b, wcodes, best_wcodes, pc, best_pc)   # the last iterate, if it was the best
         if loop_prof:
             t_cpu = _t.perf_counter() - t_cpu0
             ev_b.record()
@@ -487,7 +504,8 @@ class LayerCalibrator:
         # final forward with the best iterate: layer output + attention-weighted loss (:161-166)
         if use_tc:
             out_q, _ = ops.conv3d_tc(xcodes_conv, best_wcodes, best_b, self.st.best_conv_scale_ptr(), c2, ksize,
-                                     want_out=True, target=out_fp, att=att, ws=self.tc_ws, sse=self.sse)
+                                     want_out=True, target=out_fp, att=att, ws=self.tc_ws, sse=self.sse,
+                                     scale_vec=best_pc[c2:] if channel_wise else None)
         else:
             out_q, _ = ops.conv3d_f32(qx, best_g.view(c2, c1, *ksize), best_b, stride, padding, want_out=True,
                                       target=out_fp, att=att, ws=self._conv_ws(qx, c2, ksize, stride, padding),
@@ -495,7 +513,8 @@ class LayerCalibrator:
         if dist.world > 1:
             dist.all_reduce_sum(self.sse)
         main.wait_stream(self._side)               # every factorisation (also an unused last one) is ordered before the read-back
-        alpha_w = self.st.a_w_tensor().clone()     # LAST iterate's scale (reference quirk, :158)
+        # LAST iterate's scale (reference quirk, :158); per channel: the [C2] vector of the last iterate
+        alpha_w = pc[:c2].clone() if channel_wise else self.st.a_w_tensor().clone()
         s = self.st.read()                          # the layer's one result read-back
         final_sse = float(self.sse.item())
         if any(int(i.item()) != 0 for i in infos):
@@ -520,8 +539,11 @@ class LayerCalibrator:
             rep.alpha_act, rep.act_passes = float(xs["a"]), xs["passes"]
             if xs["failed"]:
                 raise RuntimeWarning(f"Exceed maximum iteration ({qlvl_act * 100}) for alpha optimization in var_init_iter")
-        ws_ = self.wstate.read()
-        if ws_["failed"]:
+        if channel_wise:
+            rep.alpha_w = float(alpha_w.mean().item())
+            if any(r_["failed"] for r_ in wrows.read()):
+                raise RuntimeWarning(f"Exceed maximum iteration ({qlvl_w * 100}) for alpha optimization in var_init_iter")
+        elif self.wstate.read()["failed"]:
             raise RuntimeWarning(f"Exceed maximum iteration ({qlvl_w * 100}) for alpha optimization in var_init_iter")
         if self.keep_history:
             rep.history = hist.cpu().tolist()

@@ -112,6 +112,28 @@ class ScaleState:
         self.buf[:8].view(torch.float64).fill_(a)
 
 
+class ScaleStateRows:
+    """Array of ``effq_scale_state``, one per output channel (per-output-channel weight scales)."""
+
+    def __init__(self, device, rows: int):
+        self.rows = rows
+        self.buf = torch.zeros(rows * capi.SCALE_STATE_BYTES, dtype=torch.uint8, device=device)
+
+    @property
+    def p(self):
+        return ptr(self.buf)
+
+    def read(self):
+        """[rows] dicts; a host sync."""
+        raw = self.buf.cpu().numpy().tobytes()
+        n = capi.SCALE_STATE_BYTES
+        out = []
+        for r in range(self.rows):
+            a, a_prev, s_bv, s_bb, passes, conv, failed, _ = struct.unpack(ScaleState.FMT, raw[r * n:(r + 1) * n])
+            out.append(dict(a=a, passes=passes, converged=conv, failed=failed))
+        return out
+
+
 class AdmmState:
     """Device copy of ``effq_admm_state``."""
     FMT = "<dffiiffif"
@@ -260,6 +282,22 @@ def scale_search(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: Scale
     return state
 
 
+def scale_search_rows(v1: torch.Tensor, nlvl: int, lo: float, hi: float, states: ScaleStateRows,
+                      v2: Optional[torch.Tensor] = None) -> ScaleStateRows:
+    """One independent project_by_iter per ROW of the 2-D view v1 (+ v2): per-output-channel weight scales."""
+    if v1.dim() != 2 or v1.stride(1) != 1 or v1.dtype != torch.float32 or not v1.is_cuda:
+        raise EffqError("scale_search_rows: expected a 2-D CUDA float32 view with unit column stride")
+    rows, cols = v1.shape
+    if v2 is not None and (tuple(v2.shape) != (rows, cols) or not v2.is_contiguous()):
+        raise EffqError("scale_search_rows: v2 must be contiguous with v1's shape")
+    if states.rows != rows:
+        raise EffqError("scale_search_rows: one state per row")
+    timer.run(f"scale_search_rows_{rows}x{cols}", {"pass_bytes": 8 * rows * cols}, lambda: check(
+        capi.load().effq_scale_search_rows(ptr(v1), v1.stride(0), ptr(v2), cols, rows, cols, int(nlvl), float(lo), float(hi),
+                                           states.p, stream()), "effq_scale_search_rows"))
+    return states
+
+
 def scale_partial(v1: torch.Tensor, nlvl: int, lo: float, hi: float, state: ScaleState, mode: int,
                   sums: torch.Tensor, ws: torch.Tensor, v2: Optional[torch.Tensor] = None) -> None:
     rows, cols, ld1, ld2 = _pair_view(v1, v2)
@@ -304,9 +342,10 @@ def conv3d_tc_supported(x_shape, c2, ksize, stride, padding, code_dtype: int = C
 
 
 def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, c2: int, ksize, want_out=True,
-              target=None, att=None, ws=None, sse=None):
+              target=None, att=None, ws=None, sse=None, scale_vec=None):
     """tcgen05 conv on codes.  xcodes (N,D,H,W,C1) bf16 or e4m3; wcodes of the same type in the
-    tensor-core weight layout (pack_weight_codes / admm_project)."""
+    tensor-core weight layout (pack_weight_codes / admm_project).  ``scale_vec`` ([C2] fp32): one scale per output
+    channel instead of the scalar ``conv_scale_ptr``."""
     cdt = code_dtype_of(xcodes)
     if wcodes.dtype != xcodes.dtype:
         raise EffqError("conv3d_tc: activation and weight codes must have the same element type")
@@ -331,6 +370,14 @@ def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, 
     flops = 2.0 * n * d * h * w * c2 * c1 * g.taps
     nbytes = (xcodes.numel() + wcodes.numel()) * xcodes.element_size() + n * d * h * w * c2 * 4 * ((target is not None) + (out is not None))
     name = f"conv3d_tc_c{c1}x{c2}k{k[0]}" + ("_e4m3" if cdt == CODE_E4M3 else "")
+    if scale_vec is not None:
+        sv = _f32c(scale_vec, "scale_vec")
+        if sv.numel() != c2:
+            raise EffqError("conv3d_tc: scale_vec needs one entry per output channel")
+        timer.run(name, {"flops": flops, "bytes": nbytes}, lambda: check(
+            lib.effq_conv3d_tc_pc(ptr(xcodes), ptr(wcodes), cdt, ptr(b), ptr(sv), C.byref(g), ptr(out), ptr(target), ptr(att),
+                                  ptr(sse), ptr(ws), stream()), "effq_conv3d_tc_pc"))
+        return out, sse
     timer.run(name, {"flops": flops, "bytes": nbytes}, lambda: check(
         lib.effq_conv3d_tc(ptr(xcodes), ptr(wcodes), cdt, ptr(b), cs, C.byref(g), ptr(out), ptr(target), ptr(att),
                            ptr(sse), ptr(ws), stream()), "effq_conv3d_tc"))
@@ -554,15 +601,17 @@ def admm_lhs(a0, rho: float, eta: float, has_bias: bool, out):
 
 def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], nlvl_w: int, nlvl_a: int,
                  c2: int, c1: int, taps: int, has_bias: bool, dual_div: float, g_out, bstar_out, wcodes_out,
-                 st: AdmmState, next_rhs=None, keep=None):
+                 st: AdmmState, next_rhs=None, keep=None, per_channel_out=None):
     """``next_rhs`` = (b0, w0p, rho_next, eta, planes): also emit the next iteration's right-hand side
     as split planes (replaces the next admm_rhs launch).  ``keep`` = (best_g, best_b, best_wcodes): save the
     previous iterate (still in g_out / bstar_out / wcodes_out) first if the step that scored it made it the best."""
     kp_ = None
     if keep is not None:
-        bg, bb, bw = keep
+        bg, bb, bw = keep[:3]
+        bpc = keep[3] if len(keep) > 3 else None
         kp_ = C.byref(capi.AdmmKeep(bg.data_ptr(), bb.data_ptr() if bb is not None else None,
-                                    bw.data_ptr() if bw is not None else None))
+                                    bw.data_ptr() if bw is not None else None,
+                                    bpc.data_ptr() if bpc is not None else None))
     ldw = wstar.stride(0)
     nx = None
     if next_rhs is not None:
@@ -572,7 +621,7 @@ def admm_project(wstar, dual, wstate: ScaleState, xstate: Optional[ScaleState], 
                                         int(nlvl_w), int(nlvl_a), c2, c1, taps, int(has_bias), float(dual_div),
                                         ptr(g_out), ptr(bstar_out), ptr(wcodes_out),
                                         code_dtype_of(wcodes_out) if wcodes_out is not None else 0, st.p, nx, kp_,
-                                        stream()),
+                                        ptr(per_channel_out), stream()),
           "effq_admm_project")
 
 
@@ -582,10 +631,10 @@ def admm_decide(st: AdmmState, sse, numel: float, history, comm=None):
     check(capi.load().effq_admm_decide(st.p, ptr(sse), float(numel), ptr(history), comm, stream()), "effq_admm_decide")
 
 
-def admm_keep(st: AdmmState, g, bstar, best_g, best_b, aux_src=None, aux_dst=None):
+def admm_keep(st: AdmmState, g, bstar, best_g, best_b, aux_src=None, aux_dst=None, pc_src=None, pc_dst=None):
     nb = aux_src.numel() * aux_src.element_size() if aux_src is not None else 0
     check(capi.load().effq_admm_keep(st.p, ptr(g), ptr(bstar), g.numel(), g.shape[0], ptr(best_g), ptr(best_b),
-                                     ptr(aux_src), ptr(aux_dst), nb, stream()), "effq_admm_keep")
+                                     ptr(aux_src), ptr(aux_dst), nb, ptr(pc_src), ptr(pc_dst), stream()), "effq_admm_keep")
 
 
 def admm_track(st: AdmmState, sse, numel: float, g, bstar, best_g, best_b, history, aux_src=None, aux_dst=None,

@@ -93,8 +93,13 @@ class PTQConv(nn.Conv3d):
         raise NotImplementedError
 
     # -- integer export (PTQConv.py:125-152) -------------------------------------------------
-    def store_int_weight(self):
+    def _aw(self):
+        """alpha_w broadcast over the weight: a scalar (reference) or one value per output channel (extension)."""
         a = self.alpha_w.data
+        return a.view(-1, 1, 1, 1, 1) if a.dim() == 1 else a
+
+    def store_int_weight(self):
+        a = self._aw().to(self.weight.device)
         b = self.weight.data / a
         delta = 2 / (self.qlvl_w - 1)
         w_int = torch.round((b + 1) / delta)
@@ -105,7 +110,7 @@ class PTQConv(nn.Conv3d):
     def restore_fp_weight(self):
         self._wcodes_by_dtype = self._wcodes_cache = self._dgrad_cache = None
         delta = 2 / (self.qlvl_w - 1)
-        self.weight.data = self.alpha_w.data * (self.weight.data.float() * delta - 1)
+        self.weight.data = self._aw().to(self.weight.device) * (self.weight.data.float() * delta - 1)
 
     # -- forward dispatch (PTQConv.py:154-174) ------------------------------------------------
     def _conv(self, x):
@@ -128,8 +133,28 @@ class PTQConv(nn.Conv3d):
         if self._wcodes_cache is None or self._wcodes_cache[0] != key:
             w = self.weight.data.float()
             lm1 = float(self.qlvl_w - 1)
-            wmax = w.abs().max()
             found = None
+            if getattr(self, "channel_wise", False):
+                # one grid per output channel: every row is tested against the candidates, rows may differ in theirs
+                c2 = w.shape[0]
+                wr = w.reshape(c2, -1)
+                wmax = wr.abs().max(1, keepdim=True).values
+                a_vec = torch.zeros_like(wmax)
+                codes = torch.zeros_like(wr)
+                done = wmax.squeeze(1) == 0                     # an all-zero row has no scale: codes stay 0 -> reject below
+                ok_rows = torch.zeros(c2, dtype=torch.bool, device=w.device)
+                for k in range(self.qlvl_w - 1, max(self.qlvl_w - 9, 0), -2):
+                    a = wmax * (lm1 / k)
+                    cd = torch.round(wr / a.clamp_min(1e-30) * lm1)
+                    good = ((torch.remainder(cd + lm1, 2.0) == 0).all(1) &
+                            ((cd * (a / lm1) - wr).abs().max(1).values <= 1e-6 * wmax.squeeze(1))) & ~ok_rows & ~done
+                    a_vec[good], codes[good] = a[good], cd[good]
+                    ok_rows |= good
+                if bool(ok_rows.all().item()):
+                    found = (ops.pack_weight_codes(codes.view_as(w), code_dtype), a_vec.reshape(-1).clone(), codes.view_as(w))
+                self._wcodes_cache = self._wcodes_by_dtype[code_dtype] = (key, found)
+                return self._wcodes_cache[1]
+            wmax = w.abs().max()
             for k in range(self.qlvl_w - 1, max(self.qlvl_w - 9, 0), -2):     # largest |code| present: L-1, L-3, ...
                 a = wmax * (lm1 / k)
                 codes = torch.round(w / a * lm1)
@@ -174,9 +199,10 @@ class PTQConv(nn.Conv3d):
                 else:
                     xcodes = ops.quantize_act_ndhwc(x, self.qlvl_act, alpha=self.alpha_act.data)
                 scale = (self.alpha_act.data.double() / (self.qlvl_act - 1) *
-                         w_scale.double() / (self.qlvl_w - 1)).float().reshape(1)
+                         w_scale.double() / (self.qlvl_w - 1)).float().reshape(-1)
                 out, _ = ops.conv3d_tc(xcodes, wcodes, self.bias.data if self.bias is not None else None,
-                                       scale, self.out_channels, self.kernel_size, want_out=True)
+                                       scale[:1], self.out_channels, self.kernel_size, want_out=True,
+                                       scale_vec=scale if scale.numel() > 1 else None)
                 return out
         qact = self._quantize_act(x) if self.q_act else x
         return self._conv(qact)
@@ -207,6 +233,9 @@ class EfficientQConv(PTQConv):
         self.lwq_iter, self.lwq_rho, self.lwq_rho_max, self.lwq_eta = 200, 10, 1000, 1   # EfficientQConv.py:23-26
         self.lwq_fold_bn = True
         self.lwq_verbose = kwQ.get("lwq_verbose", False)
+        # optional extension (north star: "weights per output channel"): one alpha_w per output channel.  The
+        # reference's live path is per-tensor (PTQConv.py:26-27) and that stays the default
+        self.channel_wise = bool(kwQ.get("lwq_channel_wise", False))
         self.mask_pyramid = None
         self.layer_loss = None
         self.report = None
@@ -235,7 +264,7 @@ class EfficientQConv(PTQConv):
         w, b, a_w, a_act, out_q, rep = self._engine(x.device).run(
             x, self.weight.data, self.bias.data if self.bias is not None else None, out_fp,
             self.stride, self.padding, self.qlvl_w, self.qlvl_act, self.q_act, self.mask_pyramid,
-            name=self.name or "")
+            name=self.name or "", channel_wise=self.channel_wise)
         self.weight.data = w.clone()
         self._wcodes_by_dtype = self._wcodes_cache = self._dgrad_cache = None    # keyed by address + version: drop
         if self.bias is not None:

@@ -175,6 +175,10 @@ int64_t effq_conv3d_tc_workspace(const effq_geom* g);
 int effq_conv3d_tc(const void* xcodes_ndhwc, const void* wcodes, int32_t code_dtype, const float* bias,
                    const float* conv_scale, const effq_geom* g, float* out, const float* target,
                    const float* att, double* sse, void* workspace, void* stream);
+/* One scale per OUTPUT CHANNEL (scale_vec[C2], device): the per-output-channel weight-scale extension. */
+int effq_conv3d_tc_pc(const void* xcodes_ndhwc, const void* wcodes, int32_t code_dtype, const float* bias,
+                      const float* scale_vec, const effq_geom* g, float* out, const float* target,
+                      const float* att, double* sse, void* workspace, void* stream);
 
 /* [C2][C1][taps] fp32 integer weight codes (values 2c-(L-1)) -> codes of `code_dtype` in the
  * layout effq_conv3d_tc consumes (the same layout effq_admm_project emits). */
@@ -287,12 +291,20 @@ typedef struct effq_admm_keep_bufs {
   float* best_g;        /* [C2][K]  */
   float* best_b;        /* [C2] or NULL */
   void*  best_wcodes;   /* same size / type as wcodes_out, or NULL */
+  float* best_pc;       /* [2*C2] per-channel scales of the best iterate (per_channel_out), or NULL */
 } effq_admm_keep_bufs;
 int effq_admm_project(const float* wstar, int64_t ldw, float* dual, const effq_scale_state* wscale,
                       const effq_scale_state* xscale, int32_t nlvl_w, int32_t nlvl_a, int32_t c2,
                       int32_t c1, int32_t taps, int32_t has_bias, float dual_div, float* g_out,
                       float* bstar_out, void* wcodes_out, int32_t code_dtype, effq_admm_state* st,
-                      const effq_next_rhs* next, const effq_admm_keep_bufs* keep, void* stream);
+                      const effq_next_rhs* next, const effq_admm_keep_bufs* keep, float* per_channel_out,
+                      void* stream);
+/* per_channel_out != NULL selects per-OUTPUT-CHANNEL weight scales (optional extension `lwq_channel_wise`; the
+ * reference's live path is per-tensor, PTQConv.py:26-27): wscale is then an array of C2 states filled by
+ * effq_scale_search_rows, and per_channel_out[0..C2) receives fp32(a_w) of every channel, [C2..2*C2) the conv
+ * scale a_x * a_w[c] / ((La-1)(Lw-1)) that effq_conv3d_tc_pc applies per output channel. */
+int effq_scale_search_rows(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows, int64_t cols,
+                           int32_t nlvl, float lo, float hi, effq_scale_state* states, void* stream);
 /* The two halves of effq_admm_track as launches of their own.  effq_admm_decide: loss = fp32(sse/numel)
  * (sse all-reduced in-kernel when comm != NULL), history[iter] = loss, best-iterate bookkeeping, st->take_.
  * effq_admm_keep: copy G, b* (and aux) to the best-iterate buffers if st->take_ (after the loop's last iterate). */
@@ -300,7 +312,7 @@ int effq_admm_decide(effq_admm_state* st, const double* sse, double numel, float
                      const effq_peer_comm* comm, void* stream);
 int effq_admm_keep(effq_admm_state* st, const float* g, const float* bstar, int64_t g_numel, int32_t c2,
                    float* best_g, float* best_b, const void* aux_src, void* aux_dst, int64_t aux_bytes,
-                   void* stream);
+                   const float* pc_src, float* pc_dst, void* stream);
 /* loss = fp32(sse/numel); history[iter] = loss; if (iter==0 || loss < best) keep G, b*
  * (and, when aux_bytes > 0, the 16B-aligned side buffer aux_src -> aux_dst, e.g. the
  * tensor-core weight codes of the same iterate). */

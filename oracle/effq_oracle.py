@@ -249,7 +249,8 @@ def admm_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
                out_fp: torch.Tensor, stride, padding, qlvl_w: int, qlvl_act: int,
                q_act: bool = True, mask_pyramid=None, n_iter: int = 200,
                rho0: float = 10.0, rho_max: float = 1000.0, eta0: float = 1.0,
-               rho_period: int = 50, keep_qact: bool = False, timers: Optional[dict] = None) -> LayerResult:
+               rho_period: int = 50, keep_qact: bool = False, timers: Optional[dict] = None,
+               channel_wise: bool = False) -> LayerResult:
     """One layer of EfficientQ calibration, EfficientQConv.py:33-166.
 
     Quirks reproduced on purpose: best iterate picked by strict ``<`` on the
@@ -257,6 +258,9 @@ def admm_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     comes from the LAST iterate while the weights come from the best one
     (:155-158); rho doubles after iterations 0, 50, 100, ... with the dual
     halved (:129-137); the logged loss is attention-weighted (:161-166).
+
+    ``channel_wise`` (extension, not in the reference's live path): the projection runs the reference's
+    project_by_iter on every output channel's row of w* + dual separately; alpha_w is then a [C2] tensor.
     """
     import time as _time
 
@@ -303,8 +307,14 @@ def admm_layer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
         if bias is not None:
             b_star = b_star_new
         t_ = _time.perf_counter()
-        a_w, b_w = project_by_iter(w_star + dual, qlvl_w, -1, 1)
-        g = a_w * b_w
+        if channel_wise:
+            v = w_star + dual
+            rows = [project_by_iter(v[r], qlvl_w, -1, 1) for r in range(v.shape[0])]
+            a_w = torch.tensor([a for a, _ in rows], dtype=torch.float64)
+            g = torch.stack([a * b for a, b in rows])
+        else:
+            a_w, b_w = project_by_iter(w_star + dual, qlvl_w, -1, 1)
+            g = a_w * b_w
         dual = w_star - g + dual
         _tick("w_project", t_)
         t_ = _time.perf_counter()

@@ -127,6 +127,79 @@ def test_conv_free_scoring_matches_conv_scoring(engine_mod, golden, name, monkey
     assert float(aw1) == float(aw0)
 
 
+@pytest.mark.parametrize("name", ["w4a4_k3_c32", "w4a4_k3", "w4a4_k1_c64"])
+def test_per_output_channel_weight_scales(engine_mod, golden, name):
+    """Extension `w_per_channel` (north star: "weights per output channel"; the reference is per-tensor): every output
+    channel's row of w* + dual gets its own project_by_iter.  Checked against the oracle's restatement with the same
+    per-row projection: first iterate, the per-channel scales after 20 iterations, the layer output recomputed by
+    the oracle's conv from the GPU's weights; and it must not be worse than the per-tensor calibration."""
+    import torch.nn.functional as F
+    from oracle import effq_oracle as O
+    g = golden("layers_wide.npz" if name in WIDE else "layers.npz")
+    k, s, p, lw, la, qa = [int(t) for t in g[f"{name}_cfg"]]
+    x, w, b, y, att = [torch.from_numpy(g[f"{name}_{t}"]) for t in ("x", "w", "b", "y", "att")]
+    n_it = 20
+    ref = O.admm_layer(x, w, b, y, s, p, lw, la, bool(qa), [att], n_iter=n_it, channel_wise=True, keep_qact=True)
+    eng = engine_mod.LayerCalibrator(torch.device(DEV), n_iter=n_it, keep_history=True)
+    dv = [t.to(DEV) for t in (x, w, b, y, att)]
+    wq, bq, a_w, a_act, out_q, rep = eng.run(dv[0], dv[1], dv[2], dv[3], s, p, lw, la, bool(qa), [dv[4]], name=name,
+                                             channel_wise=True)
+    assert a_w.shape == (w.shape[0],)
+    hist = np.array(rep.history[:n_it])
+    print(name, "iterate 0", hist[0], ref.loss_history[0], "final", rep.final_loss, ref.final_loss)
+    # one fixed-point search per row: every row has its own chance that the 1e-5 stopping rule of project_by_iter
+    # ends a pass earlier or later under fp32 solve noise (tests/test_gpu_parity.py::test_one_step_ahead), so the
+    # first iterate agrees to ~1e-3 here, not to the 2e-4 of the per-tensor search
+    assert abs(hist[0] - ref.loss_history[0]) <= 3e-3 * ref.loss_history[0]
+    assert abs(rep.final_loss - ref.final_loss) <= 2e-2 * ref.final_loss
+    # every row of the returned weights lies on its own L-level grid, and the output is conv(qact, W, b) of exactly these
+    wq_c = wq.cpu()
+    assert all(torch.unique(wq_c[r]).numel() <= lw for r in range(wq_c.shape[0]))
+    out_o = F.conv3d(ref.qact, wq_c, bq.cpu(), s, p)
+    assert float((out_q.cpu() - out_o).abs().max() / out_o.abs().max()) <= 1e-5
+    # per-channel scales can only help the projection: not worse than per-tensor on the same layer (5 % slack: 20 iterations)
+    eng2 = engine_mod.LayerCalibrator(torch.device(DEV), n_iter=n_it, keep_history=True)
+    _, _, _, _, _, rep_t = eng2.run(dv[0], dv[1], dv[2], dv[3], s, p, lw, la, bool(qa), [dv[4]], name=name)
+    print("per-channel", rep.final_loss, "per-tensor", rep_t.final_loss)
+    assert rep.final_loss <= 1.05 * rep_t.final_loss
+
+
+def test_per_channel_module_roundtrip(engine_mod):
+    """Module level: calibrate with lwq_channel_wise, alpha_w becomes [C2]; store_int_weight / restore_fp_weight round
+    trip; the deployment forward (tcgen05 conv with one scale per output channel) equals conv(quantize_act(x), W)."""
+    import torch.nn.functional as F
+    from efficientq_b200.qconv import EfficientQConv
+    from oracle import effq_oracle as O
+    torch.manual_seed(3)
+    c1, c2 = 32, 32
+    m = EfficientQConv(c1, c2, 3, 1, 1, bias=True, q_weight=True, qlvl=16, q_act=True, qlvl_act=16, lwq_channel_wise=True)
+    m.lwq_iter = 10
+    x = torch.relu(torch.randn(2, c1, 8, 16, 8)) * 1.1
+    y = F.conv3d(x, m.weight.data, m.bias.data, 1, 1)
+    m.to(DEV)
+    m.name, m.layer_loss, m.output_fp = "pc", [], y.to(DEV)
+    m.set_quantizing()
+    with torch.no_grad():
+        out_cal = m(x.to(DEV))
+    assert m.alpha_w.shape == (c2,)
+    wq = m.weight.data.clone()
+    m.set_quantized()
+    with torch.no_grad():
+        out_dep = m(x.to(DEV))
+    assert m._wcodes_cache[1] is not None and m._wcodes_cache[1][1].numel() == c2        # tcgen05 path, per-channel grid
+    want = F.conv3d(O.quantize_act(x, m.alpha_act.data.cpu(), 16).double(), wq.cpu().double(), m.bias.data.cpu().double(), 1, 1).float()
+    torch.testing.assert_close(out_dep.cpu(), want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out_cal.cpu(), want, rtol=1e-5, atol=1e-5)
+    # integer export with per-channel scales.  alpha_w is the LAST iterate's scale (reference quirk), the weights the
+    # best iterate's: re-derive the grid from the weights for an exact round trip
+    m.alpha_w.data = m._wcodes_cache[1][1].clone()
+    m.cpu()
+    m.store_int_weight()
+    assert m.weight.data.dtype == torch.uint8 and int(m.weight.data.max()) <= 15
+    m.restore_fp_weight()
+    torch.testing.assert_close(m.weight.data, wq.cpu(), rtol=1e-6, atol=1e-7)
+
+
 def build_toy(task="brats"):
     from efficientq_b200 import model_blk, qconv
     from tests.golden.make_golden import TOY, TOY_LITS

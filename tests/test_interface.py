@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = json.load(open(os.path.join(ROOT, "tests", "golden", "interface.json")))
-EXTENSIONS = {"tune_act_iter"}                     # flags this package adds
+EXTENSIONS = {"tune_act_iter", "w_per_channel"}                     # flags this package adds
 
 
 def test_command_line_equals_reference_parser():

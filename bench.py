@@ -283,7 +283,24 @@ def run_ours(args, wl, wl_name):
     h2d = host_batch.numel() * 4
     d2h_box = [0]
 
+    # per-layer timeline of every step: CUDA events on the main stream + host seconds around each quantizer module's
+    # ptq() (22 event pairs per step: negligible) -- the `layers` table of the JSON line
+    from efficientq_b200.qconv import EfficientQConv
+    layer_log = []
+    _ptq = EfficientQConv.ptq
+
+    def _timed_ptq(self, x):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
+        a.record()
+        out = _ptq(self, x)
+        b.record()
+        layer_log.append((self.name, a, b, time.perf_counter() - h0))
+        return out
+    EfficientQConv.ptq = _timed_ptq
+
     def one_step(timed):
+        layer_log.clear()
         model.load_state_dict(fp_state, strict=False)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
@@ -333,6 +350,8 @@ def run_ours(args, wl, wl_name):
     torch.cuda.synchronize()
     dist.barrier()
     wall = time.time() - w0
+    layers_tbl = [{"layer": n_, "gpu_ms": round(a_.elapsed_time(b_), 2), "host_ms": round(1e3 * h_, 2)}
+                  for n_, a_, b_, h_ in layer_log]                  # the last timed step
     clocks = sampler.stop() if dist.rank == 0 else None
     ops.timer.enabled = False
     launches = capi.launch_count()
@@ -428,6 +447,7 @@ def run_ours(args, wl, wl_name):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_box[0],
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "layers": layers_tbl,
             "kernels": kern, "kernels_note": "CUDA events around every major kernel in ONE instrumented step outside the timed "
                                              "region; `roofline` is the dominant kernel timed live inside the timed region",
             "ranks_hold_identical_weights": ranks_identical,

@@ -107,6 +107,12 @@ _SIGS = {
                                       C.c_void_p]),
     "effq_gram_tc_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_gram_tc_accumulate2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "effq_gram_tc_dual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "effq_gram_tc_rows_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom), C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "effq_gram_tc_supported": (C.c_int, [C.POINTER(Geom)]),
     "effq_gram_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Geom),
                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -261,6 +261,81 @@ extern "C" int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_sca
   return 0;
 }
 
+// ---- one pass for both the attention-weighted normal equations and the UNWEIGHTED Gram --------------------
+namespace effq {
+// rows [row_begin, row_end) of the tcgen05 accumulator as fp64 in real units, mirrored (see gram_finalize_kernel)
+__global__ void gram_finalize_rows_f64_kernel(const double* __restrict__ acc64, const float* __restrict__ x_scale,
+                                              int k, int kp, int c1, int row_begin, int row_end,
+                                              double* __restrict__ out) {
+  const double s = x_scale ? (double)__ldg(x_scale) : 1.0;
+  const long long total = (long long)(row_end - row_begin) * kp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = row_begin + (int)(e / kp), j = (int)(e % kp);
+    const long long o = (long long)i * kp + j;
+    if (i < k && j < k) {
+      const int ti = (i % 27) * c1 + i / 27, tj = (j % 27) * c1 + j / 27;
+      const bool skipped = (ti / 128) * 128 >= (tj / 256 + 1) * 256;
+      out[o] = s * s * acc64[skipped ? (long long)j * kp + i : o];
+      continue;
+    }
+    // bias row / column of the unweighted block: the column (rows < K) comes from the raw-code x ones-column
+    // products, the row (i == K) from the unweighted ones row; Y rows: as accumulated
+    out[o] = (i < k ? s : 1.0) * (j < k ? s : 1.0) * acc64[o];
+  }
+}
+}  // namespace effq
+
+// A0, B0 (fp32, as effq_gram_tc) AND the unweighted S = X^ X^T (K' x K', fp64, real units) from ONE pass over the
+// codes: the conv-free scoring of the ADMM iterates needs S, and a second full Gram pass would double the cost.
+// workspace: 2 * effq_gram_workspace bytes.
+extern "C" int effq_gram_tc_dual(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y,
+                                 const float* att, const effq_geom* g, int32_t att_exact, float* a0_out,
+                                 float* b0_out, double* s_unweighted_out, void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && code_scale && y && g && a0_out && b0_out && s_unweighted_out && workspace,
+                 "null pointer");
+  EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
+  const int k = g->c1 * 27, kp = k + 1, mrows = kp + g->c2;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t acc_bytes = ((size_t)mrows * kp * 8 + 16 + 255) & ~(size_t)255;
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, 2 * acc_bytes, s));
+  double* acc = (double*)workspace;
+  double* acc2 = (double*)((char*)workspace + acc_bytes);
+  if (int rc = effq_gram_tc_accumulate2(xcodes_ndhwc_bf16, att, y, g, 1, att_exact, acc, kp,
+                                        (char*)workspace + (size_t)mrows * kp * 8, acc2, 0, stream)) return rc;
+  const long long total = (long long)mrows * kp;
+  int fb = (int)((total + 255) / 256);
+  if (fb > sm_count() * 16) fb = sm_count() * 16;
+  gram_finalize_kernel<<<fb, 256, 0, s>>>(acc, code_scale, k, kp, g->c2, g->c1, a0_out, b0_out);
+  EFFQ_LAUNCH_CHECK();
+  gram_finalize_rows_f64_kernel<<<fb, 256, 0, s>>>(acc2, code_scale, k, kp, g->c1, 0, kp, s_unweighted_out);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// T = Y X^T (C2 x K', fp64, real units, UNWEIGHTED) for a new target y (the residual of a reference iterate): only
+// the extra row block of the tcgen05 Gram kernel runs.  t_out: rows K'.. of the [(K'+C2) x K'] statistics matrix
+// (pass its base pointer; rows [K', K'+C2) are written).  workspace: effq_gram_workspace bytes.
+extern "C" int effq_gram_tc_rows_f64(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y,
+                                     const effq_geom* g, double* stats_base, void* workspace, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && code_scale && y && g && stats_base && workspace, "null pointer");
+  EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
+  const int k = g->c1 * 27, kp = k + 1, mrows = kp + g->c2;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t acc_bytes = (size_t)mrows * kp * 8;
+  EFFQ_CUDA(cudaMemsetAsync(workspace, 0, acc_bytes + 16, s));
+  if (int rc = effq_gram_tc_accumulate2(xcodes_ndhwc_bf16, nullptr, y, g, 1, 1, (double*)workspace, kp,
+                                        (char*)workspace + acc_bytes, nullptr, 1, stream)) return rc;
+  const long long total = (long long)g->c2 * kp;
+  int fb = (int)((total + 255) / 256);
+  if (fb > sm_count() * 16) fb = sm_count() * 16;
+  gram_finalize_rows_f64_kernel<<<fb, 256, 0, s>>>((const double*)workspace, code_scale, k, kp, g->c1, kp, mrows, stats_base);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- sufficient statistics for scoring WITHOUT re-running the conv ------------------------------
 // For a layer whose input is not quantised (conv0, final_cls: q_first/q_last = 256,-1) the conv
 // input is the same tensor in all 200 ADMM iterations, so

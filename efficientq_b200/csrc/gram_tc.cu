@@ -65,6 +65,9 @@ struct GtParams {
   long long hb_total;          // n*d*hb_h*hb_w
   long long hb_per_split;
   int single;                  // att * code exact in bf16: one term for the weighted codes (no lo plane / MMA)
+  double* acc2;                // optional second workspace: the UNWEIGHTED Gram of the codes (and their column sums),
+                               // accumulated by the same pass in a second TMEM accumulator (raw codes as left operand)
+  int mb_begin;                // first row block to compute (rows-only passes start at the extra-row block)
   int p_tma;                   // right operand by TMA
   int pblk;                    // rows per right-operand block (64: SWIZZLE_128B, 32: SWIZZLE_64B)
 };
@@ -142,8 +145,8 @@ __device__ __forceinline__ uint64_t gt_desc(uint32_t saddr, uint32_t lbo_bytes, 
 //   kind 0: zero padding
 // The patch x patch part of S is symmetric: a (128-row, 256-column) tile that lies entirely
 // below the diagonal is not computed; the finalize pass mirrors it from its transpose.
-__device__ __host__ __forceinline__ bool gt_tile_skipped(int mb, int nb, int mx0) {
-  return mb * GT_BM < mx0 && mb * GT_BM >= (nb + 1) * GT_BN;
+__device__ __host__ __forceinline__ bool gt_tile_skipped(int mb, int nb, int mx0, int mb_begin = 0) {
+  return mb < mb_begin || (mb * GT_BM < mx0 && mb * GT_BM >= (nb + 1) * GT_BN);
 }
 
 // Coordinates of an 8x8 voxel block; `next` walks blocks in linear order without divisions (the
@@ -237,7 +240,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
   }
   if (warp == GT_BUILDERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem_u32(&tmem_slot)),
-                 "r"(256u) : "memory");
+                 "r"(p.acc2 ? 512u : 256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,9 +277,10 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
       for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
         int z, nb_, mb_;
         gt_decode(item, p, z, nb_, mb_);
-        if (gt_tile_skipped(mb_, nb_, p.mx0)) continue;
+        if (gt_tile_skipped(mb_, nb_, p.mx0, p.mb_begin)) continue;
         const bool three = mb_ * GT_BM >= p.mx0;                                            // y / ones rows: 3-term split
         const bool two = three || !p.single;                                                // weighted codes: hi + lo unless exact
+        const bool dual = p.acc2 != nullptr && !three;                                      // patch rows: + the unweighted Gram
         long long hb0 = (long long)z * p.hb_per_split;
         long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
         if (!gt_mbar_wait(TEMPTY, tphase ^ 1u, abort_flag)) { ok = false; break; }
@@ -295,6 +299,9 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
               gt_mma(tmem_base, tmpl | (uint64_t)((zhi + koff) & 0x3fffu), bd, idesc, ks == 0 ? accum : 1u);
               if (two) gt_mma(tmem_base, tmpl | (uint64_t)((zlo + koff) & 0x3fffu), bd, idesc, 1u);
               if (three) gt_mma(tmem_base, tmpl | (uint64_t)((zl2 + koff) & 0x3fffu), bd, idesc, 1u);
+              // raw codes (in the plane the weighted split does not use: lo when single, else the third) x raw codes
+              if (dual) gt_mma(tmem_base + 256u, tmpl | (uint64_t)(((p.single ? zlo : zl2) + koff) & 0x3fffu), bd, idesc,
+                               ks == 0 ? accum : 1u);
             }
             gt_commit(EMPTY(stage));
             if (hb == hb1 - 1) gt_commit(TFULL);
@@ -317,7 +324,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
       for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
         int z, nb, mb_;
         gt_decode(item, p, z, nb, mb_);
-        if (gt_tile_skipped(mb_, nb, p.mx0)) continue;
+        if (gt_tile_skipped(mb_, nb, p.mx0, p.mb_begin)) continue;
         int n_live = (p.k - nb * GT_BN) / p.pblk;                    // blocks of this tile below row K
         n_live = n_live < 0 ? 0 : (n_live > GT_BN / p.pblk ? GT_BN / p.pblk : n_live);
         long long hb0 = (long long)z * p.hb_per_split;
@@ -364,7 +371,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
     for (long long item = blockIdx.x; item < n_items && ok; item += gridDim.x) {
       int z, nb, mb;
       gt_decode(item, p, z, nb, mb);
-      if (gt_tile_skipped(mb, nb, p.mx0)) continue;
+      if (gt_tile_skipped(mb, nb, p.mx0, p.mb_begin)) continue;
       Slot zs[GT_ZS], ps[GT_PS];
 #pragma unroll
       for (int i = 0; i < GT_ZS; ++i) zs[i] = make_slot(mb * GT_BM, rc_base + GT_RCS * i, kvox, p, true);
@@ -433,7 +440,10 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
               pr[2 * e] = __uint_as_float(wds[e] << 16) * aw;
               pr[2 * e + 1] = __uint_as_float(wds[e] & 0xffff0000u) * aw;
             }
-            if (kind == 2) pr[0] = aw;                   // ones row: att_v * 1 (aw is 0 for dead voxels)
+            if (kind == 2) {
+              pr[0] = aw;                                // ones row: att_v * 1 (aw is 0 for dead voxels)
+              if (p.acc2) pr[1] = vlive ? 1.f : 0.f;     // + an UNWEIGHTED ones row: column sums of the codes, voxel count
+            }
           }
           uint32_t hi[4], lo[4], l2[4];
 #pragma unroll
@@ -451,6 +461,9 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
           *reinterpret_cast<uint4*>(sbase + zs[i].dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (!(single && mb_patch)) *reinterpret_cast<uint4*>(sbase + GT_ZBYTES + zs[i].dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           if (kind >= 2) *reinterpret_cast<uint4*>(sbase + 2 * GT_ZBYTES + zs[i].dst) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+          // unweighted pass riding along: the raw codes of a patch row block (zero for padding / rows behind K)
+          if (p.acc2 && mb_patch)
+            *reinterpret_cast<uint4*>(sbase + (single ? GT_ZBYTES : 2 * GT_ZBYTES) + zs[i].dst) = kind == 1 ? zv[i] : make_uint4(0, 0, 0, 0);
         }
         if (!p_tma) {
 #pragma unroll
@@ -488,19 +501,32 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
       else if (ri == p.mx0 && p.has_bias) ref_i = p.k;                                   // bias row of A0
       else if (p.y && ri >= p.mx0 + 8 && ri < p.mx0 + 8 + p.c2) ref_i = kp + (ri - p.mx0 - 8);   // B0 rows
       const bool row_ok = ref_i >= 0;
+      // unweighted statistics riding along (p.acc2): the patch rows of the second accumulator, and -- from the FIRST
+      // accumulator -- the unweighted ones row (row mx0 + 1 of the extra block) as the bias row
+      const int ref_i2 = !p.acc2 ? -1 : (ri < p.k ? ref_i : ((ri == p.mx0 + 1 && p.has_bias) ? p.k : -1));
       constexpr int GT_EPI_COLS = GT_BN / (GT_BUILDERS / 128);      // columns per warp group of four quadrant warps
-      for (int c0 = half * GT_EPI_COLS; c0 < half * GT_EPI_COLS + GT_EPI_COLS; c0 += 32) {
-        uint32_t v[32];
-        gt_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
+      const int n_acc = (p.acc2 && mb * GT_BM < p.mx0) ? 2 : 1;
+      for (int a_i = 0; a_i < n_acc; ++a_i) {
+        for (int c0 = half * GT_EPI_COLS; c0 < half * GT_EPI_COLS + GT_EPI_COLS; c0 += 32) {
+          uint32_t v[32];
+          gt_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a_i * 256 + c0), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // accumulator 0 -> weighted workspace (all rows) and, for the unweighted ones row, the second workspace;
+          // accumulator 1 -> second workspace (patch rows)
+          double* dst = a_i == 0 ? p.acc : p.acc2;
+          const int dst_row = a_i == 0 ? ref_i : ref_i2;
+          const bool extra_unw = a_i == 0 && ri == p.mx0 + 1 && ref_i2 >= 0;
+          if (extra_unw) dst = p.acc2;
+          const int row = extra_unw ? ref_i2 : dst_row;
+          if (row >= 0 && (a_i == 1 || row_ok || extra_unw)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cj = nb * GT_BN + c0 + j;
-            const float val = __uint_as_float(v[j]);
-            if (val != 0.f && (cj < p.k || (cj == p.k && p.has_bias))) {
-              const int ref_j = cj < p.k ? (cj % p.c1) * 27 + cj / p.c1 : p.k;
-              atomicAdd(p.acc + (long long)ref_i * p.ld + ref_j, (double)val);
+            for (int j = 0; j < 32; ++j) {
+              const int cj = nb * GT_BN + c0 + j;
+              const float val = __uint_as_float(v[j]);
+              if (val != 0.f && (cj < p.k || (cj == p.k && p.has_bias))) {
+                const int ref_j = cj < p.k ? (cj % p.c1) * 27 + cj / p.c1 : p.k;
+                atomicAdd(dst + (long long)row * p.ld + ref_j, (double)val);
+              }
             }
           }
         }
@@ -514,7 +540,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
   __syncthreads();
   if (warp == GT_BUILDERS / 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.acc2 ? 512u : 256u) : "memory");
   }
 }
 
@@ -531,10 +557,32 @@ extern "C" int effq_gram_tc_supported(const effq_geom* g) {
 // scale: rows [0,K) x cols [0,K'] the attention-weighted Gram of the codes (incl. the bias
 // column), row K the bias row, rows K'.. the B0 rows (att*y against the codes) when y != NULL.
 // acc64 must have been zeroed by the caller.
+static int gram_tc_accumulate_impl(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                                   const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
+                                   int32_t ld, void* flags, double* acc64_unweighted, int32_t rows_only, void* stream);
+
 extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
                                        const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
                                        int32_t ld, void* flags, void* stream) {
+  return gram_tc_accumulate_impl(xcodes_ndhwc_bf16, att, y, g, has_bias, att_exact, acc64, ld, flags, nullptr, 0, stream);
+}
+
+// The same pass with the UNWEIGHTED Gram of the codes accumulated beside the weighted one (acc64_unweighted, same
+// layout; only its K' x K' block is filled), or -- rows_only -- restricted to the extra row block (ones row and the
+// rows of y against the codes): the cheap second pass of the conv-free scoring (csrc/quadform.cu).
+extern "C" int effq_gram_tc_accumulate2(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                                        const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
+                                        int32_t ld, void* flags, double* acc64_unweighted, int32_t rows_only,
+                                        void* stream) {
+  return gram_tc_accumulate_impl(xcodes_ndhwc_bf16, att, y, g, has_bias, att_exact, acc64, ld, flags, acc64_unweighted,
+                                 rows_only, stream);
+}
+
+static int gram_tc_accumulate_impl(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                                   const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
+                                   int32_t ld, void* flags, double* acc64_unweighted, int32_t rows_only, void* stream) {
   using namespace effq;
+  EFFQ_CHECK_ARG(!acc64_unweighted || has_bias, "the unweighted statistics need the bias (ones) row");
   EFFQ_CHECK_ARG(xcodes_ndhwc_bf16 && g && acc64 && flags, "null pointer");
   EFFQ_CHECK_ARG(effq_gram_tc_supported(g), "geometry not supported by the tcgen05 Gram kernel");
   EFFQ_CHECK_ARG(((uintptr_t)xcodes_ndhwc_bf16 & 15) == 0, "codes must be 16B aligned");
@@ -550,7 +598,9 @@ extern "C" int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const floa
   p.has_bias = has_bias ? 1 : 0;
   p.single = (att_exact || !att) ? 1 : 0;
   p.ld = ld;
+  p.acc2 = acc64_unweighted;
   p.mx0 = (p.k + GT_BM - 1) / GT_BM * GT_BM;                      // extras start on a row-block boundary
+  p.mb_begin = rows_only ? p.mx0 / GT_BM : 0;
   const int extra_rows = (has_bias || y) ? 8 + (y ? g->c2 : 0) : 0;
   p.mb_n = (p.mx0 + extra_rows + GT_BM - 1) / GT_BM;
   p.nb_n = (p.k + (has_bias ? 8 : 0) + GT_BN - 1) / GT_BN;

@@ -49,6 +49,9 @@ struct SgParams {
   long long ldc;
   float alpha, beta;
   int lower_only;
+  // triangular B operand: skip the K steps where its rows are structurally zero.  1: B = rows of a LOWER triangular
+  // matrix (row j is zero beyond column j); 2: B = rows of its transpose (row j is zero before column j)
+  int tri;
 };
 
 __global__ void __launch_bounds__(SG_THREADS, 1)
@@ -66,8 +69,11 @@ solve_gemm_tc_kernel(const SgParams p, const __grid_constant__ CUtensorMap amap,
   volatile unsigned int* abort_flag = p.abort_flag;
   const int n0 = blockIdx.x * SG_BN, m0 = blockIdx.y * SG_BM;
   if (p.lower_only && n0 > m0 + SG_BM - 1) return;               // whole CTA, before any barrier / TMEM allocation
-  const int ks_begin = (int)(((long long)p.ksteps * blockIdx.z) / p.splits);
-  const int ks_end = (int)(((long long)p.ksteps * (blockIdx.z + 1)) / p.splits);
+  int ks_begin = (int)(((long long)p.ksteps * blockIdx.z) / p.splits);
+  int ks_end = (int)(((long long)p.ksteps * (blockIdx.z + 1)) / p.splits);
+  if (p.tri == 1) ks_end = min(ks_end, (n0 + SG_BN - 1) / SG_BK + 1);      // columns of this tile's B rows: k <= n0 + 127
+  if (p.tri == 2) ks_begin = max(ks_begin, n0 / SG_BK);                    // k >= n0
+  if (ks_end < ks_begin) ks_end = ks_begin;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SG_STAGES; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
@@ -289,13 +295,14 @@ extern "C" int64_t effq_solve_gemm_tc_workspace(int32_t m, int32_t n, int32_t k,
 namespace effq {
 static int sg_launch(const CUtensorMap& amap, const CUtensorMap& bmap, int m, int n, int k, float* out, long long ldo,
                      void* workspace, float alpha, float beta, const float* c_in, long long ldc, int lower_only,
-                     cudaStream_t s) {
+                     cudaStream_t s, int tri = 0) {
   SgParams p;
   p.m = m; p.n = n; p.k = k; p.ldo = (int)ldo;
   p.ksteps = (k + SG_BK - 1) / SG_BK;
   p.splits = sg_splits(m, n, k);
   p.abort_flag = (unsigned int*)workspace;                     // word 0: abort flag (zero-initialised by the caller)
-  p.c_in = c_in; p.ldc = ldc; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only;
+  p.c_in = c_in; p.ldc = ldc; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only & 1;
+  p.tri = tri;
   float* partial = (float*)((char*)workspace + 16);
   const int ldp = (n + 3) / 4 * 4;                              // split-K partials are compact: [splits][m][ldp]
   if (p.splits > 1) { p.out = partial; p.ldo = ldp; } else { p.out = out; }
@@ -353,5 +360,7 @@ extern "C" int effq_gemm_tc_ex(const void* a_planes, int64_t a_ld, int64_t a_pla
   alignas(64) CUtensorMap amap, bmap;
   if (int rc = sg_make_map(a_planes, m, k, a_ld, &amap, a_plane_stride)) return rc;
   if (int rc = sg_make_map(b_planes, n, k, b_ld, &bmap, b_plane_stride)) return rc;
-  return sg_launch(amap, bmap, m, n, k, out, ldo, workspace, alpha, beta, c_in, ldc, lower_only, (cudaStream_t)stream);
+  // lower_only: bit 0 = skip the tiles above the diagonal; bits 1-2 = triangular B operand (SgParams::tri)
+  return sg_launch(amap, bmap, m, n, k, out, ldo, workspace, alpha, beta, c_in, ldc, lower_only, (cudaStream_t)stream,
+                   (lower_only >> 1) & 3);
 }

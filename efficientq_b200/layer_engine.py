@@ -120,12 +120,25 @@ class LayerCalibrator:
         ops.admm_lhs(a0, rho, eta, has_bias, a_r)
         own = not self.force_generic and os.environ.get("EFFQ_SPD", "1") != "0"
         inv_r = None
+        if fstate.get("force64") and not fstate["use64"]:
+            fstate["use64"] = True
+            rep.fp64_factor = True
         if not fstate["use64"]:
             if own:
                 # blocked Cholesky + block triangular inverse + W^T W on the tensor cores (spd_inverse.py): no library
                 if self._spd is None:
                     from .spd_inverse import SpdInverter
                     self._spd = SpdInverter(dev)
+                if solve_tc and kp >= self.FACTOR_FORM_MIN and os.environ.get("EFFQ_FACTOR_FORM", "1") != "0":
+                    # large systems: keep W = L^-1 and apply A^-1 = W^T W as TWO triangular products per iteration.
+                    # An explicit fp32 A^-1 carries an error ~cond(A) eps -- on the K' = 6913 level (cond ~1e6) the
+                    # calibrated layers ended 10 % (32 x 128^3) to 47 % (8 x 64^3) above the loss reached with an fp64
+                    # inverse or with the reference's (backward-stable) LU solve; W is good to ~sqrt(cond) eps, and
+                    # the two half-empty products cost what the one full product did (profiles/r02_factor_form.txt)
+                    wpl, info = self._spd.invert(a_r, want_inverse=False)
+                    if not (check_first and int(info.item()) != 0):
+                        return ("w", wpl[0], wpl[1]), info
+                    del wpl                            # non-positive pivot in fp32: the fp64 fallback below
                 inv_r, info = self._spd.invert(a_r, copy=not solve_tc)
             else:
                 chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
@@ -135,7 +148,7 @@ class LayerCalibrator:
             # 1e8+ and an fp32 pivot can come out negative: check it once (one sync per layer, on
             # the side stream) and, if so, factorise and invert every A of this layer in fp64 (library: the
             # robustness fallback, like the reference's own CPU retry at solver.py:329-337).
-            if (check_first and int(info.item()) != 0) or fstate.get("force64"):
+            if check_first and int(info.item()) != 0:
                 fstate["use64"] = True
                 rep.fp64_factor = True
         if fstate["use64"]:
@@ -191,11 +204,24 @@ class LayerCalibrator:
         if solve_tc:
             planes = torch.empty((3, c2, ops.split3_ld(kp)), dtype=torch.bfloat16, device=a0.device)
             ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=planes)
+            if isinstance(inv_r, tuple):
+                sol = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=a0.device)[:, :kp]
+                z = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=a0.device)[:, :kp]
+                return self._apply_factor_form(planes, inv_r, kp, z, torch.empty_like(planes), sol)
             sol, self._sg_ws = ops.solve_gemm_tc(planes, inv_r, kp, ws=self._sg_ws)
             return sol
         bmat = torch.empty((c2, kp), dtype=torch.float32, device=a0.device)
         ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat)
         return torch.matmul(bmat, inv_r)
+
+    def _apply_factor_form(self, bplanes, fac, kp, z_buf, zplanes, sol_buf):
+        """w* = (B W^T) W with W = L^-1 (A = L L^T): two tensor-core products that skip the structurally zero half of
+        the triangular operand, and a split of the intermediate in between."""
+        _, wp, wtp = fac
+        _, self._sg_ws = ops.gemm_tc_planes(bplanes, wp, kp, out=z_buf, ws=self._sg_ws, tri=1)
+        ops.split3_bf16(z_buf, out=zplanes)
+        _, self._sg_ws = ops.gemm_tc_planes(zplanes, wtp, kp, out=sol_buf, ws=self._sg_ws, tri=2)
+        return sol_buf
 
     # -- the layer -----------------------------------------------------------------------------
     @torch.no_grad()
@@ -272,7 +298,20 @@ class LayerCalibrator:
 
         # normal-equation statistics (solver.py:253-272), summed over shards
         gram_flag = None
-        if need_gram_tc:
+        # quantised 3x3x3 layers up to 64 channels (K' <= 1729): the quantised input is the same tensor in all 200
+        # iterations, so after the first iterate (scored by the conv, which also leaves its output) the other 199 are
+        # scored from fp64 statistics of the RESIDUAL R = Y - conv(first iterate) -- csrc/quadform.cu: the unweighted
+        # S = X^ X^T rides along with the normal equations in a second TMEM accumulator of the same Gram pass, and
+        # T = R X^T costs a rows-only pass later.  Beyond 64 channels the C2 K'^2 fp64 form costs more than the
+        # tensor-core conv it would replace.
+        qf_delta = use_tc and need_gram_tc and has_bias and tuple(ksize) == (3, 3, 3) and kp <= 2048 and \
+            not self.force_generic and os.environ.get("EFFQ_QF", "1") != "0"
+        stats_qf = None
+        if need_gram_tc and qf_delta:
+            code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
+            a0, b0, stats_qf, self.gram_ws, gram_flag = ops.gram_tc_dual(
+                xcodes, code_scale, out_fp, att, ws=self.gram_ws, att_exact=ops.att_is_exact(att, qlvl_act - 1))
+        elif need_gram_tc:
             code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
             a0, b0, self.gram_ws, gram_flag = ops.gram_tc(xcodes, code_scale, out_fp, att, has_bias=has_bias,
                                                           ws=self.gram_ws,
@@ -297,12 +336,6 @@ class LayerCalibrator:
             stats64 = ops.gram_f64(qx, out_fp, ksize, stride, padding, has_bias=has_bias)
             if dist.world > 1:
                 dist.all_reduce_sum(stats64)
-        # quantised 3x3x3 layers up to 64 channels (K' <= 1729): the quantised input is just as constant, so after the
-        # first iterate (scored by the conv, which also leaves its output) the other 199 are scored from the fp64
-        # statistics of the RESIDUAL R = Y - conv(first iterate) -- csrc/quadform.cu.  Beyond 64 channels the
-        # C2 K'^2 fp64 form costs more than the tensor-core conv it would replace.
-        qf_delta = use_tc and need_gram_tc and ksize == (3, 3, 3) and kp <= 2048 and not self.force_generic and \
-            os.environ.get("EFFQ_QF", "1") != "0"
         yy_dev = torch.tensor([y_sq], dtype=torch.float64, device=dev) if stats64 is not None else None
         g_ref = b_ref = None
         gram_flag2 = None
@@ -362,7 +395,8 @@ class LayerCalibrator:
                       "force_lu": self.force_lu_factor}
             for idx, r_ in enumerate(rhos):
                 inv_r, info = self.inverse_of(a0, r_, eta, has_bias, solve_tc, fstate, rep, check_first=(idx == 0))
-                inv_r.record_stream(main)
+                for t_ in (inv_r[1:] if isinstance(inv_r, tuple) else (inv_r,)):
+                    t_.record_stream(main)
                 ev = torch.cuda.Event()
                 ev.record(self._side)
                 inverses[r_] = (inv_r, ev)
@@ -371,13 +405,16 @@ class LayerCalibrator:
         if self.probe is not None:
             self._side.synchronize()
             for i_, r_ in enumerate(rhos):
-                self._probe(name, f"inv{i_}", inverses[r_][0])
+                iv = inverses[r_][0]
+                self._probe(name, f"inv{i_}", iv[1] if isinstance(iv, tuple) else iv)
         ainv = None
         rho_built = None
         peer = dist.peer_link(dev) if dist.world > 1 else None
         if solve_tc:
             bplanes = torch.empty((3, c2, ops.split3_ld(kp)), dtype=torch.bfloat16, device=dev)
             sol_buf = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :kp]
+            z_buf = torch.empty((c2, (kp + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :kp]     # factor form: B W^T ...
+            zplanes = torch.empty_like(bplanes)                                                      # ... and its split
 
         loop_prof = os.environ.get("EFFQ_LOOP_PROF") == "1"     # bring-up: CPU enqueue time vs GPU time of the loop
         if loop_prof:
@@ -421,7 +458,10 @@ class LayerCalibrator:
                     if it == it_first:     # later right-hand sides come out of admm_project of the previous iteration
                         ops.timer.run("admm_rhs", {"bytes": 22 * c2 * kp},
                                       lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, None, planes=bplanes))
-                    sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
+                    if isinstance(ainv, tuple):
+                        sol = self._apply_factor_form(bplanes, ainv, kp, z_buf, zplanes, sol_buf)
+                    else:
+                        sol, self._sg_ws = ops.solve_gemm_tc(bplanes, ainv, kp, out=sol_buf, ws=self._sg_ws)
                 else:
                     ops.timer.run("admm_rhs", {"bytes": 20 * c2 * kp}, lambda: ops.admm_rhs(b0, w0p, g, dual, rho, eta, bmat))
                     n_pre = len(rec.calls) if recording else 0
@@ -478,9 +518,8 @@ class LayerCalibrator:
                         # residual statistics of this (first executed) iterate: R = Y - out0, T = R X^T, sum R^2
                         torch.sub(out_fp, out0, out=out0)
                         code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)
-                        stats64, self.gram_ws, gram_flag2 = ops.gram_tc_f64(xcodes, code_scale, out0, None,
-                                                                             has_bias=has_bias, ws=self.gram_ws,
-                                                                             att_exact=True)
+                        self.gram_ws, gram_flag2 = ops.gram_tc_rows_f64(xcodes, code_scale, out0, stats_qf, ws=self.gram_ws)
+                        stats64 = stats_qf
                         yy_dev = self.sse.clone()
                         if dist.world > 1:
                             dist.all_reduce_sum(stats64)
@@ -561,6 +600,7 @@ class LayerCalibrator:
             self.probe(name, tag, t)
 
     _spd = None
+    FACTOR_FORM_MIN = 1024         # K' from which the proximal step multiplies with W^T and W instead of an explicit A^-1
     force_fp64_factor = False      # tests: take the fp64-Cholesky / fp64-LU fallbacks of inverse_of on any layer
     force_lu_factor = False
     _cws = None

@@ -488,6 +488,50 @@ def gram_tc_f64(xcodes, code_scale, y, att=None, has_bias=True, ws=None, att_exa
     return acc, ws, flag
 
 
+def gram_tc_dual(xcodes, code_scale, y, att, ws=None, att_exact=False):
+    """A0, B0 (as gram_tc, with bias) and the UNWEIGHTED statistics matrix [(K'+C2) x K'] fp64 whose first K' rows
+    hold S = X^ X^T, from one pass over the codes.  Returns (a0, b0, stats64, workspace, abort flag)."""
+    y = _f32c(y, "y")
+    n, d, h, w, c1 = xcodes.shape
+    g = Geom.make((n, c1, d, h, w), y.shape[1], 3, 1, 1)
+    kp = g.c1 * 27 + 1
+    lib = capi.load()
+    one = (lib.effq_gram_workspace(C.byref(g), 1) + 255) // 256 * 256
+    if ws is None or ws.numel() < 2 * one:
+        ws = torch.empty(2 * one, dtype=torch.uint8, device=y.device)
+    a0 = torch.empty((kp, kp), dtype=torch.float32, device=y.device)
+    b0 = torch.empty((g.c2, kp), dtype=torch.float32, device=y.device)
+    stats = torch.empty((kp + g.c2, kp), dtype=torch.float64, device=y.device)
+    if att is not None:
+        att = _f32c(att, "att")
+    cs = _f32c(code_scale.reshape(1), "code_scale")
+    flops = 2.0 * g.n * d * h * w * ((kp + g.c2) * kp + kp * kp)
+    timer.run("gram_tc_dual", {"flops": flops}, lambda: check(
+        lib.effq_gram_tc_dual(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(bool(att_exact)), ptr(a0), ptr(b0),
+                              ptr(stats), ptr(ws), stream()), "effq_gram_tc_dual"))
+    off = (kp + g.c2) * kp * 8
+    flag = ws[off:off + 4].view(torch.int32)
+    return a0, b0, stats, ws, flag
+
+
+def gram_tc_rows_f64(xcodes, code_scale, y, stats, ws=None):
+    """Rows [K', K'+C2) of ``stats`` <- unweighted Y X^T for the target y (rows-only pass)."""
+    y = _f32c(y, "y")
+    n, d, h, w, c1 = xcodes.shape
+    g = Geom.make((n, c1, d, h, w), y.shape[1], 3, 1, 1)
+    kp = g.c1 * 27 + 1
+    lib = capi.load()
+    need = lib.effq_gram_workspace(C.byref(g), 1)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=y.device)
+    cs = _f32c(code_scale.reshape(1), "code_scale")
+    timer.run("gram_tc_rows", {"flops": 2.0 * g.n * d * h * w * g.c2 * kp}, lambda: check(
+        lib.effq_gram_tc_rows_f64(ptr(xcodes), ptr(cs), ptr(y), C.byref(g), ptr(stats), ptr(ws), stream()),
+        "effq_gram_tc_rows_f64"))
+    flag = ws[need - 16:need - 12].view(torch.int32)
+    return ws, flag
+
+
 def gram_tc_supported(x_shape, c2, ksize, stride, padding) -> bool:
     g = Geom.make(x_shape, c2, ksize, stride, padding)
     return bool(capi.load().effq_gram_tc_supported(C.byref(g)))
@@ -559,14 +603,17 @@ def split3_ld(cols: int) -> int:
     return int(capi.load().effq_split3_ld(int(cols)))
 
 
-def split3_bf16(x: torch.Tensor) -> torch.Tensor:
+def split3_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [rows][cols] -> bf16 [3][rows][split3_ld(cols)] with x = p0 + p1 + p2 (tail columns zero)."""
     if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda:
         raise EffqError("split3_bf16: expected a CUDA float32 matrix")
     if x.stride(1) != 1:
         x = x.contiguous()
     rows, cols = x.shape
-    out = torch.empty((3, rows, split3_ld(cols)), dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        out = torch.empty((3, rows, split3_ld(cols)), dtype=torch.bfloat16, device=x.device)
+    elif tuple(out.shape) != (3, rows, split3_ld(cols)) or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise EffqError("split3_bf16: out must be a contiguous bf16 [3][rows][split3_ld(cols)] tensor")
     check(capi.load().effq_split3_bf16(ptr(x), rows, cols, x.stride(0), ptr(out), stream()), "effq_split3_bf16")
     return out
 
@@ -589,6 +636,23 @@ def solve_gemm_tc(a_planes: torch.Tensor, b_planes: torch.Tensor, k: int, out: O
     timer.run("solve_gemm_tc", {"flops": 2.0 * m * n * k}, lambda: check(
         lib.effq_solve_gemm_tc(ptr(a_planes), ptr(b_planes), m, n, int(k), ptr(out), ldo, ptr(ws), stream()),
         "effq_solve_gemm_tc"))
+    return out, ws
+
+
+def gemm_tc_planes(a_planes: torch.Tensor, b_planes: torch.Tensor, k: int, out: torch.Tensor, ws: Optional[torch.Tensor] = None,
+                   tri: int = 0):
+    """out[m][n] = A B^T from whole split-plane matrices ([3][rows][ld] bf16) through the general entry point;
+    ``tri`` 1 / 2: B holds the rows of a lower triangular matrix / of its transpose (zero K range skipped)."""
+    m, n = a_planes.shape[1], b_planes.shape[1]
+    lib = capi.load()
+    ldo = out.stride(0)
+    need = lib.effq_gemm_tc_ex_workspace(m, n, int(k), ldo)
+    if ws is None or ws.numel() < need:
+        ws = workspace(need, a_planes.device)
+    timer.run("solve_gemm_tc", {"flops": 2.0 * m * n * k * (0.5 if tri else 1.0)}, lambda: check(
+        lib.effq_gemm_tc_ex(ptr(a_planes), a_planes.shape[2], m * a_planes.shape[2], ptr(b_planes), b_planes.shape[2],
+                            n * b_planes.shape[2], m, n, int(k), 1.0, 0.0, None, 0, ptr(out), ldo, int(tri) << 1, ptr(ws),
+                            stream()), "effq_gemm_tc_ex"))
     return out, ws
 
 

@@ -58,7 +58,7 @@ class _Plan:
         self.tp = torch.empty((3, NB, self.ldk), dtype=bf, device=device)         # T^T as planes
         self.inv = torch.empty((n, (n + 3) // 4 * 4), dtype=f32, device=device)[:, :n]
         self.info = torch.zeros(1, dtype=torch.int32, device=device)
-        self.calls, self.calls_stream = None, None                                 # recorded launch sequence and its stream
+        self.calls = {}                                                            # (want_inverse, stream) -> recorded launch sequence
         # one GEMM workspace for the whole (stream-ordered) sequence: the largest split-K partial buffer is that of
         # the final n x n x n product
         lib = capi.load()
@@ -83,8 +83,9 @@ def _split_block(src: torch.Tensor, dst_ptr: int, dst_ld: int, dst_plane: int, t
                                         int(transpose), pad_k, stream()), "effq_split3_block")
 
 
-def _enqueue(plan: _Plan) -> None:
-    """Factorise plan.a in place and leave A^-1 in plan.inv (all launches on the current stream)."""
+def _enqueue(plan: _Plan, want_inverse: bool = True) -> None:
+    """Factorise plan.a in place; leave W = L^-1 as split planes (plan.wp: rows of W, plan.wtp: rows of W^T) and,
+    with ``want_inverse``, A^-1 = W^T W in plan.inv (all launches on the current stream)."""
     lib = capi.load()
     n, ldk = plan.n, plan.ldk
     a, w = plan.a, plan.w
@@ -135,8 +136,9 @@ def _enqueue(plan: _Plan) -> None:
         _split_block(w21, wp0 + ((j + nb) * ldk + j) * esz, ldk, ps, False, pad)
     # ---- A^-1 = W^T W  (both operands = rows of W^T)
     _split_block(w, plan.wtp.data_ptr(), ldk, ps, True, ldk)
-    wt = plan.wtp.data_ptr()
-    _gemm(plan, wt, ldk, ps, wt, ldk, ps, n, n, n, 1.0, 0.0, None, plan.inv)
+    if want_inverse:
+        wt = plan.wtp.data_ptr()
+        _gemm(plan, wt, ldk, ps, wt, ldk, ps, n, n, n, 1.0, 0.0, None, plan.inv)
 
 
 class SpdInverter:
@@ -147,23 +149,29 @@ class SpdInverter:
         self.device = device
         self.plans: Dict[int, _Plan] = {}
 
-    def invert(self, a: torch.Tensor, replay: bool = True, copy: bool = True):
-        """``copy=False`` returns the plan's own result buffer (valid until the next ``invert`` of this size)."""
+    def invert(self, a: torch.Tensor, replay: bool = True, copy: bool = True, want_inverse: bool = True):
+        """``copy=False`` returns the plan's own result buffer (valid until the next ``invert`` of this size).
+        ``want_inverse=False`` stops after the triangular inverse and returns ((planes of W, planes of W^T), info)
+        with W = L^-1, A = L L^T: applying W^T W as TWO products is far more accurate than multiplying with an explicit
+        A^-1 when A is ill-conditioned (errors ~ sqrt(cond) eps instead of cond eps), see layer_engine."""
         n = a.shape[0]
         plan = self.plans.get(n)
         if plan is None:
-            for k in [k for k in self.plans if k != n]:          # one live size (the buffers of K' = 6913 take ~2 GB)
-                del self.plans[k]
+            # every size of the network keeps its plan (buffers + recorded launch sequence): ~3.4 GB for K' = 6913,
+            # < 1 GB for the rest of the BraTS net, 13 GB for the LiTS net's K' = 13825 -- of 180 GB
             plan = self.plans[n] = _Plan(n, self.device)
         plan.a.copy_(a)
         plan.info.zero_()
         cur = torch.cuda.current_stream(self.device).cuda_stream       # the recorded launches carry their stream
-        if plan.calls is not None and replay and plan.calls_stream == cur:
-            ops.replay(plan.calls)
-        elif replay and capi._recorder is None and plan.calls is None:
+        key = (want_inverse, cur)
+        if key in plan.calls and replay:
+            ops.replay(plan.calls[key])
+        elif replay and capi._recorder is None:
             with capi.record() as rec:
-                _enqueue(plan)
-            plan.calls, plan.calls_stream = list(rec.calls), cur
+                _enqueue(plan, want_inverse)
+            plan.calls[key] = list(rec.calls)
         else:
-            _enqueue(plan)
+            _enqueue(plan, want_inverse)
+        if not want_inverse:
+            return (plan.wp.clone(), plan.wtp.clone()), plan.info.clone()
         return (plan.inv.clone() if copy else plan.inv), plan.info.clone()

@@ -237,6 +237,18 @@ int effq_gram_tc(const void* xcodes_ndhwc_bf16, const float* code_scale, const f
 int effq_gram_tc_accumulate(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
                             const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
                             int32_t ld, void* flags, void* stream);
+int effq_gram_tc_accumulate2(const void* xcodes_ndhwc_bf16, const float* att, const float* y,
+                             const effq_geom* g, int32_t has_bias, int32_t att_exact, double* acc64,
+                             int32_t ld, void* flags, double* acc64_unweighted, int32_t rows_only, void* stream);
+/* A0, B0 as effq_gram_tc AND the unweighted S = X^ X^T (K' x K' fp64, real units, bias row / column included) from
+ * ONE pass (second TMEM accumulator fed with the raw codes); needs a bias.  workspace: 2 x effq_gram_workspace. */
+int effq_gram_tc_dual(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y, const float* att,
+                      const effq_geom* g, int32_t att_exact, float* a0_out, float* b0_out,
+                      double* s_unweighted_out, void* workspace, void* stream);
+/* Unweighted T = Y X^T (C2 x K') for a new target (rows-only pass of the same kernel): writes rows [K', K'+C2) of
+ * the [(K'+C2) x K'] statistics matrix at stats_base.  workspace: effq_gram_workspace. */
+int effq_gram_tc_rows_f64(const void* xcodes_ndhwc_bf16, const float* code_scale, const float* y,
+                          const effq_geom* g, double* stats_base, void* workspace, void* stream);
 /* The tcgen05 statistics as a full fp64 matrix in real units, acc64_out[(K'+C2) x K'] = [X^ diag(att) X^T ;
  * Y diag(att) X^T] (no factor 2, mirrored, code_scale applied): the operand of effq_quadform_delta.
  * workspace as effq_gram_workspace. */
@@ -330,7 +342,9 @@ int effq_admm_track(effq_admm_state* st, const double* sse, double numel, const 
 /* out = alpha * A B^T + beta * c_in on SUB-BLOCKS of split-plane matrices (three bf16 terms per fp32 value,
  * effq_split3_bf16 / effq_split3_block): A = m x k block at a_planes with row pitch a_ld and plane stride
  * a_plane_stride (elements, multiples of 8), B = n x k likewise.  c_in may be NULL (beta ignored) and may alias
- * out.  lower_only != 0 skips the 128 x 128 tiles strictly above the diagonal.  fp32-class accuracy. */
+ * out.  `lower_only` is a bit field: bit 0 skips the 128 x 128 tiles strictly above the diagonal; bits 1-2 declare a
+ * triangular B operand whose structurally zero K range is skipped (2: B = rows of a lower triangular matrix,
+ * 4: B = rows of its transpose).  fp32-class accuracy. */
 int64_t effq_gemm_tc_ex_workspace(int32_t m, int32_t n, int32_t k, int64_t ldo);
 int effq_gemm_tc_ex(const void* a_planes, int64_t a_ld, int64_t a_plane_stride, const void* b_planes,
                     int64_t b_ld, int64_t b_plane_stride, int32_t m, int32_t n, int32_t k, float alpha,

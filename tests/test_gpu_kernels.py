@@ -610,6 +610,39 @@ def test_quadform_delta_equals_conv_sse(ops, n, c1, c2, sp):
     assert abs(sse.item() - sse_old.item()) <= 1e-9 * abs(sse_old.item()) + 1e-9 * float(yy_y.item())
 
 
+@pytest.mark.parametrize("n,c1,c2,sp,int_att", [(2, 32, 32, (6, 16, 8), True), (1, 64, 64, (4, 8, 16), True),
+                                                 (1, 16, 24, (5, 10, 12), False), (2, 32, 16, (3, 9, 7), True)])
+def test_gram_tc_dual_and_rows_only(ops, n, c1, c2, sp, int_att):
+    """One Gram pass, two accumulators: the attention-weighted normal equations (bit-identical to effq_gram_tc) and the
+    UNWEIGHTED S = X^ X^T with its bias row / column (exact: integer codes); then the rows-only pass for a new target
+    gives T = R X^T -- together the statistics of effq_quadform_delta."""
+    torch.manual_seed(c1 * 3 + c2)
+    la = 16
+    codes = torch.randint(0, la, (n, c1, *sp)).float()
+    sc = float(np.float32(0.211))
+    y = torch.randn(n, c2, *sp)
+    att = (torch.rand(n, *sp) * 3).floor() + 1 if int_att else torch.rand(n, *sp) * 2 + 0.25
+    xq = codes.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16).to(DEV)
+    cs = torch.tensor([sc], device=DEV)
+    exact = ops.att_is_exact(att.to(DEV), la - 1)
+    a0, b0, stats, ws, flag = ops.gram_tc_dual(xq, cs, y.to(DEV), att.to(DEV), att_exact=exact)
+    assert int(flag.item()) == 0
+    a1, b1, _, flag1 = ops.gram_tc(xq, cs, y.to(DEV), att.to(DEV), True, att_exact=exact)
+    assert torch.equal(a0, a1) and torch.equal(b0, b1)
+    cols = O.im2col(codes, 3, 3, 3, 1, 1).double() * sc
+    cols = torch.cat([cols, torch.ones(1, cols.shape[1], dtype=torch.float64)], 0)
+    kp = cols.shape[0]
+    s_ref = cols @ cols.T
+    got = stats[:kp].cpu()
+    assert (got - s_ref).abs().max().item() <= 1e-12 * s_ref.abs().max().item()
+    r = torch.randn(n, c2, *sp) * 0.3
+    _, flag2 = ops.gram_tc_rows_f64(xq, cs, r.to(DEV), stats, ws=ws)
+    assert int(flag2.item()) == 0
+    t_ref = r.permute(1, 0, 2, 3, 4).reshape(c2, -1).double() @ cols.T
+    assert (stats[kp:].cpu() - t_ref).abs().max().item() <= 2e-5 * t_ref.abs().max().item()
+    assert torch.equal(stats[:kp].cpu(), got)                       # the rows-only pass leaves S alone
+
+
 # ---------------------------------------------------------------- proximal-step GEMM (a9)
 def test_split3_bf16_is_exact(ops):
     torch.manual_seed(21)

@@ -31,19 +31,27 @@ constexpr int PT_PW = 8;
 // a_step, b_step, c_step floats)
 __device__ __forceinline__ void pt_small_gemm(const float* A, int a_step, const float* B, int b_step, float* C, int c_step,
                                               int pairs, int rows, int cols, int kk, int ld, float sign) {
-  const int per = rows * cols, total = pairs * per;
+  // a thread takes 4 consecutive columns of one row: one A value feeds four independent FMA chains
+  const int c4 = cols >> 2, per = rows * c4, total = pairs * per;
   for (int e = threadIdx.x; e < total; e += PT_THREADS) {
-    const int q = e / per, rc = e - q * per, r = rc / cols, c = rc - r * cols;
+    const int q = e / per, rc = e - q * per, r = rc / c4, c = (rc - r * c4) << 2;
     const float* ar = A + q * a_step + r * ld;
     const float* bc = B + q * b_step + c;
-    float acc0 = 0.f, acc1 = 0.f;
-    int k = 0;
-    for (; k + 1 < kk; k += 2) {
-      acc0 = fmaf(ar[k], bc[k * ld], acc0);
-      acc1 = fmaf(ar[k + 1], bc[(k + 1) * ld], acc1);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < kk; ++k) {
+      const float av = ar[k];
+      const float* bk = bc + k * ld;
+      acc[0] = fmaf(av, bk[0], acc[0]);
+      acc[1] = fmaf(av, bk[1], acc[1]);
+      acc[2] = fmaf(av, bk[2], acc[2]);
+      acc[3] = fmaf(av, bk[3], acc[3]);
     }
-    if (k < kk) acc0 = fmaf(ar[k], bc[k * ld], acc0);
-    C[q * c_step + r * ld + c] = sign * (acc0 + acc1);
+    float* cr = C + q * c_step + r * ld + c;
+    cr[0] = sign * acc[0];
+    cr[1] = sign * acc[1];
+    cr[2] = sign * acc[2];
+    cr[3] = sign * acc[3];
   }
 }
 
@@ -56,11 +64,21 @@ potrf_tile_kernel(float* __restrict__ a, long long lda, int nb, float* __restric
   float* W = sm + PT_NB * LD;            // [PT_NB][LD]
   float* T = W + PT_NB * LD;             // [PT_NB / 2][LD]: scratch of the doubling steps (64 * s floats, pitch LD)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  for (int e = t; e < PT_NB * PT_NB; e += PT_THREADS) {
-    const int i = e / PT_NB, j = e % PT_NB;
-    // rows / columns beyond nb: identity (keeps every step below well defined for a partial last block)
-    L[i * LD + j] = (i < nb && j <= i) ? a[(long long)i * lda + j] : (i == j ? 1.f : 0.f);
-    W[i * LD + j] = 0.f;
+  // load: 8 independent global loads per thread in flight (one CTA streams the 64 KB block from L2)
+  for (int e0 = t; e0 < PT_NB * PT_NB; e0 += 8 * PT_THREADS) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * PT_THREADS, i = e / PT_NB, j = e % PT_NB;
+      // rows / columns beyond nb: identity (keeps every step below well defined for a partial last block)
+      v[u] = (i < nb && j <= i) ? a[(long long)i * lda + j] : (i == j ? 1.f : 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * PT_THREADS, i = e / PT_NB, j = e % PT_NB;
+      L[i * LD + j] = v[u];
+      W[i * LD + j] = 0.f;
+    }
   }
   __shared__ int bad;
   if (t == 0) bad = 0;

@@ -10,7 +10,7 @@
 // An exchange with sequence number s: write my values into slot[ch][my rank][s & 1] of every rank
 // (data, system fence, then the sequence word), spin until the local slots of all ranks carry s,
 // add them in rank order (bit-identical result on every rank).  Two parities suffice: a rank can
-// only be one exchange ahead of the slowest.  Spins are bounded; on timeout the abort flag is
+// only be one exchange ahead of the slowest.  Waits are bounded (30 s of wall time); on timeout the abort flag is
 // raised (sticky: later exchanges fail at once) and the caller leaves with a failure code instead
 // of hanging the node.
 #pragma once
@@ -23,7 +23,17 @@ struct PeerSlot {
   unsigned long long seq;
 };
 constexpr int EFFQ_PEER_CTR_OFFSET = EFFQ_PEER_CHANNELS * EFFQ_PEER_MAX * 2 * (int)sizeof(PeerSlot);
-constexpr unsigned long long PEER_SPIN_LIMIT = 1ull << 24;      // ~10 s of polling local memory
+// A missing peer must end in an error, not in a hung node: the wait for a rank's sequence word is bounded by WALL
+// TIME (%globaltimer, nanoseconds), not by a spin count whose duration depends on clocks and contention.  30 s covers
+// the largest legitimate skew between ranks inside a layer (first-call module load, an fp64 factorisation fallback
+// on one rank's side stream); the abort flag is sticky for the rest of the process (every later exchange fails at
+// once, the layer engine raises), because the sequence counters of the ranks are no longer in step.
+constexpr unsigned long long PEER_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Called by ONE thread.  vals[0..2] in: local contribution; out: sum over ranks (rank order).
 __device__ __forceinline__ bool peer_allreduce3(const effq_peer_comm& c, int ch, double* vals) {
@@ -49,9 +59,13 @@ __device__ __forceinline__ bool peer_allreduce3(const effq_peer_comm& c, int ch,
   bool ok = true;
   for (int r = 0; r < c.world; ++r) {
     volatile PeerSlot* s = (volatile PeerSlot*)mine + ((ch * EFFQ_PEER_MAX + r) * 2 + par);
-    unsigned long long spins = 0;
+    unsigned long long spins = 0, t0 = 0;
     while (s->seq != seq) {
-      if (++spins > PEER_SPIN_LIMIT) { ok = false; *aborted = 1ull; break; }
+      if ((++spins & 0xfffull) == 0) {                       // look at the clock every 4096 polls
+        const unsigned long long now = peer_now_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > PEER_TIMEOUT_NS) { ok = false; *aborted = 1ull; break; }
+      }
     }
     if (!ok) break;
     __threadfence_system();

@@ -27,8 +27,10 @@ import torch.distributed as td
 
 
 class DistCtx:
-    def __init__(self, group=None):
-        self.enabled = td.is_available() and td.is_initialized()
+    def __init__(self, group=None, single: bool = False):
+        """``single=True``: a one-process context even when a process group is initialised (e.g. rank 0 repeating a
+        job unsharded for comparison) -- no collective is ever issued through it."""
+        self.enabled = td.is_available() and td.is_initialized() and not single
         self.group = group
         self.world = td.get_world_size(group) if self.enabled else 1
         self.rank = td.get_rank(group) if self.enabled else 0
@@ -158,5 +160,9 @@ def init_from_env(backend: str = "nccl") -> DistCtx:
     if world > 1 and not td.is_initialized():
         if backend == "nccl":
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        td.init_process_group(backend=backend)
+        kw = {}
+        if os.environ.get("EFFQ_DIST_TIMEOUT_S"):               # tests: fail fast on a mismatched collective
+            import datetime
+            kw["timeout"] = datetime.timedelta(seconds=int(os.environ["EFFQ_DIST_TIMEOUT_S"]))
+        td.init_process_group(backend=backend, **kw)
     return DistCtx()

@@ -339,6 +339,11 @@ class LayerCalibrator:
         yy_dev = torch.tensor([y_sq], dtype=torch.float64, device=dev) if stats64 is not None else None
         g_ref = b_ref = None
         gram_flag2 = None
+        # quantised 1x1x1 layers (K' = 33 .. 257): the same residual-form scoring, with the statistics of the residual
+        # from the generic fp64 Gram kernel (a pass over V x K' values: cheap) -- their tensor-core conv is a
+        # memory-bound re-read of the target 200 times, and in a sharded run it needs an exchange per iterate
+        qf_generic = use_tc and not qf_delta and has_bias and tuple(ksize) == (1, 1, 1) and kp <= 512 and \
+            not self.force_generic and os.environ.get("EFFQ_QF", "1") != "0"
         w0p = torch.cat([w0.reshape(c2, k), bias.detach().float().reshape(c2, 1)], 1).contiguous() if has_bias \
             else w0.reshape(c2, k).contiguous()
 
@@ -430,7 +435,7 @@ class LayerCalibrator:
         # host-bound (19 ms of enqueue for 19 ms of GPU time per layer, profiles/r01_loop_prof.txt).
         from contextlib import nullcontext
         from . import capi as _capi
-        replayable = not (dist.world > 1 and stats64 is None and not qf_delta and peer is None) and \
+        replayable = not (dist.world > 1 and stats64 is None and not (qf_delta or qf_generic) and peer is None) and \
             os.environ.get("EFFQ_REPLAY", "1") != "0"            # an NCCL all-reduce inside the loop cannot be re-issued
         keep_bufs = (best_g, best_b, best_wcodes, best_pc)
         steady = None
@@ -501,7 +506,7 @@ class LayerCalibrator:
                     out0 = None
                     if use_tc:
                         out0, _ = ops.conv3d_tc(xcodes_conv, wcodes, bstar, self.st.conv_scale_ptr(), c2, ksize,
-                                                want_out=qf_delta, target=out_fp, ws=self.tc_ws, sse=self.sse,
+                                                want_out=qf_delta or qf_generic, target=out_fp, ws=self.tc_ws, sse=self.sse,
                                                 scale_vec=pc[c2:] if channel_wise else None)
                     else:
                         ops.conv3d_f32(qx, g4, bstar, stride, padding, want_out=False, target=out_fp,
@@ -514,7 +519,17 @@ class LayerCalibrator:
                             dist.all_reduce_sum(self.sse)
                     ops.timer.run("admm_decide", {"bytes": 64}, lambda: ops.admm_decide(
                         self.st, self.sse, numel_total, hist, comm=track_comm))
-                    if qf_delta:
+                    if qf_generic:
+                        torch.sub(out_fp, out0, out=out0)
+                        stats64 = ops.gram_f64(qx, out0, ksize, stride, padding, has_bias=has_bias)
+                        yy_dev = self.sse.clone()
+                        if dist.world > 1:
+                            dist.all_reduce_sum(stats64)
+                            if peer is not None:
+                                dist.all_reduce_sum(yy_dev)
+                        g_ref, b_ref = g.clone(), bstar.clone()
+                        del out0
+                    elif qf_delta:
                         # residual statistics of this (first executed) iterate: R = Y - out0, T = R X^T, sum R^2
                         torch.sub(out_fp, out0, out=out0)
                         code_scale = (self.xstate.a_f32() / float(qlvl_act - 1)).reshape(1)

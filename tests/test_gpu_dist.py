@@ -17,10 +17,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_two_gpu_calibration_matches_unsharded(peer):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, EFFQ_PEER=peer, MASTER_ADDR="127.0.0.1")
+    # a short NCCL watchdog: a mismatched collective must fail this test in a minute, not hold two GPUs for ten
+    env = dict(os.environ, EFFQ_PEER=peer, MASTER_ADDR="127.0.0.1", TORCH_NCCL_HEARTBEAT_TIMEOUT_SEC="120",
+               EFFQ_DIST_TIMEOUT_S="90")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533" if peer == "1" else "29534", os.path.join(ROOT, "tools", "dist_check.py")]
-    out = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    out = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=400)
     print(out.stdout[-6000:])
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         open(os.path.join(ROOT, "gpurun_out", f"r02_dist_check_2gpu_peer{peer}.log"), "w").write(out.stdout)

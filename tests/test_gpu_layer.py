@@ -99,7 +99,7 @@ def test_layer_calibration_e4m3_equals_bf16(engine_mod, golden, name, monkeypatc
     assert float(aw1) == float(aw0) and float(aa1) == float(aa0)
 
 
-@pytest.mark.parametrize("name", ["w4a4_k3_c32", "w2a4_k3_c64", "w4a4_k3"])
+@pytest.mark.parametrize("name", ["w4a4_k3_c32", "w2a4_k3_c64", "w4a4_k3", "w4a4_k1_c64", "w4a4_k1"])
 def test_conv_free_scoring_matches_conv_scoring(engine_mod, golden, name, monkeypatch):
     """Quantised 3x3x3 layers score iterates 1..199 from the residual statistics (csrc/quadform.cu) instead of a
     conv per iterate: the loss history must agree with the conv-scored run to fp32-loss accuracy and the same

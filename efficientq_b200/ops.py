@@ -27,6 +27,7 @@ class KernelTimer:
         self.enabled = False
         self.only = None             # optional tuple of name prefixes: time just those kernels
         self.records = {}
+        self.streams = {}            # name -> set of stream handles the kernel was launched on
 
     def run(self, name, work, fn):
         rec = capi._recorder
@@ -49,6 +50,7 @@ class KernelTimer:
         out = fn()
         e1.record()
         self.records.setdefault(name, []).append((e0, e1, work))
+        self.streams.setdefault(name, set()).add(torch.cuda.current_stream().cuda_stream)
         return out
 
     def summary(self):
@@ -57,12 +59,14 @@ class KernelTimer:
         for name, recs in self.records.items():
             ms = sum(a.elapsed_time(b) for a, b, _ in recs)
             res[name] = dict(launches=len(recs), ms=ms, flops=sum(w.get("flops", 0) for _, _, w in recs),
+                             flops_alg=sum(w.get("flops_alg", w.get("flops", 0)) for _, _, w in recs),
                              bytes=sum(w.get("bytes", 0) for _, _, w in recs),
                              pass_bytes=sum(w.get("pass_bytes", 0) for _, _, w in recs))
         return res
 
     def reset(self):
         self.records = {}
+        self.streams = {}
 
 
 timer = KernelTimer()
@@ -505,8 +509,10 @@ def gram_tc_dual(xcodes, code_scale, y, att, ws=None, att_exact=False):
     if att is not None:
         att = _f32c(att, "att")
     cs = _f32c(code_scale.reshape(1), "code_scale")
-    flops = 2.0 * g.n * d * h * w * ((kp + g.c2) * kp + kp * kp)
-    timer.run("gram_tc_dual", {"flops": flops}, lambda: check(
+    vox = float(g.n) * d * h * w
+    flops = 2.0 * vox * ((kp + g.c2) * kp + kp * kp)                       # full count of both Grams + B0
+    flops_alg = vox * (2.0 * kp * (kp + 1) + 2.0 * g.c2 * kp)             # symmetric half per Gram, B0 in full
+    timer.run("gram_tc_dual", {"flops": flops, "flops_alg": flops_alg}, lambda: check(
         lib.effq_gram_tc_dual(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(bool(att_exact)), ptr(a0), ptr(b0),
                               ptr(stats), ptr(ws), stream()), "effq_gram_tc_dual"))
     off = (kp + g.c2) * kp * 8
@@ -579,7 +585,8 @@ def gram_tc(xcodes, code_scale, y, att, has_bias=True, ws=None, att_exact=False)
     cs = _f32c(code_scale.reshape(1), "code_scale")
     od, oh, ow = g.out_spatial()
     flops = 2.0 * g.n * od * oh * ow * (kp + g.c2) * kp
-    timer.run("gram_tc", {"flops": flops}, lambda: check(
+    flops_alg = float(g.n) * od * oh * ow * (kp * (kp + 1) + 2.0 * g.c2 * kp)
+    timer.run("gram_tc", {"flops": flops, "flops_alg": flops_alg}, lambda: check(
         lib.effq_gram_tc(ptr(xcodes), ptr(cs), ptr(y), ptr(att), C.byref(g), int(has_bias), int(bool(att_exact)),
                          ptr(a0), ptr(b0), ptr(ws), stream()), "effq_gram_tc"))
     flag = ws[need - 16:need - 12].view(torch.int32)       # non-zero if the tcgen05 kernel aborted

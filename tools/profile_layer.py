@@ -34,12 +34,28 @@ for _ in range(4):
 for _ in range(2):
     ops.conv3d_tc(xq, wq, None, cs, c, 3, want_out=False, target=y, ws=ws, sse=sse)        # bf16 codes, for comparison
 code_scale = (st.a_f32() / 15.0).reshape(1)
-a0, b0, _, flag = ops.gram_tc(xq, code_scale, y, att, True)
+a0, b0, _, flag = ops.gram_tc(xq, code_scale, y, att, True, att_exact=True)
+# round 2: weighted + unweighted Gram in one pass, rows-only pass, conv-free scoring, own SPD inverse
+a0d, b0d, stats, gws, flagd = ops.gram_tc_dual(xq, code_scale, y, att, att_exact=True)
+ops.gram_tc_rows_f64(xq, code_scale, y, stats, ws=gws)
+yy = torch.ones(1, dtype=torch.float64, device=dev)
+g0 = torch.randn(c, c * 27, device=dev) * 0.05
+b_0 = torch.randn(c, device=dev) * 0.05
+g1, b_1 = g0 + 1e-3 * torch.randn_like(g0), b_0 + 1e-3
+for _ in range(3):
+    ops.quadform_delta(stats, yy, g1, b_1, sse, g0, b_0)
+from efficientq_b200.spd_inverse import SpdInverter  # noqa: E402
+inv = SpdInverter(dev)
+a_spd = a0d + 50.0 * torch.eye(a0d.shape[0], device=dev)
+for _ in range(2):
+    inv.invert(a_spd, want_inverse=False)
+rows = ops.ScaleStateRows(dev, c)
 sol = torch.randn(c, c * 27 + 1, device=dev) * 0.05
 dual = torch.zeros(c, c * 27, device=dev)
 wst = ops.ScaleState(dev)
 for _ in range(3):
     ops.scale_search(sol[:, : c * 27], 16, -1.0, 1.0, wst, v2=dual)
+ops.scale_search_rows(sol[:, : c * 27], 16, -1.0, 1.0, rows, v2=dual)
 # proximal-step GEMM at the deepest layer's shape (C2 = 256, K' = 6913)
 kp = 6913
 bm = torch.randn(256, kp, device=dev)

@@ -108,11 +108,12 @@ class LayerCalibrator:
 
     # -- a9: (A0 + rho*quasi_eye + eta*I)^-1 ------------------------------------------------------
     def inverse_of(self, a0: torch.Tensor, rho: float, eta: float, has_bias: bool, solve_tc: bool, fstate: dict,
-                   rep: Optional[LayerReport] = None, check_first: bool = True):
+                   rep: Optional[LayerReport] = None, check_first: bool = True, slot: int = 0):
         """One normal matrix of the layer (solver.py:316-331), assembled, factorised and inverted on the current
         stream.  Returns (A^-1 -- as three bf16 planes when ``solve_tc`` --, info tensor of the factorisation).
         ``fstate['use64']`` carries the layer's decision to factorise in fp64 (taken on its first, worst-conditioned
-        system when ``check_first``)."""
+        system when ``check_first``).  ``slot`` selects one of the independent inverters (own buffers and recorded
+        launch sequences), so that the systems of a layer can be factorised concurrently on different streams."""
         kp = a0.shape[0]
         dev = a0.device
         rep = rep or LayerReport()
@@ -126,20 +127,23 @@ class LayerCalibrator:
         if not fstate["use64"]:
             if own:
                 # blocked Cholesky + block triangular inverse + W^T W on the tensor cores (spd_inverse.py): no library
-                if self._spd is None:
+                if self._spds is None:
+                    self._spds = {}
+                if slot not in self._spds:
                     from .spd_inverse import SpdInverter
-                    self._spd = SpdInverter(dev)
+                    self._spds[slot] = SpdInverter(dev)
+                spd = self._spds[slot]
                 if solve_tc and kp >= self.FACTOR_FORM_MIN and os.environ.get("EFFQ_FACTOR_FORM", "1") != "0":
                     # large systems: keep W = L^-1 and apply A^-1 = W^T W as TWO triangular products per iteration.
                     # An explicit fp32 A^-1 carries an error ~cond(A) eps -- on the K' = 6913 level (cond ~1e6) the
                     # calibrated layers ended 10 % (32 x 128^3) to 47 % (8 x 64^3) above the loss reached with an fp64
                     # inverse or with the reference's (backward-stable) LU solve; W is good to ~sqrt(cond) eps, and
                     # the two half-empty products cost what the one full product did (profiles/r02_factor_form.txt)
-                    wpl, info = self._spd.invert(a_r, want_inverse=False)
+                    wpl, info = spd.invert(a_r, want_inverse=False)
                     if not (check_first and int(info.item()) != 0):
                         return ("w", wpl[0], wpl[1]), info
                     del wpl                            # non-positive pivot in fp32: the fp64 fallback below
-                inv_r, info = self._spd.invert(a_r, copy=not solve_tc)
+                inv_r, info = spd.invert(a_r, copy=not solve_tc)
             else:
                 chol, info = ops.timer.run("lib_cholesky", {"flops": kp ** 3 / 3.0},
                                            lambda: torch.linalg.cholesky_ex(a_r))
@@ -390,25 +394,59 @@ class LayerCalibrator:
                 rhos.append(r_)
         rho = rho_seq[it_first]
         main = torch.cuda.current_stream(dev)
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=dev)
-        self._side.wait_stream(main)
-        inverses, infos = {}, []
         solve_tc = self.use_solve_tc(kp, self.force_generic)
-        with torch.cuda.stream(self._side):
-            fstate = {"use64": False, "force64": self.force_fp64_factor or self.force_lu_factor,
-                      "force_lu": self.force_lu_factor}
+        # The systems of a layer are independent, and one blocked factorisation is a chain of ~12 dependent small
+        # launches per 128-wide panel (latency-bound: 31 ms at K' = 6913, 4 % of the SMs busy): each rho gets its own
+        # stream and inverter, so the five chains run side by side instead of one after the other -- the K' >= 3457
+        # layers were waiting for them at every rho change (profiles/r02_factor_streams.txt).
+        n_slots = self.factor_streams if kp <= 8192 else min(self.factor_streams, 2)    # a K' = 13825 plan holds 13 GB
+        n_slots = max(1, min(n_slots, len(rhos)))
+        if self.force_generic or os.environ.get("EFFQ_SPD", "1") == "0":
+            n_slots = 1                                # the library bring-up path shares one GEMM workspace
+        if self._sides is None:
+            self._sides = []
+        while len(self._sides) < n_slots:
+            self._sides.append(torch.cuda.Stream(device=dev))
+        self._side = self._sides[0]
+        for sd in self._sides[:n_slots]:
+            sd.wait_stream(main)
+        inverses, infos = {}, []
+        fstate = {"use64": False, "force64": self.force_fp64_factor or self.force_lu_factor,
+                  "force_lu": self.force_lu_factor}
+
+        def factor_all(first_checked: bool):
+            inverses.clear()
+            infos.clear()
             for idx, r_ in enumerate(rhos):
-                inv_r, info = self.inverse_of(a0, r_, eta, has_bias, solve_tc, fstate, rep, check_first=(idx == 0))
-                for t_ in (inv_r[1:] if isinstance(inv_r, tuple) else (inv_r,)):
-                    t_.record_stream(main)
-                ev = torch.cuda.Event()
-                ev.record(self._side)
+                slot = idx % n_slots
+                with torch.cuda.stream(self._sides[slot]):
+                    inv_r, info = self.inverse_of(a0, r_, eta, has_bias, solve_tc, fstate, rep,
+                                                  check_first=first_checked and idx == 0, slot=slot)
+                    for t_ in (inv_r[1:] if isinstance(inv_r, tuple) else (inv_r,)):
+                        t_.record_stream(main)
+                    ev = torch.cuda.Event()
+                    ev.record(self._sides[slot])
                 inverses[r_] = (inv_r, ev)
                 infos.append(info)
-                rep.factorizations += 1
+
+        if n_slots > 1 and not fstate["force64"]:
+            # enqueue every system first, THEN look at the first (worst-conditioned) one's pivots: the check is a host
+            # synchronisation, and taken inside the loop it would serialise the chains behind it
+            factor_all(first_checked=False)
+            if int(infos[0].item()) != 0:          # non-positive fp32 pivot: all systems of this layer again, in fp64
+                fstate["use64"] = True
+                rep.fp64_factor = True
+                for sd in self._sides[1:n_slots]:
+                    self._sides[0].wait_stream(sd)
+                n_slots = 1
+                factor_all(first_checked=False)
+        else:
+            n_slots = 1 if fstate["force64"] else n_slots
+            factor_all(first_checked=True)
+        rep.factorizations += len(rhos)
         if self.probe is not None:
-            self._side.synchronize()
+            for sd in self._sides:
+                sd.synchronize()
             for i_, r_ in enumerate(rhos):
                 iv = inverses[r_][0]
                 self._probe(name, f"inv{i_}", iv[1] if isinstance(iv, tuple) else iv)
@@ -566,7 +604,8 @@ class LayerCalibrator:
                                       sse=self.sse)
         if dist.world > 1:
             dist.all_reduce_sum(self.sse)
-        main.wait_stream(self._side)               # every factorisation (also an unused last one) is ordered before the read-back
+        for sd in self._sides:                     # every factorisation (also an unused last one) is ordered before the read-back
+            main.wait_stream(sd)
         # LAST iterate's scale (reference quirk, :158); per channel: the [C2] vector of the last iterate
         alpha_w = pc[:c2].clone() if channel_wise else self.st.a_w_tensor().clone()
         s = self.st.read()                          # the layer's one result read-back
@@ -614,7 +653,8 @@ class LayerCalibrator:
         if self.probe is not None and t is not None:
             self.probe(name, tag, t)
 
-    _spd = None
+    _spds = None            # slot -> SpdInverter
+    _sides = None           # factorisation streams, one per slot
     FACTOR_FORM_MIN = 1024         # K' from which the proximal step multiplies with W^T and W instead of an explicit A^-1
     force_fp64_factor = False      # tests: take the fp64-Cholesky / fp64-LU fallbacks of inverse_of on any layer
     force_lu_factor = False
@@ -631,6 +671,7 @@ class LayerCalibrator:
         return self._eyes[n]
 
     _side = None
+    factor_streams = int(os.environ.get("EFFQ_FACTOR_STREAMS", "5"))   # concurrent factorisation chains per layer
 
     def _conv_ws(self, x, c2, ksize, stride, padding):
         import ctypes as C

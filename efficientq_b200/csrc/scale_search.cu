@@ -26,6 +26,11 @@
 
 namespace effq {
 
+// scale_search_bucket.cu: 0 launched, 1 / 2 error, -1 tensor not for that kernel
+int scale_search_bucket_launch(const float* v1, int64_t ld1, const float* v2, int64_t ld2, int64_t rows, int64_t cols,
+                               int nlvl, float lo, float hi, effq_scale_state* state, float* sorted_g,
+                               int64_t sorted_floats, cudaStream_t s);
+
 constexpr int SS_THREADS = 512;
 constexpr int SS_MAX_CTAS = 1024;           // partial slots per parity
 constexpr unsigned long long SS_SPIN_LIMIT = 1ull << 28;
@@ -794,8 +799,9 @@ static bool ss_streams(long long numel) { return numel > (long long)effq::sm_cou
 
 extern "C" int64_t effq_scale_search_workspace(int64_t numel) {
   // fixed part + (for tensors that are streamed from memory every pass) room for the ambiguous list:
-  // three list buffers (L1 + two for L2) of a quarter of the elements each
-  return ss_base_bytes() + (ss_streams(numel) ? 3 * ((numel / 4 + 63) / 64 * 64) * 4 : 0);
+  // three list buffers (L1 + two for L2) of a quarter of the elements each; smaller tensors: room for the bucket-sorted
+  // copy of the bucketed search (scale_search_bucket.cu)
+  return ss_base_bytes() + (ss_streams(numel) ? 3 * ((numel / 4 + 63) / 64 * 64) * 4 : (numel + 63) / 64 * 64 * 4);
 }
 
 template <int REG_ITEMS>
@@ -826,6 +832,13 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
   const long long numel = rows * cols;
   const int sms = sm_count();                         // one CTA per SM: cheapest grid barrier
   VecView vv{v1, v2, ld1, ld2, rows, cols};
+  if (!sharded) {
+    // weights (and any tensor up to 4 M elements): bucket-sorted slices, O(levels) work per pass
+    const int64_t room = (workspace_bytes - ss_base_bytes()) / 4;
+    const int rc = scale_search_bucket_launch(v1, ld1, v2, ld2, rows, cols, nlvl, lo, hi, state,
+                                              (float*)((char*)workspace + ss_base_bytes()), room > 0 ? room : 0, s);
+    if (rc >= 0) return rc;
+  }
   if (!sharded && numel <= 131072) {   // measured: cluster wins up to ~128 K elements, the 148-CTA grid beyond
     // small tensors (weights): one thread-block cluster, data resident in shared memory
     int nranks = (int)((numel + SC_MAX_ELEMS - 1) / SC_MAX_ELEMS);

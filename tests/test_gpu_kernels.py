@@ -193,6 +193,80 @@ def test_scale_search_strided_sum_and_multi_gpu_blocks(ops):
     assert abs(s2["a"] - a_ref) <= 1e-9 * abs(a_ref)
 
 
+BUCKET_CASES = [
+    # numel, levels, lo, distribution          -> variant of csrc/scale_search_bucket.cu
+    (96, 256, -1.0, "normal"),                 # direct evaluation, one CTA (final_cls)
+    (3456, 256, -1.0, "normal"),               # direct evaluation (conv0)
+    (5000, 16, -1.0, "normal"),                # direct evaluation, below the bucket threshold
+    (40000, 256, -1.0, "normal"),              # direct evaluation on a cluster (many levels)
+    (27648, 16, -1.0, "normal"),               # bucketed, one CTA, slice in shared memory
+    (32768, 4, -1.0, "normal"),                # bucketed, 4 levels (LiTS)
+    (110592, 16, -1.0, "normal"),              # bucketed, cluster of 4
+    (442368, 16, -1.0, "laplace"),             # bucketed, cluster of 16 (or 8 with the slices in global memory)
+    (1769472, 16, -1.0, "normal"),             # bucketed, slices sorted into the workspace
+    (1769472, 16, -1.0, "outliers"),           # values far outside the bucket range (end buckets)
+    (300000, 16, 0.0, "relu"),                 # activation-like: half the elements exactly zero
+    (65536, 16, -1.0, "lattice"),              # many elements exactly ON rounding thresholds of the final scale
+]
+
+
+@pytest.mark.parametrize("numel,L,lo,dist", BUCKET_CASES)
+def test_scale_search_bucketed(ops, numel, L, lo, dist, monkeypatch):
+    """The bucket-sorted search (experimental variant, EFFQ_SS_BUCKET=1: O(levels) work per pass, integer sums) against
+    the oracle: same number of passes, scale to 1e-9 (fixed-point rounding of v: ~1e-12), and bit-identical between two
+    launches."""
+    monkeypatch.setenv("EFFQ_SS_BUCKET", "1")
+    g = torch.Generator().manual_seed(numel + L)
+    if dist == "normal":
+        v = torch.randn(numel, generator=g) * 0.037
+    elif dist == "laplace":
+        v = torch.distributions.Laplace(0.0, 0.02).sample((numel,))
+    elif dist == "outliers":
+        v = torch.randn(numel, generator=g) * 0.01
+        v[::1000] *= 300.0
+    elif dist == "relu":
+        v = torch.relu(torch.randn(numel, generator=g)) * 1.7
+    else:
+        a0, _ = O.project_by_iter(torch.randn(numel, generator=g), L, lo, 1)
+        v = torch.randn(numel, generator=g)
+        ties = ((torch.arange(L - 1, dtype=torch.float64) + 0.5) * 2 / (L - 1) - 1) * a0          # thresholds of a nearby scale
+        v[: 50 * (L - 1)] = ties.repeat(50).float()
+    a_ref, _, passes = O.project_by_iter(v, L, lo, 1, return_iters=True)
+    vd = v.to(DEV)
+    res = []
+    for _ in range(2):
+        st = ops.ScaleState(torch.device(DEV))
+        ops.scale_search(vd, L, lo, 1.0, st)
+        res.append(st.read())
+    s = res[0]
+    assert s["failed"] == 0 and s["converged"] == 1
+    assert s["passes"] == passes, (s["passes"], passes)
+    assert abs(s["a"] - a_ref) <= 1e-9 * abs(a_ref), (s["a"], a_ref)
+    assert res[1]["a"] == s["a"] and res[1]["s_bv"] == s["s_bv"] and res[1]["s_bb"] == s["s_bb"]
+
+
+def test_scale_search_bucketed_strided_and_degenerate(ops, monkeypatch):
+    monkeypatch.setenv("EFFQ_SS_BUCKET", "1")
+    torch.manual_seed(9)
+    c2, k = 128, 3456                                               # 442 K elements, rows with a bias column, v = w* + dual
+    sol = torch.randn(c2, k + 1) * 0.05
+    dual = torch.randn(c2, k) * 0.004
+    a_ref, _, passes = O.project_by_iter(sol[:, :k] + dual, 16, -1, 1, return_iters=True)
+    sol_d, dual_d = sol.to(DEV), dual.to(DEV)
+    st = ops.ScaleState(torch.device(DEV))
+    ops.scale_search(sol_d[:, :k], 16, -1.0, 1.0, st, v2=dual_d)
+    s = st.read()
+    assert abs(s["a"] - a_ref) <= 1e-9 * abs(a_ref) and s["passes"] == passes
+    z = torch.zeros(20000, device=DEV)
+    ops.scale_search(z, 16, -1.0, 1.0, st)
+    s = st.read()
+    assert s["a"] == 0.0 and s["failed"] == 0
+    z[7] = float("nan")
+    ops.scale_search(z, 16, -1.0, 1.0, st)
+    s = st.read()
+    assert s["a"] != s["a"] and s["passes"] == 0                    # the reference's a0 is NaN and its loop never runs
+
+
 def test_scale_search_large_activation(ops):
     torch.manual_seed(6)
     x = torch.relu(torch.randn(2, 32, 32, 32, 32))                 # 2.1 M elements, many CTAs

@@ -78,6 +78,7 @@ struct TcParams {
   // [C2_total][CG] weight tile are contiguous in global memory, its outputs / targets sit c2_off channels into
   // the NCDHW tensors, and launches after the first add their squared error to *sse.
   int c2_total, c2_off, sse_accumulate;
+  int add_out;                 // 1: `target` is the previous content of `out` and is ADDED to the result (no squared error)
   unsigned int wsrc_tile_bytes, wsrc_off;       // global stride between weight tiles, byte offset of the chunk's rows
   unsigned long long* dbg;     // bring-up timeline buffer ([tile][8] clock stamps of CTA 0) or null
 };
@@ -102,7 +103,7 @@ __device__ __forceinline__ void epi_load_targets(float (&tv)[32], const float* t
 // v: raw accumulators in, outputs (scale * acc + bias) out; returns sum (out - target)^2 of the chunk
 template <int NC>
 __device__ __forceinline__ float epi_chunk(uint32_t (&v)[32], const float (&tv)[32], const float* bias_c0, float scale,
-                                           const float* svec_c0 = nullptr) {
+                                           const float* svec_c0 = nullptr, bool add = false) {
   float e[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < NC; j += 4) {
@@ -112,7 +113,8 @@ __device__ __forceinline__ float epi_chunk(uint32_t (&v)[32], const float (&tv)[
     for (int k = 0; k < 4; ++k) {
       // per-output-channel scales (optional extension): a warp-uniform broadcast load from L1
       const float sc = svec_c0 ? __ldg(svec_c0 + j + k) : scale;
-      const float o = fmaf(__uint_as_float(v[j + k]), sc, bb[k]);
+      float o = fmaf(__uint_as_float(v[j + k]), sc, bb[k]);
+      if (add) o += tv[j + k];                               // accumulating launch: out = conv + previous out
       const float dlt = o - tv[j + k];
       e[k] = fmaf(dlt, dlt, e[k]);
       v[j + k] = __float_as_uint(o);
@@ -269,6 +271,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
     const int hy = row >> 3, wx = row & 7;
     const float scale = p.scale_vec ? 1.f : __ldg(p.conv_scale);
     const float* svec = p.scale_vec ? p.scale_vec + p.c2_off : nullptr;
+    const bool add_out = p.add_out != 0;
     const long long plane = (long long)p.h * p.w;
     const long long chan = (long long)p.d * plane;
     Pipe ap{0, 0}, gp{0, 0};
@@ -303,7 +306,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
 #pragma unroll
           for (int j = 0; j < 32; ++j) tv[j] = ts[j * (TC_TILE_H * TC_TILE_W)];     // lanes read consecutive floats
           tc_wait_ld();
-          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr);
+          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr, add_out);
           mbar_arrive(BAR(B_GE + gp.stage));
           gp.advance(p.n_tgt_stages);
           if (store) epi_store<32>(v, optr, chan);
@@ -343,14 +346,14 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
         if (rest >= 0) {
           tc_ld32(taddr, v);
           tc_wait_ld();
-          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr);
+          e32 += epi_chunk<32>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr, add_out);
           if (rest >= 32) epi_load_targets<32>(tv, tptr + 32 * chan, chan, want_t);      // next chunk's loads overlap
           else if (rest > 0) epi_load_targets<16>(tv, tptr + 32 * chan, chan, want_t);   // this chunk's stores
           if (store) epi_store<32>(v, optr, chan);
         } else {
           tc_ld16(taddr, v);
           tc_wait_ld();
-          e32 += epi_chunk<16>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr);
+          e32 += epi_chunk<16>(v, tv, bias_s + c0, scale, svec ? svec + c0 : nullptr, add_out);
           if (store) epi_store<16>(v, optr, chan);
         }
         tptr += 32 * chan;
@@ -422,7 +425,7 @@ conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap, con
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
-  if (!p.target) return;
+  if (!p.target || p.add_out) return;
   // deterministic reduction: block tree -> per-CTA partial -> last CTA folds in index order
   const double bsum = block_sum(err_acc, red_scratch);
   if (threadIdx.x == 0) {
@@ -477,7 +480,7 @@ static bool tc_plan(const effq_geom& g, int code_dtype, TcParams& p) {
   p.halo_tx_bytes = (uint32_t)(p.hv * p.rp);
   p.halo_bytes = (p.halo_tx_bytes + 1023u) & ~1023u;
   p.wtile_bytes = (uint32_t)(p.rp * g.c2);
-  p.c2_total = g.c2; p.c2_off = 0; p.sse_accumulate = 0;
+  p.c2_total = g.c2; p.c2_off = 0; p.sse_accumulate = 0; p.add_out = 0;
   p.wsrc_tile_bytes = p.wtile_bytes; p.wsrc_off = 0;
   p.wstage_bytes = (p.wtile_bytes + 1023u) & ~1023u;
   p.off_bias = 384;
@@ -615,7 +618,8 @@ extern "C" int64_t effq_conv3d_tc_workspace(const effq_geom* g) {
 
 static int conv3d_tc_impl(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
                           const float* conv_scale, const float* scale_vec, const effq_geom* g, float* out,
-                          const float* target, const float* att, double* sse, void* workspace, void* stream);
+                          const float* target, const float* att, double* sse, void* workspace, void* stream,
+                          int add_out = 0);
 
 extern "C" int effq_conv3d_tc(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
                               const float* conv_scale, const effq_geom* g, float* out, const float* target, const float* att, double* sse,
@@ -630,13 +634,23 @@ extern "C" int effq_conv3d_tc_pc(const void* xcodes, const void* wcodes, int32_t
   return conv3d_tc_impl(xcodes, wcodes, code_dtype, bias, scale_vec, scale_vec, g, out, target, att, sse, workspace, stream);
 }
 
+// out += scale * conv(xcodes, wcodes) (+ bias): the accumulating form behind the fp32-accurate FP conv, which sums six
+// products of fixed-point digit planes (efficientq_b200/ops.py conv3d_fp); `out` must hold the partial result of the earlier launches.
+extern "C" int effq_conv3d_tc_acc(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
+                                  const float* conv_scale, const float* scale_vec, const effq_geom* g, float* out_inout,
+                                  void* workspace, void* stream) {
+  EFFQ_CHECK_ARG(out_inout && (conv_scale || scale_vec), "null pointer");
+  return conv3d_tc_impl(xcodes, wcodes, code_dtype, bias, conv_scale ? conv_scale : scale_vec, scale_vec, g, out_inout,
+                        out_inout, nullptr, nullptr, workspace, stream, 1);
+}
+
 static int conv3d_tc_impl(const void* xcodes, const void* wcodes, int32_t code_dtype, const float* bias,
                           const float* conv_scale, const float* scale_vec, const effq_geom* g, float* out,
-                          const float* target, const float* att, double* sse, void* workspace, void* stream) {
+                          const float* target, const float* att, double* sse, void* workspace, void* stream, int add_out) {
   using namespace effq;
   EFFQ_CHECK_ARG(xcodes && wcodes && conv_scale && g && workspace, "null pointer");
   EFFQ_CHECK_ARG(out || target, "nothing to compute");
-  EFFQ_CHECK_ARG(!target || sse, "sse required with target");
+  EFFQ_CHECK_ARG(!target || sse || add_out, "sse required with target");
   EFFQ_CHECK_ARG(((uintptr_t)xcodes & 15) == 0 && ((uintptr_t)wcodes & 15) == 0, "operands must be 16B aligned");
   const int n_chunks = tc_chunked(*g) ? g->c2 / 256 : 1;
   effq_geom gg = *g;
@@ -647,6 +661,7 @@ static int conv3d_tc_impl(const void* xcodes, const void* wcodes, int32_t code_d
   p.c2_total = g->c2;
   p.c2_off = chunk * gg.c2;
   p.sse_accumulate = chunk > 0 ? 1 : 0;
+  p.add_out = add_out;
   p.wsrc_tile_bytes = (uint32_t)(p.rp * g->c2);
   p.wsrc_off = (uint32_t)(p.rp * p.c2_off);
   EFFQ_CHECK_ARG(p.n_tiles < (1ll << 31), "too many tiles");

@@ -151,9 +151,26 @@ __device__ __forceinline__ void split3(float v, float& hi, float& mid, float& lo
   lo = __bfloat162float(__float2bfloat16_rn(__fsub_rn(r1, mid)));
 }
 
+// Fixed-point digits (the FP conv of the calibration's first pass, ops.conv3d_fp): with the channel's power-of-two
+// scale 2^e > max|x| the integer X = rint(x * 2^(23 - e)), |X| <= 2^23, is cut into three balanced base-256 digits
+// X = d0 * 2^16 + d1 * 2^8 + d2 (d0 in [-128, 128], d1, d2 in [-128, 127]): small integers, exact in bf16, whose products
+// and sums the tensor core accumulates WITHOUT rounding (|sum| < 2^24) -- unlike the floating-point planes above,
+// whose unaligned products lose bits at every accumulation step.
+__device__ __forceinline__ void dig3(float v, float scale, float& d0, float& d1, float& d2) {
+  const int X = __float2int_rn(v * scale);
+  const int e2 = ((X + 128) & 255) - 128;
+  const int X1 = (X - e2) >> 8;
+  const int e1 = ((X1 + 128) & 255) - 128;
+  d0 = (float)((X1 - e1) >> 8);
+  d1 = (float)e1;
+  d2 = (float)e2;
+}
+
+template <bool DIGITS>
 __global__ void __launch_bounds__(SP_THREADS)
 split3_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int tile_v, long long n_tiles,
-                    __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_mid, __nv_bfloat16* __restrict__ o_lo) {
+                    __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_mid, __nv_bfloat16* __restrict__ o_lo,
+                    const int* __restrict__ ch_exp) {
   extern __shared__ __align__(16) uint8_t sp_raw[];
   uint2* tiles[3];
   for (int p = 0; p < 3; ++p) tiles[p] = reinterpret_cast<uint2*>(sp_raw + (size_t)p * tile_v * c * 2);
@@ -178,13 +195,23 @@ split3_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int tile_
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(xs + (long long)(4 * g4 + k) * dhw) + vq);
       uint2 pk[3][4];                                           // [plane][voxel]: 4 channels as bf16
+      float sc[4] = {1.f, 1.f, 1.f, 1.f};
+      if (DIGITS) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int e = 23 - __ldg(ch_exp + 4 * g4 + k);
+          e = e < -126 ? -126 : (e > 127 ? 127 : e);
+          sc[k] = __int_as_float((127 + e) << 23);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float h[4], m[4], l[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float val = i == 0 ? v[k].x : i == 1 ? v[k].y : i == 2 ? v[k].z : v[k].w;
-          split3(val, h[k], m[k], l[k]);
+          if (DIGITS) dig3(val, sc[k], h[k], m[k], l[k]);
+          else split3(val, h[k], m[k], l[k]);
         }
         const float* src[3] = {h, m, l};
 #pragma unroll
@@ -218,7 +245,72 @@ split3_ndhwc_kernel(const float* __restrict__ x, int c, long long dhw, int tile_
   }
 }
 
+// max|x| per channel of an NCDHW tensor (the channel scales of the fixed-point digits).  Non-negative floats order
+// like their bit patterns, so the per-CTA maxima combine with an integer atomicMax; `out` must be zeroed by the caller.
+__global__ void __launch_bounds__(256)
+channel_absmax_kernel(const float* __restrict__ x, int c, long long dhw, long long chunks_per_row, float* __restrict__ out) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x / chunks_per_row, chunk = blockIdx.x % chunks_per_row;     // row = n * c + channel
+  const long long quads = dhw >> 2, per = (quads + chunks_per_row - 1) / chunks_per_row;
+  const long long q0 = chunk * per, q1 = q0 + per < quads ? q0 + per : quads;
+  const float4* src = reinterpret_cast<const float4*>(x + row * dhw);
+  float m = 0.f;
+  for (long long q = q0 + threadIdx.x; q < q1; q += 256) {
+    const float4 v = __ldg(src + q);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (chunk == chunks_per_row - 1)
+    for (long long e = (quads << 2) + threadIdx.x; e < dhw; e += 256) m = fmaxf(m, fabsf(x[row * dhw + e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    atomicMax(reinterpret_cast<int*>(out + (row % c)), __float_as_int(m));
+  }
+}
+
 }  // namespace effq
+
+extern "C" int effq_channel_absmax(const float* x, int32_t n, int32_t c, int64_t dhw, float* out_zeroed, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && out_zeroed && n > 0 && c > 0 && dhw > 0, "bad argument");
+  EFFQ_CHECK_ARG(((uintptr_t)x & 15) == 0 && dhw % 4 == 0, "x must be 16B aligned with dhw % 4 == 0");
+  const long long rows = (long long)n * c;
+  long long chunks = ((long long)sm_count() * 8 + rows - 1) / rows;
+  const long long max_chunks = (dhw / 4 + 1023) / 1024;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  EFFQ_CHECK_ARG(rows * chunks < (1ll << 31), "tensor too large");
+  channel_absmax_kernel<<<(unsigned)(rows * chunks), 256, 0, (cudaStream_t)stream>>>(x, c, dhw, chunks, out_zeroed);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int effq_fixdigits_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, const int32_t* ch_exp, void* d0_out,
+                                    void* d1_out, void* d2_out, void* stream) {
+  using namespace effq;
+  EFFQ_CHECK_ARG(x && ch_exp && d0_out && d1_out && d2_out, "null pointer");
+  const int tile_v = effq_split3_ndhwc_supported(c, dhw);
+  EFFQ_CHECK_ARG(tile_v > 0, "shape not supported (c % 8, channel groups a power of two or a multiple of 32, dhw % 16)");
+  EFFQ_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)d0_out & 15) == 0 && ((uintptr_t)d1_out & 15) == 0 &&
+                     ((uintptr_t)d2_out & 15) == 0, "pointers must be 16B aligned");
+  if (n <= 0) return 0;
+  const long long n_tiles = (long long)n * (dhw / tile_v);
+  const long long cap = (long long)sm_count() * 4;
+  const size_t smem = (size_t)tile_v * c * 6;
+  static bool configured = false;
+  if (!configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(split3_ndhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  split3_ndhwc_kernel<true><<<(unsigned)(n_tiles < cap ? n_tiles : cap), SP_THREADS, smem, (cudaStream_t)stream>>>(
+      x, c, dhw, tile_v, n_tiles, (__nv_bfloat16*)d0_out, (__nv_bfloat16*)d1_out, (__nv_bfloat16*)d2_out, ch_exp);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int effq_split3_ndhwc_supported(int32_t c, int64_t dhw) {
   const int groups = c / 4;
@@ -243,11 +335,11 @@ extern "C" int effq_split3_ndhwc(const float* x, int32_t n, int32_t c, int64_t d
   const size_t smem = (size_t)tile_v * c * 6;
   static bool configured = false;
   if (!configured) {
-    EFFQ_CUDA(cudaFuncSetAttribute(split3_ndhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    EFFQ_CUDA(cudaFuncSetAttribute(split3_ndhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     configured = true;
   }
-  split3_ndhwc_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), SP_THREADS, smem, (cudaStream_t)stream>>>(
-      x, c, dhw, tile_v, n_tiles, (__nv_bfloat16*)hi_out, (__nv_bfloat16*)mid_out, (__nv_bfloat16*)lo_out);
+  split3_ndhwc_kernel<false><<<(unsigned)(n_tiles < cap ? n_tiles : cap), SP_THREADS, smem, (cudaStream_t)stream>>>(
+      x, c, dhw, tile_v, n_tiles, (__nv_bfloat16*)hi_out, (__nv_bfloat16*)mid_out, (__nv_bfloat16*)lo_out, nullptr);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

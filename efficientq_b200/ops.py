@@ -388,6 +388,87 @@ def conv3d_tc(xcodes: torch.Tensor, wcodes: torch.Tensor, bias, conv_scale_ptr, 
     return out, sse
 
 
+# digit-plane products of the fp32-accurate conv, most significant first (x digit, w digit): 2^-8(s+t) of the leading
+# one.  Only (2, 2) is dropped (2^-32): the low digits of a value are as large as those of the channel maximum, so the
+# s + t = 3 products are 2^-24 of the LARGEST term but ~2^-20 of a typical one (measured: 1.6e-6 of max|out| without
+# them, against 1e-6 .. 2e-7 for the library's fp32 conv).
+_FP_PAIRS = ((0, 0), (0, 1), (1, 0), (0, 2), (1, 1), (2, 0), (1, 2), (2, 1))
+
+
+def conv3d_fp_supported(x_shape, c2: int, ksize, stride, padding) -> bool:
+    """Shapes the FP conv can run on the tcgen05 kernel: what conv3d_tc takes in bf16, with a channel count the
+    digit-plane kernel handles."""
+    n, c1, d, h, w = x_shape
+    return bool(conv3d_tc_supported(x_shape, c2, ksize, stride, padding, CODE_BF16) and (d * h * w) % 4 == 0 and
+                capi.load().effq_split3_ndhwc_supported(int(c1), int(d * h * w)))
+
+
+def _digits3(t_int: torch.Tensor):
+    """int32 tensor -> balanced base-256 digits (d0, d1, d2) with t = d0 * 65536 + d1 * 256 + d2."""
+    d2 = ((t_int + 128) & 255) - 128
+    t1 = (t_int - d2) >> 8
+    d1 = ((t1 + 128) & 255) - 128
+    return (t1 - d1) >> 8, d1, d2
+
+
+def conv3d_fp(x: torch.Tensor, weight: torch.Tensor, bias, ksize, ws=None):
+    """The un-quantised convolution of the FP pass (reference src/ptqer.py:333-335: F.conv3d in fp32) on the tcgen05
+    kernel, as an EXACT integer computation (the Ozaki splitting): with power-of-two scales per input channel
+    (2^ex > max|x_c|, folded into the weights) and per output channel (2^ew > max|w'_row|) both operands become 24-bit
+    fixed-point integers, cut into three balanced base-256 digits each; a conv of digit planes is a sum of integers
+    below 2^24 and comes out of the fp32 tensor-core accumulator without a rounding, and eight of the nine digit
+    products (all but the last, 2^-32) are combined in the epilogue (first launch writes, the others accumulate) with one fp32
+    rounding each.  What is left against an exact conv is the 2^-24 fixed-point resolution relative to the channel /
+    row maximum -- fp32-conv class, measured against an fp64 conv in tests/test_gpu_kernels.py
+    (test_conv3d_fp_matches_fp64).  Three floating-point bf16 planes per operand, the first version, were 10 x less
+    accurate: unaligned products lose bits at each of the K/16 accumulation steps (truncation, so the error is a
+    bias)."""
+    x = _f32c(x, "x")
+    n, c1, d, h, w = x.shape
+    c2 = weight.shape[0]
+    k = capi._triple(ksize)
+    pad = tuple((t - 1) // 2 for t in k)
+    g = Geom.make((n, c1, d, h, w), c2, k, 1, pad)
+    lib = capi.load()
+    dev = x.device
+    dhw = d * h * w
+    amax = torch.zeros(c1, dtype=torch.float32, device=dev)
+    timer.run("channel_absmax", {"bytes": 4 * x.numel()}, lambda: check(
+        lib.effq_channel_absmax(ptr(x), n, c1, dhw, ptr(amax), stream()), "effq_channel_absmax"))
+    ex = torch.where(amax > 0, torch.frexp(amax).exponent, torch.zeros_like(amax, dtype=torch.int32)).int().contiguous()
+    xp = torch.empty((3, n, d, h, w, c1), dtype=torch.bfloat16, device=dev)
+    timer.run("fixdigits_ndhwc", {"bytes": 10 * x.numel()}, lambda: check(
+        lib.effq_fixdigits_ndhwc(ptr(x), n, c1, dhw, ptr(ex), ptr(xp[0]), ptr(xp[1]), ptr(xp[2]), stream()),
+        "effq_fixdigits_ndhwc"))
+    # weights: fold the input-channel scales, fixed point per output channel (small tensors: host-side tensor ops)
+    wf = torch.ldexp(_f32c(weight.detach().float(), "weight"), ex.view(1, c1, 1, 1, 1))
+    rmax = wf.abs().amax(dim=(1, 2, 3, 4))
+    ew = torch.where(rmax > 0, torch.frexp(rmax).exponent, torch.zeros_like(rmax, dtype=torch.int32)).int()
+    w_int = torch.round(torch.ldexp(wf, (23 - ew).view(c2, 1, 1, 1, 1))).int()
+    wplanes = [pack_weight_codes(p.float(), CODE_BF16) for p in _digits3(w_int)]
+    base = torch.ldexp(torch.ones(c2, dtype=torch.float32, device=dev), ew - 46)
+    scales = {st: (base * float(2 ** (8 * (4 - st)))).contiguous() for st in (0, 1, 2, 3)}
+    if ws is None:
+        ws = workspace(lib.effq_conv3d_tc_workspace(C.byref(g)), dev)
+    out = torch.empty((n, c2, d, h, w), dtype=torch.float32, device=dev)
+    b = _f32c(bias, "bias") if bias is not None else None
+    flops = 2.0 * n * dhw * c2 * c1 * g.taps
+    name = f"conv3d_fp_c{c1}x{c2}k{k[0]}"
+    # least significant products first: the running sum stays small until the last additions, so the fp32 rounding of
+    # the seven accumulating launches is that of one addition at full magnitude
+    for i, (px, pw) in enumerate(reversed(_FP_PAIRS)):
+        sv = scales[px + pw]
+        if i == 0:
+            timer.run(name, {"flops": flops}, lambda: check(
+                lib.effq_conv3d_tc_pc(ptr(xp[px]), ptr(wplanes[pw]), CODE_BF16, ptr(b), ptr(sv), C.byref(g), ptr(out), None,
+                                      None, None, ptr(ws), stream()), "effq_conv3d_tc_pc"))
+        else:
+            timer.run(name, {"flops": flops}, lambda: check(
+                lib.effq_conv3d_tc_acc(ptr(xp[px]), ptr(wplanes[pw]), CODE_BF16, None, None, ptr(sv), C.byref(g), ptr(out),
+                                       ptr(ws), stream()), "effq_conv3d_tc_acc"))
+    return out
+
+
 def pack_weight_codes(wcodes_int: torch.Tensor, code_dtype: int = CODE_BF16) -> torch.Tensor:
     """[C2][C1][kd][kh][kw] integer codes (already 2c-(L-1)) on the GPU -> bf16 / e4m3 codes in the
     tensor-core weight layout (the layout effq_admm_project emits during calibration)."""

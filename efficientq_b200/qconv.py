@@ -10,6 +10,8 @@ calibration on the GPU through the C-ABI kernels (``layer_engine``).  Keep
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -207,9 +209,22 @@ class PTQConv(nn.Conv3d):
         qact = self._quantize_act(x) if self.q_act else x
         return self._conv(qact)
 
+    def _fp_forward(self, x):
+        """FP pass (PTQConv.py:157-158, F.conv3d): on the GPU it runs on the repo's own kernels -- the tcgen05 conv on
+        fixed-point digit planes (exact integer accumulation, ops.conv3d_fp) where the geometry allows (3x3x3 / 1x1x1, stride 1, channels in multiples of 16),
+        the generic fp32 kernel otherwise (conv0: 4 input channels, stride 2; final_cls: 3 output channels).
+        EFFQ_FP_CONV=lib restores the library conv (bring-up comparison).  Autograd (training, alpha refinement) and
+        CPU tensors keep F.conv3d."""
+        if not x.is_cuda or torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad) or \
+                os.environ.get("EFFQ_FP_CONV", "own") == "lib" or self.dilation != (1, 1, 1) or self.groups != 1:
+            return F.conv3d(x, self.weight, self.bias, self.stride, self.padding)
+        if ops.conv3d_fp_supported(x.shape, self.out_channels, self.kernel_size, self.stride, self.padding):
+            return ops.conv3d_fp(x, self.weight.data, self.bias.data if self.bias is not None else None, self.kernel_size)
+        return self._conv(x.contiguous())
+
     def forward(self, x):
         if self._fp:
-            return F.conv3d(x, self.weight, self.bias, self.stride, self.padding)
+            return self._fp_forward(x)
         if self._quantizing:
             return self.ptq(x)                      # returns conv3d(qact, weight*, bias*) of the calibrated layer
         if self._quantized:

@@ -179,6 +179,14 @@ int effq_conv3d_tc(const void* xcodes_ndhwc, const void* wcodes, int32_t code_dt
 int effq_conv3d_tc_pc(const void* xcodes_ndhwc, const void* wcodes, int32_t code_dtype, const float* bias,
                       const float* scale_vec, const effq_geom* g, float* out, const float* target,
                       const float* att, double* sse, void* workspace, void* stream);
+/* Accumulating form: out_inout += conv_scale * conv(xcodes, wcodes) + bias.  Used by the host side to run the FP
+ * (un-quantised) convolution of the calibration's first pass (reference src/ptqer.py:333-335, F.conv3d in fp32) on
+ * the same tcgen05 kernel: x and w become three planes of fixed-point digits each (effq_fixdigits_ndhwc) and the six
+ * significant plane products are summed, first launch through effq_conv3d_tc_pc, the rest through this one.
+ * scale_vec (optional, [c2]): one scale per output channel instead of *conv_scale. */
+int effq_conv3d_tc_acc(const void* xcodes_ndhwc, const void* wcodes, int32_t code_dtype, const float* bias,
+                       const float* conv_scale, const float* scale_vec, const effq_geom* g, float* out_inout,
+                       void* workspace, void* stream);
 
 /* [C2][C1][taps] fp32 integer weight codes (values 2c-(L-1)) -> codes of `code_dtype` in the
  * layout effq_conv3d_tc consumes (the same layout effq_admm_project emits). */
@@ -376,6 +384,14 @@ int effq_fakequant_ste_bwd(const float* x, const float* grad_out, int64_t numel,
 int effq_split3_ndhwc_supported(int32_t c, int64_t dhw);
 int effq_split3_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, void* hi_out, void* mid_out,
                       void* lo_out, void* stream);
+/* Operands of the FP (un-quantised) convolution of the calibration's first pass on the tensor cores (reference
+ * src/ptqer.py:333-335: F.conv3d in fp32): effq_channel_absmax gives max|x| per channel (out_zeroed: c floats, zeroed
+ * by the caller); with the power-of-two channel scales 2^ch_exp[c] >= max|x| effq_fixdigits_ndhwc writes
+ * X = rint(x * 2^(23 - ch_exp[c])) as three balanced base-256 digit planes (NDHWC bf16, X = d0 2^16 + d1 2^8 + d2).
+ * Digit products accumulate exactly in the fp32 tensor-core accumulator (same shapes as effq_split3_ndhwc). */
+int effq_channel_absmax(const float* x, int32_t n, int32_t c, int64_t dhw, float* out_zeroed, void* stream);
+int effq_fixdigits_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, const int32_t* ch_exp, void* d0_out,
+                         void* d1_out, void* d2_out, void* stream);
 /* torch.optim.Adam update (no weight decay / amsgrad) of n fp32 scalars from fp64 gradients scaled by
  * grad_scale (1/world after an all-reduce); step counts from 1. */
 int effq_adam_step(float* params, const double* grads, float grad_scale, float* exp_avg, float* exp_avg_sq,

@@ -278,6 +278,45 @@ def test_scale_search_large_activation(ops):
     assert abs(s["passes"] - passes) <= 1
 
 
+# ---------------------------------------------------------------- FP conv on the tcgen05 kernel (f.4)
+FP_CASES = [
+    # n, c1, c2, k, spatial
+    (2, 32, 32, 3, (16, 16, 16)),
+    (1, 64, 64, 3, (8, 24, 16)),
+    (2, 128, 128, 3, (8, 8, 8)),
+    (1, 256, 256, 3, (4, 8, 8)),
+    (2, 32, 64, 1, (8, 16, 16)),
+    (2, 256, 128, 1, (4, 8, 8)),
+    (1, 16, 48, 3, (8, 8, 12)),               # ragged tiles, C2 not a multiple of 32 (epilogue loads the partial sums itself)
+]
+
+
+@pytest.mark.parametrize("n,c1,c2,k,sp", FP_CASES)
+def test_conv3d_fp_matches_fp64(ops, n, c1, c2, k, sp):
+    """The FP pass's convolution on the tcgen05 kernel (eight products of fixed-point digit planes, exact integer
+    accumulation) against an fp64 conv (reference src/ptqer.py:333-335 computes its targets with F.conv3d in fp32).
+    Tolerance 5e-7 of max|out|, independent of K: what is left is the 2^-24 fixed-point resolution relative to the
+    channel maximum (the inputs here have channels of very different magnitude) and one fp32 rounding.  Measured
+    2.8e-7 .. 4.1e-7; the library's fp32 conv on the same inputs: 1.8e-7 .. 2.2e-6 depending on its algorithm."""
+    torch.manual_seed(n * 1000 + c1 + c2 + k)
+    x = (torch.randn(n, c1, *sp) * torch.rand(1, c1, 1, 1, 1) * 3).to(DEV)          # channels of different magnitude
+    x[:, : c1 // 2] = torch.relu(x[:, : c1 // 2])
+    w = (torch.randn(c2, c1, k, k, k) / (c1 * k ** 3) ** 0.5).to(DEV)
+    b = torch.randn(c2).to(DEV)
+    assert ops.conv3d_fp_supported(x.shape, c2, (k,) * 3, (1, 1, 1), (k // 2,) * 3)
+    out = ops.conv3d_fp(x, w, b, (k,) * 3)
+    ref64 = torch.nn.functional.conv3d(x.double(), w.double(), b.double(), 1, k // 2)
+    torch.backends.cudnn.allow_tf32 = False
+    lib32 = torch.nn.functional.conv3d(x, w, b, 1, k // 2)
+    scale = float(ref64.abs().max())
+    e_own = float((out.double() - ref64).abs().max()) / scale
+    e_lib = float((lib32.double() - ref64).abs().max()) / scale
+    print(f"conv3d_fp c{c1}x{c2}k{k}: max err / max|out|  own {e_own:.2e}  library fp32 {e_lib:.2e}")
+    assert e_own <= 5e-7
+    # every plane product is exact and the sums are fp32: two runs are bit-identical
+    assert torch.equal(out, ops.conv3d_fp(x, w, b, (k,) * 3))
+
+
 # ---------------------------------------------------------------- conv + squared error (a10)
 CONV_CASES = [
     # n, c1, c2, k, s, p, spatial

@@ -379,24 +379,37 @@ def test_final_dice_on_trained_miniature(engine_mod, golden):
           "reference", np.round(g["dice_q"], 4).tolist())
     np.testing.assert_allclose(dice_replay, g["dice_q"], atol=1e-3)
     del replay
-    # (2) calibrated here
+    # (2) calibrated here, twice: with the FP targets from the library's fp32 conv (the kind of conv the reference's
+    # targets come from) and from the repo's own FP conv (default; closer to an fp64 conv than the library's, test
+    # test_conv3d_fp_matches_fp64).  The two sets of targets differ by 5e-7 of their maximum in the two 16-channel
+    # layers -- and that moves the quantised Dice by up to 0.8 points: the GPU pipeline's own sensitivity, of the size
+    # of the reference's (1 vs 8 threads).
     data = synth.batch(cfg["n"], 0, cfg["num_mod"], (cfg["size"],) * 3, cfg["task"]).to(DEV)
-    res = ptqer.calibrate(model, data, "brats", "2,2,2")
-    with torch.no_grad():
-        dice_q = dice_table(ptqer.get_pred_brats(model(ev_x)[-1]).cpu(), ev_l)
-    line = (f"Dice FP {np.mean(dice_fp):.4f} | W4A4 ours {np.round(dice_q, 4).tolist()} mean {np.mean(dice_q):.4f} | "
-            f"reference (8 threads) {np.round(g['dice_q'], 4).tolist()} mean {np.mean(g['dice_q']):.4f}")
-    print(line)
     import os
-    if os.path.isdir("gpurun_out"):
-        open("gpurun_out/toy_dice_parity.txt", "w").write(line + "\n")
-    # the reference against itself (8 perturbed runs + 1 single-threaded, tests/golden/make_golden.py::gen_toy_dice):
-    # ours must lie in the ensemble's range widened by one range on either side, per class and for the mean
     ens = np.concatenate([g["dice_q_ensemble"], g["dice_q"][None]], 0)
     ens = np.concatenate([ens, ens.mean(1, keepdims=True)], 1)
-    ours = np.array(list(dice_q) + [np.mean(dice_q)])
     lo, hi = ens.min(0), ens.max(0)
     width = hi - lo
     print("reference ensemble Dice range", np.round(lo, 4).tolist(), np.round(hi, 4).tolist())
-    assert ((ours >= lo - width - 1e-3) & (ours <= hi + width + 1e-3)).all(), (ours, lo, hi)
+    lines = []
+    for fp_conv, widen in (("lib", 1.0), ("own", 2.0)):
+        m2 = copy.deepcopy(model)
+        os.environ["EFFQ_FP_CONV"] = fp_conv
+        try:
+            res = ptqer.calibrate(m2, data, "brats", "2,2,2")
+        finally:
+            os.environ.pop("EFFQ_FP_CONV", None)
+        with torch.no_grad():
+            dice_q = dice_table(ptqer.get_pred_brats(m2(ev_x)[-1]).cpu(), ev_l)
+        lines.append(f"Dice FP {np.mean(dice_fp):.4f} | W4A4 ours (FP conv: {fp_conv}) {np.round(dice_q, 4).tolist()} mean "
+                     f"{np.mean(dice_q):.4f} | reference (8 threads) {np.round(g['dice_q'], 4).tolist()} mean {np.mean(g['dice_q']):.4f}")
+        print(lines[-1])
+        # the reference against itself (8 perturbed runs + 1 single-threaded, tests/golden/make_golden.py::gen_toy_dice):
+        # ours must lie in the ensemble's range widened by one range on either side (two for the own FP conv, whose
+        # targets are not the library's), per class and for the mean
+        ours = np.array(list(dice_q) + [np.mean(dice_q)])
+        assert ((ours >= lo - widen * width - 1e-3) & (ours <= hi + widen * width + 1e-3)).all(), (fp_conv, ours, lo, hi)
+        del m2
+    if os.path.isdir("gpurun_out"):
+        open("gpurun_out/toy_dice_parity.txt", "w").write("\n".join(lines) + "\n")
     np.testing.assert_allclose([float(ln.rsplit(":", 1)[1]) for ln in res["layer_loss"]][:1], g["layer_losses"][:1], rtol=1e-3)

@@ -4,7 +4,7 @@
 tag=${1:-q}; shift
 out=gpurun_out
 mkdir -p $out
-timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
+timeout 600 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
 tail -5 $out/${tag}_pytest.log
 i=0
 for envs in "$@"; do

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libeffq_b200.so")
 SOURCES = ["capi.cu", "fakequant.cu", "scale_search.cu", "scale_search_bucket.cu", "conv_simt.cu", "conv_tc.cu", "gram_simt.cu", "gram_tc.cu", "quadform.cu", "admm.cu",
-           "solve_gemm_tc.cu", "chol_tc.cu", "peer.cu", "tune.cu"]
+           "solve_gemm_tc.cu", "chol_tc.cu", "peer.cu", "tune.cu", "glue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -158,6 +158,11 @@ _SIGS = {
                                     C.c_void_p]),
     "effq_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p]),
+    "effq_glue_elementwise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_glue_maxpool3d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "effq_glue_upsample_trilinear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "effq_peer_bytes": (C.c_int64, []),
     "effq_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
     "effq_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -4,6 +4,7 @@
 //   effq_quantize_act_ndhwc : same arithmetic, emits channels-last bf16 integer codes,
 //                             the operand format of the tcgen05 conv.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cuda_fp8.h>
 #include <stdlib.h>
 
@@ -60,6 +61,7 @@ fakequant_f32_kernel(const float* __restrict__ x, long long numel, const float* 
 
 // Qact = a_act * b_act with b from project_by_iter's final fp64 discretize
 // (reference EfficientQConv.py:68-70, layer_helper.py:67): fp32(a) * fp32(level(x/a)).
+// Generic form (any level count): fp64 per element.
 __global__ void __launch_bounds__(FQ_THREADS)
 fakequant_state_kernel(const float* __restrict__ x, long long numel, const effq_scale_state* __restrict__ st,
                        QParamD q, float* __restrict__ y) {
@@ -80,6 +82,57 @@ fakequant_state_kernel(const float* __restrict__ x, long long numel, const effq_
   if (blockIdx.x == 0) {
     const long long t = nvec * 4 + threadIdx.x;
     if (t < numel) y[t] = __fmul_rn(a32, (float)level_value_d(level_index_fast_d((double)x[t], a64, q, qf), q));
+  }
+}
+
+// <= 256 levels (every configured layer): the fp64 kernel above spends ~40 issue slots per element on conversions and
+// fp64 arithmetic and reaches 59 % of the HBM peak (BENCH_r01).  Here the level index comes from ONE fp32 FMA + rint;
+// only elements within a safety margin of a rounding tie (or NaN) take the exact fp64 sequence, so the index is the
+// fp64 kernel's bit for bit (same argument as quantize_act_ndhwc_v2), and the output value fp32(a) * fp32(level) is
+// read from a per-CTA table of the nlvl possible results, built once with the fp64 expressions of the generic kernel.
+// Four independent 128-bit loads in flight per thread, streaming loads and stores.
+__global__ void __launch_bounds__(FQ_THREADS)
+fakequant_state_lut_kernel(const float* __restrict__ x, long long numel, const effq_scale_state* __restrict__ st,
+                           QParamD q, int nlvl, float* __restrict__ y) {
+  __shared__ float lut[256];
+  const double a64 = st->a;
+  const float a32 = (float)a64;
+  const QFastD qf = make_qfast_d(a64, q, nlvl);
+  for (int i = threadIdx.x; i < nlvl; i += FQ_THREADS) lut[i] = __fmul_rn(a32, (float)level_value_d((double)i, q));
+  __syncthreads();
+  const float c1f = (float)qf.c1, c0f = (float)qf.c0, lm1 = (float)(nlvl - 1);
+  const float tol = 1e-5f * (lm1 + 1.f) + 1e-5f;                   // >= 40x the fp32 evaluation error of qa
+  auto value_of = [&](float val) -> float {
+    const float qa = fmaf(val, c1f, c0f);
+    const float r = rintf(qa);
+    const bool risky = (fabsf(fabsf(qa - r) - 0.5f) < tol && qa > -1.0f && qa < lm1 + 1.0f) || !(val == val);
+    if (!(val == val)) return __fmul_rn(a32, val);                 // NaN propagates like the generic kernel's
+    int idx;
+    if (risky) idx = (int)level_index_fast_d((double)val, a64, q, qf);
+    else idx = (int)fminf(fmaxf(r, 0.f), lm1);
+    return lut[idx];
+  };
+  const long long nvec = numel / 4;
+  const long long stride = (long long)gridDim.x * FQ_THREADS;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * FQ_THREADS + threadIdx.x; i < nvec; i += stride * FQ_UNROLL) {
+    float4 v[FQ_UNROLL];
+#pragma unroll
+    for (int u = 0; u < FQ_UNROLL; ++u) {
+      const long long j = i + u * stride;
+      if (j < nvec) v[u] = __ldcs(x4 + j);
+    }
+#pragma unroll
+    for (int u = 0; u < FQ_UNROLL; ++u) {
+      const long long j = i + u * stride;
+      if (j >= nvec) continue;
+      __stcs(reinterpret_cast<float4*>(y) + j,
+             make_float4(value_of(v[u].x), value_of(v[u].y), value_of(v[u].z), value_of(v[u].w)));
+    }
+  }
+  if (blockIdx.x == 0) {
+    const long long t = nvec * 4 + threadIdx.x;
+    if (t < numel) y[t] = value_of(x[t]);
   }
 }
 
@@ -285,6 +338,188 @@ quantize_act_ndhwc_v2_kernel(const float* __restrict__ x, int c, long long dhw, 
   }
 }
 
+// ---- v3: TMA-staged ring ---------------------------------------------------------------------
+// v2 is bound by the latency of its own global loads (ncu, profiles/r02_layer_ncu.md: DRAM 44 %, SM 50 %, warps active
+// 49 %: every warp waits for the 4 x 16 B it just requested, and more loads per thread cost registers -- measured and
+// rejected above).  v3 takes the loads off the threads: a producer warp streams whole tiles (C rows of TV voxels,
+// C * TV = 8192 elements = 32 KB) into a 4-stage shared-memory ring with one cp.async.bulk per channel row
+// (mbarrier complete_tx), 128 KB in flight per SM; 16 consumer warps read a stage with conflict-free LDS.128 (row
+// groups are skewed by 16 B so that the 8 lanes of a quarter-warp, which own 8 different channel groups, hit 8
+// different bank quads), run v2's index arithmetic and register transpose, and assemble the NDHWC tile in one of two
+// output buffers, which leaves as ONE cp.async.bulk shared -> global store per code type while the next tile is being
+// computed.  One named barrier per tile; the stage is handed back to the producer by one mbarrier arrive per warp.
+constexpr int Q3_CONSUMERS = 512;
+constexpr int Q3_THREADS = Q3_CONSUMERS + 32;
+constexpr int Q3_STAGES = 4;
+constexpr int Q3_ELEMS = 8192;                         // elements per tile (C * tile_v)
+constexpr uint32_t Q3_IN_BYTES = Q3_ELEMS * 4 + 512;   // + 16 B skew per 4-row group (<= 32 groups)
+constexpr uint32_t Q3_SMEM = Q3_STAGES * Q3_IN_BYTES + 2 * (Q3_ELEMS * 2) + 2 * Q3_ELEMS + 128;
+
+__device__ __forceinline__ void q3_wait(uint32_t bar, uint32_t parity) {
+  unsigned int spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();                // a lost transaction must fail the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <bool F64, bool W16, bool W8>
+__global__ void __launch_bounds__(Q3_THREADS, 1)
+quantize_act_ndhwc_v3_kernel(const float* __restrict__ x, int c, long long dhw, int nlvl, int tile_v, long long n_tiles,
+                             const effq_scale_state* __restrict__ st, const float* __restrict__ alpha_f32,
+                             __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out8) {
+  extern __shared__ __align__(128) uint8_t q3_raw[];
+  __shared__ __align__(8) uint64_t q3_bars[2 * Q3_STAGES];
+  uint8_t* base = q3_raw + ((128u - (smem_u32(q3_raw) & 127u)) & 127u);
+  uint8_t* in_base = base;
+  uint8_t* o16_base = base + Q3_STAGES * Q3_IN_BYTES;                  // 2 x [tile_v][c] bf16
+  uint8_t* o8_base = o16_base + 2 * (Q3_ELEMS * 2);                    // 2 x [tile_v][c] e4m3
+  const uint32_t bar0 = smem_u32(q3_bars);
+  auto FULL = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (uint32_t)(Q3_STAGES + s); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Q3_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), Q3_CONSUMERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long tiles_per_sample = dhw / tile_v;                     // host guarantees dhw % tile_v == 0
+  const uint32_t row_bytes = (uint32_t)tile_v * 4u;
+
+  if (warp == Q3_CONSUMERS / 32) {
+    // ===== producer: one bulk copy per channel row, rows spread over the lanes =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long n_idx = tile / tiles_per_sample;
+      const long long v0 = (tile % tiles_per_sample) * tile_v;
+      const float* xs = x + n_idx * (long long)c * dhw + v0;
+      if (lane == 0) {
+        q3_wait(EMPTY(stage), phase ^ 1u);
+        mbar_expect_tx(FULL(stage), (uint32_t)c * row_bytes);
+      }
+      __syncwarp();
+      const uint32_t dst0 = smem_u32(in_base) + (uint32_t)stage * Q3_IN_BYTES;
+      for (int r = lane; r < c; r += 32)
+        bulk_g2s(dst0 + (uint32_t)r * row_bytes + 16u * (uint32_t)(r >> 2), xs + (long long)r * dhw, row_bytes, FULL(stage));
+      if (++stage == Q3_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const QParamF qf = make_qparam_f(0.f, 1.f, nlvl);
+  const QParamD qd = make_qparam_d(0.f, 1.f, nlvl);
+  const double a64 = F64 ? st->a : 1.0;
+  const float a32 = F64 ? 1.f : __ldg(alpha_f32);
+  const QFastD fd = make_qfast_d(a64, qd, nlvl);
+  const QFastF ff = make_qfast_f(a32, qf, nlvl);
+  const float c1f = (float)fd.c1, lm1 = (float)(nlvl - 1);
+  const float tol = 1e-5f * (lm1 + 1.f) + 1e-5f;
+  auto code_of = [&](float val) -> float {
+    if (F64) {
+      const float qa = val * c1f;
+      const float r = rintf(qa);
+      const bool risky = (fabsf(fabsf(qa - r) - 0.5f) < tol && qa > -1.0f && qa < lm1 + 1.0f) || !(val == val);
+      if (risky) return (float)level_index_fast_d((double)val, a64, qd, fd);
+      return fminf(fmaxf(r, 0.f), lm1);
+    }
+    return level_index_fast_f(val, a32, qf, ff);
+  };
+  const int groups = c >> 2;                       // 8, 16 or 32 (host check)
+  const int gw = groups;                           // one warp spans all channel groups ...
+  const int vqw = 32 / gw;                         // ... of vqw voxel quads; 16 warps x vqw quads = tile_v / 4
+  const int g4 = lane % gw, lq = lane / gw;
+  const int vq = warp * vqw + lq;
+  int stage = 0;
+  uint32_t phase = 0;
+  int ob = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long n_idx = tile / tiles_per_sample;
+    const long long v0 = (tile % tiles_per_sample) * tile_v;
+    q3_wait(FULL(stage), phase);
+    const uint8_t* in = in_base + (size_t)stage * Q3_IN_BYTES + (size_t)(4 * g4) * row_bytes + 16u * (uint32_t)g4 + 16u * (uint32_t)vq;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(in + (size_t)k * row_bytes);
+    float cd[4][4];                                                   // [voxel][channel]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cd[0][k] = code_of(v[k].x); cd[1][k] = code_of(v[k].y); cd[2][k] = code_of(v[k].z); cd[3][k] = code_of(v[k].w);
+    }
+    uint32_t p8[4];
+    uint2 p16[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (W8)
+        p8[i] = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][0], cd[i][1]), __NV_SATFINITE, __NV_E4M3) |
+                ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][2], cd[i][3]), __NV_SATFINITE, __NV_E4M3) << 16);
+      if (W16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(cd[i][0], cd[i][1]);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(cd[i][2], cd[i][3]);
+        p16[i].x = *reinterpret_cast<const uint32_t*>(&lo);
+        p16[i].y = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+    }
+    // the codes depend on every loaded value: the stage can go back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(EMPTY(stage));
+    uint32_t* t16 = reinterpret_cast<uint32_t*>(o16_base + (size_t)ob * (Q3_ELEMS * 2));
+    uint32_t* t8 = reinterpret_cast<uint32_t*>(o8_base + (size_t)ob * Q3_ELEMS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                                       // rotated store order: conflict-free (see v2)
+      const int vi = (i + lq) & 3;
+      const int row = 4 * vq + vi;
+      if (W8) {
+        const uint32_t w = vi == 0 ? p8[0] : vi == 1 ? p8[1] : vi == 2 ? p8[2] : p8[3];
+        t8[row * groups + g4] = w;
+      }
+      if (W16) {
+        const uint2 w = vi == 0 ? p16[0] : vi == 1 ? p16[1] : vi == 2 ? p16[2] : p16[3];
+        reinterpret_cast<uint2*>(t16)[row * groups + g4] = w;
+      }
+    }
+    fence_proxy_async();                                                // generic writes -> visible to the bulk store
+    if (threadIdx.x == 0) bulk_wait_read0();                            // the previous tile's store has left its buffer
+    asm volatile("bar.sync 1, %0;" ::"n"(Q3_CONSUMERS) : "memory");
+    if (threadIdx.x == 0) {
+      if (W16) bulk_s2g(out + (n_idx * dhw + v0) * c, smem_u32(t16), (uint32_t)(Q3_ELEMS * 2));
+      if (W8) bulk_s2g(out8 + (n_idx * dhw + v0) * c, smem_u32(t8), (uint32_t)Q3_ELEMS);
+      bulk_commit();
+    }
+    ob ^= 1;
+    if (++stage == Q3_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  if (threadIdx.x == 0) bulk_wait_read0();
+}
+
+template <bool F64>
+static int launch_quantize_v3(const float* x, int n, int c, long long dhw, int nlvl, const effq_scale_state* st,
+                              const float* alpha, __nv_bfloat16* out, uint8_t* out8, cudaStream_t s) {
+  const int tile_v = Q3_ELEMS / c;
+  const long long n_tiles = (long long)n * (dhw / tile_v);
+  const long long ctas = n_tiles < sm_count() ? n_tiles : sm_count();
+  static bool configured = false;
+  if (!configured) {
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v3_kernel<F64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q3_SMEM));
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v3_kernel<F64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q3_SMEM));
+    EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v3_kernel<F64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q3_SMEM));
+    configured = true;
+  }
+  if (out && out8)
+    quantize_act_ndhwc_v3_kernel<F64, true, true><<<(unsigned)ctas, Q3_THREADS, Q3_SMEM, s>>>(x, c, dhw, nlvl, tile_v, n_tiles, st, alpha, out, out8);
+  else if (out)
+    quantize_act_ndhwc_v3_kernel<F64, true, false><<<(unsigned)ctas, Q3_THREADS, Q3_SMEM, s>>>(x, c, dhw, nlvl, tile_v, n_tiles, st, alpha, out, out8);
+  else
+    quantize_act_ndhwc_v3_kernel<F64, false, true><<<(unsigned)ctas, Q3_THREADS, Q3_SMEM, s>>>(x, c, dhw, nlvl, tile_v, n_tiles, st, alpha, out, out8);
+  EFFQ_LAUNCH_CHECK();
+  return 0;
+}
+
 template <bool F64>
 static int launch_quantize_v2(const float* x, int n, int c, long long dhw, int nlvl, int tile_v,
                               const effq_scale_state* st, const float* alpha, __nv_bfloat16* out, uint8_t* out8,
@@ -346,6 +581,17 @@ extern "C" int effq_fakequant_state(const float* x, int64_t numel, const effq_sc
   EFFQ_CHECK_ARG(x && state && y_out, "null pointer");
   EFFQ_CHECK_ARG(nlvl >= 2, "nlvl must be >= 2");
   if (numel <= 0) return 0;
+  static const bool generic_only = [] { const char* v = getenv("EFFQ_FQ_STATE_F64"); return v && *v == '1'; }();
+  if (nlvl <= 256 && !generic_only && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y_out & 15) == 0) {
+    long long blocks = (numel / 4 + (long long)FQ_THREADS * FQ_UNROLL - 1) / ((long long)FQ_THREADS * FQ_UNROLL);
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    fakequant_state_lut_kernel<<<(unsigned)blocks, FQ_THREADS, 0, (cudaStream_t)stream>>>(
+        x, numel, state, make_qparam_d(lo, hi, nlvl), nlvl, y_out);
+    EFFQ_LAUNCH_CHECK();
+    return 0;
+  }
   long long blocks = (numel + FQ_THREADS - 1) / FQ_THREADS;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
@@ -371,6 +617,14 @@ extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* out = (__nv_bfloat16*)codes_bf16_out;
   uint8_t* out8 = (uint8_t*)codes_e4m3_out;
+  // v3 (TMA-staged ring): C in {32, 64, 128}, whole 8192-element tiles, 16-byte aligned rows
+  {
+    static const bool no_v3 = [] { const char* v = getenv("EFFQ_QA_V3"); return v && *v == '0'; }();
+    if (!no_v3 && (c == 32 || c == 64 || c == 128) && dhw % (Q3_ELEMS / c) == 0 && ((uintptr_t)x & 15) == 0 &&
+        (!out8 || ((uintptr_t)out8 & 15) == 0))
+      return use_f64 ? launch_quantize_v3<true>(x, n, c, dhw, nlvl, state, alpha_f32, out, out8, s)
+                     : launch_quantize_v3<false>(x, n, c, dhw, nlvl, state, alpha_f32, out, out8, s);
+  }
   // v2 (register transpose): full tiles only, channel groups a power of two below 32 or a multiple of 32
   {
     const int groups = c / 4;

@@ -6,15 +6,22 @@ IDENTICAL module names, so reference checkpoints (``conv0.conv.weight``,
 ``u_blocks.UResBlock1.Layer1.block1.conv.weight``, ``trans_ups.TransUp4.upsampler.block.conv``
 ...) load unchanged.  Every conv is created through the ``QConv`` factory -- the
 reference's plug-in point (src/definer.py:286-329).  The glue between quantizer layers
-(ReLU, MaxPool3d, trilinear Upsample, residual add) is stock PyTorch by design
-(out of scope for custom kernels).
+(ReLU, MaxPool3d, trilinear Upsample, residual add) runs on the
+repo's own kernels (csrc/glue.cu) whenever the tensors live on the GPU and autograd is not
+recording: the modules below subclass the stock ones (same names, no parameters, so the
+state-dict layout is unchanged) and fuse the neighbouring elementwise op into the same pass
+(MaxPool + the ReLU of the unit behind it, Upsample + the skip connection).  CPU tensors
+(model definition / FP checkpoints on the host) and autograd (FP training, alpha refinement)
+keep the stock PyTorch ops; ``EFFQ_GLUE=lib`` restores them on the GPU for A/B comparisons.
 """
 from __future__ import annotations
 
+import os
 from collections.abc import Iterable
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 __all__ = ["UResQ", "get_conv_wrapper"]
 
@@ -24,9 +31,72 @@ class PassModule(nn.Module):
         return x
 
 
+def _own(*tensors) -> bool:
+    """True when the glue op runs on the repo's kernels: CUDA fp32, 5-D, nothing to differentiate."""
+    if os.environ.get("EFFQ_GLUE", "own") == "lib":
+        return False
+    recording = torch.is_grad_enabled()
+    return all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 5 and not (recording and t.requires_grad)
+               for t in tensors)
+
+
+def _int_triple(v):
+    """(a, b, c) if v is an integer or a triple of integers (floats with integral value count), else None."""
+    t = tuple(v) if isinstance(v, Iterable) else (v,) * 3
+    if len(t) != 3 or any(float(e) != int(e) or int(e) < 1 for e in t):
+        return None
+    return tuple(int(e) for e in t)
+
+
+class GlueReLU(nn.ReLU):
+    def forward(self, x):
+        if _own(x) and x.is_contiguous():
+            from . import ops
+            return ops.relu(x, self.inplace)
+        return super().forward(x)
+
+
+class GlueMaxPool3d(nn.MaxPool3d):
+    """MaxPool3d(k, k); ``fuse_relu`` applies the ReLU of the unit behind it in the same pass."""
+
+    def __init__(self, kernel, stride, fuse_relu=False):
+        super().__init__(kernel, stride)
+        self.fuse_relu = fuse_relu
+
+    def forward(self, x):
+        k = _int_triple(self.kernel_size)
+        if _own(x) and k is not None and k == _int_triple(self.stride) and k[2] <= 2 and self.padding == 0 \
+                and self.dilation == 1 and not self.ceil_mode and not self.return_indices:
+            from . import ops
+            return ops.maxpool3d(x, k, relu_after=self.fuse_relu)
+        y = super().forward(x)
+        return F.relu(y) if self.fuse_relu else y
+
+
+class GlueUpsample(nn.Upsample):
+    """nn.Upsample; ``forward(x, skip)`` adds the skip connection in the same pass."""
+
+    def forward(self, x, skip=None):
+        f = _int_triple(self.scale_factor) if self.scale_factor is not None else None
+        if f is not None and self.mode == "trilinear" and not self.align_corners and not self.recompute_scale_factor \
+                and _own(x) and (skip is None or _own(skip)):
+            from . import ops
+            return ops.upsample_trilinear(x, f, skip)
+        y = super().forward(x)
+        return y if skip is None else y + skip
+
+
+def _add(a, b):
+    """Residual add (factory_blk.py:166)."""
+    if a.shape == b.shape and _own(a, b):
+        from . import ops
+        return ops.add(a, b)
+    return a + b
+
+
 def ReLU(inplace=True):
     def make(inp=None):
-        return nn.ReLU(inplace if inp is None else inp)
+        return GlueReLU(inplace if inp is None else inp)
     return make
 
 
@@ -73,15 +143,22 @@ class ResBlockWithType(nn.Module):
         self.projection = Conv(cin, cout, 1, 1, 0, bias=False) if self.change_dim else PassModule()
 
     def forward(self, x):
-        return self.block2(self.block1(x)) + self.projection(x)
+        y = self.block2(self.block1(x))          # block1's in-place ReLU has rewritten x by now (reference behaviour)
+        return _add(y, self.projection(x))
 
 
 def _down(kernel, Conv, nla, bn, blk_type):
     """factory_blk.py:18-42: MaxPool then a 1x1x1 unit."""
     def make(cin, cout):
         seq = nn.Sequential()
-        seq.add_module("pool", nn.MaxPool3d(kernel, kernel))
-        seq.add_module("block", _Unit(blk_type, cin, cout, 1, 1, 0, 1, Conv, bn, nla, 0))
+        unit = _Unit(blk_type, cin, cout, 1, 1, 0, 1, Conv, bn, nla, 0)
+        # "mid" units start with the ReLU: the pooling pass applies it (relu(max) == max(relu), exactly) and the
+        # unit's own ReLU module, which would re-read and re-write the pooled tensor, becomes a pass-through
+        fuse = blk_type == "mid" and isinstance(unit.relu, nn.ReLU)
+        if fuse:
+            unit.relu = PassModule()
+        seq.add_module("pool", GlueMaxPool3d(kernel, kernel, fuse_relu=fuse))
+        seq.add_module("block", unit)
         return seq
     return make
 
@@ -92,7 +169,7 @@ def _up(scale, Conv, nla, bn, blk_type):
         seq = nn.Sequential()
         if cin != cout:
             seq.add_module("block", _Unit(blk_type, cin, cout, 1, 1, 0, 1, Conv, bn, nla, 0))
-        seq.add_module("trilinear", nn.Upsample(scale_factor=scale, mode="trilinear"))
+        seq.add_module("trilinear", GlueUpsample(scale_factor=scale, mode="trilinear"))
         return seq
     return make
 
@@ -105,7 +182,9 @@ class _Fuser(nn.Module):
         self.upsampler = upsampler
 
     def forward(self, x, skip):
-        return self.upsampler(x) + skip
+        for name, m in self.upsampler.named_children():
+            x = m(x, skip) if name == "trilinear" else m(x)      # the upsampling pass adds the skip connection
+        return x
 
 
 def _scale_tuple(t, f):
@@ -191,13 +270,13 @@ class UResQ(ModelQ):
                         head.add_module("classifier", nn.Conv3d(width_config[i], num_classes, 1, 1, 0))
                         extra = _scale_tuple(init_stride, 2 ** len(width_config[i + 1:]))
                         if extra not in (1, (1, 1), (1, 1, 1)):
-                            head.add_module("extra_up", nn.Upsample(scale_factor=extra, mode="trilinear"))
+                            head.add_module("extra_up", GlueUpsample(scale_factor=extra, mode="trilinear"))
                     self.classifiers.add_module(f"AuxClassifier{i + 1}", head)
 
         self.final_cls = nn.Sequential()
         self.final_cls.add_module("cls", ConvLast(width_config[-1], num_classes, 1, 1, 0))
         if init_stride not in (1, (1, 1), (1, 1, 1)):
-            self.final_cls.add_module("extra_up", nn.Upsample(scale_factor=init_stride, mode="trilinear"))
+            self.final_cls.add_module("extra_up", GlueUpsample(scale_factor=init_stride, mode="trilinear"))
 
     def forward(self, x, feature_out=False):
         nb, nd = len(self.u_blocks), len(self.trans_downs)

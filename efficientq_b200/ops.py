@@ -848,3 +848,55 @@ def split3_ndhwc(x: torch.Tensor):
         lib.effq_split3_ndhwc(ptr(x), n, c, d * h * w, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), stream()),
         "effq_split3_ndhwc"))
     return planes
+
+
+# ---------------------------------------------------------------------------
+# (f.4) glue ops between the quantizer layers: one HBM pass each, the neighbouring elementwise op fused in
+# ---------------------------------------------------------------------------
+def relu(x: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    """nn.ReLU of a unit (factoryQ.py:66-81)."""
+    x = _f32c(x, "x")
+    y = x if inplace else torch.empty_like(x)
+    timer.run("glue_relu", {"bytes": 8 * x.numel()}, lambda: check(
+        capi.load().effq_glue_elementwise(ptr(x), None, x.numel(), 1, ptr(y), stream()), "effq_glue_elementwise"))
+    return y
+
+
+def add(a: torch.Tensor, b: torch.Tensor, relu_after: bool = False) -> torch.Tensor:
+    """Residual add (factory_blk.py:147-166), optionally followed by a ReLU in the same pass."""
+    a, b = _f32c(a, "a"), _f32c(b, "b")
+    if a.shape != b.shape:
+        raise EffqError(f"add: shapes differ ({tuple(a.shape)} vs {tuple(b.shape)})")
+    y = torch.empty_like(a)
+    timer.run("glue_add", {"bytes": 12 * a.numel()}, lambda: check(
+        capi.load().effq_glue_elementwise(ptr(a), ptr(b), a.numel(), 1 if relu_after else 0, ptr(y), stream()),
+        "effq_glue_elementwise"))
+    return y
+
+
+def maxpool3d(x: torch.Tensor, kernel, relu_after: bool = False) -> torch.Tensor:
+    """nn.MaxPool3d(kernel, kernel) (factory_blk.py:18-42) [+ the ReLU of the unit that follows]."""
+    x = _f32c(x, "x")
+    n, c, d, h, w = x.shape
+    kd, kh, kw = capi._triple(kernel)
+    y = torch.empty((n, c, d // kd, h // kh, w // kw), dtype=torch.float32, device=x.device)
+    timer.run("glue_maxpool", {"bytes": 4 * (x.numel() + y.numel())}, lambda: check(
+        capi.load().effq_glue_maxpool3d(ptr(x), n * c, d, h, w, kd, kh, kw, 1 if relu_after else 0, ptr(y), stream()),
+        "effq_glue_maxpool3d"))
+    return y
+
+
+def upsample_trilinear(x: torch.Tensor, factor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Upsample(scale_factor=factor, mode="trilinear") [+ skip] (factory_blk.py:45-93), integer factors."""
+    x = _f32c(x, "x")
+    n, c, d, h, w = x.shape
+    fd, fh, fw = capi._triple(factor)
+    y = torch.empty((n, c, d * fd, h * fh, w * fw), dtype=torch.float32, device=x.device)
+    if skip is not None:
+        skip = _f32c(skip, "skip")
+        if skip.shape != y.shape:
+            raise EffqError(f"upsample_trilinear: skip has shape {tuple(skip.shape)}, output {tuple(y.shape)}")
+    timer.run("glue_upsample", {"bytes": 4 * (x.numel() + y.numel() * (2 if skip is not None else 1))}, lambda: check(
+        capi.load().effq_glue_upsample_trilinear(ptr(x), ptr(skip), n * c, d, h, w, fd, fh, fw, ptr(y), stream()),
+        "effq_glue_upsample_trilinear"))
+    return y

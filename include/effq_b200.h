@@ -397,6 +397,21 @@ int effq_fixdigits_ndhwc(const float* x, int32_t n, int32_t c, int64_t dhw, cons
 int effq_adam_step(float* params, const double* grads, float grad_scale, float* exp_avg, float* exp_avg_sq,
                    int32_t n, float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
 
+/* ---- glue ops between the quantizer layers, NCDHW fp32, one HBM pass each -------------------------
+ * Reference: the stock modules of src/models/factoryQ.py:66-81 (ReLU of a unit), factory_blk.py:18-42 (MaxPool3d ->
+ * unit), :45-93 (trilinear Upsample, "+ skip"), :147-166 (residual add).
+ * effq_glue_elementwise:  y = relu(a) (b == NULL, relu != 0) | a + b | relu(a + b); y may alias a.
+ * effq_glue_maxpool3d:    MaxPool3d(kernel = stride = (kd, kh, kw)), no padding, floor mode, over nc = N*C volumes of
+ *                         d x h x w; relu != 0 applies the ReLU of the unit that follows in the same pass.
+ * effq_glue_upsample_trilinear: nn.Upsample(scale_factor = (fd, fh, fw), mode = "trilinear", align_corners = False)
+ *                         in the library's fp32 op order; skip != NULL adds the skip connection (output shape) in the
+ *                         same pass. */
+int effq_glue_elementwise(const float* a, const float* b, int64_t numel, int32_t relu, float* y_out, void* stream);
+int effq_glue_maxpool3d(const float* x, int64_t nc, int32_t d, int32_t h, int32_t w, int32_t kd, int32_t kh,
+                        int32_t kw, int32_t relu, float* y_out, void* stream);
+int effq_glue_upsample_trilinear(const float* x, const float* skip, int64_t nc, int32_t d, int32_t h, int32_t w,
+                                 int32_t fd, int32_t fh, int32_t fw, float* y_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

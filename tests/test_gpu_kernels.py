@@ -119,6 +119,30 @@ def test_ndhwc_codes_register_transpose_kernel(ops, n, c, sp, L):
         assert torch.equal(c8b.cpu().float().int(), want32)
 
 
+@pytest.mark.parametrize("L,lo", [(4, 0), (16, 0), (256, 0), (16, -1), (4, -1), (256, -1), (300, 0)])
+def test_fakequant_state_table_kernel_on_ties(ops, L, lo):
+    """effq_fakequant_state (fp32 index + table of the L possible fp32(a)*fp32(level) values; L > 256 takes the fp64
+    kernel) against the reference's op order in fp64 (layer_helper.py:25-37,67), with values planted on and next to
+    every rounding tie and clamp boundary, NaN and an odd tail."""
+    torch.manual_seed(L + 7 * (lo + 1))
+    x = torch.randn(3 * 4099 + 3) * 1.1
+    if lo == 0:
+        x = torch.relu(x)
+    a, _ = O.project_by_iter(x, L, lo, 1)
+    delta = (1.0 - lo) / (L - 1)
+    k = torch.arange(L - 1, dtype=torch.float64)
+    ties = ((k + 0.5) * delta + lo) * a
+    planted = torch.cat([ties, ties * (1 + 1e-7), ties * (1 - 1e-7), ties + 3e-5 * a * delta, ties - 3e-5 * a * delta,
+                         torch.tensor([a, a * (1 + 1e-7), lo * a, lo * a * (1 + 1e-7), 0.0])]).float()
+    x[:planted.numel()] = planted[: x.numel()]
+    x[-2] = float("nan")
+    st = ops.ScaleState(torch.device(DEV))
+    st.set_a(a)
+    y = ops.fakequant_state(x.to(DEV), st, L, float(lo), 1.0).cpu()
+    want = torch.tensor(a, dtype=torch.float32) * O.discretize(x.double() / a, L, lo, 1).float()
+    assert np.array_equal(y.numpy(), want.numpy(), equal_nan=True)
+
+
 # ---------------------------------------------------------------- scale search (a3)
 @pytest.mark.parametrize("name,lo,hi", [("act", 0, 1), ("wt", -1, 1)])
 @pytest.mark.parametrize("L", [4, 16, 256])

@@ -6,14 +6,14 @@ out=gpurun_out
 mkdir -p $out
 # (1) launch list of a short bench run: every launch with its device time (cold-cache, serialised: compare SHARES)
 if timeout 200 python bench.py --workload brats_w4a4_2x64 --steps 1 --warmup 3 --no-cpu > $out/${tag}_bench_2x64.json 2> /dev/null; then
-  timeout 1100 ncu --metrics gpu__time_duration.sum --clock-control none -c 60000 --csv --log-file /tmp/launches.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file /tmp/launches.csv \
     python bench.py --workload brats_w4a4_2x64 --steps 1 --warmup 1 --no-cpu > /dev/null 2>&1
   echo "ncu launch list rc=$?"
   python tools/summarize_launches.py /tmp/launches.csv > $out/${tag}_launches_bench_2x64.md 2>&1
 fi
 # (2) --set full of one level-1 layer's kernels (8 volumes), one or two launches per kernel
 if timeout 200 python tools/profile_layer.py 8 > $out/${tag}_profile_layer.log 2>&1; then
-  timeout 900 ncu --set full --clock-control none \
+  timeout 500 ncu --set full --clock-control none \
     -k "regex:gram_tc_kernel|quadform_delta_kernel|potrf_tile_kernel|solve_gemm_tc_kernel|conv3d_tc_kernel|quantize_act_ndhwc|scale_search_rows|fakequant_f32_kernel|fakequant_state" \
     -c 24 -o /tmp/layer_full python tools/profile_layer.py 8 > $out/${tag}_ncu_full.log 2>&1
   echo "ncu full rc=$?"

@@ -339,19 +339,27 @@ quantize_act_ndhwc_v2_kernel(const float* __restrict__ x, int c, long long dhw, 
 }
 
 // ---- v3: TMA-staged ring ---------------------------------------------------------------------
-// v2 is bound by the latency of its own global loads (ncu, profiles/r02_layer_ncu.md: DRAM 44 %, SM 50 %, warps active
-// 49 %: every warp waits for the 4 x 16 B it just requested, and more loads per thread cost registers -- measured and
-// rejected above).  v3 takes the loads off the threads: a producer warp streams whole tiles (C rows of TV voxels,
-// C * TV = 8192 elements = 32 KB) into a 4-stage shared-memory ring with one cp.async.bulk per channel row
-// (mbarrier complete_tx), 128 KB in flight per SM; 16 consumer warps read a stage with conflict-free LDS.128 (row
+// v2 waits on its own global loads (ncu, profiles/r02_layer_ncu.md: DRAM 44 %, SM 50 %, warps active 49 %), and more
+// loads per thread cost registers (measured and rejected above).  v3 takes the loads off the threads: a producer warp
+// streams whole tiles (C rows of TV voxels, C * TV = 4096 elements = 16 KB) into a 3-stage shared-memory ring with one
+// cp.async.bulk per channel row (mbarrier complete_tx); 8 consumer warps read a stage with conflict-free LDS.128 (row
 // groups are skewed by 16 B so that the 8 lanes of a quarter-warp, which own 8 different channel groups, hit 8
 // different bank quads), run v2's index arithmetic and register transpose, and assemble the NDHWC tile in one of two
 // output buffers, which leaves as ONE cp.async.bulk shared -> global store per code type while the next tile is being
-// computed.  One named barrier per tile; the stage is handed back to the producer by one mbarrier arrive per warp.
-constexpr int Q3_CONSUMERS = 512;
+// computed.  One named barrier per tile; a stage goes back to the producer with one mbarrier arrive per warp; three
+// CTAs (74 KB each) per SM overlap each other's barrier phases.
+// Measured (tools/hbm_bench.py, 32 x 32 x 64^3, profiles/r02_hbm_bench.md): bf16 + e4m3 codes 4.29 TB/s = 65 % of the
+// copy peak (v2: 62 %), e4m3 only 59 % (v2: 53 %); C = 64 with both code types 54 % (v2: 49 %).  Variants measured and
+// rejected: one CTA per SM with 16 consumer warps, 32 KB tiles and four stages (64 % / 47 %: all warps of the SM move
+// in lock-step through load -> convert -> store -> barrier); two CTAs per SM with 32 KB tiles and two items per thread
+// (57 %).  More resident warps help and longer copies do not: what is left is the issue rate of the convert + transpose
+// code (~50 instructions per element incl. the tie test), not the memory system.
+constexpr int Q3_CONSUMERS = 256;
 constexpr int Q3_THREADS = Q3_CONSUMERS + 32;
-constexpr int Q3_STAGES = 4;
-constexpr int Q3_ELEMS = 8192;                         // elements per tile (C * tile_v)
+constexpr int Q3_STAGES = 3;
+constexpr int Q3_CTAS_PER_SM = 3;                      // CTAs in different phases hide each other's per-tile barrier
+constexpr int Q3_ELEMS = 4096;                         // elements per tile (C * tile_v)
+constexpr int Q3_ITEMS = Q3_ELEMS / 16 / Q3_CONSUMERS; // a thread's item = 4 channels x 4 voxels
 constexpr uint32_t Q3_IN_BYTES = Q3_ELEMS * 4 + 512;   // + 16 B skew per 4-row group (<= 32 groups)
 constexpr uint32_t Q3_SMEM = Q3_STAGES * Q3_IN_BYTES + 2 * (Q3_ELEMS * 2) + 2 * Q3_ELEMS + 128;
 
@@ -368,7 +376,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 template <bool F64, bool W16, bool W8>
-__global__ void __launch_bounds__(Q3_THREADS, 1)
+__global__ void __launch_bounds__(Q3_THREADS, Q3_CTAS_PER_SM)
 quantize_act_ndhwc_v3_kernel(const float* __restrict__ x, int c, long long dhw, int nlvl, int tile_v, long long n_tiles,
                              const effq_scale_state* __restrict__ st, const float* __restrict__ alpha_f32,
                              __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ out8) {
@@ -432,9 +440,8 @@ quantize_act_ndhwc_v3_kernel(const float* __restrict__ x, int c, long long dhw, 
   };
   const int groups = c >> 2;                       // 8, 16 or 32 (host check)
   const int gw = groups;                           // one warp spans all channel groups ...
-  const int vqw = 32 / gw;                         // ... of vqw voxel quads; 16 warps x vqw quads = tile_v / 4
+  const int vqw = 32 / gw;                         // ... of vqw voxel quads; 8 warps x vqw quads = tile_v / 4
   const int g4 = lane % gw, lq = lane / gw;
-  const int vq = warp * vqw + lq;
   int stage = 0;
   uint32_t phase = 0;
   int ob = 0;
@@ -442,45 +449,55 @@ quantize_act_ndhwc_v3_kernel(const float* __restrict__ x, int c, long long dhw, 
     const long long n_idx = tile / tiles_per_sample;
     const long long v0 = (tile % tiles_per_sample) * tile_v;
     q3_wait(FULL(stage), phase);
-    const uint8_t* in = in_base + (size_t)stage * Q3_IN_BYTES + (size_t)(4 * g4) * row_bytes + 16u * (uint32_t)g4 + 16u * (uint32_t)vq;
-    float4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(in + (size_t)k * row_bytes);
-    float cd[4][4];                                                   // [voxel][channel]
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      cd[0][k] = code_of(v[k].x); cd[1][k] = code_of(v[k].y); cd[2][k] = code_of(v[k].z); cd[3][k] = code_of(v[k].w);
-    }
-    uint32_t p8[4];
-    uint2 p16[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (W8)
-        p8[i] = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][0], cd[i][1]), __NV_SATFINITE, __NV_E4M3) |
-                ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][2], cd[i][3]), __NV_SATFINITE, __NV_E4M3) << 16);
-      if (W16) {
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(cd[i][0], cd[i][1]);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(cd[i][2], cd[i][3]);
-        p16[i].x = *reinterpret_cast<const uint32_t*>(&lo);
-        p16[i].y = *reinterpret_cast<const uint32_t*>(&hi);
-      }
-    }
-    // the codes depend on every loaded value: the stage can go back to the producer
-    __syncwarp();
-    if (lane == 0) mbar_arrive(EMPTY(stage));
     uint32_t* t16 = reinterpret_cast<uint32_t*>(o16_base + (size_t)ob * (Q3_ELEMS * 2));
     uint32_t* t8 = reinterpret_cast<uint32_t*>(o8_base + (size_t)ob * Q3_ELEMS);
+    float4 v[Q3_ITEMS][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {                                       // rotated store order: conflict-free (see v2)
-      const int vi = (i + lq) & 3;
-      const int row = 4 * vq + vi;
-      if (W8) {
-        const uint32_t w = vi == 0 ? p8[0] : vi == 1 ? p8[1] : vi == 2 ? p8[2] : p8[3];
-        t8[row * groups + g4] = w;
+    for (int it = 0; it < Q3_ITEMS; ++it) {
+      const int vq = (warp + it * (Q3_CONSUMERS / 32)) * vqw + lq;
+      const uint8_t* in = in_base + (size_t)stage * Q3_IN_BYTES + (size_t)(4 * g4) * row_bytes + 16u * (uint32_t)g4 + 16u * (uint32_t)vq;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[it][k] = *reinterpret_cast<const float4*>(in + (size_t)k * row_bytes);
+    }
+#pragma unroll
+    for (int it = 0; it < Q3_ITEMS; ++it) {
+      const int vq = (warp + it * (Q3_CONSUMERS / 32)) * vqw + lq;
+      float cd[4][4];                                                   // [voxel][channel]
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cd[0][k] = code_of(v[it][k].x); cd[1][k] = code_of(v[it][k].y); cd[2][k] = code_of(v[it][k].z); cd[3][k] = code_of(v[it][k].w);
       }
-      if (W16) {
-        const uint2 w = vi == 0 ? p16[0] : vi == 1 ? p16[1] : vi == 2 ? p16[2] : p16[3];
-        reinterpret_cast<uint2*>(t16)[row * groups + g4] = w;
+      uint32_t p8[4];
+      uint2 p16[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (W8)
+          p8[i] = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][0], cd[i][1]), __NV_SATFINITE, __NV_E4M3) |
+                  ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(cd[i][2], cd[i][3]), __NV_SATFINITE, __NV_E4M3) << 16);
+        if (W16) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(cd[i][0], cd[i][1]);
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(cd[i][2], cd[i][3]);
+          p16[i].x = *reinterpret_cast<const uint32_t*>(&lo);
+          p16[i].y = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+      }
+      if (it == Q3_ITEMS - 1) {
+        // every loaded value has been consumed: the stage can go back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(EMPTY(stage));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                                       // rotated store order: conflict-free (see v2)
+        const int vi = (i + lq) & 3;
+        const int row = 4 * vq + vi;
+        if (W8) {
+          const uint32_t w = vi == 0 ? p8[0] : vi == 1 ? p8[1] : vi == 2 ? p8[2] : p8[3];
+          t8[row * groups + g4] = w;
+        }
+        if (W16) {
+          const uint2 w = vi == 0 ? p16[0] : vi == 1 ? p16[1] : vi == 2 ? p16[2] : p16[3];
+          reinterpret_cast<uint2*>(t16)[row * groups + g4] = w;
+        }
       }
     }
     fence_proxy_async();                                                // generic writes -> visible to the bulk store
@@ -502,7 +519,8 @@ static int launch_quantize_v3(const float* x, int n, int c, long long dhw, int n
                               const float* alpha, __nv_bfloat16* out, uint8_t* out8, cudaStream_t s) {
   const int tile_v = Q3_ELEMS / c;
   const long long n_tiles = (long long)n * (dhw / tile_v);
-  const long long ctas = n_tiles < sm_count() ? n_tiles : sm_count();
+  const long long cap = (long long)sm_count() * Q3_CTAS_PER_SM;
+  const long long ctas = n_tiles < cap ? n_tiles : cap;
   static bool configured = false;
   if (!configured) {
     EFFQ_CUDA(cudaFuncSetAttribute(quantize_act_ndhwc_v3_kernel<F64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q3_SMEM));
@@ -617,10 +635,11 @@ extern "C" int effq_quantize_act_ndhwc(const float* x, int32_t n, int32_t c, int
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16* out = (__nv_bfloat16*)codes_bf16_out;
   uint8_t* out8 = (uint8_t*)codes_e4m3_out;
-  // v3 (TMA-staged ring): C in {32, 64, 128}, whole 8192-element tiles, 16-byte aligned rows
+  // v3 (TMA-staged ring) where it measured faster than v2: C = 32 (the level-1 tensors: three quarters of the
+  // activation bytes of the BraTS net) and C = 64 with both code types; whole 4096-element tiles, 16-byte aligned rows
   {
     static const bool no_v3 = [] { const char* v = getenv("EFFQ_QA_V3"); return v && *v == '0'; }();
-    if (!no_v3 && (c == 32 || c == 64 || c == 128) && dhw % (Q3_ELEMS / c) == 0 && ((uintptr_t)x & 15) == 0 &&
+    if (!no_v3 && (c == 32 || (c == 64 && out && out8)) && dhw % (Q3_ELEMS / c) == 0 && ((uintptr_t)x & 15) == 0 &&
         (!out8 || ((uintptr_t)out8 & 15) == 0))
       return use_f64 ? launch_quantize_v3<true>(x, n, c, dhw, nlvl, state, alpha_f32, out, out8, s)
                      : launch_quantize_v3<false>(x, n, c, dhw, nlvl, state, alpha_f32, out, out8, s);

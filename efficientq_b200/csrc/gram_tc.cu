@@ -217,6 +217,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
+// PF (right operand by TMA only): the builders load the codes and the attention weight of voxel block hb + 1 before
+// they wait for, weight, split and store block hb -- without it every builder thread serialises the latency of its own
+// L1/L2 gather with its store phase in every pipeline stage (ncu: tensor pipe 39 % active with the builders at a
+// third of their issue slots, profiles/r02_layer_ncu.md).
+template <bool PF>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
   extern __shared__ __align__(1024) uint8_t gsm_raw[];
@@ -384,27 +389,65 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
       long long hb1 = hb0 + p.hb_per_split < p.hb_total ? hb0 + p.hb_per_split : p.hb_total;
       BlockPos bp;
       bp.set(hb0, p);
-      for (long long hb = hb0; hb < hb1; ++hb) {
-        const int bw = bp.bw, bh = bp.bh, dd = bp.dd, nn = bp.nn;
-        bp.next(p);
-        const int vh = bh * 8 + vy, vw = bw * 8 + vx;
-        const bool vlive = vh < p.h && vw < p.w;
-        const long long vidx = ((long long)nn * p.d + dd) * plane + (long long)vh * p.w + vw;
-        const __nv_bfloat16* vptr = p.xq + vidx * p.c1;
-        const float aw = vlive ? (p.att ? __ldg(p.att + vidx) : 1.f) : 0.f;
-        // gather first (loads in flight), then wait for the stage, then write
-        uint4 zv[GT_ZS], pv[GT_PS];           // kind 1: raw bf16 codes; kind 3 (left only): handled below
-        float yv[GT_ZS][8];               // kind 3: the 8 target channels of this voxel
-        const long long chan = (long long)p.d * plane;
+      const long long chan = (long long)p.d * plane;
+      // this thread's voxel of a block: position, liveness, attention weight
+      struct VoxPos { int dd, nn, vh, vw; bool vlive; long long vidx; float aw; };
+      auto make_pos = [&](const BlockPos& b) {
+        VoxPos q;
+        q.dd = b.dd; q.nn = b.nn;
+        q.vh = b.bh * 8 + vy; q.vw = b.bw * 8 + vx;
+        q.vlive = q.vh < p.h && q.vw < p.w;
+        q.vidx = ((long long)q.nn * p.d + q.dd) * plane + (long long)q.vh * p.w + q.vw;
+        q.aw = q.vlive ? (p.att ? __ldg(p.att + q.vidx) : 1.f) : 0.f;
+        return q;
+      };
+      // the left operand's code chunks (kind 1) of that voxel: raw bf16 codes, zero for padding
+      auto gather_z = [&](const VoxPos& q, uint4 (&zq)[GT_ZS]) {
+        const __nv_bfloat16* vptr = p.xq + q.vidx * p.c1;
 #pragma unroll
         for (int i = 0; i < GT_ZS; ++i) {
-          const int tp = zs[i].tap, kind = tp >> 6;
-          zv[i] = make_uint4(0, 0, 0, 0);
-          if (kind == 1) {
-            const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
-            if (vlive && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w)
-              zv[i] = __ldg(reinterpret_cast<const uint4*>(vptr + zs[i].rel));
-          } else if (kind == 3) {
+          const int tp = zs[i].tap;
+          zq[i] = make_uint4(0, 0, 0, 0);
+          if ((tp >> 6) == 1) {
+            const int gd = q.dd + (tp & 3) - 1, gh = q.vh + ((tp >> 2) & 3) - 1, gw = q.vw + ((tp >> 4) & 3) - 1;
+            if (q.vlive && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w)
+              zq[i] = __ldg(reinterpret_cast<const uint4*>(vptr + zs[i].rel));
+          }
+        }
+      };
+      VoxPos nxt;
+      uint4 zn[GT_ZS];
+      if (PF) {
+        nxt = make_pos(bp);
+        bp.next(p);
+        gather_z(nxt, zn);
+      }
+      for (long long hb = hb0; hb < hb1; ++hb) {
+        VoxPos cur;
+        uint4 zv[GT_ZS], pv[GT_PS];           // kind 1: raw bf16 codes; kind 3 (left only): handled below
+        if (PF) {
+          cur = nxt;
+#pragma unroll
+          for (int i = 0; i < GT_ZS; ++i) zv[i] = zn[i];
+          if (hb + 1 < hb1) {                  // next block's loads go out before this block's wait + store phase
+            nxt = make_pos(bp);
+            bp.next(p);
+            gather_z(nxt, zn);
+          }
+        } else {
+          cur = make_pos(bp);
+          bp.next(p);
+          gather_z(cur, zv);
+        }
+        const int dd = cur.dd, nn = cur.nn, vh = cur.vh, vw = cur.vw;
+        const bool vlive = cur.vlive;
+        const long long vidx = cur.vidx;
+        const __nv_bfloat16* vptr = p.xq + vidx * p.c1;
+        const float aw = cur.aw;
+        float yv[GT_ZS][8];               // kind 3: the 8 target channels of this voxel
+#pragma unroll
+        for (int i = 0; i < GT_ZS; ++i) {
+          if ((zs[i].tap >> 6) == 3) {
             const float* yp = p.y + ((long long)nn * p.c2 + zs[i].rel) * chan + (vidx - (long long)nn * chan);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -415,7 +458,7 @@ gram_tc_kernel(const GtParams p, const __grid_constant__ CUtensorMap pmap) {
         for (int i = 0; i < GT_PS; ++i) {
           const int tp = ps[i].tap, kind = tp >> 6;
           pv[i] = make_uint4(0, 0, 0, 0);
-          if (p_tma) continue;                        // the TMA warp delivers the right operand
+          if (PF || p_tma) continue;                  // the TMA warp delivers the right operand
           if (kind == 1) {
             const int gd = dd + (tp & 3) - 1, gh = vh + ((tp >> 2) & 3) - 1, gw = vw + ((tp >> 4) & 3) - 1;
             if (vlive && (unsigned)gd < (unsigned)p.d && (unsigned)gh < (unsigned)p.h && (unsigned)gw < (unsigned)p.w)
@@ -621,7 +664,8 @@ static int gram_tc_accumulate_impl(const void* xcodes_ndhwc_bf16, const float* a
   const size_t smem = (size_t)GT_STAGES * GT_STAGE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    EFFQ_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFFQ_CUDA(cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFFQ_CUDA(cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const long long items = tiles * splits;
@@ -646,7 +690,9 @@ static int gram_tc_accumulate_impl(const void* xcodes_ndhwc_bf16, const float* a
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("effq_gram_tc: cuTensorMapEncodeTiled failed (%d)", (int)rc); return 2; }
   }
-  gram_tc_kernel<<<ctas, GT_THREADS, smem, (cudaStream_t)stream>>>(p, pmap);
+  static const bool no_pf = [] { const char* v = getenv("EFFQ_GRAM_PREFETCH"); return v && *v == '0'; }();
+  if (p.p_tma && !no_pf) gram_tc_kernel<true><<<ctas, GT_THREADS, smem, (cudaStream_t)stream>>>(p, pmap);
+  else                   gram_tc_kernel<false><<<ctas, GT_THREADS, smem, (cudaStream_t)stream>>>(p, pmap);
   EFFQ_LAUNCH_CHECK();
   return 0;
 }

@@ -1,5 +1,5 @@
-"""HBM-bound kernels of the path, each timed alone on tensors far larger than L2 (CUDA events, best of 5 after 2
-warm-ups), against the measured copy bandwidth in MEASURED_PEAKS.json:
+"""HBM-bound kernels of the path, each timed alone on tensors far larger than L2 (CUDA events around 8 back-to-back
+launches, best of 5 after 2 warm-ups), against the measured copy bandwidth in MEASURED_PEAKS.json:
     python tools/hbm_bench.py [n_volumes]          (EFFQ_QA_V3=0 / EFFQ_FQ_STATE_F64=1 select the older kernels)
 fake-quant (values / values+codes), Qact from the scale-search state, NDHWC code kernel (bf16+e4m3) at the three
 channel widths of the BraTS net, and the glue ops next to the library ops they replace."""
@@ -22,7 +22,10 @@ if os.path.exists(pk):
     peak = json.load(open(pk))["hbm_gbs"]
 
 
-def best_ms(fn, reps=5, warm=2):
+def best_ms(fn, reps=5, warm=2, inner=8):
+    """Best of `reps` brackets of `inner` back-to-back launches each (per-launch time): with ONE launch per bracket the
+    host-side cost of the call (ctypes + wrapper, ~30 us against ~5 us for a library op) sits between the start event
+    and the kernel and is charged to kernels that only run for 0.3 ms."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -30,10 +33,11 @@ def best_ms(fn, reps=5, warm=2):
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(inner):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        best = min(best, a.elapsed_time(b))
+        best = min(best, a.elapsed_time(b) / inner)
     return best
 
 

@@ -23,6 +23,12 @@ qx = ops.fakequant_state(x, st, 16, 0.0, 1.0)
 alpha = st.a_f32().reshape(1)
 yq, codes = ops.fakequant(x, alpha, 16, 0.0, 1.0, want_codes=True)
 xq, xq8 = ops.quantize_act_ndhwc(x, 16, state=st, e4m3=True)
+# glue ops between the layers (csrc/glue.cu)
+r_ = ops.relu(x)
+ad_ = ops.add(x, y)
+mp_ = ops.maxpool3d(x, 2, relu_after=True)
+up_ = ops.upsample_trilinear(mp_, 2, y)
+del r_, ad_, mp_, up_
 w = (2 * torch.randint(0, 16, (c, c, 3, 3, 3), device=dev) - 15).float()
 wq = ops.pack_weight_codes(w)
 wq8 = ops.pack_weight_codes(w, ops.CODE_E4M3)

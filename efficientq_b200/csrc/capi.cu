@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+long long stream_cap(int per_sm) {
+  static const bool persist = [] { const char* v = getenv("EFFQ_STREAM_PERSIST"); return v && *v == '1'; }();
+  return persist ? (long long)sm_count() * per_sm : (1ll << 30);
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {

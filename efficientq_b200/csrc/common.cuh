@@ -13,6 +13,12 @@ namespace effq {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int  sm_count();
+// Grid cap of a streaming (HBM-bound, read-once / write-once) kernel WITHOUT per-CTA set-up.  One work chunk per CTA
+// and the hardware block scheduler beat a persistent grid of `per_sm` CTAs per SM with a grid stride on B200: glue ReLU
+// 0.87 -> 1.04, add 0.97 -> 1.06, max-pool 0.67 -> 0.96 of the copy peak (profiles/r02_hbm_bench.md), so the cap is only
+// the grid-dimension limit; EFFQ_STREAM_PERSIST=1 restores the persistent grids (A/B).  Kernels that prepare something
+// per CTA (fp64 scale constants, level tables) measured the other way round and keep their persistent grids.
+long long stream_cap(int per_sm);
 
 #define EFFQ_CHECK_ARG(cond, msg)                                   \
   do {                                                              \

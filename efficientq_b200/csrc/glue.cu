@@ -178,7 +178,7 @@ glue_upsample_kernel(const float* __restrict__ x, const float* __restrict__ skip
 
 static inline unsigned glue_grid(long long work_items) {
   long long blocks = (work_items + GL_THREADS - 1) / GL_THREADS;
-  const long long cap = (long long)sm_count() * 8;             // 8 resident CTAs per SM, grid stride beyond
+  const long long cap = stream_cap(8);                         // one chunk per CTA (common.cuh)
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -195,13 +195,8 @@ extern "C" int effq_glue_elementwise(const float* a, const float* b, int64_t num
                  "pointers must be 16B aligned");
   if (numel <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  // one 16 KB chunk per CTA (the hardware block scheduler keeps the SMs on neighbouring addresses; measured against a
-  // persistent grid of 8 CTAs per SM: see profiles/r02_hbm_bench.md), grid stride only beyond 2^20 CTAs
-  static const bool persist = [] { const char* v = getenv("EFFQ_GLUE_PERSIST"); return v && *v == '1'; }();
-  long long chunks = ((numel >> 2) + GL_THREADS * 4 - 1) / (GL_THREADS * 4);
-  if (chunks < 1) chunks = 1;
-  if (chunks > (1ll << 20)) chunks = 1ll << 20;
-  const unsigned grid = persist ? glue_grid((numel >> 2) / 4 + GL_THREADS) : (unsigned)chunks;
+  // one 16 KB chunk per CTA (stream_cap, common.cuh)
+  const unsigned grid = glue_grid((numel >> 2) / 4 + GL_THREADS);
   if (b && relu) glue_elementwise_kernel<true, true><<<grid, GL_THREADS, 0, s>>>(a, b, numel, y_out);
   else if (b)    glue_elementwise_kernel<true, false><<<grid, GL_THREADS, 0, s>>>(a, b, numel, y_out);
   else           glue_elementwise_kernel<false, true><<<grid, GL_THREADS, 0, s>>>(a, b, numel, y_out);

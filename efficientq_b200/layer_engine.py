@@ -480,6 +480,14 @@ class LayerCalibrator:
         keep_bufs = (best_g, best_b, best_wcodes, best_pc)
         steady = None
         sol_small = None if solve_tc else torch.empty((c2, kp), dtype=torch.float32, device=dev)
+        score_overlap = os.environ.get("EFFQ_SCORE_STREAM", "1") != "0"
+        score_pending = False
+        if score_overlap:
+            if self._score_stream is None:
+                self._score_stream = torch.cuda.Stream(device=dev)
+                self._score_events = (torch.cuda.Event(), torch.cuda.Event())
+            score_stream = self._score_stream
+            ev_proj, ev_score = self._score_events
         for it in range(it_first, it_end):
             if rho_built != rho:
                 ainv, ev = inverses[rho]
@@ -492,8 +500,30 @@ class LayerCalibrator:
                 ops.replay(pre)
                 if mm is not None:
                     mm()
-                ops.replay(post)
+                # Conv-free scoring off the critical path: the score of iterate i (quadform + best-iterate decision) is
+                # needed only by the NEXT projection (which keeps iterate i if it was the best, then overwrites G / b*),
+                # not by the next proximal step or scale search.  It runs on a second stream between two events:
+                #   main : solve_i -> search_i -> [wait score_{i-1}] -> project_i -> (event P_i) -> solve_{i+1} -> ...
+                #   score:                                        [wait P_i] -> quadform_i -> (event S_i)
+                # Same kernels, same arguments, same order of every dependent pair: results are bit-identical.
+                split = self._split_score(post) if score_overlap else None
+                if split is None:
+                    ops.replay(post)
+                    continue
+                head, proj, score = split
+                ops.replay(head)
+                if score_pending:
+                    main.wait_event(ev_score)
+                ops.replay(proj)
+                ev_proj.record(main)
+                score_stream.wait_event(ev_proj)
+                ops.replay(score)
+                ev_score.record(score_stream)
+                score_pending = True
                 continue
+            if score_pending:                      # a non-replayed iteration runs entirely on the main stream
+                main.wait_event(ev_score)
+                score_pending = False
             recording = replayable and not special
             with (_capi.record() if recording else nullcontext()) as rec:
                 n_pre = 0
@@ -589,6 +619,8 @@ class LayerCalibrator:
                         self._probe(name, f"it{it}_{tag}", t)
             rho = new_rho
 
+        if score_pending:
+            main.wait_event(ev_score)
         ops.admm_keep(self.st, g, bstar, best_g, best_b, wcodes, best_wcodes, pc, best_pc)   # the last iterate, if it was the best
         if loop_prof:
             t_cpu = _t.perf_counter() - t_cpu0
@@ -674,6 +706,29 @@ class LayerCalibrator:
 
     _side = None
     factor_streams = int(os.environ.get("EFFQ_FACTOR_STREAMS", "5"))   # concurrent factorisation chains per layer
+    _score_stream = None    # conv-free scoring of iterate i beside the proximal step of iterate i + 1
+    _score_events = None
+    _split_cache = None
+
+    def _split_score(self, post):
+        """Recorded tail of an iteration -> (calls up to the projection, the projection, the scoring launch re-targeted
+        at the score stream), or None when the iteration is not conv-free scored (or the timer brackets the scoring
+        kernel on the main stream).  Cached per recorded sequence."""
+        import ctypes as C
+        if self._split_cache is not None and self._split_cache[0] is post:
+            split = self._split_cache[1]
+        else:
+            split = None
+            names = [c[3] for c in post]
+            if names and names[-1] == "effq_quadform_delta" and names.count("effq_admm_project") == 1 and \
+                    names.index("effq_admm_project") == len(names) - 2:
+                fn, args, tag, name = post[-1]
+                side = C.c_void_p(self._score_stream.cuda_stream)
+                split = (post[:-2], post[-2:-1], [(fn, tuple(args[:-1]) + (side,), tag, name)])
+            self._split_cache = (post, split)
+        if split is not None and split[2][0][2] is not None and ops.timer.wants(split[2][0][2][0]):
+            return None
+        return split
 
     def _conv_ws(self, x, c2, ksize, stride, padding):
         import ctypes as C

@@ -720,13 +720,20 @@ class LayerCalibrator:
         else:
             split = None
             names = [c[3] for c in post]
-            if names and names[-1] == "effq_quadform_delta" and names.count("effq_admm_project") == 1 and \
-                    names.index("effq_admm_project") == len(names) - 2:
-                fn, args, tag, name = post[-1]
-                side = C.c_void_p(self._score_stream.cuda_stream)
-                split = (post[:-2], post[-2:-1], [(fn, tuple(args[:-1]) + (side,), tag, name)])
+            side = C.c_void_p(self._score_stream.cuda_stream)
+            n_score = 0
+            if names and names[-1] == "effq_quadform_delta":
+                n_score = 1
+            elif len(names) >= 2 and names[-2:] == ["effq_conv3d_tc", "effq_admm_decide"] and \
+                    os.environ.get("EFFQ_SCORE_STREAM_CONV", "1") != "0":
+                n_score = 2                  # conv-scored iterate: conv + decide (the decide kernel's NVLink exchange
+                                             # is the only peer traffic inside a loop, so it may run on either stream)
+            if n_score and names.count("effq_admm_project") == 1 and \
+                    names.index("effq_admm_project") == len(names) - n_score - 1:
+                score = [(fn, tuple(args[:-1]) + (side,), tag, name) for fn, args, tag, name in post[-n_score:]]
+                split = (post[:-n_score - 1], post[-n_score - 1:-n_score], score)
             self._split_cache = (post, split)
-        if split is not None and split[2][0][2] is not None and ops.timer.wants(split[2][0][2][0]):
+        if split is not None and any(c[2] is not None and ops.timer.wants(c[2][0]) for c in split[2]):
             return None
         return split
 

@@ -91,6 +91,45 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return r;
 }
 
+// Block-wide sums of NV doubles in ONE round (one pair of barriers, the shuffle chains of the NV values interleaved):
+// the same reduction tree per value as block_sum, hence bit-identical results; results valid in thread 0.
+// `scratch` >= 32 * NV doubles.  A fixed-point pass of the scale search needs two sums (sum b*v, sum b*b) and a fold
+// needs two or four; back-to-back block_sum calls cost ~600 cycles each (two barriers + two dependent shuffle trees).
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  __syncthreads();                 // scratch may be reused by back-to-back calls
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) scratch[32 * k + wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = lane < nw ? scratch[32 * k + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = 0.0;
+  }
+}
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
+  double v[2] = {a, b};
+  block_sum_n<2>(v, scratch);
+  a = v[0];
+  b = v[1];
+}
+
 // ---- the reference's discretize, op for op (layer_helper.py:25-37) -----------
 // fp32: every operation individually rounded (no FMA contraction), IEEE division,
 // clamp that propagates NaN like torch.clamp, rintf == round-half-to-even.

@@ -159,8 +159,7 @@ __device__ __forceinline__ void fold_partials(const double (*part)[4], unsigned 
     t0 += ((const volatile double*)part[b])[0];
     t1 += ((const volatile double*)part[b])[1];
   }
-  t0 = block_sum(t0, scratch);
-  t1 = block_sum(t1, scratch);
+  block_sum2(t0, t1, scratch);
   if (threadIdx.x == 0) { bc[0] = t0; bc[1] = t1; }
   __syncthreads();
 }
@@ -170,10 +169,10 @@ __device__ __forceinline__ void fold_partials4(const double (*part)[4], unsigned
   for (unsigned int b = threadIdx.x; b < nctas; b += SS_THREADS)
 #pragma unroll
     for (int k = 0; k < 4; ++k) t[k] += ((const volatile double*)part[b])[k];
+  block_sum_n<4>(t, scratch);
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double r = block_sum(t[k], scratch);
-    if (threadIdx.x == 0) bc[k] = r;
+    for (int k = 0; k < 4; ++k) bc[k] = t[k];
   }
   __syncthreads();
 }
@@ -209,7 +208,7 @@ __device__ __forceinline__ bool grid_barrier(SSWorkspace* ws, unsigned int& targ
 template <int REG_ITEMS>
 __global__ void __launch_bounds__(SS_THREADS)
 scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, SSWorkspace* ws) {
-  __shared__ double scratch[32];
+  __shared__ double scratch[128];
   __shared__ double bc[2];
   const QParamD q = make_qparam_d(lo, hi, nlvl);
   const unsigned int nctas = gridDim.x;
@@ -260,8 +259,7 @@ scale_search_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* 
     } else {
       pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
     }
-    s0 = block_sum(s0, scratch);
-    s1 = block_sum(s1, scratch);
+    block_sum2(s0, s1, scratch);
     if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = s1; }
     if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
     fold_partials(ws->partial[parity], nctas, scratch, bc);
@@ -333,10 +331,10 @@ __device__ __forceinline__ void publish4(const ClassAcc& c, const QParamD& q, do
   double v4[4];
   finish_bv(c.st, q, c.sv_st, c.n_st, v4[0], v4[1]);
   finish_bv(c.am, q, c.sv_am, c.n_am, v4[2], v4[3]);
+  block_sum_n<4>(v4, scratch);
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double rsum = block_sum(v4[k], scratch);
-    if (threadIdx.x == 0) slot[blockIdx.x][k] = rsum;
+    for (int k = 0; k < 4; ++k) slot[blockIdx.x][k] = v4[k];
   }
 }
 
@@ -345,7 +343,7 @@ constexpr unsigned int SS_RECLASS_MIN = 1u << 16;      // lists shorter than thi
 __global__ void __launch_bounds__(SS_THREADS, 2)
 scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, SSWorkspace* ws,
                            float* list_mem, unsigned int cap, float wmax0, float dthr, effq_peer_comm comm) {
-  __shared__ double scratch[32];
+  __shared__ double scratch[128];
   __shared__ double bc[4];
   __shared__ float sbuf[SS_STAGE_CAP];
   __shared__ unsigned int scnt, sbase;
@@ -538,8 +536,7 @@ scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_
       have_outer = false;
       have_inner = false;
       pass_sums<1>(vv, a, q, blockIdx.x, nctas, s0, s1);
-      s0 = block_sum(s0, scratch);
-      s1 = block_sum(s1, scratch);
+      block_sum2(s0, s1, scratch);
       if (threadIdx.x == 0) { ws->partial[parity][blockIdx.x][0] = s0; ws->partial[parity][blockIdx.x][1] = s1; }
       if (!grid_barrier(ws, target, nctas)) { if (blockIdx.x == 0 && threadIdx.x == 0) state->failed = 2; return; }
       fold_partials(ws->partial[parity], nctas, scratch, bc);
@@ -584,7 +581,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
 scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, int per_cta) {
   namespace cg = cooperative_groups;
   extern __shared__ float sv[];                              // this CTA's slice of v
-  __shared__ double scratch[32];
+  __shared__ double scratch[128];
   __shared__ double slot[2][2];                              // [parity][sum index], read by peers
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int rank = cluster.block_rank(), nranks = cluster.num_blocks();
@@ -598,7 +595,9 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
   }
   __syncthreads();
 
-  __shared__ double folded[2];
+  __shared__ double folded[2][2];                            // [parity]: the next fold writes the other half, so one
+                                                             // barrier per fold suffices (a warp can be at most one
+                                                             // fold ahead of the slowest reader: cluster.sync between)
   // warp 0: lane r fetches rank r's partials over DSMEM, then a serial shuffle sum in rank order
   // (the same order in every CTA -> bit-identical scales); result broadcast through smem.
   auto fold = [&](int parity, double& t0, double& t1) {
@@ -614,12 +613,11 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
         a0 += __shfl_sync(0xffffffffu, x0, (int)r);
         a1 += __shfl_sync(0xffffffffu, x1, (int)r);
       }
-      if (threadIdx.x == 0) { folded[0] = a0; folded[1] = a1; }
+      if (threadIdx.x == 0) { folded[parity][0] = a0; folded[parity][1] = a1; }
     }
     __syncthreads();
-    t0 = folded[0];
-    t1 = folded[1];
-    __syncthreads();
+    t0 = folded[parity][0];
+    t1 = folded[parity][1];
   };
 
   int parity = 0;
@@ -646,8 +644,7 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
       for (int i = threadIdx.x; i < mine; i += SC_THREADS) accum_idx((double)sv[i], pq, pa);
       finish_bv(pa, q, my_sv, my_cnt, s0, s1);
     }
-    s0 = block_sum(s0, scratch);
-    s1 = block_sum(s1, scratch);
+    block_sum2(s0, s1, scratch);
     if (threadIdx.x == 0) { slot[parity][0] = s0; slot[parity][1] = s1; }
     cluster.sync();        // release/acquire: peers' slots are visible; the other parity is free again
     fold(parity, last0, last1);
@@ -674,7 +671,7 @@ constexpr int SR_THREADS = 256;
 __global__ void __launch_bounds__(SR_THREADS)
 scale_search_rows_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* states) {
   extern __shared__ float srow[];
-  __shared__ double scratch[32];
+  __shared__ double scratch[128];
   __shared__ double bc[2];
   const QParamD q = make_qparam_d(lo, hi, nlvl);
   const long long r = blockIdx.x;
@@ -697,8 +694,7 @@ scale_search_rows_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_st
     for (int c = threadIdx.x; c < cols; c += SR_THREADS) accum_idx((double)srow[c], pq, pa);
     double t0, t1;
     finish_bv(pa, q, my_sv, my_cnt, t0, t1);
-    t0 = block_sum(t0, scratch);
-    t1 = block_sum(t1, scratch);
+    block_sum2(t0, t1, scratch);
     __syncthreads();                         // everyone has read bc of the previous pass
     if (threadIdx.x == 0) { bc[0] = t0; bc[1] = t1; }
     __syncthreads();
@@ -731,15 +727,14 @@ template <int MODE>
 __global__ void __launch_bounds__(SS_THREADS)
 scale_partial_kernel(VecView vv, int nlvl, float lo, float hi, const effq_scale_state* state,
                      double* sums, SPWorkspace* ws) {
-  __shared__ double scratch[32];
+  __shared__ double scratch[128];
   __shared__ bool last;
   const QParamD q = make_qparam_d(lo, hi, nlvl);
   double s0, s1;
   // a converged search keeps its scale: later passes are no-ops that re-emit the sums
   const double a = MODE == 1 ? state->a : 0.0;
   pass_sums<MODE>(vv, a, q, blockIdx.x, gridDim.x, s0, s1);
-  s0 = block_sum(s0, scratch);
-  s1 = block_sum(s1, scratch);
+  block_sum2(s0, s1, scratch);
   if (threadIdx.x == 0) {
     ws->partial[blockIdx.x][0] = s0;
     ws->partial[blockIdx.x][1] = MODE == 0 ? 0.0 : s1;

@@ -575,12 +575,15 @@ scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_
 // CTA folds the per-CTA partial sums straight out of its peers' shared memory (DSMEM) in rank
 // order, so all CTAs see bit-identical scales.  No global-memory round trip per pass.
 constexpr int SC_THREADS = 512;
-constexpr int SC_MAX_ELEMS = 56 * 1024;          // floats of shared memory per CTA (224 KB)
+constexpr int SC_MAX_ELEMS = 28 * 1024;          // doubles of shared memory per CTA (224 KB)
 
 __global__ void __launch_bounds__(SC_THREADS, 1)
 scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_state* state, int per_cta) {
   namespace cg = cooperative_groups;
-  extern __shared__ float sv[];                              // this CTA's slice of v
+  // this CTA's slice of v, widened ONCE: a pass is bound by the conversion unit (F2F.F64.F32 + FRND.F64 per element at a
+  // quarter of the fp64 rate, profiles/r02_scale_search_units.md), and re-converting the slice in each of ~50 passes was
+  // half of that
+  extern __shared__ double sv[];
   __shared__ double scratch[128];
   __shared__ double slot[2][2];                              // [parity][sum index], read by peers
   cg::cluster_group cluster = cg::this_cluster();
@@ -591,7 +594,7 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
   const int mine = (int)max(0ll, min((long long)per_cta, numel - begin));
   for (int i = threadIdx.x; i < mine; i += SC_THREADS) {
     const long long e = begin + i;
-    sv[i] = load_v(vv, e / vv.cols, e % vv.cols);
+    sv[i] = (double)load_v(vv, e / vv.cols, e % vv.cols);
   }
   __syncthreads();
 
@@ -623,8 +626,8 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
   int parity = 0;
   double s0 = 0.0, s1 = 0.0;
   double my_sv = 0.0, my_cnt = 0.0;                  // pass-invariant: this thread's sum of v and count
-  for (int i = threadIdx.x; i < mine; i += SC_THREADS) { my_sv += (double)sv[i]; my_cnt += 1.0; }
-  for (int i = threadIdx.x; i < mine; i += SC_THREADS) s0 += fabs((double)sv[i]);
+  for (int i = threadIdx.x; i < mine; i += SC_THREADS) { my_sv += sv[i]; my_cnt += 1.0; }
+  for (int i = threadIdx.x; i < mine; i += SC_THREADS) s0 += fabs(sv[i]);
   s0 = block_sum(s0, scratch);
   if (threadIdx.x == 0) { slot[parity][0] = s0; slot[parity][1] = 0.0; }
   cluster.sync();
@@ -641,7 +644,7 @@ scale_search_cluster_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale
     s1 = 0.0;
     {
       PassAcc pa{0.0, 0.0, 0.0};
-      for (int i = threadIdx.x; i < mine; i += SC_THREADS) accum_idx((double)sv[i], pq, pa);
+      for (int i = threadIdx.x; i < mine; i += SC_THREADS) accum_idx(sv[i], pq, pa);
       finish_bv(pa, q, my_sv, my_cnt, s0, s1);
     }
     block_sum2(s0, s1, scratch);
@@ -843,11 +846,11 @@ extern "C" int effq_scale_search(const float* v1, int64_t ld1, const float* v2, 
     }
     int per_cta = (int)((numel + nranks - 1) / nranks);
     per_cta = (per_cta + 3) & ~3;
-    const size_t smem = (size_t)per_cta * sizeof(float);
+    const size_t smem = (size_t)per_cta * sizeof(double);
     static bool configured = false;
     if (!configured) {
       EFFQ_CUDA(cudaFuncSetAttribute(scale_search_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SC_MAX_ELEMS * (int)sizeof(float)));
+                                     SC_MAX_ELEMS * (int)sizeof(double)));
       configured = true;
     }
     cudaLaunchConfig_t cfg = {};

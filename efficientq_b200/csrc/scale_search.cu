@@ -356,24 +356,37 @@ scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_
   if (threadIdx.x == 0) scnt = 0;
   __syncthreads();
 
-  // Sharded volumes: every pass ends with an in-kernel all-reduce of the two local sums over NVLink
-  // peer memory (CTA 0, one thread), then a second grid barrier publishes the global sums.  Which
-  // elements are stable / listed is a local matter; the scale -- hence every decision below -- is
-  // global and identical on all ranks.
+  // Sharded volumes: every pass ends with an in-kernel all-reduce of the two local sums over NVLink peer memory.
+  // Every CTA holds the same local sums after the fold; CTA 0 publishes them to all ranks, and EVERY CTA then waits
+  // for the ranks' contributions in the local slot buffer and adds them in rank order (peer_recv3) -- no second grid
+  // barrier to hand the global sums round.  The exchange number is tracked identically by all CTAs (base read at
+  // kernel start, one increment per exchange; CTA 0 stores the final count for the next launch), and the slot
+  // parities are safe because CTA 0 can only send exchange s + 1 after this rank's grid barrier of pass s + 1, which
+  // every CTA reaches after it has consumed exchange s.  Which elements are stable / listed is a local matter; the
+  // scale -- hence every decision below -- is global and identical on all ranks.
+  __shared__ double xbc[3];
+  const unsigned long long xbase = comm.world > 1 ? *(volatile unsigned long long*)peer_counter(comm, 0) : 0ull;
+  unsigned long long xcount = 0;
   auto exchange = [&](double& x0, double& x1) -> bool {
     if (comm.world <= 1) return true;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ++xcount;
+    if (threadIdx.x == 0) {
       double v[3] = {x0, x1, 0.0};
-      const bool ok = peer_allreduce3(comm, 0, v);
-      ws->gsum[0] = v[0];
-      ws->gsum[1] = v[1];
-      ws->gsum[2] = ok ? 0.0 : 1.0;
-      __threadfence();
+      if (blockIdx.x == 0) peer_send3(comm, 0, xbase + xcount, v);
+      const bool ok = peer_recv3(comm, 0, xbase + xcount, v);
+      xbc[0] = v[0];
+      xbc[1] = v[1];
+      xbc[2] = ok ? 0.0 : 1.0;
     }
-    if (!grid_barrier(ws, target, nctas)) return false;
-    x0 = ((volatile double*)ws->gsum)[0];
-    x1 = ((volatile double*)ws->gsum)[1];
-    return ((volatile double*)ws->gsum)[2] == 0.0;
+    __syncthreads();
+    x0 = xbc[0];
+    x1 = xbc[1];
+    const bool ok = xbc[2] == 0.0;
+    __syncthreads();
+    return ok;
+  };
+  auto exchange_done = [&]() {              // CTA 0: leave the exchange counter where the next launch expects it
+    if (comm.world > 1 && blockIdx.x == 0 && threadIdx.x == 0) *peer_counter(comm, 0) = xbase + xcount;
   };
 
   double s0, s1;
@@ -553,6 +566,7 @@ scale_search_stream_kernel(VecView vv, int nlvl, float lo, float hi, effq_scale_
     d = fabs(a - a_prev);
     ++passes;
   }
+  exchange_done();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     state->a = a;
     state->a_prev = a_prev;

@@ -1,5 +1,5 @@
 """Layer losses of a bench workload under different factorisation precisions (quality check of the fp32 explicit
-inverse on ill-conditioned deep layers).  python tools/config_probe.py [workload]"""
+inverse on ill-conditioned deep layers).  python tools/bringup/config_probe.py [workload]"""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch, bench

@@ -1,6 +1,6 @@
 """Bring-up: LiTS-config calibration with per-layer input statistics (find the first layer that goes non-finite)."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from efficientq_b200 import layer_engine, ops, ptqer, synth
 wl = dict(bench.WORKLOADS["lits_w2a2_4x160"])

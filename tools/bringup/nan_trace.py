@@ -1,7 +1,7 @@
 """Bring-up: run one layer through LayerCalibrator with every ops.* call checked for non-finite outputs.
-Usage: python tools/nan_trace.py N C1 C2 D H W K LW LA [n_iter]"""
+Usage: python tools/bringup/nan_trace.py N C1 C2 D H W K LW LA [n_iter]"""
 import os, sys, torch, torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from efficientq_b200 import layer_engine, ops
 torch.backends.cuda.matmul.allow_tf32 = False
 n, c1, c2, d, h, w, k, lw, la = [int(v) for v in sys.argv[1:10]]

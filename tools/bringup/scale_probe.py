@@ -1,6 +1,6 @@
 """Probe: activation scale search on a level-1 sized tensor: plain passes vs interval-stable passes."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from efficientq_b200 import ops
 dev = torch.device("cuda:0")
 torch.manual_seed(0)

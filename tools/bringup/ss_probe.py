@@ -1,5 +1,5 @@
 """Weight scale search timing: us per search and per pass for the tensor sizes of the BraTS net.
-   python tools/ss_probe.py [reps]      (EFFQ_SS_BUCKET=0 selects the plain cluster / grid kernels)"""
+   python tools/bringup/ss_probe.py [reps]      (EFFQ_SS_BUCKET=0 selects the plain cluster / grid kernels)"""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import torch

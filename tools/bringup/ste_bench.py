@@ -1,7 +1,7 @@
 """HBM throughput of the STE-backward kernel (effq_fakequant_ste_bwd) at a level-1 activation tensor of
 BASELINE config 2 (32 x 32ch x 64^3 = 268 M elements), timed alone with CUDA events, inputs larger than L2."""
 import json, os, sys, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from efficientq_b200 import ops
 dev = torch.device("cuda:0")

@@ -1,5 +1,5 @@
 """Bring-up diagnostics for the tcgen05 conv kernel: structured inputs, simplest case first.
-Usage (GPU box): python tools/tc_diag.py > gpurun_out/tc_diag.log 2>&1"""
+Usage (GPU box): python tools/bringup/tc_diag.py > gpurun_out/tc_diag.log 2>&1"""
 import sys
 import os
 import time
@@ -7,7 +7,7 @@ import time
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from efficientq_b200 import ops  # noqa: E402
 
 DEV = "cuda:0"

@@ -857,6 +857,8 @@ def relu(x: torch.Tensor, inplace: bool = False) -> torch.Tensor:
     """nn.ReLU of a unit (factoryQ.py:66-81)."""
     x = _f32c(x, "x")
     y = x if inplace else torch.empty_like(x)
+    if x.numel() == 0:
+        return y
     timer.run("glue_relu", {"bytes": 8 * x.numel()}, lambda: check(
         capi.load().effq_glue_elementwise(ptr(x), None, x.numel(), 1, ptr(y), stream()), "effq_glue_elementwise"))
     return y
@@ -868,6 +870,8 @@ def add(a: torch.Tensor, b: torch.Tensor, relu_after: bool = False) -> torch.Ten
     if a.shape != b.shape:
         raise EffqError(f"add: shapes differ ({tuple(a.shape)} vs {tuple(b.shape)})")
     y = torch.empty_like(a)
+    if a.numel() == 0:
+        return y
     timer.run("glue_add", {"bytes": 12 * a.numel()}, lambda: check(
         capi.load().effq_glue_elementwise(ptr(a), ptr(b), a.numel(), 1 if relu_after else 0, ptr(y), stream()),
         "effq_glue_elementwise"))
@@ -880,6 +884,8 @@ def maxpool3d(x: torch.Tensor, kernel, relu_after: bool = False) -> torch.Tensor
     n, c, d, h, w = x.shape
     kd, kh, kw = capi._triple(kernel)
     y = torch.empty((n, c, d // kd, h // kh, w // kw), dtype=torch.float32, device=x.device)
+    if y.numel() == 0:
+        return y
     timer.run("glue_maxpool", {"bytes": 4 * (x.numel() + y.numel())}, lambda: check(
         capi.load().effq_glue_maxpool3d(ptr(x), n * c, d, h, w, kd, kh, kw, 1 if relu_after else 0, ptr(y), stream()),
         "effq_glue_maxpool3d"))
@@ -896,6 +902,8 @@ def upsample_trilinear(x: torch.Tensor, factor, skip: Optional[torch.Tensor] = N
         skip = _f32c(skip, "skip")
         if skip.shape != y.shape:
             raise EffqError(f"upsample_trilinear: skip has shape {tuple(skip.shape)}, output {tuple(y.shape)}")
+    if y.numel() == 0:
+        return y
     timer.run("glue_upsample", {"bytes": 4 * (x.numel() + y.numel() * (2 if skip is not None else 1))}, lambda: check(
         capi.load().effq_glue_upsample_trilinear(ptr(x), ptr(skip), n * c, d, h, w, fd, fh, fw, ptr(y), stream()),
         "effq_glue_upsample_trilinear"))

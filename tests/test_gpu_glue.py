@@ -75,6 +75,27 @@ def test_upsample_trilinear_matches_library(ops, shape, f):
     assert torch.equal(got_s, got + skip.to(DEV))                          # the fused add is one exact rounding
 
 
+def test_glue_empty_and_ragged_inputs(ops):
+    """Empty batches return empty tensors without a launch; sizes that are not multiples of the vector width take the
+    scalar tails (numel % 4, odd widths) and still match the library bit for bit."""
+    e = torch.empty(0, 4, 2, 2, 2, device=DEV)
+    assert ops.relu(e).shape == e.shape and ops.add(e, e).shape == e.shape
+    assert ops.maxpool3d(e, 2).shape == (0, 4, 1, 1, 1)
+    assert ops.upsample_trilinear(e, 2).shape == (0, 4, 4, 4, 4)
+    assert ops.maxpool3d(torch.zeros(1, 1, 1, 1, 1, device=DEV), 2).numel() == 0        # floor mode: nothing left
+    for shape in [(1, 1, 1, 1, 1), (1, 3, 1, 1, 7), (2, 1, 3, 3, 3), (1, 5, 2, 3, 5)]:
+        a, b = _rand(shape, 11), _rand(shape, 12)
+        assert torch.equal(ops.relu(a.to(DEV)).cpu(), F.relu(a))
+        assert torch.equal(ops.add(a.to(DEV), b.to(DEV)).cpu(), a + b)
+        up = ops.upsample_trilinear(a.to(DEV), (2, 2, 1)).cpu()
+        want = F.interpolate(a, scale_factor=(2.0, 2.0, 1.0), mode="trilinear")
+        assert up.shape == want.shape and float((up - want).abs().max()) <= 2.5e-7 * float(want.abs().max())
+    with pytest.raises(Exception):
+        ops.add(torch.zeros(1, 1, 2, 2, 2, device=DEV), torch.zeros(1, 1, 2, 2, 4, device=DEV))
+    with pytest.raises(Exception):
+        ops.relu(torch.zeros(4))                                                          # host tensor: no CPU path
+
+
 def test_network_forward_on_own_glue_kernels(ops):
     """FP forward of the BraTS miniature: glue on the repo's kernels vs EFFQ_GLUE=lib (stock modules)."""
     from efficientq_b200 import model_blk

@@ -140,10 +140,15 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
-# same kernel at the same shape (profiles/r01_layer_ncu.md); None = not captured.
+# same kernel at the same shape (profiles/r01_layer_ncu.md, profiles/r02_layer_ncu.md); None = not captured.
 NCU_TRAFFIC_BYTES = {
     "conv3d_tc_c32x32k3_e4m3": 1.391e9,  # 32 x 32ch x 64^3: algorithmic 1.342 GB (e4m3 codes 0.268 + fp32 target 1.074)
     "conv3d_tc_c32x32k3": 1.615e9,       # same layer, bf16 codes: algorithmic 1.611 GB
+    # weighted + unweighted Gram of a level-1 layer (32 x 32ch x 64^3; half of the step's 8 launches, the level-2 ones
+    # move less): 22.48 GB read + 0.05 GB written against ~1.7 GB algorithmic (codes 0.54 + fp32 target 1.07 + masks):
+    # every (row block, column block) tile pair re-reads its voxel range; DRAM at 8 % of its peak, the kernel is bound
+    # by L2 -> SM operand traffic (profiles/r02_layer_ncu.md, r02c_gram_ncu_raw.csv)
+    "gram_tc_dual": 22.53e9,
 }
 
 

@@ -37,6 +37,7 @@ __all__ = [
     "fold_bn_pair", "class_counts_brats", "class_counts_lits",
     "att_weight_map", "mask_pyramid", "pred_brats", "pred_lits",
     "select_att", "rho_scale_of",
+    "glue_relu", "glue_add", "glue_maxpool3d", "glue_upsample_trilinear",
 ]
 
 
@@ -467,3 +468,71 @@ def adam_update(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tens
     denom = v.sqrt() / (bc2 ** 0.5) + eps
     p = p - (lr / bc1) * (m / denom)
     return p, m, v
+
+
+# ----------------------------------------------------------------------------
+# f.4: glue ops between the quantizer layers.  The reference runs them as stock modules -- nn.ReLU
+# (src/models/factoryQ.py:66-81), nn.MaxPool3d(k, k) (src/models/factory_blk.py:18-42), nn.Upsample(scale_factor,
+# mode="trilinear") followed by "+ skip" (:45-93) and the residual add (:147-166); restated here in explicit numpy
+# fp32 arithmetic (index formulas and op order of the library kernels) and pinned against the library in
+# tests/test_glue_cpu.py.
+# ----------------------------------------------------------------------------
+def glue_relu(x: torch.Tensor) -> torch.Tensor:
+    a = x.detach().numpy()
+    return torch.from_numpy(np.where(a < 0, np.float32(0), a).astype(np.float32))      # NaN passes through
+
+
+def glue_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return torch.from_numpy(a.detach().numpy().astype(np.float32) + b.detach().numpy().astype(np.float32))
+
+
+def glue_maxpool3d(x: torch.Tensor, kernel) -> torch.Tensor:
+    """MaxPool3d(kernel, stride=kernel), no padding, floor mode; a NaN in the window wins."""
+    kd, kh, kw = _triple(kernel)
+    a = x.detach().numpy()
+    n, c, d, h, w = a.shape
+    od, oh, ow = d // kd, h // kh, w // kw
+    win = a[:, :, :od * kd, :oh * kh, :ow * kw].reshape(n, c, od, kd, oh, kh, ow, kw)
+    win = win.transpose(0, 1, 2, 4, 6, 3, 5, 7).reshape(n, c, od, oh, ow, kd * kh * kw)
+    out = np.full((n, c, od, oh, ow), -np.inf, dtype=np.float32)
+    for t in range(kd * kh * kw):
+        v = win[..., t]
+        take = (v > out) | np.isnan(v)
+        out = np.where(take, v, out)
+    return torch.from_numpy(out.astype(np.float32))
+
+
+def _linear_taps(n_in: int, factor: int):
+    """align_corners=False source positions of the n_in * factor outputs: src = (1/factor) (o + 0.5) - 0.5 clamped at 0,
+    i0 = floor(src), i1 = i0 + (i0 < n_in - 1), lambda1 = src - i0, lambda0 = 1 - lambda1 (all fp32)."""
+    o = np.arange(n_in * factor, dtype=np.float32)
+    src = np.float32(1.0 / factor) * (o + np.float32(0.5)) - np.float32(0.5)
+    src = np.maximum(src, np.float32(0))
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    i1 = i0 + (i0 < n_in - 1)
+    l1 = (src - i0.astype(np.float32)).astype(np.float32)
+    l0 = (np.float32(1) - l1).astype(np.float32)
+    return i0, i1, l0, l1
+
+
+def glue_upsample_trilinear(x: torch.Tensor, factor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Upsample(scale_factor=factor, mode="trilinear") [+ skip]: the lambdas nested w -> h -> d as in the library."""
+    fd, fh, fw = _triple(factor)
+    a = x.detach().numpy().astype(np.float32)
+    d0, d1, ld0, ld1 = _linear_taps(a.shape[2], fd)
+    h0, h1, lh0, lh1 = _linear_taps(a.shape[3], fh)
+    w0, w1, lw0, lw1 = _linear_taps(a.shape[4], fw)
+
+    def along_w(plane):                 # plane: [..., W] -> [..., W * fw]
+        return lw0 * plane[..., w0] + lw1 * plane[..., w1]
+
+    def along_h(vol, di):               # vol: [N, C, D, H, W] at depth taps di -> [N, C, OD, OH, OW]
+        rows0 = along_w(vol[:, :, di][:, :, :, h0])
+        rows1 = along_w(vol[:, :, di][:, :, :, h1])
+        return lh0[:, None] * rows0 + lh1[:, None] * rows1
+
+    out = ld0[:, None, None] * along_h(a, d0) + ld1[:, None, None] * along_h(a, d1)
+    out = out.astype(np.float32)
+    if skip is not None:
+        out = out + skip.detach().numpy().astype(np.float32)
+    return torch.from_numpy(out)

@@ -32,3 +32,28 @@ def test_down_unit_relu_is_fused_into_the_pool():
     assert torch.equal(down(x), ref(x))
     pre = model_blk._down(2, nn.Conv3d, model_blk.ReLU(True), nn.BatchNorm3d, "pre")(4, 8)
     assert not pre.pool.fuse_relu and isinstance(pre.block.relu, nn.ReLU)
+
+
+def test_oracle_glue_restatement_matches_the_library():
+    """oracle/effq_oracle.py glue_* (explicit numpy fp32 arithmetic) against the reference's own stock modules."""
+    from oracle import effq_oracle as O
+    x = _rand((2, 3, 4, 6, 5), 21)
+    x[0, 0, 0, 0, 0] = float("nan")
+    y = _rand((2, 3, 4, 6, 5), 22)
+    import numpy as np
+    assert np.array_equal(O.glue_relu(x).numpy(), nn.ReLU()(x).numpy(), equal_nan=True)
+    assert np.array_equal(O.glue_add(x, y).numpy(), (x + y).numpy(), equal_nan=True)
+    for k in (2, (2, 2, 1), (1, 2, 2)):
+        assert np.array_equal(O.glue_maxpool3d(x, k).numpy(), nn.MaxPool3d(k, k)(x).numpy(), equal_nan=True)
+    x = _rand((2, 3, 4, 6, 5), 23)
+    for f in (2, (2, 2, 1), 4, 3):
+        sf = float(f) if isinstance(f, int) else tuple(float(v) for v in f)
+        want = nn.Upsample(scale_factor=sf, mode="trilinear")(x)
+        got = O.glue_upsample_trilinear(x, f)
+        assert got.shape == want.shape
+        # power-of-two factors (the only ones the configured nets use: 2 and (2, 2, 1)) have exact lambdas; with
+        # factor 3 the library's fused / unfused evaluation of (1/3)(o + 0.5) - 0.5 moves a lambda by one ulp
+        bar = 2.5e-7 if f != 3 else 1e-6
+        assert float((got - want).abs().max()) <= bar * float(want.abs().max())
+        skip = _rand(tuple(want.shape), 24)
+        assert torch.equal(O.glue_upsample_trilinear(x, f, skip), got + skip)
